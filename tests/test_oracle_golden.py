@@ -1,0 +1,138 @@
+"""CPU: the oracle restatement vs golden vectors produced by the reference's own layer.py/model.py."""
+import pytest
+import torch
+
+from oracle import glam_oracle as O
+from helpers import case, ns
+
+TAGS = ["f32", "f64"]
+
+
+def _tol(tag):
+    return dict(rtol=2e-4, atol=2e-5) if tag == "f32" else dict(rtol=1e-10, atol=1e-11)
+
+
+def _check_grads(named_params, grads, golden, tag):
+    for (n, _), g in zip(named_params, grads):
+        torch.testing.assert_close(g, golden[n], msg=lambda m, n=n: f"{n}: {m}", **_tol(tag))
+
+
+@pytest.mark.parametrize("tag", TAGS)
+@pytest.mark.parametrize("name,C,De", [("triplet_C36", 36, 3), ("triplet_C60", 60, 4), ("triplet_C15_edge", 15, 4)])
+def test_triplet_message(golden_layers, name, C, De, tag):
+    c = case(golden_layers, f"{name}_{tag}")
+    m = O.TripletMessage(C, De).to(c["x"].dtype)
+    m.load_state_dict(c["state"])
+    x = c["x"].clone().requires_grad_(True)
+    out = m(x, c["edge_index"], c["edge_attr"])
+    torch.testing.assert_close(out, c["out"], **_tol(tag))
+    g = torch.autograd.grad((out * c["cot"]).sum(), [x] + list(m.parameters()))
+    torch.testing.assert_close(g[0], c["grad_x"], **_tol(tag))
+    _check_grads(list(m.named_parameters()), g[1:], c["grad_params"], tag)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+@pytest.mark.parametrize("name,C,De", [("light_C36", 36, 3), ("light_C45_edge", 45, 4)])
+def test_triplet_light(golden_layers, name, C, De, tag):
+    c = case(golden_layers, f"{name}_{tag}")
+    m = O.TripletMessageLight(C, De).to(c["x"].dtype)
+    m.load_state_dict(c["state"])
+    x = c["x"].clone().requires_grad_(True)
+    out = m(x, c["edge_index"], c["edge_attr"])
+    torch.testing.assert_close(out, c["out"], **_tol(tag))
+    g = torch.autograd.grad((out * c["cot"]).sum(), [x] + list(m.parameters()))
+    torch.testing.assert_close(g[0], c["grad_x"], **_tol(tag))
+    _check_grads(list(m.named_parameters()), g[1:], c["grad_params"], tag)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+@pytest.mark.parametrize("name", ["block_triplet_C36", "block_triplet_pn_C60", "block_light_C30"])
+def test_message_block(golden_layers, name, tag):
+    c = case(golden_layers, f"{name}_{tag}")
+    cfg = golden_layers[f"{name}_f32"]["cfg"]
+    blk = O.MessageBlock(cfg["C"], cfg["C"], cfg["De"], norm=cfg["norm"], dropout="_None()", conv=cfg["conv"],
+                         act=cfg["act"], res=cfg["res"]).to(c["x"].dtype)
+    blk.load_state_dict(c["state"])
+    x0 = c["x"].clone().requires_grad_(True)
+    x, h = x0, None
+    for _ in range(cfg["steps"]):
+        x, h = blk(x, c["edge_index"], c["edge_attr"], h=h, batch=c["batch"])
+    torch.testing.assert_close(x, c["out"], **_tol(tag))
+    torch.testing.assert_close(h, c["h"], **_tol(tag))
+    g = torch.autograd.grad((x * c["cot"]).sum() + (h * c["coth"]).sum(), [x0] + list(blk.parameters()))
+    torch.testing.assert_close(g[0], c["grad_x"], **_tol(tag))
+    _check_grads(list(blk.named_parameters()), g[1:], c["grad_params"], tag)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+@pytest.mark.parametrize("name,kind,C", [("set2set_C36", "s2s", 36), ("set2set_C30", "s2s", 30),
+                                         ("lapool_C36", "la", 36), ("lapool_C45", "la", 45)])
+def test_readouts(golden_layers, name, kind, C, tag):
+    c = case(golden_layers, f"{name}_{tag}")
+    m = (O.Set2Set(C, 3) if kind == "s2s" else O.GlobalLAPool(C)).to(c["x"].dtype)
+    m.load_state_dict(c["state"])
+    x = c["x"].clone().requires_grad_(True)
+    out = m(x, c["batch"])
+    torch.testing.assert_close(out, c["out"], **_tol(tag))
+    g = torch.autograd.grad((out * c["cot"]).sum(), [x] + list(m.parameters()))
+    torch.testing.assert_close(g[0], c["grad_x"], **_tol(tag))
+    _check_grads(list(m.named_parameters()), g[1:], c["grad_params"], tag)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+@pytest.mark.parametrize("name", ["dotpool_ddi_C36", "dotpool_dti_C60"])
+def test_dot_pool(golden_layers, name, tag):
+    c = case(golden_layers, f"{name}_{tag}")
+    xa = c["xa"].clone().requires_grad_(True)
+    xb = c["xb"].clone().requires_grad_(True)
+    out = O.dot_and_global_pool2(xa, xb, c["batch_a"], c["batch_b"])
+    torch.testing.assert_close(out, c["out"], **_tol(tag))
+    ga, gb = torch.autograd.grad((out * c["cot"]).sum(), [xa, xb])
+    torch.testing.assert_close(ga, c["grad_xa"], **_tol(tag))
+    torch.testing.assert_close(gb, c["grad_xb"], **_tol(tag))
+
+
+@pytest.mark.parametrize("name", ["gp_set2set", "gp_lapool_light", "gp_set2set_pairnorm"])
+def test_model_gp(golden_models, name):
+    c = golden_models[name]
+    cfg = c["cfg"]
+    m = O.ArchitectureGP(cfg["Din"], cfg["De"], hid_dim_alpha=4, e_dim=cfg["e_dim"], out_dim=1, mol_block=cfg["block"],
+                         message_steps=3, mol_readout=cfg["readout"], graph_norm=cfg["graph_norm"],
+                         pre_act="ReLU", graph_act="CELU", flat_act="LeakyReLU")
+    assert list(m.state_dict().keys()) == list(c["state"].keys())
+    m.load_state_dict(c["state"])
+    m.eval()
+    out = m(ns(c["x"], c["edge_index"], c["edge_attr"], c["batch"]))
+    torch.testing.assert_close(out, c["out"], rtol=2e-4, atol=2e-5)
+    loss = torch.nn.functional.mse_loss(out, c["y"])
+    g = torch.autograd.grad(loss, list(m.parameters()))
+    _check_grads(list(m.named_parameters()), g, c["grad_params"], "f32")
+
+
+def test_model_ddi(golden_models):
+    c = golden_models["ddi_set2set"]
+    cfg = c["cfg"]
+    m = O.ArchitecturePair(cfg["Din"], cfg["Din"], cfg["De"], cfg["De"], prefixes=("mol1", "mol2"), hid_dim_alpha=4,
+                           e_dim=cfg["e_dim"], out_dim=1, graph_act="ReLU", pre_act="ReLU", flat_act="CELU",
+                           end_act="ReLU")
+    assert list(m.state_dict().keys()) == list(c["state"].keys())
+    m.load_state_dict(c["state"])
+    m.eval()
+    out = m(ns(c["a_x"], c["a_edge_index"], c["a_edge_attr"], c["a_batch"]),
+            ns(c["b_x"], c["b_edge_index"], c["b_edge_attr"], c["b_batch"]))
+    torch.testing.assert_close(out, c["out"], rtol=2e-4, atol=2e-5)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(out, c["y"])
+    g = torch.autograd.grad(loss, list(m.parameters()))
+    _check_grads(list(m.named_parameters()), g, c["grad_params"], "f32")
+
+
+def test_seeded_init_matches_reference(golden_layers):
+    """Same parameter registration order + init calls => same seeded init as the reference (make_golden seeds
+    torch before constructing the module; bias is then overwritten, so skip it)."""
+    c = golden_layers["triplet_C36_f32"]
+    from glam_b200.synth import make_molecule_batch
+    torch.manual_seed(1234)
+    make_molecule_batch(4, node_dim=36, edge_dim=3, seed=1234, features="normal")
+    m = O.TripletMessage(36, 3)
+    for k in ("weight_node", "weight_edge", "weight_triplet_att", "weight_scale"):
+        torch.testing.assert_close(m.state_dict()[k], c["state"][k], rtol=0, atol=0)
