@@ -1,0 +1,68 @@
+// Shared helpers for the glam_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/glam_b200.h"
+
+namespace glam {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; persistent grids are sized in multiples of this
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define GLAM_REQUIRE(cond, ...)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            glam::set_error(__VA_ARGS__);       \
+            return -1;                          \
+        }                                       \
+    } while (0)
+
+#define GLAM_CHECK_LAUNCH()                                                     \
+    do {                                                                        \
+        cudaError_t e__ = cudaGetLastError();                                   \
+        if (e__ != cudaSuccess) {                                               \
+            glam::set_error("%s:%d CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return (int)e__;                                                    \
+        }                                                                       \
+        glam::count_launch();                                                   \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float celu1(float x) { return x > 0.f ? x : expm1f(x); }
+
+// activation codes shared with the host side (glam_b200/functional.py)
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_CELU = 3 };
+__device__ __forceinline__ float act_fwd(float x, int act, float p) {
+    switch (act) {
+        case ACT_RELU: return x > 0.f ? x : 0.f;
+        case ACT_LEAKY: return x > 0.f ? x : p * x;
+        case ACT_CELU: return celu1(x);
+        default: return x;
+    }
+}
+// derivative expressed with the activation OUTPUT y (all four are sign-preserving)
+__device__ __forceinline__ float act_grad_from_out(float y, int act, float p) {
+    switch (act) {
+        case ACT_RELU: return y > 0.f ? 1.f : 0.f;
+        case ACT_LEAKY: return y > 0.f ? 1.f : p;
+        case ACT_CELU: return y > 0.f ? 1.f : y + 1.f;
+        default: return 1.f;
+    }
+}
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace glam

@@ -1,0 +1,258 @@
+"""Autograd bindings of the hot-path kernels.
+
+Every Function below is a fixed sequence of C-ABI calls (glam_b200.ops); nothing here computes with
+torch ops on node- or edge-sized tensors.  Backward formulas follow SURVEY.md Appendix C.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+from .ops import (ACT_NONE, EPI_ACCUM, EPI_CELU, EPI_MUL_CELU_GRAD, EPI_NONE)
+
+
+def _c(t):
+    return None if t is None else (t if t.is_contiguous() else t.contiguous())
+
+
+# --------------------------------------------------------------------------------------------------
+# shared forward/backward pieces
+# --------------------------------------------------------------------------------------------------
+def _conv_fwd(x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels, slope, epilogue):
+    xpe = ops.gemm(x, w_ext)                                                   # [N, ldxp]: xp | s_i | s_j | 0
+    agg, alpha = ops.triplet_edge_fwd(xpe, ea, w_edge, att_edge, g, heads, channels, slope)
+    out = agg if w_scale is None else ops.gemm(agg, w_scale, bias=bias, epilogue=epilogue)
+    return xpe, agg, alpha, out
+
+
+def _conv_bwd(g_pre, x, w_ext, w_edge, att_edge, w_scale, xpe, agg, alpha, ea, g, heads, channels, slope):
+    """g_pre: gradient w.r.t. the layer output before any activation ([N,C], or [N,HC] for the Light layer)."""
+    if w_scale is not None:
+        g_agg = ops.gemm(g_pre, w_scale, transpose_w=True)                     # [N,HC]
+        g_w_scale = ops.gemm_tn(agg, g_pre)
+        g_bias = ops.colsum(g_pre)
+    else:
+        g_agg, g_w_scale, g_bias = g_pre, None, None
+    g_xpe, g_logit, g_w_edge = ops.triplet_edge_bwd(xpe, ea, w_edge, att_edge, alpha, g_agg, g, heads, channels, slope)
+    g_att_edge = ops.gemm_tn(ea, g_logit)                                      # [De,H]
+    g_x = ops.gemm(g_xpe, w_ext, transpose_w=True)                             # [N,C]
+    g_w_ext = ops.gemm_tn(x, g_xpe)                                            # [C,ldxp]
+    return g_x, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias
+
+
+def _gru_fwd(m, h, identity, w_ih, w_hh, b_ih, b_hh, act, act_param):
+    gi = ops.gemm(m, w_ih, transpose_w=True, bias=b_ih)                        # [N,3C]
+    gh = ops.gemm(h, w_hh, transpose_w=True, bias=b_hh)
+    h_new, x_out = ops.gru_gates_fwd(gi, gh, h, identity, act, act_param)      # gi now holds r|z|n
+    return gi, gh, h_new, x_out
+
+
+def _gru_bwd(g_x_out, g_h_new, rzn, gh, h, m, x_out, w_ih, w_hh, act, act_param, want_identity, celu_aux):
+    g_gi, g_gh, g_h_prev, g_id = ops.gru_gates_bwd(rzn, gh, h, x_out, g_x_out, g_h_new, act, act_param, want_identity)
+    if celu_aux is not None:                                                   # m = celu(pre): return d/d pre
+        g_m = ops.gemm(g_gi, w_ih, epilogue=EPI_MUL_CELU_GRAD, aux=celu_aux)
+    else:
+        g_m = ops.gemm(g_gi, w_ih)
+    ops.gemm(g_gh, w_hh, epilogue=EPI_ACCUM, out=g_h_prev)
+    g_w_ih = ops.gemm_tn(g_gi, m)
+    g_w_hh = ops.gemm_tn(g_gh, h)
+    return g_m, g_h_prev, g_id, g_w_ih, g_w_hh, ops.colsum(g_gi), ops.colsum(g_gh)
+
+
+# --------------------------------------------------------------------------------------------------
+# TripletMessage / TripletMessageLight propagate (src_1gp/layer.py:36-61, :83-101)
+# --------------------------------------------------------------------------------------------------
+class TripletConvFn(Function):
+    """out = (segment-softmax attention aggregate) @ w_scale + bias; for the Light layer (w_edge and w_scale
+    None) returns the aggregate itself and the caller adds the bias."""
+
+    @staticmethod
+    def forward(ctx, x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels, slope):
+        x, w_ext, w_edge, att_edge, w_scale, bias = map(_c, (x, w_ext, w_edge, att_edge, w_scale, bias))
+        ops._need_cuda(x, w_ext)
+        xpe, agg, alpha, out = _conv_fwd(x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels, slope, EPI_NONE)
+        ctx.save_for_backward(x, w_ext, w_edge, att_edge, w_scale, xpe, agg, alpha, ea)
+        ctx.g, ctx.cfg = g, (heads, channels, slope)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, w_ext, w_edge, att_edge, w_scale, xpe, agg, alpha, ea = ctx.saved_tensors
+        heads, channels, slope = ctx.cfg
+        g_x, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias = _conv_bwd(
+            _c(g_out), x, w_ext, w_edge, att_edge, w_scale, xpe, agg, alpha, ea, ctx.g, heads, channels, slope)
+        return g_x, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# GRU node update (src_1gp/layer.py:260-266) on a given message m
+# --------------------------------------------------------------------------------------------------
+class GRUUpdateFn(Function):
+    @staticmethod
+    def forward(ctx, m, h, identity, w_ih, w_hh, b_ih, b_hh, act, act_param):
+        m, h, identity, w_ih, w_hh, b_ih, b_hh = map(_c, (m, h, identity, w_ih, w_hh, b_ih, b_hh))
+        ops._need_cuda(m, h)
+        rzn, gh, h_new, x_out = _gru_fwd(m, h, identity, w_ih, w_hh, b_ih, b_hh, act, act_param)
+        ctx.save_for_backward(m, h, w_ih, w_hh, rzn, gh, x_out)
+        ctx.cfg = (act, act_param, identity is not None)
+        ctx.set_materialize_grads(False)
+        return x_out, h_new
+
+    @staticmethod
+    def backward(ctx, g_x_out, g_h_new):
+        m, h, w_ih, w_hh, rzn, gh, x_out = ctx.saved_tensors
+        act, act_param, has_id = ctx.cfg
+        g_m, g_h, g_id, g_w_ih, g_w_hh, g_b_ih, g_b_hh = _gru_bwd(
+            _c(g_x_out), _c(g_h_new), rzn, gh, h, m, x_out, w_ih, w_hh, act, act_param, has_id, None)
+        return g_m, g_h, g_id, g_w_ih, g_w_hh, g_b_ih, g_b_hh, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# fused MessageBlock core: conv -> CELU -> GRU -> (+identity) -> act   (src_1gp/layer.py:259-266)
+# --------------------------------------------------------------------------------------------------
+class MessageBlockFn(Function):
+    @staticmethod
+    def forward(ctx, x, identity, h, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, ea, g,
+                heads, channels, slope, act, act_param):
+        (x, identity, h, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh) = map(
+            _c, (x, identity, h, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh))
+        ops._need_cuda(x, h)
+        xpe, agg, alpha, m = _conv_fwd(x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels, slope, EPI_CELU)
+        rzn, gh, h_new, x_out = _gru_fwd(m, h, identity, w_ih, w_hh, b_ih, b_hh, act, act_param)
+        ctx.save_for_backward(x, h, w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, xpe, agg, alpha, m, rzn, gh, x_out, ea)
+        ctx.g, ctx.cfg = g, (heads, channels, slope, act, act_param, identity is not None)
+        ctx.set_materialize_grads(False)
+        return x_out, h_new
+
+    @staticmethod
+    def backward(ctx, g_x_out, g_h_new):
+        (x, h, w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, xpe, agg, alpha, m, rzn, gh, x_out, ea) = ctx.saved_tensors
+        heads, channels, slope, act, act_param, has_id = ctx.cfg
+        g_pre, g_h, g_id, g_w_ih, g_w_hh, g_b_ih, g_b_hh = _gru_bwd(
+            _c(g_x_out), _c(g_h_new), rzn, gh, h, m, x_out, w_ih, w_hh, act, act_param, has_id, m)
+        g_x, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias = _conv_bwd(
+            g_pre, x, w_ext, w_edge, att_edge, w_scale, xpe, agg, alpha, ea, ctx.g, heads, channels, slope)
+        return (g_x, g_id, g_h, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias, g_w_ih, g_w_hh, g_b_ih, g_b_hh,
+                None, None, None, None, None, None, None)
+
+
+# --------------------------------------------------------------------------------------------------
+# small dense layer on graph-level rows (LSTM gates of Set2Set, nn of GlobalAttention)
+# --------------------------------------------------------------------------------------------------
+class LinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x, weight, bias = map(_c, (x, weight, bias))
+        ops._need_cuda(x, weight)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return ops.gemm(x, weight, transpose_w=True, bias=bias)
+
+    @staticmethod
+    def backward(ctx, g_y):
+        x, weight = ctx.saved_tensors
+        g_y = _c(g_y)
+        return ops.gemm(g_y, weight), ops.gemm_tn(g_y, x), (ops.colsum(g_y) if ctx.has_bias else None)
+
+
+class LSTMGatesFn(Function):
+    """(gates_pre [B,4C], c_prev) -> (h_new, c_new); torch.nn.LSTM gate order i,f,g,o."""
+
+    @staticmethod
+    def forward(ctx, gates, c_prev):
+        gates = gates.contiguous().clone()       # activated in place by the kernel
+        c_prev = _c(c_prev)
+        h_new, c_new = ops.lstm_gates_fwd(gates, c_prev)
+        ctx.save_for_backward(gates, c_prev, c_new)
+        ctx.set_materialize_grads(False)
+        return h_new, c_new
+
+    @staticmethod
+    def backward(ctx, g_h, g_c):
+        gates, c_prev, c_new = ctx.saved_tensors
+        g_gates, g_c_prev = ops.lstm_gates_bwd(gates, c_prev, c_new, _c(g_h), _c(g_c))
+        return g_gates, g_c_prev
+
+
+# --------------------------------------------------------------------------------------------------
+# per-graph attention pooling (GlobalAttention gate + pool; one Set2Set step)
+# --------------------------------------------------------------------------------------------------
+class SegAttnPoolFn(Function):
+    """e[n] = <x[n], q[g]> (+ bias); a = softmax per graph (PyG form); returns (r[g] = sum a x, asum[g] = sum a).
+    `q` is [B,C] (per graph) or [1,C] (shared, GlobalAttention's gate_nn weight)."""
+
+    @staticmethod
+    def forward(ctx, x, q, q_bias, gptr, num_graphs):
+        x, q, q_bias = map(_c, (x, q, q_bias))
+        ops._need_cuda(x, q)
+        shared = q.shape[0] == 1 and num_graphs != 1
+        stride = 0 if (shared or q.shape[0] == 1) else q.shape[1]
+        a, r, asum = ops.seg_attn_pool_fwd(x, q, stride, q_bias, gptr, num_graphs)
+        ctx.save_for_backward(x, q, a, gptr)
+        ctx.cfg = (num_graphs, stride, q.shape[0], q_bias is not None)
+        ctx.set_materialize_grads(False)
+        return r, asum
+
+    @staticmethod
+    def backward(ctx, g_r, g_asum):
+        x, q, a, gptr = ctx.saved_tensors
+        num_graphs, stride, q_rows, has_bias = ctx.cfg
+        if g_r is None:
+            g_r = torch.zeros((num_graphs, x.shape[1]), dtype=x.dtype, device=x.device)
+        g_x = torch.empty_like(x)
+        g_q, g_e = ops.seg_attn_pool_bwd(x, q, stride, a, _c(g_r), _c(g_asum), gptr, num_graphs, g_x, False)
+        if q_rows == 1 and num_graphs != 1:
+            g_q = ops.colsum(g_q).view(1, -1)
+        g_b = ops.colsum(g_e.view(-1, 1)) if has_bias else None
+        return g_x, g_q, g_b, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# cross-graph dot pool (src_2gi_ddi/layer.py:270-283)
+# --------------------------------------------------------------------------------------------------
+class PairDotPoolFn(Function):
+    @staticmethod
+    def forward(ctx, xa, xb, ptr_a, ptr_b, num_pairs):
+        xa, xb = _c(xa), _c(xb)
+        ops._need_cuda(xa, xb)
+        out, argmax, sa, sb = ops.pair_dot_pool_fwd(xa, xb, ptr_a, ptr_b, num_pairs)
+        ctx.save_for_backward(xa, xb, ptr_a, ptr_b, argmax, sa, sb)
+        ctx.num_pairs = num_pairs
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        xa, xb, ptr_a, ptr_b, argmax, sa, sb = ctx.saved_tensors
+        g_xa, g_xb = ops.pair_dot_pool_bwd(xa, xb, ptr_a, ptr_b, _c(g_out), argmax, sa, sb, ctx.num_pairs)
+        return g_xa, g_xb, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter-space preparation (derived weights of the triplet layers)
+# --------------------------------------------------------------------------------------------------
+class TripletPrepFn(Function):
+    """(weight_node, weight_edge|None, weight_triplet_att) -> (w_ext [C,ldxp], att_edge [De,H])."""
+
+    @staticmethod
+    def forward(ctx, weight_node, weight_edge, att, channels, heads, edge_dim, ldxp):
+        light = weight_edge is None
+        weight_node, weight_edge, att = map(_c, (weight_node, weight_edge, att))
+        ops._need_cuda(weight_node, att)
+        w_ext, att_edge = ops.triplet_prep_fwd(weight_node, weight_edge, att, channels, heads, edge_dim, light, ldxp)
+        ctx.save_for_backward(weight_node, weight_edge, att)
+        ctx.cfg = (channels, heads, edge_dim, light, ldxp)
+        ctx.set_materialize_grads(False)
+        return w_ext, att_edge
+
+    @staticmethod
+    def backward(ctx, g_w_ext, g_att_edge):
+        weight_node, weight_edge, att = ctx.saved_tensors
+        channels, heads, edge_dim, light, ldxp = ctx.cfg
+        if g_w_ext is None:
+            g_w_ext = torch.zeros((channels, ldxp), dtype=torch.float32, device=att.device)
+        if g_att_edge is None:
+            g_att_edge = torch.zeros((edge_dim, heads), dtype=torch.float32, device=att.device)
+        g_wn, g_we, g_att = ops.triplet_prep_bwd(weight_node, weight_edge, att, _c(g_w_ext), _c(g_att_edge), None,
+                                                 channels, heads, edge_dim, light, ldxp)
+        return g_wn, g_we, g_att, None, None, None, None

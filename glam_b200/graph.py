@@ -1,0 +1,92 @@
+"""Per-batch graph index: the dst-/src-sorted CSR and per-graph node ranges.
+
+The reference re-derives gather indices and atomics-scatters on every layer call (PyG
+`MessagePassing.propagate`, reached from src_1gp/layer.py:40,86).  Here the index is built once per
+batch on the device and shared by all `message_steps` applications of the block and by backward
+(SURVEY.md §8b "Ownership").  Lookups are keyed on the identity *and version* of the caller's
+`edge_index` tensor, so the drop-in `forward(x, edge_index, edge_attr)` signature stays unchanged;
+the cache holds a reference to the key tensor, so its storage cannot be recycled for another batch
+while the entry is alive, and an in-place refill (`copy_`) bumps the version and rebuilds.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+
+from . import ops
+
+_CACHE_SIZE = 16
+
+
+class GraphIndex:
+    """Device-resident index of one batch (all int32; see include/glam_b200.h (1))."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+        self.num_nodes = int(num_nodes)
+        self.num_edges = int(edge_index.shape[1])
+        csr = ops.build_csr(edge_index, self.num_nodes)
+        self.dst_rowptr = csr["dst_rowptr"]
+        self.dst_src = csr["dst_src"]
+        self.dst_perm = csr["dst_perm"]
+        self.src_rowptr = csr["src_rowptr"]
+        self.src_pos = csr["src_pos"]
+        self.src_dst = csr["src_dst"]
+        self._edge_attr_key = None
+        self._edge_attr_sorted = None
+
+    def sorted_edge_attr(self, edge_attr: torch.Tensor) -> torch.Tensor:
+        """edge_attr rows permuted into destination order (done once per batch, reused by every step)."""
+        key = (edge_attr.data_ptr(), edge_attr._version, tuple(edge_attr.shape))
+        if self._edge_attr_key != key:
+            ea = edge_attr if edge_attr.dim() == 2 else edge_attr.view(edge_attr.shape[0], -1)
+            self._edge_attr_sorted = ops.gather_rows(ea, self.dst_perm)
+            self._edge_attr_key = key
+            self._edge_attr_ref = edge_attr
+        return self._edge_attr_sorted
+
+
+_graph_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+_ptr_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+
+def _capturing() -> bool:
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
+def graph_index(edge_index: torch.Tensor, num_nodes: int) -> GraphIndex:
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), int(num_nodes), edge_index.device)
+    hit = _graph_cache.get(key)
+    if hit is not None:
+        _graph_cache.move_to_end(key)
+        return hit[1]
+    gi = GraphIndex(edge_index, num_nodes)
+    _graph_cache[key] = (edge_index, gi)
+    while len(_graph_cache) > _CACHE_SIZE:
+        _graph_cache.popitem(last=False)
+    return gi
+
+
+def graph_ptr(batch: torch.Tensor, num_graphs: Optional[int] = None):
+    """(graph_ptr int32 [B+1], B).  `num_graphs=None` reads batch[-1] back to the host once per batch tensor
+    (the reference does `batch.max().item()` on every readout call)."""
+    key = (batch.data_ptr(), batch._version, tuple(batch.shape), num_graphs, batch.device)
+    hit = _ptr_cache.get(key)
+    if hit is not None:
+        _ptr_cache.move_to_end(key)
+        return hit[1], hit[2]
+    if num_graphs is None:
+        if _capturing():
+            raise RuntimeError("num_graphs must be passed explicitly while a CUDA graph is being captured")
+        num_graphs = int(batch[-1].item()) + 1 if batch.numel() > 0 else 0
+    ptr = ops.graph_ptr(batch, num_graphs)
+    _ptr_cache[key] = (batch, ptr, int(num_graphs))
+    while len(_ptr_cache) > _CACHE_SIZE:
+        _ptr_cache.popitem(last=False)
+    return ptr, int(num_graphs)
+
+
+def clear_caches() -> None:
+    _graph_cache.clear()
+    _ptr_cache.clear()

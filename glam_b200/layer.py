@@ -1,0 +1,422 @@
+"""Drop-in mirror of the reference's `layer.py` namespace (src_1gp/layer.py, identical copies in
+src_2gi_ddi/ and src_2gi_dti_scr/) for the message-passing hot path.
+
+Same class names, constructor signatures, forward signatures, parameter names / shapes /
+registration order / init, so `state_dict`s interchange with the reference and the reference's
+`model.py` can build its blocks from the same name strings (`mol_block='_TripletMessage'`,
+`mol_readout='Set2Set'`, `graph_act='RReLU'`, `graph_do='Dropout(0.2)'` ...).  What is different is
+underneath: every node-/edge-sized computation of TripletMessage, TripletMessageLight, the GRU update,
+GlobalLAPool / Set2Set and dot_and_global_pool2 runs in hand-written sm_100a kernels behind the C ABI
+(include/glam_b200.h).  There is no CPU path: CPU tensors raise.
+
+Out of the hot path and therefore plain torch here: the norm wrappers, dropout,
+activations, `LinearBlock`, `GlobalPool5`.  `_NNConv/_GCNConv/_GATConv` are third-party PyG layers and are
+not provided.
+"""
+from __future__ import annotations
+
+import re
+from typing import Optional
+
+import torch
+from torch import nn
+from torch.nn import Parameter
+from torch.nn.init import kaiming_uniform_, zeros_
+
+from . import functional as Fn
+from . import graph as G
+from . import ops
+
+
+def _ldxp(heads: int, channels: int) -> int:
+    """Row pitch of the extended projection xp | s_i | s_j, padded to 16 bytes."""
+    return (heads * channels + 2 * heads + 3) // 4 * 4
+
+
+# --------------------------------------------------------------------------------------------------
+# message layers
+# --------------------------------------------------------------------------------------------------
+class TripletMessage(nn.Module):
+    """Multi-head attention over (target node, edge, source node) triplets — src_1gp/layer.py:15-64.
+
+    forward(x [N,C], edge_index int64 [2,E] (row 0 source, row 1 target), edge_attr [E,De]) -> [N,C]
+    """
+
+    def __init__(self, node_channels, edge_channels, heads=3, negative_slope=0.2, **kwargs):
+        super().__init__()
+        self.node_channels = node_channels
+        self.edge_channels = edge_channels
+        self.heads = heads
+        self.negative_slope = negative_slope
+        self.weight_node = Parameter(torch.empty(node_channels, heads * node_channels))
+        self.weight_edge = Parameter(torch.empty(edge_channels, heads * node_channels))
+        self.weight_triplet_att = Parameter(torch.empty(1, heads, 3 * node_channels))
+        self.weight_scale = Parameter(torch.empty(heads * node_channels, node_channels))
+        self.bias = Parameter(torch.empty(node_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for w in (self.weight_node, self.weight_edge, self.weight_triplet_att, self.weight_scale):
+            kaiming_uniform_(w)
+        zeros_(self.bias)
+
+    def derived(self):
+        """(w_ext, att_edge) for the current parameters: one tiny kernel, differentiable."""
+        C, H = self.node_channels, self.heads
+        return Fn.TripletPrepFn.apply(self.weight_node, self.weight_edge, self.weight_triplet_att.view(H, 3 * C), C, H,
+                                      self.edge_channels, _ldxp(H, C))
+
+    def forward(self, x, edge_index, edge_attr, size=None):
+        g = G.graph_index(edge_index, x.shape[0])
+        ea = g.sorted_edge_attr(edge_attr)
+        w_ext, att_edge = self.derived()
+        return Fn.TripletConvFn.apply(x, w_ext, self.weight_edge, att_edge, self.weight_scale, self.bias, ea, g, self.heads,
+                                      self.node_channels, self.negative_slope)
+
+    def extra_repr(self):
+        return f"{self.node_channels}, {self.node_channels}, heads={self.heads}"
+
+
+class TripletMessageLight(nn.Module):
+    """Single-head variant without edge/output projections — src_1gp/layer.py:67-104."""
+
+    def __init__(self, node_channels, edge_channels, negative_slope=0.2, **kwargs):
+        super().__init__()
+        self.node_channels = node_channels
+        self.edge_channels = edge_channels
+        self.negative_slope = negative_slope
+        self.weight_node = Parameter(torch.empty(node_channels, node_channels))
+        self.weight_triplet_att = Parameter(torch.empty(1, 2 * node_channels + edge_channels))
+        self.bias = Parameter(torch.empty(node_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        kaiming_uniform_(self.weight_node)
+        kaiming_uniform_(self.weight_triplet_att)
+        zeros_(self.bias)
+
+    def derived(self):
+        C = self.node_channels
+        return Fn.TripletPrepFn.apply(self.weight_node, None, self.weight_triplet_att.view(-1), C, 1, self.edge_channels,
+                                      _ldxp(1, C))
+
+    def forward(self, x, edge_index, edge_attr, size=None):
+        g = G.graph_index(edge_index, x.shape[0])
+        ea = g.sorted_edge_attr(edge_attr)
+        w_ext, att_edge = self.derived()
+        agg = Fn.TripletConvFn.apply(x, w_ext, None, att_edge, None, None, ea, g, 1, self.node_channels, self.negative_slope)
+        return agg + self.bias
+
+    def extra_repr(self):
+        return f"{self.node_channels}, {self.node_channels}"
+
+
+class _None(nn.Module):
+    """Placeholder for "no norm / dropout / activation" (src_1gp/layer.py:107-112)."""
+
+    def __init__(self, **params):
+        super().__init__()
+
+    def forward(self, x, batch=None):
+        return x
+
+
+class _TripletMessage(nn.Module):
+    def __init__(self, in_dim, out_dim, edge_in_dim):
+        super().__init__()
+        self.conv = TripletMessage(in_dim, edge_in_dim)      # out_dim ignored, as in the reference (:128)
+
+    def forward(self, x, edge_index, edge_attr):
+        return self.conv(x, edge_index, edge_attr)
+
+
+class _TripletMessageLight(nn.Module):
+    def __init__(self, in_dim, out_dim, edge_in_dim):
+        super().__init__()
+        self.conv = TripletMessageLight(in_dim, edge_in_dim)
+
+    def forward(self, x, edge_index, edge_attr):
+        return self.conv(x, edge_index, edge_attr)
+
+
+def _third_party(name):
+    class _Missing(nn.Module):
+        def __init__(self, *a, **k):
+            raise NotImplementedError(
+                f"{name} wraps a torch_geometric layer that is outside the triplet hot path (SURVEY.md §2.1); "
+                "use '_TripletMessage' or '_TripletMessageLight'")
+    _Missing.__name__ = name
+    return _Missing
+
+
+_NNConv, _GCNConv, _GATConv = _third_party("_NNConv"), _third_party("_GCNConv"), _third_party("_GATConv")
+
+
+# --------------------------------------------------------------------------------------------------
+# norm wrappers (torch; PyG-1.7.2 semantics) — not on the hot path
+# --------------------------------------------------------------------------------------------------
+def _seg_mean(x, batch, B):
+    out = x.new_zeros((B,) + tuple(x.shape[1:])).index_add_(0, batch, x)
+    cnt = x.new_zeros(B).index_add_(0, batch, x.new_ones(x.shape[0])).clamp_(min=1)
+    return out / cnt.view(-1, *([1] * (x.dim() - 1)))
+
+
+class _BatchNorm(nn.Module):
+    def __init__(self, in_channels):
+        super().__init__()
+        self.norm = nn.Module()
+        self.norm.module = nn.BatchNorm1d(in_channels)       # PyG BatchNorm keeps it under `.module`
+
+    def forward(self, x, batch=None):
+        return self.norm.module(x)
+
+
+class _LayerNorm(nn.Module):
+    """PyG LayerNorm: statistics over all nodes AND channels of each graph."""
+
+    def __init__(self, in_channels, eps=1e-5):
+        super().__init__()
+        self.norm = nn.Module()
+        self.norm.weight = Parameter(torch.ones(in_channels))
+        self.norm.bias = Parameter(torch.zeros(in_channels))
+        self.eps = eps
+
+    def forward(self, x, batch=None):
+        if batch is None:
+            x = x - x.mean()
+            out = x / (x.std(unbiased=False) + self.eps)
+        else:
+            B = int(batch[-1]) + 1
+            mean = _seg_mean(x, batch, B).mean(dim=-1, keepdim=True)
+            x = x - mean[batch]
+            var = _seg_mean(x * x, batch, B).mean(dim=-1, keepdim=True)
+            out = x / (var + self.eps).sqrt()[batch]
+        return out * self.norm.weight + self.norm.bias
+
+
+class _PairNorm(nn.Module):
+    def __init__(self, in_channels, eps=1e-5):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, x, batch=None, num_graphs=None):
+        if batch is None:
+            x = x - x.mean(dim=0, keepdim=True)
+            return x / (self.eps + x.pow(2).sum(-1).mean()).sqrt()
+        B = int(batch[-1]) + 1 if num_graphs is None else num_graphs
+        x = x - _seg_mean(x, batch, B)[batch]
+        return x / torch.sqrt(self.eps + _seg_mean(x.pow(2).sum(-1, keepdim=True), batch, B)[batch])
+
+
+class _GraphSizeNorm(nn.Module):
+    def __init__(self, in_channels):
+        super().__init__()
+
+    def forward(self, x, batch=None):
+        return x / (x.shape[0] ** 0.5)                       # called without batch in the reference (:194)
+
+
+# --------------------------------------------------------------------------------------------------
+# readouts
+# --------------------------------------------------------------------------------------------------
+class GlobalAttention(nn.Module):
+    """PyG GlobalAttention(gate_nn=Linear(C,1), nn=Linear(C,2C)) @1.7.2.
+
+    Uses linearity of `nn`: sum_n a_n (W x_n + b) = W (sum_n a_n x_n) + b sum_n a_n, so the [N,2C] projection is
+    never formed; gate, softmax and pooling are one kernel."""
+
+    def __init__(self, gate_nn, nn=None):
+        super().__init__()
+        self.gate_nn = gate_nn
+        self.nn = nn
+
+    def forward(self, x, batch, size=None, num_graphs=None):
+        if not (isinstance(self.gate_nn, nn.Linear) and self.gate_nn.out_features == 1
+                and (self.nn is None or isinstance(self.nn, nn.Linear))):
+            raise NotImplementedError("GlobalAttention kernel path needs gate_nn=Linear(C,1) and nn=Linear|None")
+        gptr, B = G.graph_ptr(batch, size if size is not None else num_graphs)
+        pooled, asum = Fn.SegAttnPoolFn.apply(x, self.gate_nn.weight, self.gate_nn.bias, gptr, B)
+        if self.nn is None:
+            return pooled
+        return Fn.LinearFn.apply(pooled, self.nn.weight, None) + asum.unsqueeze(1) * self.nn.bias
+
+
+class GlobalLAPool(nn.Module):
+    """Global linear-attention pool, [N,C] -> [B,2C] — src_1gp/layer.py:206-220."""
+
+    def __init__(self, in_channels, **params):
+        super().__init__()
+        self.pool = GlobalAttention(gate_nn=nn.Linear(in_channels, 1), nn=nn.Linear(in_channels, 2 * in_channels))
+
+    def forward(self, x, batch, num_graphs=None):
+        return self.pool(x, batch, num_graphs=num_graphs)
+
+
+class Set2Set(nn.Module):
+    """PyG Set2Set(in_channels, processing_steps, num_layers=1) @1.7.2 (imported by src_1gp/model.py:2,
+    constructed at :41).  The LSTM parameters live in a torch.nn.LSTM so names/init match (`lstm.weight_ih_l0` ...);
+    its cell math runs through the library's GEMM + gate kernels, the attention + pooling through one kernel."""
+
+    def __init__(self, in_channels, processing_steps, num_layers=1):
+        super().__init__()
+        if num_layers != 1:
+            raise NotImplementedError("Set2Set: only num_layers=1 (the reference never passes another value)")
+        self.in_channels = in_channels
+        self.out_channels = 2 * in_channels
+        self.processing_steps = processing_steps
+        self.num_layers = num_layers
+        self.lstm = nn.LSTM(self.out_channels, in_channels, num_layers)
+
+    def forward(self, x, batch, num_graphs=None):
+        gptr, B = G.graph_ptr(batch, num_graphs)
+        C, l = self.in_channels, self.lstm
+        h = x.new_zeros((B, C))
+        c = x.new_zeros((B, C))
+        q_star = x.new_zeros((B, 2 * C))
+        for _ in range(self.processing_steps):
+            gates = Fn.LinearFn.apply(q_star, l.weight_ih_l0, l.bias_ih_l0) + Fn.LinearFn.apply(h, l.weight_hh_l0, l.bias_hh_l0)
+            h, c = Fn.LSTMGatesFn.apply(gates, c)
+            r, _ = Fn.SegAttnPoolFn.apply(x, h, None, gptr, B)
+            q_star = torch.cat([h, r], dim=-1)
+        return q_star
+
+
+class GlobalPool5(nn.Module):
+    """mean | sum | sort-pool(k=3) readout (src_1gp/layer.py:197-203); torch ops, not on the hot path."""
+
+    def __init__(self, **params):
+        super().__init__()
+
+    def forward(self, x, batch, num_graphs=None):
+        B = int(batch[-1]) + 1 if num_graphs is None else num_graphs
+        C = x.shape[1]
+        total = x.new_zeros((B, C)).index_add_(0, batch, x)
+        cnt = torch.bincount(batch, minlength=B)
+        mean = total / cnt.clamp(min=1).view(-1, 1).to(x.dtype)
+        # global_sort_pool: per graph, nodes sorted by last channel (descending), first 3 kept, zero padded
+        key = x[:, -1]
+        order = torch.argsort(key, descending=True, stable=True)
+        order = order[torch.argsort(batch[order], stable=True)]
+        start = torch.cumsum(cnt, 0) - cnt
+        rank = torch.arange(x.shape[0], device=x.device) - start[batch[order]]
+        keep = rank < 3
+        top = x.new_zeros((B, 3, C))
+        top[batch[order][keep], rank[keep]] = x[order][keep]
+        return torch.cat([mean, total, top.view(B, 3 * C)], dim=-1)
+
+
+# --------------------------------------------------------------------------------------------------
+# blocks
+# --------------------------------------------------------------------------------------------------
+_NORMS = {"_None": _None, "_BatchNorm": _BatchNorm, "_LayerNorm": _LayerNorm, "_PairNorm": _PairNorm,
+          "_GraphSizeNorm": _GraphSizeNorm}
+_CONVS = {"_TripletMessage": _TripletMessage, "_TripletMessageLight": _TripletMessageLight, "_NNConv": _NNConv,
+          "_GCNConv": _GCNConv, "_GATConv": _GATConv}
+
+
+def _build_dropout(spec) -> nn.Module:
+    """The reference passes dropouts as constructor strings: '_None()', 'Dropout(0.2)' (run.py:31-34)."""
+    if isinstance(spec, nn.Module):
+        return spec
+    m = re.fullmatch(r"\s*(_None|Dropout)\s*\(\s*([0-9.eE+-]*)\s*\)\s*", spec)
+    if m is None:
+        raise ValueError(f"unknown dropout spec {spec!r}")
+    return _None() if m.group(1) == "_None" else nn.Dropout(float(m.group(2) or 0.5))
+
+
+def _build_act(name) -> nn.Module:
+    """Activations are passed by class name without parentheses: '_None', 'ReLU', 'RReLU', 'CELU' ... (run.py:35-37)."""
+    if isinstance(name, nn.Module):
+        return name
+    if name == "_None":
+        return _None()
+    cls = getattr(nn, name.replace("nn.", "").rstrip("()"), None)
+    if cls is None or not issubclass(cls, nn.Module):
+        raise ValueError(f"unknown activation {name!r}")
+    return cls()
+
+
+def _fusable_act(act: nn.Module, training: bool):
+    """(code, param) if the activation can run inside the GRU-update kernel, else None."""
+    if isinstance(act, _None):
+        return ops.ACT_NONE, 0.0
+    if type(act) is nn.ReLU:
+        return ops.ACT_RELU, 0.0
+    if type(act) is nn.LeakyReLU:
+        return ops.ACT_LEAKY, float(act.negative_slope)
+    if type(act) is nn.CELU and act.alpha == 1.0:
+        return ops.ACT_CELU, 1.0
+    if type(act) is nn.RReLU and not training:                # eval-mode RReLU is leaky_relu((lower+upper)/2)
+        return ops.ACT_LEAKY, float((act.lower + act.upper) / 2)
+    return None
+
+
+class LinearBlock(nn.Module):
+    """norm -> dropout -> Linear -> act (src_1gp/layer.py:223-237)."""
+
+    def __init__(self, in_dim=32, out_dim=64, norm="_None", dropout="_None()", act="ReLU"):
+        super().__init__()
+        self.norm = _NORMS[norm](in_channels=in_dim)
+        self.dropout = _build_dropout(dropout)
+        self.linear = nn.Linear(in_dim, out_dim)
+        self.act = _build_act(act)
+
+    def forward(self, x, batch=None):
+        return self.act(self.linear(self.dropout(self.norm(x, batch))))
+
+
+class MessageBlock(nn.Module):
+    """One message-passing step: norm -> dropout -> conv -> CELU -> GRU -> (+identity) -> act
+    (src_1gp/layer.py:240-267).  forward(x, edge_index, edge_attr, h=None, batch=None) -> (x, h)."""
+
+    def __init__(self, in_dim=32, out_dim=64, in_edge_dim=13, norm="_None", dropout="Dropout(0.2)", conv="_TripletMessage",
+                 act="ReLU", res=True):
+        super().__init__()
+        self.norm = _NORMS[norm](in_channels=in_dim)
+        self.dropout = _build_dropout(dropout)
+        self.conv = _CONVS[conv](in_dim, out_dim, in_edge_dim)
+        self.gru = nn.GRU(in_dim, out_dim)
+        if conv in ("_GCNConv", "_GATConv"):
+            self.gru = None
+        self.act = _build_act(act)
+        self.res = res
+
+    def forward(self, x, edge_index, edge_attr, h=None, batch=None):
+        identity = x
+        if h is None:
+            h = x.unsqueeze(0)
+        x = self.dropout(self.norm(x, batch))
+        if self.gru is None:
+            x = self.conv(x, edge_index, edge_attr)
+            x = x + identity if self.res else x
+            return self.act(x), h
+        gru = self.gru
+        fused = _fusable_act(self.act, self.training)
+        act_code, act_param = fused if fused is not None else (ops.ACT_NONE, 0.0)
+        ident = identity if self.res else None
+        inner = getattr(self.conv, "conv", None)
+        if isinstance(inner, TripletMessage):
+            g = G.graph_index(edge_index, x.shape[0])
+            ea = g.sorted_edge_attr(edge_attr)
+            w_ext, att_edge = inner.derived()
+            x, h_new = Fn.MessageBlockFn.apply(
+                x, ident, h[0], w_ext, inner.weight_edge, att_edge, inner.weight_scale, inner.bias,
+                gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, ea, g,
+                inner.heads, inner.node_channels, inner.negative_slope, act_code, act_param)
+        else:
+            m = torch.celu(self.conv(x, edge_index, edge_attr))
+            x, h_new = Fn.GRUUpdateFn.apply(m, h[0], ident, gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0,
+                                            gru.bias_hh_l0, act_code, act_param)
+        if fused is None:
+            x = self.act(x)
+        return x, h_new.unsqueeze(0)
+
+
+# --------------------------------------------------------------------------------------------------
+# cross-graph interaction pool
+# --------------------------------------------------------------------------------------------------
+def dot_and_global_pool2(mol_out, pro_out, mol_batch, pro_batch, num_graphs: Optional[int] = None):
+    """Per pair [max, mean] of X_mol X_pro^T — src_2gi_ddi/layer.py:270-283 — as one kernel launch, no host loop."""
+    ptr_a, B = G.graph_ptr(mol_batch, num_graphs)
+    ptr_b, _ = G.graph_ptr(pro_batch, B)
+    return Fn.PairDotPoolFn.apply(mol_out, pro_out, ptr_a, ptr_b, B)

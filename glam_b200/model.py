@@ -1,0 +1,145 @@
+"""Model wiring for the three GLAM variants, built from glam_b200.layer.
+
+The reference's `model.py` files stay the caller of the hot path: they only assemble
+LinearBlock -> message_steps x (shared) MessageBlock -> readout -> LinearBlocks.  They cannot be
+imported in this image (torch_geometric is absent), so the same wiring — same attribute names, hence
+the same state_dict keys — is restated here for the benchmarks and the end-to-end parity tests:
+
+  ArchitectureGP   src_1gp/model.py:23-62           forward(data_mol)
+  ArchitectureDDI  src_2gi_ddi/model.py:9-61        forward(mol1, mol2)
+  ArchitectureDTI  src_2gi_dti_scr/model.py:14-68   forward(data_mol, data_pro)
+
+`data_*` are PyG-Batch-like objects with fields x, edge_index, edge_attr, batch (and optionally
+num_graphs, which saves the reference's `batch.max().item()` host sync).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .layer import (GlobalLAPool, GlobalPool5, LinearBlock, MessageBlock, Set2Set, dot_and_global_pool2)
+
+_READOUTS = {"Set2Set": Set2Set, "GlobalLAPool": GlobalLAPool, "GlobalPool5": GlobalPool5}
+
+
+def _readout(name: str, hid: int) -> nn.Module:
+    return _READOUTS[name](in_channels=hid, processing_steps=3)
+
+
+def _readout_width(name: str) -> int:
+    return 5 if name == "GlobalPool5" else 2
+
+
+def _num_graphs(data):
+    return getattr(data, "num_graphs", None)
+
+
+class _Tower(object):
+    """Helper that runs one tower's pieces by attribute prefix (keeps the reference's flat attribute names)."""
+
+    def __init__(self, owner: nn.Module, prefix: str):
+        self.o, self.p = owner, prefix
+
+    def __getattr__(self, name):
+        return getattr(self.o, f"{self.p}_{name}")
+
+
+class ArchitectureGP(nn.Module):
+    def __init__(self, mol_in_dim=15, mol_edge_in_dim=4, hid_dim_alpha=4, e_dim=1024, out_dim=1,
+                 mol_block="_TripletMessage", message_steps=3, mol_readout="Set2Set",
+                 pre_norm="_None", graph_norm="_None", flat_norm="_None", end_norm="_None",
+                 pre_do="_None()", graph_do="Dropout(0.2)", flat_do="_None()", end_do="Dropout(0.2)",
+                 pre_act="RReLU", graph_act="RReLU", flat_act="RReLU", graph_res=True):
+        super().__init__()
+        hid = mol_in_dim * hid_dim_alpha
+        self.mol_lin0 = LinearBlock(mol_in_dim, hid, norm=pre_norm, dropout=pre_do, act=pre_act)
+        self.mol_conv = MessageBlock(hid, hid, mol_edge_in_dim, norm=graph_norm, dropout=graph_do, conv=mol_block,
+                                     act=graph_act, res=bool(graph_res))
+        self.message_steps = message_steps
+        self.mol_readout = _readout(mol_readout, hid)
+        self.mol_flat = LinearBlock(_readout_width(mol_readout) * hid, e_dim, norm=flat_norm, dropout=flat_do, act=flat_act)
+        self.lin_out1 = LinearBlock(e_dim, out_dim, norm=end_norm, dropout=end_do, act="_None")
+
+    def forward(self, data_mol):
+        B = _num_graphs(data_mol)
+        xm = self.mol_lin0(data_mol.x, batch=data_mol.batch)
+        hm = None
+        for _ in range(self.message_steps):
+            xm, hm = self.mol_conv(xm, data_mol.edge_index, data_mol.edge_attr, h=hm, batch=data_mol.batch)
+        outm = self.mol_readout(xm, data_mol.batch, num_graphs=B)
+        return self.lin_out1(self.mol_flat(outm))
+
+
+class _PairArchitecture(nn.Module):
+    """Two towers stepped in lock-step with a dot-pool fusion after every message step."""
+
+    prefixes = ("a", "b")
+
+    def _build(self, in_dims, edge_dims, blocks, readouts, hid, e_dim, out_dim, message_steps, norms, dos, acts, res):
+        pre_norm, graph_norm, flat_norm, end_norm = norms
+        pre_do, graph_do, flat_do, end_do = dos
+        pre_act, graph_act, flat_act, end_act = acts
+        pa, pb = self.prefixes
+        for p, d in zip((pa, pb), in_dims):
+            setattr(self, f"{p}_lin0", LinearBlock(d, hid, norm=pre_norm, dropout=pre_do, act=pre_act))
+        for p, de, blk in zip((pa, pb), edge_dims, blocks):
+            setattr(self, f"{p}_conv", MessageBlock(hid, hid, de, norm=graph_norm, dropout=graph_do, conv=blk,
+                                                    act=graph_act, res=bool(res)))
+        self.message_steps = message_steps
+        for p, ro in zip((pa, pb), readouts):
+            setattr(self, f"{p}_readout", _readout(ro, hid))
+        for p, ro in zip((pa, pb), readouts):
+            setattr(self, f"{p}_flat", LinearBlock(_readout_width(ro) * hid, hid, norm=flat_norm, dropout=flat_do, act=flat_act))
+        self.lin_out0 = LinearBlock(hid * 2 + message_steps * 2, e_dim, norm=end_norm, dropout=end_do, act=end_act)
+        self.lin_out1 = LinearBlock(e_dim, out_dim, norm=end_norm, dropout=end_do, act="_None")
+
+    def forward(self, da, db):
+        ta, tb = _Tower(self, self.prefixes[0]), _Tower(self, self.prefixes[1])
+        B = _num_graphs(da)
+        xa = ta.lin0(da.x, batch=da.batch)
+        xb = tb.lin0(db.x, batch=db.batch)
+        ha = hb = None
+        fusion = []
+        for _ in range(self.message_steps):
+            xa, ha = ta.conv(xa, da.edge_index, da.edge_attr, h=ha, batch=da.batch)
+            xb, hb = tb.conv(xb, db.edge_index, db.edge_attr, h=hb, batch=db.batch)
+            fusion.append(dot_and_global_pool2(xa, xb, da.batch, db.batch, num_graphs=B))
+        oa = ta.flat(ta.readout(xa, da.batch, num_graphs=B))
+        ob = tb.flat(tb.readout(xb, db.batch, num_graphs=B))
+        out = self.lin_out0(torch.cat([oa, ob] + fusion, dim=-1))
+        return self.lin_out1(out)
+
+
+class ArchitectureDDI(_PairArchitecture):
+    prefixes = ("mol1", "mol2")
+
+    def __init__(self, mol_in_dim=15, mol_edge_in_dim=4, hid_dim_alpha=4, e_dim=1024, out_dim=1,
+                 mol_block="_TripletMessage", message_steps=3, mol_readout="Set2Set",
+                 pre_norm="_None", graph_norm="_None", flat_norm="_None", end_norm="_None",
+                 pre_do="_None()", graph_do="Dropout(0.2)", flat_do="_None()", end_do="Dropout(0.2)",
+                 pre_act="RReLU", graph_act="RReLU", flat_act="RReLU", end_act="RReLU", graph_res=True):
+        super().__init__()
+        self._build((mol_in_dim, mol_in_dim), (mol_edge_in_dim, mol_edge_in_dim), (mol_block, mol_block),
+                    (mol_readout, mol_readout), mol_in_dim * hid_dim_alpha, e_dim, out_dim, message_steps,
+                    (pre_norm, graph_norm, flat_norm, end_norm), (pre_do, graph_do, flat_do, end_do),
+                    (pre_act, graph_act, flat_act, end_act), graph_res)
+
+
+class ArchitectureDTI(_PairArchitecture):
+    prefixes = ("mol", "pro")
+
+    def __init__(self, mol_in_dim=15, pro_in_dim=49, mol_edge_in_dim=4, pro_edge_in_dim=8, hid_dim_alpha=4, e_dim=1024,
+                 out_dim=1, mol_block="_TripletMessage", pro_block="_TripletMessage", message_steps=3,
+                 mol_readout="Set2Set", pro_readout="Set2Set",
+                 pre_norm="_None", graph_norm="_None", flat_norm="_None", end_norm="_None",
+                 pre_do="_None()", graph_do="Dropout(0.2)", flat_do="_None()", end_do="Dropout(0.2)",
+                 pre_act="RReLU", graph_act="RReLU", flat_act="RReLU", end_act="RReLU", graph_res=True):
+        super().__init__()
+        self._build((mol_in_dim, pro_in_dim), (mol_edge_in_dim, pro_edge_in_dim), (mol_block, pro_block),
+                    (mol_readout, pro_readout), mol_in_dim * hid_dim_alpha, e_dim, out_dim, message_steps,
+                    (pre_norm, graph_norm, flat_norm, end_norm), (pre_do, graph_do, flat_do, end_do),
+                    (pre_act, graph_act, flat_act, end_act), graph_res)
+
+
+Architecture = ArchitectureGP
+Model = ArchitectureGP

@@ -1,0 +1,175 @@
+/*
+ * glam_b200 — C ABI of the B200-native (sm_100a) GLAM message-passing hot path.
+ *
+ * This is the drop-in boundary: plain device pointers + sizes + a cudaStream_t, no torch types.
+ * The reference (yvquanli/GLAM) is pure Python; its hot path sits behind the `layer.py` module
+ * namespace.  `glam_b200/layer.py` mirrors that namespace and binds these entry
+ * points with ctypes (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with `h_`;
+ *   - matrices are row-major fp32 with an explicit leading dimension (`ld*`, in elements);
+ *   - indices inside the library are int32; `edge_index` / `batch` come in as the reference's int64;
+ *   - inputs are borrowed and never written; outputs / workspaces are caller-allocated;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises;
+ *   - return value: 0 = ok, <0 = invalid argument (see glam_last_error()), >0 = cudaError_t;
+ *   - no atomics on floating point anywhere: every reduction has a fixed order, results are
+ *     bitwise reproducible run to run.
+ *
+ * Reference citations are `path:line` under the upstream tree (yvquanli/GLAM).
+ */
+#ifndef GLAM_B200_H
+#define GLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLAM_B200_ABI_VERSION 1
+#define GLAM_MAX_HEADS 4
+
+int glam_abi_version(void);
+/* Human-readable description of the last non-zero status returned on this host thread. */
+const char* glam_last_error(void);
+/* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
+int64_t glam_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (1) Destination-sorted CSR builder.
+ * Replaces PyG's per-call `index_select(edge_index[0|1])` + atomic `scatter` (MessagePassing.propagate,
+ * reached from src_1gp/layer.py:40,86) with one index build per batch, reused by every message step
+ * and by backward.  Bit-exact against `torch.argsort(edge_index[1], stable=True)`:
+ *   dst_perm[p]   original edge id of the p-th edge in (dst, original order) order
+ *   dst_rowptr[i] .. dst_rowptr[i+1]  = in-edges of node i in that order
+ *   dst_src[p]    source node of edge dst_perm[p]
+ * and the same for sources (backward scatters by SOURCE):
+ *   src_perm / src_rowptr  (stable by edge_index[0]);  src_pos[k] = position p (dst order) of edge
+ *   src_perm[k];  src_dst[k] = destination node of that edge.
+ * workspace: >= glam_csr_workspace_bytes(N, E) bytes.
+ * --------------------------------------------------------------------------------------------- */
+size_t glam_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int glam_build_csr(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes,
+                   int32_t* dst_rowptr, int32_t* dst_src, int32_t* dst_perm,
+                   int32_t* src_rowptr, int32_t* src_pos, int32_t* src_dst,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* graph_ptr[g] = first node of graph g (B+1 entries) from the sorted int64 `batch` vector
+ * (PyG Batch.batch; replaces np.bincount(batch.cpu()) + cumsum, src_2gi_ddi/layer.py:271-272). */
+int glam_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs, int32_t* graph_ptr, void* stream);
+/* out[p, :] = in[perm[p], :]  (edge_attr into dst order, once per batch). */
+int glam_gather_rows(const float* in, const int32_t* perm, int64_t rows, int64_t cols, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2) Small dense contractions (projections).  Y[M,N] = epilogue(X[M,K] * W + bias).
+ * W(k,n) is addressed as W[k*w_sk + n*w_sn] so both `x @ W` (src_1gp/layer.py:37,59) and
+ * `x @ W^T` (torch.nn.GRU / Linear weights) are served without a transpose copy.
+ * epilogue: 0 none | 1 celu(alpha=1) (src_1gp/layer.py:261) | 2 Y = acc * celu'(aux) with aux the
+ * saved celu OUTPUT | 3 Y += acc.
+ * --------------------------------------------------------------------------------------------- */
+int glam_gemm(const float* X, int64_t ldx, const float* W, int64_t w_sk, int64_t w_sn, const float* bias,
+              const float* aux, int64_t ldaux, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K,
+              int epilogue, void* stream);
+/* Weight gradients: out[Ka,Kb] = sum_m A[m,Ka] * B[m,Kb]; fixed-order two-stage reduction.
+ * workspace >= glam_gemm_tn_workspace_bytes(M, Ka, Kb). */
+size_t glam_gemm_tn_workspace_bytes(int64_t M, int64_t Ka, int64_t Kb);
+int glam_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Kb,
+                 float* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream);
+/* Bias gradients: out[n] = sum_m G[m,n]; fixed order. workspace >= glam_colsum_workspace_bytes(M, N). */
+size_t glam_colsum_workspace_bytes(int64_t M, int64_t N);
+int glam_colsum(const float* G, int64_t ldg, int64_t M, int64_t N, float* out, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (3) Triplet attention edge phase — TripletMessage.message + aggregate (src_1gp/layer.py:42-55, :17)
+ * and TripletMessageLight.message (:88-97), restructured per SURVEY.md Appendix C.
+ *
+ * xpe [N, ldxp]: columns [0,HC) = x@weight_node, [HC,HC+H) = s_i (= <a_i, xp_h>), [HC+H,HC+2H) = s_j.
+ * edge_attr is in DST order ([E,De]); w_edge [De,HC] (NULL for the Light layer: e_ij == 1 in the message);
+ * att_edge [De,H] = per-head dot of w_edge rows with the edge slice of weight_triplet_att (Light: the raw
+ * edge slice).  One warp per destination node: logits -> leaky_relu -> PyG softmax
+ * exp(a-max)/(sum+1e-16) -> agg[i] = sum_e alpha * e_ij (.) x_j.  Writes alpha [E,H] (dst order).
+ * --------------------------------------------------------------------------------------------- */
+int glam_triplet_edge_fwd(const float* xpe, int64_t ldxp, const float* edge_attr, const float* w_edge,
+                          const float* att_edge, const int32_t* dst_rowptr, const int32_t* dst_src,
+                          int64_t num_nodes, int64_t num_edges, int heads, int channels, int edge_dim,
+                          float negative_slope, float* agg, float* alpha, void* stream);
+/* Backward, destination pass: from g_agg [N,HC] computes g_logit [E,H] (dst order), g_s_i into
+ * g_xpe[:, HC:HC+H], and per-warp partials of g_w_edge reduced in fixed order into g_w_edge [De,HC]
+ * (skipped when w_edge == NULL).  workspace >= glam_triplet_bwd_workspace_bytes(...). */
+size_t glam_triplet_bwd_workspace_bytes(int heads, int channels, int edge_dim);
+int glam_triplet_edge_bwd_dst(const float* xpe, int64_t ldxp, const float* edge_attr, const float* w_edge,
+                              const float* att_edge, const float* alpha, const float* g_agg,
+                              const int32_t* dst_rowptr, const int32_t* dst_src,
+                              int64_t num_nodes, int64_t num_edges, int heads, int channels, int edge_dim,
+                              float negative_slope, float* g_logit, float* g_xpe, float* g_w_edge,
+                              void* workspace, size_t workspace_bytes, void* stream);
+/* Backward, source pass: g_xpe[j, 0:HC] = sum over out-edges of alpha * g_agg[dst] (.) e_ij,
+ * g_xpe[j, HC+H:HC+2H] = sum g_logit, pad columns zeroed. */
+int glam_triplet_edge_bwd_src(const float* edge_attr, const float* w_edge, const float* alpha, const float* g_agg,
+                              const float* g_logit, const int32_t* src_rowptr, const int32_t* src_pos,
+                              const int32_t* src_dst, int64_t num_nodes, int64_t num_edges, int heads,
+                              int channels, int edge_dim, float* g_xpe, int64_t ldxp, void* stream);
+
+/* Derived weights of the triplet layers (parameter space, tiny): w_ext [C, ldxp] = weight_node | weight_node_h a_i,h |
+ * weight_node_h a_j,h | 0 and att_edge [De,H] = weight_edge_h a_e,h, with a_i|a_e|a_j the three slices of
+ * weight_triplet_att (concat order of src_1gp/layer.py:48).  light != 0: TripletMessageLight (:92), att is
+ * [2C+De], weight_edge unused.  The backward chains (g_w_ext, g_att_edge, optional direct g_w_edge) to the
+ * reference's parameters weight_node, weight_edge, weight_triplet_att. */
+int glam_triplet_prep_fwd(const float* weight_node, const float* weight_edge, const float* att, int channels, int heads,
+                          int edge_dim, int light, int ldxp, float* w_ext, float* att_edge, void* stream);
+int glam_triplet_prep_bwd(const float* weight_node, const float* weight_edge, const float* att, const float* g_w_ext,
+                          const float* g_att_edge, const float* g_w_edge_direct, int channels, int heads, int edge_dim,
+                          int light, int ldxp, float* g_weight_node, float* g_weight_edge, float* g_att, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (4) GRU node update of MessageBlock (src_1gp/layer.py:260-266): gates from gi = m W_ih^T + b_ih,
+ * gh = h W_hh^T + b_hh (both [N,3C], gate order r,z,n), h' = (1-z) n + z h, x_out = act(h' + identity).
+ * In place: gi is overwritten with [r|z|n] (saved for backward); gh's n-chunk is kept.
+ * act: 0 none | 1 relu | 2 leaky_relu(act_param) | 3 celu(alpha=1).  identity may be NULL (res=False).
+ * --------------------------------------------------------------------------------------------- */
+int glam_gru_gates_fwd(float* gi_rzn, const float* gh, const float* h, const float* identity, int64_t num_nodes,
+                       int channels, int act, float act_param, float* h_new, float* x_out, void* stream);
+/* Backward: g_x_out, g_h_carry (may be NULL) -> g_gi, g_gh [N,3C], g_h_prev (= g_h' * z), g_identity (may be NULL). */
+int glam_gru_gates_bwd(const float* rzn, const float* gh, const float* h, const float* x_out, const float* g_x_out,
+                       const float* g_h_carry, int64_t num_nodes, int channels, int act, float act_param,
+                       float* g_gi, float* g_gh, float* g_h_prev, float* g_identity, void* stream);
+/* LSTM cell gates for Set2Set (torch.nn.LSTM inside PyG Set2Set; src_1gp/model.py:41): gates [B,4C] (i,f,g,o,
+ * pre-activation, overwritten with the activated gates), c_prev -> c_new, h_new. */
+int glam_lstm_gates_fwd(float* gates, const float* c_prev, int64_t rows, int channels, float* c_new, float* h_new,
+                        void* stream);
+int glam_lstm_gates_bwd(const float* gates_act, const float* c_prev, const float* c_new, const float* g_h,
+                        const float* g_c_in, int64_t rows, int channels, float* g_gates, float* g_c_prev,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (5) Per-graph attention pooling shared by GlobalLAPool/GlobalAttention (src_1gp/layer.py:206-220) and
+ * one Set2Set step: e[n] = <x[n], q[g]> + q_bias, a = PyG softmax over the nodes of graph g,
+ * r[g] = sum_n a[n] x[n], asum[g] = sum_n a[n].   q_stride = 0 shares one q between graphs.
+ * --------------------------------------------------------------------------------------------- */
+int glam_seg_attn_pool_fwd(const float* x, int64_t ldx, const float* q, int64_t q_stride, const float* q_bias,
+                           const int32_t* graph_ptr, int64_t num_graphs, int channels,
+                           float* a, float* r, int64_t ldr, float* asum, void* stream);
+/* Backward: g_r [B,*], g_asum (may be NULL) -> g_x (+= if accumulate), g_q per graph [B,C], g_e [N]. */
+int glam_seg_attn_pool_bwd(const float* x, int64_t ldx, const float* q, int64_t q_stride, const float* a,
+                           const float* g_r, int64_t ldgr, const float* g_asum, const int32_t* graph_ptr,
+                           int64_t num_graphs, int channels, int accumulate,
+                           float* g_x, int64_t ldgx, float* g_q, float* g_e, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (6) Cross-graph interaction pool — dot_and_global_pool2 (src_2gi_ddi/layer.py:270-283, identical in
+ * src_2gi_dti_scr/layer.py): per pair g, S = Xa[g] Xb[g]^T, out[g] = [max S, mean S]; one CTA per
+ * pair, no host sync.  Saves argmax (a,b) as node indices and the per-graph column sums for backward.
+ * --------------------------------------------------------------------------------------------- */
+int glam_pair_dot_pool_fwd(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b,
+                           int64_t num_pairs, int channels, float* out, int32_t* argmax, float* sum_a,
+                           float* sum_b, void* stream);
+int glam_pair_dot_pool_bwd(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b,
+                           const float* g_out, const int32_t* argmax, const float* sum_a, const float* sum_b,
+                           int64_t num_pairs, int channels, float* g_xa, float* g_xb, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLAM_B200_H */

@@ -1,0 +1,405 @@
+"""GPU parity tests: the sm_100a kernels (through the C ABI / glam_b200.layer) against the CPU oracle and the
+golden vectors produced by the reference's own code.
+
+Tolerance (SURVEY.md §8c, fp32 mode): |ours - ref64| <= max(2*|ref32 - ref64|, 1e-5 + 1e-4*scale) on outputs and
+gradients; CSR / indices bit-exact; run-to-run bitwise identical.
+"""
+import copy
+
+import pytest
+import torch
+
+from helpers import case, ns, tol_check
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _load(mod, state):
+    mod.load_state_dict(state)
+    return mod.to(DEV)
+
+
+def _check_param_grads(mod, g32, g64, tag):
+    for n, p in mod.named_parameters():
+        assert p.grad is not None, f"{tag}: no grad for {n}"
+        tol_check(p.grad, g32[n], g64[n], f"{tag}.grad[{n}]")
+
+
+# ---------------------------------------------------------------------------------------------- CSR
+@pytest.mark.parametrize("kind", ["molecules", "random", "hub", "empty", "protein"])
+def test_csr_bit_exact(kind):
+    from glam_b200 import ops
+    from glam_b200.synth import make_molecule_batch, make_protein_batch
+    g = torch.Generator().manual_seed(5)
+    if kind == "molecules":
+        b = make_molecule_batch(300, seed=11)
+        ei, N = b.edge_index, b.num_nodes
+    elif kind == "protein":
+        b = make_protein_batch(3, seed=3)
+        ei, N = b.edge_index, b.num_nodes
+    elif kind == "random":
+        N = 1000
+        ei = torch.randint(0, N, (2, 20000), generator=g)          # duplicates, self loops, unsorted
+    elif kind == "hub":
+        N = 500
+        ei = torch.randint(0, N, (2, 5000), generator=g)
+        ei[1, :3000] = 7                                            # in-degree 3000 > 32: multi-chunk paths
+        ei[0, 1000:2500] = 9
+    else:
+        N, ei = 17, torch.zeros((2, 0), dtype=torch.int64)
+    csr = ops.build_csr(ei.to(DEV), N)
+    torch.cuda.synchronize()
+    src, dst = ei[0], ei[1]
+    perm = torch.argsort(dst, stable=True)
+    assert torch.equal(csr["dst_perm"].cpu().long(), perm)
+    assert torch.equal(csr["dst_src"].cpu().long(), src[perm])
+    rowptr = torch.zeros(N + 1, dtype=torch.long)
+    rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=N), 0)
+    assert torch.equal(csr["dst_rowptr"].cpu().long(), rowptr)
+    sperm = torch.argsort(src, stable=True)
+    srowptr = torch.zeros(N + 1, dtype=torch.long)
+    srowptr[1:] = torch.cumsum(torch.bincount(src, minlength=N), 0)
+    assert torch.equal(csr["src_rowptr"].cpu().long(), srowptr)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(perm.numel())
+    assert torch.equal(csr["src_pos"].cpu().long(), inv[sperm])
+    assert torch.equal(csr["src_dst"].cpu().long(), dst[sperm])
+    if kind == "molecules":
+        # reference-ordered batches: stable sort by dst == sort by key dst*N+src (torch_sparse convention)
+        assert torch.equal(perm, torch.argsort(dst * N + src))
+
+
+def test_graph_ptr_and_gather():
+    from glam_b200 import ops
+    batch = torch.tensor([0, 0, 0, 2, 2, 5, 5, 5, 5], dtype=torch.int64)       # graphs 1, 3, 4, 6 are empty
+    ptr = ops.graph_ptr(batch.to(DEV), 7).cpu()
+    assert ptr.tolist() == [0, 3, 3, 5, 5, 5, 9, 9]
+    x = torch.randn(50, 5)
+    perm = torch.randperm(50)
+    out = ops.gather_rows(x.to(DEV), perm.to(DEV).int()).cpu()
+    assert torch.equal(out, x[perm])
+
+
+# ---------------------------------------------------------------------------------------------- dense pieces
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (63, 36, 36), (1000, 116, 36), (777, 60, 180), (4096, 188, 60), (130, 270, 90)])
+def test_gemm_variants(M, N, K):
+    from glam_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    X, W, b = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g), torch.randn(N, generator=g)
+    ref = X.double() @ W.double() + b.double()
+    Y = ops.gemm(X.to(DEV), W.to(DEV), bias=b.to(DEV)).cpu()
+    tol_check(Y, (X @ W + b), ref, "gemm nn")
+    Yt = ops.gemm(X.to(DEV), W.t().contiguous().to(DEV), transpose_w=True, bias=b.to(DEV)).cpu()
+    tol_check(Yt, (X @ W + b), ref, "gemm nt")
+    Yc = ops.gemm(X.to(DEV), W.to(DEV), bias=b.to(DEV), epilogue=ops.EPI_CELU).cpu()
+    tol_check(Yc, torch.celu(X @ W + b), torch.celu(ref), "gemm celu")
+    acc = torch.randn(M, N, generator=g)
+    out = acc.clone().to(DEV)
+    ops.gemm(X.to(DEV), W.to(DEV), epilogue=ops.EPI_ACCUM, out=out)
+    tol_check(out.cpu(), acc + X @ W, acc.double() + X.double() @ W.double(), "gemm accum")
+    aux = torch.celu(torch.randn(M, N, generator=g))
+    Yg = ops.gemm(X.to(DEV), W.to(DEV), epilogue=ops.EPI_MUL_CELU_GRAD, aux=aux.to(DEV)).cpu()
+    d = torch.where(aux > 0, torch.ones_like(aux), aux + 1)
+    tol_check(Yg, (X @ W) * d, (X.double() @ W.double()) * d.double(), "gemm celu-grad")
+    # weight / bias gradients
+    A, B = torch.randn(M, K, generator=g), torch.randn(M, N, generator=g)
+    tol_check(ops.gemm_tn(A.to(DEV), B.to(DEV)).cpu(), A.t() @ B, A.double().t() @ B.double(), "gemm_tn")
+    tol_check(ops.colsum(B.to(DEV)).cpu(), B.sum(0), B.double().sum(0), "colsum")
+
+
+def test_gemm_tn_long_and_deterministic():
+    from glam_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    A, B = torch.randn(100_003, 36, generator=g).to(DEV), torch.randn(100_003, 116, generator=g).to(DEV)
+    o1, o2 = ops.gemm_tn(A, B), ops.gemm_tn(A, B)
+    assert torch.equal(o1, o2)
+    tol_check(o1.cpu(), (A.t() @ B).cpu(), (A.double().t() @ B.double()).cpu(), "gemm_tn long", rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------- golden layer cases
+@pytest.mark.parametrize("name,C,De", [("triplet_C36", 36, 3), ("triplet_C60", 60, 4), ("triplet_C15_edge", 15, 4)])
+def test_triplet_message_golden(golden_layers, name, C, De):
+    from glam_b200 import layer
+    c32, c64 = golden_layers[f"{name}_f32"], case(golden_layers, f"{name}_f64")
+    m = _load(layer.TripletMessage(C, De), c32["state"])
+    x = c32["x"].to(DEV).requires_grad_(True)
+    out = m(x, c32["edge_index"].to(DEV), c32["edge_attr"].to(DEV))
+    tol_check(out, c32["out"], c64["out"], f"{name}.out")
+    (out * c32["cot"].to(DEV)).sum().backward()
+    tol_check(x.grad, c32["grad_x"], c64["grad_x"], f"{name}.grad_x")
+    _check_param_grads(m, c32["grad_params"], c64["grad_params"], name)
+
+
+@pytest.mark.parametrize("name,C,De", [("light_C36", 36, 3), ("light_C45_edge", 45, 4)])
+def test_triplet_light_golden(golden_layers, name, C, De):
+    from glam_b200 import layer
+    c32, c64 = golden_layers[f"{name}_f32"], case(golden_layers, f"{name}_f64")
+    m = _load(layer.TripletMessageLight(C, De), c32["state"])
+    x = c32["x"].to(DEV).requires_grad_(True)
+    out = m(x, c32["edge_index"].to(DEV), c32["edge_attr"].to(DEV))
+    tol_check(out, c32["out"], c64["out"], f"{name}.out")
+    (out * c32["cot"].to(DEV)).sum().backward()
+    tol_check(x.grad, c32["grad_x"], c64["grad_x"], f"{name}.grad_x")
+    _check_param_grads(m, c32["grad_params"], c64["grad_params"], name)
+
+
+@pytest.mark.parametrize("name", ["block_triplet_C36", "block_triplet_pn_C60", "block_light_C30"])
+def test_message_block_golden(golden_layers, name):
+    from glam_b200 import layer
+    c32, c64 = golden_layers[f"{name}_f32"], case(golden_layers, f"{name}_f64")
+    cfg = c32["cfg"]
+    blk = _load(layer.MessageBlock(cfg["C"], cfg["C"], cfg["De"], norm=cfg["norm"], dropout="_None()", conv=cfg["conv"],
+                                   act=cfg["act"], res=cfg["res"]), c32["state"])
+    x0 = c32["x"].to(DEV).requires_grad_(True)
+    ei, ea, batch = c32["edge_index"].to(DEV), c32["edge_attr"].to(DEV), c32["batch"].to(DEV)
+    x, h = x0, None
+    for _ in range(cfg["steps"]):
+        x, h = blk(x, ei, ea, h=h, batch=batch)
+    tol_check(x, c32["out"], c64["out"], f"{name}.out")
+    tol_check(h, c32["h"], c64["h"], f"{name}.h")
+    ((x * c32["cot"].to(DEV)).sum() + (h * c32["coth"].to(DEV)).sum()).backward()
+    tol_check(x0.grad, c32["grad_x"], c64["grad_x"], f"{name}.grad_x")
+    _check_param_grads(blk, c32["grad_params"], c64["grad_params"], name)
+
+
+@pytest.mark.parametrize("name,kind,C", [("set2set_C36", "s2s", 36), ("set2set_C30", "s2s", 30),
+                                         ("lapool_C36", "la", 36), ("lapool_C45", "la", 45)])
+def test_readouts_golden(golden_layers, name, kind, C):
+    from glam_b200 import layer
+    c32, c64 = golden_layers[f"{name}_f32"], case(golden_layers, f"{name}_f64")
+    m = _load(layer.Set2Set(C, 3) if kind == "s2s" else layer.GlobalLAPool(C), c32["state"])
+    x = c32["x"].to(DEV).requires_grad_(True)
+    out = m(x, c32["batch"].to(DEV))
+    tol_check(out, c32["out"], c64["out"], f"{name}.out")
+    (out * c32["cot"].to(DEV)).sum().backward()
+    tol_check(x.grad, c32["grad_x"], c64["grad_x"], f"{name}.grad_x")
+    _check_param_grads(m, c32["grad_params"], c64["grad_params"], name)
+
+
+@pytest.mark.parametrize("name", ["dotpool_ddi_C36", "dotpool_dti_C60"])
+def test_dot_pool_golden(golden_layers, name):
+    from glam_b200 import layer
+    c32, c64 = golden_layers[f"{name}_f32"], case(golden_layers, f"{name}_f64")
+    xa = c32["xa"].to(DEV).requires_grad_(True)
+    xb = c32["xb"].to(DEV).requires_grad_(True)
+    out = layer.dot_and_global_pool2(xa, xb, c32["batch_a"].to(DEV), c32["batch_b"].to(DEV))
+    tol_check(out, c32["out"], c64["out"], f"{name}.out")
+    (out * c32["cot"].to(DEV)).sum().backward()
+    tol_check(xa.grad, c32["grad_xa"], c64["grad_xa"], f"{name}.grad_xa")
+    tol_check(xb.grad, c32["grad_xb"], c64["grad_xb"], f"{name}.grad_xb")
+
+
+# ---------------------------------------------------------------------------------------------- golden models
+@pytest.mark.parametrize("name", ["gp_set2set", "gp_lapool_light", "gp_set2set_pairnorm"])
+def test_model_gp_golden(golden_models, name):
+    from glam_b200 import model
+    from oracle import glam_oracle as O
+    c = golden_models[name]
+    cfg = c["cfg"]
+    kw = dict(hid_dim_alpha=4, e_dim=cfg["e_dim"], out_dim=1, mol_block=cfg["block"], message_steps=3,
+              mol_readout=cfg["readout"], graph_norm=cfg["graph_norm"], pre_act="ReLU", graph_act="CELU", flat_act="LeakyReLU")
+    m = model.ArchitectureGP(cfg["Din"], cfg["De"], graph_do="_None()", end_do="_None()", **kw)
+    m = _load(m, c["state"]).eval()
+    o64 = O.ArchitectureGP(cfg["Din"], cfg["De"], **kw)
+    o64.load_state_dict(c["state"])
+    o64 = o64.double().eval()
+    d64 = ns(c["x"].double(), c["edge_index"], c["edge_attr"].double(), c["batch"])
+    out64 = o64(d64)
+    loss64 = torch.nn.functional.mse_loss(out64, c["y"].double())
+    g64 = dict(zip([n for n, _ in o64.named_parameters()], torch.autograd.grad(loss64, list(o64.parameters()))))
+    data = ns(c["x"].to(DEV), c["edge_index"].to(DEV), c["edge_attr"].to(DEV), c["batch"].to(DEV))
+    out = m(data)
+    tol_check(out, c["out"], out64, f"{name}.out", rtol=2e-4)
+    loss = torch.nn.functional.mse_loss(out, c["y"].to(DEV))
+    loss.backward()
+    for n, p in m.named_parameters():
+        tol_check(p.grad, c["grad_params"][n], g64[n], f"{name}.grad[{n}]", rtol=2e-4)
+
+
+def test_model_ddi_golden(golden_models):
+    from glam_b200 import model
+    from oracle import glam_oracle as O
+    c = golden_models["ddi_set2set"]
+    cfg = c["cfg"]
+    m = model.ArchitectureDDI(cfg["Din"], cfg["De"], hid_dim_alpha=4, e_dim=cfg["e_dim"], out_dim=1, graph_do="_None()",
+                              end_do="_None()", pre_act="ReLU", graph_act="ReLU", flat_act="CELU", end_act="ReLU")
+    m = _load(m, c["state"]).eval()
+    o64 = O.ArchitecturePair(cfg["Din"], cfg["Din"], cfg["De"], cfg["De"], prefixes=("mol1", "mol2"), hid_dim_alpha=4,
+                             e_dim=cfg["e_dim"], out_dim=1, graph_act="ReLU", pre_act="ReLU", flat_act="CELU", end_act="ReLU")
+    o64.load_state_dict(c["state"])
+    o64 = o64.double().eval()
+    a64 = ns(c["a_x"].double(), c["a_edge_index"], c["a_edge_attr"].double(), c["a_batch"])
+    b64 = ns(c["b_x"].double(), c["b_edge_index"], c["b_edge_attr"].double(), c["b_batch"])
+    out64 = o64(a64, b64)
+    loss64 = torch.nn.functional.binary_cross_entropy_with_logits(out64, c["y"].double())
+    g64 = dict(zip([n for n, _ in o64.named_parameters()], torch.autograd.grad(loss64, list(o64.parameters()))))
+    a = ns(*[c[k].to(DEV) for k in ("a_x", "a_edge_index", "a_edge_attr", "a_batch")])
+    b = ns(*[c[k].to(DEV) for k in ("b_x", "b_edge_index", "b_edge_attr", "b_batch")])
+    out = m(a, b)
+    tol_check(out, c["out"], out64, "ddi.out", rtol=2e-4)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(out, c["y"].to(DEV))
+    loss.backward()
+    for n, p in m.named_parameters():
+        tol_check(p.grad, c["grad_params"][n], g64[n], f"ddi.grad[{n}]", rtol=2e-4)
+
+
+# ---------------------------------------------------------------------------------------------- oracle on seeded inputs
+def _gp_pair(Din, De, readout, block, act="CELU"):
+    from glam_b200 import model
+    from oracle import glam_oracle as O
+    kw = dict(hid_dim_alpha=4, e_dim=128, out_dim=1, mol_block=block, message_steps=3, mol_readout=readout,
+              pre_act="ReLU", graph_act=act, flat_act="ReLU")
+    torch.manual_seed(99)
+    o = O.ArchitectureGP(Din, De, **kw).eval()
+    m = model.ArchitectureGP(Din, De, graph_do="_None()", end_do="_None()", **kw)
+    m.load_state_dict(o.state_dict())
+    return m.to(DEV).eval(), o
+
+
+@pytest.mark.parametrize("Din,De,readout,block,B", [(9, 3, "Set2Set", "_TripletMessage", 128),
+                                                   (15, 4, "GlobalLAPool", "_TripletMessage", 96),
+                                                   (15, 4, "Set2Set", "_TripletMessageLight", 64)])
+def test_gp_training_step_vs_oracle(Din, De, readout, block, B):
+    """BASELINE config 1 shape (128 ESOL-like molecules): forward + backward against the fp32 and fp64 oracle."""
+    from glam_b200.synth import make_molecule_batch
+    m, o32 = _gp_pair(Din, De, readout, block)
+    o64 = copy.deepcopy(o32).double()
+    b = make_molecule_batch(B, node_dim=Din, edge_dim=De, seed=2024)
+    d32 = ns(b.x, b.edge_index, b.edge_attr, b.batch)
+    d64 = ns(b.x.double(), b.edge_index, b.edge_attr.double(), b.batch)
+    out32, out64 = o32(d32), o64(d64)
+    l32 = torch.nn.functional.mse_loss(out32, b.y)
+    l64 = torch.nn.functional.mse_loss(out64, b.y.double())
+    g32 = torch.autograd.grad(l32, list(o32.parameters()))
+    g64 = torch.autograd.grad(l64, list(o64.parameters()))
+    bd = b.to(DEV)
+    out = m(bd)
+    tol_check(out, out32, out64, "gp.out", rtol=2e-4)
+    torch.nn.functional.mse_loss(out, bd.y).backward()
+    for (n, p), a, c in zip(m.named_parameters(), g32, g64):
+        tol_check(p.grad, a, c, f"gp.grad[{n}]", rtol=2e-4)
+
+
+def test_dti_shaped_pair_vs_oracle():
+    """BASELINE config 4 shape: ligand graph + protein contact-map graph (hundreds of residues, De=8, duplicate edges)."""
+    from glam_b200 import model
+    from glam_b200.synth import make_molecule_batch, make_protein_batch
+    from oracle import glam_oracle as O
+    torch.manual_seed(5)
+    kw = dict(hid_dim_alpha=2, e_dim=64, out_dim=2, message_steps=2)
+    o32 = O.ArchitecturePair(15, 49, 4, 8, prefixes=("mol", "pro"), graph_act="CELU", **kw).eval()
+    m = model.ArchitectureDTI(15, 49, 4, 8, graph_do="_None()", end_do="_None()", pre_act="ReLU", graph_act="CELU",
+                              flat_act="ReLU", end_act="ReLU", **kw)
+    m.load_state_dict(o32.state_dict())
+    m = m.to(DEV).eval()
+    o64 = copy.deepcopy(o32).double()
+    a = make_molecule_batch(6, node_dim=15, edge_dim=4, seed=8)
+    p = make_protein_batch(6, seed=9, min_len=150, max_len=320)
+    y = torch.randint(0, 2, (6,))
+    out32 = o32(ns(a.x, a.edge_index, a.edge_attr, a.batch), ns(p.x, p.edge_index, p.edge_attr, p.batch))
+    out64 = o64(ns(a.x.double(), a.edge_index, a.edge_attr.double(), a.batch),
+                ns(p.x.double(), p.edge_index, p.edge_attr.double(), p.batch))
+    g32 = torch.autograd.grad(torch.nn.functional.cross_entropy(out32, y), list(o32.parameters()))
+    g64 = torch.autograd.grad(torch.nn.functional.cross_entropy(out64, y), list(o64.parameters()))
+    out = m(a.to(DEV), p.to(DEV))
+    tol_check(out, out32, out64, "dti.out", rtol=2e-4)
+    torch.nn.functional.cross_entropy(out, y.to(DEV)).backward()
+    for (n, prm), g_a, g_c in zip(m.named_parameters(), g32, g64):
+        tol_check(prm.grad, g_a, g_c, f"dti.grad[{n}]", rtol=2e-4)
+
+
+# ---------------------------------------------------------------------------------------------- properties
+def test_hub_node_multichunk_softmax():
+    """A destination with in-degree > 32 exercises the multi-chunk softmax path; isolated nodes give `bias`."""
+    from glam_b200 import layer
+    from oracle import glam_oracle as O
+    torch.manual_seed(1)
+    N, C, De = 300, 36, 3
+    g = torch.Generator().manual_seed(2)
+    ei = torch.randint(0, N - 10, (2, 1500), generator=g)
+    ei[1, :200] = 5
+    ei[1, 200:240] = 6
+    ea = torch.eye(De)[torch.randint(0, De, (1500,), generator=g)] * torch.rand(1500, 1, generator=g)
+    x = torch.randn(N, C, generator=g)
+    o = O.TripletMessage(C, De)
+    with torch.no_grad():
+        o.bias.uniform_(-1, 1)
+    m = layer.TripletMessage(C, De)
+    m.load_state_dict(o.state_dict())
+    m = m.to(DEV)
+    x32 = x.clone().requires_grad_(True)
+    x64 = x.double().requires_grad_(True)
+    o64 = copy.deepcopy(o).double()
+    out32, out64 = o(x32, ei, ea), o64(x64, ei, ea.double())
+    cot = torch.randn(N, C, generator=g)
+    g32 = torch.autograd.grad((out32 * cot).sum(), [x32] + list(o.parameters()))
+    g64 = torch.autograd.grad((out64 * cot.double()).sum(), [x64] + list(o64.parameters()))
+    xd = x.to(DEV).requires_grad_(True)
+    out = m(xd, ei.to(DEV), ea.to(DEV))
+    tol_check(out, out32, out64, "hub.out")
+    assert torch.equal(out[N - 5:].detach().cpu(), o.bias.detach().expand(5, C))      # isolated nodes -> bias exactly
+    (out * cot.to(DEV)).sum().backward()
+    tol_check(xd.grad, g32[0], g64[0], "hub.grad_x")
+    for (n, p), a, c in zip(m.named_parameters(), g32[1:], g64[1:]):
+        tol_check(p.grad, a, c, f"hub.grad[{n}]")
+
+
+def test_edge_permutation_invariance_and_determinism():
+    from glam_b200 import layer, graph
+    from glam_b200.synth import make_molecule_batch
+    torch.manual_seed(3)
+    b = make_molecule_batch(200, node_dim=36, edge_dim=3, seed=77, features="normal").to(DEV)
+    m = layer.TripletMessage(36, 3).to(DEV)
+    with torch.no_grad():
+        out1 = m(b.x, b.edge_index, b.edge_attr)
+        graph.clear_caches()
+        out2 = m(b.x, b.edge_index.clone(), b.edge_attr.clone())
+        assert torch.equal(out1, out2)                                       # bitwise reproducible
+        perm = torch.randperm(b.num_edges, device=DEV)
+        out3 = m(b.x, b.edge_index[:, perm].contiguous(), b.edge_attr[perm].contiguous())
+    torch.testing.assert_close(out3, out1, rtol=1e-5, atol=1e-6)             # summation order may change
+
+
+def test_batch_of_one_equals_unbatched():
+    from glam_b200 import layer
+    from glam_b200.synth import make_molecule_batch, shard_by_graph
+    torch.manual_seed(4)
+    b = make_molecule_batch(8, node_dim=36, edge_dim=3, seed=5, features="normal")
+    blk = layer.MessageBlock(36, 36, 3, norm="_None", dropout="_None()", conv="_TripletMessage", act="ReLU").to(DEV).eval()
+    ro = layer.Set2Set(36, 3).to(DEV)
+    bd = b.to(DEV)
+    with torch.no_grad():
+        x, h = blk(bd.x, bd.edge_index, bd.edge_attr, batch=bd.batch)
+        full = ro(x, bd.batch)
+        for gidx in (0, 3, 7):
+            one = shard_by_graph(b, gidx, 8).to(DEV)
+            x1, _ = blk(one.x, one.edge_index, one.edge_attr, batch=one.batch)
+            r1 = ro(x1, one.batch)
+            torch.testing.assert_close(r1[0], full[gidx], rtol=1e-5, atol=1e-6)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (4096 graphs): attention rows sum to 1 per (destination, head) and the aggregate
+    conserves mass: sum_i agg[i] == sum_e alpha_e * e_ij (.) x_j (checksum of checksums)."""
+    from glam_b200 import layer, graph, ops
+    from glam_b200.synth import make_molecule_batch
+    torch.manual_seed(6)
+    b = make_molecule_batch(4096, node_dim=36, edge_dim=3, seed=1234, features="normal").to(DEV)
+    m = layer.TripletMessage(36, 3).to(DEV)
+    with torch.no_grad():
+        g = graph.graph_index(b.edge_index, b.num_nodes)
+        ea = g.sorted_edge_attr(b.edge_attr)
+        w_ext, att_edge = m.derived()
+        xpe = ops.gemm(b.x, w_ext)
+        agg, alpha = ops.triplet_edge_fwd(xpe, ea, m.weight_edge, att_edge, g, 3, 36, 0.2)
+        seg = torch.zeros(b.num_nodes, 3, device=DEV).index_add_(0, b.edge_index[1][g.dst_perm.long()], alpha)
+        has_in = (g.dst_rowptr[1:] > g.dst_rowptr[:-1])
+        torch.testing.assert_close(seg[has_in], torch.ones_like(seg[has_in]), rtol=1e-5, atol=1e-5)
+        ep = (ea @ m.weight_edge).view(-1, 3, 36)
+        xj = xpe[g.dst_src.long(), :108].view(-1, 3, 36)
+        total = (alpha.unsqueeze(-1) * ep * xj).double().sum(0).view(-1)
+        torch.testing.assert_close(agg.double().sum(0), total, rtol=1e-6, atol=1e-3)
+        out = m(b.x, b.edge_index, b.edge_attr)
+    assert torch.isfinite(out).all() and out.shape == (b.num_nodes, 36)
