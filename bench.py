@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's headline metric on its headline config.
+
+Metric: molecular graphs/sec, forward+backward(+Adam) of GLAM-GP on 4096-graph synthetic
+MoleculeNet-shaped batches (BASELINE.json configs[1]; ~25 atoms, ~54 directed bonds, 9-dim atom /
+3-dim bond features, C = 36, H = 3, 3 message steps, Set2Set readout, e_dim 1024).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (one process per GPU under torchrun)
+  python bench.py --impl reference ...                         the reference's CPU path (oracle port) on host cores
+
+One JSON line on stdout from rank 0 (see README / DESIGN.md §Measurement for every key).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "molecular graphs/sec fwd+bwd (GLAM-GP training step)"
+UNIT = "graphs/s"
+DIMS = dict(node_dim=9, edge_dim=3)
+GRAPHS = 4096
+TOTAL_NODES = 25 * GRAPHS            # 102 400 (config 2)
+TOTAL_EDGES = 54 * GRAPHS            # 221 184
+MODEL_KW = dict(hid_dim_alpha=4, e_dim=1024, out_dim=1, mol_block="_TripletMessage", message_steps=3,
+                mol_readout="Set2Set", pre_act="ReLU", graph_act="CELU", flat_act="ReLU")
+N_RESIDENT = 16                      # distinct batches rotated through (16 x 10.7 MB inputs; each step also writes
+                                     # ~0.7 GB of activations) -> nothing survives in the 126 MB L2 between steps
+
+
+def workload_config(world):
+    return {"workload": "GLAM-GP training step, 4096-graph synthetic MoleculeNet-shaped batches per GPU "
+                        "(BASELINE.json configs[1])",
+            "graphs_per_gpu_batch": GRAPHS, "nodes": TOTAL_NODES, "edges": TOTAL_EDGES, **DIMS, "hidden": 36, "heads": 3,
+            "message_steps": 3, "readout": "Set2Set", "e_dim": 1024, "loss": "mse", "optimizer": "Adam",
+            "parallelism": f"dp{world} (graphs sharded by molecule; one NCCL all-reduce of a flat fp32 grad bucket)"
+                           if world > 1 else "single GPU",
+            "l2": f"inputs rotate over {N_RESIDENT} distinct batches (171 MB) and every step streams ~0.7 GB of "
+                  "activations: larger than the 126 MB L2"}
+
+
+def make_batches(n, rank, pin):
+    from glam_b200.synth import make_molecule_batch
+    out = []
+    for i in range(n):
+        b = make_molecule_batch(GRAPHS, seed=1234 + 1000 * rank + i, total_nodes=TOTAL_NODES, total_edges=TOTAL_EDGES, **DIMS)
+        out.append(b.pin_memory() if pin else b)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md's clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def oracle_model(seed=0):
+    from oracle import glam_oracle as O
+    torch.manual_seed(seed)
+    return O.ArchitectureGP(DIMS["node_dim"], DIMS["edge_dim"], **MODEL_KW)
+
+
+def cpu_train_throughput(sample_graphs, steps, warmup):
+    """The reference's unfused CPU path (oracle port): fwd + MSE + bwd + Adam on `sample_graphs`-graph batches."""
+    from glam_b200.synth import make_molecule_batch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = oracle_model().train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    batches = [make_molecule_batch(sample_graphs, seed=77 + i, **DIMS) for i in range(2)]
+
+    def one(b):
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(model(b), b.y)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    for i in range(warmup):
+        one(batches[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(batches[i % 2])
+    dt = time.perf_counter() - t0
+    return sample_graphs * steps / dt, dt / steps, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 512
+    gps, sec, threads = cpu_train_throughput(sample, args.steps, max(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": gps, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample}-graph slices of the workload per step (oracle/glam_oracle.py: pure-PyTorch "
+                                       "restatement of the reference's unfused layer.py path; the reference itself needs "
+                                       "torch_geometric, absent from this image)"},
+            "e2e": {"value": gps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ roofline of the top kernel
+def kernel_bytes_model(label, N, E, B, C=36, H=3, De=3):
+    """Algorithmic bytes of one launch: every operand read or written exactly once,
+    fp32 activations, int32 indices, parameters amortised to zero."""
+    HC, ld = H * C, (H * C + 2 * H + 3) // 4 * 4
+    if label.startswith("glam_triplet_edge_fwd"):
+        return 4 * (N * ld + N * HC + E * De + E * H) + 4 * (E + N + 1)
+    if label.startswith("glam_triplet_edge_bwd_dst"):
+        return 4 * (N * ld + N * HC + E * De + 2 * E * H + N * H) + 4 * (E + N + 1)
+    if label.startswith("glam_triplet_edge_bwd_src"):
+        return 4 * (N * HC + N * ld + E * De + 2 * E * H) + 4 * (3 * E + N + 1)
+    if label.startswith("glam_gemm_tn"):
+        import re
+        m = re.search(r"M=(\d+),Ka=(\d+),Kb=(\d+)", label)
+        M, Ka, Kb = map(int, m.groups())
+        return 4 * (M * Ka + M * Kb + Ka * Kb)
+    if label.startswith("glam_gemm["):
+        import re
+        m = re.search(r"M=(\d+),N=(\d+),K=(\d+),\w+,epi=(\d)", label)
+        M, Nn, K, epi = map(int, m.groups())
+        extra = M * Nn if epi in (2, 3) else 0
+        return 4 * (M * K + M * Nn + extra)
+    if label.startswith("glam_colsum"):
+        import re
+        m = re.search(r"M=(\d+),N=(\d+)", label)
+        M, Nn = map(int, m.groups())
+        return 4 * (M * Nn + Nn)
+    if label.startswith("glam_gru_gates_fwd"):
+        return 4 * N * C * (6 + 2 + 3 + 2)
+    if label.startswith("glam_gru_gates_bwd"):
+        return 4 * N * C * (3 + 1 + 1 + 1 + 2 + 6 + 2)
+    return None
+
+
+def profile_kernels(ts, dev_batches, reps):
+    """Eager (un-graphed) training steps with a CUDA-event pair around every C-ABI call on the launching stream."""
+    from glam_b200 import ops, graph as G
+    sink = []
+    ops.set_profile(sink)
+    world, ts.world = ts.world, 1                    # rank-local measurement: no collective here
+    try:
+        for i in range(reps):
+            ts.load(dev_batches[i % len(dev_batches)])
+            G.clear_caches()
+            ts._body()
+        torch.cuda.synchronize()
+    finally:
+        ops.set_profile(None)
+        ts.world = world
+    agg = {}
+    for name, e0, e1 in sink:
+        t, n = agg.get(name, (0.0, 0))
+        agg[name] = (t + e0.elapsed_time(e1), n + 1)
+    return {k: (t / reps, n // reps, t / n) for k, (t, n) in agg.items()}     # ms per step, launches per step, ms per launch
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from glam_b200 import _lib, model as M
+    from glam_b200.engine import TrainStep
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    _lib.load()                                      # fail loudly if the CUDA library is missing
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)                             # identical replicas on every rank
+    net = M.ArchitectureGP(DIMS["node_dim"], DIMS["edge_dim"], graph_do="_None()", flat_do="_None()", end_do="_None()",
+                           **MODEL_KW).train()
+    host = make_batches(N_RESIDENT, rank, pin=True)
+    resident = [b.to(dev) for b in host]
+    n0 = _lib.launch_count()
+    ts = TrainStep(net, torch.nn.functional.mse_loss, resident[0], lr=1e-3, device=dev, world_size=world,
+                   use_cuda_graph=not args.no_cuda_graph, warmup=3)
+    captured = ts.graph is not None
+    # kernels of ours in one step = launches seen during the capture pass (the capture ran the body exactly once)
+    n1 = _lib.launch_count()
+    ts_probe_before = _lib.launch_count()
+    if not captured:
+        ts.run_resident()
+    launches_per_step = (n1 - n0) // 4 if captured else _lib.launch_count() - ts_probe_before   # 3 warm-ups + 1 capture
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    # ---- arm 1: inputs resident in HBM
+    def step_resident(i):
+        ts.load(resident[i % N_RESIDENT])
+        ts.run_resident()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    with ClockSampler(local) as clk:
+        ms_total = timed(step_resident, args.steps)
+    ms_per_step = ms_total / args.steps
+    value = GRAPHS * world / (ms_per_step * 1e-3)
+
+    # ---- arm 2: end to end through the public API with pinned HOST batches, loss read back every step
+    losses = []
+
+    def step_e2e(i):
+        loss = ts.step(host[i % N_RESIDENT])
+        losses.append(loss.item())                   # D2H read of the step's result
+
+    for i in range(args.warmup):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = GRAPHS * world / (ms_e2e * 1e-3)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world), "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host[0].nbytes(), "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+            "cuda_graph": captured, "final_loss": losses[-1] if losses else None}
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel: CUDA events around every library call, eager, same inputs
+        prof = profile_kernels(ts, resident, reps=3)
+        top = max(prof.items(), key=lambda kv: kv[1][0])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        nbytes = kernel_bytes_model(top[0], TOTAL_NODES, TOTAL_EDGES, GRAPHS)
+        total_ms = sum(v[0] for v in prof.values())
+        achieved = (nbytes / (top[1][2] * 1e-3) / 1e9) if nbytes else None
+        line["roofline"] = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": (achieved / peak) if achieved else None, "traffic": None,
+                            "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
+                            "ms_per_launch": top[1][2], "launches_per_step": top[1][1],
+                            "share_of_library_time": top[1][0] / total_ms, "algorithmic_bytes_per_launch": nbytes}
+        line["kernel_profile_ms_per_step"] = {k: round(v[0], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:12]}
+        line["kernel_profile_total_ms"] = round(total_ms, 4)
+        if world == 1 and not args.no_cpu_baseline:
+            gps, sec, threads = cpu_train_throughput(512, 6, 2)
+            line["cpu_baseline"] = {"value": gps, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "6 training steps on 512-graph slices of the same synthetic workload "
+                                              "(oracle/glam_oracle.py, all host threads)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,27 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+_profile = None     # when a list: (name, start_event, end_event) per C-ABI call (bench.py's per-kernel timing)
+
+
+def set_profile(sink):
+    """Enable (sink = list) or disable (None) CUDA-event timing of every library call on the current stream."""
+    global _profile
+    _profile = sink
+
+
+def _call(name: str, *args, label: str = ""):
+    fn = getattr(_lib.load(), name)
+    if _profile is None:
+        _lib.check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(fn(*args), name)
+    e1.record()
+    _profile.append((name + label, e0, e1))
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -55,9 +76,9 @@ def build_csr(edge_index: torch.Tensor, num_nodes: int):
     }
     nbytes = lib.glam_csr_workspace_bytes(N, E)
     ws = _ws(nbytes, dev)
-    _lib.check(lib.glam_build_csr(_p(edge_index), E, N, _p(out["dst_rowptr"]), _p(out["dst_src"]), _p(out["dst_perm"]),
+    _call("glam_build_csr", _p(edge_index), E, N, _p(out["dst_rowptr"]), _p(out["dst_src"]), _p(out["dst_perm"]),
                                   _p(out["src_rowptr"]), _p(out["src_pos"]), _p(out["src_dst"]), _p(ws), ws.numel(),
-                                  _stream(edge_index)), "glam_build_csr")
+                                  _stream(edge_index))
     return out
 
 
@@ -67,8 +88,7 @@ def graph_ptr(batch: torch.Tensor, num_graphs: int) -> torch.Tensor:
         raise _lib.GlamError("batch must be int64 [N]")
     batch = batch.contiguous()
     out = torch.empty(int(num_graphs) + 1, dtype=torch.int32, device=batch.device)
-    _lib.check(_lib.load().glam_graph_ptr(_p(batch), batch.shape[0], int(num_graphs), _p(out), _stream(batch)),
-               "glam_graph_ptr")
+    _call("glam_graph_ptr", _p(batch), batch.shape[0], int(num_graphs), _p(out), _stream(batch))
     return out
 
 
@@ -77,8 +97,7 @@ def gather_rows(src: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
     src = _f32c(src, "gather_rows")
     src2 = src.view(src.shape[0], -1) if src.dim() != 2 else src
     out = torch.empty((perm.shape[0], src2.shape[1]), dtype=torch.float32, device=src.device)
-    _lib.check(_lib.load().glam_gather_rows(_p(src2), _p(perm), perm.shape[0], src2.shape[1], _p(out), _stream(src)),
-               "glam_gather_rows")
+    _call("glam_gather_rows", _p(src2), _p(perm), perm.shape[0], src2.shape[1], _p(out), _stream(src))
     return out
 
 
@@ -104,9 +123,9 @@ def gemm(X: torch.Tensor, W: torch.Tensor, transpose_w: bool = False, bias: Opti
     ld = out.stride(0)
     if aux is not None:
         assert aux.stride(1) == 1
-    _lib.check(_lib.load().glam_gemm(_p(X), X.stride(0), _p(W), w_sk, w_sn, _p(bias), _p(aux),
-                                     0 if aux is None else aux.stride(0), _p(out), ld, M, N, K, epilogue, _stream(X)),
-               "glam_gemm")
+    _call("glam_gemm", _p(X), X.stride(0), _p(W), w_sk, w_sn, _p(bias), _p(aux),
+                                     0 if aux is None else aux.stride(0), _p(out), ld, M, N, K, epilogue, _stream(X),
+          label=f"[M={M},N={N},K={K},{'nt' if transpose_w else 'nn'},epi={epilogue}]")
     return out
 
 
@@ -119,8 +138,8 @@ def gemm_tn(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty((Ka, Kb), dtype=torch.float32, device=A.device)
     ws = _ws(lib.glam_gemm_tn_workspace_bytes(M, Ka, Kb), A.device)
-    _lib.check(lib.glam_gemm_tn(_p(A), A.stride(0), _p(B), B.stride(0), M, Ka, Kb, _p(out), Kb, _p(ws), ws.numel(),
-                                _stream(A)), "glam_gemm_tn")
+    _call("glam_gemm_tn", _p(A), A.stride(0), _p(B), B.stride(0), M, Ka, Kb, _p(out), Kb, _p(ws), ws.numel(),
+          _stream(A), label=f"[M={M},Ka={Ka},Kb={Kb}]")
     return out
 
 
@@ -131,7 +150,7 @@ def colsum(G: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty((N,), dtype=torch.float32, device=G.device)
     ws = _ws(lib.glam_colsum_workspace_bytes(M, N), G.device)
-    _lib.check(lib.glam_colsum(_p(G), G.stride(0), M, N, _p(out), _p(ws), ws.numel(), _stream(G)), "glam_colsum")
+    _call("glam_colsum", _p(G), G.stride(0), M, N, _p(out), _p(ws), ws.numel(), _stream(G), label=f"[M={M},N={N}]")
     return out
 
 
@@ -141,10 +160,9 @@ def triplet_edge_fwd(xpe, ea_sorted, w_edge, att_edge, g, heads, channels, slope
     HC = heads * channels
     agg = torch.empty((N, HC), dtype=torch.float32, device=dev)
     alpha = torch.empty((E, heads), dtype=torch.float32, device=dev)
-    _lib.check(_lib.load().glam_triplet_edge_fwd(_p(xpe), xpe.stride(0), _p(ea_sorted), _p(w_edge), _p(att_edge),
+    _call("glam_triplet_edge_fwd", _p(xpe), xpe.stride(0), _p(ea_sorted), _p(w_edge), _p(att_edge),
                                                  _p(g.dst_rowptr), _p(g.dst_src), N, E, heads, channels,
-                                                 ea_sorted.shape[1], float(slope), _p(agg), _p(alpha), _stream(xpe)),
-               "glam_triplet_edge_fwd")
+                                                 ea_sorted.shape[1], float(slope), _p(agg), _p(alpha), _stream(xpe))
     return agg, alpha
 
 
@@ -161,13 +179,13 @@ def triplet_edge_bwd(xpe, ea_sorted, w_edge, att_edge, alpha, g_agg, g, heads, c
         g_we = torch.empty((De, HC), dtype=torch.float32, device=dev)
         ws = _ws(lib.glam_triplet_bwd_workspace_bytes(heads, channels, De), dev)
     st = _stream(xpe)
-    _lib.check(lib.glam_triplet_edge_bwd_dst(_p(xpe), ld, _p(ea_sorted), _p(w_edge), _p(att_edge), _p(alpha), _p(g_agg),
+    _call("glam_triplet_edge_bwd_dst", _p(xpe), ld, _p(ea_sorted), _p(w_edge), _p(att_edge), _p(alpha), _p(g_agg),
                                              _p(g.dst_rowptr), _p(g.dst_src), N, E, heads, channels, De, float(slope),
                                              _p(g_logit), _p(g_xpe), _p(g_we), _p(ws), 0 if ws is None else ws.numel(),
-                                             st), "glam_triplet_edge_bwd_dst")
-    _lib.check(lib.glam_triplet_edge_bwd_src(_p(ea_sorted), _p(w_edge), _p(alpha), _p(g_agg), _p(g_logit),
+                                             st)
+    _call("glam_triplet_edge_bwd_src", _p(ea_sorted), _p(w_edge), _p(alpha), _p(g_agg), _p(g_logit),
                                              _p(g.src_rowptr), _p(g.src_pos), _p(g.src_dst), N, E, heads, channels, De,
-                                             _p(g_xpe), ld, st), "glam_triplet_edge_bwd_src")
+                                             _p(g_xpe), ld, st)
     return g_xpe, g_logit, g_we
 
 
@@ -175,9 +193,8 @@ def triplet_prep_fwd(weight_node, weight_edge, att, channels, heads, edge_dim, l
     dev = weight_node.device
     w_ext = torch.empty((channels, ldxp), dtype=torch.float32, device=dev)
     att_edge = torch.empty((edge_dim, heads), dtype=torch.float32, device=dev)
-    _lib.check(_lib.load().glam_triplet_prep_fwd(_p(weight_node), _p(weight_edge), _p(att), channels, heads, edge_dim,
-                                                 1 if light else 0, ldxp, _p(w_ext), _p(att_edge), _stream(weight_node)),
-               "glam_triplet_prep_fwd")
+    _call("glam_triplet_prep_fwd", _p(weight_node), _p(weight_edge), _p(att), channels, heads, edge_dim,
+                                                 1 if light else 0, ldxp, _p(w_ext), _p(att_edge), _stream(weight_node))
     return w_ext, att_edge
 
 
@@ -186,10 +203,9 @@ def triplet_prep_bwd(weight_node, weight_edge, att, g_w_ext, g_att_edge, g_w_edg
     g_wn = torch.empty_like(weight_node)
     g_we = None if light else torch.empty_like(weight_edge)
     g_att = torch.empty_like(att)
-    _lib.check(_lib.load().glam_triplet_prep_bwd(_p(weight_node), _p(weight_edge), _p(att), _p(g_w_ext), _p(g_att_edge),
+    _call("glam_triplet_prep_bwd", _p(weight_node), _p(weight_edge), _p(att), _p(g_w_ext), _p(g_att_edge),
                                                  _p(g_w_edge_direct), channels, heads, edge_dim, 1 if light else 0, ldxp,
-                                                 _p(g_wn), _p(g_we), _p(g_att), _stream(weight_node)),
-               "glam_triplet_prep_bwd")
+                                                 _p(g_wn), _p(g_we), _p(g_att), _stream(weight_node))
     return g_wn, g_we, g_att
 
 
@@ -198,8 +214,8 @@ def gru_gates_fwd(gi, gh, h, identity, act, act_param):
     N, C = h.shape
     h_new = torch.empty_like(h)
     x_out = torch.empty_like(h)
-    _lib.check(_lib.load().glam_gru_gates_fwd(_p(gi), _p(gh), _p(h), _p(identity), N, C, act, float(act_param),
-                                              _p(h_new), _p(x_out), _stream(h)), "glam_gru_gates_fwd")
+    _call("glam_gru_gates_fwd", _p(gi), _p(gh), _p(h), _p(identity), N, C, act, float(act_param),
+                                              _p(h_new), _p(x_out), _stream(h))
     return h_new, x_out
 
 
@@ -209,9 +225,8 @@ def gru_gates_bwd(rzn, gh, h, x_out, g_x_out, g_h_carry, act, act_param, want_id
     g_gh = torch.empty_like(rzn)
     g_h_prev = torch.empty_like(h)
     g_id = torch.empty_like(h) if want_identity else None
-    _lib.check(_lib.load().glam_gru_gates_bwd(_p(rzn), _p(gh), _p(h), _p(x_out), _p(g_x_out), _p(g_h_carry), N, C, act,
-                                              float(act_param), _p(g_gi), _p(g_gh), _p(g_h_prev), _p(g_id), _stream(h)),
-               "glam_gru_gates_bwd")
+    _call("glam_gru_gates_bwd", _p(rzn), _p(gh), _p(h), _p(x_out), _p(g_x_out), _p(g_h_carry), N, C, act,
+                                              float(act_param), _p(g_gi), _p(g_gh), _p(g_h_prev), _p(g_id), _stream(h))
     return g_gi, g_gh, g_h_prev, g_id
 
 
@@ -219,8 +234,7 @@ def lstm_gates_fwd(gates, c_prev):
     R, C = c_prev.shape
     c_new = torch.empty_like(c_prev)
     h_new = torch.empty_like(c_prev)
-    _lib.check(_lib.load().glam_lstm_gates_fwd(_p(gates), _p(c_prev), R, C, _p(c_new), _p(h_new), _stream(gates)),
-               "glam_lstm_gates_fwd")
+    _call("glam_lstm_gates_fwd", _p(gates), _p(c_prev), R, C, _p(c_new), _p(h_new), _stream(gates))
     return h_new, c_new
 
 
@@ -228,8 +242,8 @@ def lstm_gates_bwd(gates_act, c_prev, c_new, g_h, g_c):
     R, C = c_prev.shape
     g_gates = torch.empty_like(gates_act)
     g_c_prev = torch.empty_like(c_prev)
-    _lib.check(_lib.load().glam_lstm_gates_bwd(_p(gates_act), _p(c_prev), _p(c_new), _p(g_h), _p(g_c), R, C, _p(g_gates),
-                                               _p(g_c_prev), _stream(gates_act)), "glam_lstm_gates_bwd")
+    _call("glam_lstm_gates_bwd", _p(gates_act), _p(c_prev), _p(c_new), _p(g_h), _p(g_c), R, C, _p(g_gates),
+                                               _p(g_c_prev), _stream(gates_act))
     return g_gates, g_c_prev
 
 
@@ -239,9 +253,8 @@ def seg_attn_pool_fwd(x, q, q_stride, q_bias, gptr, num_graphs, r_out=None):
     a = torch.empty((N,), dtype=torch.float32, device=x.device)
     r = torch.empty((num_graphs, C), dtype=torch.float32, device=x.device) if r_out is None else r_out
     asum = torch.empty((num_graphs,), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().glam_seg_attn_pool_fwd(_p(x), x.stride(0), _p(q), q_stride, _p(q_bias), _p(gptr), num_graphs,
-                                                  C, _p(a), _p(r), r.stride(0), _p(asum), _stream(x)),
-               "glam_seg_attn_pool_fwd")
+    _call("glam_seg_attn_pool_fwd", _p(x), x.stride(0), _p(q), q_stride, _p(q_bias), _p(gptr), num_graphs,
+                                                  C, _p(a), _p(r), r.stride(0), _p(asum), _stream(x))
     return a, r, asum
 
 
@@ -249,9 +262,9 @@ def seg_attn_pool_bwd(x, q, q_stride, a, g_r, g_asum, gptr, num_graphs, g_x, acc
     N, C = x.shape
     g_q = torch.empty((num_graphs, C), dtype=torch.float32, device=x.device)
     g_e = torch.empty((N,), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().glam_seg_attn_pool_bwd(_p(x), x.stride(0), _p(q), q_stride, _p(a), _p(g_r), g_r.stride(0),
+    _call("glam_seg_attn_pool_bwd", _p(x), x.stride(0), _p(q), q_stride, _p(a), _p(g_r), g_r.stride(0),
                                                   _p(g_asum), _p(gptr), num_graphs, C, 1 if accumulate else 0, _p(g_x),
-                                                  g_x.stride(0), _p(g_q), _p(g_e), _stream(x)), "glam_seg_attn_pool_bwd")
+                                                  g_x.stride(0), _p(g_q), _p(g_e), _stream(x))
     return g_q, g_e
 
 
@@ -261,15 +274,14 @@ def pair_dot_pool_fwd(xa, xb, ptr_a, ptr_b, num_pairs):
     argmax = torch.empty((num_pairs, 2), dtype=torch.int32, device=dev)
     sa = torch.empty((num_pairs, C), dtype=torch.float32, device=dev)
     sb = torch.empty((num_pairs, C), dtype=torch.float32, device=dev)
-    _lib.check(_lib.load().glam_pair_dot_pool_fwd(_p(xa), _p(xb), _p(ptr_a), _p(ptr_b), num_pairs, C, _p(out), _p(argmax),
-                                                  _p(sa), _p(sb), _stream(xa)), "glam_pair_dot_pool_fwd")
+    _call("glam_pair_dot_pool_fwd", _p(xa), _p(xb), _p(ptr_a), _p(ptr_b), num_pairs, C, _p(out), _p(argmax),
+                                                  _p(sa), _p(sb), _stream(xa))
     return out, argmax, sa, sb
 
 
 def pair_dot_pool_bwd(xa, xb, ptr_a, ptr_b, g_out, argmax, sa, sb, num_pairs):
     g_xa = torch.empty_like(xa)
     g_xb = torch.empty_like(xb)
-    _lib.check(_lib.load().glam_pair_dot_pool_bwd(_p(xa), _p(xb), _p(ptr_a), _p(ptr_b), _p(g_out), _p(argmax), _p(sa),
-                                                  _p(sb), num_pairs, xa.shape[1], _p(g_xa), _p(g_xb), _stream(xa)),
-               "glam_pair_dot_pool_bwd")
+    _call("glam_pair_dot_pool_bwd", _p(xa), _p(xb), _p(ptr_a), _p(ptr_b), _p(g_out), _p(argmax), _p(sa),
+                                                  _p(sb), num_pairs, xa.shape[1], _p(g_xa), _p(g_xb), _stream(xa))
     return g_xa, g_xb

@@ -60,9 +60,10 @@ def molecule_sizes(rng: np.random.Generator, num_graphs: int, mean_atoms: float 
     return np.clip(n, lo, hi)
 
 
-def _molecule_edges(rng: np.random.Generator, sizes: np.ndarray):
+def _molecule_edges(rng: np.random.Generator, sizes: np.ndarray, n_rings: Optional[int] = None):
     """Undirected bonds: a chain-like random tree (each atom bonds to one of its 3 predecessors, so at
-    most 3 children + 1 parent) plus ring closures (a, a+5|6) on ~8 % of atoms -> ~1.08 n bonds."""
+    most 3 children + 1 parent) plus ring closures (a, a+5|6) on ~8 % of atoms -> ~1.08 n bonds
+    (or exactly `n_rings` closures)."""
     B = sizes.shape[0]
     offs = np.zeros(B + 1, dtype=np.int64)
     np.cumsum(sizes, out=offs[1:])
@@ -76,17 +77,36 @@ def _molecule_edges(rng: np.random.Generator, sizes: np.ndarray):
     parent = offs[gid[child]] + parent_local
     # ring closures
     span = 5 + (rng.random(N) < 0.5).astype(np.int64)
-    can = (local + span < sizes[gid]) & (rng.random(N) < 0.085)
-    ra = np.nonzero(can)[0]
+    fits = local + span < sizes[gid]
+    if n_rings is None:
+        ra = np.nonzero(fits & (rng.random(N) < 0.085))[0]
+    else:                                   # exactly n_rings closures (fixed edge count, e.g. for CUDA-graph replay)
+        cand = np.nonzero(fits)[0]
+        assert 0 <= n_rings <= cand.shape[0], "total_edges not reachable for these molecule sizes"
+        ra = np.sort(rng.choice(cand, size=n_rings, replace=False))
     rb = ra + span[ra]
     a = np.concatenate([child, ra])
     b = np.concatenate([parent, rb])
     return a, b, offs, gid, N
 
 
+def _fit_total(rng: np.random.Generator, sizes: np.ndarray, total: int, lo: int = 4, hi: int = 128) -> np.ndarray:
+    """Nudge random molecules by +-1 atom until the batch has exactly `total` atoms."""
+    sizes = sizes.copy()
+    diff = int(total - sizes.sum())
+    while diff != 0:
+        step = 1 if diff > 0 else -1
+        ok = np.nonzero((sizes + step >= lo) & (sizes + step <= hi))[0]
+        pick = rng.choice(ok, size=min(abs(diff), ok.shape[0]), replace=False)
+        sizes[pick] += step
+        diff = int(total - sizes.sum())
+    return sizes
+
+
 def make_molecule_batch(num_graphs: int, node_dim: int = 9, edge_dim: int = 3, seed: int = 1234,
                         features: str = "chem", sizes: Optional[np.ndarray] = None,
-                        targets: str = "regression") -> GraphBatch:
+                        targets: str = "regression", total_nodes: Optional[int] = None,
+                        total_edges: Optional[int] = None) -> GraphBatch:
     """One PyG-shaped batch of `num_graphs` synthetic molecules.
 
     features="chem": one-hot atom-type block + small non-negative integer columns (like
@@ -96,7 +116,13 @@ def make_molecule_batch(num_graphs: int, node_dim: int = 9, edge_dim: int = 3, s
     if sizes is None:
         sizes = molecule_sizes(rng, num_graphs)
     sizes = np.asarray(sizes, dtype=np.int64)
-    a, b, offs, gid, N = _molecule_edges(rng, sizes)
+    if total_nodes is not None:
+        sizes = _fit_total(rng, sizes, total_nodes)
+    n_rings = None
+    if total_edges is not None:
+        assert total_edges % 2 == 0
+        n_rings = total_edges // 2 - int(sizes.sum() - num_graphs)
+    a, b, offs, gid, N = _molecule_edges(rng, sizes, n_rings)
     bond_type = rng.choice(edge_dim, size=a.shape[0], p=_bond_probs(edge_dim))
     src = np.concatenate([a, b])
     dst = np.concatenate([b, a])
