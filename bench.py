@@ -171,12 +171,12 @@ def kernel_bytes_model(label, N, E, B, C=36, H=3, De=3):
         return 4 * (N * ld + N * HC + E * De + 2 * E * H + N * H) + 4 * (E + N + 1)
     if label.startswith("glam_triplet_edge_bwd_src"):
         return 4 * (N * HC + N * ld + E * De + 2 * E * H) + 4 * (3 * E + N + 1)
-    if label.startswith("glam_gemm_tn"):
+    if label.startswith("glam_gemm_tn"):  # incl. glam_gemm_tn_ex
         import re
         m = re.search(r"M=(\d+),Ka=(\d+),Kb=(\d+)", label)
         M, Ka, Kb = map(int, m.groups())
         return 4 * (M * Ka + M * Kb + Ka * Kb)
-    if label.startswith("glam_gemm["):
+    if label.startswith("glam_gemm_ex["):
         import re
         m = re.search(r"M=(\d+),N=(\d+),K=(\d+),\w+,epi=(\d)", label)
         M, Nn, K, epi = map(int, m.groups())

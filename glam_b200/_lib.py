@@ -21,13 +21,18 @@ SIGNATURES = {
     "glam_abi_version": (I32, []),
     "glam_last_error": (C.c_char_p, []),
     "glam_launch_count": (I64, []),
+    "glam_set_math_mode": (I32, [I32]),
+    "glam_get_math_mode": (I32, []),
     "glam_csr_workspace_bytes": (SZ, [I64, I64]),
     "glam_build_csr": (I32, [P, I64, I64, P, P, P, P, P, P, P, SZ, P]),
     "glam_graph_ptr": (I32, [P, I64, I64, P, P]),
     "glam_gather_rows": (I32, [P, P, I64, I64, P, P]),
     "glam_gemm": (I32, [P, I64, P, I64, I64, P, P, I64, P, I64, I64, I64, I64, I32, P]),
+    "glam_gemm_ex": (I32, [P, I64, P, I64, I64, P, P, I64, P, I64, I64, I64, I64, I32, I32, I32, P]),
     "glam_gemm_tn_workspace_bytes": (SZ, [I64, I64, I64]),
     "glam_gemm_tn": (I32, [P, I64, P, I64, I64, I64, I64, P, I64, P, SZ, P]),
+    "glam_gemm_tn_ex_workspace_bytes": (SZ, [I64, I64, I64, I32]),
+    "glam_gemm_tn_ex": (I32, [P, I64, P, I64, I64, I64, I64, P, I64, I32, P, P, SZ, P]),
     "glam_colsum_workspace_bytes": (SZ, [I64, I64]),
     "glam_colsum": (I32, [P, I64, I64, I64, P, P, SZ, P]),
     "glam_triplet_edge_fwd": (I32, [P, I64, P, P, P, P, P, I64, I64, I32, I32, I32, F32, P, P, P]),
@@ -71,6 +76,9 @@ def load() -> C.CDLL:
     if got != ABI_VERSION:
         raise GlamError(f"libglam_b200.so ABI {got} != expected {ABI_VERSION}: rebuild")
     _lib = lib
+    env = os.environ.get("GLAM_B200_MATH")
+    if env:
+        check(lib.glam_set_math_mode({"fp32": 0, "tf32": 1}[env.lower()]), "glam_set_math_mode")
     return lib
 
 
@@ -78,6 +86,16 @@ def check(status: int, what: str) -> None:
     if status != 0:
         msg = load().glam_last_error().decode(errors="replace")
         raise GlamError(f"{what} failed (status {status}): {msg}")
+
+
+def set_math_mode(mode) -> None:
+    """'tf32' / 1: projections on the tcgen05 tensor cores (default); 'fp32' / 0: exact fp32 on the CUDA cores."""
+    code = {"fp32": 0, "tf32": 1}.get(mode, mode)
+    check(load().glam_set_math_mode(int(code)), "glam_set_math_mode")
+
+
+def get_math_mode() -> str:
+    return "tf32" if load().glam_get_math_mode() == 1 else "fp32"
 
 
 def launch_count() -> int:

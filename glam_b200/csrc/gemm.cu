@@ -7,6 +7,16 @@
 
 namespace glam {
 
+bool tc_gemm_eligible(const float* X, int64_t ldx, const float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K);
+int tc_gemm_launch(const float* X, int64_t ldx, const float* W, int64_t w_sk, int64_t w_sn, const float* bias,
+                   const float* aux, int64_t ldaux, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K, int epi,
+                   int exact_begin, int exact_end, cudaStream_t stream);
+
+bool tc_gemm_tn_eligible(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Kb, int want_colsum);
+size_t tc_gemm_tn_workspace(int64_t M, int64_t Ka, int64_t Kb, int want_colsum);
+int tc_gemm_tn_launch(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Kb, float* out,
+                      int64_t ldo, int transpose_out, float* colsum_b, void* workspace, cudaStream_t stream);
+
 constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
 constexpr int kGemmThreads = (BM / TM) * (BN / TN);  // 256
 
@@ -139,12 +149,12 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
 
 // out[r*ldo + c] = sum_{s<S} partial[s][r*cols + c], s ascending (fixed order => reproducible)
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int S, int64_t rows, int cols, float* __restrict__ out,
-                                       int64_t ldo) {
+                                       int64_t ldo, int transpose_out = 0) {
     int64_t total = rows * cols;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         float s = 0.f;
         for (int k = 0; k < S; ++k) s += partial[(int64_t)k * total + i];
-        out[(i / cols) * ldo + (i % cols)] = s;
+        if (transpose_out) out[(i % cols) * ldo + (i / cols)] = s; else out[(i / cols) * ldo + (i % cols)] = s;
     }
 }
 
@@ -172,6 +182,81 @@ __global__ void colsum_partial_kernel(const float* __restrict__ G, int64_t ldg, 
     }
 }
 
+// Skinny weight gradients in exact fp32: out[Wp, Wq] = sum_m P[m, Wp] * Q[m, Wq] with Wq <= 8 (attention-logit
+// columns s_i/s_j, edge-attention weights).  These sums cancel almost completely (softmax gradients are zero-sum per
+// destination), so they are kept out of the TF32 path; they are also far too narrow for a tensor-core tile.
+// One warp per row (lanes over the wide operand's features), 8 warps x S CTAs, fixed-order reductions.
+constexpr int kSkinnyWarps = 8;
+template <int KPL>
+__global__ void __launch_bounds__(kSkinnyWarps * 32)
+skinny_tn_kernel(const float* __restrict__ P, int64_t ldp, int Wp, const float* __restrict__ Q, int64_t ldq, int Wq, int64_t M,
+                 int64_t rows_per_cta, float* __restrict__ partial) {
+    extern __shared__ float red[];                     // [kSkinnyWarps][Wp][8]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t mbeg = (int64_t)blockIdx.x * rows_per_cta;
+    int64_t mend = mbeg + rows_per_cta;
+    if (mend > M) mend = M;
+    float acc[KPL][8];
+#pragma unroll
+    for (int t = 0; t < KPL; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+    for (int64_t m = mbeg + warp; m < mend; m += kSkinnyWarps) {
+        float q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[j] = j < Wq ? Q[m * ldq + j] : 0.f;
+#pragma unroll
+        for (int t = 0; t < KPL; ++t) {
+            const int f = lane + 32 * t;
+            const float a = f < Wp ? P[m * ldp + f] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(a, q[j], acc[t][j]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < KPL; ++t) {
+        const int f = lane + 32 * t;
+        if (f < Wp)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) red[((size_t)warp * Wp + f) * 8 + j] = acc[t][j];
+    }
+    __syncthreads();
+    float* out = partial + (int64_t)blockIdx.x * Wp * Wq;
+    for (int idx = threadIdx.x; idx < Wp * Wq; idx += blockDim.x) {
+        const int f = idx / Wq, j = idx - f * Wq;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kSkinnyWarps; ++w) v += red[((size_t)w * Wp + f) * 8 + j];
+        out[idx] = v;
+    }
+}
+
+// out[r, c] (or transposed) = sum_s partial[s][r*cols + c]; 4 thread rows split S, combined in a fixed order
+__global__ void __launch_bounds__(256)
+reduce4_kernel(const float* __restrict__ partial, int S, int rows, int cols, float* __restrict__ out, int64_t ldo, int transpose_out) {
+    __shared__ float red4[4][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int total = rows * cols, i = blockIdx.x * 64 + tx;
+    float s = 0.f;
+    if (i < total) {
+        const int per = (S + 3) / 4, k0 = ty * per, k1 = min(S, k0 + per);
+        for (int k = k0; k < k1; ++k) s += partial[(int64_t)k * total + i];
+    }
+    red4[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < total) {
+        const float v = ((red4[0][tx] + red4[1][tx]) + red4[2][tx]) + red4[3][tx];
+        const int r = i / cols, c = i - r * cols;
+        if (transpose_out) out[(int64_t)c * ldo + r] = v; else out[(int64_t)r * ldo + c] = v;
+    }
+}
+
+static int skinny_grid(int64_t M) {
+    int64_t g = (M + 511) / 512;
+    if (g > 2 * kNumSMs) g = 2 * kNumSMs;
+    return (int)(g < 1 ? 1 : g);
+}
+
 static int tn_splits(int64_t M, int64_t Ka, int64_t Kb) {
     int64_t tiles = ((Ka + BM - 1) / BM) * ((Kb + BN - 1) / BN);
     int64_t s = (2 * kNumSMs + tiles - 1) / tiles;
@@ -191,9 +276,19 @@ static int colsum_splits(int64_t M) {
 
 using namespace glam;
 
+extern "C" int glam_gemm_ex(const float* X, int64_t ldx, const float* W, int64_t w_sk, int64_t w_sn, const float* bias,
+                            const float* aux, int64_t ldaux, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K,
+                            int epilogue, int exact_col_begin, int exact_col_end, void* stream_);
+
 extern "C" int glam_gemm(const float* X, int64_t ldx, const float* W, int64_t w_sk, int64_t w_sn, const float* bias,
                          const float* aux, int64_t ldaux, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K,
                          int epilogue, void* stream_) {
+    return glam_gemm_ex(X, ldx, W, w_sk, w_sn, bias, aux, ldaux, Y, ldy, M, N, K, epilogue, 0, 0, stream_);
+}
+
+extern "C" int glam_gemm_ex(const float* X, int64_t ldx, const float* W, int64_t w_sk, int64_t w_sn, const float* bias,
+                            const float* aux, int64_t ldaux, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K,
+                            int epilogue, int exact_col_begin, int exact_col_end, void* stream_) {
     GLAM_REQUIRE(M >= 0 && N > 0 && K > 0, "glam_gemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
     if (M == 0) return 0;
     GLAM_REQUIRE(X && W && Y, "glam_gemm: null pointer");
@@ -201,6 +296,10 @@ extern "C" int glam_gemm(const float* X, int64_t ldx, const float* W, int64_t w_
     GLAM_REQUIRE(epilogue >= 0 && epilogue <= 3, "glam_gemm: unknown epilogue %d", epilogue);
     GLAM_REQUIRE(epilogue != EPI_MUL_CELU_GRAD || (aux && ldaux >= N), "glam_gemm: epilogue 2 needs aux");
     GLAM_REQUIRE(N <= 65535 * BN && K < (1 << 30), "glam_gemm: N/K too large");
+    GLAM_REQUIRE(exact_col_begin >= 0 && exact_col_begin <= exact_col_end && exact_col_end <= N, "glam_gemm_ex: bad exact column range");
+    if (tc_gemm_eligible(X, ldx, Y, ldy, M, N, K))
+        return tc_gemm_launch(X, ldx, W, w_sk, w_sn, bias, aux, ldaux, Y, ldy, M, N, K, epilogue, exact_col_begin,
+                              exact_col_end, (cudaStream_t)stream_);
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
     gemm_kernel<<<grid, kGemmThreads, 0, (cudaStream_t)stream_>>>(X, ldx, W, w_sk, w_sn, bias, aux, ldaux, Y, ldy, M, (int)N,
                                                                  (int)K, epilogue);
@@ -256,5 +355,76 @@ extern "C" int glam_colsum(const float* G, int64_t ldg, int64_t M, int64_t N, fl
     GLAM_CHECK_LAUNCH();
     reduce_partials_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>((const float*)workspace, S, 1, (int)N, out, N);
     GLAM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" size_t glam_gemm_tn_ex_workspace_bytes(int64_t M, int64_t Ka, int64_t Kb, int want_colsum) {
+    size_t a = glam_gemm_tn_workspace_bytes(M, Ka, Kb), b = want_colsum ? glam_colsum_workspace_bytes(M, Kb) : 0;
+    size_t c = tc_gemm_tn_workspace(M, Ka, Kb, want_colsum);
+    size_t d = sizeof(float) * (size_t)skinny_grid(M) * (size_t)Ka * (size_t)Kb;
+    size_t m = a > b ? a : b;
+    m = m > c ? m : c;
+    return m > d ? m : d;
+}
+
+extern "C" int glam_gemm_tn_ex(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Kb,
+                               float* out, int64_t ldo, int transpose_out, float* colsum_b, void* workspace,
+                               size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GLAM_REQUIRE(M >= 0 && Ka > 0 && Kb > 0 && out && ldo >= (transpose_out ? Ka : Kb), "glam_gemm_tn_ex: bad arguments");
+    GLAM_REQUIRE(Ka < 65536 && Kb < 65536, "glam_gemm_tn_ex: Ka/Kb too large");
+    if (M == 0) {
+        if (transpose_out) cudaMemset2DAsync(out, ldo * sizeof(float), 0, Ka * sizeof(float), Kb, stream);
+        else cudaMemset2DAsync(out, ldo * sizeof(float), 0, Kb * sizeof(float), Ka, stream);
+        if (colsum_b) cudaMemsetAsync(colsum_b, 0, sizeof(float) * Kb, stream);
+        return 0;
+    }
+    GLAM_REQUIRE(A && B && lda >= Ka && ldb >= Kb, "glam_gemm_tn_ex: bad inputs");
+    GLAM_REQUIRE(workspace && workspace_bytes >= glam_gemm_tn_ex_workspace_bytes(M, Ka, Kb, colsum_b != nullptr),
+                 "glam_gemm_tn_ex: workspace too small");
+    if (!colsum_b && (Ka <= 8 || Kb <= 8) && Ka <= 288 && Kb <= 288) {
+        // skinny product: exact fp32, result partial is [Wp][Wq] with the wide operand first
+        const bool a_wide = Kb <= 8;
+        const float* P = a_wide ? A : B; const float* Q = a_wide ? B : A;
+        const int64_t ldp = a_wide ? lda : ldb, ldq = a_wide ? ldb : lda;
+        const int Wp = (int)(a_wide ? Ka : Kb), Wq = (int)(a_wide ? Kb : Ka);
+        const int S = skinny_grid(M);
+        const int64_t rpc = (M + S - 1) / S;
+        const size_t smem = sizeof(float) * kSkinnyWarps * Wp * 8;
+        const int kpl = (Wp + 31) / 32;
+        auto launch = [&](auto fn) {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            fn<<<S, kSkinnyWarps * 32, smem, stream>>>(P, ldp, Wp, Q, ldq, Wq, M, rpc, (float*)workspace);
+        };
+        if (kpl <= 2) launch(skinny_tn_kernel<2>); else if (kpl <= 4) launch(skinny_tn_kernel<4>);
+        else if (kpl <= 6) launch(skinny_tn_kernel<6>); else launch(skinny_tn_kernel<9>);
+        GLAM_CHECK_LAUNCH();
+        // partial holds [Wp][Wq]; out is [Ka][Kb]: transposed w.r.t. the partial exactly when A is the narrow operand
+        const int tr = (a_wide ? 0 : 1) ^ (transpose_out ? 1 : 0);
+        reduce4_kernel<<<(Wp * Wq + 63) / 64, 256, 0, stream>>>((const float*)workspace, S, Wp, Wq, out, ldo, tr);
+        GLAM_CHECK_LAUNCH();
+        return 0;
+    }
+    if (tc_gemm_tn_eligible(A, lda, B, ldb, M, Ka, Kb, colsum_b != nullptr))
+        return tc_gemm_tn_launch(A, lda, B, ldb, M, Ka, Kb, out, ldo, transpose_out, colsum_b, workspace, stream);
+    const int S = tn_splits(M, Ka, Kb);
+    const int tiles_a = (int)((Ka + BM - 1) / BM), tiles_b = (int)((Kb + BN - 1) / BN);
+    int64_t rps = (M + S - 1) / S;
+    rps = (rps + BK - 1) / BK * BK;
+    gemm_tn_kernel<<<dim3(tiles_a * tiles_b, S), kGemmThreads, 0, stream>>>(A, lda, B, ldb, M, (int)Ka, (int)Kb, tiles_b, rps,
+                                                                          (float*)workspace);
+    GLAM_CHECK_LAUNCH();
+    int64_t total = Ka * Kb;
+    reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const float*)workspace, S, Ka, (int)Kb, out, ldo,
+                                                                               transpose_out);
+    GLAM_CHECK_LAUNCH();
+    if (colsum_b) {
+        const int S2 = colsum_splits(M);
+        int64_t rps2 = (M + S2 - 1) / S2;
+        colsum_partial_kernel<<<S2, dim3(32, 8), 0, stream>>>(B, ldb, M, (int)Kb, rps2, (float*)workspace);
+        GLAM_CHECK_LAUNCH();
+        reduce_partials_kernel<<<(unsigned)((Kb + 255) / 256), 256, 0, stream>>>((const float*)workspace, S2, 1, (int)Kb, colsum_b, Kb);
+        GLAM_CHECK_LAUNCH();
+    }
     return 0;
 }

@@ -20,7 +20,8 @@ def _c(t):
 # shared forward/backward pieces
 # --------------------------------------------------------------------------------------------------
 def _conv_fwd(x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels, slope, epilogue):
-    xpe = ops.gemm(x, w_ext)                                                   # [N, ldxp]: xp | s_i | s_j | 0
+    hc = heads * channels                                                      # [N, ldxp]: xp | s_i | s_j | 0
+    xpe = ops.gemm(x, w_ext, exact_cols=(hc, hc + 2 * heads))                  # logit columns always exact fp32
     agg, alpha = ops.triplet_edge_fwd(xpe, ea, w_edge, att_edge, g, heads, channels, slope)
     out = agg if w_scale is None else ops.gemm(agg, w_scale, bias=bias, epilogue=epilogue)
     return xpe, agg, alpha, out
@@ -30,14 +31,16 @@ def _conv_bwd(g_pre, x, w_ext, w_edge, att_edge, w_scale, xpe, agg, alpha, ea, g
     """g_pre: gradient w.r.t. the layer output before any activation ([N,C], or [N,HC] for the Light layer)."""
     if w_scale is not None:
         g_agg = ops.gemm(g_pre, w_scale, transpose_w=True)                     # [N,HC]
-        g_w_scale = ops.gemm_tn(agg, g_pre)
-        g_bias = ops.colsum(g_pre)
+        g_w_scale, g_bias = ops.gemm_tn_ex(agg, g_pre, want_colsum=True)
     else:
         g_agg, g_w_scale, g_bias = g_pre, None, None
     g_xpe, g_logit, g_w_edge = ops.triplet_edge_bwd(xpe, ea, w_edge, att_edge, alpha, g_agg, g, heads, channels, slope)
-    g_att_edge = ops.gemm_tn(ea, g_logit)                                      # [De,H]
+    g_att_edge, _ = ops.gemm_tn_ex(ea, g_logit)                                # [De,H]
     g_x = ops.gemm(g_xpe, w_ext, transpose_w=True)                             # [N,C]
-    g_w_ext = ops.gemm_tn(x, g_xpe)                                            # [C,ldxp]
+    g_w_ext, _ = ops.gemm_tn_ex(x, g_xpe)                                      # [C,ldxp]
+    # the 2H logit columns are near-total cancellations (softmax gradients are zero-sum per destination): exact fp32
+    hc = heads * channels
+    ops.gemm_tn_ex(x, g_xpe[:, hc:hc + 2 * heads], out=g_w_ext[:, hc:hc + 2 * heads])
     return g_x, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias
 
 
@@ -55,9 +58,9 @@ def _gru_bwd(g_x_out, g_h_new, rzn, gh, h, m, x_out, w_ih, w_hh, act, act_param,
     else:
         g_m = ops.gemm(g_gi, w_ih)
     ops.gemm(g_gh, w_hh, epilogue=EPI_ACCUM, out=g_h_prev)
-    g_w_ih = ops.gemm_tn(g_gi, m)
-    g_w_hh = ops.gemm_tn(g_gh, h)
-    return g_m, g_h_prev, g_id, g_w_ih, g_w_hh, ops.colsum(g_gi), ops.colsum(g_gh)
+    g_w_ih, g_b_ih = ops.gemm_tn_ex(m, g_gi, transpose_out=True, want_colsum=True)     # (m^T g_gi)^T = [3C,C]
+    g_w_hh, g_b_hh = ops.gemm_tn_ex(h, g_gh, transpose_out=True, want_colsum=True)
+    return g_m, g_h_prev, g_id, g_w_ih, g_w_hh, g_b_ih, g_b_hh
 
 
 # --------------------------------------------------------------------------------------------------
@@ -153,7 +156,8 @@ class LinearFn(Function):
     def backward(ctx, g_y):
         x, weight = ctx.saved_tensors
         g_y = _c(g_y)
-        return ops.gemm(g_y, weight), ops.gemm_tn(g_y, x), (ops.colsum(g_y) if ctx.has_bias else None)
+        g_w, g_b = ops.gemm_tn_ex(x, g_y, transpose_out=True, want_colsum=ctx.has_bias)       # (x^T g_y)^T = [N,K]
+        return ops.gemm(g_y, weight), g_w, g_b
 
 
 class LSTMGatesFn(Function):

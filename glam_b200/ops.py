@@ -104,7 +104,7 @@ def gather_rows(src: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------ GEMMs
 def gemm(X: torch.Tensor, W: torch.Tensor, transpose_w: bool = False, bias: Optional[torch.Tensor] = None,
          epilogue: int = EPI_NONE, aux: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-         ldy: Optional[int] = None) -> torch.Tensor:
+         ldy: Optional[int] = None, exact_cols=(0, 0)) -> torch.Tensor:
     """Y = epilogue(X @ W + bias) (W is [K,N]) or X @ W.T (W is [N,K], transpose_w=True).
     X may be a row-strided 2-D view (stride(1) == 1)."""
     _need_cuda(X, W)
@@ -123,8 +123,8 @@ def gemm(X: torch.Tensor, W: torch.Tensor, transpose_w: bool = False, bias: Opti
     ld = out.stride(0)
     if aux is not None:
         assert aux.stride(1) == 1
-    _call("glam_gemm", _p(X), X.stride(0), _p(W), w_sk, w_sn, _p(bias), _p(aux),
-                                     0 if aux is None else aux.stride(0), _p(out), ld, M, N, K, epilogue, _stream(X),
+    _call("glam_gemm_ex", _p(X), X.stride(0), _p(W), w_sk, w_sn, _p(bias), _p(aux),
+          0 if aux is None else aux.stride(0), _p(out), ld, M, N, K, epilogue, int(exact_cols[0]), int(exact_cols[1]), _stream(X),
           label=f"[M={M},N={N},K={K},{'nt' if transpose_w else 'nn'},epi={epilogue}]")
     return out
 
@@ -141,6 +141,25 @@ def gemm_tn(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     _call("glam_gemm_tn", _p(A), A.stride(0), _p(B), B.stride(0), M, Ka, Kb, _p(out), Kb, _p(ws), ws.numel(),
           _stream(A), label=f"[M={M},Ka={Ka},Kb={Kb}]")
     return out
+
+
+def gemm_tn_ex(A: torch.Tensor, B: torch.Tensor, transpose_out: bool = False, want_colsum: bool = False,
+               out: Optional[torch.Tensor] = None):
+    """(A^T @ B  [Ka,Kb] — or its transpose [Kb,Ka] —, colsum(B) [Kb] | None), reduction over the long row
+    dimension in a fixed order; tensor cores in TF32 mode."""
+    _need_cuda(A, B)
+    assert A.dim() == 2 and B.dim() == 2 and A.shape[0] == B.shape[0] and A.stride(1) == 1 and B.stride(1) == 1
+    M, Ka = A.shape
+    Kb = B.shape[1]
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((Kb, Ka) if transpose_out else (Ka, Kb), dtype=torch.float32, device=A.device)
+    assert out.stride(1) == 1 and tuple(out.shape) == ((Kb, Ka) if transpose_out else (Ka, Kb))
+    cs = torch.empty((Kb,), dtype=torch.float32, device=A.device) if want_colsum else None
+    ws = _ws(lib.glam_gemm_tn_ex_workspace_bytes(M, Ka, Kb, 1 if want_colsum else 0), A.device)
+    _call("glam_gemm_tn_ex", _p(A), A.stride(0), _p(B), B.stride(0), M, Ka, Kb, _p(out), out.stride(0),
+          1 if transpose_out else 0, _p(cs), _p(ws), ws.numel(), _stream(A), label=f"[M={M},Ka={Ka},Kb={Kb}]")
+    return out, cs
 
 
 def colsum(G: torch.Tensor) -> torch.Tensor:

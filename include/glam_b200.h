@@ -36,6 +36,11 @@ int glam_abi_version(void);
 const char* glam_last_error(void);
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 int64_t glam_launch_count(void);
+/* Arithmetic of the dense projections: 1 (default) = TF32 operands on the tcgen05 tensor cores with fp32
+ * accumulation (what torch 1.10, the reference's pinned version, does by default for fp32 matmul on Ampere+);
+ * 0 = exact fp32 FMAs on the CUDA cores.  Everything else (softmax, gates, reductions) is always fp32. */
+int glam_set_math_mode(int mode);
+int glam_get_math_mode(void);
 
 /* ---------------------------------------------------------------------------------------------
  * (1) Destination-sorted CSR builder.
@@ -71,11 +76,25 @@ int glam_gather_rows(const float* in, const int32_t* perm, int64_t rows, int64_t
 int glam_gemm(const float* X, int64_t ldx, const float* W, int64_t w_sk, int64_t w_sn, const float* bias,
               const float* aux, int64_t ldaux, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K,
               int epilogue, void* stream);
+/* Same, with output columns [exact_col_begin, exact_col_end) always computed with exact fp32 FMAs even in TF32 math
+ * mode: the attention-logit columns s_i | s_j of the extended node projection feed a softmax whose gradients are
+ * zero-sum per destination, so operand rounding there is amplified in the attention-vector gradient. */
+int glam_gemm_ex(const float* X, int64_t ldx, const float* W, int64_t w_sk, int64_t w_sn, const float* bias,
+                 const float* aux, int64_t ldaux, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K,
+                 int epilogue, int exact_col_begin, int exact_col_end, void* stream);
 /* Weight gradients: out[Ka,Kb] = sum_m A[m,Ka] * B[m,Kb]; fixed-order two-stage reduction.
  * workspace >= glam_gemm_tn_workspace_bytes(M, Ka, Kb). */
 size_t glam_gemm_tn_workspace_bytes(int64_t M, int64_t Ka, int64_t Kb);
 int glam_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Kb,
                  float* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream);
+/* Same contraction with the bias gradient folded in: out = A^T B (written transposed when transpose_out != 0, i.e.
+ * directly in torch.nn.GRU's [3C,C] weight layout) and, when colsum_b != NULL, colsum_b[Kb] = sum_m B[m,:].  In TF32
+ * math mode this runs on the tensor cores (rows are the MMA K dimension, operands MN-major) and the column sums come
+ * from a constant-1 feature appended to A; otherwise it is the exact fp32 path.  Deterministic either way. */
+size_t glam_gemm_tn_ex_workspace_bytes(int64_t M, int64_t Ka, int64_t Kb, int want_colsum);
+int glam_gemm_tn_ex(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Kb,
+                    float* out, int64_t ldo, int transpose_out, float* colsum_b, void* workspace, size_t workspace_bytes,
+                    void* stream);
 /* Bias gradients: out[n] = sum_m G[m,n]; fixed order. workspace >= glam_colsum_workspace_bytes(M, N). */
 size_t glam_colsum_workspace_bytes(int64_t M, int64_t N);
 int glam_colsum(const float* G, int64_t ldg, int64_t M, int64_t N, float* out, void* workspace,

@@ -25,6 +25,25 @@ from torch import nn
 
 Tensor = torch.Tensor
 
+# Optional operand pre-processing for every dense projection (tests use it to emulate TF32 tensor-core
+# operands: fp32 words with the 13 low mantissa bits ignored).  None = exact.
+MM_OPERAND_HOOK = None
+
+
+def tf32_truncate(t: Tensor) -> Tensor:
+    """Value of `t` as a TF32 tensor-core operand (straight-through for autograd)."""
+    if t.dtype == torch.float32:
+        q = (t.detach().contiguous().view(torch.int32) & -8192).view(torch.float32)
+    else:
+        q = (t.detach().float().contiguous().view(torch.int32) & -8192).view(torch.float32).to(t.dtype)
+    return t + (q - t).detach()
+
+
+def _mm(a: Tensor, b: Tensor) -> Tensor:
+    if MM_OPERAND_HOOK is not None:
+        a, b = MM_OPERAND_HOOK(a), MM_OPERAND_HOOK(b)
+    return a @ b
+
 
 # --------------------------------------------------------------------------------------------------
 # third-party primitives (torch_scatter / torch_geometric.utils @1.7.2)
@@ -59,8 +78,8 @@ def triplet_message(x, edge_index, edge_attr, weight_node, weight_edge, weight_t
     """TripletMessage.forward/message/update — src_1gp/layer.py:36-61 (+ PyG propagate: x_j =
     x[edge_index[0]], x_i = x[edge_index[1]], scatter-add over edge_index[1])."""
     N, C = x.shape[0], weight_node.shape[0]
-    xp = x @ weight_node                                    # :37
-    ep = edge_attr @ weight_edge                            # :38
+    xp = _mm(x, weight_node)                                # :37
+    ep = edge_attr @ weight_edge                            # :38 (K = De: not a tensor-core contraction)
     src, dst = edge_index[0], edge_index[1]
     x_j = xp.index_select(0, src).view(-1, heads, C)        # :44
     x_i = xp.index_select(0, dst).view(-1, heads, C)        # :45
@@ -71,7 +90,7 @@ def triplet_message(x, edge_index, edge_attr, weight_node, weight_edge, weight_t
     alpha = seg_softmax(alpha, dst, N)                      # :51
     msg = alpha.view(-1, heads, 1) * e_ij * x_j             # :55
     agg = seg_sum(msg, dst, N).view(N, heads * C)           # aggr='add', node_dim=0 (:17), :58
-    out = agg @ weight_scale + bias                         # :59-60
+    out = _mm(agg, weight_scale) + bias                     # :59-60
     return (out, alpha) if return_alpha else out
 
 
@@ -79,7 +98,7 @@ def triplet_message_light(x, edge_index, edge_attr, weight_node, weight_triplet_
                           negative_slope: float = 0.2):
     """TripletMessageLight — src_1gp/layer.py:83-101 (single head, raw edge_attr in the logit only)."""
     N = x.shape[0]
-    xp = x @ weight_node                                    # :84
+    xp = _mm(x, weight_node)                                # :84
     src, dst = edge_index[0], edge_index[1]
     x_j, x_i = xp.index_select(0, src), xp.index_select(0, dst)
     triplet = torch.cat([x_i, edge_attr, x_j], dim=-1)      # :92
@@ -91,8 +110,8 @@ def triplet_message_light(x, edge_index, edge_attr, weight_node, weight_triplet_
 
 def gru_cell(m, h, weight_ih, weight_hh, bias_ih, bias_hh):
     """torch.nn.GRU, one layer, seq_len 1 (src_1gp/layer.py:247,262); gate order r, z, n."""
-    gi = m @ weight_ih.t() + bias_ih
-    gh = h @ weight_hh.t() + bias_hh
+    gi = _mm(m, weight_ih.t()) + bias_ih
+    gh = _mm(h, weight_hh.t()) + bias_hh
     i_r, i_z, i_n = gi.chunk(3, dim=1)
     h_r, h_z, h_n = gh.chunk(3, dim=1)
     r = torch.sigmoid(i_r + h_r)
@@ -123,7 +142,7 @@ def global_attention(x, batch, num_graphs, gate_w, gate_b, nn_w, nn_b):
 
 def lstm_cell(inp, h, c, weight_ih, weight_hh, bias_ih, bias_hh):
     """torch.nn.LSTM one layer, one step; gate order i, f, g, o."""
-    g = inp @ weight_ih.t() + bias_ih + h @ weight_hh.t() + bias_hh
+    g = _mm(inp, weight_ih.t()) + bias_ih + _mm(h, weight_hh.t()) + bias_hh
     i, f, gg, o = g.chunk(4, dim=1)
     c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
     return torch.sigmoid(o) * torch.tanh(c2), c2

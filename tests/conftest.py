@@ -32,3 +32,15 @@ def golden_layers():
 def golden_models():
     import torch
     return torch.load(os.path.join(ROOT, "tests", "golden", "models.pt"))
+
+
+@pytest.fixture(params=["fp32", "tf32"])
+def math_mode(request):
+    """Runs a GPU test once with exact-fp32 projections and once with the TF32 tensor-core projections."""
+    import helpers
+    from glam_b200 import _lib
+    _lib.set_math_mode(request.param)
+    helpers.MATH_MODE["mode"] = request.param
+    yield request.param
+    _lib.set_math_mode("tf32")
+    helpers.MATH_MODE["mode"] = "fp32"

@@ -9,7 +9,7 @@ import copy
 import pytest
 import torch
 
-from helpers import case, ns, tol_check
+from helpers import case, ns, tol_check, tf32_emulated
 
 pytestmark = pytest.mark.gpu
 
@@ -84,7 +84,7 @@ def test_graph_ptr_and_gather():
 
 # ---------------------------------------------------------------------------------------------- dense pieces
 @pytest.mark.parametrize("M,N,K", [(1, 1, 1), (63, 36, 36), (1000, 116, 36), (777, 60, 180), (4096, 188, 60), (130, 270, 90)])
-def test_gemm_variants(M, N, K):
+def test_gemm_variants(M, N, K, math_mode):
     from glam_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
     X, W, b = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g), torch.randn(N, generator=g)
@@ -107,20 +107,33 @@ def test_gemm_variants(M, N, K):
     A, B = torch.randn(M, K, generator=g), torch.randn(M, N, generator=g)
     tol_check(ops.gemm_tn(A.to(DEV), B.to(DEV)).cpu(), A.t() @ B, A.double().t() @ B.double(), "gemm_tn")
     tol_check(ops.colsum(B.to(DEV)).cpu(), B.sum(0), B.double().sum(0), "colsum")
+    for tr in (False, True):
+        for cs in (False, True):
+            o, c = ops.gemm_tn_ex(A.to(DEV), B.to(DEV), transpose_out=tr, want_colsum=cs)
+            r32, r64 = A.t() @ B, A.double().t() @ B.double()
+            tol_check(o.cpu(), r32.t() if tr else r32, r64.t() if tr else r64, f"gemm_tn_ex tr={tr} cs={cs}")
+            if cs:
+                tol_check(c.cpu(), B.sum(0), B.double().sum(0), "gemm_tn_ex colsum")
 
 
-def test_gemm_tn_long_and_deterministic():
+def test_gemm_tn_long_and_deterministic(math_mode):
     from glam_b200 import ops
     g = torch.Generator().manual_seed(3)
     A, B = torch.randn(100_003, 36, generator=g).to(DEV), torch.randn(100_003, 116, generator=g).to(DEV)
     o1, o2 = ops.gemm_tn(A, B), ops.gemm_tn(A, B)
     assert torch.equal(o1, o2)
     tol_check(o1.cpu(), (A.t() @ B).cpu(), (A.double().t() @ B.double()).cpu(), "gemm_tn long", rtol=1e-4)
+    for (ka, kb) in [(36, 116), (108, 36), (180, 60), (60, 188), (3, 3)]:
+        A, B = torch.randn(50_001, ka, generator=g).to(DEV), torch.randn(50_001, kb, generator=g).to(DEV)
+        (o1, c1), (o2, c2) = ops.gemm_tn_ex(A, B, want_colsum=True), ops.gemm_tn_ex(A, B, want_colsum=True)
+        assert torch.equal(o1, o2) and torch.equal(c1, c2)                    # bitwise reproducible
+        tol_check(o1.cpu(), (A.t() @ B).cpu(), (A.double().t() @ B.double()).cpu(), f"gemm_tn_ex {ka}x{kb}")
+        tol_check(c1.cpu(), B.sum(0).cpu(), B.double().sum(0).cpu(), f"gemm_tn_ex colsum {ka}x{kb}")
 
 
 # ---------------------------------------------------------------------------------------------- golden layer cases
 @pytest.mark.parametrize("name,C,De", [("triplet_C36", 36, 3), ("triplet_C60", 60, 4), ("triplet_C15_edge", 15, 4)])
-def test_triplet_message_golden(golden_layers, name, C, De):
+def test_triplet_message_golden(golden_layers, name, C, De, math_mode):
     from glam_b200 import layer
     c32, c64 = golden_layers[f"{name}_f32"], case(golden_layers, f"{name}_f64")
     m = _load(layer.TripletMessage(C, De), c32["state"])
@@ -133,7 +146,7 @@ def test_triplet_message_golden(golden_layers, name, C, De):
 
 
 @pytest.mark.parametrize("name,C,De", [("light_C36", 36, 3), ("light_C45_edge", 45, 4)])
-def test_triplet_light_golden(golden_layers, name, C, De):
+def test_triplet_light_golden(golden_layers, name, C, De, math_mode):
     from glam_b200 import layer
     c32, c64 = golden_layers[f"{name}_f32"], case(golden_layers, f"{name}_f64")
     m = _load(layer.TripletMessageLight(C, De), c32["state"])
@@ -146,8 +159,10 @@ def test_triplet_light_golden(golden_layers, name, C, De):
 
 
 @pytest.mark.parametrize("name", ["block_triplet_C36", "block_triplet_pn_C60", "block_light_C30"])
-def test_message_block_golden(golden_layers, name):
+def test_message_block_golden(golden_layers, name, math_mode):
     from glam_b200 import layer
+    if math_mode == "tf32" and "_pn_" in name:
+        pytest.skip("PairNorm gradients are ill-conditioned w.r.t. TF32 operands: see test_pairnorm_block_tf32_vs_tf32_oracle")
     c32, c64 = golden_layers[f"{name}_f32"], case(golden_layers, f"{name}_f64")
     cfg = c32["cfg"]
     blk = _load(layer.MessageBlock(cfg["C"], cfg["C"], cfg["De"], norm=cfg["norm"], dropout="_None()", conv=cfg["conv"],
@@ -166,7 +181,7 @@ def test_message_block_golden(golden_layers, name):
 
 @pytest.mark.parametrize("name,kind,C", [("set2set_C36", "s2s", 36), ("set2set_C30", "s2s", 30),
                                          ("lapool_C36", "la", 36), ("lapool_C45", "la", 45)])
-def test_readouts_golden(golden_layers, name, kind, C):
+def test_readouts_golden(golden_layers, name, kind, C, math_mode):
     from glam_b200 import layer
     c32, c64 = golden_layers[f"{name}_f32"], case(golden_layers, f"{name}_f64")
     m = _load(layer.Set2Set(C, 3) if kind == "s2s" else layer.GlobalLAPool(C), c32["state"])
@@ -191,10 +206,48 @@ def test_dot_pool_golden(golden_layers, name):
     tol_check(xb.grad, c32["grad_xb"], c64["grad_xb"], f"{name}.grad_xb")
 
 
+def test_pairnorm_block_tf32_vs_tf32_oracle(golden_layers):
+    """With PairNorm in the block the gradients amplify operand rounding ~300x (the fp64 oracle with TF32-truncated
+    matmul operands is 3e-1 away from the exact one on grad_x).  The tensor-core path must agree with THAT oracle:
+    the deviation is the operand format (what torch 1.10 does by default on Ampere+), not the kernels."""
+    from glam_b200 import layer, _lib
+    from oracle import glam_oracle as O
+    name = "block_triplet_pn_C60"
+    c32, c64 = golden_layers[f"{name}_f32"], case(golden_layers, f"{name}_f64")
+    cfg = c32["cfg"]
+    O.MM_OPERAND_HOOK = O.tf32_truncate
+    try:
+        ob = O.MessageBlock(cfg["C"], cfg["C"], cfg["De"], norm=cfg["norm"], dropout="_None()", conv=cfg["conv"], act=cfg["act"],
+                            res=cfg["res"]).double()
+        ob.load_state_dict(c64["state"])
+        x0 = c64["x"].clone().requires_grad_(True)
+        x, h = x0, None
+        for _ in range(cfg["steps"]):
+            x, h = ob(x, c32["edge_index"], c64["edge_attr"], h=h, batch=c32["batch"])
+        g_ref = torch.autograd.grad((x * c64["cot"]).sum() + (h * c64["coth"]).sum(), [x0] + list(ob.parameters()))
+    finally:
+        O.MM_OPERAND_HOOK = None
+    _lib.set_math_mode("tf32")
+    blk = _load(layer.MessageBlock(cfg["C"], cfg["C"], cfg["De"], norm=cfg["norm"], dropout="_None()", conv=cfg["conv"],
+                                   act=cfg["act"], res=cfg["res"]), c32["state"])
+    xd = c32["x"].to(DEV).requires_grad_(True)
+    y, hh = xd, None
+    for _ in range(cfg["steps"]):
+        y, hh = blk(y, c32["edge_index"].to(DEV), c32["edge_attr"].to(DEV), h=hh, batch=c32["batch"].to(DEV))
+    ((y * c32["cot"].to(DEV)).sum() + (hh * c32["coth"].to(DEV)).sum()).backward()
+    rel = lambda a, b: ((a.double().cpu() - b).abs().max() / b.abs().max()).item()
+    assert rel(y, x.detach()) < 2e-3
+    assert rel(xd.grad, g_ref[0]) < 5e-2, rel(xd.grad, g_ref[0])
+    for (n, p), g in zip(blk.named_parameters(), g_ref[1:]):
+        assert rel(p.grad, g) < 5e-2, (n, rel(p.grad, g))
+
+
 # ---------------------------------------------------------------------------------------------- golden models
 @pytest.mark.parametrize("name", ["gp_set2set", "gp_lapool_light", "gp_set2set_pairnorm"])
-def test_model_gp_golden(golden_models, name):
+def test_model_gp_golden(golden_models, name, math_mode):
     from glam_b200 import model
+    if math_mode == "tf32" and "pairnorm" in name:
+        pytest.skip("PairNorm gradients are ill-conditioned w.r.t. TF32 operands: see test_pairnorm_block_tf32_vs_tf32_oracle")
     from oracle import glam_oracle as O
     c = golden_models[name]
     cfg = c["cfg"]
@@ -209,16 +262,18 @@ def test_model_gp_golden(golden_models, name):
     out64 = o64(d64)
     loss64 = torch.nn.functional.mse_loss(out64, c["y"].double())
     g64 = dict(zip([n for n, _ in o64.named_parameters()], torch.autograd.grad(loss64, list(o64.parameters()))))
+    emu = tf32_emulated(lambda: torch.autograd.grad(torch.nn.functional.mse_loss(o64(d64), c["y"].double()), list(o64.parameters())))
+    gemu = dict(zip([n for n, _ in o64.named_parameters()], emu))
     data = ns(c["x"].to(DEV), c["edge_index"].to(DEV), c["edge_attr"].to(DEV), c["batch"].to(DEV))
     out = m(data)
     tol_check(out, c["out"], out64, f"{name}.out", rtol=2e-4)
     loss = torch.nn.functional.mse_loss(out, c["y"].to(DEV))
     loss.backward()
     for n, p in m.named_parameters():
-        tol_check(p.grad, c["grad_params"][n], g64[n], f"{name}.grad[{n}]", rtol=2e-4)
+        tol_check(p.grad, c["grad_params"][n], g64[n], f"{name}.grad[{n}]", rtol=2e-4, emu64=gemu[n])
 
 
-def test_model_ddi_golden(golden_models):
+def test_model_ddi_golden(golden_models, math_mode):
     from glam_b200 import model
     from oracle import glam_oracle as O
     c = golden_models["ddi_set2set"]
@@ -235,6 +290,9 @@ def test_model_ddi_golden(golden_models):
     out64 = o64(a64, b64)
     loss64 = torch.nn.functional.binary_cross_entropy_with_logits(out64, c["y"].double())
     g64 = dict(zip([n for n, _ in o64.named_parameters()], torch.autograd.grad(loss64, list(o64.parameters()))))
+    emu = tf32_emulated(lambda: torch.autograd.grad(
+        torch.nn.functional.binary_cross_entropy_with_logits(o64(a64, b64), c["y"].double()), list(o64.parameters())))
+    gemu = dict(zip([n for n, _ in o64.named_parameters()], emu))
     a = ns(*[c[k].to(DEV) for k in ("a_x", "a_edge_index", "a_edge_attr", "a_batch")])
     b = ns(*[c[k].to(DEV) for k in ("b_x", "b_edge_index", "b_edge_attr", "b_batch")])
     out = m(a, b)
@@ -242,7 +300,7 @@ def test_model_ddi_golden(golden_models):
     loss = torch.nn.functional.binary_cross_entropy_with_logits(out, c["y"].to(DEV))
     loss.backward()
     for n, p in m.named_parameters():
-        tol_check(p.grad, c["grad_params"][n], g64[n], f"ddi.grad[{n}]", rtol=2e-4)
+        tol_check(p.grad, c["grad_params"][n], g64[n], f"ddi.grad[{n}]", rtol=2e-4, emu64=gemu[n])
 
 
 # ---------------------------------------------------------------------------------------------- oracle on seeded inputs
@@ -261,7 +319,7 @@ def _gp_pair(Din, De, readout, block, act="CELU"):
 @pytest.mark.parametrize("Din,De,readout,block,B", [(9, 3, "Set2Set", "_TripletMessage", 128),
                                                    (15, 4, "GlobalLAPool", "_TripletMessage", 96),
                                                    (15, 4, "Set2Set", "_TripletMessageLight", 64)])
-def test_gp_training_step_vs_oracle(Din, De, readout, block, B):
+def test_gp_training_step_vs_oracle(Din, De, readout, block, B, math_mode):
     """BASELINE config 1 shape (128 ESOL-like molecules): forward + backward against the fp32 and fp64 oracle."""
     from glam_b200.synth import make_molecule_batch
     m, o32 = _gp_pair(Din, De, readout, block)
@@ -274,15 +332,16 @@ def test_gp_training_step_vs_oracle(Din, De, readout, block, B):
     l64 = torch.nn.functional.mse_loss(out64, b.y.double())
     g32 = torch.autograd.grad(l32, list(o32.parameters()))
     g64 = torch.autograd.grad(l64, list(o64.parameters()))
+    gemu = tf32_emulated(lambda: torch.autograd.grad(torch.nn.functional.mse_loss(o64(d64), b.y.double()), list(o64.parameters())))
     bd = b.to(DEV)
     out = m(bd)
     tol_check(out, out32, out64, "gp.out", rtol=2e-4)
     torch.nn.functional.mse_loss(out, bd.y).backward()
-    for (n, p), a, c in zip(m.named_parameters(), g32, g64):
-        tol_check(p.grad, a, c, f"gp.grad[{n}]", rtol=2e-4)
+    for (n, p), a, c, e in zip(m.named_parameters(), g32, g64, gemu):
+        tol_check(p.grad, a, c, f"gp.grad[{n}]", rtol=2e-4, emu64=e)
 
 
-def test_dti_shaped_pair_vs_oracle():
+def test_dti_shaped_pair_vs_oracle(math_mode):
     """BASELINE config 4 shape: ligand graph + protein contact-map graph (hundreds of residues, De=8, duplicate edges)."""
     from glam_b200 import model
     from glam_b200.synth import make_molecule_batch, make_protein_batch
@@ -303,15 +362,18 @@ def test_dti_shaped_pair_vs_oracle():
                 ns(p.x.double(), p.edge_index, p.edge_attr.double(), p.batch))
     g32 = torch.autograd.grad(torch.nn.functional.cross_entropy(out32, y), list(o32.parameters()))
     g64 = torch.autograd.grad(torch.nn.functional.cross_entropy(out64, y), list(o64.parameters()))
+    gemu = tf32_emulated(lambda: torch.autograd.grad(torch.nn.functional.cross_entropy(
+        o64(ns(a.x.double(), a.edge_index, a.edge_attr.double(), a.batch),
+            ns(p.x.double(), p.edge_index, p.edge_attr.double(), p.batch)), y), list(o64.parameters())))
     out = m(a.to(DEV), p.to(DEV))
     tol_check(out, out32, out64, "dti.out", rtol=2e-4)
     torch.nn.functional.cross_entropy(out, y.to(DEV)).backward()
-    for (n, prm), g_a, g_c in zip(m.named_parameters(), g32, g64):
-        tol_check(prm.grad, g_a, g_c, f"dti.grad[{n}]", rtol=2e-4)
+    for (n, prm), g_a, g_c, g_e in zip(m.named_parameters(), g32, g64, gemu):
+        tol_check(prm.grad, g_a, g_c, f"dti.grad[{n}]", rtol=2e-4, emu64=g_e)
 
 
 # ---------------------------------------------------------------------------------------------- properties
-def test_hub_node_multichunk_softmax():
+def test_hub_node_multichunk_softmax(math_mode):
     """A destination with in-degree > 32 exercises the multi-chunk softmax path; isolated nodes give `bias`."""
     from glam_b200 import layer
     from oracle import glam_oracle as O
@@ -346,7 +408,7 @@ def test_hub_node_multichunk_softmax():
         tol_check(p.grad, a, c, f"hub.grad[{n}]")
 
 
-def test_edge_permutation_invariance_and_determinism():
+def test_edge_permutation_invariance_and_determinism(math_mode):
     from glam_b200 import layer, graph
     from glam_b200.synth import make_molecule_batch
     torch.manual_seed(3)
@@ -359,7 +421,9 @@ def test_edge_permutation_invariance_and_determinism():
         assert torch.equal(out1, out2)                                       # bitwise reproducible
         perm = torch.randperm(b.num_edges, device=DEV)
         out3 = m(b.x, b.edge_index[:, perm].contiguous(), b.edge_attr[perm].contiguous())
-    torch.testing.assert_close(out3, out1, rtol=1e-5, atol=1e-6)             # summation order may change
+    # summation order changes: fp32 round-off, which a TF32 operand of the next projection may amplify to ~1e-3
+    tol = dict(rtol=1e-5, atol=1e-6) if math_mode == "fp32" else dict(rtol=5e-3, atol=5e-4)
+    torch.testing.assert_close(out3, out1, **tol)
 
 
 def test_batch_of_one_equals_unbatched():
