@@ -41,7 +41,13 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-__device__ __forceinline__ float celu1(float x) { return x > 0.f ? x : expm1f(x); }
+// CELU(alpha = 1) = max(0,x) + min(0, exp(x) - 1).  Branch-free expm1 for x <= 0: degree-7 Taylor polynomial on
+// [-0.25, 0] (truncation error < 4e-10), exp(x) - 1 below (cancellation error <= 1 ulp of 1 * 2^-2 relative there).
+__device__ __forceinline__ float expm1_neg(float x) {
+    const float p = x * (1.f + x * (0.5f + x * (1.f / 6 + x * (1.f / 24 + x * (1.f / 120 + x * (1.f / 720 + x * (1.f / 5040)))))));
+    return x > -0.25f ? p : expf(x) - 1.f;
+}
+__device__ __forceinline__ float celu1(float x) { return x > 0.f ? x : expm1_neg(x); }
 
 // activation codes shared with the host side (glam_b200/functional.py)
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_CELU = 3 };

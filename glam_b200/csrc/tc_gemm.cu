@@ -2,12 +2,19 @@
 //
 //   Y[M,N] = epilogue(X[M,K] * W + bias)        M = nodes (10^5..10^8), K,N = 36..288
 //
-// The contraction is tiny per row, so the kernel is a streaming one: a persistent CTA keeps the whole weight
-// matrix resident in shared memory (K-major, SWIZZLE_128B panels, staged once), then for every 128-row tile
-// stages X with coalesced 16-byte loads into the swizzled operand image, issues ceil(K/8) tcgen05.mma from one
-// thread into a TMEM accumulator (128 lanes x N columns), and drains it with tcgen05.ld straight into the
-// epilogue (bias / CELU / CELU' mask / accumulate) and global stores.  Several CTAs share an SM so that one
-// CTA's loads overlap another's MMA + epilogue.
+// The contraction is tiny per row, so this is a streaming kernel whose job is to keep HBM busy.  One persistent
+// CTA per SM, warp-specialised:
+//   warp 0  (1 lane)  TMA producer: cp.async.bulk.tensor loads of 128-row X tiles (32-feature panels, hardware
+//                     SWIZZLE_128B, out-of-bounds rows/columns zero-filled) into a 2..4-stage shared-memory ring;
+//   warp 1  (1 lane)  MMA issuer: ceil(K/8) tcgen05.mma.kind::tf32 per tile into one of two TMEM accumulators,
+//                     tcgen05.commit releases the smem stage and publishes the accumulator;
+//   warps 2-5         epilogue: tcgen05.ld (thread = row = TMEM lane) -> bias / CELU / CELU' mask / accumulate ->
+//                     16-byte global stores; they also stage W once (K-major swizzled image) at kernel start.
+// Loads of tile i+2.., MMA of tile i+1 and the epilogue of tile i overlap; the accumulator is double-buffered.
+//
+// Output columns [exact_begin, exact_end) bypass the tensor core: the attention-logit columns s_i|s_j of the
+// extended node projection are computed with exact fp32 FMAs from the staged operands (see glam_gemm_ex).
+#include <cuda.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -15,142 +22,369 @@ namespace glam {
 
 using namespace tc;
 
-constexpr int kTcThreads = 128;
+constexpr int kEpiGroups = 2;                          // two 4-warp epilogue groups, one per TMEM accumulator
+constexpr int kTcThreads = 64 + kEpiGroups * 128;
 constexpr int kTileM = 128;
+constexpr int kMaxStages = 4;
+constexpr int kPanelBytes = kTileM * kPanelRowBytes;   // 16 KB: one 32-feature panel of a 128-row tile
 
 enum Epi { EPI_NONE = 0, EPI_CELU = 1, EPI_MUL_CELU_GRAD = 2, EPI_ACCUM = 3 };
 
 struct TcGemmParams {
-    const float* X; int64_t ldx;
     const float* W; int64_t w_sk, w_sn;
     const float* bias;
     const float* aux; int64_t ldaux;
     float* Y; int64_t ldy;
     int64_t M; int N, K, epi;
-    int KP, Npad, tmem_cols, vec_store;
+    int KP, Npad, tmem_cols, vec_store, stages, staged_out;
     int exact_begin, exact_end;   // output columns computed with exact fp32 FMAs (attention-logit columns)
 };
 
-__global__ void __launch_bounds__(kTcThreads)
-tc_gemm_kernel(const TcGemmParams p) {
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2], w_bar;
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int panels = (p.KP + kPanelFeatures - 1) / kPanelFeatures;
-    uint8_t* Xs = smem;                                         // [panels][128][128 B]
-    uint8_t* Ws = smem + (size_t)panels * kTileM * kPanelRowBytes;   // [panels][Npad][128 B]
+    const int stage_bytes = panels * kPanelBytes;
+    uint8_t* Xs = smem;                                          // [stages][panels][128][128 B]
+    uint8_t* Ws = smem + (size_t)p.stages * stage_bytes;         // [panels][Npad][128 B]
+    float* Os = reinterpret_cast<float*>(Ws + (size_t)panels * p.Npad * kPanelRowBytes);   // [128][N] output staging
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const bool has_exact = p.exact_end > p.exact_begin;
 
-    if (t == 0) { mbar_init(&mma_bar, 1); fence_mbar_init(); }
-    if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
-    // stage W once: Ws(n, k) = W[k*w_sk + n*w_sn], zero padded to [Npad][KP]
-    for (int idx = t; idx < p.Npad * p.KP; idx += kTcThreads) {
-        int n, k;
-        if (p.w_sn == 1) { k = idx / p.Npad; n = idx - k * p.Npad; } else { n = idx / p.KP; k = idx - n * p.KP; }
-        float v = (n < p.N && k < p.K) ? p.W[(int64_t)k * p.w_sk + (int64_t)n * p.w_sn] : 0.f;
-        *reinterpret_cast<float*>(Ws + panel_offset(n, k, p.Npad)) = v;
+    if (t == 0) {
+        for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], has_exact ? 5 : 1); }   // MMA commit (+ 4 epilogue warps)
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        mbar_init(&w_bar, 4 * kEpiGroups);
+        fence_mbar_init();
     }
+    if (warp == 1) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
-    const uint32_t idesc = make_idesc_tf32(kTileM, p.Npad, 0, 0);
-    const uint32_t xs_addr = smem_u32(Xs), ws_addr = smem_u32(Ws);
-    const int KQ = p.K >> 2, KPQ = p.KP >> 2;
     const int64_t ntiles = (p.M + kTileM - 1) / kTileM;
-    uint32_t phase = 0;
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t m0 = tile * kTileM;
-        // ---- stage X tile (coalesced 16 B loads -> swizzled 16 B stores)
-        for (int idx = t; idx < kTileM * KPQ; idx += kTcThreads) {
-            const int r = idx / KPQ, q = idx - r * KPQ;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (q < KQ && m0 + r < p.M) v = *reinterpret_cast<const float4*>(p.X + (m0 + r) * p.ldx + 4 * q);
-            *reinterpret_cast<float4*>(Xs + panel_chunk_offset(r, q, kTileM)) = v;
-        }
-        fence_proxy_async_smem();
-        __syncthreads();
-        // ---- MMA: one thread, ceil(K/8) instructions, accumulator in TMEM
-        if (t == 0) {
-            tc_fence_after_sync();
-            const int ksteps = p.KP >> 3;
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t pan = ks >> 2, within = (ks & 3) * 32;
-                const uint64_t da = make_smem_desc(xs_addr + pan * (kTileM * kPanelRowBytes) + within, 16, 1024);
-                const uint64_t db = make_smem_desc(ws_addr + pan * (p.Npad * kPanelRowBytes) + within, 16, 1024);
-                mma_tf32_ss(tmem_base, da, db, idesc, ks > 0 ? 1u : 0u);
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            prefetch_tensormap(&tmap_x);
+            int it = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                for (int pn = 0; pn < panels; ++pn)
+                    tma_load_2d(Xs + (size_t)s * stage_bytes + (size_t)pn * kPanelBytes, &tmap_x, pn * kPanelFeatures,
+                                (int)(tile * kTileM), &full_bar[s]);
             }
-            mma_commit(&mma_bar);
         }
-        mbar_wait(&mma_bar, phase);
-        phase ^= 1;
-        tc_fence_after_sync();
-        // ---- epilogue: thread = row = TMEM lane
-        const int64_t m = m0 + t;
-        const bool row_ok = m < p.M;
-        float* yrow = p.Y + m * p.ldy;
-        const float* arow = p.aux ? p.aux + m * p.ldaux : nullptr;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int c0 = 0; c0 < p.Npad; c0 += 16) {
-            float v[16];
-            tmem_ld16(lane_base + (uint32_t)c0, v);
-            if (!row_ok) continue;
-            if (c0 < p.exact_end && c0 + 16 > p.exact_begin) {
-                // attention-logit columns: exact fp32 dot products from the staged operands (this thread's X row is
-                // row t of the swizzled image; the W rows are broadcast reads)
-                for (int n = max(c0, p.exact_begin); n < min(c0 + 16, p.exact_end); ++n) {
-                    float acc = 0.f;
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(kTileM, p.Npad, 0, 0);
+            const uint32_t xs_addr = smem_u32(Xs), ws_addr = smem_u32(Ws);
+            const int ksteps = p.KP >> 3;
+            mbar_wait(&w_bar, 0);
+            int it = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int s = it % p.stages, a = it & 1;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u, aph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&tempty_bar[a], aph ^ 1u);
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.Npad);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint32_t pan = ks >> 2, within = (ks & 3) * 32;
+                    const uint64_t da = make_smem_desc(xs_addr + s * stage_bytes + pan * kPanelBytes + within, 16, 1024);
+                    const uint64_t db = make_smem_desc(ws_addr + pan * (p.Npad * kPanelRowBytes) + within, 16, 1024);
+                    mma_tf32_ss(d_tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+                }
+                mma_commit(&empty_bar[s]);       // smem stage free once these MMAs have read it
+                mma_commit(&tfull_bar[a]);       // accumulator ready
+            }
+        }
+    } else {
+        // ================================ epilogue warps ===============================
+        const int eall = t - 64;                                 // 0 .. 128*kEpiGroups-1 (W staging)
+        const int grp = (warp - 2) >> 2;                         // epilogue group = TMEM accumulator index
+        const int wg = (warp - 2) & 3;                           // warp within the group
+        const int q4 = warp & 3;                                 // TMEM lane quarter this warp may read
+        const int row_in_tile = q4 * 32 + lane;
+        float* Og = Os + (size_t)grp * kTileM * p.N;             // this group's staging tile
+        // ---- stage W once: K-major swizzled image [panels][Npad][128 B], zero padded to [Npad][KP]
+        {
+            const int KPQ = p.KP >> 2;
+            const int items = p.Npad * KPQ;
+            constexpr int kWT = 128 * kEpiGroups;
+            for (int base = 0; base < items; base += kWT * 4) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = base + u * kWT + eall;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx < items) {
+                        int n, q;
+                        if (p.w_sn == 1) { q = idx / p.Npad; n = idx - q * p.Npad; } else { n = idx / KPQ; q = idx - n * KPQ; }
+                        if (n < p.N) {
+                            const int k = 4 * q;
+                            const float* w = p.W + (int64_t)k * p.w_sk + (int64_t)n * p.w_sn;
+                            if (k < p.K) v[u].x = w[0];
+                            if (k + 1 < p.K) v[u].y = w[p.w_sk];
+                            if (k + 2 < p.K) v[u].z = w[2 * p.w_sk];
+                            if (k + 3 < p.K) v[u].w = w[3 * p.w_sk];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = base + u * kWT + eall;
+                    if (idx < items) {
+                        int n, q;
+                        if (p.w_sn == 1) { q = idx / p.Npad; n = idx - q * p.Npad; } else { n = idx / KPQ; q = idx - n * KPQ; }
+                        *reinterpret_cast<float4*>(Ws + panel_chunk_offset(n, q, p.Npad)) = v[u];
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&w_bar);
+            if (has_exact) mbar_wait(&w_bar, 0);                 // the exact columns read W rows from shared memory
+        }
+        const int KQ = p.K >> 2;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int s = it % p.stages, a = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            if (a != grp) continue;
+            mbar_wait(&tfull_bar[a], aph);
+            tc_fence_after_sync();
+            const int64_t m = tile * kTileM + row_in_tile;
+            const bool row_ok = m < p.M;
+            float* yrow = p.Y + m * p.ldy;
+            const float* arow = p.aux ? p.aux + m * p.ldaux : nullptr;
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * p.Npad);
+            const uint8_t* Xrow = Xs + (size_t)s * stage_bytes;
+            if (p.staged_out) {
+                // ---- phase 1 (thread = row): TMEM -> registers -> row-major staging tile in shared memory
+                float xs[6];                                     // exact fp32 logit columns (<= 2*GLAM_MAX_HEADS... 6 used)
+                const int nex = has_exact ? min(p.exact_end - p.exact_begin, 6) : 0;
+                if (nex > 0) {
+#pragma unroll
+                    for (int e = 0; e < 6; ++e) xs[e] = 0.f;
                     for (int q = 0; q < KQ; ++q) {
-                        const float4 xv = *reinterpret_cast<const float4*>(Xs + panel_chunk_offset(t, q, kTileM));
-                        const float4 wv = *reinterpret_cast<const float4*>(Ws + panel_chunk_offset(n, q, p.Npad));
-                        acc = fmaf(xv.x, wv.x, acc); acc = fmaf(xv.y, wv.y, acc);
-                        acc = fmaf(xv.z, wv.z, acc); acc = fmaf(xv.w, wv.w, acc);
+                        const float4 xv = *reinterpret_cast<const float4*>(Xrow + panel_chunk_offset(row_in_tile, q, kTileM));
+#pragma unroll
+                        for (int e = 0; e < 6; ++e) {
+                            if (e < nex) {
+                                const float4 wv = *reinterpret_cast<const float4*>(Ws + panel_chunk_offset(p.exact_begin + e, q, p.Npad));
+                                xs[e] = fmaf(xv.x, wv.x, xs[e]); xs[e] = fmaf(xv.y, wv.y, xs[e]);
+                                xs[e] = fmaf(xv.z, wv.z, xs[e]); xs[e] = fmaf(xv.w, wv.w, xs[e]);
+                            }
+                        }
+                    }
+                }
+                for (int c0 = 0; c0 < p.Npad; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(lane_base + (uint32_t)c0, v);      // Npad is a multiple of 16: the second half may be padding
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (c0 + j < p.N)
+                            *reinterpret_cast<float4*>(Og + row_in_tile * p.N + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+                if (nex > 0) {                                   // overwrite the logit columns with the exact values
+#pragma unroll
+                    for (int e = 0; e < 6; ++e)
+                        if (e < nex) Og[row_in_tile * p.N + p.exact_begin + e] = xs[e];
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {                                 // accumulator and X stage are free again
+                    mbar_arrive(&tempty_bar[a]);
+                    if (has_exact) mbar_arrive(&empty_bar[s]);
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                // ---- phase 2: warp per row, lanes over 16-byte column chunks -> fully coalesced global accesses
+                const int nq = p.N >> 2;
+                const int64_t rows_left = p.M - tile * kTileM;
+                const int rows_here = rows_left < kTileM ? (int)rows_left : kTileM;
+                if (nq >= 24) {
+                    // wide rows: warp per row, lanes over the row's 16-byte chunks (bias hoisted, no index math)
+                    for (int cq = lane; cq < nq; cq += 32) {
+                        const int c = cq << 2;
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias) b = *reinterpret_cast<const float4*>(p.bias + c);
+#pragma unroll 4
+                        for (int r = wg; r < rows_here; r += 4) {
+                            float4 v = *reinterpret_cast<const float4*>(Og + r * p.N + c);
+                            const int64_t mm = tile * kTileM + r;
+                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                            if (p.epi == EPI_CELU) { v.x = celu1(v.x); v.y = celu1(v.y); v.z = celu1(v.z); v.w = celu1(v.w); }
+                            else if (p.epi == EPI_MUL_CELU_GRAD) {
+                                const float4 y = *reinterpret_cast<const float4*>(p.aux + mm * p.ldaux + c);
+                                v.x *= (y.x > 0.f ? 1.f : y.x + 1.f); v.y *= (y.y > 0.f ? 1.f : y.y + 1.f);
+                                v.z *= (y.z > 0.f ? 1.f : y.z + 1.f); v.w *= (y.w > 0.f ? 1.f : y.w + 1.f);
+                            } else if (p.epi == EPI_ACCUM) {
+                                const float4 y = *reinterpret_cast<const float4*>(p.Y + mm * p.ldy + c);
+                                v.x += y.x; v.y += y.y; v.z += y.z; v.w += y.w;
+                            }
+                            *reinterpret_cast<float4*>(p.Y + mm * p.ldy + c) = v;
+                        }
+                    }
+                } else {
+                // narrow rows: flat sweep over the tile's 16-byte chunks, 4 independent chunks per thread in flight
+                const int total = rows_here * nq;
+                const float inv_nq = 1.0f / (float)nq;
+                for (int i0 = wg * 32 + lane; i0 < total; i0 += 128 * 4) {
+                    float4 v[4], y[4];
+                    int64_t off[4];
+                    int cc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + 128 * u;
+                        if (i < total) {
+                            const int r = (int)(((float)i + 0.5f) * inv_nq);      // exact for i < 2^13
+                            cc[u] = (i - r * nq) << 2;
+                            off[u] = (tile * kTileM + r);
+                            v[u] = *reinterpret_cast<const float4*>(Og + (i << 2));
+                            if (p.epi == EPI_MUL_CELU_GRAD) y[u] = *reinterpret_cast<const float4*>(p.aux + off[u] * p.ldaux + cc[u]);
+                            else if (p.epi == EPI_ACCUM) y[u] = *reinterpret_cast<const float4*>(p.Y + off[u] * p.ldy + cc[u]);
+                        }
                     }
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (c0 + j == n) v[j] = acc;
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + 128 * u;
+                        if (i < total) {
+                            float4 w = v[u];
+                            if (p.bias) {
+                                const float4 b = *reinterpret_cast<const float4*>(p.bias + cc[u]);
+                                w.x += b.x; w.y += b.y; w.z += b.z; w.w += b.w;
+                            }
+                            if (p.epi == EPI_CELU) { w.x = celu1(w.x); w.y = celu1(w.y); w.z = celu1(w.z); w.w = celu1(w.w); }
+                            else if (p.epi == EPI_MUL_CELU_GRAD) {
+                                w.x *= (y[u].x > 0.f ? 1.f : y[u].x + 1.f); w.y *= (y[u].y > 0.f ? 1.f : y[u].y + 1.f);
+                                w.z *= (y[u].z > 0.f ? 1.f : y[u].z + 1.f); w.w *= (y[u].w > 0.f ? 1.f : y[u].w + 1.f);
+                            } else if (p.epi == EPI_ACCUM) { w.x += y[u].x; w.y += y[u].y; w.z += y[u].z; w.w += y[u].w; }
+                            *reinterpret_cast<float4*>(p.Y + off[u] * p.ldy + cc[u]) = w;
+                        }
+                    }
+                }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // staging tile free for this group's next tile
+                continue;
+            }
+            for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+                float v[16];
+                tmem_ld16(lane_base + (uint32_t)c0, v);
+                if (!row_ok) continue;
+                if (c0 < p.exact_end && c0 + 16 > p.exact_begin) {
+                    for (int n = max(c0, p.exact_begin); n < min(c0 + 16, p.exact_end); ++n) {
+                        float acc = 0.f;
+                        for (int q = 0; q < KQ; ++q) {
+                            const float4 xv = *reinterpret_cast<const float4*>(Xrow + panel_chunk_offset(row_in_tile, q, kTileM));
+                            const float4 wv = *reinterpret_cast<const float4*>(Ws + panel_chunk_offset(n, q, p.Npad));
+                            acc = fmaf(xv.x, wv.x, acc); acc = fmaf(xv.y, wv.y, acc);
+                            acc = fmaf(xv.z, wv.z, acc); acc = fmaf(xv.w, wv.w, acc);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (c0 + j == n) v[j] = acc;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = c0 + j;
+                    if (n < p.N) {
+                        float acc = v[j];
+                        if (p.bias) acc += p.bias[n];
+                        if (p.epi == EPI_CELU) acc = celu1(acc);
+                        else if (p.epi == EPI_MUL_CELU_GRAD) { float y = arow[n]; acc *= (y > 0.f ? 1.f : y + 1.f); }
+                        else if (p.epi == EPI_ACCUM) acc += yrow[n];
+                        v[j] = acc;
+                    }
+                }
+                if (p.vec_store && c0 + 16 <= p.N) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(yrow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < p.N) yrow[c0 + j] = v[j];
                 }
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = c0 + j;
-                if (n < p.N) {
-                    float a = v[j];
-                    if (p.bias) a += p.bias[n];
-                    if (p.epi == EPI_CELU) a = celu1(a);
-                    else if (p.epi == EPI_MUL_CELU_GRAD) { float y = arow[n]; a *= (y > 0.f ? 1.f : y + 1.f); }
-                    else if (p.epi == EPI_ACCUM) a += yrow[n];
-                    v[j] = a;
-                }
-            }
-            if (p.vec_store && c0 + 16 <= p.N) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(yrow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j < p.N) yrow[c0 + j] = v[j];
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&tempty_bar[a]);
+                if (has_exact) mbar_arrive(&empty_bar[s]);
             }
         }
-        tc_fence_before_sync();
-        __syncthreads();
     }
-    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-    (void)lane;
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 static int g_math_mode = 1;   // 0 = fp32 on the CUDA cores (exact), 1 = TF32 tensor cores (default)
 int g_math_mode_get() { return g_math_mode; }
 
+// ---- host: tensor map encoding through the driver entry point (no link-time dependency on libcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] with leading dimension ld; box = box_rows x 32 features
+int make_tmap_rows(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int swizzle) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return -1; }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)kPanelFeatures, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows, (long long)cols, (long long)ld);
+        return -1;
+    }
+    return 0;
+}
+
+// Shared-memory plan: W image + (optionally) the [128][N] output staging tile + as many X stages as fit (<= 4).
+static size_t tc_smem_bytes(int64_t N, int64_t K, bool want_staged, int* stages_out, int* staged_out) {
+    const int64_t KP = (K + 7) / 8 * 8, Npad = (N + 15) / 16 * 16;
+    const int64_t panels = (KP + kPanelFeatures - 1) / kPanelFeatures;
+    const int64_t wbytes = panels * Npad * kPanelRowBytes, stage = panels * kPanelBytes;
+    const int64_t obytes = (int64_t)kEpiGroups * kTileM * N * sizeof(float);
+    const int64_t limit = 222 * 1024;
+    int64_t staged = want_staged ? 1 : 0;
+    int64_t stages = (limit - wbytes - staged * obytes) / stage;
+    if (staged && stages < 2) { staged = 0; stages = (limit - wbytes) / stage; }   // keep the load pipeline alive first
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages_out) *stages_out = (int)stages;
+    if (staged_out) *staged_out = (int)staged;
+    return stages < 1 ? 0 : (size_t)(wbytes + staged * obytes + stages * stage + 1024);
+}
+
 bool tc_gemm_eligible(const float* X, int64_t ldx, const float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K) {
     if (g_math_mode == 0) return false;
     if (N > 256 || K > 288 || K < 4 || (K & 3) || (ldx & 3) || ((uintptr_t)X & 15)) return false;
-    if (M < 1) return false;
-    const int64_t panels = ((K + 7) / 8 * 8 + kPanelFeatures - 1) / kPanelFeatures;
-    const int64_t smem = panels * (kTileM + (N + 15) / 16 * 16) * kPanelRowBytes + 1024;
-    if (smem > 220 * 1024) return false;             // operands must fit next to each other in shared memory
+    if (M < 1 || M >= ((int64_t)1 << 31)) return false;
+    if (tc_smem_bytes(N, K, false, nullptr, nullptr) == 0) return false;  // operands must fit in shared memory
     (void)Y; (void)ldy;
     return true;
 }
@@ -160,31 +394,28 @@ int tc_gemm_launch(const float* X, int64_t ldx, const float* W, int64_t w_sk, in
                    int exact_begin, int exact_end, cudaStream_t stream) {
     TcGemmParams p;
     p.exact_begin = exact_begin; p.exact_end = exact_end;
-    p.X = X; p.ldx = ldx; p.W = W; p.w_sk = w_sk; p.w_sn = w_sn; p.bias = bias; p.aux = aux; p.ldaux = ldaux;
+    p.W = W; p.w_sk = w_sk; p.w_sn = w_sn; p.bias = bias; p.aux = aux; p.ldaux = ldaux;
     p.Y = Y; p.ldy = ldy; p.M = M; p.N = (int)N; p.K = (int)K; p.epi = epi;
     p.KP = (int)((K + 7) / 8 * 8);
     p.Npad = (int)((N + 15) / 16 * 16);
-    p.tmem_cols = (int)tmem_cols_pow2((uint32_t)p.Npad);
+    p.tmem_cols = (int)tmem_cols_pow2((uint32_t)(p.Npad + (p.Npad + 31) / 32 * 32));   // epilogue reads 32-column groups
     p.vec_store = ((ldy & 3) == 0 && ((uintptr_t)Y & 15) == 0) ? 1 : 0;
-    const int panels = (p.KP + kPanelFeatures - 1) / kPanelFeatures;
-    const size_t smem = (size_t)panels * (kTileM + p.Npad) * kPanelRowBytes + 1024;
-    GLAM_REQUIRE(smem <= 220 * 1024, "tc_gemm: operands do not fit in shared memory (N=%lld K=%lld)", (long long)N, (long long)K);
+    const bool al16 = ((N & 3) == 0) && ((ldy & 3) == 0) && (((uintptr_t)Y & 15) == 0) && (((uintptr_t)bias & 15) == 0) &&
+                      (aux == nullptr || (((ldaux & 3) == 0) && (((uintptr_t)aux & 15) == 0)));
+    const size_t smem = tc_smem_bytes(N, K, al16, &p.stages, &p.staged_out);
+    GLAM_REQUIRE(smem > 0, "tc_gemm: operands do not fit in shared memory (N=%lld K=%lld)", (long long)N, (long long)K);
+    CUtensorMap tmap;
+    if (int rc = make_tmap_rows(&tmap, X, M, K, ldx, kTileM, (int)CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("tc_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         configured = smem;
     }
-    // CTAs per SM limited by shared memory and by TMEM columns (512 per SM)
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    const int by_tmem = 512 / p.tmem_cols;
-    if (per_sm > by_tmem) per_sm = by_tmem;
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm < 1) per_sm = 1;
     const int64_t ntiles = (M + kTileM - 1) / kTileM;
-    int64_t grid = (int64_t)kNumSMs * per_sm;
+    int64_t grid = kNumSMs;
     if (grid > ntiles) grid = ntiles;
-    tc_gemm_kernel<<<(unsigned)grid, kTcThreads, smem, stream>>>(p);
+    tc_gemm_kernel<<<(unsigned)grid, kTcThreads, smem, stream>>>(tmap, p);
     GLAM_CHECK_LAUNCH();
     return 0;
 }

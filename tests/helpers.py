@@ -45,7 +45,7 @@ def tol_check(ours, ref32, ref64, name="", rtol=1e-4, atol=1e-5, emu64=None):
     deviation that operand rounding alone causes in the oracle (some gradients amplify it well beyond 5e-3)."""
     extra = 0.0
     if MATH_MODE["mode"] == "tf32":
-        rtol = max(rtol, TF32_RTOL)
+        rtol = max(rtol, TF32_RTOL) if rtol < TF32_RTOL else rtol
         if emu64 is not None:
             extra = 4 * (emu64.double().cpu() - ref64.double().cpu()).abs().max()
     """SURVEY.md §8c tolerance: |ours - ref64| <= max(2*|ref32 - ref64|, atol + rtol*|ref64|), evaluated with a

@@ -1,0 +1,47 @@
+"""Ad-hoc micro-benchmark of individual library calls at the bench shapes (CUDA events, L2 flushed between reps)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from glam_b200 import ops, _lib, graph
+from glam_b200.synth import make_molecule_batch
+_lib.load()
+dev = "cuda"
+N, C, H, De = 102400, 36, 3, 3
+HC, ld = H * C, 116
+flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+
+def timeit(name, fn, nbytes, reps=10):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort(); t = ts[len(ts) // 2]
+    print(f"{name:44s} {t*1e3:8.1f} us  {nbytes/t/1e6:8.1f} GB/s  ({nbytes/1e6:.1f} MB)")
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+x = torch.randn(N, C, device=dev); w_ext = torch.randn(C, ld, device=dev); agg = torch.randn(N, HC, device=dev)
+w_scale = torch.randn(HC, C, device=dev); bias = torch.randn(C, device=dev); w_ih = torch.randn(3 * C, C, device=dev); b3 = torch.randn(3 * C, device=dev)
+g108 = torch.randn(N, HC, device=dev); g116 = torch.randn(N, ld, device=dev)
+if which in ("all", "gemm"):
+    timeit("gemm node_proj [N,36]x[36,116] exact6", lambda: ops.gemm(x, w_ext, exact_cols=(108, 114)), 4 * N * (C + ld))
+    timeit("gemm scale [N,108]x[108,36] celu", lambda: ops.gemm(agg, w_scale, bias=bias, epilogue=1), 4 * N * (HC + C))
+    timeit("gemm scale [N,108]x[108,36] bias only", lambda: ops.gemm(agg, w_scale, bias=bias, epilogue=0), 4 * N * (HC + C))
+    timeit("gemm scale^T [N,108]x[36,108]^T", lambda: ops.gemm(agg, w_scale.t().contiguous(), transpose_w=True), 4 * N * (HC + C))
+    timeit("gemm gru [N,36]x[36,108]^T", lambda: ops.gemm(x, w_ih, transpose_w=True, bias=b3), 4 * N * (C + HC))
+    timeit("gemm dgrad [N,116]x[116,36]^T", lambda: ops.gemm(g116, w_ext, transpose_w=True), 4 * N * (ld + C))
+if which in ("all", "tn"):
+    timeit("gemm_tn [N,36]^T[N,108] +colsum", lambda: ops.gemm_tn_ex(x, g108, transpose_out=True, want_colsum=True), 4 * N * (C + HC))
+    timeit("gemm_tn [N,36]^T[N,116]", lambda: ops.gemm_tn_ex(x, g116), 4 * N * (C + ld))
+    timeit("skinny_tn [N,36]^T[N,6]", lambda: ops.gemm_tn_ex(x, g116[:, 108:114]), 4 * N * (C + 6))
+if which in ("all", "edge"):
+    b = make_molecule_batch(4096, total_nodes=N, total_edges=221184, seed=1).to(dev)
+    g = graph.graph_index(b.edge_index, N); ea = g.sorted_edge_attr(b.edge_attr); E = b.num_edges
+    xpe = torch.randn(N, ld, device=dev); we = torch.randn(De, HC, device=dev); ae = torch.randn(De, H, device=dev)
+    timeit("edge_fwd", lambda: ops.triplet_edge_fwd(xpe, ea, we, ae, g, H, C, 0.2), 4 * (N * ld + N * HC + E * De + E * H) + 4 * (E + N))
+    aggo, alpha = ops.triplet_edge_fwd(xpe, ea, we, ae, g, H, C, 0.2)
+    timeit("edge_bwd (dst+src)", lambda: ops.triplet_edge_bwd(xpe, ea, we, ae, alpha, g108, g, H, C, 0.2), 4 * (2 * N * ld + 2 * N * HC + 2 * E * De + 5 * E * H) + 4 * (4 * E + 2 * N))
+    gi = torch.randn(N, 3 * C, device=dev); gh = torch.randn(N, 3 * C, device=dev); h = torch.randn(N, C, device=dev)
+    timeit("gru_gates_fwd", lambda: ops.gru_gates_fwd(gi.clone(), gh, h, x, 3, 1.0), 4 * N * C * 13)
