@@ -227,6 +227,8 @@ def run_ours(args):
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     _lib.load()                                      # fail loudly if the CUDA library is missing
+    # the LinearBlocks around the hot path are torch.nn.Linear: same operand format as the library's projections
+    torch.backends.cuda.matmul.allow_tf32 = _lib.get_math_mode() == "tf32"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:

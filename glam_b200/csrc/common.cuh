@@ -71,4 +71,13 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act, float p) {
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// out = sum over S partials (each `stride` floats, partial s at partial + s*stride) in a fixed order: block = 32 outputs x 8
+// slices; a thread adds its slices' partials in ascending s (4 loads in flight), the 8 slices are combined in order.
+// Element i < rows*cols goes to out[r*ldo + c] (or transposed); element i >= rows*cols goes to out2[i - rows*cols].
+__global__ void __launch_bounds__(256)
+reduce_partials_fixed_kernel(const float* __restrict__ partial, int S, int rows, int cols, int extra, float* __restrict__ out,
+                             int64_t ldo, int transpose_out, float* __restrict__ out2);
+int launch_reduce_partials(const float* partial, int S, int rows, int cols, int extra, float* out, int64_t ldo, int transpose_out,
+                           float* out2, cudaStream_t stream);
+
 }  // namespace glam

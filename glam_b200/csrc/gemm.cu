@@ -201,17 +201,27 @@ skinny_tn_kernel(const float* __restrict__ P, int64_t ldp, int Wp, const float* 
     for (int t = 0; t < KPL; ++t)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
-    for (int64_t m = mbeg + warp; m < mend; m += kSkinnyWarps) {
-        float q[8];
+    // 4 rows per iteration: 4 independent load groups in flight per warp
+    for (int64_t m0 = mbeg + warp; m0 < mend; m0 += 4 * kSkinnyWarps) {
+        float q[4][8], a[4][KPL];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) q[j] = j < Wq ? Q[m * ldq + j] : 0.f;
+        for (int u = 0; u < 4; ++u) {
+            const int64_t m = m0 + (int64_t)u * kSkinnyWarps;
+            const bool ok = m < mend;
 #pragma unroll
-        for (int t = 0; t < KPL; ++t) {
-            const int f = lane + 32 * t;
-            const float a = f < Wp ? P[m * ldp + f] : 0.f;
+            for (int j = 0; j < 8; ++j) q[u][j] = (ok && j < Wq) ? Q[m * ldq + j] : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(a, q[j], acc[t][j]);
+            for (int t = 0; t < KPL; ++t) {
+                const int f = lane + 32 * t;
+                a[u][t] = (ok && f < Wp) ? P[m * ldp + f] : 0.f;
+            }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int t = 0; t < KPL; ++t)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(a[u][t], q[u][j], acc[t][j]);
     }
 #pragma unroll
     for (int t = 0; t < KPL; ++t) {
@@ -266,7 +276,7 @@ static int tn_splits(int64_t M, int64_t Ka, int64_t Kb) {
     return (int)s;
 }
 static int colsum_splits(int64_t M) {
-    int64_t s = (M + 511) / 512;
+    int64_t s = (M + 63) / 64;
     if (s > 2 * kNumSMs) s = 2 * kNumSMs;
     if (s < 1) s = 1;
     return (int)s;
@@ -401,12 +411,19 @@ extern "C" int glam_gemm_tn_ex(const float* A, int64_t lda, const float* B, int6
         GLAM_CHECK_LAUNCH();
         // partial holds [Wp][Wq]; out is [Ka][Kb]: transposed w.r.t. the partial exactly when A is the narrow operand
         const int tr = (a_wide ? 0 : 1) ^ (transpose_out ? 1 : 0);
-        reduce4_kernel<<<(Wp * Wq + 63) / 64, 256, 0, stream>>>((const float*)workspace, S, Wp, Wq, out, ldo, tr);
-        GLAM_CHECK_LAUNCH();
-        return 0;
+        return launch_reduce_partials((const float*)workspace, S, Wp, Wq, 0, out, ldo, tr, nullptr, stream);
     }
     if (tc_gemm_tn_eligible(A, lda, B, ldb, M, Ka, Kb, colsum_b != nullptr))
         return tc_gemm_tn_launch(A, lda, B, ldb, M, Ka, Kb, out, ldo, transpose_out, colsum_b, workspace, stream);
+    if (colsum_b && tc_gemm_tn_eligible(A, lda, B, ldb, M, Ka, Kb, 0)) {
+        // B is too wide for the M side: product on the tensor cores, column sums by the exact reduction
+        if (int rc = tc_gemm_tn_launch(A, lda, B, ldb, M, Ka, Kb, out, ldo, transpose_out, nullptr, workspace, stream)) return rc;
+        const int S2 = colsum_splits(M);
+        int64_t rps2 = (M + S2 - 1) / S2;
+        colsum_partial_kernel<<<S2, dim3(32, 8), 0, stream>>>(B, ldb, M, (int)Kb, rps2, (float*)workspace);
+        GLAM_CHECK_LAUNCH();
+        return launch_reduce_partials((const float*)workspace, S2, 1, (int)Kb, 0, colsum_b, Kb, 0, nullptr, stream);
+    }
     const int S = tn_splits(M, Ka, Kb);
     const int tiles_a = (int)((Ka + BM - 1) / BM), tiles_b = (int)((Kb + BN - 1) / BN);
     int64_t rps = (M + S - 1) / S;

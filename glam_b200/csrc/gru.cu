@@ -86,9 +86,99 @@ __global__ void lstm_gates_bwd_kernel(const float* __restrict__ ga, const float*
     }
 }
 
+
+// ---- 16-byte vectorised variants (channels % 4 == 0, 16-byte aligned rows): one thread = 4 channels of one node ----
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+#define GLAM_F4_MAP(out, expr) { out.x = (expr(x)); out.y = (expr(y)); out.z = (expr(z)); out.w = (expr(w)); }
+
+__global__ void __launch_bounds__(256)
+gru_gates_fwd_vec_kernel(float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ h,
+                         const float* __restrict__ identity, int64_t N, int C, int act, float act_param,
+                         float* __restrict__ h_new, float* __restrict__ x_out) {
+    const int cq = C >> 2;
+    const int64_t total = N * cq;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = idx / cq;
+        const int c = (int)(idx - n * cq) << 2;
+        const int64_t b = n * 3 * C + c, o = n * C + c;
+        const float4 ir = ld4(gi + b), iz = ld4(gi + b + C), in = ld4(gi + b + 2 * C);
+        const float4 hr = ld4(gh + b), hz = ld4(gh + b + C), hn = ld4(gh + b + 2 * C);
+        const float4 hv = ld4(h + o);
+        float4 idv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (identity) idv = ld4(identity + o);
+        float4 r, z, nn, hnw, xo;
+#define R_(k) sigmoidf_(ir.k + hr.k)
+        GLAM_F4_MAP(r, R_)
+#define Z_(k) sigmoidf_(iz.k + hz.k)
+        GLAM_F4_MAP(z, Z_)
+#define N_(k) tanhf(in.k + r.k * hn.k)
+        GLAM_F4_MAP(nn, N_)
+#define H_(k) ((1.f - z.k) * nn.k + z.k * hv.k)
+        GLAM_F4_MAP(hnw, H_)
+#define X_(k) act_fwd(hnw.k + idv.k, act, act_param)
+        GLAM_F4_MAP(xo, X_)
+#undef R_
+#undef Z_
+#undef N_
+#undef H_
+#undef X_
+        st4(gi + b, r); st4(gi + b + C, z); st4(gi + b + 2 * C, nn);
+        st4(h_new + o, hnw);
+        st4(x_out + o, xo);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gru_gates_bwd_vec_kernel(const float* __restrict__ rzn, const float* __restrict__ gh, const float* __restrict__ h,
+                         const float* __restrict__ x_out, const float* __restrict__ g_x_out,
+                         const float* __restrict__ g_h_carry, int64_t N, int C, int act, float act_param,
+                         float* __restrict__ g_gi, float* __restrict__ g_gh, float* __restrict__ g_h_prev,
+                         float* __restrict__ g_identity) {
+    const int cq = C >> 2;
+    const int64_t total = N * cq;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = idx / cq;
+        const int c = (int)(idx - n * cq) << 2;
+        const int64_t b = n * 3 * C + c, o = n * C + c;
+        const float4 r = ld4(rzn + b), z = ld4(rzn + b + C), nn = ld4(rzn + b + 2 * C), ghn = ld4(gh + b + 2 * C), hv = ld4(h + o);
+        float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g_x_out) {
+            const float4 gx = ld4(g_x_out + o), xo = ld4(x_out + o);
+#define G_(k) (gx.k * act_grad_from_out(xo.k, act, act_param))
+            GLAM_F4_MAP(gs, G_)
+#undef G_
+        }
+        if (g_identity) st4(g_identity + o, gs);
+        float4 ghp = gs;
+        if (g_h_carry) { const float4 cr = ld4(g_h_carry + o); ghp.x += cr.x; ghp.y += cr.y; ghp.z += cr.z; ghp.w += cr.w; }
+        float4 gnp, gzp, grp, ghprev, gnr;
+#define NP_(k) (ghp.k * (1.f - z.k) * (1.f - nn.k * nn.k))
+        GLAM_F4_MAP(gnp, NP_)
+#define ZP_(k) (ghp.k * (hv.k - nn.k) * z.k * (1.f - z.k))
+        GLAM_F4_MAP(gzp, ZP_)
+#define RP_(k) (gnp.k * ghn.k * r.k * (1.f - r.k))
+        GLAM_F4_MAP(grp, RP_)
+#define HP_(k) (ghp.k * z.k)
+        GLAM_F4_MAP(ghprev, HP_)
+#define NR_(k) (gnp.k * r.k)
+        GLAM_F4_MAP(gnr, NR_)
+#undef NP_
+#undef ZP_
+#undef RP_
+#undef HP_
+#undef NR_
+        st4(g_h_prev + o, ghprev);
+        st4(g_gi + b, grp); st4(g_gi + b + C, gzp); st4(g_gi + b + 2 * C, gnp);
+        st4(g_gh + b, grp); st4(g_gh + b + C, gzp); st4(g_gh + b + 2 * C, gnr);
+    }
+}
+
+static bool al16(const void* p) { return p == nullptr || (((uintptr_t)p) & 15) == 0; }
+
 static int ew_grid(int64_t total) {
     int64_t g = (total + 255) / 256;
-    int64_t cap = (int64_t)kNumSMs * 8;
+    int64_t cap = (int64_t)kNumSMs * 16;
     if (g > cap) g = cap;
     return (int)(g < 1 ? 1 : g);
 }
@@ -102,7 +192,10 @@ extern "C" int glam_gru_gates_fwd(float* gi_rzn, const float* gh, const float* h
     GLAM_REQUIRE(N >= 0 && C > 0 && act >= 0 && act <= 3, "glam_gru_gates_fwd: bad arguments");
     if (N == 0) return 0;
     GLAM_REQUIRE(gi_rzn && gh && h && h_new && x_out, "glam_gru_gates_fwd: null pointer");
-    gru_gates_fwd_kernel<<<ew_grid(N * C), 256, 0, (cudaStream_t)stream_>>>(gi_rzn, gh, h, identity, N, C, act, act_param, h_new, x_out);
+    if ((C & 3) == 0 && al16(gi_rzn) && al16(gh) && al16(h) && al16(identity) && al16(h_new) && al16(x_out))
+        gru_gates_fwd_vec_kernel<<<ew_grid(N * C / 4), 256, 0, (cudaStream_t)stream_>>>(gi_rzn, gh, h, identity, N, C, act, act_param, h_new, x_out);
+    else
+        gru_gates_fwd_kernel<<<ew_grid(N * C), 256, 0, (cudaStream_t)stream_>>>(gi_rzn, gh, h, identity, N, C, act, act_param, h_new, x_out);
     GLAM_CHECK_LAUNCH();
     return 0;
 }
@@ -113,8 +206,13 @@ extern "C" int glam_gru_gates_bwd(const float* rzn, const float* gh, const float
     GLAM_REQUIRE(N >= 0 && C > 0 && act >= 0 && act <= 3, "glam_gru_gates_bwd: bad arguments");
     if (N == 0) return 0;
     GLAM_REQUIRE(rzn && gh && h && x_out && g_gi && g_gh && g_h_prev, "glam_gru_gates_bwd: null pointer");
-    gru_gates_bwd_kernel<<<ew_grid(N * C), 256, 0, (cudaStream_t)stream_>>>(rzn, gh, h, x_out, g_x_out, g_h_carry, N, C, act,
-                                                                            act_param, g_gi, g_gh, g_h_prev, g_identity);
+    if ((C & 3) == 0 && al16(rzn) && al16(gh) && al16(h) && al16(x_out) && al16(g_x_out) && al16(g_h_carry) && al16(g_gi) &&
+        al16(g_gh) && al16(g_h_prev) && al16(g_identity))
+        gru_gates_bwd_vec_kernel<<<ew_grid(N * C / 4), 256, 0, (cudaStream_t)stream_>>>(rzn, gh, h, x_out, g_x_out, g_h_carry, N, C, act,
+                                                                                    act_param, g_gi, g_gh, g_h_prev, g_identity);
+    else
+        gru_gates_bwd_kernel<<<ew_grid(N * C), 256, 0, (cudaStream_t)stream_>>>(rzn, gh, h, x_out, g_x_out, g_h_carry, N, C, act,
+                                                                                act_param, g_gi, g_gh, g_h_prev, g_identity);
     GLAM_CHECK_LAUNCH();
     return 0;
 }

@@ -247,10 +247,8 @@ int tc_gemm_tn_launch(const float* A, int64_t lda, const float* B, int64_t ldb, 
     GLAM_CHECK_LAUNCH();
     const int extra = colsum_b ? (int)Kb : 0;
     const int total = (int)(Ka * Kb) + extra;
-    tn_reduce_kernel<<<(total + 63) / 64, 256, 0, stream>>>((const float*)workspace, grid, (int)Ka, (int)Kb, extra, out, ldo,
-                                                           transpose_out ? 1 : 0, colsum_b);
-    GLAM_CHECK_LAUNCH();
-    return 0;
+    (void)total;
+    return launch_reduce_partials((const float*)workspace, grid, (int)Ka, (int)Kb, extra, out, ldo, transpose_out ? 1 : 0, colsum_b, stream);
 }
 
 }  // namespace glam

@@ -279,12 +279,20 @@ triplet_edge_bwd_dst_kernel(const float* __restrict__ xpe, int64_t ldxp, const f
     }
 }
 
-__global__ void reduce_cta_partials_kernel(const float* __restrict__ partial, int S, int count, float* __restrict__ out) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < S; ++k) s += partial[(int64_t)k * count + i];
-        out[i] = s;
+// out[i] = sum_s partial[s][i]: 64 outputs per CTA, the S range split over 4 thread rows combined in a fixed order
+__global__ void __launch_bounds__(256)
+reduce_cta_partials_kernel(const float* __restrict__ partial, int S, int count, float* __restrict__ out) {
+    __shared__ float red[4][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + tx;
+    float s = 0.f;
+    if (i < count) {
+        const int per = (S + 3) / 4, k0 = ty * per, k1 = min(S, k0 + per);
+        for (int k = k0; k < k1; ++k) s += partial[(int64_t)k * count + i];
     }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < count) out[i] = ((red[0][tx] + red[1][tx]) + red[2][tx]) + red[3][tx];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -379,6 +387,19 @@ static cudaError_t allow_smem(F fn, size_t bytes) {
     return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+bool edge_vec_eligible(const float* xpe, int64_t ldxp, int heads, int C, int De, const float* a1, const float* a2);
+int edge_vec_fwd(const float* xpe, int64_t ldxp, const float* ea, const float* w_edge, const float* att_edge,
+                 const int32_t* rowptr, const int32_t* srcs, int64_t N, int heads, int C, int De, float slope, float* agg,
+                 float* alpha, cudaStream_t stream);
+size_t edge_vec_bwd_workspace(int heads, int C, int De);
+int edge_vec_bwd_dst(const float* xpe, int64_t ldxp, const float* ea, const float* w_edge, const float* att_edge,
+                     const float* alpha, const float* g_agg, const int32_t* rowptr, const int32_t* srcs, int64_t N, int heads,
+                     int C, int De, float slope, float* g_logit, float* g_xpe, float* g_w_edge, void* workspace,
+                     cudaStream_t stream, int* grid_out);
+int edge_vec_bwd_src(const float* ea, const float* w_edge, const float* alpha, const float* g_agg, const float* g_logit,
+                     const int32_t* src_rowptr, const int32_t* src_pos, const int32_t* src_dst, int64_t N, int heads, int C,
+                     int De, float* g_xpe, int64_t ldxp, cudaStream_t stream);
+
 }  // namespace glam
 
 using namespace glam;
@@ -422,6 +443,8 @@ extern "C" int glam_triplet_edge_fwd(const float* xpe, int64_t ldxp, const float
     const int HC = heads * C, kpl = pick_kpl(HC);
     const size_t smem = sizeof(float) * ((use_ep ? De * HC : 0) + De * heads);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (edge_vec_eligible(xpe, ldxp, heads, C, De, agg, w_edge))
+        return edge_vec_fwd(xpe, ldxp, edge_attr, w_edge, att_edge, dst_rowptr, dst_src, N, heads, C, De, slope, agg, alpha, stream);
     GLAM_DISPATCH_EDGE(heads, use_ep, kpl, {
         auto fn = triplet_edge_fwd_kernel<HH_, KPL_, UE_>;
         allow_smem(fn, smem);
@@ -433,7 +456,9 @@ extern "C" int glam_triplet_edge_fwd(const float* xpe, int64_t ldxp, const float
 }
 
 extern "C" size_t glam_triplet_bwd_workspace_bytes(int heads, int channels, int edge_dim) {
-    return sizeof(float) * (size_t)kNumSMs * kEdgeCtasPerSM * (size_t)edge_dim * heads * channels;
+    size_t a = sizeof(float) * (size_t)kNumSMs * kEdgeCtasPerSM * (size_t)edge_dim * heads * channels;
+    size_t b = edge_vec_bwd_workspace(heads, channels, edge_dim);
+    return a > b ? a : b;
 }
 
 extern "C" int glam_triplet_edge_bwd_dst(const float* xpe, int64_t ldxp, const float* edge_attr, const float* w_edge,
@@ -453,6 +478,15 @@ extern "C" int glam_triplet_edge_bwd_dst(const float* xpe, int64_t ldxp, const f
                  "glam_triplet_edge_bwd_dst: null pointer");
     GLAM_REQUIRE(!use_ep || (g_w_edge && workspace && workspace_bytes >= glam_triplet_bwd_workspace_bytes(heads, C, De)),
                  "glam_triplet_edge_bwd_dst: g_w_edge/workspace missing or too small");
+    if (edge_vec_eligible(xpe, ldxp, heads, C, De, g_agg, w_edge)) {
+        int vgrid = 0;
+        if (int rc = edge_vec_bwd_dst(xpe, ldxp, edge_attr, w_edge, att_edge, alpha, g_agg, dst_rowptr, dst_src, N, heads, C, De,
+                                      slope, g_logit, g_xpe, g_w_edge, workspace, stream, &vgrid)) return rc;
+        if (use_ep) {
+            return launch_reduce_partials((const float*)workspace, vgrid, 1, De * HC, 0, g_w_edge, De * HC, 0, nullptr, stream);
+        }
+        return 0;
+    }
     const size_t smem = sizeof(float) * ((use_ep ? De * HC : 0) + De * heads + (use_ep ? kEdgeWarps * De * HC : 0));
     GLAM_REQUIRE(smem <= 200 * 1024, "glam_triplet_edge_bwd_dst: edge_dim*heads*channels too large for shared memory");
     const int grid = edge_grid(N);
@@ -464,8 +498,7 @@ extern "C" int glam_triplet_edge_bwd_dst(const float* xpe, int64_t ldxp, const f
     })
     GLAM_CHECK_LAUNCH();
     if (use_ep) {
-        reduce_cta_partials_kernel<<<(De * HC + 127) / 128, 128, 0, stream>>>((const float*)workspace, grid, De * HC, g_w_edge);
-        GLAM_CHECK_LAUNCH();
+        if (int rc = launch_reduce_partials((const float*)workspace, grid, 1, De * HC, 0, g_w_edge, De * HC, 0, nullptr, stream)) return rc;
     }
     return 0;
 }
@@ -482,6 +515,9 @@ extern "C" int glam_triplet_edge_bwd_src(const float* edge_attr, const float* w_
     const int HC = heads * C, kpl = pick_kpl(HC);
     const size_t smem = sizeof(float) * (use_ep ? De * HC : 0);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (edge_vec_eligible(g_xpe, ldxp, heads, C, De, g_agg, w_edge))
+        return edge_vec_bwd_src(edge_attr, w_edge, alpha, g_agg, g_logit, src_rowptr, src_pos, src_dst, N, heads, C, De, g_xpe, ldxp,
+                                stream);
     GLAM_DISPATCH_EDGE(heads, use_ep, kpl, {
         auto fn = triplet_edge_bwd_src_kernel<HH_, KPL_, UE_>;
         allow_smem(fn, smem);
