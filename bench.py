@@ -330,8 +330,13 @@ def run_ours(args):
                                               "(oracle/glam_oracle.py, all host threads)"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # all ranks leave together; the captured graph holds NCCL kernels, so drop it before the communicator and skip
+        # the (occasionally hanging) communicator teardown: the process is exiting anyway
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        del ts
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
