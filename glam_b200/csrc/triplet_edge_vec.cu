@@ -25,6 +25,27 @@ __device__ __forceinline__ float4 f4fma(float s, float4 a, float4 c) {
 }
 __device__ __forceinline__ float f4dot(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
 
+// edge_attr row summary: molecular bond features are one-hot, so e_ij = edge_attr . weight_edge is a single scaled row of
+// weight_edge; general rows (protein contact features) take the full De-term sum.
+struct EaRow { int nz, ty; float val; };
+__device__ __forceinline__ EaRow scan_ea(const float* __restrict__ row, int De) {
+    EaRow r{0, 0, 0.f};
+    for (int d = 0; d < De; ++d) {
+        const float e = row[d];
+        if (e != 0.f) { ++r.nz; r.ty = d; r.val = e; }
+    }
+    return r;
+}
+__device__ __forceinline__ float4 ep_chunk(const EaRow& r, const float* __restrict__ row, int De, const float4* We4, int nq, int q) {
+    if (r.nz == 1) {
+        const float4 w = We4[r.ty * nq + q];
+        return make_float4(r.val * w.x, r.val * w.y, r.val * w.z, r.val * w.w);
+    }
+    float4 ep = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int d = 0; d < De; ++d) ep = f4fma(row[d], We4[d * nq + q], ep);
+    return ep;
+}
+
 template <int H>
 __device__ __forceinline__ float pickh(const float (&a)[H], int h) {
     float v = a[0];
@@ -83,7 +104,9 @@ edge_alpha_fwd_kernel(const float* __restrict__ xpe, int64_t ld, const float* __
 }
 
 // ------------------------------------------------------------------------------------------------ aggregate (fwd)
-template <int H, int CPL, bool USE_EP>
+// G lanes per destination (32/G destinations per warp), each lane owns CPL 16-byte chunks (q = gl + G*t): the per-edge
+// scalar work (index, alpha, edge_attr loads) is amortised over CPL chunks instead of being repeated by every lane.
+template <int H, int G, int CPL, bool USE_EP>
 __global__ void __launch_bounds__(kVecThreads)
 edge_aggregate_fwd_kernel(const float* __restrict__ xpe, int64_t ld, const float* __restrict__ ea, const float* __restrict__ w_edge,
                           const float* __restrict__ alpha, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ srcs,
@@ -93,43 +116,261 @@ edge_aggregate_fwd_kernel(const float* __restrict__ xpe, int64_t ld, const float
     if (USE_EP)
         for (int i = threadIdx.x; i < De * nq; i += blockDim.x) We4[i] = ldg4(w_edge + 4 * i);
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane / G, gl = lane % G;
+    constexpr int kPerWarp = 32 / G;
     int hq[CPL];
 #pragma unroll
-    for (int t = 0; t < CPL; ++t) hq[t] = (4 * (lane + 32 * t)) / C;
+    for (int t = 0; t < CPL; ++t) hq[t] = (4 * (gl + G * t)) / C;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = warp0; i < N; i += nwarps) {
+    for (int64_t base = warp0 * kPerWarp; base < N; base += nwarps * kPerWarp) {
+        const int64_t i = base + sub;
+        if (i >= N) continue;
         const int beg = rowptr[i], end = rowptr[i + 1];
         float4 acc[CPL];
 #pragma unroll
         for (int t = 0; t < CPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int p = beg; p < end; ++p) {
-            const int64_t j = srcs[p];
-            float a[H];
+        // two edges per iteration: both gathers (2 x CPL 16-byte loads per lane) are in flight before any math
+        for (int p = beg; p < end; p += 2) {
+            const bool two = p + 1 < end;
+            const int p1 = two ? p + 1 : p;
+            const float* xj0 = xpe + (int64_t)srcs[p] * ld;
+            const float* xj1 = xpe + (int64_t)srcs[p1] * ld;
+            float a0[H], a1[H];
 #pragma unroll
-            for (int h = 0; h < H; ++h) a[h] = alpha[(int64_t)p * H + h];
+            for (int h = 0; h < H; ++h) { a0[h] = alpha[(int64_t)p * H + h]; a1[h] = two ? alpha[(int64_t)p1 * H + h] : 0.f; }
+            float4 m0[CPL], m1[CPL];
 #pragma unroll
             for (int t = 0; t < CPL; ++t) {
-                const int q = lane + 32 * t;
+                const int q = gl + G * t;
+                if (q < nq) { m0[t] = ldg4(xj0 + 4 * q); m1[t] = ldg4(xj1 + 4 * q); }
+            }
+            const float* ea0 = ea + (int64_t)p * De;
+            const float* ea1 = ea + (int64_t)p1 * De;
+            EaRow e0{0, 0, 0.f}, e1{0, 0, 0.f};
+            if (USE_EP) { e0 = scan_ea(ea0, De); e1 = scan_ea(ea1, De); }
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) {
+                const int q = gl + G * t;
                 if (q < nq) {
-                    float4 m = ldg4(xpe + j * ld + 4 * q);
-                    if (USE_EP) {
-                        float4 ep = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int d = 0; d < De; ++d) {
-                            const float ed = ea[(int64_t)p * De + d];
-                            if (ed != 0.f) ep = f4fma(ed, We4[d * nq + q], ep);
-                        }
-                        m = f4mul(m, ep);
-                    }
-                    acc[t] = f4fma(pickh<H>(a, hq[t]), m, acc[t]);
+                    float4 v0 = m0[t], v1 = m1[t];
+                    if (USE_EP) { v0 = f4mul(v0, ep_chunk(e0, ea0, De, We4, nq, q)); v1 = f4mul(v1, ep_chunk(e1, ea1, De, We4, nq, q)); }
+                    acc[t] = f4fma(pickh<H>(a0, hq[t]), v0, acc[t]);
+                    acc[t] = f4fma(pickh<H>(a1, hq[t]), v1, acc[t]);
                 }
             }
         }
 #pragma unroll
         for (int t = 0; t < CPL; ++t) {
-            const int q = lane + 32 * t;
+            const int q = gl + G * t;
             if (q < nq) *reinterpret_cast<float4*>(agg + i * HC + 4 * q) = acc[t];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ fused tile forward
+// One CTA owns a tile of 64 consecutive destinations.  The per-edge scalar work is done ONCE per edge by one thread
+// (coalesced index loads, s_j gather, edge_attr summary) into shared-memory records; a thread per destination runs the
+// softmax over its records; then sub-warp groups aggregate, reading the records as broadcasts and gathering x_j chunks
+// with two edges in flight.  Dependent global round trips per tile: rowptr -> (src, edge_attr) -> s_j -> x_j gathers.
+constexpr int kTileDst = 128;
+constexpr int kTileEdges = 1536;
+
+template <int H, int G, int CPL, bool USE_EP>
+__global__ void __launch_bounds__(kVecThreads)
+edge_tile_fwd_kernel(const float* __restrict__ xpe, int64_t ld, const float* __restrict__ ea, const float* __restrict__ w_edge,
+                     const float* __restrict__ att_edge, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ srcs,
+                     int64_t N, int C, int De, float slope, float* __restrict__ agg, float* __restrict__ alpha) {
+    extern __shared__ float4 We4[];                                   // [De][nq]
+    __shared__ float Ae[kVecMaxDe * H];
+    __shared__ int rec_src[kTileEdges], rec_ty[kTileEdges], rp[kTileDst + 1];
+    __shared__ float rec_val[kTileEdges], rec_a[kTileEdges][H];
+    const int HC = H * C, nq = HC >> 2;
+    if (USE_EP)
+        for (int i = threadIdx.x; i < De * nq; i += blockDim.x) We4[i] = ldg4(w_edge + 4 * i);
+    for (int i = threadIdx.x; i < De * H; i += blockDim.x) Ae[i] = att_edge[i];
+    const int tid = threadIdx.x, lane = tid & 31, grp = tid / G, gl = lane % G;
+    constexpr int kGroups = kVecThreads / G;
+    int hq[CPL];
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) hq[t] = (4 * (gl + G * t)) / C;
+    const int64_t ntiles = (N + kTileDst - 1) / kTileDst;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t t0 = tile * kTileDst;
+        const int nd = (int)min((int64_t)kTileDst, N - t0);
+        __syncthreads();                                              // previous tile's records are dead
+        if (tid <= nd) rp[tid] = rowptr[t0 + tid];
+        __syncthreads();
+        const int e0 = rp[0], ne = rp[nd] - e0;
+        if (ne > kTileEdges) {
+            // ---- oversized tile (hub destinations): per-destination routine straight from global memory
+            for (int d = tid; d < nd; d += blockDim.x) {
+                const int64_t i = t0 + d;
+                const int beg = rp[d], end = rp[d + 1];
+                float si[H], mx[H], sum[H];
+#pragma unroll
+                for (int h = 0; h < H; ++h) { si[h] = xpe[i * ld + HC + h]; mx[h] = -INFINITY; sum[h] = 0.f; }
+                for (int p = beg; p < end; ++p) {
+                    const int64_t j = srcs[p];
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        float l = si[h] + xpe[j * ld + HC + H + h];
+                        for (int dd = 0; dd < De; ++dd) l = fmaf(ea[(int64_t)p * De + dd], Ae[dd * H + h], l);
+                        l = l > 0.f ? l : slope * l;
+                        mx[h] = fmaxf(mx[h], l);
+                        alpha[(int64_t)p * H + h] = l;
+                    }
+                }
+                for (int p = beg; p < end; ++p)
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        const float e = expf(alpha[(int64_t)p * H + h] - mx[h]);
+                        alpha[(int64_t)p * H + h] = e;
+                        sum[h] += e;
+                    }
+                for (int p = beg; p < end; ++p)
+#pragma unroll
+                    for (int h = 0; h < H; ++h) alpha[(int64_t)p * H + h] = alpha[(int64_t)p * H + h] / (sum[h] + 1e-16f);
+            }
+            __syncthreads();
+            for (int d = grp; d < nd; d += kGroups) {
+                const int64_t i = t0 + d;
+                float4 acc[CPL];
+#pragma unroll
+                for (int t = 0; t < CPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int p = rp[d]; p < rp[d + 1]; ++p) {
+                    const float* xj = xpe + (int64_t)srcs[p] * ld;
+                    const float* earow = ea + (int64_t)p * De;
+                    EaRow er{0, 0, 0.f};
+                    if (USE_EP) er = scan_ea(earow, De);
+                    float a[H];
+#pragma unroll
+                    for (int h = 0; h < H; ++h) a[h] = alpha[(int64_t)p * H + h];
+#pragma unroll
+                    for (int t = 0; t < CPL; ++t) {
+                        const int q = gl + G * t;
+                        if (q < nq) {
+                            float4 m = ldg4(xj + 4 * q);
+                            if (USE_EP) m = f4mul(m, ep_chunk(er, earow, De, We4, nq, q));
+                            acc[t] = f4fma(pickh<H>(a, hq[t]), m, acc[t]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < CPL; ++t) {
+                    const int q = gl + G * t;
+                    if (q < nq) *reinterpret_cast<float4*>(agg + i * HC + 4 * q) = acc[t];
+                }
+            }
+            continue;
+        }
+        // ---- phase A: one thread per edge -> records (source, edge_attr summary, s_j + s_e part of the logit)
+        for (int e = tid; e < ne; e += blockDim.x) {
+            const int p = e0 + e;
+            const int j = srcs[p];
+            const float* earow = ea + (int64_t)p * De;
+            float l[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) l[h] = xpe[(int64_t)j * ld + HC + H + h];
+            int nz = 0, ty = 0;
+            float val = 0.f;
+            for (int d = 0; d < De; ++d) {
+                const float v = earow[d];
+                if (v != 0.f) { ++nz; ty = d; val = v; }
+#pragma unroll
+                for (int h = 0; h < H; ++h) l[h] = fmaf(v, Ae[d * H + h], l[h]);
+            }
+            rec_src[e] = j;
+            rec_ty[e] = nz == 1 ? ty : -1;
+            rec_val[e] = val;
+#pragma unroll
+            for (int h = 0; h < H; ++h) rec_a[e][h] = l[h];
+        }
+        __syncthreads();
+        // ---- phase B: one thread per destination -> PyG softmax over its records; alpha to global (saved for backward)
+        if (tid < nd) {
+            const int64_t i = t0 + tid;
+            const int beg = rp[tid] - e0, end = rp[tid + 1] - e0;
+            float si[H], mx[H], sum[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) { si[h] = xpe[i * ld + HC + h]; mx[h] = -INFINITY; sum[h] = 0.f; }
+            for (int e = beg; e < end; ++e)
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    float l = si[h] + rec_a[e][h];
+                    l = l > 0.f ? l : slope * l;
+                    rec_a[e][h] = l;
+                    mx[h] = fmaxf(mx[h], l);
+                }
+            for (int e = beg; e < end; ++e)
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const float x = expf(rec_a[e][h] - mx[h]);
+                    rec_a[e][h] = x;
+                    sum[h] += x;
+                }
+            for (int e = beg; e < end; ++e)
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const float a = rec_a[e][h] / (sum[h] + 1e-16f);
+                    rec_a[e][h] = a;
+                    alpha[(int64_t)(e0 + e) * H + h] = a;
+                }
+        }
+        __syncthreads();
+        // ---- phase C: sub-warp group per destination, lanes over 16-byte chunks, two edges in flight
+        for (int d = grp; d < nd; d += kGroups) {
+            const int64_t i = t0 + d;
+            const int beg = rp[d] - e0, end = rp[d + 1] - e0;
+            float4 acc[CPL];
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int e = beg; e < end; e += 2) {
+                const bool two = e + 1 < end;
+                const int e1 = two ? e + 1 : e;
+                const float* xj0 = xpe + (int64_t)rec_src[e] * ld;
+                const float* xj1 = xpe + (int64_t)rec_src[e1] * ld;
+                float4 m0[CPL], m1[CPL];
+#pragma unroll
+                for (int t = 0; t < CPL; ++t) {
+                    const int q = gl + G * t;
+                    if (q < nq) { m0[t] = ldg4(xj0 + 4 * q); m1[t] = ldg4(xj1 + 4 * q); }
+                }
+                float a0[H], a1[H];
+#pragma unroll
+                for (int h = 0; h < H; ++h) { a0[h] = rec_a[e][h]; a1[h] = two ? rec_a[e1][h] : 0.f; }
+                const int ty0 = rec_ty[e], ty1 = rec_ty[e1];
+                const float v0 = rec_val[e], v1 = rec_val[e1];
+#pragma unroll
+                for (int t = 0; t < CPL; ++t) {
+                    const int q = gl + G * t;
+                    if (q < nq) {
+                        float4 x0 = m0[t], x1 = m1[t];
+                        float c0 = pickh<H>(a0, hq[t]), c1 = pickh<H>(a1, hq[t]);
+                        if (USE_EP) {
+                            if (ty0 >= 0) { x0 = f4mul(x0, We4[ty0 * nq + q]); c0 *= v0; }
+                            else {
+                                float4 ep = make_float4(0.f, 0.f, 0.f, 0.f);
+                                for (int dd = 0; dd < De; ++dd) ep = f4fma(ea[(int64_t)(e0 + e) * De + dd], We4[dd * nq + q], ep);
+                                x0 = f4mul(x0, ep);
+                            }
+                            if (ty1 >= 0) { x1 = f4mul(x1, We4[ty1 * nq + q]); c1 *= v1; }
+                            else {
+                                float4 ep = make_float4(0.f, 0.f, 0.f, 0.f);
+                                for (int dd = 0; dd < De; ++dd) ep = f4fma(ea[(int64_t)(e0 + e1) * De + dd], We4[dd * nq + q], ep);
+                                x1 = f4mul(x1, ep);
+                            }
+                        }
+                        acc[t] = f4fma(c0, x0, acc[t]);
+                        acc[t] = f4fma(c1, x1, acc[t]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) {
+                const int q = gl + G * t;
+                if (q < nq) *reinterpret_cast<float4*>(agg + i * HC + 4 * q) = acc[t];
+            }
         }
     }
 }
@@ -175,6 +416,9 @@ edge_dots_bwd_kernel(const float* __restrict__ xpe, int64_t ld, const float* __r
             float a[H], part[H];
 #pragma unroll
             for (int h = 0; h < H; ++h) { a[h] = alpha[(int64_t)p * H + h]; part[h] = 0.f; }
+            const float* earow = ea + (int64_t)p * De;
+            EaRow er{0, 0, 0.f};
+            if (USE_EP) er = scan_ea(earow, De);
 #pragma unroll
             for (int t = 0; t < CPL; ++t) {
                 const int q = lane + 32 * t;
@@ -182,19 +426,19 @@ edge_dots_bwd_kernel(const float* __restrict__ xpe, int64_t ld, const float* __r
                     const float4 gm = f4mul(ga[t], ldg4(xpe + j * ld + 4 * q));
                     float v;
                     if (USE_EP) {
-                        float4 ep = make_float4(0.f, 0.f, 0.f, 0.f);
                         const float ah = pickh<H>(a, hq[t]);
+                        v = f4dot(gm, ep_chunk(er, earow, De, We4, nq, q));
+                        if (er.nz == 1) {
+                            // one-hot bond feature: a single weight_edge row receives this edge's gradient
+                            const float c = er.val * ah;
 #pragma unroll
-                        for (int d = 0; d < kVecMaxDe; ++d) {
-                            if (d < De) {
-                                const float ed = ea[(int64_t)p * De + d];
-                                if (ed != 0.f) {
-                                    ep = f4fma(ed, We4[d * nq + q], ep);
-                                    gw[d][t] = f4fma(ed * ah, gm, gw[d][t]);
-                                }
-                            }
+                            for (int d = 0; d < kVecMaxDe; ++d)
+                                if (d == er.ty) gw[d][t] = f4fma(c, gm, gw[d][t]);
+                        } else {
+#pragma unroll
+                            for (int d = 0; d < kVecMaxDe; ++d)
+                                if (d < De) gw[d][t] = f4fma(earow[d] * ah, gm, gw[d][t]);
                         }
-                        v = f4dot(gm, ep);
                     } else {
                         v = gm.x + gm.y + gm.z + gm.w;
                     }
@@ -273,7 +517,7 @@ edge_softmax_bwd_kernel(const float* __restrict__ xpe, int64_t ld, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------ backward 3: scatter by source
-template <int H, int CPL, bool USE_EP>
+template <int H, int G, int CPL, bool USE_EP>
 __global__ void __launch_bounds__(kVecThreads)
 edge_source_bwd_kernel(const float* __restrict__ ea, const float* __restrict__ w_edge, const float* __restrict__ alpha,
                        const float* __restrict__ g_agg, const float* __restrict__ g_logit, const int32_t* __restrict__ src_rowptr,
@@ -284,13 +528,16 @@ edge_source_bwd_kernel(const float* __restrict__ ea, const float* __restrict__ w
     if (USE_EP)
         for (int i = threadIdx.x; i < De * nq; i += blockDim.x) We4[i] = ldg4(w_edge + 4 * i);
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane / G, gl = lane % G;
+    constexpr int kPerWarp = 32 / G;
     int hq[CPL];
 #pragma unroll
-    for (int t = 0; t < CPL; ++t) hq[t] = (4 * (lane + 32 * t)) / C;
+    for (int t = 0; t < CPL; ++t) hq[t] = (4 * (gl + G * t)) / C;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t j = warp0; j < N; j += nwarps) {
+    for (int64_t base = warp0 * kPerWarp; base < N; base += nwarps * kPerWarp) {
+        const int64_t j = base + sub;
+        if (j >= N) continue;
         const int beg = src_rowptr[j], end = src_rowptr[j + 1];
         float4 acc[CPL];
 #pragma unroll
@@ -298,24 +545,20 @@ edge_source_bwd_kernel(const float* __restrict__ ea, const float* __restrict__ w
         float gsj = 0.f;
         for (int k = beg; k < end; ++k) {
             const int p = src_pos[k];
-            const int64_t i = src_dst[k];
+            const float* gi = g_agg + (int64_t)src_dst[k] * HC;
             float a[H];
 #pragma unroll
             for (int h = 0; h < H; ++h) a[h] = alpha[(int64_t)p * H + h];
-            if (lane < H) gsj += g_logit[(int64_t)p * H + lane];
+            if (gl < H) gsj += g_logit[(int64_t)p * H + gl];
+            const float* earow = ea + (int64_t)p * De;
+            EaRow er{0, 0, 0.f};
+            if (USE_EP) er = scan_ea(earow, De);
 #pragma unroll
             for (int t = 0; t < CPL; ++t) {
-                const int q = lane + 32 * t;
+                const int q = gl + G * t;
                 if (q < nq) {
-                    float4 m = ldg4(g_agg + i * HC + 4 * q);
-                    if (USE_EP) {
-                        float4 ep = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int d = 0; d < De; ++d) {
-                            const float ed = ea[(int64_t)p * De + d];
-                            if (ed != 0.f) ep = f4fma(ed, We4[d * nq + q], ep);
-                        }
-                        m = f4mul(m, ep);
-                    }
+                    float4 m = ldg4(gi + 4 * q);
+                    if (USE_EP) m = f4mul(m, ep_chunk(er, earow, De, We4, nq, q));
                     acc[t] = f4fma(pickh<H>(a, hq[t]), m, acc[t]);
                 }
             }
@@ -323,11 +566,11 @@ edge_source_bwd_kernel(const float* __restrict__ ea, const float* __restrict__ w
         float* out = g_xpe + j * ld;
 #pragma unroll
         for (int t = 0; t < CPL; ++t) {
-            const int q = lane + 32 * t;
+            const int q = gl + G * t;
             if (q < nq) *reinterpret_cast<float4*>(out + 4 * q) = acc[t];
         }
-        if (lane < H) out[HC + H + lane] = gsj;
-        for (int k = HC + 2 * H + lane; k < ld; k += 32) out[k] = 0.f;
+        if (gl < H) out[HC + H + gl] = gsj;
+        for (int k = HC + 2 * H + gl; k < ld; k += G) out[k] = 0.f;
     }
 }
 
@@ -352,6 +595,24 @@ bool edge_vec_eligible(const float* xpe, int64_t ldxp, int heads, int C, int De,
     return true;
 }
 
+// sub-warp geometry: G lanes per destination, CPL chunks per lane  (nq = H*C/4 chunks per row)
+static void vec_geometry(int nq, int* G, int* cpl) {
+    if (nq <= 32) { *G = 8; *cpl = 4; } else if (nq <= 64) { *G = 16; *cpl = 4; } else { *G = 32; *cpl = 3; }
+}
+#define GLAM_VEC_GEO(H_, EP_, g, ...)                                              \
+    switch (g) {                                                                   \
+        case 8: { constexpr int HH_ = H_, G_ = 8, CPL_ = 4; constexpr bool UE_ = EP_; __VA_ARGS__; } break;   \
+        case 16: { constexpr int HH_ = H_, G_ = 16, CPL_ = 4; constexpr bool UE_ = EP_; __VA_ARGS__; } break; \
+        default: { constexpr int HH_ = H_, G_ = 32, CPL_ = 3; constexpr bool UE_ = EP_; __VA_ARGS__; } break; \
+    }
+#define GLAM_VEC_GDISPATCH(heads, use_ep, g, ...)                       \
+    if (!(use_ep)) { GLAM_VEC_GEO(1, false, g, __VA_ARGS__) }           \
+    else switch (heads) {                                               \
+        case 1: GLAM_VEC_GEO(1, true, g, __VA_ARGS__) break;            \
+        case 2: GLAM_VEC_GEO(2, true, g, __VA_ARGS__) break;            \
+        case 3: GLAM_VEC_GEO(3, true, g, __VA_ARGS__) break;            \
+        default: GLAM_VEC_GEO(4, true, g, __VA_ARGS__) break;           \
+    }
 #define GLAM_VEC_CPL(H_, EP_, cpl, ...)                                            \
     switch (cpl) {                                                                 \
         case 1: { constexpr int HH_ = H_, CPL_ = 1; constexpr bool UE_ = EP_; __VA_ARGS__; } break; \
@@ -383,16 +644,17 @@ int edge_vec_fwd(const float* xpe, int64_t ldxp, const float* ea, const float* w
                  const int32_t* rowptr, const int32_t* srcs, int64_t N, int heads, int C, int De, float slope, float* agg,
                  float* alpha, cudaStream_t stream) {
     const bool use_ep = w_edge != nullptr;
-    const int HC = heads * C, nq = HC / 4, cpl = (nq + 31) / 32;
-    GLAM_VEC_HEADS(heads, {
-        edge_alpha_fwd_kernel<HH_><<<vec_thread_grid(N), 256, 0, stream>>>(xpe, ldxp, ea, att_edge, rowptr, srcs, N, HC, De, slope, alpha);
-    })
-    GLAM_CHECK_LAUNCH();
+    const int HC = heads * C, nq = HC / 4;
     const size_t smem = use_ep ? sizeof(float4) * De * nq : 0;
-    GLAM_VEC_DISPATCH(heads, use_ep, cpl, {
-        auto fn = edge_aggregate_fwd_kernel<HH_, CPL_, UE_>;
+    int G, gcpl;
+    vec_geometry(nq, &G, &gcpl);
+    const int64_t ntiles = (N + kTileDst - 1) / kTileDst;
+    int64_t grid = (int64_t)kNumSMs * 4;
+    if (grid > ntiles) grid = ntiles;
+    GLAM_VEC_GDISPATCH(heads, use_ep, G, {
+        auto fn = edge_tile_fwd_kernel<HH_, G_, CPL_, UE_>;
         vec_allow_smem(fn, smem);
-        fn<<<vec_warp_grid(N), kVecThreads, smem, stream>>>(xpe, ldxp, ea, w_edge, alpha, rowptr, srcs, N, C, De, agg);
+        fn<<<(unsigned)grid, kVecThreads, smem, stream>>>(xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, N, C, De, slope, agg, alpha);
     })
     GLAM_CHECK_LAUNCH();
     return 0;
@@ -431,11 +693,13 @@ int edge_vec_bwd_src(const float* ea, const float* w_edge, const float* alpha, c
     const bool use_ep = w_edge != nullptr;
     const int HC = heads * C, nq = HC / 4, cpl = (nq + 31) / 32;
     const size_t smem = use_ep ? sizeof(float4) * De * nq : 0;
-    GLAM_VEC_DISPATCH(heads, use_ep, cpl, {
-        auto fn = edge_source_bwd_kernel<HH_, CPL_, UE_>;
+    int G, gcpl;
+    vec_geometry(nq, &G, &gcpl);
+    GLAM_VEC_GDISPATCH(heads, use_ep, G, {
+        auto fn = edge_source_bwd_kernel<HH_, G_, CPL_, UE_>;
         vec_allow_smem(fn, smem);
-        fn<<<vec_warp_grid(N), kVecThreads, smem, stream>>>(ea, w_edge, alpha, g_agg, g_logit, src_rowptr, src_pos, src_dst, N, C, De,
-                                                            g_xpe, ldxp);
+        fn<<<vec_warp_grid((N + 32 / G_ - 1) / (32 / G_)), kVecThreads, smem, stream>>>(ea, w_edge, alpha, g_agg, g_logit, src_rowptr, src_pos,
+                                                                                        src_dst, N, C, De, g_xpe, ldxp);
     })
     GLAM_CHECK_LAUNCH();
     return 0;

@@ -17,6 +17,50 @@ def _c(t):
 
 
 # --------------------------------------------------------------------------------------------------
+# side stream for weight gradients: they are off the critical path of backward (nothing downstream in the same
+# step consumes them), and each is a latency-bound streaming kernel, so they overlap with the dgrad chain.
+# Every fork starts with side.wait_stream(main) and backward joins before returning, which also keeps the caching
+# allocator's stream-ordered reuse valid.  Works under CUDA-graph capture (fork/join become graph branches).
+# --------------------------------------------------------------------------------------------------
+_side_streams = {}
+OVERLAP_WGRAD = True
+
+
+class _Side:
+    """with _Side(t): ... runs the body on the device's side stream after everything enqueued so far on the
+    current stream."""
+
+    def __init__(self, ref: torch.Tensor):
+        self.dev = ref.device
+        self.on = OVERLAP_WGRAD and ref.is_cuda
+
+    def __enter__(self):
+        if not self.on:
+            return self
+        self.main = torch.cuda.current_stream(self.dev)
+        side = _side_streams.get(self.dev)
+        if side is None:
+            side = _side_streams[self.dev] = torch.cuda.Stream(device=self.dev)
+        self.side = side
+        side.wait_stream(self.main)
+        self.ctx = torch.cuda.stream(side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.on:
+            self.ctx.__exit__(*a)
+        return False
+
+
+def _join(ref: torch.Tensor):
+    if OVERLAP_WGRAD and ref.is_cuda:
+        side = _side_streams.get(ref.device)
+        if side is not None:
+            torch.cuda.current_stream(ref.device).wait_stream(side)
+
+
+# --------------------------------------------------------------------------------------------------
 # shared forward/backward pieces
 # --------------------------------------------------------------------------------------------------
 def _conv_fwd(x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels, slope, epilogue):
@@ -30,17 +74,20 @@ def _conv_fwd(x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels,
 def _conv_bwd(g_pre, x, w_ext, w_edge, att_edge, w_scale, xpe, agg, alpha, ea, g, heads, channels, slope):
     """g_pre: gradient w.r.t. the layer output before any activation ([N,C], or [N,HC] for the Light layer)."""
     if w_scale is not None:
+        with _Side(g_pre):
+            g_w_scale, g_bias = ops.gemm_tn_ex(agg, g_pre, want_colsum=True)
         g_agg = ops.gemm(g_pre, w_scale, transpose_w=True)                     # [N,HC]
-        g_w_scale, g_bias = ops.gemm_tn_ex(agg, g_pre, want_colsum=True)
     else:
         g_agg, g_w_scale, g_bias = g_pre, None, None
     g_xpe, g_logit, g_w_edge = ops.triplet_edge_bwd(xpe, ea, w_edge, att_edge, alpha, g_agg, g, heads, channels, slope)
-    g_att_edge, _ = ops.gemm_tn_ex(ea, g_logit)                                # [De,H]
+    with _Side(g_xpe):
+        g_att_edge, _ = ops.gemm_tn_ex(ea, g_logit)                            # [De,H]
+        g_w_ext, _ = ops.gemm_tn_ex(x, g_xpe)                                  # [C,ldxp]
+        # the 2H logit columns are near-total cancellations (softmax gradients are zero-sum per destination): exact fp32
+        hc = heads * channels
+        ops.gemm_tn_ex(x, g_xpe[:, hc:hc + 2 * heads], out=g_w_ext[:, hc:hc + 2 * heads])
     g_x = ops.gemm(g_xpe, w_ext, transpose_w=True)                             # [N,C]
-    g_w_ext, _ = ops.gemm_tn_ex(x, g_xpe)                                      # [C,ldxp]
-    # the 2H logit columns are near-total cancellations (softmax gradients are zero-sum per destination): exact fp32
-    hc = heads * channels
-    ops.gemm_tn_ex(x, g_xpe[:, hc:hc + 2 * heads], out=g_w_ext[:, hc:hc + 2 * heads])
+    _join(g_x)
     return g_x, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias
 
 
@@ -53,13 +100,14 @@ def _gru_fwd(m, h, identity, w_ih, w_hh, b_ih, b_hh, act, act_param):
 
 def _gru_bwd(g_x_out, g_h_new, rzn, gh, h, m, x_out, w_ih, w_hh, act, act_param, want_identity, celu_aux):
     g_gi, g_gh, g_h_prev, g_id = ops.gru_gates_bwd(rzn, gh, h, x_out, g_x_out, g_h_new, act, act_param, want_identity)
+    with _Side(g_gi):
+        g_w_ih, g_b_ih = ops.gemm_tn_ex(m, g_gi, transpose_out=True, want_colsum=True)     # (m^T g_gi)^T = [3C,C]
+        g_w_hh, g_b_hh = ops.gemm_tn_ex(h, g_gh, transpose_out=True, want_colsum=True)
     if celu_aux is not None:                                                   # m = celu(pre): return d/d pre
         g_m = ops.gemm(g_gi, w_ih, epilogue=EPI_MUL_CELU_GRAD, aux=celu_aux)
     else:
         g_m = ops.gemm(g_gi, w_ih)
     ops.gemm(g_gh, w_hh, epilogue=EPI_ACCUM, out=g_h_prev)
-    g_w_ih, g_b_ih = ops.gemm_tn_ex(m, g_gi, transpose_out=True, want_colsum=True)     # (m^T g_gi)^T = [3C,C]
-    g_w_hh, g_b_hh = ops.gemm_tn_ex(h, g_gh, transpose_out=True, want_colsum=True)
     return g_m, g_h_prev, g_id, g_w_ih, g_w_hh, g_b_ih, g_b_hh
 
 
@@ -108,6 +156,7 @@ class GRUUpdateFn(Function):
         act, act_param, has_id = ctx.cfg
         g_m, g_h, g_id, g_w_ih, g_w_hh, g_b_ih, g_b_hh = _gru_bwd(
             _c(g_x_out), _c(g_h_new), rzn, gh, h, m, x_out, w_ih, w_hh, act, act_param, has_id, None)
+        _join(g_m)
         return g_m, g_h, g_id, g_w_ih, g_w_hh, g_b_ih, g_b_hh, None, None
 
 
