@@ -195,25 +195,53 @@ def kernel_bytes_model(label, N, E, B, C=36, H=3, De=3):
 
 
 def profile_kernels(ts, dev_batches, reps):
-    """Eager (un-graphed) training steps with a CUDA-event pair around every C-ABI call on the launching stream."""
-    from glam_b200 import ops, graph as G
+    """Eager (un-graphed) training steps with a CUDA-event pair around every C-ABI call on the launching stream.
+    Each step starts with a ~15 ms device-side sleep so that the host has enqueued the whole step before the GPU
+    reaches it: the event intervals are then pure device time, not host launch latency."""
+    from glam_b200 import ops, graph as G, functional as Fn
     sink = []
-    ops.set_profile(sink)
     world, ts.world = ts.world, 1                    # rank-local measurement: no collective here
+    overlap, Fn.OVERLAP_WGRAD = Fn.OVERLAP_WGRAD, False   # one stream: every interval is one kernel family, nothing concurrent
     try:
         for i in range(reps):
             ts.load(dev_batches[i % len(dev_batches)])
             G.clear_caches()
+            torch.cuda.synchronize()
+            torch.cuda._sleep(30_000_000)
+            ops.set_profile(sink)
             ts._body()
+            ops.set_profile(None)
         torch.cuda.synchronize()
     finally:
         ops.set_profile(None)
         ts.world = world
+        Fn.OVERLAP_WGRAD = overlap
     agg = {}
     for name, e0, e1 in sink:
         t, n = agg.get(name, (0.0, 0))
         agg[name] = (t + e0.elapsed_time(e1), n + 1)
     return {k: (t / reps, n // reps, t / n) for k, (t, n) in agg.items()}     # ms per step, launches per step, ms per launch
+
+
+def screening_throughput(net, rank, dev, graphs=16384, n_batches=4, steps=12, warmup=3):
+    """BASELINE.json configs[4] shape per GPU: eval-mode forward (virtual screening) on `graphs`-graph batches, inputs
+    resident in HBM, CUDA-graph replay; graphs shard by molecule across ranks with no collective."""
+    from glam_b200.engine import ScreenStep
+    from glam_b200.synth import make_molecule_batch
+    batches = [make_molecule_batch(graphs, seed=5000 + 100 * rank + i, total_nodes=25 * graphs, total_edges=54 * graphs,
+                                   **DIMS).to(dev) for i in range(n_batches)]
+    ss = ScreenStep(net, batches[0], device=dev)
+    for i in range(warmup):
+        ss.step(batches[i % n_batches])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        ss.step(batches[i % n_batches])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return graphs / (ms * 1e-3), ms
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -303,6 +331,15 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
             "cuda_graph": captured, "final_loss": losses[-1] if losses else None}
 
+    # ---- screening (forward only, eval mode): second half of BASELINE.json's metric; every rank, no collective
+    scr_gps, scr_ms = screening_throughput(net, rank, dev)
+    if world > 1:
+        t = torch.tensor([scr_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        scr_gps, scr_ms = 16384 / (float(t) * 1e-3), float(t)
+    line["screening"] = {"value": scr_gps * world, "unit": UNIT, "graphs_per_gpu_batch": 16384, "ms_per_batch": scr_ms,
+                         "note": "eval-mode forward, inputs resident in HBM, graphs sharded by molecule, no collective"}
+
     if rank == 0:
         # ---- roofline of the dominant kernel: CUDA events around every library call, eager, same inputs
         prof = profile_kernels(ts, resident, reps=3)
@@ -316,8 +353,13 @@ def run_ours(args):
         nbytes = kernel_bytes_model(top[0], TOTAL_NODES, TOTAL_EDGES, GRAPHS)
         total_ms = sum(v[0] for v in prof.values())
         achieved = (nbytes / (top[1][2] * 1e-3) / 1e9) if nbytes else None
+        traffic = None
+        try:                                             # dram__bytes_read+write per launch from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top[0])
+        except (OSError, ValueError):
+            pass
         line["roofline"] = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": (achieved / peak) if achieved else None, "traffic": None,
+                            "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                             "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
                             "ms_per_launch": top[1][2], "launches_per_step": top[1][1],
                             "share_of_library_time": top[1][0] / total_ms, "algorithmic_bytes_per_launch": nbytes}

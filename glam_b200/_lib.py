@@ -24,7 +24,7 @@ SIGNATURES = {
     "glam_set_math_mode": (I32, [I32]),
     "glam_get_math_mode": (I32, []),
     "glam_csr_workspace_bytes": (SZ, [I64, I64]),
-    "glam_build_csr": (I32, [P, I64, I64, P, P, P, P, P, P, P, SZ, P]),
+    "glam_build_csr": (I32, [P, I64, I64, P, P, P, P, P, P, P, P, SZ, P]),
     "glam_graph_ptr": (I32, [P, I64, I64, P, P]),
     "glam_gather_rows": (I32, [P, P, I64, I64, P, P]),
     "glam_gemm": (I32, [P, I64, P, I64, I64, P, P, I64, P, I64, I64, I64, I64, I32, P]),
@@ -37,7 +37,7 @@ SIGNATURES = {
     "glam_colsum": (I32, [P, I64, I64, I64, P, P, SZ, P]),
     "glam_triplet_edge_fwd": (I32, [P, I64, P, P, P, P, P, I64, I64, I32, I32, I32, F32, P, P, P]),
     "glam_triplet_bwd_workspace_bytes": (SZ, [I32, I32, I32]),
-    "glam_triplet_edge_bwd_dst": (I32, [P, I64, P, P, P, P, P, P, P, I64, I64, I32, I32, I32, F32, P, P, P, P, SZ, P]),
+    "glam_triplet_edge_bwd_dst": (I32, [P, I64, P, P, P, P, P, P, P, P, I64, I64, I32, I32, I32, F32, P, P, P, P, SZ, P]),
     "glam_triplet_edge_bwd_src": (I32, [P, P, P, P, P, P, P, P, I64, I64, I32, I32, I32, P, I64, P]),
     "glam_triplet_prep_fwd": (I32, [P, P, P, I32, I32, I32, I32, I32, P, P, P]),
     "glam_triplet_prep_bwd": (I32, [P, P, P, P, P, P, I32, I32, I32, I32, I32, P, P, P, P]),

@@ -151,7 +151,7 @@ __global__ void csr_fill_kernel(const int64_t* __restrict__ edge_index, int64_t 
 // One warp per node: rank-sort the bucket by edge id (ids are unique) and emit the final arrays.
 __global__ void csr_sort_kernel(const int64_t* __restrict__ edge_index, int64_t E, int64_t N,
                                 const int32_t* __restrict__ rowptr2, const int32_t* __restrict__ tmp,
-                                int32_t* dst_perm, int32_t* dst_src, int32_t* inv_dst, int32_t* src_perm) {
+                                int32_t* dst_perm, int32_t* dst_src, int32_t* dst_dst, int32_t* inv_dst, int32_t* src_perm) {
     const int which = blockIdx.y;
     const int32_t* rp = rowptr2 + (int64_t)which * (N + 1);
     const int32_t* t = tmp + (int64_t)which * E;
@@ -166,7 +166,7 @@ __global__ void csr_sort_kernel(const int64_t* __restrict__ edge_index, int64_t 
             for (int k = 0; k < deg; ++k) rank += (__shfl_sync(0xffffffffu, v, k) < v);
             if (lane < deg) {
                 int p = beg + rank;
-                if (which == 0) { dst_perm[p] = v; dst_src[p] = (int32_t)edge_index[v]; inv_dst[v] = p; }
+                if (which == 0) { dst_perm[p] = v; dst_src[p] = (int32_t)edge_index[v]; inv_dst[v] = p; if (dst_dst) dst_dst[p] = (int32_t)i; }
                 else src_perm[p] = v;
             }
         } else {
@@ -175,7 +175,7 @@ __global__ void csr_sort_kernel(const int64_t* __restrict__ edge_index, int64_t 
                 int rank = 0;
                 for (int k = 0; k < deg; ++k) rank += (t[beg + k] < v);
                 int p = beg + rank;
-                if (which == 0) { dst_perm[p] = v; dst_src[p] = (int32_t)edge_index[v]; inv_dst[v] = p; }
+                if (which == 0) { dst_perm[p] = v; dst_src[p] = (int32_t)edge_index[v]; inv_dst[v] = p; if (dst_dst) dst_dst[p] = (int32_t)i; }
                 else src_perm[p] = v;
             }
         }
@@ -229,7 +229,7 @@ extern "C" size_t glam_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges)
 }
 
 extern "C" int glam_build_csr(const int64_t* edge_index, int64_t E, int64_t N, int32_t* dst_rowptr, int32_t* dst_src,
-                              int32_t* dst_perm, int32_t* src_rowptr, int32_t* src_pos, int32_t* src_dst,
+                              int32_t* dst_perm, int32_t* dst_dst, int32_t* src_rowptr, int32_t* src_pos, int32_t* src_dst,
                               void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GLAM_REQUIRE(N >= 0 && E >= 0, "glam_build_csr: negative sizes");
@@ -257,7 +257,7 @@ extern "C" int glam_build_csr(const int64_t* edge_index, int64_t E, int64_t N, i
         csr_fill_kernel<<<dim3(grid_for(E, 256), 2), 256, 0, stream>>>(edge_index, E, N, w.counts, w.cursor, w.tmp);
         GLAM_CHECK_LAUNCH();
         csr_sort_kernel<<<dim3(grid_for(N * 32, 256), 2), 256, 0, stream>>>(edge_index, E, N, w.counts, w.tmp, dst_perm, dst_src,
-                                                                          w.inv_dst, w.src_perm);
+                                                                          dst_dst, w.inv_dst, w.src_perm);
         GLAM_CHECK_LAUNCH();
         csr_src_finish_kernel<<<grid_for(E, 256), 256, 0, stream>>>(edge_index, E, w.src_perm, w.inv_dst, src_pos, src_dst);
         GLAM_CHECK_LAUNCH();

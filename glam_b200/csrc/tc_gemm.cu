@@ -38,7 +38,146 @@ struct TcGemmParams {
     int64_t M; int N, K, epi;
     int KP, Npad, tmem_cols, vec_store, stages, staged_out;
     int exact_begin, exact_end;   // output columns computed with exact fp32 FMAs (attention-logit columns)
+    unsigned long long* dbg;      // optional phase timestamps of CTA 0 (globaltimer ns), 8 slots
 };
+
+
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define GLAM_DBG(slot) do { if (p.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0) p.dbg[slot] = gtime(); } while (0)
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
+template <int EPI>
+__device__ __forceinline__ float4 epi_apply(float4 v, float4 b, float4 y) {
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    if (EPI == EPI_CELU) { v.x = celu1(v.x); v.y = celu1(v.y); v.z = celu1(v.z); v.w = celu1(v.w); }
+    else if (EPI == EPI_MUL_CELU_GRAD) {
+        v.x *= (y.x > 0.f ? 1.f : y.x + 1.f); v.y *= (y.y > 0.f ? 1.f : y.y + 1.f);
+        v.z *= (y.z > 0.f ? 1.f : y.z + 1.f); v.w *= (y.w > 0.f ? 1.f : y.w + 1.f);
+    } else if (EPI == EPI_ACCUM) { v.x += y.x; v.y += y.y; v.z += y.z; v.w += y.w; }
+    return v;
+}
+
+// The whole tile loop of one epilogue group, specialised on the epilogue so that the inner loops carry no mode branches.
+// Phase 1 (thread = row = TMEM lane): tcgen05.ld -> row-major staging tile; exact fp32 logit columns from the staged
+// operands.  Phase 2: the group's four warps sweep the tile with fully coalesced 16-byte global accesses.
+template <int EPI>
+__device__ __forceinline__ void staged_epilogue_loop(const TcGemmParams& p, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                                     uint64_t* empty_bar, uint32_t tmem_base, uint32_t xs_addr, uint32_t ws_addr,
+                                                     uint32_t og_addr, int stage_bytes, int grp, int wg, int q4, int lane,
+                                                     int64_t ntiles) {
+    const bool has_exact = p.exact_end > p.exact_begin;
+    const int nex = has_exact ? min(p.exact_end - p.exact_begin, 8) : 0;
+    const int row_in_tile = q4 * 32 + lane;
+    const int KQ = p.K >> 2, nq = p.N >> 2, N = p.N;
+    const uint32_t my_row = og_addr + (uint32_t)(row_in_tile * N) * 4u;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % p.stages, a = it & 1;
+        if (a != grp) continue;
+        mbar_wait(&tfull_bar[a], (uint32_t)(it >> 1) & 1u);
+        if (it == 0 && wg == 0) GLAM_DBG(4);
+        tc_fence_after_sync();
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * p.Npad);
+        // ---- phase 1
+        float xs[8];
+        if (nex > 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xs[e] = 0.f;
+            const uint32_t xrow = xs_addr + (uint32_t)(s * stage_bytes);
+            for (int q = 0; q < KQ; ++q) {
+                const float4 xv = lds128(xrow + panel_chunk_offset(row_in_tile, q, kTileM));
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (e < nex) {
+                        const float4 wv = lds128(ws_addr + panel_chunk_offset(p.exact_begin + e, q, p.Npad));
+                        xs[e] = fmaf(xv.x, wv.x, xs[e]); xs[e] = fmaf(xv.y, wv.y, xs[e]);
+                        xs[e] = fmaf(xv.z, wv.z, xs[e]); xs[e] = fmaf(xv.w, wv.w, xs[e]);
+                    }
+            }
+        }
+        for (int c0 = 0; c0 < p.Npad; c0 += 32) {
+            float v[32];
+            tmem_ld32(lane_base + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                if (c0 + j < N) sts128(my_row + (uint32_t)(c0 + j) * 4u, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        }
+        if (nex > 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (e < nex) sts32(my_row + (uint32_t)(p.exact_begin + e) * 4u, xs[e]);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {                                     // accumulator and X stage are free again
+            mbar_arrive(&tempty_bar[a]);
+            if (has_exact) mbar_arrive(&empty_bar[s]);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        // ---- phase 2
+        const int64_t row0 = tile * kTileM;
+        const int64_t rows_left = p.M - row0;
+        const int rows_here = rows_left < kTileM ? (int)rows_left : kTileM;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nq >= 24) {
+            // wide rows: warp per row, lanes over the row's 16-byte chunks (bias hoisted, pointer increments only)
+            for (int cq = lane; cq < nq; cq += 32) {
+                const int c = cq << 2;
+                const float4 b = p.bias ? *reinterpret_cast<const float4*>(p.bias + c) : zero4;
+                uint32_t og = og_addr + (uint32_t)(wg * N + c) * 4u;
+                float* y = p.Y + (row0 + wg) * p.ldy + c;
+                const float* ax = (EPI == EPI_MUL_CELU_GRAD) ? p.aux + (row0 + wg) * p.ldaux + c : nullptr;
+                const uint32_t og_step = (uint32_t)(4 * N) * 4u;
+                const int64_t y_step = 4 * p.ldy, a_step = 4 * p.ldaux;
+#pragma unroll 4
+                for (int r = wg; r < rows_here; r += 4) {
+                    float4 yv = zero4;
+                    if (EPI == EPI_MUL_CELU_GRAD) yv = *reinterpret_cast<const float4*>(ax);
+                    else if (EPI == EPI_ACCUM) yv = *reinterpret_cast<const float4*>(y);
+                    *reinterpret_cast<float4*>(y) = epi_apply<EPI>(lds128(og), b, yv);
+                    og += og_step; y += y_step;
+                    if (EPI == EPI_MUL_CELU_GRAD) ax += a_step;
+                }
+            }
+        } else {
+            // narrow rows: flat sweep over the tile's 16-byte chunks, 4 independent chunks per thread in flight
+            const int total = rows_here * nq;
+            const float inv_nq = 1.0f / (float)nq;
+            for (int i0 = wg * 32 + lane; i0 < total; i0 += 128 * 4) {
+                float4 v[4], yv[4], b[4];
+                float* yp[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + 128 * u;
+                    yv[u] = zero4; b[u] = zero4; yp[u] = nullptr;
+                    if (i < total) {
+                        const int r = (int)(((float)i + 0.5f) * inv_nq);      // exact for i < 2^13
+                        const int c = (i - r * nq) << 2;
+                        v[u] = lds128(og_addr + (uint32_t)i * 16u);
+                        yp[u] = p.Y + (row0 + r) * p.ldy + c;
+                        if (p.bias) b[u] = *reinterpret_cast<const float4*>(p.bias + c);
+                        if (EPI == EPI_MUL_CELU_GRAD) yv[u] = *reinterpret_cast<const float4*>(p.aux + (row0 + r) * p.ldaux + c);
+                        else if (EPI == EPI_ACCUM) yv[u] = *reinterpret_cast<const float4*>(yp[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (yp[u]) *reinterpret_cast<float4*>(yp[u]) = epi_apply<EPI>(v[u], b[u], yv[u]);
+            }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // staging tile free for this group's next tile
+        if (it == 0 && wg == 0) GLAM_DBG(5);
+    }
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p) {
@@ -53,6 +192,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p)
     float* Os = reinterpret_cast<float*>(Ws + (size_t)panels * p.Npad * kPanelRowBytes);   // [128][N] output staging
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const bool has_exact = p.exact_end > p.exact_begin;
+    if (t == 0) GLAM_DBG(0);
 
     if (t == 0) {
         for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], has_exact ? 5 : 1); }   // MMA commit (+ 4 epilogue warps)
@@ -66,6 +206,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p)
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
     const int64_t ntiles = (p.M + kTileM - 1) / kTileM;
+    if (t == 0) GLAM_DBG(1);
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -89,12 +230,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p)
             const uint32_t xs_addr = smem_u32(Xs), ws_addr = smem_u32(Ws);
             const int ksteps = p.KP >> 3;
             mbar_wait(&w_bar, 0);
+            GLAM_DBG(2);
             int it = 0;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int s = it % p.stages, a = it & 1;
                 const uint32_t ph = (uint32_t)(it / p.stages) & 1u, aph = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(&tempty_bar[a], aph ^ 1u);
                 mbar_wait(&full_bar[s], ph);
+                if (it == 0) GLAM_DBG(3);
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.Npad);
                 for (int ks = 0; ks < ksteps; ++ks) {
@@ -154,6 +297,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p)
             if (lane == 0) mbar_arrive(&w_bar);
             if (has_exact) mbar_wait(&w_bar, 0);                 // the exact columns read W rows from shared memory
         }
+        if (p.staged_out) {
+            const uint32_t xs_a = smem_u32(Xs), ws_a = smem_u32(Ws), og_a = smem_u32(Og);
+            switch (p.epi) {
+                case EPI_CELU: staged_epilogue_loop<EPI_CELU>(p, tfull_bar, tempty_bar, empty_bar, tmem_base, xs_a, ws_a, og_a, stage_bytes, grp, wg, q4, lane, ntiles); break;
+                case EPI_MUL_CELU_GRAD: staged_epilogue_loop<EPI_MUL_CELU_GRAD>(p, tfull_bar, tempty_bar, empty_bar, tmem_base, xs_a, ws_a, og_a, stage_bytes, grp, wg, q4, lane, ntiles); break;
+                case EPI_ACCUM: staged_epilogue_loop<EPI_ACCUM>(p, tfull_bar, tempty_bar, empty_bar, tmem_base, xs_a, ws_a, og_a, stage_bytes, grp, wg, q4, lane, ntiles); break;
+                default: staged_epilogue_loop<EPI_NONE>(p, tfull_bar, tempty_bar, empty_bar, tmem_base, xs_a, ws_a, og_a, stage_bytes, grp, wg, q4, lane, ntiles); break;
+            }
+        } else {
         const int KQ = p.K >> 2;
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -168,114 +320,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p)
             const float* arow = p.aux ? p.aux + m * p.ldaux : nullptr;
             const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * p.Npad);
             const uint8_t* Xrow = Xs + (size_t)s * stage_bytes;
-            if (p.staged_out) {
-                // ---- phase 1 (thread = row): TMEM -> registers -> row-major staging tile in shared memory
-                float xs[6];                                     // exact fp32 logit columns (<= 2*GLAM_MAX_HEADS... 6 used)
-                const int nex = has_exact ? min(p.exact_end - p.exact_begin, 6) : 0;
-                if (nex > 0) {
-#pragma unroll
-                    for (int e = 0; e < 6; ++e) xs[e] = 0.f;
-                    for (int q = 0; q < KQ; ++q) {
-                        const float4 xv = *reinterpret_cast<const float4*>(Xrow + panel_chunk_offset(row_in_tile, q, kTileM));
-#pragma unroll
-                        for (int e = 0; e < 6; ++e) {
-                            if (e < nex) {
-                                const float4 wv = *reinterpret_cast<const float4*>(Ws + panel_chunk_offset(p.exact_begin + e, q, p.Npad));
-                                xs[e] = fmaf(xv.x, wv.x, xs[e]); xs[e] = fmaf(xv.y, wv.y, xs[e]);
-                                xs[e] = fmaf(xv.z, wv.z, xs[e]); xs[e] = fmaf(xv.w, wv.w, xs[e]);
-                            }
-                        }
-                    }
-                }
-                for (int c0 = 0; c0 < p.Npad; c0 += 32) {
-                    float v[32];
-                    tmem_ld32(lane_base + (uint32_t)c0, v);      // Npad is a multiple of 16: the second half may be padding
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (c0 + j < p.N)
-                            *reinterpret_cast<float4*>(Og + row_in_tile * p.N + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-                if (nex > 0) {                                   // overwrite the logit columns with the exact values
-#pragma unroll
-                    for (int e = 0; e < 6; ++e)
-                        if (e < nex) Og[row_in_tile * p.N + p.exact_begin + e] = xs[e];
-                }
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) {                                 // accumulator and X stage are free again
-                    mbar_arrive(&tempty_bar[a]);
-                    if (has_exact) mbar_arrive(&empty_bar[s]);
-                }
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-                // ---- phase 2: warp per row, lanes over 16-byte column chunks -> fully coalesced global accesses
-                const int nq = p.N >> 2;
-                const int64_t rows_left = p.M - tile * kTileM;
-                const int rows_here = rows_left < kTileM ? (int)rows_left : kTileM;
-                if (nq >= 24) {
-                    // wide rows: warp per row, lanes over the row's 16-byte chunks (bias hoisted, no index math)
-                    for (int cq = lane; cq < nq; cq += 32) {
-                        const int c = cq << 2;
-                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias) b = *reinterpret_cast<const float4*>(p.bias + c);
-#pragma unroll 4
-                        for (int r = wg; r < rows_here; r += 4) {
-                            float4 v = *reinterpret_cast<const float4*>(Og + r * p.N + c);
-                            const int64_t mm = tile * kTileM + r;
-                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                            if (p.epi == EPI_CELU) { v.x = celu1(v.x); v.y = celu1(v.y); v.z = celu1(v.z); v.w = celu1(v.w); }
-                            else if (p.epi == EPI_MUL_CELU_GRAD) {
-                                const float4 y = *reinterpret_cast<const float4*>(p.aux + mm * p.ldaux + c);
-                                v.x *= (y.x > 0.f ? 1.f : y.x + 1.f); v.y *= (y.y > 0.f ? 1.f : y.y + 1.f);
-                                v.z *= (y.z > 0.f ? 1.f : y.z + 1.f); v.w *= (y.w > 0.f ? 1.f : y.w + 1.f);
-                            } else if (p.epi == EPI_ACCUM) {
-                                const float4 y = *reinterpret_cast<const float4*>(p.Y + mm * p.ldy + c);
-                                v.x += y.x; v.y += y.y; v.z += y.z; v.w += y.w;
-                            }
-                            *reinterpret_cast<float4*>(p.Y + mm * p.ldy + c) = v;
-                        }
-                    }
-                } else {
-                // narrow rows: flat sweep over the tile's 16-byte chunks, 4 independent chunks per thread in flight
-                const int total = rows_here * nq;
-                const float inv_nq = 1.0f / (float)nq;
-                for (int i0 = wg * 32 + lane; i0 < total; i0 += 128 * 4) {
-                    float4 v[4], y[4];
-                    int64_t off[4];
-                    int cc[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + 128 * u;
-                        if (i < total) {
-                            const int r = (int)(((float)i + 0.5f) * inv_nq);      // exact for i < 2^13
-                            cc[u] = (i - r * nq) << 2;
-                            off[u] = (tile * kTileM + r);
-                            v[u] = *reinterpret_cast<const float4*>(Og + (i << 2));
-                            if (p.epi == EPI_MUL_CELU_GRAD) y[u] = *reinterpret_cast<const float4*>(p.aux + off[u] * p.ldaux + cc[u]);
-                            else if (p.epi == EPI_ACCUM) y[u] = *reinterpret_cast<const float4*>(p.Y + off[u] * p.ldy + cc[u]);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + 128 * u;
-                        if (i < total) {
-                            float4 w = v[u];
-                            if (p.bias) {
-                                const float4 b = *reinterpret_cast<const float4*>(p.bias + cc[u]);
-                                w.x += b.x; w.y += b.y; w.z += b.z; w.w += b.w;
-                            }
-                            if (p.epi == EPI_CELU) { w.x = celu1(w.x); w.y = celu1(w.y); w.z = celu1(w.z); w.w = celu1(w.w); }
-                            else if (p.epi == EPI_MUL_CELU_GRAD) {
-                                w.x *= (y[u].x > 0.f ? 1.f : y[u].x + 1.f); w.y *= (y[u].y > 0.f ? 1.f : y[u].y + 1.f);
-                                w.z *= (y[u].z > 0.f ? 1.f : y[u].z + 1.f); w.w *= (y[u].w > 0.f ? 1.f : y[u].w + 1.f);
-                            } else if (p.epi == EPI_ACCUM) { w.x += y[u].x; w.y += y[u].y; w.z += y[u].z; w.w += y[u].w; }
-                            *reinterpret_cast<float4*>(p.Y + off[u] * p.ldy + cc[u]) = w;
-                        }
-                    }
-                }
-                }
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // staging tile free for this group's next tile
-                continue;
-            }
             for (int c0 = 0; c0 < p.Npad; c0 += 16) {
                 float v[16];
                 tmem_ld16(lane_base + (uint32_t)c0, v);
@@ -322,12 +366,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p)
                 if (has_exact) mbar_arrive(&empty_bar[s]);
             }
         }
+        }
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (t == 64) GLAM_DBG(6);
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (t == 32) GLAM_DBG(7);
 }
 
+static unsigned long long* g_tc_dbg = nullptr;
 static int g_math_mode = 1;   // 0 = fp32 on the CUDA cores (exact), 1 = TF32 tensor cores (default)
 int g_math_mode_get() { return g_math_mode; }
 
@@ -394,6 +442,7 @@ int tc_gemm_launch(const float* X, int64_t ldx, const float* W, int64_t w_sk, in
                    int exact_begin, int exact_end, cudaStream_t stream) {
     TcGemmParams p;
     p.exact_begin = exact_begin; p.exact_end = exact_end;
+    p.dbg = g_tc_dbg;
     p.W = W; p.w_sk = w_sk; p.w_sn = w_sn; p.bias = bias; p.aux = aux; p.ldaux = ldaux;
     p.Y = Y; p.ldy = ldy; p.M = M; p.N = (int)N; p.K = (int)K; p.epi = epi;
     p.KP = (int)((K + 7) / 8 * 8);
@@ -428,3 +477,5 @@ extern "C" int glam_set_math_mode(int mode) {
     return 0;
 }
 extern "C" int glam_get_math_mode(void) { return glam::g_math_mode; }
+// debugging aid (not part of the public header): device buffer of 8 u64 receiving CTA-0 phase timestamps of tc_gemm
+extern "C" void glam_debug_tc_timestamps(void* buf) { glam::g_tc_dbg = (unsigned long long*)buf; }

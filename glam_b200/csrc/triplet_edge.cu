@@ -393,7 +393,7 @@ int edge_vec_fwd(const float* xpe, int64_t ldxp, const float* ea, const float* w
                  float* alpha, cudaStream_t stream);
 size_t edge_vec_bwd_workspace(int heads, int C, int De);
 int edge_vec_bwd_dst(const float* xpe, int64_t ldxp, const float* ea, const float* w_edge, const float* att_edge,
-                     const float* alpha, const float* g_agg, const int32_t* rowptr, const int32_t* srcs, int64_t N, int heads,
+                     const float* alpha, const float* g_agg, const int32_t* rowptr, const int32_t* srcs, const int32_t* dsts, int64_t N, int64_t E, int heads,
                      int C, int De, float slope, float* g_logit, float* g_xpe, float* g_w_edge, void* workspace,
                      cudaStream_t stream, int* grid_out);
 int edge_vec_bwd_src(const float* ea, const float* w_edge, const float* alpha, const float* g_agg, const float* g_logit,
@@ -463,7 +463,7 @@ extern "C" size_t glam_triplet_bwd_workspace_bytes(int heads, int channels, int 
 
 extern "C" int glam_triplet_edge_bwd_dst(const float* xpe, int64_t ldxp, const float* edge_attr, const float* w_edge,
                                          const float* att_edge, const float* alpha, const float* g_agg,
-                                         const int32_t* dst_rowptr, const int32_t* dst_src, int64_t N, int64_t E,
+                                         const int32_t* dst_rowptr, const int32_t* dst_src, const int32_t* dst_dst, int64_t N, int64_t E,
                                          int heads, int C, int De, float slope, float* g_logit, float* g_xpe,
                                          float* g_w_edge, void* workspace, size_t workspace_bytes, void* stream_) {
     const bool use_ep = w_edge != nullptr;
@@ -480,7 +480,7 @@ extern "C" int glam_triplet_edge_bwd_dst(const float* xpe, int64_t ldxp, const f
                  "glam_triplet_edge_bwd_dst: g_w_edge/workspace missing or too small");
     if (edge_vec_eligible(xpe, ldxp, heads, C, De, g_agg, w_edge)) {
         int vgrid = 0;
-        if (int rc = edge_vec_bwd_dst(xpe, ldxp, edge_attr, w_edge, att_edge, alpha, g_agg, dst_rowptr, dst_src, N, heads, C, De,
+        if (int rc = edge_vec_bwd_dst(xpe, ldxp, edge_attr, w_edge, att_edge, alpha, g_agg, dst_rowptr, dst_src, dst_dst, N, E, heads, C, De,
                                       slope, g_logit, g_xpe, g_w_edge, workspace, stream, &vgrid)) return rc;
         if (use_ep) {
             return launch_reduce_partials((const float*)workspace, vgrid, 1, De * HC, 0, g_w_edge, De * HC, 0, nullptr, stream);

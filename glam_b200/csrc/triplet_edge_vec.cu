@@ -475,6 +475,105 @@ edge_dots_bwd_kernel(const float* __restrict__ xpe, int64_t ld, const float* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------------ backward 1': edge-parallel dots
+// g_alpha[p,h] depends on edge p alone, so with dst_dst[p] available the dots need no segment structure: one sub-warp
+// group per EDGE (grid-stride), both row gathers (g_agg[dst], xp[src]) issued up front, no degree loops, no divergence.
+// g_weight_edge (edge_dim <= 4) accumulates in registers with one predicated FMA per weight_edge row.
+constexpr int kEpMaxDe = 4;
+template <int H, int G, int CPL, bool USE_EP>
+__global__ void __launch_bounds__(kVecThreads)
+edge_dots_ep_kernel(const float* __restrict__ xpe, int64_t ld, const float* __restrict__ ea, const float* __restrict__ w_edge,
+                    const float* __restrict__ alpha, const float* __restrict__ g_agg, const int32_t* __restrict__ srcs,
+                    const int32_t* __restrict__ dsts, int64_t E, int C, int De, float* __restrict__ g_logit,
+                    float* __restrict__ gwe_partial) {
+    extern __shared__ float4 smem4[];
+    const int HC = H * C, nq = HC >> 2;
+    constexpr int kGroups = kVecThreads / G;
+    float4* We4 = smem4;                               // [De][nq]
+    float4* red4 = smem4 + (USE_EP ? De * nq : 0);     // [kGroups][De][nq]  (end of kernel only)
+    if (USE_EP)
+        for (int i = threadIdx.x; i < De * nq; i += blockDim.x) We4[i] = ldg4(w_edge + 4 * i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, grp = threadIdx.x / G, gl = lane % G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
+    int hq[CPL];
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) hq[t] = (4 * (gl + G * t)) / C;
+    // g_weight_edge accumulates in this group's private shared-memory slab [De][nq] (zeroed here, reduced over the groups
+    // in a fixed order at the end): no registers held across the edge loop, no predicated per-row FMAs
+    float4* slab = red4 + grp * De * nq;
+    if (USE_EP)
+        for (int i = threadIdx.x; i < kGroups * De * nq; i += blockDim.x) red4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const int64_t g0 = (int64_t)blockIdx.x * kGroups + grp, gstride = (int64_t)gridDim.x * kGroups;
+    for (int64_t p = g0; p < E; p += gstride) {
+        const float* xj = xpe + (int64_t)srcs[p] * ld;
+        const float* gi = g_agg + (int64_t)dsts[p] * HC;
+        float4 xv[CPL], gv[CPL];
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) {
+            const int q = gl + G * t;
+            if (q < nq) { xv[t] = ldg4(xj + 4 * q); gv[t] = ldg4(gi + 4 * q); }
+        }
+        float a[H], part[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) { a[h] = alpha[p * H + h]; part[h] = 0.f; }
+        const float* earow = ea + p * De;
+        EaRow er{0, 0, 0.f};
+        if (USE_EP) er = scan_ea(earow, De);
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) {
+            const int q = gl + G * t;
+            if (q < nq) {
+                const float4 gm = f4mul(gv[t], xv[t]);
+                float v;
+                if (USE_EP) {
+                    const float ah = pickh<H>(a, hq[t]);
+                    if (er.nz == 1) {
+                        v = er.val * f4dot(gm, We4[er.ty * nq + q]);
+                        float4* w = slab + er.ty * nq + q;
+                        *w = f4fma(er.val * ah, gm, *w);
+                    } else {
+                        float4 ep = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int dd = 0; dd < kEpMaxDe; ++dd)
+                            if (dd < De) {
+                                const float ed = earow[dd];
+                                ep = f4fma(ed, We4[dd * nq + q], ep);
+                                float4* w = slab + dd * nq + q;
+                                *w = f4fma(ed * ah, gm, *w);
+                            }
+                        v = f4dot(gm, ep);
+                    }
+                } else {
+                    v = gm.x + gm.y + gm.z + gm.w;
+                }
+#pragma unroll
+                for (int h = 0; h < H; ++h) part[h] += (hq[t] == h) ? v : 0.f;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) part[h] += __shfl_xor_sync(gmask, part[h], o);
+        }
+        if (gl < H) g_logit[p * H + gl] = pickh<H>(part, gl);
+    }
+    if (USE_EP) {
+        // fixed-order reduction of the per-group slabs -> one partial per CTA
+        __syncthreads();
+        float4* P = reinterpret_cast<float4*>(gwe_partial) + (int64_t)blockIdx.x * De * nq;
+        for (int idx = threadIdx.x; idx < De * nq; idx += blockDim.x) {
+            float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int w = 0; w < kGroups; ++w) {
+                const float4 v = red4[w * De * nq + idx];
+                sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w;
+            }
+            P[idx] = sacc;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ backward 2: softmax + leaky
 template <int H>
 __global__ void __launch_bounds__(256)
@@ -663,9 +762,34 @@ int edge_vec_fwd(const float* xpe, int64_t ldxp, const float* ea, const float* w
 size_t edge_vec_bwd_workspace(int heads, int C, int De) { return sizeof(float) * (size_t)kNumSMs * 8 * De * heads * C; }
 
 int edge_vec_bwd_dst(const float* xpe, int64_t ldxp, const float* ea, const float* w_edge, const float* att_edge,
-                     const float* alpha, const float* g_agg, const int32_t* rowptr, const int32_t* srcs, int64_t N, int heads,
-                     int C, int De, float slope, float* g_logit, float* g_xpe, float* g_w_edge, void* workspace,
-                     cudaStream_t stream, int* grid_out) {
+                     const float* alpha, const float* g_agg, const int32_t* rowptr, const int32_t* srcs, const int32_t* dsts,
+                     int64_t N, int64_t E, int heads, int C, int De, float slope, float* g_logit, float* g_xpe, float* g_w_edge,
+                     void* workspace, cudaStream_t stream, int* grid_out) {
+    if (dsts != nullptr && De <= kEpMaxDe) {
+        const bool use_ep_t = w_edge != nullptr;
+        const int HCt = heads * C, nq_t = HCt / 4;
+        int G, gcpl;
+        vec_geometry(nq_t, &G, &gcpl);
+        int tgrid = kNumSMs * 4;
+        if (E > 0) {
+            GLAM_VEC_GDISPATCH(heads, use_ep_t, G, {
+                const size_t smem_t = use_ep_t ? sizeof(float4) * (size_t)(De * nq_t) * (1 + kVecThreads / G_) : 0;
+                auto fn = edge_dots_ep_kernel<HH_, G_, CPL_, UE_>;
+                vec_allow_smem(fn, smem_t);
+                fn<<<tgrid, kVecThreads, smem_t, stream>>>(xpe, ldxp, ea, w_edge, alpha, g_agg, srcs, dsts, E, C, De, g_logit, (float*)workspace);
+            })
+            GLAM_CHECK_LAUNCH();
+        } else if (use_ep_t) {
+            cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)tgrid * De * HCt, stream);
+        }
+        GLAM_VEC_HEADS(heads, {
+            edge_softmax_bwd_kernel<HH_><<<vec_thread_grid(N), 256, 0, stream>>>(xpe, ldxp, ea, att_edge, alpha, rowptr, srcs, N, HCt, De, slope,
+                                                                              g_logit, g_xpe);
+        })
+        GLAM_CHECK_LAUNCH();
+        *grid_out = tgrid;
+        return 0;
+    }
     const bool use_ep = w_edge != nullptr;
     const int HC = heads * C, nq = HC / 4, cpl = (nq + 31) / 32;
     int grid = vec_warp_grid(N);

@@ -70,7 +70,7 @@ class TrainStep:
         self.static = _static_like(example, self.device)
         _copy_into(self.static, example)
         self.grads = FlatGrads(self.model.parameters())
-        self.opt = torch.optim.Adam(self.grads.params, lr=lr, capturable=use_cuda_graph, foreach=True)
+        self.opt = torch.optim.Adam(self.grads.params, lr=lr, capturable=use_cuda_graph, fused=True)
         self.loss = torch.zeros((), device=self.device)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_cuda_graph = use_cuda_graph

@@ -30,6 +30,7 @@ class GraphIndex:
         self.dst_rowptr = csr["dst_rowptr"]
         self.dst_src = csr["dst_src"]
         self.dst_perm = csr["dst_perm"]
+        self.dst_dst = csr["dst_dst"]
         self.src_rowptr = csr["src_rowptr"]
         self.src_pos = csr["src_pos"]
         self.src_dst = csr["src_dst"]

@@ -72,12 +72,13 @@ def build_csr(edge_index: torch.Tensor, num_nodes: int):
     i32 = dict(dtype=torch.int32, device=dev)
     out = {
         "dst_rowptr": torch.empty(N + 1, **i32), "dst_src": torch.empty(E, **i32), "dst_perm": torch.empty(E, **i32),
+        "dst_dst": torch.empty(E, **i32),
         "src_rowptr": torch.empty(N + 1, **i32), "src_pos": torch.empty(E, **i32), "src_dst": torch.empty(E, **i32),
     }
     nbytes = lib.glam_csr_workspace_bytes(N, E)
     ws = _ws(nbytes, dev)
     _call("glam_build_csr", _p(edge_index), E, N, _p(out["dst_rowptr"]), _p(out["dst_src"]), _p(out["dst_perm"]),
-                                  _p(out["src_rowptr"]), _p(out["src_pos"]), _p(out["src_dst"]), _p(ws), ws.numel(),
+          _p(out["dst_dst"]), _p(out["src_rowptr"]), _p(out["src_pos"]), _p(out["src_dst"]), _p(ws), ws.numel(),
                                   _stream(edge_index))
     return out
 
@@ -199,7 +200,7 @@ def triplet_edge_bwd(xpe, ea_sorted, w_edge, att_edge, alpha, g_agg, g, heads, c
         ws = _ws(lib.glam_triplet_bwd_workspace_bytes(heads, channels, De), dev)
     st = _stream(xpe)
     _call("glam_triplet_edge_bwd_dst", _p(xpe), ld, _p(ea_sorted), _p(w_edge), _p(att_edge), _p(alpha), _p(g_agg),
-                                             _p(g.dst_rowptr), _p(g.dst_src), N, E, heads, channels, De, float(slope),
+                                             _p(g.dst_rowptr), _p(g.dst_src), _p(g.dst_dst), N, E, heads, channels, De, float(slope),
                                              _p(g_logit), _p(g_xpe), _p(g_we), _p(ws), 0 if ws is None else ws.numel(),
                                              st)
     _call("glam_triplet_edge_bwd_src", _p(ea_sorted), _p(w_edge), _p(alpha), _p(g_agg), _p(g_logit),

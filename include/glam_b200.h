@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLAM_B200_ABI_VERSION 1
+#define GLAM_B200_ABI_VERSION 2
 #define GLAM_MAX_HEADS 4
 
 int glam_abi_version(void);
@@ -50,6 +50,7 @@ int glam_get_math_mode(void);
  *   dst_perm[p]   original edge id of the p-th edge in (dst, original order) order
  *   dst_rowptr[i] .. dst_rowptr[i+1]  = in-edges of node i in that order
  *   dst_src[p]    source node of edge dst_perm[p]
+ *   dst_dst[p]    destination node of that edge (optional, may be NULL; lets backward run edge-parallel)
  * and the same for sources (backward scatters by SOURCE):
  *   src_perm / src_rowptr  (stable by edge_index[0]);  src_pos[k] = position p (dst order) of edge
  *   src_perm[k];  src_dst[k] = destination node of that edge.
@@ -57,7 +58,7 @@ int glam_get_math_mode(void);
  * --------------------------------------------------------------------------------------------- */
 size_t glam_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges);
 int glam_build_csr(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes,
-                   int32_t* dst_rowptr, int32_t* dst_src, int32_t* dst_perm,
+                   int32_t* dst_rowptr, int32_t* dst_src, int32_t* dst_perm, int32_t* dst_dst,
                    int32_t* src_rowptr, int32_t* src_pos, int32_t* src_dst,
                    void* workspace, size_t workspace_bytes, void* stream);
 /* graph_ptr[g] = first node of graph g (B+1 entries) from the sorted int64 `batch` vector
@@ -120,7 +121,7 @@ int glam_triplet_edge_fwd(const float* xpe, int64_t ldxp, const float* edge_attr
 size_t glam_triplet_bwd_workspace_bytes(int heads, int channels, int edge_dim);
 int glam_triplet_edge_bwd_dst(const float* xpe, int64_t ldxp, const float* edge_attr, const float* w_edge,
                               const float* att_edge, const float* alpha, const float* g_agg,
-                              const int32_t* dst_rowptr, const int32_t* dst_src,
+                              const int32_t* dst_rowptr, const int32_t* dst_src, const int32_t* dst_dst,
                               int64_t num_nodes, int64_t num_edges, int heads, int channels, int edge_dim,
                               float negative_slope, float* g_logit, float* g_xpe, float* g_w_edge,
                               void* workspace, size_t workspace_bytes, void* stream);

@@ -55,6 +55,7 @@ def test_csr_bit_exact(kind):
     perm = torch.argsort(dst, stable=True)
     assert torch.equal(csr["dst_perm"].cpu().long(), perm)
     assert torch.equal(csr["dst_src"].cpu().long(), src[perm])
+    assert torch.equal(csr["dst_dst"].cpu().long(), dst[perm])
     rowptr = torch.zeros(N + 1, dtype=torch.long)
     rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=N), 0)
     assert torch.equal(csr["dst_rowptr"].cpu().long(), rowptr)
