@@ -36,7 +36,7 @@ struct TcGemmParams {
     const float* aux; int64_t ldaux;
     float* Y; int64_t ldy;
     int64_t M; int N, K, epi;
-    int KP, Npad, tmem_cols, vec_store, stages, staged_out;
+    int KP, Npad, tmem_cols, vec_store, stages, staged_out, og_groups, w_vec;
     int exact_begin, exact_end;   // output columns computed with exact fp32 FMAs (attention-logit columns)
     unsigned long long* dbg;      // optional phase timestamps of CTA 0 (globaltimer ns), 8 slots
 };
@@ -257,16 +257,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p)
         const int wg = (warp - 2) & 3;                           // warp within the group
         const int q4 = warp & 3;                                 // TMEM lane quarter this warp may read
         const int row_in_tile = q4 * 32 + lane;
-        float* Og = Os + (size_t)grp * kTileM * p.N;             // this group's staging tile
+        float* Og = Os + (size_t)(p.og_groups == 1 ? 0 : grp) * kTileM * p.N;   // this group's staging tile (one CTA-tile launches only use group 0)
         // ---- stage W once: K-major swizzled image [panels][Npad][128 B], zero padded to [Npad][KP]
         {
             const int KPQ = p.KP >> 2;
             const int items = p.Npad * KPQ;
             constexpr int kWT = 128 * kEpiGroups;
-            for (int base = 0; base < items; base += kWT * 4) {
-                float4 v[4];
+            constexpr int kWU = 8;                               // loads in flight per thread
+            for (int base = 0; base < items; base += kWT * kWU) {
+                float4 v[kWU];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kWU; ++u) {
                     const int idx = base + u * kWT + eall;
                     v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (idx < items) {
@@ -275,6 +276,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p)
                         if (n < p.N) {
                             const int k = 4 * q;
                             const float* w = p.W + (int64_t)k * p.w_sk + (int64_t)n * p.w_sn;
+                            if (p.w_vec) { if (k < p.K) v[u] = __ldg(reinterpret_cast<const float4*>(w)); continue; }   // K % 4 == 0
                             if (k < p.K) v[u].x = w[0];
                             if (k + 1 < p.K) v[u].y = w[p.w_sk];
                             if (k + 2 < p.K) v[u].z = w[2 * p.w_sk];
@@ -283,7 +285,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p)
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kWU; ++u) {
                     const int idx = base + u * kWT + eall;
                     if (idx < items) {
                         int n, q;
@@ -413,15 +415,18 @@ int make_tmap_rows(CUtensorMap* map, const float* base, int64_t rows, int64_t co
 }
 
 // Shared-memory plan: W image + (optionally) the [128][N] output staging tile + as many X stages as fit (<= 4).
-static size_t tc_smem_bytes(int64_t N, int64_t K, bool want_staged, int* stages_out, int* staged_out) {
+// single_tile: every CTA processes at most one tile (M <= 128 * grid), so one load stage and one epilogue group's
+// staging tile are enough — that keeps the coalesced epilogue for wide N x K that would not fit otherwise.
+static size_t tc_smem_bytes(int64_t N, int64_t K, bool want_staged, int* stages_out, int* staged_out, bool single_tile = false) {
     const int64_t KP = (K + 7) / 8 * 8, Npad = (N + 15) / 16 * 16;
     const int64_t panels = (KP + kPanelFeatures - 1) / kPanelFeatures;
     const int64_t wbytes = panels * Npad * kPanelRowBytes, stage = panels * kPanelBytes;
-    const int64_t obytes = (int64_t)kEpiGroups * kTileM * N * sizeof(float);
+    const int64_t obytes = (int64_t)(single_tile ? 1 : kEpiGroups) * kTileM * N * sizeof(float);
     const int64_t limit = 222 * 1024;
     int64_t staged = want_staged ? 1 : 0;
     int64_t stages = (limit - wbytes - staged * obytes) / stage;
-    if (staged && stages < 2) { staged = 0; stages = (limit - wbytes) / stage; }   // keep the load pipeline alive first
+    if (staged && stages < (single_tile ? 1 : 2)) { staged = 0; stages = (limit - wbytes) / stage; }   // keep the load pipeline alive first
+    if (single_tile && stages > 1) stages = 1;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages_out) *stages_out = (int)stages;
     if (staged_out) *staged_out = (int)staged;
@@ -451,7 +456,10 @@ int tc_gemm_launch(const float* X, int64_t ldx, const float* W, int64_t w_sk, in
     p.vec_store = ((ldy & 3) == 0 && ((uintptr_t)Y & 15) == 0) ? 1 : 0;
     const bool al16 = ((N & 3) == 0) && ((ldy & 3) == 0) && (((uintptr_t)Y & 15) == 0) && (((uintptr_t)bias & 15) == 0) &&
                       (aux == nullptr || (((ldaux & 3) == 0) && (((uintptr_t)aux & 15) == 0)));
-    const size_t smem = tc_smem_bytes(N, K, al16, &p.stages, &p.staged_out);
+    const bool single_tile = M <= (int64_t)kTileM * kNumSMs;
+    const size_t smem = tc_smem_bytes(N, K, al16, &p.stages, &p.staged_out, single_tile);
+    p.og_groups = single_tile ? 1 : kEpiGroups;
+    p.w_vec = (w_sk == 1 && (w_sn & 3) == 0 && ((uintptr_t)W & 15) == 0) ? 1 : 0;
     GLAM_REQUIRE(smem > 0, "tc_gemm: operands do not fit in shared memory (N=%lld K=%lld)", (long long)N, (long long)K);
     CUtensorMap tmap;
     if (int rc = make_tmap_rows(&tmap, X, M, K, ldx, kTileM, (int)CU_TENSOR_MAP_SWIZZLE_128B)) return rc;

@@ -261,6 +261,50 @@ class SegAttnPoolFn(Function):
         return g_x, g_q, g_b, None, None
 
 
+class Set2SetFn(Function):
+    """PyG Set2Set: (x, lstm weights) -> q* [B,2C].  Per round one tensor-core GEMM for the gates of all graphs and one
+    warp-per-graph kernel for cell + attention + pooled read (csrc/set2set.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, gptr, num_graphs, steps):
+        x, w_ih, w_hh, b_ih, b_hh = map(_c, (x, w_ih, w_hh, b_ih, b_hh))
+        ops._need_cuda(x, w_ih)
+        N, C = x.shape
+        B, S, dev = num_graphs, steps, x.device
+        w_cat = torch.cat([w_ih, w_hh], 1)                                  # [4C,3C] against u = [h | r | h]
+        b_sum = b_ih + b_hh
+        U = torch.empty((S + 1, B, 3 * C), dtype=torch.float32, device=dev)
+        cs = torch.empty((S + 1, B, C), dtype=torch.float32, device=dev)
+        gates = torch.empty((S, B, 4 * C), dtype=torch.float32, device=dev)
+        att = torch.empty((S, N), dtype=torch.float32, device=dev)
+        out = torch.empty((B, 2 * C), dtype=torch.float32, device=dev)
+        U[0].zero_()
+        cs[0].zero_()
+        for s in range(S):
+            ops.gemm(U[s], w_cat, transpose_w=True, bias=b_sum, out=gates[s])
+            ops.set2set_round_fwd(x, gates[s], cs[s], cs[s + 1], gptr, B, att[s], U[s + 1], out if s == S - 1 else None)
+        ctx.save_for_backward(x, w_cat, gptr, U, cs, gates, att)
+        ctx.cfg = (B, S)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, w_cat, gptr, U, cs, gates, att = ctx.saved_tensors
+        B, S = ctx.cfg
+        N, C = x.shape
+        dev = x.device
+        G = torch.empty((S, B, 4 * C), dtype=torch.float32, device=dev)
+        g_c = torch.zeros((B, C), dtype=torch.float32, device=dev)
+        g_x = torch.empty((N, C), dtype=torch.float32, device=dev)
+        g_u = _c(g_out)
+        for s in range(S - 1, -1, -1):
+            ops.set2set_round_bwd(x, gates[s], cs[s], cs[s + 1], att[s], gptr, B, g_u, g_c, g_x, s != S - 1, G[s])
+            if s > 0:
+                g_u = ops.gemm(G[s], w_cat)                                 # [B,3C]
+        g_w, g_b = ops.gemm_tn_ex(U[:S].reshape(S * B, 3 * C), G.view(S * B, 4 * C), transpose_out=True, want_colsum=True)
+        return g_x, g_w[:, :2 * C], g_w[:, 2 * C:], g_b, g_b, None, None, None
+
+
 # --------------------------------------------------------------------------------------------------
 # cross-graph dot pool (src_2gi_ddi/layer.py:270-283)
 # --------------------------------------------------------------------------------------------------

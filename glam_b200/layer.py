@@ -267,9 +267,14 @@ class Set2Set(nn.Module):
         self.num_layers = num_layers
         self.lstm = nn.LSTM(self.out_channels, in_channels, num_layers)
 
+    fused = True     # one kernel per direction for all rounds; False = the composed GEMM + gates + pooling path
+
     def forward(self, x, batch, num_graphs=None):
         gptr, B = G.graph_ptr(batch, num_graphs)
         C, l = self.in_channels, self.lstm
+        if self.fused and C <= 128 and self.processing_steps <= 8:
+            return Fn.Set2SetFn.apply(x, l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0, gptr, B,
+                                      self.processing_steps)
         h = x.new_zeros((B, C))
         c = x.new_zeros((B, C))
         q_star = x.new_zeros((B, 2 * C))

@@ -288,6 +288,17 @@ def seg_attn_pool_bwd(x, q, q_stride, a, g_r, g_asum, gptr, num_graphs, g_x, acc
     return g_q, g_e
 
 
+def set2set_round_fwd(x, gates, c_prev, c_new, gptr, num_graphs, att, u_next, q_star=None):
+    _call("glam_set2set_round_fwd", _p(x), x.stride(0), _p(gptr), num_graphs, x.shape[1], _p(gates), _p(c_prev), _p(c_new),
+          _p(att), _p(u_next), _p(q_star), _stream(x))
+
+
+def set2set_round_bwd(x, gates, c_prev, c_new, att, gptr, num_graphs, g_u, g_c, g_x, accumulate, G):
+    assert g_u.stride(1) == 1
+    _call("glam_set2set_round_bwd", _p(x), x.stride(0), _p(gptr), num_graphs, x.shape[1], _p(gates), _p(c_prev), _p(c_new),
+          _p(att), _p(g_u), g_u.stride(0), g_u.shape[1], _p(g_c), _p(g_x), 1 if accumulate else 0, _p(G), _stream(x))
+
+
 def pair_dot_pool_fwd(xa, xb, ptr_a, ptr_b, num_pairs):
     C, dev = xa.shape[1], xa.device
     out = torch.empty((num_pairs, 2), dtype=torch.float32, device=dev)

@@ -177,6 +177,23 @@ int glam_seg_attn_pool_bwd(const float* x, int64_t ldx, const float* q, int64_t 
                            int64_t num_graphs, int channels, int accumulate,
                            float* g_x, int64_t ldgx, float* g_q, float* g_e, void* stream);
 
+/* Set2Set rounds (PyG Set2Set(in_channels=C, processing_steps=S) @1.7.2, src_1gp/model.py:2,41).  A round is
+ *   gates = U [B,3C] x [W_ih | W_hh]^T + (b_ih + b_hh)         -- glam_gemm_ex (shared weights: tensor cores)
+ *   glam_set2set_round_fwd: gate non-linearities (i,f,g,o), c' = f c + i g, h = o tanh c', a = softmax_n <x_n, h>
+ *       (PyG softmax), r = sum_n a_n x_n, u_next = [h | r | h] (the next round's GEMM operand; q* = [h | r] is also
+ *       written to q_star when non-NULL).  gates is activated in place; att [N] keeps this round's weights.
+ * One warp per graph.  Backward per round (reverse order): g_u is the gradient of the round's output ([h|r], 2C columns,
+ * for the last round; [h|r|h], 3C columns = G_next x [W_ih|W_hh], otherwise); g_c carries the cell-state gradient;
+ * g_x is overwritten (accumulate == 0) or added to; G [B,4C] receives the gate pre-activation gradients, from which
+ * [g_w_ih | g_w_hh] = sum_rounds G^T U and g_b_ih = g_b_hh = colsum(G) follow as one glam_gemm_tn_ex. */
+int glam_set2set_round_fwd(const float* x, int64_t ldx, const int32_t* graph_ptr, int64_t num_graphs, int channels,
+                           float* gates, const float* c_prev, float* c_new, float* att, float* u_next, float* q_star,
+                           void* stream);
+int glam_set2set_round_bwd(const float* x, int64_t ldx, const int32_t* graph_ptr, int64_t num_graphs, int channels,
+                           const float* gates, const float* c_prev, const float* c_new, const float* att,
+                           const float* g_u, int64_t ldgu, int gu_cols, float* g_c, float* g_x, int accumulate,
+                           float* G, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (6) Cross-graph interaction pool — dot_and_global_pool2 (src_2gi_ddi/layer.py:270-283, identical in
  * src_2gi_dti_scr/layer.py): per pair g, S = Xa[g] Xb[g]^T, out[g] = [max S, mean S]; one CTA per

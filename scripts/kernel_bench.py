@@ -45,3 +45,22 @@ if which in ("all", "edge"):
     timeit("edge_bwd (dst+src)", lambda: ops.triplet_edge_bwd(xpe, ea, we, ae, alpha, g108, g, H, C, 0.2), 4 * (2 * N * ld + 2 * N * HC + 2 * E * De + 5 * E * H) + 4 * (4 * E + 2 * N))
     gi = torch.randn(N, 3 * C, device=dev); gh = torch.randn(N, 3 * C, device=dev); h = torch.randn(N, C, device=dev)
     timeit("gru_gates_fwd", lambda: ops.gru_gates_fwd(gi.clone(), gh, h, x, 3, 1.0), 4 * N * C * 13)
+if which in ("all", "s2s"):
+    B = 4096
+    b = make_molecule_batch(B, total_nodes=N, total_edges=221184, seed=1).to(dev)
+    gptr, _ = graph.graph_ptr(b.batch, B)
+    U = torch.randn(B, 3 * C, device=dev); wc = torch.randn(4 * C, 3 * C, device=dev); bs = torch.randn(4 * C, device=dev)
+    gates = torch.empty(B, 4 * C, device=dev)
+    timeit("s2s gates gemm [4096,108]x[144,108]^T", lambda: ops.gemm(U, wc, transpose_w=True, bias=bs, out=gates), 4 * B * 7 * C)
+    Gm = torch.randn(B, 4 * C, device=dev)
+    timeit("s2s g_u gemm [4096,144]x[144,108]", lambda: ops.gemm(Gm, wc), 4 * B * 7 * C)
+    c0 = torch.zeros(B, C, device=dev); c1 = torch.empty(B, C, device=dev); att = torch.empty(N, device=dev); un = torch.empty(B, 3 * C, device=dev)
+    pre = torch.randn(B, 4 * C, device=dev)
+    def fwd():
+        gates.copy_(pre)
+        ops.set2set_round_fwd(x, gates, c0, c1, gptr, B, att, un, None)
+    timeit("s2s round_fwd (+copy)", fwd, 4 * (N * C + N + B * 12 * C))
+    gu = torch.randn(B, 3 * C, device=dev); gc = torch.zeros(B, C, device=dev); gx = torch.zeros(N, C, device=dev); Go = torch.empty(B, 4 * C, device=dev)
+    timeit("s2s round_bwd (overwrite)", lambda: ops.set2set_round_bwd(x, gates, c0, c1, att, gptr, B, gu, gc, gx, False, Go), 4 * (2 * N * C + N + B * 13 * C))
+    timeit("s2s round_bwd (accumulate)", lambda: ops.set2set_round_bwd(x, gates, c0, c1, att, gptr, B, gu, gc, gx, True, Go), 4 * (3 * N * C + N + B * 13 * C))
+    timeit("s2s wgrad tn [12288,108]^T[12288,144]", lambda: ops.gemm_tn_ex(torch.randn(3 * B, 3 * C, device=dev), torch.randn(3 * B, 4 * C, device=dev), transpose_out=True, want_colsum=True), 4 * 3 * B * 7 * C)
