@@ -364,6 +364,7 @@ def run_ours(args):
                             "ms_per_launch": top[1][2], "launches_per_step": top[1][1],
                             "share_of_library_time": top[1][0] / total_ms, "algorithmic_bytes_per_launch": nbytes}
         line["kernel_profile_ms_per_step"] = {k: round(v[0], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:12]}
+        line["kernel_profile_launches_per_step"] = {k: v[1] for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:12]}
         line["kernel_profile_total_ms"] = round(total_ms, 4)
         if world == 1 and not args.no_cpu_baseline:
             gps, sec, threads = cpu_train_throughput(512, 6, 2)

@@ -365,8 +365,12 @@ set2set_round_bwd_rows_kernel(const S2SRoundBwd p) {
     if (g >= p.B) return;
     const int n0 = p.gptr[g], n = p.gptr[g + 1] - n0;
     const int nch = (n + 31) >> 5;
-    float4 xr[C4];
+    float4 xr[C4], old[C4];
     if (lane < n) load_row<C4>(xr, p.x + (int64_t)(n0 + lane) * p.ldx);
+    if (p.accumulate && lane < n) {              // previous rounds' g_x row: in flight while the logits are computed
+#pragma unroll
+        for (int q = 0; q < C4; ++q) old[q] = *(reinterpret_cast<const float4*>(p.g_x + (int64_t)(n0 + lane) * C) + q);
+    }
     const float* gs = p.gates + g * 4 * C;
     const float* gu = p.g_u + g * p.ldgu;
     float gh[2] = {0.f, 0.f}, tc[2] = {0.f, 0.f};
@@ -406,7 +410,7 @@ set2set_round_bwd_rows_kernel(const S2SRoundBwd p) {
             for (int q = 0; q < C4; ++q) {
                 const float4 r4 = *reinterpret_cast<const float4*>(g_r + 4 * q), h4 = *reinterpret_cast<const float4*>(h + 4 * q);
                 float4 v = make_float4(fmaf(a, r4.x, ge * h4.x), fmaf(a, r4.y, ge * h4.y), fmaf(a, r4.z, ge * h4.z), fmaf(a, r4.w, ge * h4.w));
-                if (p.accumulate) { const float4 o = gxr[q]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                if (p.accumulate) { const float4 o = ch == 0 ? old[q] : gxr[q]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
                 gxr[q] = v;
             }
             scatter_scaled_row<C4>(tile, lane, xr, ge);

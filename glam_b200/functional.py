@@ -190,6 +190,92 @@ class MessageBlockFn(Function):
 
 
 # --------------------------------------------------------------------------------------------------
+# `message_steps` applications of ONE MessageBlock (shared weights; src_1gp/model.py:60-62 loops the same block) as a
+# single autograd node.  Activations of all steps live in stacked [S, N, .] buffers, so every weight gradient is ONE
+# fixed-order A^T B over S*N rows instead of S contractions that autograd then adds up, and the derived weights
+# (w_ext, att_edge) are prepared once.  Dropout on the block input (graph_do) stays torch's (philox, graph-safe).
+# --------------------------------------------------------------------------------------------------
+class MessageStackFn(Function):
+    @staticmethod
+    def forward(ctx, x0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, ea, g,
+                heads, channels, slope, act, act_param, res, steps, p_drop):
+        (x0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh) = map(
+            _c, (x0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh))
+        ops._need_cuda(x0, w_ext)
+        N, C = x0.shape
+        S, H, HC, ld, E, dev = steps, heads, heads * channels, w_ext.shape[1], ea.shape[0], x0.device
+        new = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype, device=dev)
+        X, HH = new(S + 1, N, C), new(S + 1, N, C)               # block inputs / GRU states; [s+1] = outputs of step s
+        X[0].copy_(x0)
+        HH[0].copy_(x0)                                          # h = x.unsqueeze(0) on the first step (layer.py:254)
+        drop = p_drop > 0.0
+        XD = new(S, N, C) if drop else X                         # conv inputs (after dropout)
+        MASK = new(S, N, C, dtype=torch.bool) if drop else None
+        XPE, AGG, ALPHA = new(S, N, ld), new(S, N, HC), new(S, E, H)
+        M, RZN, GH = new(S, N, C), new(S, N, 3 * C), new(S, N, 3 * C)
+        for s in range(S):
+            if drop:
+                torch.ops.aten.native_dropout.out(X[s], p_drop, True, out0=XD[s], out1=MASK[s])
+            ops.gemm(XD[s], w_ext, exact_cols=(HC, HC + 2 * H), out=XPE[s])
+            ops.triplet_edge_fwd(XPE[s], ea, w_edge, att_edge, g, H, channels, slope, agg=AGG[s], alpha=ALPHA[s])
+            ops.gemm(AGG[s], w_scale, bias=bias, epilogue=EPI_CELU, out=M[s])
+            ops.gemm(M[s], w_ih, transpose_w=True, bias=b_ih, out=RZN[s])
+            ops.gemm(HH[s], w_hh, transpose_w=True, bias=b_hh, out=GH[s])
+            ops.gru_gates_fwd(RZN[s], GH[s], HH[s], X[s] if res else None, act, act_param, h_new=HH[s + 1], x_out=X[s + 1])
+        ctx.save_for_backward(w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ea, X, HH, XD, MASK, XPE, AGG, ALPHA, M, RZN, GH)
+        ctx.g, ctx.cfg = g, (H, channels, slope, act, act_param, res, S, p_drop)
+        ctx.set_materialize_grads(False)
+        return tuple(X[s + 1] for s in range(S)) + (HH[S],)      # every step's output (the pair models pool them) + final h
+
+    @staticmethod
+    def backward(ctx, *grads):
+        (w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ea, X, HH, XD, MASK, XPE, AGG, ALPHA, M, RZN, GH) = ctx.saved_tensors
+        H, C, slope, act, act_param, res, S, p_drop = ctx.cfg
+        g = ctx.g
+        N, HC, ld, E, De, dev = X.shape[1], H * C, XPE.shape[2], ea.shape[0], ea.shape[1], X.device
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        G_GI, G_GH, G_PRE = new(S, N, 3 * C), new(S, N, 3 * C), new(S, N, C)
+        G_XPE, G_LOGIT, G_WE = new(S, N, ld), new(S, E, H), new(S, De, HC)
+        g_ext, g_h, g_x = grads[:S], _c(grads[S]), None
+        for s in range(S - 1, -1, -1):
+            if g_ext[s] is not None:                             # gradient arriving at this step's output from outside
+                g_x = _c(g_ext[s]) if g_x is None else g_x.add_(g_ext[s])
+            if g_x is None:
+                g_x = torch.zeros((N, C), dtype=torch.float32, device=dev)
+            _, _, g_h_prev, g_id = ops.gru_gates_bwd(RZN[s], GH[s], HH[s], X[s + 1], g_x, g_h, act, act_param, res,
+                                                     g_gi=G_GI[s], g_gh=G_GH[s])
+            ops.gemm(G_GI[s], w_ih, epilogue=EPI_MUL_CELU_GRAD, aux=M[s], out=G_PRE[s])       # d/d(pre-CELU message)
+            ops.gemm(G_GH[s], w_hh, epilogue=EPI_ACCUM, out=g_h_prev)
+            g_agg = ops.gemm(G_PRE[s], w_scale, transpose_w=True)                             # [N,HC]
+            ops.triplet_edge_bwd(XPE[s], ea, w_edge, att_edge, ALPHA[s], g_agg, g, H, C, slope,
+                                 g_xpe=G_XPE[s], g_logit=G_LOGIT[s], g_we=G_WE[s])
+            if p_drop > 0.0:
+                g_xd = ops.gemm(G_XPE[s], w_ext, transpose_w=True)
+                g_x = torch.ops.aten.native_dropout_backward(g_xd, MASK[s], 1.0 / (1.0 - p_drop))
+                if res:
+                    g_x.add_(g_id)
+            elif res:
+                g_x = ops.gemm(G_XPE[s], w_ext, transpose_w=True, epilogue=EPI_ACCUM, out=g_id)
+            else:
+                g_x = ops.gemm(G_XPE[s], w_ext, transpose_w=True)
+            g_h = g_h_prev
+        g_x0 = g_x.add_(g_h)                                                                  # X[0] and HH[0] are both x0
+        SN = S * N
+        g_w_ih, g_b_ih = ops.gemm_tn_ex(M.view(SN, C), G_GI.view(SN, 3 * C), transpose_out=True, want_colsum=True)
+        g_w_hh, g_b_hh = ops.gemm_tn_ex(HH[:S].view(SN, C), G_GH.view(SN, 3 * C), transpose_out=True, want_colsum=True)
+        g_w_scale, g_bias = ops.gemm_tn_ex(AGG.view(SN, HC), G_PRE.view(SN, C), want_colsum=True)
+        xd = XD[:S].view(SN, C)
+        gxpe = G_XPE.view(SN, ld)
+        g_w_ext, _ = ops.gemm_tn_ex(xd, gxpe)
+        # the 2H logit columns are near-total cancellations (softmax gradients are zero-sum per destination): exact fp32
+        ops.gemm_tn_ex(xd, gxpe[:, HC:HC + 2 * H], out=g_w_ext[:, HC:HC + 2 * H])
+        g_att_edge, _ = ops.gemm_tn_ex(ea, G_LOGIT.sum(0) if S > 1 else G_LOGIT[0])
+        g_w_edge = G_WE.sum(0) if S > 1 else G_WE[0]
+        return (g_x0, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias, g_w_ih, g_w_hh, g_b_ih, g_b_hh,
+                None, None, None, None, None, None, None, None, None, None)
+
+
+# --------------------------------------------------------------------------------------------------
 # small dense layer on graph-level rows (LSTM gates of Set2Set, nn of GlobalAttention)
 # --------------------------------------------------------------------------------------------------
 class LinearFn(Function):
@@ -206,7 +292,8 @@ class LinearFn(Function):
         x, weight = ctx.saved_tensors
         g_y = _c(g_y)
         g_w, g_b = ops.gemm_tn_ex(x, g_y, transpose_out=True, want_colsum=ctx.has_bias)       # (x^T g_y)^T = [N,K]
-        return ops.gemm(g_y, weight), g_w, g_b
+        g_x = ops.gemm(g_y, weight) if ctx.needs_input_grad[0] else None                      # raw features need none
+        return g_x, g_w, g_b
 
 
 class LSTMGatesFn(Function):

@@ -367,7 +367,13 @@ class LinearBlock(nn.Module):
         self.act = _build_act(act)
 
     def forward(self, x, batch=None):
-        return self.act(self.linear(self.dropout(self.norm(x, batch))))
+        z = self.dropout(self.norm(x, batch))
+        lin = self.linear
+        # node-level projections (many rows, narrow) go through the library's GEMMs: the weight gradient is a long
+        # fixed-order A^T B there; wide graph-level layers ([B, e_dim]) are plain library GEMMs (cuBLAS via torch)
+        if z.is_cuda and z.dim() == 2 and lin.out_features <= 256 and lin.in_features <= 288:
+            return self.act(Fn.LinearFn.apply(z, lin.weight, lin.bias))
+        return self.act(lin(z))
 
 
 class MessageBlock(nn.Module):
@@ -385,6 +391,33 @@ class MessageBlock(nn.Module):
             self.gru = None
         self.act = _build_act(act)
         self.res = res
+
+    def run_steps(self, x, edge_index, edge_attr, steps, batch=None):
+        """`steps` applications of this block starting from h=None (the loop of src_1gp/model.py:60-62), returning
+        ([x_1 .. x_steps], h).  With the triplet layer, no norm and a fusable activation the whole loop is one
+        autograd node (functional.MessageStackFn); otherwise it is the plain loop over forward()."""
+        inner = getattr(self.conv, "conv", None)
+        fused = _fusable_act(self.act, self.training)
+        drop = self.dropout
+        stackable = (self.gru is not None and isinstance(inner, TripletMessage) and isinstance(self.norm, _None)
+                     and fused is not None and isinstance(drop, (_None, nn.Dropout)) and x.is_cuda and steps >= 1
+                     and x.shape[1] == inner.node_channels and self.gru.hidden_size == x.shape[1])
+        if not stackable:
+            xs, h = [], None
+            for _ in range(steps):
+                x, h = self.forward(x, edge_index, edge_attr, h=h, batch=batch)
+                xs.append(x)
+            return xs, h
+        p_drop = float(drop.p) if (isinstance(drop, nn.Dropout) and self.training) else 0.0
+        g = G.graph_index(edge_index, x.shape[0])
+        ea = g.sorted_edge_attr(edge_attr)
+        w_ext, att_edge = inner.derived()
+        gru = self.gru
+        out = Fn.MessageStackFn.apply(
+            x, w_ext, inner.weight_edge, att_edge, inner.weight_scale, inner.bias,
+            gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, ea, g,
+            inner.heads, inner.node_channels, inner.negative_slope, fused[0], fused[1], bool(self.res), int(steps), p_drop)
+        return list(out[:steps]), out[steps].unsqueeze(0)
 
     def forward(self, x, edge_index, edge_attr, h=None, batch=None):
         identity = x

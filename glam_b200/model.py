@@ -63,10 +63,8 @@ class ArchitectureGP(nn.Module):
     def forward(self, data_mol):
         B = _num_graphs(data_mol)
         xm = self.mol_lin0(data_mol.x, batch=data_mol.batch)
-        hm = None
-        for _ in range(self.message_steps):
-            xm, hm = self.mol_conv(xm, data_mol.edge_index, data_mol.edge_attr, h=hm, batch=data_mol.batch)
-        outm = self.mol_readout(xm, data_mol.batch, num_graphs=B)
+        xs, _ = self.mol_conv.run_steps(xm, data_mol.edge_index, data_mol.edge_attr, self.message_steps, batch=data_mol.batch)
+        outm = self.mol_readout(xs[-1], data_mol.batch, num_graphs=B)
         return self.lin_out1(self.mol_flat(outm))
 
 
@@ -98,14 +96,12 @@ class _PairArchitecture(nn.Module):
         B = _num_graphs(da)
         xa = ta.lin0(da.x, batch=da.batch)
         xb = tb.lin0(db.x, batch=db.batch)
-        ha = hb = None
-        fusion = []
-        for _ in range(self.message_steps):
-            xa, ha = ta.conv(xa, da.edge_index, da.edge_attr, h=ha, batch=da.batch)
-            xb, hb = tb.conv(xb, db.edge_index, db.edge_attr, h=hb, batch=db.batch)
-            fusion.append(dot_and_global_pool2(xa, xb, da.batch, db.batch, num_graphs=B))
-        oa = ta.flat(ta.readout(xa, da.batch, num_graphs=B))
-        ob = tb.flat(tb.readout(xb, db.batch, num_graphs=B))
+        # the towers only meet in the pools, so each runs all its steps first (same values as the lock-step loop)
+        xas, _ = ta.conv.run_steps(xa, da.edge_index, da.edge_attr, self.message_steps, batch=da.batch)
+        xbs, _ = tb.conv.run_steps(xb, db.edge_index, db.edge_attr, self.message_steps, batch=db.batch)
+        fusion = [dot_and_global_pool2(a, b, da.batch, db.batch, num_graphs=B) for a, b in zip(xas, xbs)]
+        oa = ta.flat(ta.readout(xas[-1], da.batch, num_graphs=B))
+        ob = tb.flat(tb.readout(xbs[-1], db.batch, num_graphs=B))
         out = self.lin_out0(torch.cat([oa, ob] + fusion, dim=-1))
         return self.lin_out1(out)
 

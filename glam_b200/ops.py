@@ -175,28 +175,31 @@ def colsum(G: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ edge phase
-def triplet_edge_fwd(xpe, ea_sorted, w_edge, att_edge, g, heads, channels, slope):
+def triplet_edge_fwd(xpe, ea_sorted, w_edge, att_edge, g, heads, channels, slope, agg=None, alpha=None):
     N, E, dev = xpe.shape[0], ea_sorted.shape[0], xpe.device
     HC = heads * channels
-    agg = torch.empty((N, HC), dtype=torch.float32, device=dev)
-    alpha = torch.empty((E, heads), dtype=torch.float32, device=dev)
+    agg = torch.empty((N, HC), dtype=torch.float32, device=dev) if agg is None else agg
+    alpha = torch.empty((E, heads), dtype=torch.float32, device=dev) if alpha is None else alpha
+    assert agg.is_contiguous() and alpha.is_contiguous()
     _call("glam_triplet_edge_fwd", _p(xpe), xpe.stride(0), _p(ea_sorted), _p(w_edge), _p(att_edge),
                                                  _p(g.dst_rowptr), _p(g.dst_src), N, E, heads, channels,
                                                  ea_sorted.shape[1], float(slope), _p(agg), _p(alpha), _stream(xpe))
     return agg, alpha
 
 
-def triplet_edge_bwd(xpe, ea_sorted, w_edge, att_edge, alpha, g_agg, g, heads, channels, slope):
+def triplet_edge_bwd(xpe, ea_sorted, w_edge, att_edge, alpha, g_agg, g, heads, channels, slope,
+                     g_xpe=None, g_logit=None, g_we=None):
     """Returns g_xpe [N, ldxp], g_logit [E,H] (dst order), g_w_edge [De,HC] or None."""
     lib = _lib.load()
     N, E, dev = xpe.shape[0], ea_sorted.shape[0], xpe.device
     De, HC, ld = ea_sorted.shape[1], heads * channels, xpe.stride(0)
-    g_xpe = torch.empty((N, ld), dtype=torch.float32, device=dev)
-    g_logit = torch.empty((E, heads), dtype=torch.float32, device=dev)
-    g_we = None
+    g_xpe = torch.empty((N, ld), dtype=torch.float32, device=dev) if g_xpe is None else g_xpe
+    g_logit = torch.empty((E, heads), dtype=torch.float32, device=dev) if g_logit is None else g_logit
+    assert g_xpe.is_contiguous() and g_logit.is_contiguous() and g_xpe.shape[1] == ld
     ws = None
     if w_edge is not None:
-        g_we = torch.empty((De, HC), dtype=torch.float32, device=dev)
+        g_we = torch.empty((De, HC), dtype=torch.float32, device=dev) if g_we is None else g_we
+        assert g_we.is_contiguous()
         ws = _ws(lib.glam_triplet_bwd_workspace_bytes(heads, channels, De), dev)
     st = _stream(xpe)
     _call("glam_triplet_edge_bwd_dst", _p(xpe), ld, _p(ea_sorted), _p(w_edge), _p(att_edge), _p(alpha), _p(g_agg),
@@ -230,19 +233,21 @@ def triplet_prep_bwd(weight_node, weight_edge, att, g_w_ext, g_att_edge, g_w_edg
 
 
 # ------------------------------------------------------------------------------------------------ cells
-def gru_gates_fwd(gi, gh, h, identity, act, act_param):
+def gru_gates_fwd(gi, gh, h, identity, act, act_param, h_new=None, x_out=None):
     N, C = h.shape
-    h_new = torch.empty_like(h)
-    x_out = torch.empty_like(h)
+    h_new = torch.empty_like(h) if h_new is None else h_new
+    x_out = torch.empty_like(h) if x_out is None else x_out
+    assert h_new.is_contiguous() and x_out.is_contiguous()
     _call("glam_gru_gates_fwd", _p(gi), _p(gh), _p(h), _p(identity), N, C, act, float(act_param),
                                               _p(h_new), _p(x_out), _stream(h))
     return h_new, x_out
 
 
-def gru_gates_bwd(rzn, gh, h, x_out, g_x_out, g_h_carry, act, act_param, want_identity):
+def gru_gates_bwd(rzn, gh, h, x_out, g_x_out, g_h_carry, act, act_param, want_identity, g_gi=None, g_gh=None):
     N, C = h.shape
-    g_gi = torch.empty_like(rzn)
-    g_gh = torch.empty_like(rzn)
+    g_gi = torch.empty_like(rzn) if g_gi is None else g_gi
+    g_gh = torch.empty_like(rzn) if g_gh is None else g_gh
+    assert g_gi.is_contiguous() and g_gh.is_contiguous()
     g_h_prev = torch.empty_like(h)
     g_id = torch.empty_like(h) if want_identity else None
     _call("glam_gru_gates_bwd", _p(rzn), _p(gh), _p(h), _p(x_out), _p(g_x_out), _p(g_h_carry), N, C, act,
