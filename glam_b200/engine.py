@@ -40,24 +40,78 @@ def _copy_into(dst: GraphBatch, src: GraphBatch) -> int:
 
 
 class FlatGrads:
-    """All parameter gradients as views into one flat fp32 buffer (one all-reduce per step)."""
+    """All parameter gradients in one flat fp32 buffer (one all-reduce per step).
 
-    def __init__(self, params):
+    gather=False: every p.grad is a view into the buffer and autograd accumulates in place (one add kernel per
+    parameter per step).  gather=True: p.grad is cleared before backward, autograd hands over each gradient tensor
+    as is, and collect() packs them into the buffer with one batched copy — ~20 launches fewer per step."""
+
+    def __init__(self, params, gather: bool = False):
         self.params = [p for p in params if p.requires_grad]
+        self.gather = gather
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=self.params[0].device)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        if not gather:
+            off = 0
+            for p in self.params:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
 
     def zero(self):
-        self.flat.zero_()
+        if self.gather:
+            for p in self.params:
+                p.grad = None
+        else:
+            self.flat.zero_()
+
+    def collect(self):
+        if self.gather:
+            parts = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+            torch.cat(parts, out=self.flat)
 
     def all_reduce_mean(self, world: int):
         import torch.distributed as dist
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         self.flat.mul_(1.0 / world)
+
+    def all_reduce_sum(self):
+        import torch.distributed as dist
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+
+
+class FlatAdam:
+    """torch.optim.Adam(params, lr) (the reference trainer's optimizer, src_1gp/trainer.py:49-50) on flat buffers:
+    the parameters are re-pointed at views of one fp32 buffer, and a step is one library call over
+    (parameters, gradient bucket, exp_avg, exp_avg_sq).  `lr` is a device scalar: set_lr() works between CUDA-graph
+    replays, which is what a ReduceLROnPlateau scheduler needs."""
+
+    def __init__(self, grads: FlatGrads, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        from . import ops
+        self._ops = ops
+        self.grads = grads
+        dev = grads.flat.device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatAdam runs on the CUDA library only (no CPU path)")
+        self.flat = torch.empty_like(grads.flat)
+        off = 0
+        with torch.no_grad():
+            for p in grads.params:
+                n = p.numel()
+                self.flat[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat[off:off + n].view_as(p)
+                off += n
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.state = torch.zeros(3, dtype=torch.float32, device=dev)
+        self.lr = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
+
+    def set_lr(self, lr: float):
+        self.lr.fill_(float(lr))
+
+    def step(self, grad_scale: float = 1.0):
+        self._ops.adam_step(self.flat, self.grads.flat, self.exp_avg, self.exp_avg_sq, self.lr, self.state, self.betas[0],
+                            self.betas[1], self.eps, self.weight_decay, grad_scale)
 
 
 class TrainStep:
@@ -69,8 +123,8 @@ class TrainStep:
         self.world = world_size
         self.static = _static_like(example, self.device)
         _copy_into(self.static, example)
-        self.grads = FlatGrads(self.model.parameters())
-        self.opt = torch.optim.Adam(self.grads.params, lr=lr, capturable=use_cuda_graph, fused=True)
+        self.grads = FlatGrads(self.model.parameters(), gather=True)
+        self.opt = FlatAdam(self.grads, lr=lr)
         self.loss = torch.zeros((), device=self.device)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_cuda_graph = use_cuda_graph
@@ -82,9 +136,10 @@ class TrainStep:
         out = self.model(self.static)
         loss = self.loss_fn(out, self.static.y)
         loss.backward()
+        self.grads.collect()
         if self.world > 1:
-            self.grads.all_reduce_mean(self.world)
-        self.opt.step()
+            self.grads.all_reduce_sum()
+        self.opt.step(grad_scale=1.0 / self.world)              # mean over ranks folded into the gradient load
         self.loss.copy_(loss.detach())
 
     def _capture(self, warmup: int):

@@ -321,3 +321,14 @@ def pair_dot_pool_bwd(xa, xb, ptr_a, ptr_b, g_out, argmax, sa, sb, num_pairs):
     _call("glam_pair_dot_pool_bwd", _p(xa), _p(xb), _p(ptr_a), _p(ptr_b), _p(g_out), _p(argmax), _p(sa),
                                                   _p(sb), num_pairs, xa.shape[1], _p(g_xa), _p(g_xb), _stream(xa))
     return g_xa, g_xb
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, state, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+              grad_scale=1.0):
+    """torch.optim.Adam semantics on flat fp32 buffers; lr [1] and state [3] are device tensors (see the header)."""
+    _need_cuda(param, grad)
+    n = param.numel()
+    assert param.is_contiguous() and grad.is_contiguous() and grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
+    _call("glam_adam_step", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), n, _p(lr), _p(state), float(beta1), float(beta2),
+          float(eps), float(weight_decay), float(grad_scale), _stream(param))

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLAM_B200_ABI_VERSION 2
+#define GLAM_B200_ABI_VERSION 3
 #define GLAM_MAX_HEADS 4
 
 int glam_abi_version(void);
@@ -205,6 +205,16 @@ int glam_pair_dot_pool_fwd(const float* xa, const float* xb, const int32_t* ptr_
 int glam_pair_dot_pool_bwd(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b,
                            const float* g_out, const int32_t* argmax, const float* sum_a, const float* sum_b,
                            int64_t num_pairs, int channels, float* g_xa, float* g_xb, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (7) Optimizer step of the data-parallel training step — torch.optim.Adam(model.parameters(), lr) as the reference
+ * trainer builds it (src_1gp/trainer.py:49-50): one pass over flat fp32 buffers (parameters, the all-reduced gradient
+ * bucket, both moments).  lr [1] and state [3] = {step, 1-beta1^step, 1-beta2^step} are device memory (CUDA-graph
+ * replayable; state must start as zeros); the call first advances state, then updates.  grad_scale multiplies the
+ * gradients on load (1/world_size after a sum all-reduce).
+ * --------------------------------------------------------------------------------------------- */
+int glam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr,
+                   float* state, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -475,3 +475,60 @@ def test_full_size_properties():
         torch.testing.assert_close(agg.double().sum(0), total, rtol=1e-6, atol=1e-3)
         out = m(b.x, b.edge_index, b.edge_attr)
     assert torch.isfinite(out).all() and out.shape == (b.num_nodes, 36)
+
+
+# ---------------------------------------------------------------------------------------------- optimizer / engine
+def test_adam_step_matches_torch():
+    """glam_adam_step == torch.optim.Adam (the reference trainer's optimizer, src_1gp/trainer.py:49-50) on flat buffers."""
+    from glam_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    n = 108_429
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone().double())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    p = p0.clone().to(DEV)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    state = torch.zeros(3, device=DEV)
+    lr = torch.full((1,), 1e-3, device=DEV)
+    for step in range(5):
+        grad = torch.randn(n, generator=g) * (10.0 ** (step - 2))
+        ref.grad = grad.double() * 0.5
+        opt.step()
+        ops.adam_step(p, grad.to(DEV), m, v, lr, state, grad_scale=0.5)
+    assert state[0].item() == 5.0
+    torch.testing.assert_close(p.cpu(), ref.detach().float(), rtol=2e-6, atol=2e-7)
+
+
+def test_captured_train_steps_follow_oracle_training():
+    """engine.TrainStep (CUDA graph, gathered flat gradients, flat Adam) against the oracle model trained with
+    torch.optim.Adam on the same batches: losses and parameters after several steps (fp32 math mode)."""
+    from glam_b200._lib import set_math_mode, get_math_mode
+    from glam_b200.engine import TrainStep
+    from glam_b200.synth import make_molecule_batch
+    prev = get_math_mode()
+    set_math_mode("fp32")
+    try:
+        m, o32 = _gp_pair(9, 3, "Set2Set", "_TripletMessage")
+        batches = [make_molecule_batch(48, seed=700 + i, total_nodes=48 * 20, total_edges=48 * 42) for i in range(4)]
+        opt = torch.optim.Adam(o32.parameters(), lr=1e-3)
+        ref_losses = []
+        for b in batches:
+            opt.zero_grad()
+            loss = torch.nn.functional.mse_loss(o32(ns(b.x, b.edge_index, b.edge_attr, b.batch)), b.y)
+            loss.backward()
+            opt.step()
+            ref_losses.append(loss.item())
+        ts = TrainStep(m, torch.nn.functional.mse_loss, batches[0], lr=1e-3, device=DEV, use_cuda_graph=True, warmup=0)
+        # capture ran the body (warm-up + capture pass) on batch 0: rewind parameters and optimizer state
+        sd = {k: v.to(DEV) for k, v in _gp_pair(9, 3, "Set2Set", "_TripletMessage")[1].state_dict().items()}
+        with torch.no_grad():
+            for k, p in m.state_dict().items():
+                p.copy_(sd[k])
+        ts.opt.exp_avg.zero_(); ts.opt.exp_avg_sq.zero_(); ts.opt.state.zero_()
+        losses = [ts.step(b.pin_memory()).item() for b in batches]
+        for a, r in zip(losses, ref_losses):
+            assert abs(a - r) <= 2e-4 * max(1.0, abs(r)), (losses, ref_losses)
+        for (n, p), q in zip(m.named_parameters(), o32.parameters()):
+            torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=2e-3, atol=2e-4, msg=lambda s, n=n: f"{n}: {s}")
+    finally:
+        set_math_mode(prev)
