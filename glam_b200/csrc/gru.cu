@@ -24,7 +24,7 @@ __global__ void gru_gates_fwd_kernel(float* __restrict__ gi, const float* __rest
     }
 }
 
-__global__ void gru_gates_bwd_kernel(const float* __restrict__ rzn, const float* __restrict__ gh, const float* __restrict__ h,
+__global__ void gru_gates_bwd_kernel(const float* __restrict__ rzn, const float* __restrict__ gh_n, int64_t ldghn, const float* __restrict__ h,
                                      const float* __restrict__ x_out, const float* __restrict__ g_x_out,
                                      const float* __restrict__ g_h_carry, int64_t N, int C, int act, float act_param,
                                      float* __restrict__ g_gi, float* __restrict__ g_gh, float* __restrict__ g_h_prev,
@@ -34,7 +34,7 @@ __global__ void gru_gates_bwd_kernel(const float* __restrict__ rzn, const float*
         const int64_t n = idx / C;
         const int c = (int)(idx - n * C);
         const int64_t b = n * 3 * C + c;
-        const float r = rzn[b], z = rzn[b + C], nn = rzn[b + 2 * C], ghn = gh[b + 2 * C], hv = h[idx];
+        const float r = rzn[b], z = rzn[b + C], nn = rzn[b + 2 * C], ghn = gh_n[n * ldghn + c], hv = h[idx];
         const float gs = g_x_out ? g_x_out[idx] * act_grad_from_out(x_out[idx], act, act_param) : 0.f;
         if (g_identity) g_identity[idx] = gs;
         const float ghp = gs + (g_h_carry ? g_h_carry[idx] : 0.f);
@@ -130,7 +130,7 @@ gru_gates_fwd_vec_kernel(float* __restrict__ gi, const float* __restrict__ gh, c
 }
 
 __global__ void __launch_bounds__(256)
-gru_gates_bwd_vec_kernel(const float* __restrict__ rzn, const float* __restrict__ gh, const float* __restrict__ h,
+gru_gates_bwd_vec_kernel(const float* __restrict__ rzn, const float* __restrict__ gh_n, int64_t ldghn, const float* __restrict__ h,
                          const float* __restrict__ x_out, const float* __restrict__ g_x_out,
                          const float* __restrict__ g_h_carry, int64_t N, int C, int act, float act_param,
                          float* __restrict__ g_gi, float* __restrict__ g_gh, float* __restrict__ g_h_prev,
@@ -141,7 +141,7 @@ gru_gates_bwd_vec_kernel(const float* __restrict__ rzn, const float* __restrict_
         const int64_t n = idx / cq;
         const int c = (int)(idx - n * cq) << 2;
         const int64_t b = n * 3 * C + c, o = n * C + c;
-        const float4 r = ld4(rzn + b), z = ld4(rzn + b + C), nn = ld4(rzn + b + 2 * C), ghn = ld4(gh + b + 2 * C), hv = ld4(h + o);
+        const float4 r = ld4(rzn + b), z = ld4(rzn + b + C), nn = ld4(rzn + b + 2 * C), ghn = ld4(gh_n + n * ldghn + c), hv = ld4(h + o);
         float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g_x_out) {
             const float4 gx = ld4(g_x_out + o), xo = ld4(x_out + o);
@@ -200,21 +200,30 @@ extern "C" int glam_gru_gates_fwd(float* gi_rzn, const float* gh, const float* h
     return 0;
 }
 
-extern "C" int glam_gru_gates_bwd(const float* rzn, const float* gh, const float* h, const float* x_out, const float* g_x_out,
-                                  const float* g_h_carry, int64_t N, int C, int act, float act_param, float* g_gi,
-                                  float* g_gh, float* g_h_prev, float* g_identity, void* stream_) {
-    GLAM_REQUIRE(N >= 0 && C > 0 && act >= 0 && act <= 3, "glam_gru_gates_bwd: bad arguments");
+// gh_n: the hidden-side pre-activation of the n gate (W_hn h + b_hn), row n at gh_n + n * ld_ghn
+extern "C" int glam_gru_gates_bwd_ex(const float* rzn, const float* gh_n, int64_t ld_ghn, const float* h, const float* x_out,
+                                     const float* g_x_out, const float* g_h_carry, int64_t N, int C, int act, float act_param,
+                                     float* g_gi, float* g_gh, float* g_h_prev, float* g_identity, void* stream_) {
+    GLAM_REQUIRE(N >= 0 && C > 0 && act >= 0 && act <= 3 && ld_ghn >= C, "glam_gru_gates_bwd: bad arguments");
     if (N == 0) return 0;
-    GLAM_REQUIRE(rzn && gh && h && x_out && g_gi && g_gh && g_h_prev, "glam_gru_gates_bwd: null pointer");
-    if ((C & 3) == 0 && al16(rzn) && al16(gh) && al16(h) && al16(x_out) && al16(g_x_out) && al16(g_h_carry) && al16(g_gi) &&
-        al16(g_gh) && al16(g_h_prev) && al16(g_identity))
-        gru_gates_bwd_vec_kernel<<<ew_grid(N * C / 4), 256, 0, (cudaStream_t)stream_>>>(rzn, gh, h, x_out, g_x_out, g_h_carry, N, C, act,
-                                                                                    act_param, g_gi, g_gh, g_h_prev, g_identity);
+    GLAM_REQUIRE(rzn && gh_n && h && x_out && g_gi && g_gh && g_h_prev, "glam_gru_gates_bwd: null pointer");
+    if ((C & 3) == 0 && (ld_ghn & 3) == 0 && al16(rzn) && al16(gh_n) && al16(h) && al16(x_out) && al16(g_x_out) && al16(g_h_carry) &&
+        al16(g_gi) && al16(g_gh) && al16(g_h_prev) && al16(g_identity))
+        gru_gates_bwd_vec_kernel<<<ew_grid(N * C / 4), 256, 0, (cudaStream_t)stream_>>>(rzn, gh_n, ld_ghn, h, x_out, g_x_out, g_h_carry, N, C,
+                                                                                    act, act_param, g_gi, g_gh, g_h_prev, g_identity);
     else
-        gru_gates_bwd_kernel<<<ew_grid(N * C), 256, 0, (cudaStream_t)stream_>>>(rzn, gh, h, x_out, g_x_out, g_h_carry, N, C, act,
+        gru_gates_bwd_kernel<<<ew_grid(N * C), 256, 0, (cudaStream_t)stream_>>>(rzn, gh_n, ld_ghn, h, x_out, g_x_out, g_h_carry, N, C, act,
                                                                                 act_param, g_gi, g_gh, g_h_prev, g_identity);
     GLAM_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int glam_gru_gates_bwd(const float* rzn, const float* gh, const float* h, const float* x_out, const float* g_x_out,
+                                  const float* g_h_carry, int64_t N, int C, int act, float act_param, float* g_gi,
+                                  float* g_gh, float* g_h_prev, float* g_identity, void* stream_) {
+    GLAM_REQUIRE(gh != nullptr || N == 0, "glam_gru_gates_bwd: null pointer");
+    return glam_gru_gates_bwd_ex(rzn, gh ? gh + 2 * (int64_t)C : nullptr, 3 * (int64_t)C, h, x_out, g_x_out, g_h_carry, N, C, act, act_param,
+                                 g_gi, g_gh, g_h_prev, g_identity, stream_);
 }
 
 extern "C" int glam_lstm_gates_fwd(float* gates, const float* c_prev, int64_t R, int C, float* c_new, float* h_new, void* stream_) {

@@ -92,6 +92,8 @@ def _conv_bwd(g_pre, x, w_ext, w_edge, att_edge, w_scale, xpe, agg, alpha, ea, g
 
 
 def _gru_fwd(m, h, identity, w_ih, w_hh, b_ih, b_hh, act, act_param):
+    if ops.gru_fused_supported(m, h, h.shape[1]):
+        return ops.gru_fused_fwd(m, h, identity, w_ih, w_hh, b_ih, b_hh, act, act_param)   # rzn, gh (n-part), h_new, x_out
     gi = ops.gemm(m, w_ih, transpose_w=True, bias=b_ih)                        # [N,3C]
     gh = ops.gemm(h, w_hh, transpose_w=True, bias=b_hh)
     h_new, x_out = ops.gru_gates_fwd(gi, gh, h, identity, act, act_param)      # gi now holds r|z|n
@@ -212,16 +214,21 @@ class MessageStackFn(Function):
         XD = new(S, N, C) if drop else X                         # conv inputs (after dropout)
         MASK = new(S, N, C, dtype=torch.bool) if drop else None
         XPE, AGG, ALPHA = new(S, N, ld), new(S, N, HC), new(S, E, H)
-        M, RZN, GH = new(S, N, C), new(S, N, 3 * C), new(S, N, 3 * C)
+        fused_gru = ops.gru_fused_supported(XPE[0], HH[0], C)        # then only the n-gate part of gh is kept: [N,C]
+        M, RZN, GH = new(S, N, C), new(S, N, 3 * C), new(S, N, C if fused_gru else 3 * C)
         for s in range(S):
             if drop:
                 torch.ops.aten.native_dropout.out(X[s], p_drop, True, out0=XD[s], out1=MASK[s])
             ops.gemm(XD[s], w_ext, exact_cols=(HC, HC + 2 * H), out=XPE[s])
             ops.triplet_edge_fwd(XPE[s], ea, w_edge, att_edge, g, H, channels, slope, agg=AGG[s], alpha=ALPHA[s])
             ops.gemm(AGG[s], w_scale, bias=bias, epilogue=EPI_CELU, out=M[s])
-            ops.gemm(M[s], w_ih, transpose_w=True, bias=b_ih, out=RZN[s])
-            ops.gemm(HH[s], w_hh, transpose_w=True, bias=b_hh, out=GH[s])
-            ops.gru_gates_fwd(RZN[s], GH[s], HH[s], X[s] if res else None, act, act_param, h_new=HH[s + 1], x_out=X[s + 1])
+            if fused_gru:
+                ops.gru_fused_fwd(M[s], HH[s], X[s] if res else None, w_ih, w_hh, b_ih, b_hh, act, act_param,
+                                  rzn=RZN[s], gh=GH[s], h_new=HH[s + 1], x_out=X[s + 1])
+            else:
+                ops.gemm(M[s], w_ih, transpose_w=True, bias=b_ih, out=RZN[s])
+                ops.gemm(HH[s], w_hh, transpose_w=True, bias=b_hh, out=GH[s])
+                ops.gru_gates_fwd(RZN[s], GH[s], HH[s], X[s] if res else None, act, act_param, h_new=HH[s + 1], x_out=X[s + 1])
         ctx.save_for_backward(w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ea, X, HH, XD, MASK, XPE, AGG, ALPHA, M, RZN, GH)
         ctx.g, ctx.cfg = g, (H, channels, slope, act, act_param, res, S, p_drop)
         ctx.set_materialize_grads(False)

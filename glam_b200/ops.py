@@ -243,14 +243,41 @@ def gru_gates_fwd(gi, gh, h, identity, act, act_param, h_new=None, x_out=None):
     return h_new, x_out
 
 
-def gru_gates_bwd(rzn, gh, h, x_out, g_x_out, g_h_carry, act, act_param, want_identity, g_gi=None, g_gh=None):
+def gru_fused_supported(m, h, channels) -> bool:
+    return (bool(_lib.load().glam_gru_fused_supported(int(channels))) and m.stride(0) % 4 == 0 and h.stride(0) % 4 == 0
+            and m.data_ptr() % 16 == 0 and h.data_ptr() % 16 == 0)
+
+
+def gru_fused_fwd(m, h, identity, w_ih, w_hh, b_ih, b_hh, act, act_param, rzn=None, gh=None, h_new=None, x_out=None):
+    """gi/gh GEMMs + gates in one tensor-core kernel; returns (rzn [N,3C], gh_n [N,C], h_new, x_out)."""
+    _need_cuda(m, h)
     N, C = h.shape
+    dev = h.device
+    rzn = torch.empty((N, 3 * C), dtype=torch.float32, device=dev) if rzn is None else rzn
+    gh = torch.empty((N, C), dtype=torch.float32, device=dev) if gh is None else gh
+    assert tuple(gh.shape) == (N, C)
+    h_new = torch.empty((N, C), dtype=torch.float32, device=dev) if h_new is None else h_new
+    x_out = torch.empty((N, C), dtype=torch.float32, device=dev) if x_out is None else x_out
+    assert rzn.is_contiguous() and gh.is_contiguous() and h_new.is_contiguous() and x_out.is_contiguous()
+    assert w_ih.is_contiguous() and w_hh.is_contiguous() and m.stride(1) == 1 and h.stride(1) == 1
+    assert identity is None or identity.is_contiguous()
+    _call("glam_gru_fused_fwd", _p(m), m.stride(0), _p(h), h.stride(0), _p(identity), _p(w_ih), _p(w_hh), _p(b_ih), _p(b_hh),
+          N, C, act, float(act_param), _p(rzn), _p(gh), _p(h_new), _p(x_out), _stream(h))
+    return rzn, gh, h_new, x_out
+
+
+def gru_gates_bwd(rzn, gh, h, x_out, g_x_out, g_h_carry, act, act_param, want_identity, g_gi=None, g_gh=None):
+    """gh: either the full hidden-side pre-activations [N,3C] (unfused forward) or the n-gate part alone [N,C]
+    (glam_gru_fused_fwd)."""
+    N, C = h.shape
+    gh_n = gh[:, 2 * C:] if gh.shape[1] == 3 * C else gh
+    assert gh_n.shape[1] == C and gh_n.stride(1) == 1
     g_gi = torch.empty_like(rzn) if g_gi is None else g_gi
     g_gh = torch.empty_like(rzn) if g_gh is None else g_gh
     assert g_gi.is_contiguous() and g_gh.is_contiguous()
     g_h_prev = torch.empty_like(h)
     g_id = torch.empty_like(h) if want_identity else None
-    _call("glam_gru_gates_bwd", _p(rzn), _p(gh), _p(h), _p(x_out), _p(g_x_out), _p(g_h_carry), N, C, act,
+    _call("glam_gru_gates_bwd_ex", _p(rzn), _p(gh_n), gh_n.stride(0), _p(h), _p(x_out), _p(g_x_out), _p(g_h_carry), N, C, act,
                                               float(act_param), _p(g_gi), _p(g_gh), _p(g_h_prev), _p(g_id), _stream(h))
     return g_gi, g_gh, g_h_prev, g_id
 

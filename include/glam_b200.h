@@ -155,6 +155,11 @@ int glam_gru_gates_fwd(float* gi_rzn, const float* gh, const float* h, const flo
 int glam_gru_gates_bwd(const float* rzn, const float* gh, const float* h, const float* x_out, const float* g_x_out,
                        const float* g_h_carry, int64_t num_nodes, int channels, int act, float act_param,
                        float* g_gi, float* g_gh, float* g_h_prev, float* g_identity, void* stream);
+/* Same with the n-gate hidden pre-activation passed on its own: row n at gh_n + n*ld_ghn (glam_gru_gates_bwd is this with
+ * gh_n = gh + 2C, ld_ghn = 3C); glam_gru_fused_fwd writes gh_n as a compact [N,C] tensor. */
+int glam_gru_gates_bwd_ex(const float* rzn, const float* gh_n, int64_t ld_ghn, const float* h, const float* x_out,
+                          const float* g_x_out, const float* g_h_carry, int64_t num_nodes, int channels, int act,
+                          float act_param, float* g_gi, float* g_gh, float* g_h_prev, float* g_identity, void* stream);
 /* LSTM cell gates for Set2Set (torch.nn.LSTM inside PyG Set2Set; src_1gp/model.py:41): gates [B,4C] (i,f,g,o,
  * pre-activation, overwritten with the activated gates), c_prev -> c_new, h_new. */
 int glam_lstm_gates_fwd(float* gates, const float* c_prev, int64_t rows, int channels, float* c_new, float* h_new,
@@ -205,6 +210,18 @@ int glam_pair_dot_pool_fwd(const float* xa, const float* xb, const int32_t* ptr_
 int glam_pair_dot_pool_bwd(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b,
                            const float* g_out, const int32_t* argmax, const float* sum_a, const float* sum_b,
                            int64_t num_pairs, int channels, float* g_xa, float* g_xb, void* stream);
+
+/* Fused GRU update (tf32 math mode, channels in {32,36,40,44}): both gate GEMMs (m W_ih^T, h W_hh^T) on the tensor cores
+ * into one TMEM accumulator (columns permuted per channel to r_pre, z_pre, gi_n, gh_n; the h-side product accumulates
+ * onto the m-side one), and the gate arithmetic of glam_gru_gates_fwd in the epilogue — the [N,3C] pre-activations
+ * never reach HBM.  Writes rzn [N,3C] (r|z|n, saved for backward), gh_n [N,C] (for glam_gru_gates_bwd_ex), h_new and
+ * x_out [N,C] (contiguous).  glam_gru_fused_supported(channels) tells whether the current math mode / shape can use it;
+ * otherwise call glam_gemm_ex twice + glam_gru_gates_fwd. */
+int glam_gru_fused_supported(int channels);
+int glam_gru_fused_fwd(const float* m, int64_t ldm, const float* h, int64_t ldh, const float* identity,
+                       const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int64_t N,
+                       int channels, int act, float act_param, float* rzn, float* gh_n, float* h_new, float* x_out,
+                       void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (7) Optimizer step of the data-parallel training step — torch.optim.Adam(model.parameters(), lr) as the reference

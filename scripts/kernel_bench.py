@@ -64,3 +64,10 @@ if which in ("all", "s2s"):
     timeit("s2s round_bwd (overwrite)", lambda: ops.set2set_round_bwd(x, gates, c0, c1, att, gptr, B, gu, gc, gx, False, Go), 4 * (2 * N * C + N + B * 13 * C))
     timeit("s2s round_bwd (accumulate)", lambda: ops.set2set_round_bwd(x, gates, c0, c1, att, gptr, B, gu, gc, gx, True, Go), 4 * (3 * N * C + N + B * 13 * C))
     timeit("s2s wgrad tn [12288,108]^T[12288,144]", lambda: ops.gemm_tn_ex(torch.randn(3 * B, 3 * C, device=dev), torch.randn(3 * B, 4 * C, device=dev), transpose_out=True, want_colsum=True), 4 * 3 * B * 7 * C)
+if which in ("all", "gru"):
+    m = torch.randn(N, C, device=dev); h = torch.randn(N, C, device=dev); w_hh = torch.randn(3 * C, C, device=dev)
+    timeit("gru fused fwd (2 GEMMs + gates)", lambda: ops.gru_fused_fwd(m, h, x, w_ih, w_hh, b3, b3, 3, 1.0), 4 * N * C * 9)
+    def unf():
+        gi = ops.gemm(m, w_ih, transpose_w=True, bias=b3); gh = ops.gemm(h, w_hh, transpose_w=True, bias=b3)
+        ops.gru_gates_fwd(gi, gh, h, x, 3, 1.0)
+    timeit("gru unfused fwd (3 launches)", unf, 4 * N * C * 9)

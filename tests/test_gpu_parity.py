@@ -532,3 +532,40 @@ def test_captured_train_steps_follow_oracle_training():
             torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=2e-3, atol=2e-4, msg=lambda s, n=n: f"{n}: {s}")
     finally:
         set_math_mode(prev)
+
+
+@pytest.mark.parametrize("N,C,act,with_id", [(1, 36, 3, True), (127, 36, 0, False), (128 * 3 + 5, 32, 1, True), (40_000, 36, 3, True),
+                                             (1000, 40, 2, True), (300, 44, 3, False)])
+def test_gru_fused_kernel_matches_gate_math(N, C, act, with_id):
+    """glam_gru_fused_fwd (two tcgen05 GEMMs + gates in the epilogue) against fp64 torch gate math; TF32 operand rounding
+    is the only difference (|W|,|x| ~ 1, K = C: abs error ~ 1e-3 on the pre-activations)."""
+    from glam_b200 import ops
+    from glam_b200._lib import set_math_mode, get_math_mode
+    prev = get_math_mode()
+    set_math_mode("tf32")
+    try:
+        g = torch.Generator().manual_seed(N + C)
+        m, h, ident = (torch.randn(N, C, generator=g) for _ in range(3))
+        w_ih, w_hh = (torch.randn(3 * C, C, generator=g) / C ** 0.5 for _ in range(2))
+        b_ih, b_hh = (torch.randn(3 * C, generator=g) * 0.1 for _ in range(2))
+        assert ops.gru_fused_supported(m.to(DEV), h.to(DEV), C)
+        d = lambda t: t.to(DEV)
+        rzn, gh, h_new, x_out = ops.gru_fused_fwd(d(m), d(h), d(ident) if with_id else None, d(w_ih), d(w_hh), d(b_ih), d(b_hh), act, 0.1)
+        torch.cuda.synchronize()
+        gi64 = m.double() @ w_ih.double().t() + b_ih.double()
+        gh64 = h.double() @ w_hh.double().t() + b_hh.double()
+        r = torch.sigmoid(gi64[:, :C] + gh64[:, :C]); z = torch.sigmoid(gi64[:, C:2 * C] + gh64[:, C:2 * C])
+        n = torch.tanh(gi64[:, 2 * C:] + r * gh64[:, 2 * C:])
+        hn = (1 - z) * n + z * h.double()
+        pre = hn + (ident.double() if with_id else 0)
+        xo = {0: pre, 1: torch.relu(pre), 2: torch.nn.functional.leaky_relu(pre, 0.1), 3: torch.nn.functional.celu(pre)}[act]
+        tol = dict(rtol=0, atol=5e-3)
+        torch.testing.assert_close(rzn.cpu().double(), torch.cat([r, z, n], 1), **tol)
+        torch.testing.assert_close(gh.cpu().double(), gh64[:, 2 * C:], **tol)
+        torch.testing.assert_close(h_new.cpu().double(), hn, **tol)
+        torch.testing.assert_close(x_out.cpu().double(), xo, **tol)
+        # and bit-identical run to run
+        again = ops.gru_fused_fwd(d(m), d(h), d(ident) if with_id else None, d(w_ih), d(w_hh), d(b_ih), d(b_hh), act, 0.1)
+        assert torch.equal(again[3], x_out) and torch.equal(again[0], rzn)
+    finally:
+        set_math_mode(prev)
