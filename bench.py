@@ -157,7 +157,7 @@ def run_reference(args):
                                        "restatement of the reference's unfused layer.py path; the reference itself needs "
                                        "torch_geometric, absent from this image)"},
             "e2e": {"value": gps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ roofline of the top kernel
@@ -371,7 +371,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": gps, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "6 training steps on 512-graph slices of the same synthetic workload "
                                               "(oracle/glam_oracle.py, all host threads)"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         # all ranks leave together; the captured graph holds NCCL kernels, so drop it before the communicator and skip
         # the (occasionally hanging) communicator teardown: the process is exiting anyway
@@ -380,6 +380,17 @@ def run_ours(args):
         del ts
         sys.stdout.flush()
         os._exit(0)
+
+
+_JSON_FD = None
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -392,6 +403,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # exactly ONE line on stdout: native libraries (NCCL prints its version banner there) get stderr instead
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -50,6 +50,10 @@ SIGNATURES = {
     "glam_seg_attn_pool_bwd": (I32, [P, I64, P, I64, P, P, I64, P, P, I64, I32, I32, P, I64, P, P, P]),
     "glam_gru_fused_supported": (I32, [I32]),
     "glam_gru_fused_fwd": (I32, [P, I64, P, I64, P, P, P, P, P, I64, I32, I32, F32, P, P, P, P, P]),
+    "glam_pool5_fwd": (I32, [P, I64, P, I64, I32, P, P, P]),
+    "glam_pool5_bwd": (I32, [P, P, P, I64, I32, P, I64, P]),
+    "glam_csr_aggregate": (I32, [P, I64, P, P, P, P, P, P, I64, I32, P, I64, I32, P]),
+    "glam_gcn_norm": (I32, [P, P, P, P, I64, P, P, P, P]),
     "glam_adam_step": (I32, [P, P, P, P, I64, P, P, F32, F32, F32, F32, F32, P]),
     "glam_set2set_round_fwd": (I32, [P, I64, P, I64, I32, P, P, P, P, P, P, P]),
     "glam_set2set_round_bwd": (I32, [P, I64, P, I64, I32, P, P, P, P, P, I64, I32, P, P, I32, P, P]),

@@ -447,3 +447,53 @@ class TripletPrepFn(Function):
         g_wn, g_we, g_att = ops.triplet_prep_bwd(weight_node, weight_edge, att, _c(g_w_ext), _c(g_att_edge), None,
                                                  channels, heads, edge_dim, light, ldxp)
         return g_wn, g_we, g_att, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# "next" rows (SURVEY.md §8f): GlobalPool5 readout, GCN tower
+# --------------------------------------------------------------------------------------------------
+class Pool5Fn(Function):
+    """[mean | sum | sort-pool(k=3)] per graph (src_1gp/layer.py:197-203)."""
+
+    @staticmethod
+    def forward(ctx, x, gptr, num_graphs):
+        x = _c(x)
+        ops._need_cuda(x)
+        out, top = ops.pool5_fwd(x, gptr, num_graphs)
+        ctx.save_for_backward(gptr, top)
+        ctx.cfg = (num_graphs, x.shape[0], x.shape[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        gptr, top = ctx.saved_tensors
+        B, N, C = ctx.cfg
+        return ops.pool5_bwd(_c(g_out), gptr, top, B, N, C), None, None
+
+
+class GCNConvFn(Function):
+    """PyG GCNConv(in,out) @1.7.2: D^-1/2 (A + I) D^-1/2 (x W) + b over the cached graph index; backward aggregates over the
+    source-sorted CSR (the transposed normalised adjacency) — no atomics."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, g, norm):
+        x, weight, bias = map(_c, (x, weight, bias))
+        ops._need_cuda(x, weight)
+        dinv2, w_dst, w_src = norm
+        xw = ops.gemm(x, weight)                                                   # [N,out]
+        out = ops.csr_aggregate(xw, g.dst_rowptr, g.dst_src, edge_w=w_dst, self_w=dinv2, bias=bias)
+        ctx.save_for_backward(x, weight, dinv2, w_src)
+        ctx.g = g
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, weight, dinv2, w_src = ctx.saved_tensors
+        g = ctx.g
+        g_out = _c(g_out)
+        g_xw = ops.csr_aggregate(g_out, g.src_rowptr, g.src_dst, edge_w=w_src, self_w=dinv2)
+        g_w, _ = ops.gemm_tn_ex(x, g_xw)                                           # [in,out]
+        g_b = ops.colsum(g_out) if ctx.has_bias else None
+        g_x = ops.gemm(g_xw, weight, transpose_w=True) if ctx.needs_input_grad[0] else None
+        return g_x, g_w, g_b, None, None

@@ -36,6 +36,14 @@ class GraphIndex:
         self.src_dst = csr["src_dst"]
         self._edge_attr_key = None
         self._edge_attr_sorted = None
+        self._gcn = None
+
+    def gcn_norm(self):
+        """(dinv^2 [N], w_dst [E], w_src [E]) of PyG GCNConv's normalisation, computed once per batch."""
+        if self._gcn is None:
+            dinv, w_dst, w_src = ops.gcn_norm(self)
+            self._gcn = (dinv * dinv, w_dst, w_src)
+        return self._gcn
 
     def sorted_edge_attr(self, edge_attr: torch.Tensor) -> torch.Tensor:
         """edge_attr rows permuted into destination order (done once per batch, reused by every step)."""

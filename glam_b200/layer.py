@@ -149,7 +149,41 @@ def _third_party(name):
     return _Missing
 
 
-_NNConv, _GCNConv, _GATConv = _third_party("_NNConv"), _third_party("_GCNConv"), _third_party("_GATConv")
+class GCNConv(nn.Module):
+    """PyG GCNConv(in_channels, out_channels) @1.7.2 defaults (self loops, symmetric normalisation, bias): parameters
+    `weight [in,out]` (glorot) and `bias [out]` (zeros), as `_GCNConv` builds it (src_1gp/layer.py:143-149)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = Parameter(torch.empty(in_channels, out_channels))
+        self.bias = Parameter(torch.empty(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        bound = (6.0 / (self.in_channels + self.out_channels)) ** 0.5
+        nn.init.uniform_(self.weight, -bound, bound)
+        zeros_(self.bias)
+
+    def forward(self, x, edge_index, edge_weight=None):
+        if edge_weight is not None:
+            raise NotImplementedError("GCNConv: edge weights are not used by the reference (layer.py:149 passes none)")
+        g = G.graph_index(edge_index, x.shape[0])
+        return Fn.GCNConvFn.apply(x, self.weight, self.bias, g, g.gcn_norm())
+
+
+class _GCNConv(nn.Module):
+    """src_1gp/layer.py:143-149 (default protein block of the drug-target model, src_2gi_dti_scr/run.py:19)."""
+
+    def __init__(self, in_dim, out_dim, edge_in_dim):
+        super().__init__()
+        self.conv = GCNConv(in_dim, out_dim)
+
+    def forward(self, x, edge_index, edge_attr):
+        return self.conv(x, edge_index)
+
+
+_NNConv, _GATConv = _third_party("_NNConv"), _third_party("_GATConv")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -287,12 +321,17 @@ class Set2Set(nn.Module):
 
 
 class GlobalPool5(nn.Module):
-    """mean | sum | sort-pool(k=3) readout (src_1gp/layer.py:197-203); torch ops, not on the hot path."""
+    """mean | sum | sort-pool(k=3) readout (src_1gp/layer.py:197-203; the reference's default mol_readout): one warp per
+    graph (csrc/pool5.cu).  `composed_forward` is the same thing in torch ops, kept as an independent cross-check."""
 
     def __init__(self, **params):
         super().__init__()
 
     def forward(self, x, batch, num_graphs=None):
+        gptr, B = G.graph_ptr(batch, num_graphs)
+        return Fn.Pool5Fn.apply(x, gptr, B)
+
+    def composed_forward(self, x, batch, num_graphs=None):
         B = int(batch[-1]) + 1 if num_graphs is None else num_graphs
         C = x.shape[1]
         total = x.new_zeros((B, C)).index_add_(0, batch, x)

@@ -125,8 +125,8 @@ class ArchitectureDTI(_PairArchitecture):
     prefixes = ("mol", "pro")
 
     def __init__(self, mol_in_dim=15, pro_in_dim=49, mol_edge_in_dim=4, pro_edge_in_dim=8, hid_dim_alpha=4, e_dim=1024,
-                 out_dim=1, mol_block="_TripletMessage", pro_block="_TripletMessage", message_steps=3,
-                 mol_readout="Set2Set", pro_readout="Set2Set",
+                 out_dim=1, mol_block="_TripletMessage", pro_block="_GCNConv", message_steps=3,
+                 mol_readout="GlobalPool5", pro_readout="GlobalPool5",
                  pre_norm="_None", graph_norm="_None", flat_norm="_None", end_norm="_None",
                  pre_do="_None()", graph_do="Dropout(0.2)", flat_do="_None()", end_do="Dropout(0.2)",
                  pre_act="RReLU", graph_act="RReLU", flat_act="RReLU", end_act="RReLU", graph_res=True):

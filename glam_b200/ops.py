@@ -350,6 +350,43 @@ def pair_dot_pool_bwd(xa, xb, ptr_a, ptr_b, g_out, argmax, sa, sb, num_pairs):
     return g_xa, g_xb
 
 
+# ------------------------------------------------------------------------------------------------ next rows (§8f)
+def pool5_fwd(x, gptr, num_graphs):
+    N, C = x.shape
+    out = torch.empty((num_graphs, 5 * C), dtype=torch.float32, device=x.device)
+    top = torch.empty((num_graphs, 3), dtype=torch.int32, device=x.device)
+    _call("glam_pool5_fwd", _p(x), x.stride(0), _p(gptr), num_graphs, C, _p(out), _p(top), _stream(x))
+    return out, top
+
+
+def pool5_bwd(g_out, gptr, top, num_graphs, N, C):
+    g_x = torch.empty((N, C), dtype=torch.float32, device=g_out.device)
+    _call("glam_pool5_bwd", _p(g_out), _p(gptr), _p(top), num_graphs, C, _p(g_x), g_x.stride(0), _stream(g_out))
+    return g_x
+
+
+def csr_aggregate(Y, rowptr, col, edge_w=None, self_w=None, row_scale=None, bias=None, out=None, accumulate=False):
+    _need_cuda(Y)
+    assert Y.dim() == 2 and Y.stride(1) == 1
+    N, F = Y.shape
+    if out is None:
+        out = torch.empty((N, F), dtype=torch.float32, device=Y.device)
+    _call("glam_csr_aggregate", _p(Y), Y.stride(0), _p(rowptr), _p(col), _p(edge_w), _p(self_w), _p(row_scale), _p(bias), N, F,
+          _p(out), out.stride(0), 1 if accumulate else 0, _stream(Y))
+    return out
+
+
+def gcn_norm(g):
+    """(dinv [N], w_dst [E], w_src [E]) of PyG GCNConv's symmetric normalisation for the graph index g."""
+    dev = g.dst_rowptr.device
+    dinv = torch.empty((g.num_nodes,), dtype=torch.float32, device=dev)
+    w_dst = torch.empty((g.num_edges,), dtype=torch.float32, device=dev)
+    w_src = torch.empty((g.num_edges,), dtype=torch.float32, device=dev)
+    _call("glam_gcn_norm", _p(g.dst_rowptr), _p(g.dst_src), _p(g.src_rowptr), _p(g.src_dst), g.num_nodes, _p(dinv), _p(w_dst),
+          _p(w_src), _stream(dinv))
+    return dinv, w_dst, w_src
+
+
 # ------------------------------------------------------------------------------------------------ optimizer
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, state, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
               grad_scale=1.0):

@@ -224,6 +224,29 @@ int glam_gru_fused_fwd(const float* m, int64_t ldm, const float* h, int64_t ldh,
                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * (6b) "Next" rows of the scope table: the reference's default readout and its GCN tower.
+ *
+ * glam_pool5_fwd/bwd — GlobalPool5 (src_1gp/layer.py:197-203; default mol_readout, src_1gp/run.py:25):
+ *   out [B,5C] = [mean | sum | PyG global_sort_pool(k=3): rows sorted by the last channel, descending, ties by node
+ *   order, missing rows zero]; top_idx [B,3] = chosen node ids (-1 = missing), saved for backward.
+ * glam_csr_aggregate — out[i,:] = (accumulate ? out[i,:] : 0) + row_scale[i] * (sum_{p in row i} edge_w[p] * Y[col[p],:]
+ *   + self_w[i] * Y[i,:]) + bias; edge_w / self_w / row_scale / bias may be NULL (1 / 0 / 1 / 0).  Deterministic.
+ * glam_gcn_norm — PyG GCNConv(in,out) normalisation @1.7.2 (`_GCNConv`, src_1gp/layer.py:143-149; default pro_block,
+ *   src_2gi_dti_scr/run.py:19): self edges are replaced by one unit self loop per node, dinv[i] = (1 + non-self
+ *   in-degree)^-1/2, w_dst[p] = dinv[dst] dinv[src] in destination order (0 on self edges), w_src likewise in source order
+ *   (for the transposed aggregation of backward; may be NULL).  out = aggregate(x W, w_dst, self_w = dinv^2) + bias.
+ * --------------------------------------------------------------------------------------------- */
+int glam_pool5_fwd(const float* x, int64_t ldx, const int32_t* graph_ptr, int64_t num_graphs, int channels, float* out,
+                   int32_t* top_idx, void* stream);
+int glam_pool5_bwd(const float* g_out, const int32_t* graph_ptr, const int32_t* top_idx, int64_t num_graphs, int channels,
+                   float* g_x, int64_t ldgx, void* stream);
+int glam_csr_aggregate(const float* Y, int64_t ldy, const int32_t* rowptr, const int32_t* col, const float* edge_w,
+                       const float* self_w, const float* row_scale, const float* bias, int64_t num_rows, int features,
+                       float* out, int64_t ldo, int accumulate, void* stream);
+int glam_gcn_norm(const int32_t* dst_rowptr, const int32_t* dst_src, const int32_t* src_rowptr, const int32_t* src_dst,
+                  int64_t num_nodes, float* dinv, float* w_dst, float* w_src, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * (7) Optimizer step of the data-parallel training step — torch.optim.Adam(model.parameters(), lr) as the reference
  * trainer builds it (src_1gp/trainer.py:49-50): one pass over flat fp32 buffers (parameters, the all-reduced gradient
  * bucket, both moments).  lr [1] and state [3] = {step, 1-beta1^step, 1-beta2^step} are device memory (CUDA-graph

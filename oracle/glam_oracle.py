@@ -181,6 +181,38 @@ def dot_and_global_pool2(mol_out, pro_out, mol_batch, pro_batch):
 # module mirrors (same parameter names / registration order / init as the reference, so that
 # state_dicts interchange with the reference and with glam_b200.layer)
 # --------------------------------------------------------------------------------------------------
+def global_pool5(x, batch, num_graphs):
+    """GlobalPool5 (src_1gp/layer.py:197-203): [global_mean_pool | global_add_pool | global_sort_pool(k=3)]; the sort
+    pool keeps each graph's first 3 rows by last channel, descending, ties in node order, zero padded
+    (PyG global_sort_pool @1.7.2)."""
+    C = x.shape[1]
+    total = seg_sum(x, batch, num_graphs)
+    cnt = torch.bincount(batch, minlength=num_graphs).clamp(min=1).to(x.dtype).view(-1, 1)
+    top = x.new_zeros((num_graphs, 3, C))
+    for g in range(num_graphs):
+        idx = (batch == g).nonzero().view(-1)
+        if idx.numel() == 0:
+            continue
+        order = torch.argsort(x[idx, -1], descending=True, stable=True)[:3]
+        top[g, :order.numel()] = x[idx[order]]
+    return torch.cat([total / cnt, total, top.view(num_graphs, 3 * C)], dim=-1)
+
+
+def gcn_conv(x, edge_index, weight, bias):
+    """PyG GCNConv(in,out) @1.7.2 defaults as `_GCNConv` builds it (src_1gp/layer.py:143-149): existing self edges are
+    replaced by one unit self loop per node, symmetric normalisation by in-degree, linear, sum aggregation, bias."""
+    N = x.shape[0]
+    src, dst = edge_index[0], edge_index[1]
+    keep = src != dst
+    loops = torch.arange(N)
+    src, dst = torch.cat([src[keep], loops]), torch.cat([dst[keep], loops])
+    deg = torch.zeros(N, dtype=x.dtype).index_add_(0, dst, torch.ones(dst.numel(), dtype=x.dtype))
+    dis = deg.pow(-0.5)
+    norm = dis[src] * dis[dst]
+    xw = _mm(x, weight)
+    return seg_sum(norm.view(-1, 1) * xw[src], dst, N) + bias
+
+
 class TripletMessage(nn.Module):
     """src_1gp/layer.py:15-64."""
 
@@ -253,7 +285,29 @@ class _PairNorm(nn.Module):
         return pair_norm(x, batch)
 
 
-_CONVS = {"_TripletMessage": _TripletMessage, "_TripletMessageLight": _TripletMessageLight}
+class _GCNInner(nn.Module):
+    """PyG GCNConv parameters: weight [in,out] (glorot), bias [out] (zeros)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(in_channels, out_channels))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        bound = math.sqrt(6.0 / (in_channels + out_channels))
+        nn.init.uniform_(self.weight, -bound, bound)
+
+
+class _GCNConv(nn.Module):
+    """src_1gp/layer.py:143-149."""
+
+    def __init__(self, in_dim, out_dim, edge_in_dim):
+        super().__init__()
+        self.conv = _GCNInner(in_dim, out_dim)
+
+    def forward(self, x, edge_index, edge_attr):
+        return gcn_conv(x, edge_index, self.conv.weight, self.conv.bias)
+
+
+_CONVS = {"_TripletMessage": _TripletMessage, "_TripletMessageLight": _TripletMessageLight, "_GCNConv": _GCNConv}
 _NORMS = {"_None": _None, "_PairNorm": _PairNorm}
 _ACTS = {"_None": _None, "ReLU": nn.ReLU, "CELU": nn.CELU, "LeakyReLU": nn.LeakyReLU, "RReLU": nn.RReLU}
 
@@ -275,6 +329,8 @@ class MessageBlock(nn.Module):
         self.dropout = _make_dropout(dropout)
         self.conv = _CONVS[conv](in_dim, out_dim, in_edge_dim)
         self.gru = nn.GRU(in_dim, out_dim)
+        if conv in ("_GCNConv", "_GATConv"):
+            self.gru = None                                  # :248
         self.act = _ACTS[act]()
         self.res = res
 
@@ -284,6 +340,9 @@ class MessageBlock(nn.Module):
             h = x.unsqueeze(0)                               # :254 (pre-norm x)
         x = self.dropout(self.norm(x, batch))                # :255-256
         x = self.conv(x, edge_index, edge_attr)              # :259
+        if self.gru is None:                                 # :260 (GCN / GAT blocks have no GRU)
+            x = x + identity if self.res else x
+            return self.act(x), h
         x = F.celu(x)                                        # :261
         hn = gru_cell(x, h[0], self.gru.weight_ih_l0, self.gru.weight_hh_l0,
                       self.gru.bias_ih_l0, self.gru.bias_hh_l0)  # :262
@@ -326,7 +385,18 @@ class Set2Set(nn.Module):
                        self.processing_steps)
 
 
-_READOUTS = {"Set2Set": Set2Set, "GlobalLAPool": GlobalLAPool}
+class GlobalPool5(nn.Module):
+    """src_1gp/layer.py:197-203."""
+
+    def __init__(self, **params):
+        super().__init__()
+
+    def forward(self, x, batch):
+        return global_pool5(x, batch, int(batch[-1]) + 1)
+
+
+_READOUTS = {"Set2Set": Set2Set, "GlobalLAPool": GlobalLAPool, "GlobalPool5": GlobalPool5}
+_READOUT_WIDTH = {"Set2Set": 2, "GlobalLAPool": 2, "GlobalPool5": 5}
 
 
 class LinearBlock(nn.Module):
@@ -358,7 +428,7 @@ class ArchitectureGP(nn.Module):
                                      conv=mol_block, act=graph_act, res=graph_res)
         self.message_steps = message_steps
         self.mol_readout = _READOUTS[mol_readout](in_channels=hid, processing_steps=3)
-        self.mol_flat = LinearBlock(2 * hid, e_dim, norm=flat_norm, dropout=flat_do, act=flat_act)
+        self.mol_flat = LinearBlock(_READOUT_WIDTH[mol_readout] * hid, e_dim, norm=flat_norm, dropout=flat_do, act=flat_act)
         self.lin_out1 = LinearBlock(e_dim, out_dim, norm=end_norm, dropout=end_do, act="_None")
 
     def forward(self, data_mol):
@@ -394,8 +464,8 @@ class ArchitecturePair(nn.Module):
         for p, din, de, blk, ro in ((self.pa, a_in_dim, a_edge_in_dim, a_block, a_readout),
                                     (self.pb, b_in_dim, b_edge_in_dim, b_block, b_readout)):
             mods[p + "_readout"] = _READOUTS[ro](in_channels=hid, processing_steps=3)
-        for p in (self.pa, self.pb):
-            mods[p + "_flat"] = LinearBlock(2 * hid, hid, act=flat_act)
+        for p, ro in ((self.pa, a_readout), (self.pb, b_readout)):
+            mods[p + "_flat"] = LinearBlock(_READOUT_WIDTH[ro] * hid, hid, act=flat_act)
         for k, v in mods.items():
             self.add_module(k, v)
         self.lin_out0 = LinearBlock(hid * 2 + message_steps * 2, e_dim, act=end_act)

@@ -169,6 +169,92 @@ def case_model_ddi(model_mod, seed, Din=9, De=3, B=6):
     return d
 
 
+def case_pool5(layer, C, seed, dtype, sizes=None):
+    """GlobalPool5 incl. graphs with fewer than k=3 nodes and tied keys in the sort channel."""
+    torch.manual_seed(seed)
+    if sizes is None:
+        b = make_molecule_batch(6, node_dim=C, edge_dim=3, seed=seed, features="normal")
+        x, batch = b.x, b.batch
+    else:
+        batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+        x = torch.randn(int(sum(sizes)), C)
+        x[-4:-2, -1] = 0.5                       # a tie inside the last graph
+    mod = layer.GlobalPool5()
+    x = x.to(dtype).requires_grad_(True)
+    out = mod(x, batch)
+    cot = torch.randn(out.shape).to(dtype)
+    g = grads_of(out, cot, [x])
+    return {"x": x.detach(), "batch": batch, "cot": cot, "out": out.detach(), "grad_x": g[0]}
+
+
+def case_gcn_layer(layer, C, seed, dtype, protein=False):
+    torch.manual_seed(seed)
+    if protein:
+        b = make_protein_batch(3, node_dim=C, edge_dim=8, seed=seed, min_len=30, max_len=60)
+        x = torch.randn(b.x.shape[0], C)
+        ei = torch.cat([b.edge_index, torch.tensor([[0, 5, 5], [0, 5, 5]])], dim=1)      # explicit + duplicate self loops
+    else:
+        b = make_molecule_batch(4, node_dim=C, edge_dim=3, seed=seed, features="normal")
+        x, ei = b.x, b.edge_index
+    mod = layer._GCNConv(C, C, 3)
+    with torch.no_grad():
+        mod.conv.bias.uniform_(-0.1, 0.1)
+    mod = mod.to(dtype)
+    x = x.to(dtype).requires_grad_(True)
+    out = mod(x, ei, None)
+    cot = torch.randn(out.shape).to(dtype)
+    params = list(mod.parameters())
+    g = grads_of(out, cot, [x] + params)
+    return {"x": x.detach(), "edge_index": ei, "cot": cot,
+            "state": {k: v.detach().clone() for k, v in mod.state_dict().items()},
+            "out": out.detach(), "grad_x": g[0],
+            "grad_params": {n: gg for (n, _), gg in zip(mod.named_parameters(), g[1:])}}
+
+
+def case_model_dti(model_mod, seed, Din=9, De=3, Pin=49, Pe=8, B=4):
+    """The drug-target model with the reference's default protein block and readouts (src_2gi_dti_scr/run.py:18-25)."""
+    torch.manual_seed(seed)
+    a = make_molecule_batch(B, node_dim=Din, edge_dim=De, seed=seed, features="chem", targets="binary")
+    p = make_protein_batch(B, node_dim=Pin, edge_dim=Pe, seed=seed + 3, min_len=40, max_len=80)
+    m = model_mod.Model(Din, Pin, De, Pe, hid_dim_alpha=4, e_dim=32, out_dim=1, mol_block="_TripletMessage",
+                        pro_block="_GCNConv", message_steps=3, mol_readout="GlobalPool5", pro_readout="GlobalPool5",
+                        graph_do="_None()", end_do="_None()", pre_act="ReLU", graph_act="LeakyReLU", flat_act="CELU", end_act="ReLU")
+    # graph_act must not produce exact ties in the sort-pool key (ReLU zeros): PyG sorts with an unstable torch.sort, so
+    # which of several tied rows is kept is not defined by the reference
+    m.eval()
+    ns = lambda b: types.SimpleNamespace(x=b.x, edge_index=b.edge_index, edge_attr=b.edge_attr, batch=b.batch)
+    out = m(ns(a), ns(p))
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(out, a.y)
+    g = torch.autograd.grad(loss, list(m.parameters()))
+    pack = lambda b, q: {q + "x": b.x, q + "edge_index": b.edge_index, q + "edge_attr": b.edge_attr, q + "batch": b.batch}
+    d = {"y": a.y, "cfg": {"Din": Din, "De": De, "Pin": Pin, "Pe": Pe, "e_dim": 32},
+         "state": {k: v.detach().clone() for k, v in m.state_dict().items()},
+         "out": out.detach(), "loss": loss.detach(),
+         "grad_params": {n: gg.clone() for (n, _), gg in zip(m.named_parameters(), g)}}
+    d.update(pack(a, "a_")); d.update(pack(p, "b_"))
+    return d
+
+
+def main_next():
+    """Fixtures for the SURVEY.md §8(f) rows added after the first golden set (kept in their own file)."""
+    layer = load_ref("src_1gp", "layer")
+    fx = {}
+    for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        fx[f"pool5_C36_{tag}"] = case_pool5(layer, 36, 1301, dtype)
+        fx[f"pool5_small_C30_{tag}"] = case_pool5(layer, 30, 1302, dtype, sizes=[1, 2, 3, 7, 40, 6])
+        fx[f"gcn_C36_{tag}"] = case_gcn_layer(layer, 36, 1303, dtype)
+        fx[f"gcn_protein_C30_{tag}"] = case_gcn_layer(layer, 30, 1304, dtype, protein=True)
+        fx[f"block_gcn_C36_{tag}"] = case_block(layer, "_GCNConv", "_None", "ReLU", True, 36, 3, 1305, dtype, steps=2)
+    for k in [k for k in fx if k.endswith("_f64")]:
+        fx[k].pop("state", None)
+        for name in ("edge_index", "batch", "cfg", "x", "cot", "coth", "edge_attr"):
+            fx[k].pop(name, None)
+    model_dti = load_ref("src_2gi_dti_scr", "model")
+    fx["dti_gcn_pool5"] = case_model_dti(model_dti, 1306)
+    torch.save(fx, os.path.join(OUT, "next.pt"))
+    print("next.pt", os.path.getsize(os.path.join(OUT, "next.pt")) // 1024, "KiB")
+
+
 def main():
     layer = load_ref("src_1gp", "layer")
     layer_ddi = load_ref("src_2gi_ddi", "layer")
@@ -209,4 +295,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "next":
+        main_next()
+    else:
+        main()

@@ -358,7 +358,8 @@ def test_dti_shaped_pair_vs_oracle(math_mode):
     kw = dict(hid_dim_alpha=2, e_dim=64, out_dim=2, message_steps=2)
     o32 = O.ArchitecturePair(15, 49, 4, 8, prefixes=("mol", "pro"), graph_act="CELU", **kw).eval()
     m = model.ArchitectureDTI(15, 49, 4, 8, graph_do="_None()", end_do="_None()", pre_act="ReLU", graph_act="CELU",
-                              flat_act="ReLU", end_act="ReLU", **kw)
+                              flat_act="ReLU", end_act="ReLU", pro_block="_TripletMessage", mol_readout="Set2Set",
+                              pro_readout="Set2Set", **kw)
     m.load_state_dict(o32.state_dict())
     m = m.to(DEV).eval()
     o64 = copy.deepcopy(o32).double()
@@ -569,3 +570,77 @@ def test_gru_fused_kernel_matches_gate_math(N, C, act, with_id):
         assert torch.equal(again[3], x_out) and torch.equal(again[0], rzn)
     finally:
         set_math_mode(prev)
+
+
+# ---------------------------------------------------------------------------------------------- §8(f) rows
+@pytest.mark.parametrize("name,C", [("pool5_C36", 36), ("pool5_small_C30", 30)])
+def test_pool5_golden(golden_next, name, C):
+    """GlobalPool5 kernel against the reference's own output (graphs with < 3 nodes, tied sort keys)."""
+    from glam_b200 import layer
+    c32, c64 = golden_next[f"{name}_f32"], case(golden_next, f"{name}_f64")
+    m = layer.GlobalPool5()
+    x = c32["x"].to(DEV).requires_grad_(True)
+    out = m(x, c32["batch"].to(DEV))
+    tol_check(out, c32["out"], c64["out"], f"{name}.out")
+    (out * c32["cot"].to(DEV)).sum().backward()
+    tol_check(x.grad, c32["grad_x"], c64["grad_x"], f"{name}.grad_x")
+    x2 = c32["x"].to(DEV)
+    assert torch.allclose(m.composed_forward(x2, c32["batch"].to(DEV)), out.detach(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,C", [("gcn_C36", 36), ("gcn_protein_C30", 30)])
+def test_gcn_conv_golden(golden_next, name, C, math_mode):
+    from glam_b200 import layer
+    c32, c64 = golden_next[f"{name}_f32"], case(golden_next, f"{name}_f64")
+    m = _load(layer._GCNConv(C, C, 3), c32["state"])
+    x = c32["x"].to(DEV).requires_grad_(True)
+    out = m(x, c32["edge_index"].to(DEV), None)
+    tol_check(out, c32["out"], c64["out"], f"{name}.out")
+    (out * c32["cot"].to(DEV)).sum().backward()
+    tol_check(x.grad, c32["grad_x"], c64["grad_x"], f"{name}.grad_x")
+    _check_param_grads(m, c32["grad_params"], c64["grad_params"], name)
+
+
+def test_gcn_block_golden(golden_next, math_mode):
+    from glam_b200 import layer
+    name = "block_gcn_C36"
+    c32, c64 = golden_next[f"{name}_f32"], case(golden_next, f"{name}_f64")
+    cfg = c32["cfg"]
+    blk = _load(layer.MessageBlock(cfg["C"], cfg["C"], cfg["De"], norm=cfg["norm"], dropout="_None()", conv=cfg["conv"],
+                                   act=cfg["act"], res=cfg["res"]), c32["state"])
+    x0 = c32["x"].to(DEV).requires_grad_(True)
+    ei, ea, batch = c32["edge_index"].to(DEV), c32["edge_attr"].to(DEV), c32["batch"].to(DEV)
+    xs, h = blk.run_steps(x0, ei, ea, cfg["steps"], batch=batch)
+    tol_check(xs[-1], c32["out"], c64["out"], f"{name}.out")
+    tol_check(h, c32["h"], c64["h"], f"{name}.h")
+    ((xs[-1] * c32["cot"].to(DEV)).sum() + (h * c32["coth"].to(DEV)).sum()).backward()
+    tol_check(x0.grad, c32["grad_x"], c64["grad_x"], f"{name}.grad_x")
+    _check_param_grads(blk, c32["grad_params"], c64["grad_params"], name)
+
+
+def test_model_dti_reference_defaults_golden(golden_next, math_mode):
+    """Drug-target model with the reference's default protein block (_GCNConv) and readouts (GlobalPool5) against the
+    reference's own output and parameter gradients."""
+    from glam_b200 import model
+    c = golden_next["dti_gcn_pool5"]
+    cfg = c["cfg"]
+    m = model.ArchitectureDTI(cfg["Din"], cfg["Pin"], cfg["De"], cfg["Pe"], hid_dim_alpha=4, e_dim=cfg["e_dim"], out_dim=1,
+                              mol_block="_TripletMessage", pro_block="_GCNConv", message_steps=3, mol_readout="GlobalPool5",
+                              pro_readout="GlobalPool5", graph_do="_None()", end_do="_None()", pre_act="ReLU",
+                              graph_act="LeakyReLU", flat_act="CELU", end_act="ReLU")
+    m = _load(m, c["state"]).eval()
+    da = ns(c["a_x"].to(DEV), c["a_edge_index"].to(DEV), c["a_edge_attr"].to(DEV), c["a_batch"].to(DEV))
+    db = ns(c["b_x"].to(DEV), c["b_edge_index"].to(DEV), c["b_edge_attr"].to(DEV), c["b_batch"].to(DEV))
+    out = m(da, db)
+    tf32 = math_mode == "tf32"
+    torch.testing.assert_close(out.cpu(), c["out"], rtol=2e-2 if tf32 else 2e-4, atol=2e-2 if tf32 else 2e-5)
+    torch.nn.functional.binary_cross_entropy_with_logits(out, c["y"].to(DEV)).backward()
+    for n, p in m.named_parameters():
+        ref = c["grad_params"][n]
+        scale = ref.abs().max().clamp(min=1e-6)
+        err = (p.grad.cpu() - ref).abs().max() / scale
+        cos = torch.nn.functional.cosine_similarity(p.grad.cpu().flatten(), ref.flatten(), dim=0)
+        if tf32:                         # max-routing of the dot-pool can flip under TF32 (see test_model_ddi_golden)
+            assert err < 2e-1 and cos > 0.999, f"{n}: rel err {err:.3e}, cos {cos:.6f}"
+        else:
+            assert err < 2e-3, f"{n}: rel err {err:.3e}"

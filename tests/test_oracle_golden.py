@@ -136,3 +136,53 @@ def test_seeded_init_matches_reference(golden_layers):
     m = O.TripletMessage(36, 3)
     for k in ("weight_node", "weight_edge", "weight_triplet_att", "weight_scale"):
         torch.testing.assert_close(m.state_dict()[k], c["state"][k], rtol=0, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------- §8(f) rows
+@pytest.mark.parametrize("name", ["pool5_C36", "pool5_small_C30"])
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_oracle_pool5_matches_reference(golden_next, name, tag):
+    from oracle import glam_oracle as O
+    c = case(golden_next, f"{name}_{tag}")
+    x = c["x"].clone().requires_grad_(True)
+    out = O.global_pool5(x, c["batch"], int(c["batch"][-1]) + 1)
+    tol = dict(rtol=1e-10, atol=1e-12) if tag == "f64" else dict(rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out, c["out"], **tol)
+    (out * c["cot"]).sum().backward()
+    torch.testing.assert_close(x.grad, c["grad_x"], **tol)
+
+
+@pytest.mark.parametrize("name", ["gcn_C36", "gcn_protein_C30"])
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_oracle_gcn_matches_reference(golden_next, name, tag):
+    from oracle import glam_oracle as O
+    c = case(golden_next, f"{name}_{tag}")
+    x = c["x"].clone().requires_grad_(True)
+    w = c["state"]["conv.weight"].clone().requires_grad_(True)
+    b = c["state"]["conv.bias"].clone().requires_grad_(True)
+    out = O.gcn_conv(x, c["edge_index"], w, b)
+    tol = dict(rtol=1e-10, atol=1e-12) if tag == "f64" else dict(rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out, c["out"], **tol)
+    (out * c["cot"]).sum().backward()
+    torch.testing.assert_close(x.grad, c["grad_x"], **tol)
+    torch.testing.assert_close(w.grad, c["grad_params"]["conv.weight"], **tol)
+    torch.testing.assert_close(b.grad, c["grad_params"]["conv.bias"], **tol)
+
+
+def test_oracle_dti_model_matches_reference(golden_next):
+    """Drug-target wiring with the reference's default protein block and readouts (src_2gi_dti_scr/model.py, run.py:18-25)."""
+    from oracle import glam_oracle as O
+    c = golden_next["dti_gcn_pool5"]
+    cfg = c["cfg"]
+    m = O.ArchitecturePair(cfg["Din"], cfg["Pin"], cfg["De"], cfg["Pe"], prefixes=("mol", "pro"), hid_dim_alpha=4,
+                           e_dim=cfg["e_dim"], out_dim=1, a_block="_TripletMessage", b_block="_GCNConv", message_steps=3,
+                           a_readout="GlobalPool5", b_readout="GlobalPool5", graph_act="LeakyReLU", pre_act="ReLU",
+                           flat_act="CELU", end_act="ReLU")
+    m.load_state_dict(c["state"])
+    da = ns(c["a_x"], c["a_edge_index"], c["a_edge_attr"], c["a_batch"])
+    db = ns(c["b_x"], c["b_edge_index"], c["b_edge_attr"], c["b_batch"])
+    out = m(da, db)
+    torch.testing.assert_close(out, c["out"], rtol=1e-4, atol=1e-5)
+    torch.nn.functional.binary_cross_entropy_with_logits(out, c["y"]).backward()
+    for n, p in m.named_parameters():
+        torch.testing.assert_close(p.grad, c["grad_params"][n], rtol=2e-3, atol=1e-6, msg=lambda s, n=n: f"{n}: {s}")
