@@ -35,10 +35,13 @@ SIGNATURES = {
     "glam_gemm_tn_ex": (I32, [P, I64, P, I64, I64, I64, I64, P, I64, I32, P, P, SZ, P]),
     "glam_colsum_workspace_bytes": (SZ, [I64, I64]),
     "glam_colsum": (I32, [P, I64, I64, I64, P, P, SZ, P]),
-    "glam_triplet_edge_fwd": (I32, [P, I64, P, P, P, P, P, I64, I64, I32, I32, I32, F32, P, P, P]),
+    "glam_edge_tile_rows": (I32, [I64]),
+    "glam_edge_tile_count": (I64, [I64]),
+    "glam_build_edge_tiles": (I32, [P, P, P, P, I64, I64, P, P, P]),
+    "glam_triplet_edge_fwd": (I32, [P, I64, P, P, P, P, P, P, I64, I64, I32, I32, I32, F32, P, P, P]),
     "glam_triplet_bwd_workspace_bytes": (SZ, [I32, I32, I32]),
-    "glam_triplet_edge_bwd_dst": (I32, [P, I64, P, P, P, P, P, P, P, P, I64, I64, I32, I32, I32, F32, P, P, P, P, SZ, P]),
-    "glam_triplet_edge_bwd_src": (I32, [P, P, P, P, P, P, P, P, I64, I64, I32, I32, I32, P, I64, P]),
+    "glam_triplet_edge_bwd_dst": (I32, [P, I64, P, P, P, P, P, P, P, P, P, I64, I64, I32, I32, I32, F32, P, P, P, P, SZ, P]),
+    "glam_triplet_edge_bwd_src": (I32, [P, P, P, P, P, P, P, P, P, I64, I64, I32, I32, I32, P, I64, P]),
     "glam_triplet_prep_fwd": (I32, [P, P, P, I32, I32, I32, I32, I32, P, P, P]),
     "glam_triplet_prep_bwd": (I32, [P, P, P, P, P, P, I32, I32, I32, I32, I32, P, P, P, P]),
     "glam_gru_gates_fwd": (I32, [P, P, P, P, I64, I32, I32, F32, P, P, P]),

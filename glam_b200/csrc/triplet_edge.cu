@@ -400,9 +400,39 @@ int edge_vec_bwd_src(const float* ea, const float* w_edge, const float* alpha, c
                      const int32_t* src_rowptr, const int32_t* src_pos, const int32_t* src_dst, int64_t N, int heads, int C,
                      int De, float* g_xpe, int64_t ldxp, cudaStream_t stream);
 
+bool edge_win_eligible(int heads, int C, int De, int64_t ldxp);
+int edge_tile_rows(int64_t N);
+int64_t edge_tile_count(int64_t N);
+int edge_win_build_tiles(const int32_t* dst_rowptr, const int32_t* dst_src, const int32_t* src_rowptr, const int32_t* src_dst,
+                         int64_t N, int32_t* dst_tiles, int32_t* src_tiles, cudaStream_t stream);
+int edge_win_fwd(const float* xpe, int64_t ldxp, const float* ea, const float* w_edge, const float* att_edge, const int32_t* rowptr,
+                 const int32_t* srcs, const int32_t* tiles, int64_t N, int heads, int C, int De, float slope, float* agg, float* alpha,
+                 cudaStream_t stream, int* launched);
+int edge_win_bwd_dst_grid(int64_t N);
+int edge_win_bwd_dst(const float* xpe, int64_t ldxp, const float* ea, const float* w_edge, const float* att_edge, const float* alpha,
+                     const float* g_agg, const int32_t* rowptr, const int32_t* srcs, const int32_t* tiles, int64_t N, int heads, int C,
+                     int De, float slope, float* g_logit, float* g_xpe, float* gwe_partial, cudaStream_t stream, int* launched);
+int edge_win_bwd_src(const float* ea, const float* w_edge, const float* alpha, const float* g_agg, const float* g_logit,
+                     const int32_t* src_rowptr, const int32_t* src_pos, const int32_t* src_dst, const int32_t* tiles, int64_t N, int heads,
+                     int C, int De, float* g_xpe, int64_t ldxp, cudaStream_t stream, int* launched);
+
 }  // namespace glam
 
 using namespace glam;
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+extern "C" int glam_edge_tile_rows(int64_t num_nodes) { return edge_tile_rows(num_nodes); }
+extern "C" int64_t glam_edge_tile_count(int64_t num_nodes) { return edge_tile_count(num_nodes); }
+extern "C" int glam_build_edge_tiles(const int32_t* dst_rowptr, const int32_t* dst_src, const int32_t* src_rowptr,
+                                     const int32_t* src_dst, int64_t N, int64_t E, int32_t* dst_tiles, int32_t* src_tiles,
+                                     void* stream) {
+    if (N == 0) return 0;
+    GLAM_REQUIRE(dst_rowptr && dst_tiles && (E == 0 || dst_src), "glam_build_edge_tiles: null pointer");
+    GLAM_REQUIRE(!src_tiles || (src_rowptr && (E == 0 || src_dst)), "glam_build_edge_tiles: src_tiles needs src_rowptr/src_dst");
+    GLAM_REQUIRE(aligned16(dst_tiles) && aligned16(src_tiles), "glam_build_edge_tiles: tile arrays must be 16-byte aligned");
+    return edge_win_build_tiles(dst_rowptr, dst_src, src_rowptr, src_dst, N, dst_tiles, src_tiles, (cudaStream_t)stream);
+}
 
 #define GLAM_KPL_CASE(H_, EP_, K_, ...) \
     { constexpr int KPL_ = K_; constexpr int HH_ = H_; constexpr bool UE_ = EP_; __VA_ARGS__; }
@@ -433,8 +463,8 @@ static int check_edge_args(const char* fn, int heads, int channels, int edge_dim
 
 extern "C" int glam_triplet_edge_fwd(const float* xpe, int64_t ldxp, const float* edge_attr, const float* w_edge,
                                      const float* att_edge, const int32_t* dst_rowptr, const int32_t* dst_src,
-                                     int64_t N, int64_t E, int heads, int C, int De, float slope, float* agg,
-                                     float* alpha, void* stream_) {
+                                     const int32_t* dst_tiles, int64_t N, int64_t E, int heads, int C, int De, float slope,
+                                     float* agg, float* alpha, void* stream_) {
     const bool use_ep = w_edge != nullptr;
     if (int rc = check_edge_args("glam_triplet_edge_fwd", heads, C, De, use_ep, ldxp)) return rc;
     if (N == 0) return 0;
@@ -443,6 +473,13 @@ extern "C" int glam_triplet_edge_fwd(const float* xpe, int64_t ldxp, const float
     const int HC = heads * C, kpl = pick_kpl(HC);
     const size_t smem = sizeof(float) * ((use_ep ? De * HC : 0) + De * heads);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (dst_tiles && E > 0 && edge_win_eligible(heads, C, De, ldxp) && aligned16(xpe) && aligned16(agg) && aligned16(w_edge) &&
+        aligned16(dst_tiles)) {
+        int launched = 0;
+        if (int rc = edge_win_fwd(xpe, ldxp, edge_attr, w_edge, att_edge, dst_rowptr, dst_src, dst_tiles, N, heads, C, De, slope, agg,
+                                  alpha, stream, &launched)) return rc;
+        if (launched) return 0;
+    }
     if (edge_vec_eligible(xpe, ldxp, heads, C, De, agg, w_edge))
         return edge_vec_fwd(xpe, ldxp, edge_attr, w_edge, att_edge, dst_rowptr, dst_src, N, heads, C, De, slope, agg, alpha, stream);
     GLAM_DISPATCH_EDGE(heads, use_ep, kpl, {
@@ -463,7 +500,8 @@ extern "C" size_t glam_triplet_bwd_workspace_bytes(int heads, int channels, int 
 
 extern "C" int glam_triplet_edge_bwd_dst(const float* xpe, int64_t ldxp, const float* edge_attr, const float* w_edge,
                                          const float* att_edge, const float* alpha, const float* g_agg,
-                                         const int32_t* dst_rowptr, const int32_t* dst_src, const int32_t* dst_dst, int64_t N, int64_t E,
+                                         const int32_t* dst_rowptr, const int32_t* dst_src, const int32_t* dst_dst,
+                                         const int32_t* dst_tiles, int64_t N, int64_t E,
                                          int heads, int C, int De, float slope, float* g_logit, float* g_xpe,
                                          float* g_w_edge, void* workspace, size_t workspace_bytes, void* stream_) {
     const bool use_ep = w_edge != nullptr;
@@ -478,6 +516,18 @@ extern "C" int glam_triplet_edge_bwd_dst(const float* xpe, int64_t ldxp, const f
                  "glam_triplet_edge_bwd_dst: null pointer");
     GLAM_REQUIRE(!use_ep || (g_w_edge && workspace && workspace_bytes >= glam_triplet_bwd_workspace_bytes(heads, C, De)),
                  "glam_triplet_edge_bwd_dst: g_w_edge/workspace missing or too small");
+    if (dst_tiles && E > 0 && edge_win_eligible(heads, C, De, ldxp) && aligned16(xpe) && aligned16(g_agg) && aligned16(w_edge) &&
+        aligned16(dst_tiles) && aligned16(workspace)) {
+        int launched = 0;
+        if (int rc = edge_win_bwd_dst(xpe, ldxp, edge_attr, w_edge, att_edge, alpha, g_agg, dst_rowptr, dst_src, dst_tiles, N, heads, C, De,
+                                      slope, g_logit, g_xpe, (float*)workspace, stream, &launched)) return rc;
+        if (launched) {
+            if (use_ep)
+                return launch_reduce_partials((const float*)workspace, edge_win_bwd_dst_grid(N), 1, De * HC, 0, g_w_edge, De * HC, 0,
+                                              nullptr, stream);
+            return 0;
+        }
+    }
     if (edge_vec_eligible(xpe, ldxp, heads, C, De, g_agg, w_edge)) {
         int vgrid = 0;
         if (int rc = edge_vec_bwd_dst(xpe, ldxp, edge_attr, w_edge, att_edge, alpha, g_agg, dst_rowptr, dst_src, dst_dst, N, E, heads, C, De,
@@ -505,8 +555,8 @@ extern "C" int glam_triplet_edge_bwd_dst(const float* xpe, int64_t ldxp, const f
 
 extern "C" int glam_triplet_edge_bwd_src(const float* edge_attr, const float* w_edge, const float* alpha,
                                          const float* g_agg, const float* g_logit, const int32_t* src_rowptr,
-                                         const int32_t* src_pos, const int32_t* src_dst, int64_t N, int64_t E, int heads,
-                                         int C, int De, float* g_xpe, int64_t ldxp, void* stream_) {
+                                         const int32_t* src_pos, const int32_t* src_dst, const int32_t* src_tiles, int64_t N,
+                                         int64_t E, int heads, int C, int De, float* g_xpe, int64_t ldxp, void* stream_) {
     const bool use_ep = w_edge != nullptr;
     if (int rc = check_edge_args("glam_triplet_edge_bwd_src", heads, C, De, use_ep, ldxp)) return rc;
     if (N == 0) return 0;
@@ -515,6 +565,13 @@ extern "C" int glam_triplet_edge_bwd_src(const float* edge_attr, const float* w_
     const int HC = heads * C, kpl = pick_kpl(HC);
     const size_t smem = sizeof(float) * (use_ep ? De * HC : 0);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (src_tiles && E > 0 && edge_win_eligible(heads, C, De, ldxp) && aligned16(g_xpe) && aligned16(g_agg) && aligned16(w_edge) &&
+        aligned16(src_tiles)) {
+        int launched = 0;
+        if (int rc = edge_win_bwd_src(edge_attr, w_edge, alpha, g_agg, g_logit, src_rowptr, src_pos, src_dst, src_tiles, N, heads, C, De,
+                                      g_xpe, ldxp, stream, &launched)) return rc;
+        if (launched) return 0;
+    }
     if (edge_vec_eligible(g_xpe, ldxp, heads, C, De, g_agg, w_edge))
         return edge_vec_bwd_src(edge_attr, w_edge, alpha, g_agg, g_logit, src_rowptr, src_pos, src_dst, N, heads, C, De, g_xpe, ldxp,
                                 stream);

@@ -34,6 +34,7 @@ class GraphIndex:
         self.src_rowptr = csr["src_rowptr"]
         self.src_pos = csr["src_pos"]
         self.src_dst = csr["src_dst"]
+        self.dst_tiles, self.src_tiles = ops.build_edge_tiles(csr, self.num_nodes)
         self._edge_attr_key = None
         self._edge_attr_sorted = None
         self._gcn = None

@@ -83,6 +83,24 @@ def build_csr(edge_index: torch.Tensor, num_nodes: int):
     return out
 
 
+# windowed (bulk-copy staged) edge kernels; False = per-edge gather kernels (kept for A/B timing and as the tested fallback)
+USE_EDGE_TILES = True
+
+
+def build_edge_tiles(csr: dict, num_nodes: int):
+    """(dst_tiles, src_tiles) int32 [T,4]: tile descriptors of the windowed edge kernels (include/glam_b200.h)."""
+    lib = _lib.load()
+    N = int(num_nodes)
+    dev = csr["dst_rowptr"].device
+    T = int(lib.glam_edge_tile_count(N))
+    dst_tiles = torch.empty((max(T, 1), 4), dtype=torch.int32, device=dev)
+    src_tiles = torch.empty((max(T, 1), 4), dtype=torch.int32, device=dev)
+    E = csr["dst_src"].shape[0]
+    _call("glam_build_edge_tiles", _p(csr["dst_rowptr"]), _p(csr["dst_src"]), _p(csr["src_rowptr"]), _p(csr["src_dst"]), N, E,
+          _p(dst_tiles), _p(src_tiles), _stream(dst_tiles))
+    return dst_tiles, src_tiles
+
+
 def graph_ptr(batch: torch.Tensor, num_graphs: int) -> torch.Tensor:
     _need_cuda(batch)
     if batch.dtype != torch.int64 or batch.dim() != 1:
@@ -182,7 +200,8 @@ def triplet_edge_fwd(xpe, ea_sorted, w_edge, att_edge, g, heads, channels, slope
     alpha = torch.empty((E, heads), dtype=torch.float32, device=dev) if alpha is None else alpha
     assert agg.is_contiguous() and alpha.is_contiguous()
     _call("glam_triplet_edge_fwd", _p(xpe), xpe.stride(0), _p(ea_sorted), _p(w_edge), _p(att_edge),
-                                                 _p(g.dst_rowptr), _p(g.dst_src), N, E, heads, channels,
+                                                 _p(g.dst_rowptr), _p(g.dst_src), _p(g.dst_tiles if USE_EDGE_TILES else None),
+                                                 N, E, heads, channels,
                                                  ea_sorted.shape[1], float(slope), _p(agg), _p(alpha), _stream(xpe))
     return agg, alpha
 
@@ -203,11 +222,13 @@ def triplet_edge_bwd(xpe, ea_sorted, w_edge, att_edge, alpha, g_agg, g, heads, c
         ws = _ws(lib.glam_triplet_bwd_workspace_bytes(heads, channels, De), dev)
     st = _stream(xpe)
     _call("glam_triplet_edge_bwd_dst", _p(xpe), ld, _p(ea_sorted), _p(w_edge), _p(att_edge), _p(alpha), _p(g_agg),
-                                             _p(g.dst_rowptr), _p(g.dst_src), _p(g.dst_dst), N, E, heads, channels, De, float(slope),
+                                             _p(g.dst_rowptr), _p(g.dst_src), _p(g.dst_dst),
+                                             _p(g.dst_tiles if USE_EDGE_TILES else None), N, E, heads, channels, De, float(slope),
                                              _p(g_logit), _p(g_xpe), _p(g_we), _p(ws), 0 if ws is None else ws.numel(),
                                              st)
     _call("glam_triplet_edge_bwd_src", _p(ea_sorted), _p(w_edge), _p(alpha), _p(g_agg), _p(g_logit),
-                                             _p(g.src_rowptr), _p(g.src_pos), _p(g.src_dst), N, E, heads, channels, De,
+                                             _p(g.src_rowptr), _p(g.src_pos), _p(g.src_dst),
+                                             _p(g.src_tiles if USE_EDGE_TILES else None), N, E, heads, channels, De,
                                              _p(g_xpe), ld, st)
     return g_xpe, g_logit, g_we
 

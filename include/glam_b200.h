@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLAM_B200_ABI_VERSION 3
+#define GLAM_B200_ABI_VERSION 4
 #define GLAM_MAX_HEADS 4
 
 int glam_abi_version(void);
@@ -101,6 +101,21 @@ size_t glam_colsum_workspace_bytes(int64_t M, int64_t N);
 int glam_colsum(const float* G, int64_t ldg, int64_t M, int64_t N, float* out, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* Tile descriptors of the windowed edge kernels (once per batch, next to the CSR).  Nodes are cut into tiles of
+ * glam_edge_tile_rows(N) consecutive ids; a PyG batch is block-diagonal with graph-by-graph numbering
+ * (src_1gp/dataset.py:75-87 + Batch.from_data_list), so the sources of a tile's in-edges (and the destinations of its
+ * out-edges) span one short contiguous range of rows, which the kernels stage in shared memory with bulk async copies
+ * instead of gathering row by row.  dst_tiles[t] = {lo, hi, e0, e1}: rows [lo,hi) cover the tile's own rows and every
+ * source of its in-edges [e0,e1) (dst order); src_tiles[t] = {lo, hi, k0, k1}: rows [lo,hi) cover the destinations of
+ * its out-edges [k0,k1) (src order).  Both arrays: 4 * glam_edge_tile_count(N) int32, 16-byte aligned; src_tiles may be
+ * NULL (forward only).  The edge entry points below take them as an optional argument (NULL = per-edge gather path);
+ * tiles whose window does not fit in shared memory are handled inside the same launch from global memory. */
+int glam_edge_tile_rows(int64_t num_nodes);
+int64_t glam_edge_tile_count(int64_t num_nodes);
+int glam_build_edge_tiles(const int32_t* dst_rowptr, const int32_t* dst_src, const int32_t* src_rowptr,
+                          const int32_t* src_dst, int64_t num_nodes, int64_t num_edges, int32_t* dst_tiles,
+                          int32_t* src_tiles, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (3) Triplet attention edge phase — TripletMessage.message + aggregate (src_1gp/layer.py:42-55, :17)
  * and TripletMessageLight.message (:88-97), restructured per SURVEY.md Appendix C.
@@ -113,7 +128,7 @@ int glam_colsum(const float* G, int64_t ldg, int64_t M, int64_t N, float* out, v
  * --------------------------------------------------------------------------------------------- */
 int glam_triplet_edge_fwd(const float* xpe, int64_t ldxp, const float* edge_attr, const float* w_edge,
                           const float* att_edge, const int32_t* dst_rowptr, const int32_t* dst_src,
-                          int64_t num_nodes, int64_t num_edges, int heads, int channels, int edge_dim,
+                          const int32_t* dst_tiles, int64_t num_nodes, int64_t num_edges, int heads, int channels, int edge_dim,
                           float negative_slope, float* agg, float* alpha, void* stream);
 /* Backward, destination pass: from g_agg [N,HC] computes g_logit [E,H] (dst order), g_s_i into
  * g_xpe[:, HC:HC+H], and per-warp partials of g_w_edge reduced in fixed order into g_w_edge [De,HC]
@@ -122,15 +137,15 @@ size_t glam_triplet_bwd_workspace_bytes(int heads, int channels, int edge_dim);
 int glam_triplet_edge_bwd_dst(const float* xpe, int64_t ldxp, const float* edge_attr, const float* w_edge,
                               const float* att_edge, const float* alpha, const float* g_agg,
                               const int32_t* dst_rowptr, const int32_t* dst_src, const int32_t* dst_dst,
-                              int64_t num_nodes, int64_t num_edges, int heads, int channels, int edge_dim,
-                              float negative_slope, float* g_logit, float* g_xpe, float* g_w_edge,
+                              const int32_t* dst_tiles, int64_t num_nodes, int64_t num_edges, int heads, int channels,
+                              int edge_dim, float negative_slope, float* g_logit, float* g_xpe, float* g_w_edge,
                               void* workspace, size_t workspace_bytes, void* stream);
 /* Backward, source pass: g_xpe[j, 0:HC] = sum over out-edges of alpha * g_agg[dst] (.) e_ij,
  * g_xpe[j, HC+H:HC+2H] = sum g_logit, pad columns zeroed. */
 int glam_triplet_edge_bwd_src(const float* edge_attr, const float* w_edge, const float* alpha, const float* g_agg,
                               const float* g_logit, const int32_t* src_rowptr, const int32_t* src_pos,
-                              const int32_t* src_dst, int64_t num_nodes, int64_t num_edges, int heads,
-                              int channels, int edge_dim, float* g_xpe, int64_t ldxp, void* stream);
+                              const int32_t* src_dst, const int32_t* src_tiles, int64_t num_nodes, int64_t num_edges,
+                              int heads, int channels, int edge_dim, float* g_xpe, int64_t ldxp, void* stream);
 
 /* Derived weights of the triplet layers (parameter space, tiny): w_ext [C, ldxp] = weight_node | weight_node_h a_i,h |
  * weight_node_h a_j,h | 0 and att_edge [De,H] = weight_edge_h a_e,h, with a_i|a_e|a_j the three slices of

@@ -40,9 +40,29 @@ if which in ("all", "edge"):
     b = make_molecule_batch(4096, total_nodes=N, total_edges=221184, seed=1).to(dev)
     g = graph.graph_index(b.edge_index, N); ea = g.sorted_edge_attr(b.edge_attr); E = b.num_edges
     xpe = torch.randn(N, ld, device=dev); we = torch.randn(De, HC, device=dev); ae = torch.randn(De, H, device=dev)
-    timeit("edge_fwd", lambda: ops.triplet_edge_fwd(xpe, ea, we, ae, g, H, C, 0.2), 4 * (N * ld + N * HC + E * De + E * H) + 4 * (E + N))
-    aggo, alpha = ops.triplet_edge_fwd(xpe, ea, we, ae, g, H, C, 0.2)
-    timeit("edge_bwd (dst+src)", lambda: ops.triplet_edge_bwd(xpe, ea, we, ae, alpha, g108, g, H, C, 0.2), 4 * (2 * N * ld + 2 * N * HC + 2 * E * De + 5 * E * H) + 4 * (4 * E + 2 * N))
+    fwd_bytes = 4 * (N * ld + N * HC + E * De + E * H) + 4 * (E + N)
+    dst_bytes = 4 * (N * ld + N * HC + E * De + 2 * E * H + N * H) + 4 * (E + N)
+    src_bytes = 4 * (N * HC + N * ld + E * De + 2 * E * H) + 4 * (3 * E + N)
+    res = {}
+    for tiles in (False, True):
+        ops.USE_EDGE_TILES = tiles
+        tag = "windowed" if tiles else "gather  "
+        timeit(f"edge_fwd [{tag}]", lambda: ops.triplet_edge_fwd(xpe, ea, we, ae, g, H, C, 0.2), fwd_bytes)
+        aggo, alpha = ops.triplet_edge_fwd(xpe, ea, we, ae, g, H, C, 0.2)
+        timeit(f"edge_bwd dst+src [{tag}]", lambda: ops.triplet_edge_bwd(xpe, ea, we, ae, alpha, g108, g, H, C, 0.2), dst_bytes + src_bytes)
+        sink = []
+        ops.set_profile(sink)
+        for _ in range(5):
+            flush.zero_()
+            ops.triplet_edge_bwd(xpe, ea, we, ae, alpha, g108, g, H, C, 0.2)
+        ops.set_profile(None); torch.cuda.synchronize()
+        for nm, nb in (("glam_triplet_edge_bwd_dst", dst_bytes), ("glam_triplet_edge_bwd_src", src_bytes)):
+            ts = sorted(e0.elapsed_time(e1) for n, e0, e1 in sink if n == nm); t = ts[len(ts) // 2]
+            print(f"   {nm:41s} {t*1e3:8.1f} us  {nb/t/1e6:8.1f} GB/s  ({nb/1e6:.1f} MB)")
+        res[tiles] = (aggo, alpha) + tuple(ops.triplet_edge_bwd(xpe, ea, we, ae, alpha, g108, g, H, C, 0.2))
+    for nm, a_, b_ in zip(("agg", "alpha", "g_xpe", "g_logit", "g_we"), res[False], res[True]):
+        d = (a_ - b_).abs().max().item()
+        print(f"   windowed vs gather {nm:8s} max|diff| = {d:.3e}  bitwise_equal = {bool(torch.equal(a_, b_))}  (scale {a_.abs().max().item():.3e})")
     gi = torch.randn(N, 3 * C, device=dev); gh = torch.randn(N, 3 * C, device=dev); h = torch.randn(N, C, device=dev)
     timeit("gru_gates_fwd", lambda: ops.gru_gates_fwd(gi.clone(), gh, h, x, 3, 1.0), 4 * N * C * 13)
 if which in ("all", "s2s"):

@@ -43,7 +43,7 @@ def test_arity_matches_header():
 
 
 def test_abi_version_and_workspace_queries(lib):
-    assert lib.glam_abi_version() == 3
+    assert lib.glam_abi_version() == 4
     assert lib.glam_csr_workspace_bytes(1000, 2000) > 4 * (2 * 1001 + 4 * 2000)
     assert lib.glam_gemm_tn_workspace_bytes(100000, 36, 116) >= 36 * 116 * 4
     assert lib.glam_colsum_workspace_bytes(100000, 108) >= 108 * 4
@@ -52,7 +52,7 @@ def test_abi_version_and_workspace_queries(lib):
 
 def test_argument_errors_are_reported(lib):
     from glam_b200 import _lib
-    rc = lib.glam_triplet_edge_fwd(None, 0, None, None, None, None, None, 10, 10, 9, 36, 3, 0.2, None, None, None)
+    rc = lib.glam_triplet_edge_fwd(None, 0, None, None, None, None, None, None, 10, 10, 9, 36, 3, 0.2, None, None, None)
     assert rc < 0 and b"heads" in lib.glam_last_error()
     with pytest.raises(_lib.GlamError):
         _lib.check(rc, "glam_triplet_edge_fwd")
