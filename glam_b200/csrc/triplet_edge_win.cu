@@ -17,6 +17,7 @@
 // as triplet_edge_vec.cu; no atomics.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace glam {
 
@@ -102,6 +103,7 @@ struct WinArgs {
     const int4* tiles;
     int64_t N; int C, De, D, rmax; int64_t T;
     float slope;
+    int dbg;                                              // profiling only: 1 skip softmax, 2 skip aggregate, 4 skip window copy, 8 skip records
 };
 
 // shared-memory carve-up (all kernels): rows | We4 | records ... ; offsets in floats from a 128-byte aligned base
@@ -321,7 +323,7 @@ edge_win_fwd_kernel(const __grid_constant__ WinArgs a, float* __restrict__ agg, 
         if (nxt < a.T) desc = a.tiles[nxt];                         // next descriptor in flight during this tile
         const bool overflow = ne > kWinMaxEdges;
         const bool near = !overflow && nrows <= a.rmax && ne > 0;
-        if (near && warp == 0) {
+        if (near && warp == 0 && !(a.dbg & 4)) {
             tc::fence_proxy_async_smem();
             bulk_window(s.rows, a.xpe + (int64_t)lo * a.ld, (uint32_t)nrows * (uint32_t)ld * 4u, s.bar, lane);
         }
@@ -334,7 +336,7 @@ edge_win_fwd_kernel(const __grid_constant__ WinArgs a, float* __restrict__ agg, 
         }
         // ---- records: one thread per edge (coalesced index / edge_attr reads; overlaps the window copy)
         const int base = near ? lo : 0;
-        for (int e = tid; e < ne; e += kWinThreads) {
+        for (int e = tid; e < ((a.dbg & 8) ? 0 : ne); e += kWinThreads) {
             const int p = e0 + e;
             const float* earow = a.ea + (int64_t)p * De;
             float l[H];
@@ -355,17 +357,302 @@ edge_win_fwd_kernel(const __grid_constant__ WinArgs a, float* __restrict__ agg, 
         }
         __syncthreads();
         if (near) {
-            tc::mbar_wait(s.bar, parity);
-            parity ^= 1u;
-            fwd_softmax<H, USE_EP, int>(s.rows, ld, (int)(t0 - lo), HC, nd, e0, a.slope, s.rp, rec_st, rec_val, rec_c, alpha);
+            if (!(a.dbg & 4)) {
+                tc::mbar_wait(s.bar, parity);
+                parity ^= 1u;
+            }
+            if (!(a.dbg & 1))
+                fwd_softmax<H, USE_EP, int>(s.rows, ld, (int)(t0 - lo), HC, nd, e0, a.slope, s.rp, rec_st, rec_val, rec_c, alpha);
             __syncthreads();
-            win_aggregate<H, CPI, USE_EP, int>(s.rows, ld, nq, ig, nd, t0, De, a.ea, nullptr, e0, s.We4, s.rp, rec_st, rec_c, agg, HC);
+            if (!(a.dbg & 2))
+                win_aggregate<H, CPI, USE_EP, int>(s.rows, ld, nq, ig, nd, t0, De, a.ea, nullptr, e0, s.We4, s.rp, rec_st, rec_c, agg, HC);
+            else
+                for (int i = tid; i < nd * nq; i += kWinThreads) reinterpret_cast<float4*>(agg + t0 * HC)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
             fwd_softmax<H, USE_EP, int64_t>(a.xpe, ld, t0, HC, nd, e0, a.slope, s.rp, rec_st, rec_val, rec_c, alpha);
             __syncthreads();
             win_aggregate<H, CPI, USE_EP, int64_t>(a.xpe, ld, nq, ig, nd, t0, De, a.ea, nullptr, e0, s.We4, s.rp, rec_st, rec_c, agg, HC);
         }
         __syncthreads();                                            // records and window are dead
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ forward, pipelined
+// Same phases as edge_win_fwd_kernel with the memory latency taken off the per-tile critical path:
+//   * two window buffers per CTA (two CTAs per SM): the bulk copy of tile k+1 is issued as soon as tile k's records are
+//     published and lands while tile k computes;
+//   * the index / edge_attr words of tile k+1 are loaded into REGISTERS during tile k (up to two edges per thread) and
+//     only turned into records at the top of tile k+1 — no global load is waited for between tiles;
+//   * the block size is chosen by the host so that the (node, item) work of a tile fills every pass.
+constexpr int kWin2CtasPerSM = 2;
+constexpr int kWin2MaxThreads = 256;      // 8 warps x 2 CTAs = 4 warps per SM sub-partition at up to 128 registers
+constexpr int kWin2SmemBudget = 108 * 1024;
+constexpr int kWin2PrefDe = 4;               // edge_attr words prefetched per edge (wider rows are read at the top of the tile)
+
+template <int H>
+__device__ __forceinline__ int item_head(int g, int tph) {
+    int h = 0;
+#pragma unroll
+    for (int q = 1; q < H; ++q) h += (g >= q * tph) ? 1 : 0;
+    return h;
+}
+
+template <int H, bool USE_EP, typename IDX>
+__device__ __forceinline__ void fwd_softmax2(const float* rows, int ld, IDX own0, int HC, int nd, int e0, float slope, const int* rp,
+                                             const int2* rec_st, const float* rec_val, float* rec_c, float* __restrict__ alpha) {
+    for (int idx = threadIdx.x; idx < nd * H; idx += blockDim.x) {
+        const int d = idx / H, h = idx - d * H;
+        const int beg = rp[d], end = rp[d + 1], deg = end - beg;
+        const float si = rows[(own0 + d) * ld + HC + h];
+        if (deg <= 4) {
+            float l[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                l[k] = -INFINITY;
+                if (k < deg) {
+                    const int e = beg + k;
+                    const float v = si + rec_c[e * H + h] + rows[(IDX)rec_st[e].x * ld + HC + H + h];
+                    l[k] = v > 0.f ? v : slope * v;
+                }
+            }
+            const float mx = fmaxf(fmaxf(l[0], l[1]), fmaxf(l[2], l[3]));
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                l[k] = k < deg ? expf(l[k] - mx) : 0.f;
+                if (k < deg) sum += l[k];
+            }
+            sum += 1e-16f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < deg) {
+                    const int e = beg + k;
+                    const float a = l[k] / sum;
+                    alpha[(int64_t)(e0 + e) * H + h] = a;
+                    rec_c[e * H + h] = USE_EP ? a * rec_val[e] : a;
+                }
+            continue;
+        }
+        float mx = -INFINITY, sum = 0.f;
+        for (int e = beg; e < end; ++e) {
+            float l = si + rec_c[e * H + h] + rows[(IDX)rec_st[e].x * ld + HC + H + h];
+            l = l > 0.f ? l : slope * l;
+            rec_c[e * H + h] = l;
+            mx = fmaxf(mx, l);
+        }
+        for (int e = beg; e < end; ++e) {
+            const float x = expf(rec_c[e * H + h] - mx);
+            rec_c[e * H + h] = x;
+            sum += x;
+        }
+        sum += 1e-16f;
+        for (int e = beg; e < end; ++e) {
+            const float a = rec_c[e * H + h] / sum;
+            alpha[(int64_t)(e0 + e) * H + h] = a;
+            rec_c[e * H + h] = USE_EP ? a * rec_val[e] : a;
+        }
+    }
+}
+
+template <int H, int CPI, bool USE_EP, typename IDX>
+__device__ __forceinline__ void win_aggregate2(const float* rows, int ld, int nq, ItemGeom ig, int nd, int64_t t0, int De,
+                                               const float* __restrict__ ea, const int32_t* __restrict__ ea_pos, int e0,
+                                               const float4* We4, const int* rp, const int2* rec_st, const float* rec_c,
+                                               float* __restrict__ out, int64_t ldo, int d, int g, int dstep, int gstep) {
+    const int total = nd * ig.ni;
+    for (int item = threadIdx.x; item < total; item += blockDim.x) {
+        const int beg = rp[d], end = rp[d + 1];
+        const int q0 = g * CPI, h = item_head<H>(g, ig.tph);
+        float4 acc[CPI];
+#pragma unroll
+        for (int k = 0; k < CPI; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = beg; e < end; ++e) {
+            const int2 st = rec_st[e];
+            const float c = rec_c[e * H + h];
+            const float4* xj = reinterpret_cast<const float4*>(rows + (IDX)st.x * ld) + q0;
+            float4 m[CPI];
+#pragma unroll
+            for (int k = 0; k < CPI; ++k) m[k] = xj[k];
+            if (USE_EP) {
+                if (st.y >= 0) {
+                    const float4* w = We4 + st.y * nq + q0;
+#pragma unroll
+                    for (int k = 0; k < CPI; ++k) m[k] = mul4(m[k], w[k]);
+                } else {
+                    const int64_t p = ea_pos ? (int64_t)ea_pos[e0 + e] : (int64_t)(e0 + e);
+#pragma unroll
+                    for (int k = 0; k < CPI; ++k) m[k] = mul4(m[k], ep_general(ea + p * De, De, We4, nq, q0 + k));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CPI; ++k) acc[k] = fma4(c, m[k], acc[k]);
+        }
+        float4* o = reinterpret_cast<float4*>(out + (t0 + d) * ldo) + q0;
+#pragma unroll
+        for (int k = 0; k < CPI; ++k) o[k] = acc[k];
+        g += gstep; d += dstep;
+        if (g >= ig.ni) { g -= ig.ni; ++d; }
+    }
+}
+
+__device__ __forceinline__ void win2_issue_window(const WinArgs& a, const int4& dsc, float* dst, uint64_t* bar, int warp, int lane) {
+    const int nrows = dsc.y - dsc.x, ne = dsc.w - dsc.z;
+    const bool near = ne <= kWinMaxEdges && nrows <= a.rmax && ne > 0;
+    if (near && warp == 0) {
+        tc::fence_proxy_async_smem();
+        bulk_window(dst, a.xpe + (int64_t)dsc.x * a.ld, (uint32_t)nrows * (uint32_t)a.ld * 4u, bar, lane);
+    }
+}
+// index / edge_attr words of a tile into registers (nothing here is waited for: the values are first used at the top of
+// the tile they belong to).  Plain scalars: arrays here ended up in local memory, which turns every prefetch into a
+// blocking load.
+struct WinPref { int j0, j1, rp; float a0, a1, a2, a3, b0, b1, b2, b3; };
+__device__ __forceinline__ void win2_prefetch(const WinArgs& a, const int4& dsc, int64_t tile, int tid, int nthr, bool pref_ok,
+                                              WinPref& pf) {
+    const int e0 = dsc.z, ne = dsc.w - dsc.z, De = a.De;
+    const int64_t t0 = tile * a.D;
+    const int nd = (int)min((int64_t)a.D, a.N - t0);
+    if (tid <= nd) pf.rp = a.rowptr[t0 + tid];
+    if (ne <= kWinMaxEdges && pref_ok) {
+        if (tid < ne) {
+            const int64_t p = e0 + tid;
+            const float* r = a.ea + p * De;
+            pf.j0 = a.other[p];
+            pf.a0 = r[0];
+            if (De > 1) pf.a1 = r[1];
+            if (De > 2) pf.a2 = r[2];
+            if (De > 3) pf.a3 = r[3];
+        }
+        if (tid + nthr < ne) {
+            const int64_t p = e0 + tid + nthr;
+            const float* r = a.ea + p * De;
+            pf.j1 = a.other[p];
+            pf.b0 = r[0];
+            if (De > 1) pf.b1 = r[1];
+            if (De > 2) pf.b2 = r[2];
+            if (De > 3) pf.b3 = r[3];
+        }
+    }
+}
+
+// one prefetched edge -> record
+template <int H>
+__device__ __forceinline__ void win2_make_record(int e, int j, float v0, float v1, float v2, float v3, int De, int base, const float* Ae,
+                                                 int2* rec_st, float* rec_val, float* rec_c) {
+    float l[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) l[h] = 0.f;
+    int nz = 0, ty = 0;
+    float val = 0.f;
+    const float v[4] = {v0, v1, v2, v3};
+#pragma unroll
+    for (int dd = 0; dd < 4; ++dd)
+        if (dd < De) {
+            if (v[dd] != 0.f) { ++nz; ty = dd; val = v[dd]; }
+#pragma unroll
+            for (int h = 0; h < H; ++h) l[h] = fmaf(v[dd], Ae[dd * H + h], l[h]);
+        }
+    rec_st[e] = make_int2(j - base, nz == 1 ? ty : -1);
+    rec_val[e] = nz == 1 ? val : 1.f;
+#pragma unroll
+    for (int h = 0; h < H; ++h) rec_c[e * H + h] = l[h];
+}
+
+template <int H, int CPI, bool USE_EP>
+__global__ void __launch_bounds__(kWin2MaxThreads, kWin2CtasPerSM)
+edge_win2_fwd_kernel(const __grid_constant__ WinArgs a, float* __restrict__ agg, float* __restrict__ alpha) {
+    extern __shared__ __align__(128) float smem_f[];
+    const int HC = H * a.C, nq = HC >> 2, De = a.De, ld = (int)a.ld;
+    const ItemGeom ig{nq / CPI, (a.C >> 2) / CPI};
+    WinSmem s = win_carve(smem_f, 2 * a.rmax, a.ld, De, nq, H, USE_EP);
+    const int bufstride = a.rmax * ld;                            // floats between the two window buffers
+    uint64_t* bar = s.bar;                                        // two mbarriers (16 bytes reserved)
+    int2* rec_st = reinterpret_cast<int2*>(s.rec);
+    float* rec_val = s.rec + 2 * kWinMaxEdges;
+    float* rec_c = rec_val + kWinMaxEdges;                        // [kWinMaxEdges][H]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+    if (USE_EP)
+        for (int i = tid; i < De * nq; i += nthr) s.We4[i] = ld4(a.w_edge + 4 * i);
+    for (int i = tid; i < De * H; i += nthr) s.Ae[i] = a.att_edge[i];
+    if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_init(bar + 1, 1); tc::fence_mbar_init(); }
+    const int d_first = tid / ig.ni, g_first = tid - d_first * ig.ni, dstep = nthr / ig.ni, gstep = nthr - dstep * ig.ni;
+    const bool pref_ok = De <= kWin2PrefDe;
+    WinPref pf{0, 0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};    // two edges per thread + one rowptr word
+    __syncthreads();
+    int4 desc = blockIdx.x < a.T ? a.tiles[blockIdx.x] : make_int4(0, 0, 0, 0);
+    int4 desc_n = make_int4(0, 0, 0, 0);
+    if (blockIdx.x < a.T) {
+        win2_issue_window(a, desc, s.rows, bar, warp, lane);
+        win2_prefetch(a, desc, blockIdx.x, tid, nthr, pref_ok, pf);
+        if ((int64_t)blockIdx.x + gridDim.x < a.T) desc_n = a.tiles[blockIdx.x + gridDim.x];
+    }
+    uint32_t par = 0;
+    int k = 0;
+    for (int64_t tile = blockIdx.x; tile < a.T; tile += gridDim.x, ++k) {
+        const int cur = k & 1;
+        const int64_t t0 = tile * a.D;
+        const int nd = (int)min((int64_t)a.D, a.N - t0);
+        const int lo = desc.x, nrows = desc.y - desc.x, e0 = desc.z, ne = desc.w - desc.z;
+        const bool overflow = ne > kWinMaxEdges;
+        const bool near = !overflow && nrows <= a.rmax && ne > 0;
+        const int base = near ? lo : 0;
+        // ---- records of this tile from the prefetched registers
+        if (tid <= nd) s.rp[tid] = pf.rp - e0;
+        if (!overflow) {
+            if (pref_ok) {
+                if (tid < ne) win2_make_record<H>(tid, pf.j0, pf.a0, pf.a1, pf.a2, pf.a3, De, base, s.Ae, rec_st, rec_val, rec_c);
+                if (tid + nthr < ne)
+                    win2_make_record<H>(tid + nthr, pf.j1, pf.b0, pf.b1, pf.b2, pf.b3, De, base, s.Ae, rec_st, rec_val, rec_c);
+            } else {
+                for (int e = tid; e < ne; e += nthr) {
+                    const int p = e0 + e;
+                    const float* earow = a.ea + (int64_t)p * De;
+                    float l[H];
+#pragma unroll
+                    for (int h = 0; h < H; ++h) l[h] = 0.f;
+                    int nz = 0, ty = 0;
+                    float val = 0.f;
+                    for (int dd = 0; dd < De; ++dd) {
+                        const float v = earow[dd];
+                        if (v != 0.f) { ++nz; ty = dd; val = v; }
+#pragma unroll
+                        for (int h = 0; h < H; ++h) l[h] = fmaf(v, s.Ae[dd * H + h], l[h]);
+                    }
+                    rec_st[e] = make_int2(a.other[p] - base, nz == 1 ? ty : -1);
+                    rec_val[e] = nz == 1 ? val : 1.f;
+#pragma unroll
+                    for (int h = 0; h < H; ++h) rec_c[e * H + h] = l[h];
+                }
+            }
+        }
+        __syncthreads();                                            // records visible; every thread is done with tile k-1
+        // ---- tile k+1: window copy into the other buffer, index words into registers, descriptor of k+2
+        const int64_t nxt = tile + gridDim.x;
+        int4 desc_nn = make_int4(0, 0, 0, 0);
+        if (nxt < a.T) {
+            win2_issue_window(a, desc_n, s.rows + (cur ^ 1) * bufstride, bar + (cur ^ 1), warp, lane);
+            win2_prefetch(a, desc_n, nxt, tid, nthr, pref_ok, pf);
+            if (nxt + gridDim.x < a.T) desc_nn = a.tiles[nxt + gridDim.x];
+        }
+        if (overflow) {
+            fwd_overflow_tile<H, USE_EP>(a, s.We4, s.Ae, s.rp, nd, t0, e0, agg, alpha);
+        } else if (near) {
+            tc::mbar_wait(bar + cur, (par >> cur) & 1u);
+            par ^= 1u << cur;
+            const float* rows = s.rows + cur * bufstride;
+            fwd_softmax2<H, USE_EP, int>(rows, ld, (int)(t0 - lo), HC, nd, e0, a.slope, s.rp, rec_st, rec_val, rec_c, alpha);
+            __syncthreads();
+            win_aggregate2<H, CPI, USE_EP, int>(rows, ld, nq, ig, nd, t0, De, a.ea, nullptr, e0, s.We4, s.rp, rec_st, rec_c, agg, HC,
+                                                d_first, g_first, dstep, gstep);
+        } else {
+            fwd_softmax2<H, USE_EP, int64_t>(a.xpe, ld, t0, HC, nd, e0, a.slope, s.rp, rec_st, rec_val, rec_c, alpha);
+            __syncthreads();
+            win_aggregate2<H, CPI, USE_EP, int64_t>(a.xpe, ld, nq, ig, nd, t0, De, a.ea, nullptr, e0, s.We4, s.rp, rec_st, rec_c, agg, HC,
+                                                    d_first, g_first, dstep, gstep);
+        }
+        __syncthreads();                                            // records are dead
+        desc = desc_n;
+        desc_n = desc_nn;
     }
 }
 
@@ -817,6 +1104,7 @@ bool edge_win_eligible(int heads, int C, int De, int64_t ldxp) {
 template <typename F>
 static void win_allow_smem(F fn, size_t bytes) {
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 static int win_grid(int64_t T, int ctas_per_sm) {
@@ -840,18 +1128,55 @@ int edge_win_build_tiles(const int32_t* dst_rowptr, const int32_t* dst_src, cons
     return 0;
 }
 
+static int win_debug() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GLAM_B200_EDGE_WIN_DEBUG");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+static int win_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GLAM_B200_EDGE_WIN");
+        v = e ? atoi(e) : 2;
+    }
+    return v;
+}
+
 // *launched = 1 when the windowed kernel took the call, 0 when the configuration does not fit (caller takes the gather path)
 int edge_win_fwd(const float* xpe, int64_t ldxp, const float* ea, const float* w_edge, const float* att_edge, const int32_t* rowptr,
                  const int32_t* srcs, const int32_t* tiles, int64_t N, int heads, int C, int De, float slope, float* agg, float* alpha,
                  cudaStream_t stream, int* launched) {
     *launched = 0;
     const bool use_ep = w_edge != nullptr;
-    const int HC = heads * C, nq = HC / 4, cpi = pick_cpi(C);
+    const int HC = heads * C, nq = HC / 4, cpi = pick_cpi(C), ni = nq / cpi;
     const int D = edge_tile_rows(N);
     const int rec = 3 + heads;
+    const int64_t T = (N + D - 1) / D;
+    if (win_variant() >= 2) {
+        // pipelined kernel: two window buffers, block size fitted to the (node, item) work of a tile
+        const int rmax2 = win_rmax(kWin2SmemBudget, 2 * ldxp, De, nq, use_ep, rec, 0);
+        const int items = D * ni, passes = (items + kWin2MaxThreads - 1) / kWin2MaxThreads;
+        int nthr = ((items + passes - 1) / passes + 31) / 32 * 32;
+        if (nthr < 256) nthr = 256;
+        if (rmax2 >= D + 24 && nthr <= kWin2MaxThreads && ni <= nthr) {
+            WinArgs a{xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax2, T, slope, win_debug()};
+            const size_t smem = win_smem_bytes(2 * rmax2, ldxp, De, nq, use_ep, rec, 0);
+            GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
+                auto fn = edge_win2_fwd_kernel<HH_, CPI_, UE_>;
+                win_allow_smem(fn, smem);
+                fn<<<win_grid(T, kWin2CtasPerSM), nthr, smem, stream>>>(a, agg, alpha);
+            })
+            GLAM_CHECK_LAUNCH();
+            *launched = 1;
+            return 0;
+        }
+    }
     const int rmax = win_rmax(kWinSmemBudget, ldxp, De, nq, use_ep, rec, 0);
-    if (rmax < D + 8 || nq / cpi > kWinThreads) return 0;
-    WinArgs a{xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax, (N + D - 1) / D, slope};
+    if (rmax < D + 8 || ni > kWinThreads) return 0;
+    WinArgs a{xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax, T, slope, win_debug()};
     const size_t smem = win_smem_bytes(rmax, ldxp, De, nq, use_ep, rec, 0);
     GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
         auto fn = edge_win_fwd_kernel<HH_, CPI_, UE_>;
@@ -879,7 +1204,7 @@ int edge_win_bwd_dst(const float* xpe, int64_t ldxp, const float* ea, const floa
     const int rmax = win_rmax(kWinDstSmemBudget, ldxp, De, nq, use_ep, rec, extra);
     const size_t stage = sizeof(float4) * (size_t)kWinWarps * (32 / ni) * De * nq;     // end-of-kernel staging lives in the window area
     if (rmax < D + 8 || (use_ep && (size_t)rmax * ldxp * 4 < stage)) return 0;
-    WinArgs a{xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax, (N + D - 1) / D, slope};
+    WinArgs a{xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax, (N + D - 1) / D, slope, win_debug()};
     const size_t smem = win_smem_bytes(rmax, ldxp, De, nq, use_ep, rec, extra);
     GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
         auto fn = edge_win_bwd_dst_kernel<HH_, CPI_, UE_>;
@@ -902,7 +1227,7 @@ int edge_win_bwd_src(const float* ea, const float* w_edge, const float* alpha, c
     const int rmax = win_rmax(kWinSmemBudget, HC, De, nq, use_ep, rec, 0);
     if (rmax < D + 8 || nq / cpi > kWinThreads) return 0;
     WinArgs a{nullptr, ldxp, ea, w_edge, nullptr, src_rowptr, src_dst, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax,
-              (N + D - 1) / D, 0.f};
+              (N + D - 1) / D, 0.f, win_debug()};
     const size_t smem = win_smem_bytes(rmax, HC, De, nq, use_ep, rec, 0);
     GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
         auto fn = edge_win_bwd_src_kernel<HH_, CPI_, UE_>;

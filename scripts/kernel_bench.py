@@ -65,6 +65,13 @@ if which in ("all", "edge"):
         print(f"   windowed vs gather {nm:8s} max|diff| = {d:.3e}  bitwise_equal = {bool(torch.equal(a_, b_))}  (scale {a_.abs().max().item():.3e})")
     gi = torch.randn(N, 3 * C, device=dev); gh = torch.randn(N, 3 * C, device=dev); h = torch.randn(N, C, device=dev)
     timeit("gru_gates_fwd", lambda: ops.gru_gates_fwd(gi.clone(), gh, h, x, 3, 1.0), 4 * N * C * 13)
+if which == "edgefwd":
+    b = make_molecule_batch(4096, total_nodes=N, total_edges=221184, seed=1).to(dev)
+    g = graph.graph_index(b.edge_index, N); ea = g.sorted_edge_attr(b.edge_attr); E = b.num_edges
+    xpe = torch.randn(N, ld, device=dev); we = torch.randn(De, HC, device=dev); ae = torch.randn(De, H, device=dev)
+    fwd_bytes = 4 * (N * ld + N * HC + E * De + E * H) + 4 * (E + N)
+    timeit("edge_fwd windowed dbg=" + os.environ.get("GLAM_B200_EDGE_WIN_DEBUG", "0") + " v=" + os.environ.get("GLAM_B200_EDGE_WIN", "2"),
+           lambda: ops.triplet_edge_fwd(xpe, ea, we, ae, g, H, C, 0.2), fwd_bytes, reps=20)
 if which in ("all", "s2s"):
     B = 4096
     b = make_molecule_batch(B, total_nodes=N, total_edges=221184, seed=1).to(dev)
