@@ -664,14 +664,62 @@ edge_win2_fwd_kernel(const __grid_constant__ WinArgs a, float* __restrict__ agg,
 constexpr int kWinDstCtasPerSM = 2;
 constexpr int kWinDstSmemBudget = 112 * 1024;
 
-template <int H, int CPI, bool USE_EP, typename IDX>
+// math of one (edge, item) pair once its operands are in registers: returns this item's part of g_alpha and adds the
+// edge's contribution to the g_weight_edge accumulators
+template <int H, int CPI, bool USE_EP, int DR>
+__device__ __forceinline__ float dots_edge(const int4 r, const float4 (&gm)[CPI], float ah, int q0, int nq, int De, int64_t p,
+                                           const float* __restrict__ ea, const float4* We4, float4 (&gw)[DR][CPI]) {
+    float v = 0.f;
+    if (USE_EP) {
+        const float val = __int_as_float(r.w);
+        if (r.z >= 0) {
+            const float4* w = We4 + r.z * nq + q0;
+#pragma unroll
+            for (int k = 0; k < CPI; ++k) v += dot4(gm[k], w[k]);
+            v *= val;
+            const float c = val * ah;
+            if (r.z == 0) {
+#pragma unroll
+                for (int k = 0; k < CPI; ++k) gw[0][k] = fma4(c, gm[k], gw[0][k]);
+            } else if (r.z == 1) {
+#pragma unroll
+                for (int k = 0; k < CPI; ++k) gw[1][k] = fma4(c, gm[k], gw[1][k]);
+            } else if (r.z == 2) {
+#pragma unroll
+                for (int k = 0; k < CPI; ++k) gw[2][k] = fma4(c, gm[k], gw[2][k]);
+            } else if (DR > 3) {
+#pragma unroll
+                for (int k = 0; k < CPI; ++k) gw[DR - 1][k] = fma4(c, gm[k], gw[DR - 1][k]);
+            }
+        } else {
+            const float* earow = ea + p * De;
+#pragma unroll
+            for (int dd = 0; dd < DR; ++dd)
+                if (dd < De) {
+                    const float ed = earow[dd];
+#pragma unroll
+                    for (int k = 0; k < CPI; ++k) {
+                        v = fmaf(ed, dot4(gm[k], We4[dd * nq + q0 + k]), v);
+                        gw[dd][k] = fma4(ed * ah, gm[k], gw[dd][k]);
+                    }
+                }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < CPI; ++k) v += (gm[k].x + gm[k].y) + (gm[k].z + gm[k].w);
+    }
+    return v;
+}
+
+// edge-parallel dots: a warp takes 32/ni edges per pass, lane = (edge slot, item)
+template <int H, int CPI, bool USE_EP, int DR, typename IDX>
 __device__ __forceinline__ void bwd_dots(const float* rows, int ld, const float4* gagg4, int nq, ItemGeom ig, int ne, int e0, int De,
                                          const float* __restrict__ ea, const float4* We4, const int4* rec4, const float* rec_a,
-                                         float* rec_g, float4 (&gw)[kWinRegDe][CPI]) {
+                                         float* rec_g, float4 (&gw)[DR][CPI]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int epw = 32 / ig.ni;                                   // edges per warp pass
     const int el = lane / ig.ni, g = lane - el * ig.ni;
-    const int q0 = g * CPI, h = min(g / ig.tph, H - 1);
+    const int q0 = g * CPI, h = item_head<H>(min(g, ig.ni - 1), ig.tph);
     const bool lane_on = el < epw;
     const bool writer = lane_on && (g - (g / ig.tph) * ig.tph) == 0;
     for (int eb = warp * epw; eb < ne; eb += kWinWarps * epw) {
@@ -680,50 +728,13 @@ __device__ __forceinline__ void bwd_dots(const float* rows, int ld, const float4
         float v = 0.f;
         if (on) {
             const int4 r = rec4[e];
-            const float val = __int_as_float(r.w);
             const float4* xj = reinterpret_cast<const float4*>(rows + (IDX)r.x * ld) + q0;
             const float4* gi = gagg4 + r.y * nq + q0;
             float4 gm[CPI];
 #pragma unroll
             for (int k = 0; k < CPI; ++k) gm[k] = mul4(gi[k], xj[k]);
-            if (USE_EP) {
-                const float ah = rec_a[e * H + h];
-                if (r.z >= 0) {
-                    const float4* w = We4 + r.z * nq + q0;
-#pragma unroll
-                    for (int k = 0; k < CPI; ++k) v += dot4(gm[k], w[k]);
-                    v *= val;
-                    const float c = val * ah;
-                    if (r.z == 0) {
-#pragma unroll
-                        for (int k = 0; k < CPI; ++k) gw[0][k] = fma4(c, gm[k], gw[0][k]);
-                    } else if (r.z == 1) {
-#pragma unroll
-                        for (int k = 0; k < CPI; ++k) gw[1][k] = fma4(c, gm[k], gw[1][k]);
-                    } else if (r.z == 2) {
-#pragma unroll
-                        for (int k = 0; k < CPI; ++k) gw[2][k] = fma4(c, gm[k], gw[2][k]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < CPI; ++k) gw[3][k] = fma4(c, gm[k], gw[3][k]);
-                    }
-                } else {
-                    const float* earow = ea + (int64_t)(e0 + e) * De;
-#pragma unroll
-                    for (int dd = 0; dd < kWinRegDe; ++dd)
-                        if (dd < De) {
-                            const float ed = earow[dd];
-#pragma unroll
-                            for (int k = 0; k < CPI; ++k) {
-                                v = fmaf(ed, dot4(gm[k], We4[dd * nq + q0 + k]), v);
-                                gw[dd][k] = fma4(ed * ah, gm[k], gw[dd][k]);
-                            }
-                        }
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < CPI; ++k) v += (gm[k].x + gm[k].y) + (gm[k].z + gm[k].w);
-            }
+            const float ah = USE_EP ? rec_a[e * H + h] : 0.f;
+            v = dots_edge<H, CPI, USE_EP, DR>(r, gm, ah, q0, nq, De, (int64_t)(e0 + e), ea, We4, gw);
         }
         // per-head sum over the items of this edge: lanes g .. g + tph - 1 (fixed order)
         float sdot = v;
@@ -839,7 +850,7 @@ __device__ __noinline__ void bwd_dst_overflow_tile(const WinArgs& a, const float
 }
 
 // smem: rows (xpe window) | We4 | Ae | rp | bar | rec4 | rec_a | rec_g | gagg [D][HC] | ovf slabs [warps][De][nq] float4
-template <int H, int CPI, bool USE_EP>
+template <int H, int CPI, bool USE_EP, int DR>
 __global__ void __launch_bounds__(kWinThreads, kWinDstCtasPerSM)
 edge_win_bwd_dst_kernel(const __grid_constant__ WinArgs a, const float* __restrict__ alpha, const float* __restrict__ g_agg,
                         float* __restrict__ g_logit, float* __restrict__ g_xpe, float* __restrict__ gwe_partial) {
@@ -859,9 +870,9 @@ edge_win_bwd_dst_kernel(const __grid_constant__ WinArgs a, const float* __restri
     if (USE_EP)
         for (int i = tid; i < kWinWarps * De * nq; i += kWinThreads) ovf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) { tc::mbar_init(s.bar, 1); tc::fence_mbar_init(); }
-    float4 gw[kWinRegDe][CPI];
+    float4 gw[DR][CPI];
 #pragma unroll
-    for (int d = 0; d < kWinRegDe; ++d)
+    for (int d = 0; d < DR; ++d)
 #pragma unroll
         for (int k = 0; k < CPI; ++k) gw[d][k] = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t parity = 0;
@@ -895,21 +906,24 @@ edge_win_bwd_dst_kernel(const __grid_constant__ WinArgs a, const float* __restri
             __syncthreads();
             continue;
         }
-        // ---- records: thread per destination walks its in-edges (local dst index comes for free)
+        // ---- records: a thread per edge for the global words, a thread per destination for the local dst index
         const int base = near ? lo : 0;
-        for (int d = tid; d < nd; d += kWinThreads) {
-            for (int e = s.rp[d]; e < s.rp[d + 1]; ++e) {
-                const int p = e0 + e;
-                const float* earow = a.ea + (int64_t)p * De;
-                int nz = 0, ty = 0;
-                float val = 0.f;
-                for (int dd = 0; dd < De; ++dd) {
-                    const float v = earow[dd];
-                    if (v != 0.f) { ++nz; ty = dd; val = v; }
-                }
-                rec4[e] = make_int4(a.other[p] - base, d, nz == 1 ? ty : -1, __float_as_int(nz == 1 ? val : 1.f));
+        int* rec_w = reinterpret_cast<int*>(rec4);
+        for (int e = tid; e < ne; e += kWinThreads) {
+            const int p = e0 + e;
+            const float* earow = a.ea + (int64_t)p * De;
+            int nz = 0, ty = 0;
+            float val = 0.f;
+            for (int dd = 0; dd < De; ++dd) {
+                const float v = earow[dd];
+                if (v != 0.f) { ++nz; ty = dd; val = v; }
             }
+            rec_w[4 * e + 0] = a.other[p] - base;
+            rec_w[4 * e + 2] = nz == 1 ? ty : -1;
+            rec_w[4 * e + 3] = __float_as_int(nz == 1 ? val : 1.f);
         }
+        for (int d = tid; d < nd; d += kWinThreads)
+            for (int e = s.rp[d]; e < s.rp[d + 1]; ++e) rec_w[4 * e + 1] = d;
         for (int i = tid; i < ne * H; i += kWinThreads) rec_a[i] = alpha[(int64_t)e0 * H + i];
         __syncthreads();
         if (staged) {
@@ -918,12 +932,12 @@ edge_win_bwd_dst_kernel(const __grid_constant__ WinArgs a, const float* __restri
         }
         const float4* gagg4 = reinterpret_cast<const float4*>(gagg);
         if (near) {
-            bwd_dots<H, CPI, USE_EP, int>(s.rows, ld, gagg4, nq, ig, ne, e0, De, a.ea, s.We4, rec4, rec_a, rec_g, gw);
+            bwd_dots<H, CPI, USE_EP, DR, int>(s.rows, ld, gagg4, nq, ig, ne, e0, De, a.ea, s.We4, rec4, rec_a, rec_g, gw);
             __syncthreads();
             bwd_softmax<H, int>(s.rows, ld, (int)(t0 - lo), HC, nd, t0, e0, De, a.slope, a.ea, s.Ae, s.rp, rec4, rec_a, rec_g, g_logit, g_xpe,
                                 a.ld);
         } else {
-            bwd_dots<H, CPI, USE_EP, int64_t>(a.xpe, ld, gagg4, nq, ig, ne, e0, De, a.ea, s.We4, rec4, rec_a, rec_g, gw);
+            bwd_dots<H, CPI, USE_EP, DR, int64_t>(a.xpe, ld, gagg4, nq, ig, ne, e0, De, a.ea, s.We4, rec4, rec_a, rec_g, gw);
             __syncthreads();
             bwd_softmax<H, int64_t>(a.xpe, ld, t0, HC, nd, t0, e0, De, a.slope, a.ea, s.Ae, s.rp, rec4, rec_a, rec_g, g_logit, g_xpe, a.ld);
         }
@@ -936,7 +950,7 @@ edge_win_bwd_dst_kernel(const __grid_constant__ WinArgs a, const float* __restri
         const int epw = 32 / ig.ni, el = lane / ig.ni, g = lane - el * ig.ni;
         if (el < epw)
 #pragma unroll
-            for (int d = 0; d < kWinRegDe; ++d)
+            for (int d = 0; d < DR; ++d)
                 if (d < De)
 #pragma unroll
                     for (int k = 0; k < CPI; ++k) stage[((warp * epw + el) * De + d) * nq + g * CPI + k] = gw[d][k];
@@ -1206,11 +1220,19 @@ int edge_win_bwd_dst(const float* xpe, int64_t ldxp, const float* ea, const floa
     if (rmax < D + 8 || (use_ep && (size_t)rmax * ldxp * 4 < stage)) return 0;
     WinArgs a{xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax, (N + D - 1) / D, slope, win_debug()};
     const size_t smem = win_smem_bytes(rmax, ldxp, De, nq, use_ep, rec, extra);
-    GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
-        auto fn = edge_win_bwd_dst_kernel<HH_, CPI_, UE_>;
-        win_allow_smem(fn, smem);
-        fn<<<win_grid(a.T, kWinDstCtasPerSM), kWinThreads, smem, stream>>>(a, alpha, g_agg, g_logit, g_xpe, gwe_partial);
-    })
+    if (De <= 3) {
+        GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
+            auto fn = edge_win_bwd_dst_kernel<HH_, CPI_, UE_, 3>;
+            win_allow_smem(fn, smem);
+            fn<<<win_grid(a.T, kWinDstCtasPerSM), kWinThreads, smem, stream>>>(a, alpha, g_agg, g_logit, g_xpe, gwe_partial);
+        })
+    } else {
+        GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
+            auto fn = edge_win_bwd_dst_kernel<HH_, CPI_, UE_, kWinRegDe>;
+            win_allow_smem(fn, smem);
+            fn<<<win_grid(a.T, kWinDstCtasPerSM), kWinThreads, smem, stream>>>(a, alpha, g_agg, g_logit, g_xpe, gwe_partial);
+        })
+    }
     GLAM_CHECK_LAUNCH();
     *launched = 1;
     return 0;
