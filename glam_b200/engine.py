@@ -115,26 +115,45 @@ class FlatAdam:
 
 
 class TrainStep:
+    """One optimisation step (forward + loss + backward [+ all-reduce] + Adam) captured in a CUDA graph.
+
+    double_buffer=True keeps TWO sets of static input buffers, each with its own captured graph (sharing one memory
+    pool: they never run concurrently).  `step(batch, prefetch=next_batch)` then enqueues the host->device copy of the
+    NEXT batch on a copy stream while the current step computes, so the PCIe transfer disappears from the step time —
+    what a DataLoader with pinned memory and `non_blocking=True` does for the reference's `data.to(device)`
+    (src_1gp/trainer.py:175), which the reference itself leaves synchronous."""
+
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, example: GraphBatch, lr: float = 1e-3,
-                 device="cuda", world_size: int = 1, use_cuda_graph: bool = True, warmup: int = 3):
+                 device="cuda", world_size: int = 1, use_cuda_graph: bool = True, warmup: int = 3,
+                 double_buffer: bool = False):
         self.model = model.to(device)
         self.loss_fn = loss_fn
         self.device = torch.device(device)
         self.world = world_size
-        self.static = _static_like(example, self.device)
-        _copy_into(self.static, example)
+        self.statics = [_static_like(example, self.device) for _ in range(2 if double_buffer else 1)]
+        for st in self.statics:
+            _copy_into(st, example)
+        self.static = self.statics[0]
         self.grads = FlatGrads(self.model.parameters(), gather=True)
         self.opt = FlatAdam(self.grads, lr=lr)
         self.loss = torch.zeros((), device=self.device)
+        self.graphs = []
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_cuda_graph = use_cuda_graph
+        self._slot = 0
+        self._prefetched = None                                   # host batch whose copy into slot `_slot` is in flight
+        if double_buffer:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._copied = [torch.cuda.Event() for _ in self.statics]
+            self._consumed = [torch.cuda.Event() for _ in self.statics]
         if use_cuda_graph:
             self._capture(warmup)
 
-    def _body(self):
+    def _body(self, static: Optional[GraphBatch] = None):
+        static = self.static if static is None else static
         self.grads.zero()
-        out = self.model(self.static)
-        loss = self.loss_fn(out, self.static.y)
+        out = self.model(static)
+        loss = self.loss_fn(out, static.y)
         loss.backward()
         self.grads.collect()
         if self.world > 1:
@@ -151,28 +170,53 @@ class TrainStep:
                 self._body()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
-        G.clear_caches()                      # the index build must be part of the captured step
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._body()
+        pool = None
+        for st in self.statics:
+            G.clear_caches()                  # the index build must be part of the captured step
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                self._body(st)
+            pool = g.pool()
+            self.graphs.append(g)
+        self.graph = self.graphs[0]
         G.clear_caches()
 
     def run_resident(self):
-        """One step on whatever is in the static buffers (inputs already in HBM)."""
-        if self.graph is not None:
-            self.graph.replay()
+        """One step on whatever is in the static buffers of the current slot (inputs already in HBM)."""
+        if self.graphs:
+            self.graphs[self._slot].replay()
         else:
             G.clear_caches()
-            self._body()
+            self._body(self.statics[self._slot])
         return self.loss
 
     def load(self, batch: GraphBatch) -> int:
-        return _copy_into(self.static, batch)
+        return _copy_into(self.statics[self._slot], batch)
 
-    def step(self, batch: GraphBatch) -> torch.Tensor:
-        """Public API: host (pinned) or device batch in, loss tensor (device scalar) out."""
-        self.load(batch)
-        return self.run_resident()
+    def step(self, batch: GraphBatch, prefetch: Optional[GraphBatch] = None) -> torch.Tensor:
+        """Public API: host (pinned) or device batch in, loss tensor (device scalar) out.  `prefetch` (double_buffer
+        only) names the batch of the NEXT call: its copy overlaps this step's compute."""
+        if len(self.statics) == 1:
+            self.load(batch)
+            return self.run_resident()
+        main = torch.cuda.current_stream(self.device)
+        slot = self._slot
+        if self._prefetched is batch:
+            main.wait_event(self._copied[slot])                   # the copy was enqueued during the previous step
+        else:
+            _copy_into(self.statics[slot], batch)
+        self._prefetched = None
+        self.run_resident()
+        self._consumed[slot].record(main)
+        if prefetch is not None:
+            nxt = slot ^ 1
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._consumed[nxt])  # the last step that read those buffers is done
+                _copy_into(self.statics[nxt], prefetch)
+                self._copied[nxt].record(self._copy_stream)
+            self._prefetched = prefetch
+            self._slot = nxt
+        return self.loss
 
 
 class ScreenStep:

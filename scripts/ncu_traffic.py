@@ -18,9 +18,14 @@ for r in rows[2:]:
 kern = {k: {"dram_bytes_per_launch": sum(b for b, _ in v) / len(v), "us_per_launch_under_ncu": sum(t for _, t in v) / len(v),
             "launches": len(v)} for k, v in per.items()}
 label_map = {
-    "glam_triplet_edge_fwd": ["edge_tile_fwd_kernel"],
-    "glam_triplet_edge_bwd_dst": ["edge_dots_ep_kernel", "edge_softmax_bwd_kernel"],
-    "glam_triplet_edge_bwd_src": ["edge_source_bwd_kernel"],
+    "glam_triplet_edge_fwd": ["edge_win2_fwd_kernel"],
+    "glam_triplet_edge_bwd_dst": ["edge_win_bwd_dst_kernel"],
+    "glam_triplet_edge_bwd_src": ["edge_win_bwd_src_kernel"],
+    "glam_triplet_edge_fwd[gather]": ["edge_tile_fwd_kernel"],
+    "glam_triplet_edge_bwd_dst[gather]": ["edge_dots_ep_kernel", "edge_softmax_bwd_kernel"],
+    "glam_triplet_edge_bwd_src[gather]": ["edge_source_bwd_kernel"],
+    "glam_gru_fused_fwd": ["tc_gru_fwd_kernel"],
+    "glam_gru_gates_bwd_ex": ["gru_gates_bwd_vec_kernel"],
     "glam_gru_gates_fwd": ["gru_gates_fwd_vec_kernel"],
     "glam_gru_gates_bwd": ["gru_gates_bwd_vec_kernel"],
 }

@@ -531,6 +531,19 @@ def test_captured_train_steps_follow_oracle_training():
             assert abs(a - r) <= 2e-4 * max(1.0, abs(r)), (losses, ref_losses)
         for (n, p), q in zip(m.named_parameters(), o32.parameters()):
             torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=2e-3, atol=2e-4, msg=lambda s, n=n: f"{n}: {s}")
+        # double-buffered inputs with the next batch's copy in flight during the step: bitwise the same training run
+        m2, _ = _gp_pair(9, 3, "Set2Set", "_TripletMessage")
+        ts2 = TrainStep(m2, torch.nn.functional.mse_loss, batches[0], lr=1e-3, device=DEV, use_cuda_graph=True, warmup=0,
+                        double_buffer=True)
+        with torch.no_grad():
+            for k, p in m2.state_dict().items():
+                p.copy_(sd[k])
+        ts2.opt.exp_avg.zero_(); ts2.opt.exp_avg_sq.zero_(); ts2.opt.state.zero_()
+        pinned = [b.pin_memory() for b in batches]
+        losses2 = [ts2.step(b, prefetch=pinned[i + 1] if i + 1 < len(pinned) else None).item() for i, b in enumerate(pinned)]
+        assert losses2 == losses, (losses2, losses)
+        for p, q in zip(m2.parameters(), m.parameters()):
+            assert torch.equal(p, q)
     finally:
         set_math_mode(prev)
 
@@ -644,3 +657,123 @@ def test_model_dti_reference_defaults_golden(golden_next, math_mode):
             assert err < 2e-1 and cos > 0.999, f"{n}: rel err {err:.3e}, cos {cos:.6f}"
         else:
             assert err < 2e-3, f"{n}: rel err {err:.3e}"
+
+
+# ---------------------------------------------------------------------------------------------- windowed edge kernels
+def _edge_phase_ref64(xpe, ea, we, ae, src, dst, N, H, C, slope, g_agg):
+    """fp64 restatement of TripletMessage.message + aggregate on the extended projection (SURVEY.md Appendix C;
+    src_1gp/layer.py:42-55 with PyG's softmax) and its gradients by autograd."""
+    HC = H * C
+    xpe = xpe.double().requires_grad_(True)
+    ea, ae, g_agg = ea.double(), ae.double(), g_agg.double()
+    we = None if we is None else we.double().requires_grad_(True)
+    src, dst = src.long(), dst.long()
+    E = src.shape[0]
+    pre = xpe[:, HC:HC + H][dst] + xpe[:, HC + H:HC + 2 * H][src] + ea @ ae
+    pre.retain_grad()
+    l = torch.nn.functional.leaky_relu(pre, slope)
+    mx = torch.full((N, H), -float("inf"), dtype=torch.float64, device=xpe.device).scatter_reduce(
+        0, dst[:, None].expand(E, H), l, "amax", include_self=True)
+    ex = torch.exp(l - mx[dst])
+    den = torch.zeros((N, H), dtype=torch.float64, device=xpe.device).index_add_(0, dst, ex)
+    alpha = ex / (den[dst] + 1e-16)
+    msg = alpha[:, :, None] * xpe[:, :HC].view(N, H, C)[src]
+    if we is not None:
+        msg = msg * (ea @ we).view(E, H, C)
+    agg = torch.zeros((N, H, C), dtype=torch.float64, device=xpe.device).index_add_(0, dst, msg).view(N, HC)
+    (agg * g_agg).sum().backward()
+    return agg.detach(), alpha.detach(), xpe.grad, pre.grad, None if we is None else we.grad
+
+
+def _edge_case(kind, seed):
+    from glam_b200.synth import make_molecule_batch
+    g = torch.Generator().manual_seed(seed)
+    if kind == "molecules":                       # every tile near: windows staged in shared memory
+        b = make_molecule_batch(700, node_dim=9, edge_dim=3, seed=seed)
+        return b.edge_index, b.num_nodes
+    if kind == "big_molecules":                   # graphs larger than a tile: a share of the windows exceeds the buffer
+        import numpy as np
+        b = make_molecule_batch(40, node_dim=9, edge_dim=3, seed=seed, sizes=np.full(40, 110))
+        return b.edge_index, b.num_nodes
+    if kind == "random":                          # no locality at all: every tile is far (rows gathered from global memory)
+        N = 6000
+        return torch.randint(0, N, (2, 15000), generator=g), N
+    if kind == "hub":                             # tiles with more edges than the record buffer + isolated nodes
+        N = 2000
+        ei = torch.randint(0, N - 50, (2, 9000), generator=g)
+        ei[1, :3000] = 17
+        ei[1, 3000:3700] = 1203
+        ei[0, 4000:5200] = 40                     # a hub SOURCE: overflow in the source pass
+        return ei, N
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["molecules", "big_molecules", "random", "hub"])
+@pytest.mark.parametrize("H,C,De,onehot,light", [
+    (3, 36, 3, True, False),      # BASELINE dims: 3 chunks per item, 9 items
+    (3, 60, 4, True, False),      # reference dims: 15 items, two edges per warp pass in the destination pass
+    (2, 32, 3, True, False),      # 2 chunks per item
+    (1, 20, 5, False, False),     # 1 chunk per item, general edge rows, edge_dim > 4 (destination pass: gather kernels)
+    (4, 24, 8, False, False),     # protein-style 8-dim contact features
+    (1, 36, 3, True, True),       # TripletMessageLight: no edge projection
+])
+def test_windowed_edge_kernels(kind, H, C, De, onehot, light):
+    """The bulk-copy staged edge kernels (near / far / overflow tiles) and the per-edge gather kernels against an fp64
+    restatement, outputs and all three gradients; and the tile descriptors against their definition."""
+    from glam_b200 import graph, ops, _lib
+    ei, N = _edge_case(kind, 11)
+    ei = ei.to(DEV)
+    g = graph.GraphIndex(ei, N)
+    E = ei.shape[1]
+    # ---- descriptors: bit-exact against the definition in include/glam_b200.h
+    D = _lib.load().glam_edge_tile_rows(N)
+    T = (N + D - 1) // D
+    assert g.dst_tiles.shape == (T, 4) and g.src_tiles.shape == (T, 4)
+    rp, srcs = g.dst_rowptr.long().cpu(), g.dst_src.long().cpu()
+    srp, sdst = g.src_rowptr.long().cpu(), g.src_dst.long().cpu()
+    dt, st = g.dst_tiles.cpu(), g.src_tiles.cpu()
+    for t in (0, T // 3, T // 2, T - 1):
+        t0, t1 = t * D, min(N, (t + 1) * D)
+        e0, e1 = int(rp[t0]), int(rp[t1])
+        lo = min([t0] + srcs[e0:e1].tolist()); hi = max([t1 - 1] + srcs[e0:e1].tolist()) + 1
+        assert dt[t].tolist() == [lo, hi, e0, e1]
+        k0, k1 = int(srp[t0]), int(srp[t1])
+        want = [int(sdst[k0:k1].min()), int(sdst[k0:k1].max()) + 1, k0, k1] if k1 > k0 else [0, 0, k0, k1]
+        assert st[t].tolist() == want
+    # ---- kernels
+    gen = torch.Generator().manual_seed(5)
+    HC = H * C
+    ld = (HC + 2 * H + 3) // 4 * 4
+    xpe = torch.randn(N, ld, generator=gen).to(DEV)
+    if onehot:
+        ea = torch.eye(De)[torch.randint(0, De, (E,), generator=gen)] * (0.5 + torch.rand(E, 1, generator=gen))
+    else:
+        ea = torch.rand(E, De, generator=gen) * (torch.rand(E, De, generator=gen) > 0.3)
+    ea = g.sorted_edge_attr(ea.to(DEV))
+    we = None if light else (torch.randn(De, HC, generator=gen) * 0.5).to(DEV)
+    ae = (torch.randn(De, H, generator=gen) * 0.5).to(DEV)
+    g_agg = torch.randn(N, HC, generator=gen).to(DEV)
+    ref = _edge_phase_ref64(xpe[:, :HC + 2 * H].contiguous(), ea, we, ae, g.dst_src, g.dst_dst, N, H, C, 0.2, g_agg)
+    outs = {}
+    try:
+        for tiles in (True, False):
+            ops.USE_EDGE_TILES = tiles
+            agg, alpha = ops.triplet_edge_fwd(xpe, ea, we, ae, g, H, C, 0.2)
+            g_xpe, g_logit, g_we = ops.triplet_edge_bwd(xpe, ea, we, ae, alpha, g_agg, g, H, C, 0.2)
+            outs[tiles] = (agg, alpha, g_xpe[:, :HC + 2 * H], g_logit, g_we)
+            torch.cuda.synchronize()
+            assert torch.equal(g_xpe[:, HC + 2 * H:], torch.zeros_like(g_xpe[:, HC + 2 * H:]))     # pad columns zeroed
+            for name, ours, want in zip(("agg", "alpha", "g_xpe", "g_logit", "g_w_edge"), outs[tiles], ref):
+                if want is None:
+                    assert ours is None
+                    continue
+                scale = want.abs().max().clamp(min=1e-30)
+                err = (ours.double() - want).abs().max()
+                assert err <= 1e-5 + 1e-4 * scale, f"{kind} tiles={tiles} {name}: err {err:.3e} (scale {scale:.3e})"
+            # run-to-run bitwise reproducible
+            agg2, alpha2 = ops.triplet_edge_fwd(xpe, ea, we, ae, g, H, C, 0.2)
+            b2 = ops.triplet_edge_bwd(xpe, ea, we, ae, alpha, g_agg, g, H, C, 0.2)
+            assert torch.equal(agg, agg2) and torch.equal(alpha, alpha2)
+            assert torch.equal(g_xpe, b2[0]) and torch.equal(g_logit, b2[1]) and (g_we is None or torch.equal(g_we, b2[2]))
+    finally:
+        ops.USE_EDGE_TILES = True
