@@ -497,3 +497,39 @@ class GCNConvFn(Function):
         g_b = ops.colsum(g_out) if ctx.has_bias else None
         g_x = ops.gemm(g_xw, weight, transpose_w=True) if ctx.needs_input_grad[0] else None
         return g_x, g_w, g_b, None, None
+
+
+class NNConvFn(Function):
+    """PyG NNConv(aggr='mean') for one-hot bond features (`_NNConv`, src_1gp/layer.py:115-122): the per-edge [C,C] matrix
+    nn(edge_attr) takes only edge_dim distinct values, so the messages are rows of ONE grouped projection
+    Y = x @ [Theta_0 | .. | Theta_{De-1}] (a [N,C]x[C,De*C] tensor-core GEMM) and the layer is a typed gather-mean over the
+    dst CSR plus the root term; backward scatters through a CSR grouped by (source, type).  No [E,C,C] tensor, no atomics."""
+
+    @staticmethod
+    def forward(ctx, x, theta_cat, root, bias, g, idx):
+        x, theta_cat, root, bias = map(_c, (x, theta_cat, root, bias))
+        ops._need_cuda(x, theta_cat)
+        col_fwd, inv_deg, rowptr_r, col_r, w_r, De = idx
+        N, C = x.shape
+        Co = root.shape[1]
+        y = ops.gemm(x, theta_cat)                                                 # [N, De*Co]
+        out = ops.csr_aggregate(y.view(N * De, Co), g.dst_rowptr, col_fwd, row_scale=inv_deg, num_rows=N)
+        ops.gemm(x, root, bias=bias, epilogue=EPI_ACCUM, out=out)
+        ctx.save_for_backward(x, theta_cat, root, rowptr_r, col_r, w_r)
+        ctx.cfg = (De, Co, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, theta_cat, root, rowptr_r, col_r, w_r = ctx.saved_tensors
+        De, Co, has_bias = ctx.cfg
+        g_out = _c(g_out)
+        N = x.shape[0]
+        g_y = ops.csr_aggregate(g_out, rowptr_r, col_r, edge_w=w_r, num_rows=N * De).view(N, De * Co)
+        g_theta, _ = ops.gemm_tn_ex(x, g_y)                                        # [C, De*Co]
+        g_root, g_bias = ops.gemm_tn_ex(x, g_out, want_colsum=has_bias)
+        g_x = None
+        if ctx.needs_input_grad[0]:
+            g_x = ops.gemm(g_y, theta_cat, transpose_w=True)
+            ops.gemm(g_out, root, transpose_w=True, epilogue=EPI_ACCUM, out=g_x)
+        return g_x, g_theta, g_root, g_bias, None, None

@@ -38,6 +38,8 @@ class GraphIndex:
         self._edge_attr_key = None
         self._edge_attr_sorted = None
         self._gcn = None
+        self._nn_key = None
+        self._nn = None
 
     def gcn_norm(self):
         """(dinv^2 [N], w_dst [E], w_src [E]) of PyG GCNConv's normalisation, computed once per batch."""
@@ -45,6 +47,35 @@ class GraphIndex:
             dinv, w_dst, w_src = ops.gcn_norm(self)
             self._gcn = (dinv * dinv, w_dst, w_src)
         return self._gcn
+
+    def nn_index(self, edge_attr: torch.Tensor):
+        """Per-batch index of the typed NNConv path (bond features are one-hot, src_1gp/dataset.py:82): with t(e) the bond
+        type of edge e, rows r = src*De + t of the grouped projection Y [N*De, C] are what the messages read.  Returns
+        (col_fwd [E] = r per dst-ordered edge, inv_deg [N] = 1/max(in-degree,1), rowptr_r [N*De+1], col_r [E] = destination
+        of the edges grouped by r, w_r [E] = inv_deg of those destinations).  Outside CUDA-graph capture the rows are
+        checked to be exact unit one-hot (the general case would need a per-edge [C,C] matrix)."""
+        key = (edge_attr.data_ptr(), edge_attr._version, tuple(edge_attr.shape))
+        if self._nn_key == key:
+            return self._nn
+        ea = self.sorted_edge_attr(edge_attr)
+        De = ea.shape[1]
+        if not _capturing():
+            ok = bool(((ea.sum(1) == 1) & (ea.max(1).values == 1) & (ea.min(1).values == 0)).all()) if ea.numel() else True
+            if not ok:
+                raise ops._lib.GlamError("_NNConv kernel path needs exact one-hot edge_attr rows (bond types, "
+                                         "src_1gp/dataset.py:82); general rows are not supported")
+        t = ea.argmax(1).to(torch.int32)
+        col_fwd = self.dst_src * De + t
+        deg = (self.dst_rowptr[1:] - self.dst_rowptr[:-1]).clamp(min=1).to(torch.float32)
+        inv_deg = 1.0 / deg
+        fake = torch.stack([self.dst_dst.long(), col_fwd.long()])            # "edges" destination -> typed source row
+        csr = ops.build_csr(fake, self.num_nodes * De)
+        col_r = csr["dst_src"]
+        w_r = inv_deg[col_r.long()]
+        self._nn = (col_fwd, inv_deg, csr["dst_rowptr"], col_r, w_r, De)
+        self._nn_key = key
+        self._nn_ref = edge_attr
+        return self._nn
 
     def sorted_edge_attr(self, edge_attr: torch.Tensor) -> torch.Tensor:
         """edge_attr rows permuted into destination order (done once per batch, reused by every step)."""

@@ -183,7 +183,50 @@ class _GCNConv(nn.Module):
         return self.conv(x, edge_index)
 
 
-_NNConv, _GATConv = _third_party("_NNConv"), _third_party("_GATConv")
+class NNConv(nn.Module):
+    """PyG NNConv(in_channels, out_channels, nn, aggr='mean') @1.7.2 as `_NNConv` builds it (src_1gp/layer.py:115-122):
+    parameters `nn.{0,2}.{weight,bias}` (torch Linear init), `root [in,out]` (uniform(1/sqrt(in))), `bias [out]` (zeros).
+    Bond features are one-hot (src_1gp/dataset.py:82), so nn(edge_attr) has edge_dim distinct values: they are evaluated
+    in parameter space (tiny torch ops, differentiable) and the node-sized work runs in the library (Fn.NNConvFn)."""
+
+    def __init__(self, in_channels, out_channels, nn_module, aggr="mean"):
+        super().__init__()
+        if aggr != "mean":
+            raise NotImplementedError("NNConv: the reference only builds aggr='mean' (layer.py:119)")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.nn = nn_module
+        self.root = Parameter(torch.empty(in_channels, out_channels))
+        self.bias = Parameter(torch.empty(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        bound = 1.0 / (self.in_channels ** 0.5)
+        nn.init.uniform_(self.root, -bound, bound)
+        zeros_(self.bias)
+
+    def forward(self, x, edge_index, edge_attr):
+        g = G.graph_index(edge_index, x.shape[0])
+        idx = g.nn_index(edge_attr)
+        De = idx[5]
+        eye = torch.eye(De, dtype=x.dtype, device=x.device)
+        theta = self.nn(eye).view(De, self.in_channels, self.out_channels)       # Theta_t = nn(e_t)
+        theta_cat = theta.permute(1, 0, 2).reshape(self.in_channels, De * self.out_channels)
+        return Fn.NNConvFn.apply(x, theta_cat, self.root, self.bias, g, idx)
+
+
+class _NNConv(nn.Module):
+    """src_1gp/layer.py:115-122 (the reference's default mol_block, src_1gp/run.py:21)."""
+
+    def __init__(self, in_dim, out_dim, edge_in_dim):
+        super().__init__()
+        net = nn.Sequential(nn.Linear(edge_in_dim, 32), nn.ReLU(), nn.Linear(32, in_dim * out_dim))
+        self.conv = NNConv(in_dim, out_dim, net, aggr="mean")
+
+    def forward(self, x, edge_index, edge_attr):
+        return self.conv(x, edge_index, edge_attr)
+
+
+_GATConv = _third_party("_GATConv")
 
 
 # --------------------------------------------------------------------------------------------------

@@ -386,10 +386,13 @@ def pool5_bwd(g_out, gptr, top, num_graphs, N, C):
     return g_x
 
 
-def csr_aggregate(Y, rowptr, col, edge_w=None, self_w=None, row_scale=None, bias=None, out=None, accumulate=False):
+def csr_aggregate(Y, rowptr, col, edge_w=None, self_w=None, row_scale=None, bias=None, out=None, accumulate=False,
+                  num_rows=None):
+    """out [num_rows, F]; `col` indexes rows of Y, which may have a different row count (typed gathers of NNConv)."""
     _need_cuda(Y)
     assert Y.dim() == 2 and Y.stride(1) == 1
-    N, F = Y.shape
+    N, F = (Y.shape[0] if num_rows is None else int(num_rows)), Y.shape[1]
+    assert self_w is None or N == Y.shape[0]
     if out is None:
         out = torch.empty((N, F), dtype=torch.float32, device=Y.device)
     _call("glam_csr_aggregate", _p(Y), Y.stride(0), _p(rowptr), _p(col), _p(edge_w), _p(self_w), _p(row_scale), _p(bias), N, F,

@@ -307,7 +307,47 @@ class _GCNConv(nn.Module):
         return gcn_conv(x, edge_index, self.conv.weight, self.conv.bias)
 
 
-_CONVS = {"_TripletMessage": _TripletMessage, "_TripletMessageLight": _TripletMessageLight, "_GCNConv": _GCNConv}
+def nn_conv(x, edge_index, edge_attr, lin1_w, lin1_b, lin2_w, lin2_b, root, bias):
+    """PyG NNConv(in, out, nn=Sequential(Linear(De,32), ReLU(), Linear(32, in*out)), aggr='mean') @1.7.2 as `_NNConv` builds
+    it (src_1gp/layer.py:115-122): message = x_j @ nn(edge_attr).view(-1,in,out), MEAN over in-edges (nodes without
+    in-edges get 0), + x @ root + bias."""
+    N, cin = x.shape
+    cout = root.shape[1]
+    src, dst = edge_index[0], edge_index[1]
+    hid = torch.relu(_mm(edge_attr, lin1_w.t()) + lin1_b)
+    theta = (_mm(hid, lin2_w.t()) + lin2_b).view(-1, cin, cout)
+    msg = torch.matmul(x[src].unsqueeze(1), theta).squeeze(1)
+    cnt = torch.zeros(N, dtype=x.dtype).index_add_(0, dst, torch.ones(dst.numel(), dtype=x.dtype)).clamp(min=1)
+    return seg_sum(msg, dst, N) / cnt.view(-1, 1) + _mm(x, root) + bias
+
+
+class _NNInner(nn.Module):
+    """Parameter container with PyG NNConv's names: nn.{0,2}.{weight,bias}, root, bias."""
+
+    def __init__(self, in_channels, out_channels, edge_dim):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.nn = nn.Sequential(nn.Linear(edge_dim, 32), nn.ReLU(), nn.Linear(32, in_channels * out_channels))
+        self.root = nn.Parameter(torch.empty(in_channels, out_channels))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        bound = 1.0 / math.sqrt(in_channels)
+        nn.init.uniform_(self.root, -bound, bound)
+
+
+class _NNConv(nn.Module):
+    """src_1gp/layer.py:115-122 (the reference's default mol_block, src_1gp/run.py:21)."""
+
+    def __init__(self, in_dim, out_dim, edge_in_dim):
+        super().__init__()
+        self.conv = _NNInner(in_dim, out_dim, edge_in_dim)
+
+    def forward(self, x, edge_index, edge_attr):
+        c = self.conv
+        return nn_conv(x, edge_index, edge_attr, c.nn[0].weight, c.nn[0].bias, c.nn[2].weight, c.nn[2].bias, c.root, c.bias)
+
+
+_CONVS = {"_TripletMessage": _TripletMessage, "_TripletMessageLight": _TripletMessageLight, "_GCNConv": _GCNConv,
+          "_NNConv": _NNConv}
 _NORMS = {"_None": _None, "_PairNorm": _PairNorm}
 _ACTS = {"_None": _None, "ReLU": nn.ReLU, "CELU": nn.CELU, "LeakyReLU": nn.LeakyReLU, "RReLU": nn.RReLU}
 

@@ -96,7 +96,7 @@ class NNConv(MessagePassing):
         self.bias = Parameter(torch.Tensor(out_channels))
         bound = 1.0 / math.sqrt(in_channels)
         self.root.data.uniform_(-bound, bound)
-        self.bias.data.uniform_(-bound, bound)
+        self.bias.data.zero_()                               # reset_parameters @1.7.2: uniform(in, root); zeros(bias)
 
     def forward(self, x, edge_index, edge_attr=None, size=None):
         out = self.propagate(edge_index, x=x, edge_attr=edge_attr, size=size)

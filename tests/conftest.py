@@ -40,6 +40,12 @@ def golden_next():
     return torch.load(os.path.join(ROOT, "tests", "golden", "next.pt"))
 
 
+@pytest.fixture(scope="session")
+def golden_nnconv():
+    import torch
+    return torch.load(os.path.join(ROOT, "tests", "golden", "nnconv.pt"))
+
+
 @pytest.fixture(params=["fp32", "tf32"])
 def math_mode(request):
     """Runs a GPU test once with exact-fp32 projections and once with the TF32 tensor-core projections."""

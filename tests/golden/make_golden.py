@@ -235,6 +235,44 @@ def case_model_dti(model_mod, seed, Din=9, De=3, Pin=49, Pe=8, B=4):
     return d
 
 
+def case_nnconv_layer(layer, C, De, seed, dtype):
+    torch.manual_seed(seed)
+    b = make_molecule_batch(5, node_dim=C, edge_dim=De, seed=seed, features="normal")
+    x, ei, ea, batch, N = add_edge_cases(b)                  # isolated node (mean over no edges -> root term only) + duplicates
+    mod = layer._NNConv(C, C, De)
+    with torch.no_grad():
+        mod.conv.bias.uniform_(-0.1, 0.1)
+    mod = mod.to(dtype)
+    x = x.to(dtype).requires_grad_(True)
+    out = mod(x, ei, ea.to(dtype))
+    cot = torch.randn(out.shape).to(dtype)
+    params = list(mod.parameters())
+    g = grads_of(out, cot, [x] + params)
+    return {"x": x.detach(), "edge_index": ei, "edge_attr": ea.to(dtype), "cot": cot,
+            "state": {k: v.detach().clone() for k, v in mod.state_dict().items()},
+            "out": out.detach(), "grad_x": g[0],
+            "grad_params": {n: gg for (n, _), gg in zip(mod.named_parameters(), g[1:])}}
+
+
+def main_nnconv():
+    """`_NNConv` (src_1gp/layer.py:115-122), the reference's default mol_block, and the GP model with run.py's default
+    block + readout (`_NNConv` + `GlobalPool5`, src_1gp/run.py:21,25)."""
+    layer = load_ref("src_1gp", "layer")
+    fx = {}
+    for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        fx[f"nnconv_C36_{tag}"] = case_nnconv_layer(layer, 36, 3, 1401, dtype)
+        fx[f"nnconv_C20_De4_{tag}"] = case_nnconv_layer(layer, 20, 4, 1402, dtype)
+        fx[f"block_nnconv_C36_{tag}"] = case_block(layer, "_NNConv", "_None", "ReLU", True, 36, 3, 1403, dtype, steps=2)
+    for k in [k for k in fx if k.endswith("_f64")]:
+        fx[k].pop("state", None)
+        for name in ("edge_index", "batch", "cfg", "x", "cot", "coth", "edge_attr"):
+            fx[k].pop(name, None)
+    model_gp = load_ref("src_1gp", "model")
+    fx["gp_nnconv_pool5"] = case_model_gp(model_gp, "GlobalPool5", "_NNConv", 1404)
+    torch.save(fx, os.path.join(OUT, "nnconv.pt"))
+    print("nnconv.pt", os.path.getsize(os.path.join(OUT, "nnconv.pt")) // 1024, "KiB")
+
+
 def main_next():
     """Fixtures for the SURVEY.md §8(f) rows added after the first golden set (kept in their own file)."""
     layer = load_ref("src_1gp", "layer")
@@ -297,5 +335,7 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "next":
         main_next()
+    elif len(sys.argv) > 1 and sys.argv[1] == "nnconv":
+        main_nnconv()
     else:
         main()

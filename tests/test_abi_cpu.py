@@ -98,8 +98,11 @@ def test_name_string_construction():
     assert isinstance(blk.dropout, torch.nn.Dropout) and abs(blk.dropout.p - 0.1) < 1e-9
     assert isinstance(blk.act, torch.nn.RReLU)
     assert isinstance(layer.LinearBlock(4, 4, dropout="_None()", act="_None").act, layer._None)
+    nnb = layer.MessageBlock(12, 12, 3, conv="_NNConv")              # the reference's default block builds with the reference's names
+    assert list(nnb.conv.state_dict().keys()) == ["conv.root", "conv.bias", "conv.nn.0.weight", "conv.nn.0.bias",
+                                                  "conv.nn.2.weight", "conv.nn.2.bias"]
     with pytest.raises(NotImplementedError):
-        layer.MessageBlock(12, 12, 3, conv="_NNConv")
+        layer.MessageBlock(12, 12, 3, conv="_GATConv")
 
 
 def test_synth_batch_follows_reference_edge_order():

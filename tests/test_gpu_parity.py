@@ -659,6 +659,74 @@ def test_model_dti_reference_defaults_golden(golden_next, math_mode):
             assert err < 2e-3, f"{n}: rel err {err:.3e}"
 
 
+# ---------------------------------------------------------------------------------------------- _NNConv (run.py's default block)
+@pytest.mark.parametrize("name,C,De", [("nnconv_C36", 36, 3), ("nnconv_C20_De4", 20, 4)])
+def test_nnconv_golden(golden_nnconv, name, C, De, math_mode):
+    """`_NNConv` (typed grouped projection + gather-mean over the CSR) against the reference's own layer, outputs and all
+    gradients; includes an isolated node (mean over no edges) and duplicate edges."""
+    from glam_b200 import layer
+    c32, c64 = case(golden_nnconv, f"{name}_f32"), case(golden_nnconv, f"{name}_f64")
+    m = layer._NNConv(C, C, De)
+    assert list(m.state_dict().keys()) == list(c32["state"].keys())
+    m = _load(m, c32["state"])
+    x = c32["x"].to(DEV).requires_grad_(True)
+    out = m(x, c32["edge_index"].to(DEV), c32["edge_attr"].to(DEV))
+    tol_check(out, c32["out"], c64["out"], f"{name}.out", rtol=2e-4)
+    (out * c32["cot"].to(DEV)).sum().backward()
+    tol_check(x.grad, c32["grad_x"], c64["grad_x"], f"{name}.grad_x", rtol=2e-4)
+    for n, p in m.named_parameters():
+        tol_check(p.grad, c32["grad_params"][n], c64["grad_params"][n], f"{name}.grad[{n}]", rtol=2e-4)
+
+
+def test_nnconv_rejects_general_edge_rows():
+    from glam_b200 import layer, _lib
+    m = layer._NNConv(36, 36, 3).to(DEV)
+    ei = torch.tensor([[0, 1, 2], [1, 2, 0]], device=DEV)
+    with pytest.raises(_lib.GlamError):
+        m(torch.randn(3, 36, device=DEV), ei, torch.rand(3, 3, device=DEV))
+
+
+def test_nnconv_block_golden(golden_nnconv, math_mode):
+    from glam_b200 import layer
+    c32, c64 = case(golden_nnconv, "block_nnconv_C36_f32"), case(golden_nnconv, "block_nnconv_C36_f64")
+    cfg = c32["cfg"]
+    blk = layer.MessageBlock(cfg["C"], cfg["C"], cfg["De"], norm=cfg["norm"], dropout="_None()", conv=cfg["conv"], act=cfg["act"],
+                             res=cfg["res"])
+    blk = _load(blk, c32["state"])
+    x0 = c32["x"].to(DEV).requires_grad_(True)
+    x, h = x0, None
+    for _ in range(cfg["steps"]):
+        x, h = blk(x, c32["edge_index"].to(DEV), c32["edge_attr"].to(DEV), h=h, batch=c32["batch"].to(DEV))
+    tol_check(x, c32["out"], c64["out"], "block_nnconv.out", rtol=2e-4)
+    tol_check(h, c32["h"], c64["h"], "block_nnconv.h", rtol=2e-4)
+    ((x * c32["cot"].to(DEV)).sum() + (h * c32["coth"].to(DEV)).sum()).backward()
+    tol_check(x0.grad, c32["grad_x"], c64["grad_x"], "block_nnconv.grad_x", rtol=2e-4)
+    for n, p in blk.named_parameters():
+        tol_check(p.grad, c32["grad_params"][n], c64["grad_params"][n], f"block_nnconv.grad[{n}]", rtol=2e-4)
+
+
+def test_model_gp_reference_defaults_golden(golden_nnconv, math_mode):
+    """GLAM-GP with the reference's default block and readout (`_NNConv` + `GlobalPool5`, src_1gp/run.py:21,25) against the
+    reference's own output and parameter gradients."""
+    from glam_b200 import model
+    c = golden_nnconv["gp_nnconv_pool5"]
+    cfg = c["cfg"]
+    m = model.ArchitectureGP(cfg["Din"], cfg["De"], graph_do="_None()", end_do="_None()", hid_dim_alpha=4, e_dim=cfg["e_dim"],
+                             out_dim=1, mol_block=cfg["block"], message_steps=3, mol_readout=cfg["readout"],
+                             graph_norm=cfg["graph_norm"], pre_act="ReLU", graph_act="CELU", flat_act="LeakyReLU")
+    assert list(m.state_dict().keys()) == list(c["state"].keys())
+    m = _load(m, c["state"]).eval()
+    out = m(ns(c["x"].to(DEV), c["edge_index"].to(DEV), c["edge_attr"].to(DEV), c["batch"].to(DEV)))
+    tf32 = math_mode == "tf32"
+    torch.testing.assert_close(out.cpu(), c["out"], rtol=2e-2 if tf32 else 2e-4, atol=2e-2 if tf32 else 2e-5)
+    torch.nn.functional.mse_loss(out, c["y"].to(DEV)).backward()
+    for n, p in m.named_parameters():
+        ref = c["grad_params"][n]
+        scale = ref.abs().max().clamp(min=1e-6)
+        err = (p.grad.cpu() - ref).abs().max() / scale
+        assert err < (5e-2 if tf32 else 2e-3), f"{n}: rel err {err:.3e}"
+
+
 # ---------------------------------------------------------------------------------------------- windowed edge kernels
 def _edge_phase_ref64(xpe, ea, we, ae, src, dst, N, H, C, slope, g_agg):
     """fp64 restatement of TripletMessage.message + aggregate on the extended projection (SURVEY.md Appendix C;

@@ -186,3 +186,54 @@ def test_oracle_dti_model_matches_reference(golden_next):
     torch.nn.functional.binary_cross_entropy_with_logits(out, c["y"]).backward()
     for n, p in m.named_parameters():
         torch.testing.assert_close(p.grad, c["grad_params"][n], rtol=2e-3, atol=1e-6, msg=lambda s, n=n: f"{n}: {s}")
+
+
+# ---------------------------------------------------------------------------------------------- _NNConv (run.py's default block)
+@pytest.mark.parametrize("tag", TAGS)
+@pytest.mark.parametrize("name,C,De", [("nnconv_C36", 36, 3), ("nnconv_C20_De4", 20, 4)])
+def test_oracle_nnconv_matches_reference(golden_nnconv, name, C, De, tag):
+    c = case(golden_nnconv, f"{name}_{tag}")
+    m = O._NNConv(C, C, De).to(c["x"].dtype)
+    assert list(m.state_dict().keys()) == list(case(golden_nnconv, f"{name}_f32")["state"].keys())
+    m.load_state_dict(c["state"])
+    x = c["x"].clone().requires_grad_(True)
+    out = m(x, c["edge_index"], c["edge_attr"])
+    torch.testing.assert_close(out, c["out"], **_tol(tag))
+    g = torch.autograd.grad((out * c["cot"]).sum(), [x] + list(m.parameters()))
+    torch.testing.assert_close(g[0], c["grad_x"], **_tol(tag))
+    _check_grads(list(m.named_parameters()), g[1:], c["grad_params"], tag)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_oracle_nnconv_block_matches_reference(golden_nnconv, tag):
+    c = case(golden_nnconv, f"block_nnconv_C36_{tag}")
+    cfg = c["cfg"]
+    blk = O.MessageBlock(cfg["C"], cfg["C"], cfg["De"], norm=cfg["norm"], dropout="_None()", conv=cfg["conv"], act=cfg["act"],
+                         res=cfg["res"]).to(c["x"].dtype)
+    blk.load_state_dict(c["state"])
+    x0 = c["x"].clone().requires_grad_(True)
+    x, h = x0, None
+    for _ in range(cfg["steps"]):
+        x, h = blk(x, c["edge_index"], c["edge_attr"], h=h, batch=c["batch"])
+    torch.testing.assert_close(x, c["out"], **_tol(tag))
+    torch.testing.assert_close(h, c["h"], **_tol(tag))
+    g = torch.autograd.grad((x * c["cot"]).sum() + (h * c["coth"]).sum(), [x0] + list(blk.parameters()))
+    torch.testing.assert_close(g[0], c["grad_x"], **_tol(tag))
+    _check_grads(list(blk.named_parameters()), g[1:], c["grad_params"], tag)
+
+
+def test_oracle_model_gp_reference_defaults(golden_nnconv):
+    """GLAM-GP with run.py's default block and readout (`_NNConv` + `GlobalPool5`, src_1gp/run.py:21,25)."""
+    c = golden_nnconv["gp_nnconv_pool5"]
+    cfg = c["cfg"]
+    m = O.ArchitectureGP(cfg["Din"], cfg["De"], hid_dim_alpha=4, e_dim=cfg["e_dim"], out_dim=1, mol_block=cfg["block"],
+                         message_steps=3, mol_readout=cfg["readout"], graph_norm=cfg["graph_norm"],
+                         pre_act="ReLU", graph_act="CELU", flat_act="LeakyReLU")
+    assert list(m.state_dict().keys()) == list(c["state"].keys())
+    m.load_state_dict(c["state"])
+    m.eval()
+    out = m(ns(c["x"], c["edge_index"], c["edge_attr"], c["batch"]))
+    torch.testing.assert_close(out, c["out"], rtol=2e-4, atol=2e-5)
+    loss = torch.nn.functional.mse_loss(out, c["y"])
+    g = torch.autograd.grad(loss, list(m.parameters()))
+    _check_grads(list(m.named_parameters()), g, c["grad_params"], "f32")
