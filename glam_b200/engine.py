@@ -220,16 +220,28 @@ class TrainStep:
 
 
 class ScreenStep:
-    """Eval-mode forward for virtual screening; returns scores [B, out_dim] (device)."""
+    """Eval-mode forward for virtual screening; returns scores [B, out_dim] (device).
+
+    double_buffer=True: two sets of static input buffers and two captured graphs; `step(batch, prefetch=next_batch)`
+    copies the next host batch on a copy stream while the current one computes (same scheme as TrainStep).  Each slot
+    has its own output tensor, so the scores of step i stay valid while step i+1 runs."""
 
     def __init__(self, model: torch.nn.Module, example: GraphBatch, device="cuda", use_cuda_graph: bool = True,
-                 warmup: int = 3):
+                 warmup: int = 3, double_buffer: bool = False):
         self.model = model.to(device).eval()
         self.device = torch.device(device)
-        self.static = _static_like(example, self.device)
-        _copy_into(self.static, example)
-        self.out = None
-        self.graph = None
+        self.statics = [_static_like(example, self.device) for _ in range(2 if double_buffer else 1)]
+        for st in self.statics:
+            _copy_into(st, example)
+        self.static = self.statics[0]
+        self.outs = [None] * len(self.statics)
+        self.graphs = []
+        self._slot = 0
+        self._prefetched = None
+        if double_buffer:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._copied = [torch.cuda.Event() for _ in self.statics]
+            self._consumed = [torch.cuda.Event() for _ in self.statics]
         with torch.no_grad():
             if use_cuda_graph:
                 s = torch.cuda.Stream(device=self.device)
@@ -240,21 +252,49 @@ class ScreenStep:
                         self.model(self.static)
                 torch.cuda.current_stream(self.device).wait_stream(s)
                 torch.cuda.synchronize(self.device)
+                pool = None
+                for i, st in enumerate(self.statics):
+                    G.clear_caches()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool):
+                        self.outs[i] = self.model(st)
+                    pool = g.pool()
+                    self.graphs.append(g)
                 G.clear_caches()
-                self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
-                    self.out = self.model(self.static)
-                G.clear_caches()
+        self.graph = self.graphs[0] if self.graphs else None
+
+    @property
+    def out(self):
+        return self.outs[self._slot]
 
     def run_resident(self):
-        if self.graph is not None:
-            self.graph.replay()
+        if self.graphs:
+            self.graphs[self._slot].replay()
         else:
             with torch.no_grad():
                 G.clear_caches()
-                self.out = self.model(self.static)
-        return self.out
+                self.outs[self._slot] = self.model(self.statics[self._slot])
+        return self.outs[self._slot]
 
-    def step(self, batch: GraphBatch) -> torch.Tensor:
-        _copy_into(self.static, batch)
-        return self.run_resident()
+    def step(self, batch: GraphBatch, prefetch: Optional[GraphBatch] = None) -> torch.Tensor:
+        if len(self.statics) == 1:
+            _copy_into(self.static, batch)
+            return self.run_resident()
+        main = torch.cuda.current_stream(self.device)
+        slot = self._slot
+        if self._prefetched is batch:
+            main.wait_event(self._copied[slot])
+        else:
+            _copy_into(self.statics[slot], batch)
+        self._prefetched = None
+        out = self.run_resident()
+        self._consumed[slot].record(main)
+        if prefetch is not None:
+            nxt = slot ^ 1
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._consumed[nxt])
+                _copy_into(self.statics[nxt], prefetch)
+                self._copied[nxt].record(self._copy_stream)
+            self._prefetched = prefetch
+            self._slot = nxt
+        return out

@@ -845,3 +845,21 @@ def test_windowed_edge_kernels(kind, H, C, De, onehot, light):
             assert torch.equal(g_xpe, b2[0]) and torch.equal(g_logit, b2[1]) and (g_we is None or torch.equal(g_we, b2[2]))
     finally:
         ops.USE_EDGE_TILES = True
+
+
+def test_screen_step_double_buffer_matches_eager():
+    """engine.ScreenStep (captured eval forward) with and without the double-buffered host prefetch against the eager
+    module call, bitwise."""
+    from glam_b200.engine import ScreenStep
+    from glam_b200.synth import make_molecule_batch
+    m, _ = _gp_pair(9, 3, "Set2Set", "_TripletMessage")
+    m = m.to(DEV).eval()
+    batches = [make_molecule_batch(64, seed=900 + i, total_nodes=64 * 22, total_edges=64 * 46).pin_memory() for i in range(4)]
+    with torch.no_grad():
+        want = [m(b.to(DEV)).clone() for b in batches]
+    s1 = ScreenStep(m, batches[0], device=DEV)
+    s2 = ScreenStep(m, batches[0], device=DEV, double_buffer=True)
+    for i, b in enumerate(batches):
+        o1 = s1.step(b).clone()
+        o2 = s2.step(b, prefetch=batches[i + 1] if i + 1 < len(batches) else None).clone()
+        assert torch.equal(o1, want[i]) and torch.equal(o2, want[i])
