@@ -971,6 +971,246 @@ edge_win_bwd_dst_kernel(const __grid_constant__ WinArgs a, const float* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, destination pass, pipelined
+// ncu on edge_win_bwd_dst_kernel: 45 % of the warp samples sit on the two DRAM round trips at the top of every tile (rowptr,
+// then the index / edge_attr / alpha words) and on the barriers behind them.  Here
+//   * the raw words of tile k+1 (rowptr slice, sources, edge_attr rows, alpha) are copied global -> shared with cp.async
+//     (LDGSTS: no registers, nothing waits) while tile k computes, and turned into records at the top of tile k+1;
+//   * the softmax phase reads s_i / s_j from the records (stashed right after the window lands), so the window and g_agg
+//     buffers are free as soon as the dots are done: the bulk copy of tile k+1 is issued THERE and overlaps the softmax
+//     phase of tile k.
+constexpr int kDstMaxEdges = 256;            // records per tile (molecular tiles: <= 4 in-edges per atom)
+
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+struct Dst2Smem {
+    float* rows; float4* We4; float* Ae; uint64_t* bar; int* rp;
+    int4* rec4; float* rec_a; float* rec_g; float* rec_sj; float* rec_si;
+    int* raw_src; float* raw_ea; float* raw_al; int* raw_rp;
+    float* gagg; float4* ovf;
+};
+__host__ __device__ inline size_t dst2_fixed_floats(int De, int nq, int H, bool use_ep) {
+    const int HC = nq * 4;
+    return (size_t)(use_ep ? De * nq * 4 : 0) + 32 + 4 + (kWinMaxTile + 4) + (size_t)kDstMaxEdges * (4 + 3 * H) + kWinMaxTile * 4 +
+           (size_t)kDstMaxEdges * (1 + kWinRegDe + H) + (kWinMaxTile + 4) + (size_t)kWinMaxTile * HC +
+           (use_ep ? (size_t)kWinWarps * De * nq * 4 : 0);
+}
+__device__ __forceinline__ Dst2Smem dst2_carve(float* base, int rmax, int ld, int De, int nq, int H, bool use_ep) {
+    Dst2Smem s;
+    float* p = base;
+    s.rows = p; p += (size_t)rmax * ld;
+    s.We4 = reinterpret_cast<float4*>(p); p += use_ep ? De * nq * 4 : 0;
+    s.Ae = p; p += 32;
+    s.bar = reinterpret_cast<uint64_t*>(p); p += 4;
+    s.rp = reinterpret_cast<int*>(p); p += kWinMaxTile + 4;
+    s.rec4 = reinterpret_cast<int4*>(p); p += kDstMaxEdges * 4;
+    s.rec_a = p; p += kDstMaxEdges * H;
+    s.rec_g = p; p += kDstMaxEdges * H;
+    s.rec_sj = p; p += kDstMaxEdges * H;
+    s.rec_si = p; p += kWinMaxTile * 4;
+    s.raw_src = reinterpret_cast<int*>(p); p += kDstMaxEdges;
+    s.raw_ea = p; p += kDstMaxEdges * kWinRegDe;
+    s.raw_al = p; p += kDstMaxEdges * H;
+    s.raw_rp = reinterpret_cast<int*>(p); p += kWinMaxTile + 4;
+    s.gagg = p; p += (size_t)kWinMaxTile * nq * 4;
+    s.ovf = reinterpret_cast<float4*>(p);
+    return s;
+}
+
+template <int H, int CPI, bool USE_EP, int DR>
+__global__ void __launch_bounds__(kWinThreads, kWinDstCtasPerSM)
+edge_win_bwd_dst2_kernel(const __grid_constant__ WinArgs a, const float* __restrict__ alpha, const float* __restrict__ g_agg,
+                         float* __restrict__ g_logit, float* __restrict__ g_xpe, float* __restrict__ gwe_partial) {
+    extern __shared__ __align__(128) float smem_f[];
+    const int HC = H * a.C, nq = HC >> 2, De = a.De, ld = (int)a.ld;
+    const ItemGeom ig{nq / CPI, (a.C >> 2) / CPI};
+    const Dst2Smem s = dst2_carve(smem_f, a.rmax, ld, De, nq, H, USE_EP);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (USE_EP)
+        for (int i = tid; i < De * nq; i += kWinThreads) s.We4[i] = ld4(a.w_edge + 4 * i);
+    for (int i = tid; i < De * H; i += kWinThreads) s.Ae[i] = a.att_edge[i];
+    if (USE_EP)
+        for (int i = tid; i < kWinWarps * De * nq; i += kWinThreads) s.ovf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) { tc::mbar_init(s.bar, 1); tc::fence_mbar_init(); }
+    float4 gw[DR][CPI];
+#pragma unroll
+    for (int d = 0; d < DR; ++d)
+#pragma unroll
+        for (int k = 0; k < CPI; ++k) gw[d][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t parity = 0;
+
+    // raw words of a tile -> shared memory, asynchronously (every thread commits one group, possibly empty)
+    auto issue_raw = [&](const int4& dsc, int64_t tile) {
+        const int e0 = dsc.z, ne = dsc.w - dsc.z;
+        const int64_t t0 = tile * a.D;
+        const int nd = (int)min((int64_t)a.D, a.N - t0);
+        if (tid <= nd) cp_async4(s.raw_rp + tid, a.rowptr + t0 + tid);
+        if (ne <= kDstMaxEdges) {
+            for (int i = tid; i < ne; i += kWinThreads) cp_async4(s.raw_src + i, a.other + e0 + i);
+            for (int i = tid; i < ne * De; i += kWinThreads) cp_async4(s.raw_ea + i, a.ea + (int64_t)e0 * De + i);
+            for (int i = tid; i < ne * H; i += kWinThreads) cp_async4(s.raw_al + i, alpha + (int64_t)e0 * H + i);
+        }
+        cp_async_commit();
+    };
+    // window + the tile's own g_agg rows by the copy engine (warp 0)
+    auto issue_bulk = [&](const int4& dsc, int64_t tile) {
+        const int nrows = dsc.y - dsc.x, ne = dsc.w - dsc.z;
+        const int64_t t0 = tile * a.D;
+        const int nd = (int)min((int64_t)a.D, a.N - t0);
+        const bool staged = ne <= kDstMaxEdges && ne > 0;
+        if (staged && warp == 0) {
+            const bool near = nrows <= a.rmax;
+            tc::fence_proxy_async_smem();
+            const uint32_t wbytes = near ? (uint32_t)nrows * (uint32_t)ld * 4u : 0u, gbytes = (uint32_t)nd * (uint32_t)HC * 4u;
+            if (lane == 0) tc::mbar_expect_tx(s.bar, wbytes + gbytes);
+            __syncwarp();
+            for (uint32_t off = (uint32_t)lane * kBulkChunk; off < wbytes; off += 32u * kBulkChunk)
+                bulk_g2s(reinterpret_cast<char*>(s.rows) + off, reinterpret_cast<const char*>(a.xpe + (int64_t)dsc.x * a.ld) + off,
+                         min(kBulkChunk, wbytes - off), s.bar);
+            for (uint32_t off = (uint32_t)lane * kBulkChunk; off < gbytes; off += 32u * kBulkChunk)
+                bulk_g2s(reinterpret_cast<char*>(s.gagg) + off, reinterpret_cast<const char*>(g_agg + t0 * HC) + off,
+                         min(kBulkChunk, gbytes - off), s.bar);
+        }
+    };
+
+    __syncthreads();
+    int4 desc = blockIdx.x < a.T ? a.tiles[blockIdx.x] : make_int4(0, 0, 0, 0);
+    int4 desc_n = make_int4(0, 0, 0, 0);
+    if (blockIdx.x < a.T) {
+        issue_bulk(desc, blockIdx.x);
+        issue_raw(desc, blockIdx.x);
+        if ((int64_t)blockIdx.x + gridDim.x < a.T) desc_n = a.tiles[blockIdx.x + gridDim.x];
+    }
+    const float4* gagg4 = reinterpret_cast<const float4*>(s.gagg);
+    for (int64_t tile = blockIdx.x; tile < a.T; tile += gridDim.x) {
+        const int64_t t0 = tile * a.D;
+        const int nd = (int)min((int64_t)a.D, a.N - t0);
+        const int lo = desc.x, nrows = desc.y - desc.x, e0 = desc.z, ne = desc.w - desc.z;
+        const int64_t nxt = tile + gridDim.x;
+        int4 desc_nn = make_int4(0, 0, 0, 0);
+        if (nxt + gridDim.x < a.T) desc_nn = a.tiles[nxt + gridDim.x];
+        const bool overflow = ne > kDstMaxEdges;
+        const bool staged = !overflow && ne > 0;
+        const bool near = staged && nrows <= a.rmax;
+        cp_async_wait_all();
+        __syncthreads();                                            // raw words of this tile are visible; previous tile is finished
+        if (tid <= nd) s.rp[tid] = s.raw_rp[tid] - e0;
+        if (overflow) {
+            __syncthreads();
+            if (nxt < a.T) issue_raw(desc_n, nxt);
+            bwd_dst_overflow_tile<H, USE_EP>(a, s.We4, s.Ae, s.rp, nd, t0, e0, alpha, g_agg, g_logit, g_xpe, s.ovf + warp * De * nq);
+            __syncthreads();
+            if (nxt < a.T) issue_bulk(desc_n, nxt);
+            desc = desc_n;
+            desc_n = desc_nn;
+            continue;
+        }
+        // ---- records from the staged raw words
+        const int base = near ? lo : 0;
+        int* rec_w = reinterpret_cast<int*>(s.rec4);
+        for (int e = tid; e < ne; e += kWinThreads) {
+            const float* earow = s.raw_ea + e * De;
+            int nz = 0, ty = 0;
+            float val = 0.f;
+            for (int dd = 0; dd < De; ++dd) {
+                const float v = earow[dd];
+                if (v != 0.f) { ++nz; ty = dd; val = v; }
+            }
+            rec_w[4 * e + 0] = s.raw_src[e] - base;
+            rec_w[4 * e + 2] = nz == 1 ? ty : -1;
+            rec_w[4 * e + 3] = __float_as_int(nz == 1 ? val : 1.f);
+        }
+        for (int d = tid; d < nd; d += kWinThreads)
+            for (int e = s.raw_rp[d] - e0; e < s.raw_rp[d + 1] - e0; ++e) rec_w[4 * e + 1] = d;
+        for (int i = tid; i < ne * H; i += kWinThreads) s.rec_a[i] = s.raw_al[i];
+        __syncthreads();                                            // records visible; the raw buffers are free
+        if (nxt < a.T) issue_raw(desc_n, nxt);
+        if (staged) {
+            tc::mbar_wait(s.bar, parity);
+            parity ^= 1u;
+        }
+        // ---- stash s_i / s_j for the softmax phase, then the dots
+        if (near) {
+            const int own0 = (int)(t0 - lo);
+            for (int i = tid; i < ne * H; i += kWinThreads) {
+                const int e = i / H, h = i - e * H;
+                s.rec_sj[i] = s.rows[s.rec4[e].x * ld + HC + H + h];
+            }
+            for (int i = tid; i < nd * H; i += kWinThreads) {
+                const int d = i / H, h = i - d * H;
+                s.rec_si[i] = s.rows[(own0 + d) * ld + HC + h];
+            }
+            bwd_dots<H, CPI, USE_EP, DR, int>(s.rows, ld, gagg4, nq, ig, ne, e0, De, a.ea, s.We4, s.rec4, s.rec_a, s.rec_g, gw);
+        } else {
+            for (int i = tid; i < ne * H; i += kWinThreads) {
+                const int e = i / H, h = i - e * H;
+                s.rec_sj[i] = a.xpe[(int64_t)s.rec4[e].x * ld + HC + H + h];
+            }
+            for (int i = tid; i < nd * H; i += kWinThreads) {
+                const int d = i / H, h = i - d * H;
+                s.rec_si[i] = a.xpe[(t0 + d) * ld + HC + h];
+            }
+            if (ne > 0)
+                bwd_dots<H, CPI, USE_EP, DR, int64_t>(a.xpe, ld, gagg4, nq, ig, ne, e0, De, a.ea, s.We4, s.rec4, s.rec_a, s.rec_g, gw);
+        }
+        __syncthreads();                                            // dots done: window and g_agg buffers are free
+        if (nxt < a.T) issue_bulk(desc_n, nxt);
+        // ---- softmax + leaky_relu backward from the records alone (overlaps the next tile's copies)
+        for (int idx = tid; idx < nd * H; idx += kWinThreads) {
+            const int d = idx / H, h = idx - d * H;
+            const int beg = s.rp[d], end = s.rp[d + 1];
+            const float si = s.rec_si[idx];
+            float dot = 0.f, gsi = 0.f;
+            for (int e = beg; e < end; ++e) dot = fmaf(s.rec_a[e * H + h], s.rec_g[e * H + h], dot);
+            for (int e = beg; e < end; ++e) {
+                // same association as the forward: (s_i + edge part) + s_j, the edge part summed from zero
+                const int4 r = s.rec4[e];
+                float le = 0.f;
+                if (r.z >= 0) le = __fmul_rn(__int_as_float(r.w), s.Ae[r.z * H + h]);
+                else for (int dd = 0; dd < De; ++dd) le = fmaf(a.ea[(int64_t)(e0 + e) * De + dd], s.Ae[dd * H + h], le);
+                const float l = __fadd_rn(__fadd_rn(si, le), s.rec_sj[e * H + h]);
+                float g = s.rec_a[e * H + h] * (s.rec_g[e * H + h] - dot);
+                g *= (l > 0.f ? 1.f : a.slope);
+                g_logit[(int64_t)(e0 + e) * H + h] = g;
+                gsi += g;
+            }
+            g_xpe[(t0 + d) * a.ld + HC + h] = gsi;
+        }
+        desc = desc_n;
+        desc_n = desc_nn;
+    }
+    if (USE_EP) {
+        // fixed-order reduction: lanes (edge slot, item) of every warp -> staging in the (dead) window area -> one partial per CTA
+        __syncthreads();
+        float4* stage = reinterpret_cast<float4*>(s.rows);        // [kWinWarps][epw][De][nq]
+        const int epw = 32 / ig.ni, el = lane / ig.ni, g = lane - el * ig.ni;
+        if (el < epw)
+#pragma unroll
+            for (int d = 0; d < DR; ++d)
+                if (d < De)
+#pragma unroll
+                    for (int k = 0; k < CPI; ++k) stage[((warp * epw + el) * De + d) * nq + g * CPI + k] = gw[d][k];
+        __syncthreads();
+        float4* P = reinterpret_cast<float4*>(gwe_partial) + (int64_t)blockIdx.x * De * nq;
+        for (int idx = tid; idx < De * nq; idx += kWinThreads) {
+            float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int w = 0; w < kWinWarps * epw; ++w) {
+                const float4 v = stage[w * De * nq + idx];
+                sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w;
+            }
+            for (int w = 0; w < kWinWarps; ++w) {                 // hub-tile contributions
+                const float4 v = s.ovf[w * De * nq + idx];
+                sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w;
+            }
+            P[idx] = sacc;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ backward, source pass
 // tile of consecutive SOURCES; window = rows g_agg[lo:hi) of the destinations of their out-edges
 // records: {dst slot, type} | c[H] = alpha * value | gl[H] = g_logit
@@ -1213,6 +1453,33 @@ int edge_win_bwd_dst(const float* xpe, int64_t ldxp, const float* ea, const floa
     const int HC = heads * C, nq = HC / 4, cpi = pick_cpi(C), ni = nq / cpi;
     if (De > kWinRegDe || ni > 32) return 0;
     const int D = edge_tile_rows(N);
+    if (win_variant() >= 2) {
+        // pipelined kernel: cp.async staging of the next tile's raw words, next window issued behind the dots
+        const size_t fixed = sizeof(float) * dst2_fixed_floats(De, nq, heads, use_ep);
+        const size_t stage2 = sizeof(float4) * (size_t)kWinWarps * (32 / ni) * De * nq;
+        int rmax2 = fixed + 1024 < (size_t)kWinDstSmemBudget ? (int)(((size_t)kWinDstSmemBudget - fixed) / (sizeof(float) * (size_t)ldxp)) : 0;
+        if (rmax2 >= D + 24 && (!use_ep || (size_t)rmax2 * ldxp * 4 >= stage2)) {
+            WinArgs a{xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax2, (N + D - 1) / D,
+                      slope, win_debug()};
+            const size_t smem = fixed + sizeof(float) * (size_t)rmax2 * ldxp;
+            if (De <= 3) {
+                GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
+                    auto fn = edge_win_bwd_dst2_kernel<HH_, CPI_, UE_, 3>;
+                    win_allow_smem(fn, smem);
+                    fn<<<win_grid(a.T, kWinDstCtasPerSM), kWinThreads, smem, stream>>>(a, alpha, g_agg, g_logit, g_xpe, gwe_partial);
+                })
+            } else {
+                GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
+                    auto fn = edge_win_bwd_dst2_kernel<HH_, CPI_, UE_, kWinRegDe>;
+                    win_allow_smem(fn, smem);
+                    fn<<<win_grid(a.T, kWinDstCtasPerSM), kWinThreads, smem, stream>>>(a, alpha, g_agg, g_logit, g_xpe, gwe_partial);
+                })
+            }
+            GLAM_CHECK_LAUNCH();
+            *launched = 1;
+            return 0;
+        }
+    }
     const int rec = 4 + 2 * heads;
     const int extra = kWinMaxTile * HC + (use_ep ? kWinWarps * De * nq * 4 : 0);
     const int rmax = win_rmax(kWinDstSmemBudget, ldxp, De, nq, use_ep, rec, extra);
