@@ -50,6 +50,17 @@ def test_abi_version_and_workspace_queries(lib):
     assert lib.glam_triplet_bwd_workspace_bytes(3, 36, 3) >= 3 * 108 * 4
 
 
+def test_edge_tile_geometry(lib):
+    """Host side of the windowed edge kernels: tile rows / counts (no GPU needed)."""
+    for n in (1, 15, 16, 1000, 102400, 409600, 10_000_000):
+        d, t = lib.glam_edge_tile_rows(n), lib.glam_edge_tile_count(n)
+        assert 16 <= d <= 64 and t == (n + d - 1) // d
+    # the bench shape: 58-row tiles, a whole number of tiles per resident CTA (444 = 148 SMs x 3, 296 = 148 x 2)
+    assert lib.glam_edge_tile_rows(102400) == 58 and lib.glam_edge_tile_count(102400) == 1766
+    assert lib.glam_build_edge_tiles(None, None, None, None, 0, 0, None, None, None) == 0          # empty graph: nothing to do
+    assert lib.glam_build_edge_tiles(None, None, None, None, 10, 0, None, None, None) < 0           # null pointers are reported
+
+
 def test_argument_errors_are_reported(lib):
     from glam_b200 import _lib
     rc = lib.glam_triplet_edge_fwd(None, 0, None, None, None, None, None, None, 10, 10, 9, 36, 3, 0.2, None, None, None)
