@@ -65,12 +65,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.stamps = index, None, [], []
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -81,6 +81,7 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+            self.stamps.append(time.time())
 
     def __exit__(self, *a):
         if self.proc is not None:
@@ -91,10 +92,24 @@ class ClockSampler:
             except subprocess.TimeoutExpired:
                 self.proc.kill()
 
-    def summary(self):
+    def wait_first_sample(self, timeout=5.0):
+        """Block until nvidia-smi has produced its first line (NVML initialisation takes a driver-wide lock for a few
+        hundred ms: it must be over before the timed region starts) or `timeout` seconds have passed."""
+        if self.proc is None:
+            return
+        t0 = time.time()
+        while not self.lines and time.time() - t0 < timeout and self.proc.poll() is None:
+            time.sleep(0.02)
+
+    def summary(self, t0=None, t1=None):
+        """Median SM clock / reasons over the samples that arrived in [t0, t1] (the timed region); all samples if none did."""
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = list(self.lines)
+        if t0 is not None:
+            inside = [ln for ln, ts in zip(lines, list(self.stamps)) if t0 <= ts <= t1 + 0.06]
+            lines = inside or lines
+        for ln in lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -315,8 +330,15 @@ def run_ours(args):
         ts.load(resident[i % N_RESIDENT])
         ts.run_resident()
 
-    for i in range(args.warmup):
+    # clocks are sampled on rank 0 only (one nvidia-smi poller per box: eight of them starting inside the timed region took
+    # a driver-wide lock and doubled the 8-GPU step time), started BEFORE the warm-up so that NVML start-up is over
+    clk = ClockSampler(local) if rank == 0 else None
+    if clk is not None:
+        clk.__enter__()
+    for i in range(args.warmup + (10 if world > 1 else 0)):      # extra untimed replays let NCCL's graph-launched kernels settle
         step_resident(i)
+    if clk is not None:
+        clk.wait_first_sample()
     if args.ncu_range:
         # launch-list capture: `ncu --profile-from-start off ... bench.py --ncu-range` sees exactly the timed training steps
         torch.cuda.synchronize()
@@ -324,8 +346,11 @@ def run_ours(args):
         timed(step_resident, args.steps)
         torch.cuda.profiler.stop()
         os._exit(0)
-    with ClockSampler(local) as clk:
-        ms_total = timed(step_resident, args.steps)
+    t_wall0 = time.time()
+    ms_total = timed(step_resident, args.steps)
+    t_wall1 = time.time()
+    if clk is not None:
+        clk.__exit__(None, None, None)
     ms_per_step = ms_total / args.steps
     value = GRAPHS * world / (ms_per_step * 1e-3)
 
@@ -344,7 +369,7 @@ def run_ours(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(world), "clocks": clk.summary(),
+            "data": "synthetic", "config": workload_config(world), "clocks": clk.summary(t_wall0, t_wall1) if clk is not None else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host[0].nbytes(), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e,
                     "note": "TrainStep.step(host_batch, prefetch=next_host_batch): every step's H2D copy is inside the timed "
