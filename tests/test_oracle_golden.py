@@ -237,3 +237,31 @@ def test_oracle_model_gp_reference_defaults(golden_nnconv):
     loss = torch.nn.functional.mse_loss(out, c["y"])
     g = torch.autograd.grad(loss, list(m.parameters()))
     _check_grads(list(m.named_parameters()), g, c["grad_params"], "f32")
+
+
+def test_nnconv_grouped_projection_algebra():
+    """The formulation the library uses for `_NNConv` (glam_b200/functional.py::NNConvFn) restated in torch on the CPU:
+    with one-hot bond features the per-edge matrix nn(edge_attr) takes edge_dim distinct values Theta_t = nn(e_t), so
+    message_e = (x @ [Theta_0 | .. | Theta_{De-1}])[src_e, t_e*C:(t_e+1)*C] and the layer is a typed gather-mean plus the
+    root term.  Must equal the reference formulation (oracle.nn_conv, one [C,C] matrix per edge) to fp64 round-off,
+    including isolated nodes and duplicate edges."""
+    from glam_b200.synth import make_molecule_batch
+    torch.manual_seed(3)
+    C, De = 12, 4
+    b = make_molecule_batch(6, node_dim=C, edge_dim=De, seed=9, features="normal")
+    x = torch.cat([b.x, torch.randn(2, C)]).double()                       # two isolated nodes at the end
+    ei = torch.cat([b.edge_index, b.edge_index[:, :3]], dim=1)             # duplicate edges
+    ea = torch.cat([b.edge_attr, b.edge_attr[:3]]).double()
+    m = O._NNConv(C, C, De).double()
+    with torch.no_grad():
+        m.conv.bias.uniform_(-0.1, 0.1)
+    want = m(x, ei, ea)
+    N, E = x.shape[0], ei.shape[1]
+    theta = m.conv.nn(torch.eye(De, dtype=torch.float64)).view(De, C, C)
+    y = x @ theta.permute(1, 0, 2).reshape(C, De * C)                      # grouped projection [N, De*C]
+    t = ea.argmax(1)
+    rows = y.view(N * De, C)[ei[0] * De + t]                               # typed gather
+    deg = torch.zeros(N, dtype=torch.float64).index_add_(0, ei[1], torch.ones(E, dtype=torch.float64)).clamp(min=1)
+    got = torch.zeros(N, C, dtype=torch.float64).index_add_(0, ei[1], rows) / deg[:, None] + x @ m.conv.root + m.conv.bias
+    torch.testing.assert_close(got, want, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(got[-2:], (x @ m.conv.root + m.conv.bias)[-2:], rtol=0, atol=0)
