@@ -1,0 +1,695 @@
+// The message stack of GLAM as ONE kernel: `message_steps` applications of the (weight-tied) MessageBlock
+//   conv = TripletMessage (src_1gp/layer.py:36-61) -> CELU -> GRU (layer.py:260-263) -> (+identity) -> act (:265-266)
+// looped by src_1gp/model.py:53-54, on graph-aligned tiles that never leave the SM.
+//
+// Why: a PyG batch is block-diagonal (src_1gp/dataset.py:75-87 + Batch.from_data_list): no edge crosses a graph, and the
+// nodes of a graph are consecutive rows.  A tile made of WHOLE graphs (<= 128 nodes: the M of one tcgen05.mma) is
+// therefore closed under message passing — every source row of every in-edge is inside the tile — so the whole chain
+//   x --Wn--> xp --(edge softmax / aggregate)--> agg --Wscale,+b,CELU--> m --W_ih | h --W_hh--> gates --> h', x'
+// can run out of shared memory / tensor memory, step after step, with x and h resident: per tile HBM sees the input rows
+// once, the index words once (not once per step), and the output rows.  Unfused, the same work was 3 launches per step
+// for the conv alone with xp [N,HC+2H] and agg [N,HC] written and re-read (6.4x the algorithmic bytes).
+//
+// Per 128-row tile and step (512 threads, all phases by all warps, CTA barriers between them):
+//   P1  one lane issues tcgen05.mma.kind::tf32  xp = x Wn  (A = x panels, B = Wn panels, D in TMEM);
+//       meanwhile the 2H attention-logit columns s_i|s_j are computed with exact fp32 FMAs from the staged x rows
+//       (softmax gradients are zero-sum per destination: TF32 rounding there is amplified)
+//   P2  tcgen05.ld: xp -> shared memory, row-major (the edge phase gathers rows x_j by source slot)
+//   P3  segment softmax, a thread per (destination, head), PyG form exp(a-max)/(sum+1e-16)
+//   P4  aggregation sum alpha * e_ij (.) x_j into registers, a thread per (destination, 12-channel item)
+//   P5  registers -> agg operand panels (they alias the xp tile, dead by now)
+//   P6  tcgen05.mma  pre = agg Wscale
+//   P7  epilogue: + bias, CELU -> m operand panels
+//   P8  tcgen05.mma  gi = m W_ih^T, gh = h W_hh^T
+//   P9  gate epilogue (thread = row = TMEM lane): r, z, n, h' = (1-z) n + z h, x' = act(h' + x): written IN PLACE into the
+//       x / h operand panels — the next step's P1 reads them there.
+// In training ("save" mode) the tensors MessageStackFn.backward consumes (xpe, agg, alpha, m, r|z|n, gh_n, x', h') leave
+// as contiguous tile-sized copies out of shared memory; in eval mode (virtual screening) only the outputs do.
+//
+// Shared-memory operand image: tc_common.cuh's SWIZZLE_128B K-major panels (32 features x 128 rows = 16 KB).  C = 36
+// features need 32 + 8: the 8-feature tails of x, h, m share ONE panel (k-slices at byte 0 / 32 / 64 of its rows), and
+// likewise the tails of Wn, W_ih, W_hh — a K-slice of a panel is addressed by its start byte, so independent operands
+// can live side by side in one panel.  One CTA per SM: 192 KB of panels + 16 KB of records.
+#include <cuda.h>
+#include <math_constants.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace glam {
+
+using namespace tc;
+
+int g_math_mode_get();
+
+namespace {
+
+constexpr int kMpThreads = 512;
+constexpr int kMpWarps = kMpThreads / 32;
+constexpr int kMpM = 128;                    // rows per tile = UMMA M
+constexpr int kMpMaxEdges = 768;             // in-edges per tile (molecular tiles: ~2.2 per atom)
+constexpr int kMpMaxDe = 4;                  // bond types
+constexpr int kMpPanel = kMpM * kPanelRowBytes;      // 16 KB
+
+enum : int { kFlagNodes = 1, kFlagEdges = 2, kFlagCross = 4, kFlagEdgeAttr = 8 };
+
+// ------------------------------------------------------------------------------------------------ graph tiles
+// Greedy packing of consecutive whole graphs into tiles of <= max_nodes nodes and <= max_edges in-edges.  One CTA; thread c
+// packs the graphs [c*G, (c+1)*G) (tiles never span chunks: one partly filled tile per chunk), counts, block scan, emit.
+template <typename Emit>
+__device__ __forceinline__ int pack_chunk(const int32_t* __restrict__ gptr, const int32_t* __restrict__ rowptr, int64_t g0, int64_t g1,
+                                          int max_nodes, int max_edges, int& flags, Emit emit) {
+    int count = 0;
+    int64_t g = g0;
+    while (g < g1) {
+        const int n0 = gptr[g], e0 = rowptr[n0];
+        int64_t k = g;
+        int n1 = n0, e1 = e0;
+        while (k < g1) {
+            const int nn = gptr[k + 1], ee = rowptr[nn];
+            if (nn - n0 > max_nodes || ee - e0 > max_edges) break;
+            n1 = nn; e1 = ee; ++k;
+        }
+        if (k == g) {                                  // a single graph over the caps: its own (flagged) tile
+            n1 = gptr[g + 1]; e1 = rowptr[n1];
+            flags |= (n1 - n0 > max_nodes ? kFlagNodes : 0) | (e1 - e0 > max_edges ? kFlagEdges : 0);
+            k = g + 1;
+        }
+        if (n1 > n0) { emit(count, make_int4(n0, n1, e0, e1)); ++count; }
+        g = k;
+    }
+    return count;
+}
+
+__global__ void __launch_bounds__(1024)
+graph_tiles_kernel(const int32_t* __restrict__ gptr, int64_t B, const int32_t* __restrict__ rowptr, int G, int max_nodes, int max_edges,
+                   int4* __restrict__ tiles, int32_t* __restrict__ meta) {
+    __shared__ int warp_tot[32];
+    __shared__ int flags_s;
+    const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
+    if (c == 0) flags_s = 0;
+    __syncthreads();
+    const int64_t g0 = min((int64_t)c * G, B), g1 = min(B, g0 + G);
+    int flags = 0;
+    const int mine = pack_chunk(gptr, rowptr, g0, g1, max_nodes, max_edges, flags, [](int, int4) {});
+    int incl = mine;                                   // block-wide exclusive scan of the counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    if (flags) atomicOr(&flags_s, flags);
+    __syncthreads();
+    if (warp == 0) {
+        int v = warp_tot[lane], s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += u;
+        }
+        warp_tot[lane] = s - v;                        // exclusive prefix of the warp totals
+        if (lane == 31) meta[0] = s;
+    }
+    __syncthreads();
+    const int base = warp_tot[warp] + incl - mine;
+    int dummy = 0;
+    pack_chunk(gptr, rowptr, g0, g1, max_nodes, max_edges, dummy, [&](int i, int4 t) { tiles[base + i] = t; });
+    if (c == 0 && flags_s) atomicOr(&meta[1], flags_s);       // meta is zeroed by the caller; every builder ORs its findings in
+}
+
+// a warp per tile: every source of the tile's in-edges must be one of its own rows (block-diagonal batch)
+__global__ void __launch_bounds__(256)
+graph_tiles_check_kernel(const int4* __restrict__ tiles, const int32_t* __restrict__ src, int32_t* __restrict__ meta, int64_t max_tiles) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (t >= max_tiles || t >= meta[0]) return;
+    const int4 td = tiles[t];
+    int bad = 0;
+    for (int e = td.z + lane; e < td.w; e += 32) {
+        const int j = src[e];
+        bad |= (j < td.x || j >= td.y) ? 1 : 0;
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&meta[1], kFlagCross);
+}
+
+// bond type of every (dst-ordered) edge: index of the 1 in an exactly one-hot edge_attr row (src_1gp/dataset.py:82)
+__global__ void __launch_bounds__(256)
+edge_types_kernel(const float* __restrict__ ea, int64_t E, int De, uint8_t* __restrict__ etype, int32_t* __restrict__ meta) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int ty = -1, ok = 1;
+    for (int d = 0; d < De; ++d) {
+        const float v = ea[e * De + d];
+        if (v == 1.f) { ok &= (ty < 0); ty = d; }
+        else ok &= (v == 0.f);
+    }
+    ok &= (ty >= 0) && (ty < kMpMaxDe);
+    etype[e] = ok ? (uint8_t)ty : (uint8_t)0;
+    if (!ok) atomicOr(&meta[1], kFlagEdgeAttr);
+}
+
+// ------------------------------------------------------------------------------------------------ the fused kernel
+struct MpParams {
+    const float* x0; const float* h0;
+    const float* w_ext; int ldw;
+    const float* w_edge; const float* att_edge;
+    const float* w_scale; const float* bias;
+    const float* w_ih; const float* w_hh; const float* b_ih; const float* b_hh;
+    const int4* tiles; const int32_t* meta;
+    const int32_t* rowptr; const int32_t* src; const uint8_t* etype;
+    int64_t N, E;
+    int De, steps, act, res, conv_only, keep_all;
+    float slope, act_param;
+    float* x_out; float* h_out;
+    float* sX; float* sHH; float* sXPE; float* sAGG; float* sALPHA; float* sM; float* sRZN; float* sGH;
+};
+
+__device__ __forceinline__ float4 lds128(const void* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void sts128(void* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, fast_sigmoid(2.f * x), -1.f); }
+
+// byte offset of the 16-byte chunk q (4 features) of row r inside a 128-byte-row SWIZZLE_128B panel
+__device__ __forceinline__ uint32_t pan_off(int r, int q) { return (uint32_t)(r * kPanelRowBytes + (((q & 7) ^ (r & 7)) << 4)); }
+
+template <int CQ, int H>
+struct MpGeom {
+    static constexpr int C = 4 * CQ, HC = H * C, NQ = HC / 4;
+    static constexpr int LD = (HC + 2 * H + 3) / 4 * 4;                 // row pitch of the xp tile = ldxp of the unfused path
+    static constexpr int KP = (C + 7) / 8 * 8, KSX = KP / 8;            // K of the x/h/m products (k-steps of 8)
+    static constexpr int TQ = CQ > 8 ? CQ - 8 : 0;                      // 16-byte chunks in the shared tail panel (<= 2)
+    static constexpr int NXP = (HC + 15) / 16 * 16;                     // N of the node projection
+    static constexpr int KAGG = (HC + 7) / 8 * 8, KSA = KAGG / 8, NPA = (KAGG + 31) / 32;
+    static constexpr int NS = (C + 15) / 16 * 16;                       // N of the scale projection
+    static constexpr int NG = (3 * C + 15) / 16 * 16;                   // N of each GRU product
+    static constexpr int WROWS = NXP > NG ? NXP : NG;
+    static constexpr int TM_XP = 0, TM_PRE = NXP, TM_GI = NXP + NS, TM_GH = NXP + NS + NG, TM_COLS = NXP + NS + 2 * NG;
+    static constexpr int CPI = CQ % 3 == 0 ? 3 : (CQ % 2 == 0 ? 2 : 1);  // chunks per aggregation item
+    static constexpr int NI = NQ / CPI, TPH = CQ / CPI;                 // items per row / per head
+    static constexpr int TASKS = kMpM * NI, ROUNDS = (TASKS + kMpThreads - 1) / kMpThreads;
+    static constexpr int REGB0 = NPA * kMpPanel, REGB1 = kMpM * LD * 4, REGB2 = kMpM * 3 * C * 4;
+    static constexpr int REGB = ((REGB0 > REGB1 ? (REGB0 > REGB2 ? REGB0 : REGB2) : (REGB1 > REGB2 ? REGB1 : REGB2)) + 1023) / 1024 * 1024;
+    static constexpr int OFF_XM = 0, OFF_HM = kMpPanel, OFF_AT = 2 * kMpPanel, OFF_REG = 3 * kMpPanel;
+    static constexpr int OFF_WN = OFF_REG + REGB, OFF_WI = OFF_WN + NXP * 128, OFF_WH = OFF_WI + NG * 128, OFF_WT = OFF_WH + NG * 128;
+    static constexpr int OFF_WS = OFF_WT + WROWS * 128, OFF_MISC = OFF_WS + NPA * NS * 128;
+    // misc (floats / ints)
+    static constexpr int M_RP = 0, M_REC = 132, M_ALPHA = M_REC + kMpMaxEdges, M_WE = M_ALPHA + kMpMaxEdges * H;
+    static constexpr int M_AE = M_WE + kMpMaxDe * HC, M_U = M_AE + kMpMaxDe * H, M_BIAS = M_U + C * 2 * H, M_GB = M_BIAS + C;
+    static constexpr int M_END = (M_GB + 4 * C + 3) / 4 * 4;
+    static constexpr int SMEM = OFF_MISC + M_END * 4 + 1024;            // + alignment slack
+    static_assert(KSX <= 5 && TQ <= 2, "tail panel holds 8 features per operand");
+    static_assert(TM_COLS <= 512, "TMEM columns");
+    static_assert(NPA <= 4 && NXP <= 256 && NG <= 256, "shape");
+    static_assert((NS * 128) % 1024 == 0 && (NXP * 128) % 1024 == 0 && (NG * 128) % 1024 == 0, "panel alignment");
+};
+
+// copy nd rows x CQ chunks out of an operand image (main panel + tail-panel slot) to contiguous global rows
+template <int CQ>
+__device__ __forceinline__ void copy_out_panels(const uint8_t* mainp, const uint8_t* tailp, int slot, float* __restrict__ dst, int nd) {
+    for (int i = threadIdx.x; i < nd * CQ; i += kMpThreads) {
+        const int r = i / CQ, q = i - r * CQ;
+        const float4 v = q < 8 ? lds128(mainp + pan_off(r, q)) : lds128(tailp + pan_off(r, 2 * slot + q - 8));
+        reinterpret_cast<float4*>(dst)[i] = v;
+    }
+}
+__device__ __forceinline__ void copy_out_flat(const void* srcp, float* __restrict__ dst, int n4) {
+    for (int i = threadIdx.x; i < n4; i += kMpThreads) reinterpret_cast<float4*>(dst)[i] = lds128(reinterpret_cast<const uint8_t*>(srcp) + 16 * i);
+}
+
+template <int CQ, int H, bool SAVE>
+__global__ void __launch_bounds__(kMpThreads, 1)
+mp_fused_kernel(const MpParams p) {
+    using G = MpGeom<CQ, H>;
+    constexpr int C = G::C, HC = G::HC, NQ = G::NQ, LD = G::LD;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* XM = sm + G::OFF_XM;  uint8_t* HM = sm + G::OFF_HM;  uint8_t* AT = sm + G::OFF_AT;  uint8_t* REG = sm + G::OFF_REG;
+    uint8_t* WN = sm + G::OFF_WN;  uint8_t* WI = sm + G::OFF_WI;  uint8_t* WH = sm + G::OFF_WH;  uint8_t* WT = sm + G::OFF_WT;
+    uint8_t* WS = sm + G::OFF_WS;
+    float* misc = reinterpret_cast<float*>(sm + G::OFF_MISC);
+    int* rp = reinterpret_cast<int*>(misc + G::M_RP);
+    int* rec = reinterpret_cast<int*>(misc + G::M_REC);
+    float* alpha_s = misc + G::M_ALPHA;
+    float* We = misc + G::M_WE;  float* Ae = misc + G::M_AE;  float* U = misc + G::M_U;
+    float* bias_s = misc + G::M_BIAS;  float* gb = misc + G::M_GB;
+    float* xp = reinterpret_cast<float*>(REG);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = p.meta[0], flags = p.meta[1];
+
+    if (flags != 0) {
+        // the batch violates a precondition of this path (graph > 128 nodes / too many edges / edge crossing graphs / edge_attr
+        // not one-hot): poison the outputs so the failure cannot go unnoticed (the host checks meta[1] outside graph capture)
+        const float nanv = CUDART_NAN_F;
+        const int64_t nc = p.N * C, i0 = blockIdx.x * (int64_t)kMpThreads + tid, di = (int64_t)gridDim.x * kMpThreads;
+        if (p.x_out) for (int64_t i = i0; i < (p.keep_all ? (int64_t)p.steps * nc : nc); i += di) p.x_out[i] = nanv;
+        if (p.h_out) for (int64_t i = i0; i < nc; i += di) p.h_out[i] = nanv;
+        if (p.sX) for (int64_t i = i0; i < (int64_t)(p.steps + 1) * nc; i += di) p.sX[i] = nanv;
+        if (p.sHH) for (int64_t i = i0; i < (int64_t)(p.steps + 1) * nc; i += di) p.sHH[i] = nanv;
+        return;
+    }
+    if ((int)blockIdx.x >= ntiles) return;
+
+    // ---------------------------------------------------------------- one-time setup: barriers, TMEM, weights
+    if (tid == 0) { mbar_init(&mma_bar, 1); fence_mbar_init(); }
+    if (warp == 1) tmem_alloc(&tmem_slot, 512u);
+    {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < (G::OFF_MISC - G::OFF_WN) / 16; i += kMpThreads) sts128(WN + 16 * i, z);    // all weight panels
+        for (int i = tid; i < kMpPanel / 16; i += kMpThreads) sts128(AT + 16 * i, z);                      // tails incl. K padding
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    {
+        // Wn: B[n][k] = w_ext[k][n], n < HC
+        for (int i = tid; i < HC * CQ; i += kMpThreads) {
+            const int n = i / CQ, q = i - n * CQ;
+            const float* w = p.w_ext + (size_t)(4 * q) * p.ldw + n;
+            const float4 v = make_float4(__ldg(w), __ldg(w + p.ldw), __ldg(w + 2 * p.ldw), __ldg(w + 3 * p.ldw));
+            sts128(q < 8 ? WN + pan_off(n, q) : WT + pan_off(n, q - 8), v);
+        }
+        // Wscale: B[n][k] = w_scale[k][n], n < C, k < HC
+        for (int i = tid; i < C * NQ; i += kMpThreads) {
+            const int n = i / NQ, q = i - n * NQ;
+            const float* w = p.w_scale + (size_t)(4 * q) * C + n;
+            const float4 v = make_float4(__ldg(w), __ldg(w + C), __ldg(w + 2 * C), __ldg(w + 3 * C));
+            sts128(WS + (q >> 3) * (G::NS * 128) + pan_off(n, q), v);
+        }
+        if (!p.conv_only) {
+            // GRU weights are [3C][C] row-major = B[n][k] as stored
+            for (int i = tid; i < 3 * C * CQ; i += kMpThreads) {
+                const int n = i / CQ, q = i - n * CQ;
+                const float4 vi = __ldg(reinterpret_cast<const float4*>(p.w_ih + (size_t)n * C) + q);
+                const float4 vh = __ldg(reinterpret_cast<const float4*>(p.w_hh + (size_t)n * C) + q);
+                sts128(q < 8 ? WI + pan_off(n, q) : WT + pan_off(n, 2 + q - 8), vi);
+                sts128(q < 8 ? WH + pan_off(n, q) : WT + pan_off(n, 4 + q - 8), vh);
+            }
+            for (int i = tid; i < 4 * C; i += kMpThreads) {
+                const int c = i >> 2, g = i & 3;
+                gb[i] = g == 0 ? p.b_ih[c] + p.b_hh[c] : g == 1 ? p.b_ih[C + c] + p.b_hh[C + c] : g == 2 ? p.b_ih[2 * C + c] : p.b_hh[2 * C + c];
+            }
+        }
+        for (int i = tid; i < p.De * HC; i += kMpThreads) We[i] = p.w_edge[i];
+        for (int i = tid; i < p.De * H; i += kMpThreads) Ae[i] = p.att_edge[i];
+        for (int i = tid; i < C * 2 * H; i += kMpThreads) { const int c = i / (2 * H), k = i - c * 2 * H; U[i] = p.w_ext[(size_t)c * p.ldw + HC + k]; }
+        for (int i = tid; i < C; i += kMpThreads) bias_s[i] = p.bias[i];
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    const uint32_t xm_a = smem_u32(XM), hm_a = smem_u32(HM), at_a = smem_u32(AT), reg_a = smem_u32(REG);
+    const uint32_t wn_a = smem_u32(WN), wi_a = smem_u32(WI), wh_a = smem_u32(WH), wt_a = smem_u32(WT), ws_a = smem_u32(WS);
+    const int q4 = warp & 3, cg = warp >> 2;                     // TMEM lane quarter of this warp / its column group
+    const int row = q4 * 32 + lane;                              // the tile row this thread owns in the epilogues
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    uint32_t ph = 0;
+    const int64_t NC = p.N * C;
+
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int4 td = p.tiles[t];
+        const int n0 = td.x, nd = td.y - td.x, e0 = td.z, ne = td.w - td.z;
+        // ------------------------------------------------------------ tile load: x (and h) rows -> operand panels; index words
+        for (int i = tid; i < kMpM * CQ; i += kMpThreads) {
+            const int r = i / CQ, q = i - r * CQ;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f), hv = v;
+            if (r < nd) {
+                v = __ldg(reinterpret_cast<const float4*>(p.x0 + (size_t)(n0 + r) * C) + q);
+                if (p.h0) hv = __ldg(reinterpret_cast<const float4*>(p.h0 + (size_t)(n0 + r) * C) + q);
+                if (SAVE && !p.conv_only) {
+                    reinterpret_cast<float4*>(p.sX + (size_t)(n0 + r) * C)[q] = v;
+                    reinterpret_cast<float4*>(p.sHH + (size_t)(n0 + r) * C)[q] = p.h0 ? hv : v;
+                }
+            }
+            sts128(q < 8 ? XM + pan_off(r, q) : AT + pan_off(r, q - 8), v);
+            if (p.h0) sts128(q < 8 ? HM + pan_off(r, q) : AT + pan_off(r, 2 + q - 8), hv);
+        }
+        for (int i = tid; i <= kMpM; i += kMpThreads) rp[i] = i <= nd ? p.rowptr[n0 + i] - e0 : ne;
+        for (int e = tid; e < ne; e += kMpThreads) rec[e] = (p.src[e0 + e] - n0) | ((int)p.etype[e0 + e] << 8);
+        fence_proxy_async_smem();
+        __syncthreads();
+
+        for (int s = 0; s < p.steps; ++s) {
+            const bool h_is_x = (s == 0 && p.h0 == nullptr);     // first step: h = x (layer.py:253-254)
+            // -------------------------------------------------------- P1: xp = x Wn on the tensor core; exact logit columns
+            if (tid == 0) {
+                tc_fence_after_sync();
+                const uint32_t idesc = make_idesc_tf32(kMpM, G::NXP, 0, 0);
+#pragma unroll
+                for (int ks = 0; ks < G::KSX; ++ks) {
+                    const uint32_t a = ks < 4 ? xm_a + ks * 32 : at_a;
+                    const uint32_t b = ks < 4 ? wn_a + ks * 32 : wt_a;
+                    mma_tf32_ss(tmem_base + G::TM_XP, make_smem_desc(a, 16, 1024), make_smem_desc(b, 16, 1024), idesc, ks > 0 ? 1u : 0u);
+                }
+                mma_commit(&mma_bar);
+            }
+            for (int task = tid; task < kMpM * 2 * H; task += kMpThreads) {
+                const int r = task & (kMpM - 1), k = task >> 7;
+                float acc = 0.f;
+#pragma unroll
+                for (int q = 0; q < CQ; ++q) {
+                    const float4 v = q < 8 ? lds128(XM + pan_off(r, q)) : lds128(AT + pan_off(r, q - 8));
+                    const float* u = U + (4 * q) * 2 * H + k;
+                    acc = fmaf(v.x, u[0], acc); acc = fmaf(v.y, u[2 * H], acc); acc = fmaf(v.z, u[4 * H], acc); acc = fmaf(v.w, u[6 * H], acc);
+                }
+                xp[r * LD + HC + k] = acc;
+            }
+            if (LD > HC + 2 * H)
+                for (int i = tid; i < kMpM * (LD - HC - 2 * H); i += kMpThreads) {
+                    const int r = i / (LD - HC - 2 * H), k = i - r * (LD - HC - 2 * H);
+                    xp[r * LD + HC + 2 * H + k] = 0.f;
+                }
+            mbar_wait_guarded(&mma_bar, ph); ph ^= 1u;
+            tc_fence_after_sync();
+            // -------------------------------------------------------- P2: TMEM -> xp tile (row-major, pitch LD)
+            for (int c0 = 32 * cg; c0 < 32 * cg + 32 && c0 < G::NXP; c0 += 16) {
+                float v[16];
+                tmem_ld16(lane_base + G::TM_XP + c0, v);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (c0 + 4 * i < HC) sts128(xp + row * LD + c0 + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+            }
+            tc_fence_before_sync();
+            __syncthreads();
+            if (SAVE) copy_out_flat(xp, p.sXPE + ((size_t)s * p.N + n0) * LD, nd * LD / 4);
+            // -------------------------------------------------------- P3: segment softmax per (destination, head)
+            for (int task = tid; task < nd * H; task += kMpThreads) {
+                const int d = task / H, h = task - d * H;
+                const int beg = rp[d], end = rp[d + 1];
+                const float si = xp[d * LD + HC + h];
+                float mx = -INFINITY, sum = 0.f;
+                for (int e = beg; e < end; ++e) {
+                    const int rc = rec[e];
+                    float l = si + Ae[(rc >> 8) * H + h] + xp[(rc & 0xff) * LD + HC + H + h];
+                    l = l > 0.f ? l : p.slope * l;
+                    alpha_s[e * H + h] = l;
+                    mx = fmaxf(mx, l);
+                }
+                for (int e = beg; e < end; ++e) {
+                    const float x = expf(alpha_s[e * H + h] - mx);
+                    alpha_s[e * H + h] = x;
+                    sum += x;
+                }
+                sum += 1e-16f;
+                for (int e = beg; e < end; ++e) alpha_s[e * H + h] = alpha_s[e * H + h] / sum;
+            }
+            __syncthreads();
+            if (SAVE) {
+                float* ad = p.sALPHA + ((size_t)s * p.E + e0) * H;
+                for (int i = tid; i < ne * H; i += kMpThreads) ad[i] = alpha_s[i];
+            }
+            // -------------------------------------------------------- P4: aggregate into registers
+            float4 acc[G::ROUNDS][G::CPI];
+#pragma unroll
+            for (int rd = 0; rd < G::ROUNDS; ++rd) {
+#pragma unroll
+                for (int k = 0; k < G::CPI; ++k) acc[rd][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int task = tid + rd * kMpThreads;
+                if (task < G::TASKS) {
+                    const int d = task / G::NI, g = task - d * G::NI;
+                    const int h = g / G::TPH, q0 = g * G::CPI;
+                    const int beg = rp[d], end = rp[d + 1];
+                    for (int e = beg; e < end; ++e) {
+                        const int rc = rec[e];
+                        const float c = alpha_s[e * H + h];
+                        const float4* xj = reinterpret_cast<const float4*>(xp + (rc & 0xff) * LD) + q0;
+                        const float4* w = reinterpret_cast<const float4*>(We + (rc >> 8) * HC) + q0;
+#pragma unroll
+                        for (int k = 0; k < G::CPI; ++k) {
+                            const float4 a = xj[k], b = w[k];
+                            acc[rd][k].x = fmaf(c, a.x * b.x, acc[rd][k].x); acc[rd][k].y = fmaf(c, a.y * b.y, acc[rd][k].y);
+                            acc[rd][k].z = fmaf(c, a.z * b.z, acc[rd][k].z); acc[rd][k].w = fmaf(c, a.w * b.w, acc[rd][k].w);
+                        }
+                    }
+                }
+            }
+            __syncthreads();                                     // every read of the xp tile is done: its bytes become the agg panels
+            // -------------------------------------------------------- P5: registers -> agg operand panels
+#pragma unroll
+            for (int rd = 0; rd < G::ROUNDS; ++rd) {
+                const int task = tid + rd * kMpThreads;
+                if (task < G::TASKS) {
+                    const int d = task / G::NI, g = task - d * G::NI, q0 = g * G::CPI;
+#pragma unroll
+                    for (int k = 0; k < G::CPI; ++k) {
+                        const int q = q0 + k;
+                        sts128(REG + (q >> 3) * kMpPanel + pan_off(d, q), acc[rd][k]);
+                    }
+                }
+            }
+            if (G::KAGG > HC)                                    // K padding of the scale product
+                for (int i = tid; i < kMpM * (G::KAGG - HC) / 4; i += kMpThreads) {
+                    const int r = i / ((G::KAGG - HC) / 4), q = NQ + i - r * ((G::KAGG - HC) / 4);
+                    sts128(REG + (q >> 3) * kMpPanel + pan_off(r, q), make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+            fence_proxy_async_smem();
+            __syncthreads();
+            // -------------------------------------------------------- P6: pre = agg Wscale
+            if (tid == 0) {
+                tc_fence_after_sync();
+                const uint32_t idesc = make_idesc_tf32(kMpM, G::NS, 0, 0);
+#pragma unroll
+                for (int ks = 0; ks < G::KSA; ++ks) {
+                    const uint32_t pan = ks >> 2, within = (ks & 3) * 32;
+                    mma_tf32_ss(tmem_base + G::TM_PRE, make_smem_desc(reg_a + pan * kMpPanel + within, 16, 1024),
+                                make_smem_desc(ws_a + pan * (G::NS * 128) + within, 16, 1024), idesc, ks > 0 ? 1u : 0u);
+                }
+                mma_commit(&mma_bar);
+            }
+            if (SAVE) {
+                float* ag = p.sAGG + ((size_t)s * p.N + n0) * HC;
+                for (int i = tid; i < nd * NQ; i += kMpThreads) {
+                    const int r = i / NQ, q = i - r * NQ;
+                    reinterpret_cast<float4*>(ag)[i] = lds128(REG + (q >> 3) * kMpPanel + pan_off(r, q));
+                }
+            }
+            mbar_wait_guarded(&mma_bar, ph); ph ^= 1u;
+            tc_fence_after_sync();
+            __syncthreads();                                     // agg copy-out done before m overwrites panel 0
+            // -------------------------------------------------------- P7: epilogue: + bias, CELU -> m operand panels (or the conv output)
+            float* ostage = reinterpret_cast<float*>(REG + 2 * kMpPanel);        // conv-only: row-major [128][C] output staging
+            if (16 * cg < C) {
+                float v[16];
+                tmem_ld16(lane_base + G::TM_PRE + 16 * cg, v);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int cq = 4 * cg + i;
+                    if (cq < CQ) {
+                        const float4 b = lds128(bias_s + 4 * cq);
+                        float4 m4 = make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w);
+                        if (p.conv_only) {
+                            sts128(ostage + row * C + 4 * cq, m4);
+                        } else {
+                            m4.x = celu1(m4.x); m4.y = celu1(m4.y); m4.z = celu1(m4.z); m4.w = celu1(m4.w);
+                            sts128(cq < 8 ? REG + pan_off(row, cq) : AT + pan_off(row, 4 + cq - 8), m4);
+                        }
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (p.conv_only) {
+                copy_out_flat(ostage, p.x_out + (size_t)n0 * C, nd * CQ);
+                __syncthreads();
+                continue;
+            }
+            // -------------------------------------------------------- P8: gi = m W_ih^T, gh = h W_hh^T
+            if (tid == 0) {
+                tc_fence_after_sync();
+                const uint32_t idesc = make_idesc_tf32(kMpM, G::NG, 0, 0);
+#pragma unroll
+                for (int ks = 0; ks < G::KSX; ++ks) {
+                    const uint32_t a = ks < 4 ? reg_a + ks * 32 : at_a + 64;
+                    const uint32_t b = ks < 4 ? wi_a + ks * 32 : wt_a + 32;
+                    mma_tf32_ss(tmem_base + G::TM_GI, make_smem_desc(a, 16, 1024), make_smem_desc(b, 16, 1024), idesc, ks > 0 ? 1u : 0u);
+                }
+#pragma unroll
+                for (int ks = 0; ks < G::KSX; ++ks) {
+                    const uint32_t a = ks < 4 ? (h_is_x ? xm_a : hm_a) + ks * 32 : at_a + (h_is_x ? 0 : 32);
+                    const uint32_t b = ks < 4 ? wh_a + ks * 32 : wt_a + 64;
+                    mma_tf32_ss(tmem_base + G::TM_GH, make_smem_desc(a, 16, 1024), make_smem_desc(b, 16, 1024), idesc, ks > 0 ? 1u : 0u);
+                }
+                mma_commit(&mma_bar);
+            }
+            if (SAVE) copy_out_panels<CQ>(REG, AT, 2, p.sM + ((size_t)s * p.N + n0) * C, nd);
+            mbar_wait_guarded(&mma_bar, ph); ph ^= 1u;
+            tc_fence_after_sync();
+            if (SAVE) __syncthreads();                           // m copy-out done before the r|z|n staging overwrites the region
+            // -------------------------------------------------------- P9: gates; h' and x' in place
+            float* rstage = reinterpret_cast<float*>(REG);       // save mode: r|z|n rows, pitch 3C
+            float4 ghn[(CQ + 3) / 4];
+#pragma unroll
+            for (int jj = 0; jj < (CQ + 3) / 4; ++jj) {
+                const int j = cg + 4 * jj;
+                ghn[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < CQ) {                                    // warp-uniform
+                    float v[24];
+                    const uint32_t gi = lane_base + G::TM_GI + 4 * j, gh = lane_base + G::TM_GH + 4 * j;
+                    tmem_ld4x6(gi, gi + C, gi + 2 * C, gh, gh + C, gh + 2 * C, v);
+                    const uint8_t* hsrc = h_is_x ? (j < 8 ? XM + pan_off(row, j) : AT + pan_off(row, j - 8))
+                                                 : (j < 8 ? HM + pan_off(row, j) : AT + pan_off(row, 2 + j - 8));
+                    uint8_t* xdst = j < 8 ? XM + pan_off(row, j) : AT + pan_off(row, j - 8);
+                    uint8_t* hdst = j < 8 ? HM + pan_off(row, j) : AT + pan_off(row, 2 + j - 8);
+                    const float4 hv = lds128(hsrc);
+                    const float4 xv = p.res ? lds128(xdst) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 r, z, nn, gn, hw, xo;
+#define MP_GATE(k, i)                                                                          \
+    {                                                                                          \
+        const float4 b = lds128(gb + 4 * (4 * j + i));                                         \
+        gn.k = v[20 + i] + b.w;                                                                \
+        r.k = fast_sigmoid(v[i] + v[12 + i] + b.x);                                            \
+        z.k = fast_sigmoid(v[4 + i] + v[16 + i] + b.y);                                        \
+        nn.k = fast_tanh((v[8 + i] + b.z) + r.k * gn.k);                                       \
+        hw.k = (1.f - z.k) * nn.k + z.k * hv.k;                                                \
+        xo.k = act_fwd(hw.k + xv.k, p.act, p.act_param);                                       \
+    }
+                    MP_GATE(x, 0) MP_GATE(y, 1) MP_GATE(z, 2) MP_GATE(w, 3)
+#undef MP_GATE
+                    sts128(hdst, hw);
+                    sts128(xdst, xo);
+                    if (SAVE) {
+                        sts128(rstage + row * 3 * C + 4 * j, r);
+                        sts128(rstage + row * 3 * C + C + 4 * j, z);
+                        sts128(rstage + row * 3 * C + 2 * C + 4 * j, nn);
+                        ghn[jj] = gn;
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            fence_proxy_async_smem();
+            __syncthreads();
+            // -------------------------------------------------------- outputs of the step
+            if (SAVE) {
+                copy_out_panels<CQ>(XM, AT, 0, p.sX + (size_t)(s + 1) * NC + (size_t)n0 * C, nd);
+                copy_out_panels<CQ>(HM, AT, 1, p.sHH + (size_t)(s + 1) * NC + (size_t)n0 * C, nd);
+                copy_out_flat(rstage, p.sRZN + ((size_t)s * p.N + n0) * 3 * C, nd * 3 * CQ);
+                __syncthreads();
+                float* gstage = reinterpret_cast<float*>(REG);   // gh_n rows, pitch C
+#pragma unroll
+                for (int jj = 0; jj < (CQ + 3) / 4; ++jj) {
+                    const int j = cg + 4 * jj;
+                    if (j < CQ) sts128(gstage + row * C + 4 * j, ghn[jj]);
+                }
+                __syncthreads();
+                copy_out_flat(gstage, p.sGH + ((size_t)s * p.N + n0) * C, nd * CQ);
+                __syncthreads();                                 // before the next step's P1 writes the logit columns into the region
+            } else {
+                const bool last = s == p.steps - 1;
+                if (p.keep_all || last)
+                    copy_out_panels<CQ>(XM, AT, 0, p.x_out + (p.keep_all ? (size_t)s * NC : (size_t)0) + (size_t)n0 * C, nd);
+                if (last && p.h_out) copy_out_panels<CQ>(HM, AT, 1, p.h_out + (size_t)n0 * C, nd);
+            }
+        }
+        __syncthreads();                                         // all reads of the tile (copy-outs) done before the next tile load
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
+bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+template <int CQ, int H>
+int mp_launch(const MpParams& p, bool save, cudaStream_t stream) {
+    using G = MpGeom<CQ, H>;
+    auto go = [&](auto kernel) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        if (e != cudaSuccess) { set_error("glam_message_stack_fwd: cudaFuncSetAttribute(%d bytes): %s", G::SMEM, cudaGetErrorString(e)); return (int)e; }
+        kernel<<<kNumSMs, kMpThreads, G::SMEM, stream>>>(p);
+        return 0;
+    };
+    return save ? go(mp_fused_kernel<CQ, H, true>) : go(mp_fused_kernel<CQ, H, false>);
+}
+
+}  // namespace
+}  // namespace glam
+
+using namespace glam;
+
+extern "C" int glam_graph_tile_caps(int* max_nodes, int* max_edges) {
+    if (max_nodes) *max_nodes = kMpM;
+    if (max_edges) *max_edges = kMpMaxEdges;
+    return 0;
+}
+
+extern "C" int glam_build_graph_tiles(const int32_t* graph_ptr, int64_t num_graphs, const int32_t* dst_rowptr, const int32_t* dst_src,
+                                      int64_t num_nodes, int64_t num_edges, int32_t* tiles, int32_t* meta, void* stream_) {
+    GLAM_REQUIRE(num_graphs >= 0 && num_nodes >= 0 && num_edges >= 0, "glam_build_graph_tiles: bad sizes");
+    GLAM_REQUIRE(graph_ptr && dst_rowptr && tiles && meta, "glam_build_graph_tiles: null pointer");
+    GLAM_REQUIRE(al16(tiles), "glam_build_graph_tiles: tiles must be 16-byte aligned");
+    GLAM_REQUIRE(num_graphs < ((int64_t)1 << 30), "glam_build_graph_tiles: too many graphs");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int G = (int)((num_graphs + 1023) / 1024 > 0 ? (num_graphs + 1023) / 1024 : 1);
+    graph_tiles_kernel<<<1, 1024, 0, stream>>>(graph_ptr, num_graphs, dst_rowptr, G, kMpM, kMpMaxEdges, reinterpret_cast<int4*>(tiles), meta);
+    GLAM_CHECK_LAUNCH();
+    if (num_graphs > 0 && num_edges > 0 && dst_src) {
+        const int64_t warps = num_graphs;
+        graph_tiles_check_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const int4*>(tiles), dst_src, meta, num_graphs);
+        GLAM_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+extern "C" int glam_edge_types(const float* edge_attr_sorted, int64_t num_edges, int edge_dim, uint8_t* etype, int32_t* meta, void* stream_) {
+    GLAM_REQUIRE(num_edges >= 0 && edge_dim > 0, "glam_edge_types: bad sizes");
+    if (num_edges == 0) return 0;
+    GLAM_REQUIRE(edge_attr_sorted && etype && meta, "glam_edge_types: null pointer");
+    edge_types_kernel<<<(unsigned)((num_edges + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(edge_attr_sorted, num_edges, edge_dim, etype, meta);
+    GLAM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int glam_message_stack_supported(int channels, int heads, int edge_dim) {
+    if (g_math_mode_get() == 0) return 0;                        // exact-fp32 mode keeps the CUDA-core projections
+    if (heads != 3 || edge_dim < 1 || edge_dim > kMpMaxDe) return 0;
+    return (channels == 32 || channels == 36 || channels == 40) ? 1 : 0;
+}
+
+extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const float* w_ext, int64_t ldw, const float* w_edge,
+                                      const float* att_edge, const float* w_scale, const float* bias, const float* w_ih,
+                                      const float* w_hh, const float* b_ih, const float* b_hh, const int32_t* tiles,
+                                      const int32_t* tile_meta, const int32_t* dst_rowptr, const int32_t* dst_src,
+                                      const uint8_t* etype, int64_t num_nodes, int64_t num_edges, int channels, int heads,
+                                      int edge_dim, int steps, float negative_slope, int act, float act_param, int res,
+                                      int conv_only, int keep_all, float* x_out, float* h_out, float* save_x, float* save_h,
+                                      float* save_xpe, float* save_agg, float* save_alpha, float* save_m, float* save_rzn,
+                                      float* save_gh, void* stream_) {
+    GLAM_REQUIRE(glam_message_stack_supported(channels, heads, edge_dim),
+                 "glam_message_stack_fwd: unsupported (channels=%d heads=%d edge_dim=%d math mode %d); use the per-op calls", channels,
+                 heads, edge_dim, g_math_mode_get());
+    GLAM_REQUIRE(num_nodes >= 0 && num_edges >= 0 && steps >= 1, "glam_message_stack_fwd: bad sizes");
+    if (num_nodes == 0) return 0;
+    const bool save = save_xpe != nullptr;              // training: also write what MessageStackFn.backward / TripletConvFn.backward read
+    GLAM_REQUIRE(x0 && w_ext && w_edge && att_edge && w_scale && bias && tiles && tile_meta && dst_rowptr && (num_edges == 0 || (dst_src && etype)),
+                 "glam_message_stack_fwd: null pointer");
+    GLAM_REQUIRE(conv_only ? steps == 1 : (w_ih && w_hh && b_ih && b_hh), "glam_message_stack_fwd: GRU weights missing / conv-only takes one step");
+    GLAM_REQUIRE(save ? (save_agg && save_alpha && (conv_only ? x_out != nullptr : (save_x && save_h && save_m && save_rzn && save_gh)))
+                      : (x_out != nullptr),
+                 "glam_message_stack_fwd: output pointers missing");
+    const int HC = heads * channels, ld = (HC + 2 * heads + 3) / 4 * 4;
+    GLAM_REQUIRE(ldw == ld, "glam_message_stack_fwd: w_ext pitch %lld, expected %d", (long long)ldw, ld);
+    GLAM_REQUIRE(al16(x0) && al16(h0) && al16(w_ih) && al16(w_hh) && al16(x_out) && al16(h_out) && al16(save_x) && al16(save_h) &&
+                 al16(save_xpe) && al16(save_agg) && al16(save_m) && al16(save_rzn) && al16(save_gh) && al16(tiles),
+                 "glam_message_stack_fwd: pointers must be 16-byte aligned");
+    GLAM_REQUIRE(num_nodes < ((int64_t)1 << 31) && num_edges < ((int64_t)1 << 31), "glam_message_stack_fwd: too large");
+    MpParams p;
+    p.x0 = x0; p.h0 = h0; p.w_ext = w_ext; p.ldw = (int)ldw; p.w_edge = w_edge; p.att_edge = att_edge; p.w_scale = w_scale; p.bias = bias;
+    p.w_ih = w_ih; p.w_hh = w_hh; p.b_ih = b_ih; p.b_hh = b_hh; p.tiles = reinterpret_cast<const int4*>(tiles); p.meta = tile_meta;
+    p.rowptr = dst_rowptr; p.src = dst_src; p.etype = etype; p.N = num_nodes; p.E = num_edges; p.De = edge_dim; p.steps = steps;
+    p.act = act; p.res = res; p.conv_only = conv_only; p.keep_all = keep_all; p.slope = negative_slope; p.act_param = act_param;
+    p.x_out = x_out; p.h_out = h_out; p.sX = save_x; p.sHH = save_h; p.sXPE = save_xpe; p.sAGG = save_agg; p.sALPHA = save_alpha;
+    p.sM = save_m; p.sRZN = save_rzn; p.sGH = save_gh;
+    int rc = 0;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    switch (channels) {
+        case 32: rc = mp_launch<8, 3>(p, save, stream); break;
+        case 36: rc = mp_launch<9, 3>(p, save, stream); break;
+        default: rc = mp_launch<10, 3>(p, save, stream); break;
+    }
+    if (rc) return rc;
+    GLAM_CHECK_LAUNCH();
+    return 0;
+}

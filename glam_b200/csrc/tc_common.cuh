@@ -175,5 +175,45 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// six 4-column loads (addresses a0..a5) in flight behind ONE wait: the gate epilogue of the fused message kernel reads
+// r|z|n of both GRU products for a 4-channel chunk.  One asm block, so no consumer can be scheduled before the wait.
+__device__ __forceinline__ void tmem_ld4x6(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                                           float (&v)[24]) {
+    uint32_t r[24];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%24];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4, %5, %6, %7}, [%25];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8, %9, %10, %11}, [%26];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%12, %13, %14, %15}, [%27];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%16, %17, %18, %19}, [%28];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%20, %21, %22, %23}, [%29];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 24; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// mbarrier wait that traps instead of hanging the device when the expected arrival never comes (a lost tcgen05.commit
+// would otherwise spin until the watchdog): ~2^22 failed probes are far beyond any legitimate wait in these kernels.
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t it = 0;; ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (it > (1u << 22)) __trap();
+    }
+}
+
 }  // namespace tc
 }  // namespace glam

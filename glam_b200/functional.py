@@ -23,7 +23,10 @@ def _c(t):
 # allocator's stream-ordered reuse valid.  Works under CUDA-graph capture (fork/join become graph branches).
 # --------------------------------------------------------------------------------------------------
 _side_streams = {}
-OVERLAP_WGRAD = True
+# Off by default: measured gain was ~3 % (two tensor-core CTAs cannot share an SM's shared memory), and tensors
+# allocated on the main stream but consumed on the side stream would need record_stream()/a join before every free.
+# When enabled, every producer below joins before its operands go out of scope.
+OVERLAP_WGRAD = False
 
 
 class _Side:
@@ -110,6 +113,7 @@ def _gru_bwd(g_x_out, g_h_new, rzn, gh, h, m, x_out, w_ih, w_hh, act, act_param,
     else:
         g_m = ops.gemm(g_gi, w_ih)
     ops.gemm(g_gh, w_hh, epilogue=EPI_ACCUM, out=g_h_prev)
+    _join(g_m)                         # g_gi / g_gh die with this frame: the side-stream readers must be ordered before that
     return g_m, g_h_prev, g_id, g_w_ih, g_w_hh, g_b_ih, g_b_hh
 
 
@@ -121,10 +125,18 @@ class TripletConvFn(Function):
     None) returns the aggregate itself and the caller adds the bias."""
 
     @staticmethod
-    def forward(ctx, x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels, slope):
+    def forward(ctx, x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels, slope, fi):
         x, w_ext, w_edge, att_edge, w_scale, bias = map(_c, (x, w_ext, w_edge, att_edge, w_scale, bias))
         ops._need_cuda(x, w_ext)
-        xpe, agg, alpha, out = _conv_fwd(x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels, slope, EPI_NONE)
+        if fi is not None and w_scale is not None:
+            N, dev = x.shape[0], x.device
+            new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+            sv = dict(XPE=new(1, N, w_ext.shape[1]), AGG=new(1, N, heads * channels), ALPHA=new(1, ea.shape[0], heads))
+            out, _ = ops.message_stack_fwd(x, None, w_ext, w_edge, att_edge, w_scale, bias, None, None, None, None, g, fi, heads,
+                                           channels, 1, slope, ACT_NONE, 0.0, False, conv_only=True, save=sv)
+            xpe, agg, alpha, out = sv["XPE"][0], sv["AGG"][0], sv["ALPHA"][0], out[0]
+        else:
+            xpe, agg, alpha, out = _conv_fwd(x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels, slope, EPI_NONE)
         ctx.save_for_backward(x, w_ext, w_edge, att_edge, w_scale, xpe, agg, alpha, ea)
         ctx.g, ctx.cfg = g, (heads, channels, slope)
         return out
@@ -135,7 +147,7 @@ class TripletConvFn(Function):
         heads, channels, slope = ctx.cfg
         g_x, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias = _conv_bwd(
             _c(g_out), x, w_ext, w_edge, att_edge, w_scale, xpe, agg, alpha, ea, ctx.g, heads, channels, slope)
-        return g_x, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias, None, None, None, None, None
+        return g_x, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias, None, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------------------
@@ -165,15 +177,31 @@ class GRUUpdateFn(Function):
 # --------------------------------------------------------------------------------------------------
 # fused MessageBlock core: conv -> CELU -> GRU -> (+identity) -> act   (src_1gp/layer.py:259-266)
 # --------------------------------------------------------------------------------------------------
+def _stack_buffers(x0, S, H, C, ld, E):
+    """The stacked activations of `S` message steps that backward consumes (see MessageStackFn)."""
+    N, dev = x0.shape[0], x0.device
+    new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    return dict(X=new(S + 1, N, C), HH=new(S + 1, N, C), XPE=new(S, N, ld), AGG=new(S, N, H * C), ALPHA=new(S, E, H),
+                M=new(S, N, C), RZN=new(S, N, 3 * C), GH=new(S, N, C))
+
+
 class MessageBlockFn(Function):
     @staticmethod
     def forward(ctx, x, identity, h, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, ea, g,
-                heads, channels, slope, act, act_param):
+                heads, channels, slope, act, act_param, fi):
         (x, identity, h, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh) = map(
             _c, (x, identity, h, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh))
         ops._need_cuda(x, h)
-        xpe, agg, alpha, m = _conv_fwd(x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels, slope, EPI_CELU)
-        rzn, gh, h_new, x_out = _gru_fwd(m, h, identity, w_ih, w_hh, b_ih, b_hh, act, act_param)
+        if fi is not None and (identity is None or identity is x):
+            # one launch for the whole block (csrc/mp_fused.cu); the tensors backward reads come out as side outputs
+            sv = _stack_buffers(x, 1, heads, channels, w_ext.shape[1], ea.shape[0])
+            ops.message_stack_fwd(x, h, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, g, fi, heads, channels, 1,
+                                  slope, act, act_param, identity is not None, save=sv)
+            xpe, agg, alpha, m, rzn, gh, x_out, h_new = (sv["XPE"][0], sv["AGG"][0], sv["ALPHA"][0], sv["M"][0], sv["RZN"][0],
+                                                         sv["GH"][0], sv["X"][1], sv["HH"][1])
+        else:
+            xpe, agg, alpha, m = _conv_fwd(x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels, slope, EPI_CELU)
+            rzn, gh, h_new, x_out = _gru_fwd(m, h, identity, w_ih, w_hh, b_ih, b_hh, act, act_param)
         ctx.save_for_backward(x, h, w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, xpe, agg, alpha, m, rzn, gh, x_out, ea)
         ctx.g, ctx.cfg = g, (heads, channels, slope, act, act_param, identity is not None)
         ctx.set_materialize_grads(False)
@@ -188,7 +216,7 @@ class MessageBlockFn(Function):
         g_x, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias = _conv_bwd(
             g_pre, x, w_ext, w_edge, att_edge, w_scale, xpe, agg, alpha, ea, ctx.g, heads, channels, slope)
         return (g_x, g_id, g_h, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias, g_w_ih, g_w_hh, g_b_ih, g_b_hh,
-                None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -200,12 +228,24 @@ class MessageBlockFn(Function):
 class MessageStackFn(Function):
     @staticmethod
     def forward(ctx, x0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, ea, g,
-                heads, channels, slope, act, act_param, res, steps, p_drop):
+                heads, channels, slope, act, act_param, res, steps, p_drop, fi):
         (x0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh) = map(
             _c, (x0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh))
         ops._need_cuda(x0, w_ext)
         N, C = x0.shape
         S, H, HC, ld, E, dev = steps, heads, heads * channels, w_ext.shape[1], ea.shape[0], x0.device
+        if fi is not None and p_drop == 0.0:
+            # ONE launch for all steps (csrc/mp_fused.cu): x and h stay in shared memory from step to step; what backward
+            # reads leaves the SM as tile-sized contiguous copies
+            sv = _stack_buffers(x0, S, H, channels, ld, E)
+            ops.message_stack_fwd(x0, None, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, g, fi, H, channels, S,
+                                  slope, act, act_param, res, save=sv)
+            X, HH = sv["X"], sv["HH"]
+            ctx.save_for_backward(w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ea, X, HH, X, None, sv["XPE"], sv["AGG"],
+                                  sv["ALPHA"], sv["M"], sv["RZN"], sv["GH"])
+            ctx.g, ctx.cfg = g, (H, channels, slope, act, act_param, res, S, p_drop)
+            ctx.set_materialize_grads(False)
+            return tuple(X[s + 1] for s in range(S)) + (HH[S],)
         new = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype, device=dev)
         X, HH = new(S + 1, N, C), new(S + 1, N, C)               # block inputs / GRU states; [s+1] = outputs of step s
         X[0].copy_(x0)
@@ -279,7 +319,7 @@ class MessageStackFn(Function):
         g_att_edge, _ = ops.gemm_tn_ex(ea, G_LOGIT.sum(0) if S > 1 else G_LOGIT[0])
         g_w_edge = G_WE.sum(0) if S > 1 else G_WE[0]
         return (g_x0, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias, g_w_ih, g_w_hh, g_b_ih, g_b_hh,
-                None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None)
 
 
 # --------------------------------------------------------------------------------------------------

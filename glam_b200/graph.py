@@ -40,6 +40,31 @@ class GraphIndex:
         self._gcn = None
         self._nn_key = None
         self._nn = None
+        self._fused_key = None
+        self._fused = None
+
+    def fused_index(self, gptr: torch.Tensor, num_graphs: int, edge_attr: torch.Tensor):
+        """Index of the fused message kernel (csrc/mp_fused.cu) for this batch, or None when the batch does not meet its
+        preconditions (a graph with more rows / in-edges than a tile, an edge between graphs, edge_attr not one-hot).
+        Built once per batch.  The check reads one int back outside CUDA-graph capture; during capture the verdict of
+        the last eager batch of the same shape is assumed, and the kernel poisons its outputs with NaN if it is wrong."""
+        key = (gptr.data_ptr(), gptr._version, int(num_graphs), edge_attr.data_ptr(), edge_attr._version, tuple(edge_attr.shape))
+        if self._fused_key == key:
+            return self._fused
+        ea = self.sorted_edge_attr(edge_attr)
+        meta = torch.zeros(4, dtype=torch.int32, device=ea.device)
+        etype = ops.edge_types(ea, meta)
+        tiles = ops.build_graph_tiles(gptr, num_graphs, self, meta)
+        shape_key = (self.num_nodes, self.num_edges, int(num_graphs), ea.shape[1], ea.device)
+        if _capturing():
+            ok = _fused_ok.get(shape_key, False)
+        else:
+            ok = int(meta[1].item()) == 0
+            _fused_ok[shape_key] = ok
+        self._fused = FusedIndex(tiles, meta, etype, ea.shape[1]) if ok else None
+        self._fused_key = key
+        self._fused_refs = (gptr, edge_attr)
+        return self._fused
 
     def gcn_norm(self):
         """(dinv^2 [N], w_dst [E], w_src [E]) of PyG GCNConv's normalisation, computed once per batch."""
@@ -88,6 +113,14 @@ class GraphIndex:
         return self._edge_attr_sorted
 
 
+class FusedIndex:
+    """tiles int32 [B,4] {n0,n1,e0,e1}, meta int32 [4] (count, violation flags), etype uint8 [E] (dst order)."""
+
+    def __init__(self, tiles, meta, etype, edge_dim):
+        self.tiles, self.meta, self.etype, self.edge_dim = tiles, meta, etype, int(edge_dim)
+
+
+_fused_ok = {}                      # (N, E, B, De, device) -> verdict of the last host-side precondition check
 _graph_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
 _ptr_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
 

@@ -28,6 +28,28 @@ from . import graph as G
 from . import ops
 
 
+# The fused message kernel (csrc/mp_fused.cu) is used whenever its preconditions hold; False keeps the per-op kernels
+# (A/B timing, and the path tests compare it against).
+USE_FUSED_STACK = True
+
+
+def _fused_index(g, x, edge_attr, batch, num_graphs, heads, channels):
+    """FusedIndex of this batch for the fused message kernel, or None (unsupported shape / math mode, no `batch`, batch
+    violating the kernel's preconditions)."""
+    if not (USE_FUSED_STACK and batch is not None and x.is_cuda and edge_attr.dim() == 2):
+        return None
+    if not ops.message_stack_supported(channels, heads, edge_attr.shape[1]):
+        return None
+    if num_graphs is None and G._capturing():
+        return None
+    gptr, B = G.graph_ptr(batch, num_graphs)
+    return g.fused_index(gptr, B, edge_attr)
+
+
+def _wants_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def _ldxp(heads: int, channels: int) -> int:
     """Row pitch of the extended projection xp | s_i | s_j, padded to 16 bytes."""
     return (heads * channels + 2 * heads + 3) // 4 * 4
@@ -66,12 +88,20 @@ class TripletMessage(nn.Module):
         return Fn.TripletPrepFn.apply(self.weight_node, self.weight_edge, self.weight_triplet_att.view(H, 3 * C), C, H,
                                       self.edge_channels, _ldxp(H, C))
 
-    def forward(self, x, edge_index, edge_attr, size=None):
+    def forward(self, x, edge_index, edge_attr, size=None, batch=None, num_graphs=None):
+        """`batch` (optional, not in the reference signature): the PyG batch vector; with it the layer runs as one fused
+        kernel on graph-aligned tiles (projection -> edge phase -> scale projection, csrc/mp_fused.cu)."""
         g = G.graph_index(edge_index, x.shape[0])
         ea = g.sorted_edge_attr(edge_attr)
         w_ext, att_edge = self.derived()
+        fi = _fused_index(g, x, edge_attr, batch, num_graphs, self.heads, self.node_channels)
+        if fi is not None and not _wants_grad(x, *self.parameters()):
+            out, _ = ops.message_stack_fwd(x.contiguous(), None, w_ext, self.weight_edge, att_edge, self.weight_scale, self.bias,
+                                           None, None, None, None, g, fi, self.heads, self.node_channels, 1,
+                                           self.negative_slope, ops.ACT_NONE, 0.0, False, conv_only=True)
+            return out[0]
         return Fn.TripletConvFn.apply(x, w_ext, self.weight_edge, att_edge, self.weight_scale, self.bias, ea, g, self.heads,
-                                      self.node_channels, self.negative_slope)
+                                      self.node_channels, self.negative_slope, fi)
 
     def extra_repr(self):
         return f"{self.node_channels}, {self.node_channels}, heads={self.heads}"
@@ -104,7 +134,7 @@ class TripletMessageLight(nn.Module):
         g = G.graph_index(edge_index, x.shape[0])
         ea = g.sorted_edge_attr(edge_attr)
         w_ext, att_edge = self.derived()
-        agg = Fn.TripletConvFn.apply(x, w_ext, None, att_edge, None, None, ea, g, 1, self.node_channels, self.negative_slope)
+        agg = Fn.TripletConvFn.apply(x, w_ext, None, att_edge, None, None, ea, g, 1, self.node_channels, self.negative_slope, None)
         return agg + self.bias
 
     def extra_repr(self):
@@ -474,10 +504,11 @@ class MessageBlock(nn.Module):
         self.act = _build_act(act)
         self.res = res
 
-    def run_steps(self, x, edge_index, edge_attr, steps, batch=None):
+    def run_steps(self, x, edge_index, edge_attr, steps, batch=None, num_graphs=None, keep="all"):
         """`steps` applications of this block starting from h=None (the loop of src_1gp/model.py:60-62), returning
-        ([x_1 .. x_steps], h).  With the triplet layer, no norm and a fusable activation the whole loop is one
-        autograd node (functional.MessageStackFn); otherwise it is the plain loop over forward()."""
+        ([x_1 .. x_steps], h) — or ([x_steps], h) with keep="last".  With the triplet layer, no norm and a fusable
+        activation the whole loop is one autograd node (functional.MessageStackFn) and, when the batch meets the
+        preconditions of csrc/mp_fused.cu, ONE kernel launch; otherwise it is the plain loop over forward()."""
         inner = getattr(self.conv, "conv", None)
         fused = _fusable_act(self.act, self.training)
         drop = self.dropout
@@ -487,21 +518,30 @@ class MessageBlock(nn.Module):
         if not stackable:
             xs, h = [], None
             for _ in range(steps):
-                x, h = self.forward(x, edge_index, edge_attr, h=h, batch=batch)
+                x, h = self.forward(x, edge_index, edge_attr, h=h, batch=batch, num_graphs=num_graphs)
                 xs.append(x)
-            return xs, h
+            return (xs if keep == "all" else xs[-1:]), h
         p_drop = float(drop.p) if (isinstance(drop, nn.Dropout) and self.training) else 0.0
         g = G.graph_index(edge_index, x.shape[0])
         ea = g.sorted_edge_attr(edge_attr)
         w_ext, att_edge = inner.derived()
         gru = self.gru
+        fi = _fused_index(g, x, edge_attr, batch, num_graphs, inner.heads, inner.node_channels) if p_drop == 0.0 else None
+        if fi is not None and not _wants_grad(x, *self.parameters()):
+            # screening / evaluation: nothing is kept for backward, only the outputs leave the SM
+            x_out, h_out = ops.message_stack_fwd(
+                x.contiguous(), None, w_ext, inner.weight_edge, att_edge, inner.weight_scale, inner.bias,
+                gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, g, fi, inner.heads, inner.node_channels,
+                int(steps), inner.negative_slope, fused[0], fused[1], bool(self.res), keep_all=(keep == "all"))
+            return list(x_out.unbind(0)), h_out.unsqueeze(0)
         out = Fn.MessageStackFn.apply(
             x, w_ext, inner.weight_edge, att_edge, inner.weight_scale, inner.bias,
             gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, ea, g,
-            inner.heads, inner.node_channels, inner.negative_slope, fused[0], fused[1], bool(self.res), int(steps), p_drop)
-        return list(out[:steps]), out[steps].unsqueeze(0)
+            inner.heads, inner.node_channels, inner.negative_slope, fused[0], fused[1], bool(self.res), int(steps), p_drop, fi)
+        xs = list(out[:steps])
+        return (xs if keep == "all" else xs[-1:]), out[steps].unsqueeze(0)
 
-    def forward(self, x, edge_index, edge_attr, h=None, batch=None):
+    def forward(self, x, edge_index, edge_attr, h=None, batch=None, num_graphs=None):
         identity = x
         if h is None:
             h = x.unsqueeze(0)
@@ -519,10 +559,20 @@ class MessageBlock(nn.Module):
             g = G.graph_index(edge_index, x.shape[0])
             ea = g.sorted_edge_attr(edge_attr)
             w_ext, att_edge = inner.derived()
-            x, h_new = Fn.MessageBlockFn.apply(
-                x, ident, h[0], w_ext, inner.weight_edge, att_edge, inner.weight_scale, inner.bias,
-                gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, ea, g,
-                inner.heads, inner.node_channels, inner.negative_slope, act_code, act_param)
+            fi = None
+            if x is identity and gru.hidden_size == x.shape[1] == inner.node_channels:      # no norm / dropout in front of the conv
+                fi = _fused_index(g, x, edge_attr, batch, num_graphs, inner.heads, inner.node_channels)
+            if fi is not None and not _wants_grad(x, h, *self.parameters()):
+                x_o, h_o = ops.message_stack_fwd(
+                    x.contiguous(), h[0].contiguous(), w_ext, inner.weight_edge, att_edge, inner.weight_scale, inner.bias,
+                    gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, g, fi, inner.heads, inner.node_channels,
+                    1, inner.negative_slope, act_code, act_param, bool(self.res))
+                x, h_new = x_o[0], h_o
+            else:
+                x, h_new = Fn.MessageBlockFn.apply(
+                    x, ident, h[0], w_ext, inner.weight_edge, att_edge, inner.weight_scale, inner.bias,
+                    gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, ea, g,
+                    inner.heads, inner.node_channels, inner.negative_slope, act_code, act_param, fi)
         else:
             m = torch.celu(self.conv(x, edge_index, edge_attr))
             x, h_new = Fn.GRUUpdateFn.apply(m, h[0], ident, gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0,

@@ -63,7 +63,8 @@ class ArchitectureGP(nn.Module):
     def forward(self, data_mol):
         B = _num_graphs(data_mol)
         xm = self.mol_lin0(data_mol.x, batch=data_mol.batch)
-        xs, _ = self.mol_conv.run_steps(xm, data_mol.edge_index, data_mol.edge_attr, self.message_steps, batch=data_mol.batch)
+        xs, _ = self.mol_conv.run_steps(xm, data_mol.edge_index, data_mol.edge_attr, self.message_steps, batch=data_mol.batch,
+                                        num_graphs=B, keep="last")
         outm = self.mol_readout(xs[-1], data_mol.batch, num_graphs=B)
         return self.lin_out1(self.mol_flat(outm))
 
@@ -97,8 +98,8 @@ class _PairArchitecture(nn.Module):
         xa = ta.lin0(da.x, batch=da.batch)
         xb = tb.lin0(db.x, batch=db.batch)
         # the towers only meet in the pools, so each runs all its steps first (same values as the lock-step loop)
-        xas, _ = ta.conv.run_steps(xa, da.edge_index, da.edge_attr, self.message_steps, batch=da.batch)
-        xbs, _ = tb.conv.run_steps(xb, db.edge_index, db.edge_attr, self.message_steps, batch=db.batch)
+        xas, _ = ta.conv.run_steps(xa, da.edge_index, da.edge_attr, self.message_steps, batch=da.batch, num_graphs=B)
+        xbs, _ = tb.conv.run_steps(xb, db.edge_index, db.edge_attr, self.message_steps, batch=db.batch, num_graphs=B)
         fusion = [dot_and_global_pool2(a, b, da.batch, db.batch, num_graphs=B) for a, b in zip(xas, xbs)]
         oa = ta.flat(ta.readout(xas[-1], da.batch, num_graphs=B))
         ob = tb.flat(tb.readout(xbs[-1], db.batch, num_graphs=B))

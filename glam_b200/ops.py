@@ -253,6 +253,60 @@ def triplet_prep_bwd(weight_node, weight_edge, att, g_w_ext, g_att_edge, g_w_edg
     return g_wn, g_we, g_att
 
 
+# ------------------------------------------------------------------------------------------------ fused message stack
+def graph_tile_caps():
+    import ctypes as C
+    a, b = C.c_int(0), C.c_int(0)
+    _lib.check(_lib.load().glam_graph_tile_caps(C.addressof(a), C.addressof(b)), "glam_graph_tile_caps")
+    return a.value, b.value
+
+
+def build_graph_tiles(gptr: torch.Tensor, num_graphs: int, g, meta: torch.Tensor) -> torch.Tensor:
+    """Graph-aligned tiles {n0, n1, e0, e1} (int32 [B,4]; meta[0] of them are valid) for the fused message kernel."""
+    _need_cuda(gptr)
+    tiles = torch.empty((max(int(num_graphs), 1), 4), dtype=torch.int32, device=gptr.device)
+    _call("glam_build_graph_tiles", _p(gptr), int(num_graphs), _p(g.dst_rowptr), _p(g.dst_src), g.num_nodes, g.num_edges,
+          _p(tiles), _p(meta), _stream(gptr))
+    return tiles
+
+
+def edge_types(ea_sorted: torch.Tensor, meta: torch.Tensor) -> torch.Tensor:
+    E, De = ea_sorted.shape
+    et = torch.empty((max(E, 1),), dtype=torch.uint8, device=ea_sorted.device)
+    _call("glam_edge_types", _p(ea_sorted), E, De, _p(et), _p(meta), _stream(ea_sorted))
+    return et
+
+
+def message_stack_supported(channels: int, heads: int, edge_dim: int) -> bool:
+    return bool(_lib.load().glam_message_stack_supported(int(channels), int(heads), int(edge_dim)))
+
+
+def message_stack_fwd(x0, h0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, g, fi, heads, channels, steps,
+                      slope, act, act_param, res, conv_only=False, keep_all=False, save=None):
+    """The whole message stack in one launch (csrc/mp_fused.cu).  Eval (save=None): returns (x_out [S|1,N,C], h_out [N,C]|None).
+    Training: `save` = dict of preallocated stacked tensors X, HH, XPE, AGG, ALPHA, M, RZN, GH (conv_only: XPE, AGG, ALPHA) that
+    the kernel fills; returns (x_out|None, None)."""
+    _need_cuda(x0, w_ext)
+    N, C = x0.shape
+    E, dev = g.num_edges, x0.device
+    assert x0.is_contiguous() and (h0 is None or h0.is_contiguous()) and w_ext.is_contiguous()
+    x_out = h_out = None
+    if save is None or conv_only:
+        x_out = torch.empty(((steps if keep_all else 1), N, C), dtype=torch.float32, device=dev)
+    if save is None and not conv_only:
+        h_out = torch.empty((N, C), dtype=torch.float32, device=dev)
+    sv = save or {}
+    for k, t in sv.items():
+        assert t.is_contiguous(), k
+    _call("glam_message_stack_fwd", _p(x0), _p(h0), _p(w_ext), w_ext.stride(0), _p(w_edge), _p(att_edge), _p(w_scale), _p(bias),
+          _p(w_ih), _p(w_hh), _p(b_ih), _p(b_hh), _p(fi.tiles), _p(fi.meta), _p(g.dst_rowptr), _p(g.dst_src), _p(fi.etype),
+          N, E, channels, heads, fi.edge_dim, steps, float(slope), act, float(act_param), 1 if res else 0,
+          1 if conv_only else 0, 1 if keep_all else 0, _p(x_out), _p(h_out), _p(sv.get("X")), _p(sv.get("HH")), _p(sv.get("XPE")),
+          _p(sv.get("AGG")), _p(sv.get("ALPHA")), _p(sv.get("M")), _p(sv.get("RZN")), _p(sv.get("GH")), _stream(x0),
+          label=f"[N={N},S={steps},{'save' if save is not None else 'eval'}{',conv' if conv_only else ''}]")
+    return x_out, h_out
+
+
 # ------------------------------------------------------------------------------------------------ cells
 def gru_gates_fwd(gi, gh, h, identity, act, act_param, h_new=None, x_out=None):
     N, C = h.shape

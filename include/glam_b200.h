@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLAM_B200_ABI_VERSION 4
+#define GLAM_B200_ABI_VERSION 5
 #define GLAM_MAX_HEADS 4
 
 int glam_abi_version(void);
@@ -270,6 +270,45 @@ int glam_gcn_norm(const int32_t* dst_rowptr, const int32_t* dst_src, const int32
  * --------------------------------------------------------------------------------------------- */
 int glam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr,
                    float* state, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (8) The message stack as ONE kernel (csrc/mp_fused.cu): `steps` applications of the weight-tied MessageBlock —
+ * TripletMessage (src_1gp/layer.py:36-61) -> CELU -> GRU (:260-263) -> +identity -> act (:265-266), the loop of
+ * src_1gp/model.py:53-54 — on graph-aligned tiles.  A PyG batch is block-diagonal (src_1gp/dataset.py:75-87 +
+ * Batch.from_data_list), so a tile of whole graphs (<= 128 nodes) is closed under message passing: projections run on
+ * the tcgen05 tensor cores out of shared memory, the edge softmax / aggregation reads the projected rows there, and x, h
+ * stay resident from step to step.  xp [N,HC+2H] and agg [N,HC] never reach HBM (unless saved for backward).
+ *
+ * glam_build_graph_tiles — greedy packing of consecutive whole graphs (graph_ptr, B+1 entries) into tiles of
+ *   <= max_nodes rows and <= max_edges in-edges (glam_graph_tile_caps).  tiles: 4*B int32 {n0, n1, e0, e1} per tile, 16-byte
+ *   aligned; meta: int32[4], ZEROED by the caller: meta[0] = tile count, meta[1] = OR of precondition violations
+ *   (1 a graph has more rows than a tile, 2 more in-edges than a tile, 4 an edge crosses tiles i.e. graphs,
+ *   8 an edge_attr row is not one-hot).  glam_edge_types — bond type per dst-ordered edge (index of the 1 in the
+ *   one-hot row, src_1gp/dataset.py:82), ORs 8 into meta[1] otherwise.
+ * glam_message_stack_fwd — w_ext / att_edge are glam_triplet_prep_fwd's derived weights.  h0 NULL: h = x on the first
+ *   step (layer.py:253-254).  conv_only = 1: x_out = TripletMessage(x0) alone (steps must be 1, GRU arguments NULL).
+ *   Eval (save_xpe == NULL): x_out [keep_all ? steps : 1][N][C] = the step outputs (last only unless keep_all), h_out [N][C]
+ *   (may be NULL) = the final GRU state.  Training (save_xpe != NULL): what the backward kernels consume is written as
+ *   stacked tensors — save_x, save_h [steps+1][N][C] (block inputs / states; entry 0 = x0 / h0), save_xpe [steps][N][ld],
+ *   save_agg [steps][N][HC], save_alpha [steps][E][H], save_m [steps][N][C], save_rzn [steps][N][3C], save_gh [steps][N][C]
+ *   (conv_only: save_xpe, save_agg, save_alpha and x_out only).  If meta[1] != 0 the outputs are filled with NaN: callers
+ *   check meta[1] on the host when they can (outside CUDA-graph capture) and fall back to the per-op entry points.
+ *   glam_message_stack_supported: tf32 math mode, heads == 3, channels in {32,36,40}, edge_dim <= 4.
+ * --------------------------------------------------------------------------------------------- */
+int glam_graph_tile_caps(int* max_nodes, int* max_edges);
+int glam_build_graph_tiles(const int32_t* graph_ptr, int64_t num_graphs, const int32_t* dst_rowptr, const int32_t* dst_src,
+                           int64_t num_nodes, int64_t num_edges, int32_t* tiles, int32_t* meta, void* stream);
+int glam_edge_types(const float* edge_attr_sorted, int64_t num_edges, int edge_dim, uint8_t* etype, int32_t* meta, void* stream);
+int glam_message_stack_supported(int channels, int heads, int edge_dim);
+int glam_message_stack_fwd(const float* x0, const float* h0, const float* w_ext, int64_t ldw, const float* w_edge,
+                           const float* att_edge, const float* w_scale, const float* bias, const float* w_ih,
+                           const float* w_hh, const float* b_ih, const float* b_hh, const int32_t* tiles,
+                           const int32_t* tile_meta, const int32_t* dst_rowptr, const int32_t* dst_src,
+                           const uint8_t* etype, int64_t num_nodes, int64_t num_edges, int channels, int heads,
+                           int edge_dim, int steps, float negative_slope, int act, float act_param, int res,
+                           int conv_only, int keep_all, float* x_out, float* h_out, float* save_x, float* save_h,
+                           float* save_xpe, float* save_agg, float* save_alpha, float* save_m, float* save_rzn,
+                           float* save_gh, void* stream);
 
 #ifdef __cplusplus
 }
