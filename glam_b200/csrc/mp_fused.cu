@@ -32,6 +32,7 @@
 // can live side by side in one panel.  One CTA per SM: 192 KB of panels + 16 KB of records.
 #include <cuda.h>
 #include <math_constants.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -43,8 +44,6 @@ int g_math_mode_get();
 
 namespace {
 
-constexpr int kMpThreads = 512;
-constexpr int kMpWarps = kMpThreads / 32;
 constexpr int kMpM = 128;                    // rows per tile = UMMA M
 constexpr int kMpMaxEdges = 768;             // in-edges per tile (molecular tiles: ~2.2 per atom)
 constexpr int kMpMaxDe = 4;                  // bond types
@@ -166,13 +165,27 @@ struct MpParams {
 
 __device__ __forceinline__ float4 lds128(const void* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void sts128(void* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, fast_sigmoid(2.f * x), -1.f); }
+// gate non-linearities straight on the SFU: ex2.approx / rcp.approx (relative error ~2^-22 each), 4 instructions per
+// sigmoid — the gate epilogue was 31 % of the kernel's instructions with the library forms
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * x)), -1.f); }
+// CELU(alpha = 1) with exp from ex2.approx: absolute error <= 2e-7 (common.cuh's celu1 costs ~30 instructions per element)
+__device__ __forceinline__ float celu_fast(float x) { return x > 0.f ? x : ex2_approx(1.4426950408889634f * x) - 1.f; }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 
 // byte offset of the 16-byte chunk q (4 features) of row r inside a 128-byte-row SWIZZLE_128B panel
 __device__ __forceinline__ uint32_t pan_off(int r, int q) { return (uint32_t)(r * kPanelRowBytes + (((q & 7) ^ (r & 7)) << 4)); }
 
-template <int CQ, int H>
+template <int CQ, int H, int NT>
 struct MpGeom {
     static constexpr int C = 4 * CQ, HC = H * C, NQ = HC / 4;
     static constexpr int LD = (HC + 2 * H + 3) / 4 * 4;                 // row pitch of the xp tile = ldxp of the unfused path
@@ -184,51 +197,55 @@ struct MpGeom {
     static constexpr int NG = (3 * C + 15) / 16 * 16;                   // N of each GRU product
     static constexpr int WROWS = NXP > NG ? NXP : NG;
     static constexpr int TM_XP = 0, TM_PRE = NXP, TM_GI = NXP + NS, TM_GH = NXP + NS + NG, TM_COLS = NXP + NS + 2 * NG;
-    static constexpr int CPI = CQ % 3 == 0 ? 3 : (CQ % 2 == 0 ? 2 : 1);  // chunks per aggregation item
-    static constexpr int NI = NQ / CPI, TPH = CQ / CPI;                 // items per row / per head
-    static constexpr int TASKS = kMpM * NI, ROUNDS = (TASKS + kMpThreads - 1) / kMpThreads;
+    static constexpr int WQ = NT / 128;                                 // warps per TMEM lane quarter = threads per tile row
+    static constexpr int CPT = (NQ + WQ - 1) / WQ;                      // aggregation: 16-byte chunks of a row per thread
+    static constexpr int JPW = (CQ + WQ - 1) / WQ;                      // epilogues: 4-channel chunks per warp
     static constexpr int REGB0 = NPA * kMpPanel, REGB1 = kMpM * LD * 4, REGB2 = kMpM * 3 * C * 4;
     static constexpr int REGB = ((REGB0 > REGB1 ? (REGB0 > REGB2 ? REGB0 : REGB2) : (REGB1 > REGB2 ? REGB1 : REGB2)) + 1023) / 1024 * 1024;
     static constexpr int OFF_XM = 0, OFF_HM = kMpPanel, OFF_AT = 2 * kMpPanel, OFF_REG = 3 * kMpPanel;
     static constexpr int OFF_WN = OFF_REG + REGB, OFF_WI = OFF_WN + NXP * 128, OFF_WH = OFF_WI + NG * 128, OFF_WT = OFF_WH + NG * 128;
     static constexpr int OFF_WS = OFF_WT + WROWS * 128, OFF_MISC = OFF_WS + NPA * NS * 128;
     // misc (floats / ints)
-    static constexpr int M_RP = 0, M_REC = 132, M_ALPHA = M_REC + kMpMaxEdges, M_WE = M_ALPHA + kMpMaxEdges * H;
+    static constexpr int M_BAR = 0, M_RP = 4, M_REC = 136, M_ALPHA = M_REC + kMpMaxEdges, M_WE = M_ALPHA + kMpMaxEdges * H;
     static constexpr int M_AE = M_WE + kMpMaxDe * HC, M_U = M_AE + kMpMaxDe * H, M_BIAS = M_U + C * 2 * H, M_GB = M_BIAS + C;
     static constexpr int M_END = (M_GB + 4 * C + 3) / 4 * 4;
-    static constexpr int SMEM = OFF_MISC + M_END * 4 + 1024;            // + alignment slack
+    static constexpr int SMEM = OFF_MISC + M_END * 4;
+    static_assert(NT == 512 || NT == 1024, "threads");
     static_assert(KSX <= 5 && TQ <= 2, "tail panel holds 8 features per operand");
     static_assert(TM_COLS <= 512, "TMEM columns");
     static_assert(NPA <= 4 && NXP <= 256 && NG <= 256, "shape");
+    static_assert(CPT <= CQ, "an aggregation thread spans at most two heads");
     static_assert((NS * 128) % 1024 == 0 && (NXP * 128) % 1024 == 0 && (NG * 128) % 1024 == 0, "panel alignment");
 };
 
 // copy nd rows x CQ chunks out of an operand image (main panel + tail-panel slot) to contiguous global rows
-template <int CQ>
+template <int CQ, int NT>
 __device__ __forceinline__ void copy_out_panels(const uint8_t* mainp, const uint8_t* tailp, int slot, float* __restrict__ dst, int nd) {
-    for (int i = threadIdx.x; i < nd * CQ; i += kMpThreads) {
+    for (int i = threadIdx.x; i < nd * CQ; i += NT) {
         const int r = i / CQ, q = i - r * CQ;
         const float4 v = q < 8 ? lds128(mainp + pan_off(r, q)) : lds128(tailp + pan_off(r, 2 * slot + q - 8));
         reinterpret_cast<float4*>(dst)[i] = v;
     }
 }
+template <int NT>
 __device__ __forceinline__ void copy_out_flat(const void* srcp, float* __restrict__ dst, int n4) {
-    for (int i = threadIdx.x; i < n4; i += kMpThreads) reinterpret_cast<float4*>(dst)[i] = lds128(reinterpret_cast<const uint8_t*>(srcp) + 16 * i);
+    for (int i = threadIdx.x; i < n4; i += NT) reinterpret_cast<float4*>(dst)[i] = lds128(reinterpret_cast<const uint8_t*>(srcp) + 16 * i);
 }
 
-template <int CQ, int H, bool SAVE>
-__global__ void __launch_bounds__(kMpThreads, 1)
+template <int CQ, int H, int NT, bool SAVE>
+__global__ void __launch_bounds__(NT, 1)
 mp_fused_kernel(const MpParams p) {
-    using G = MpGeom<CQ, H>;
-    constexpr int C = G::C, HC = G::HC, NQ = G::NQ, LD = G::LD;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t mma_bar;
-    __shared__ uint32_t tmem_slot;
-    uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    using G = MpGeom<CQ, H, NT>;
+    constexpr int C = G::C, HC = G::HC, NQ = G::NQ, LD = G::LD, WQ = G::WQ;
+    // the dynamic shared memory IS the panel arena: every pointer below is derived from this array by plain pointer
+    // arithmetic, so the compiler keeps the shared state space (LDS/STS, 32-bit addresses) instead of generic LD/ST
+    extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t* XM = sm + G::OFF_XM;  uint8_t* HM = sm + G::OFF_HM;  uint8_t* AT = sm + G::OFF_AT;  uint8_t* REG = sm + G::OFF_REG;
     uint8_t* WN = sm + G::OFF_WN;  uint8_t* WI = sm + G::OFF_WI;  uint8_t* WH = sm + G::OFF_WH;  uint8_t* WT = sm + G::OFF_WT;
     uint8_t* WS = sm + G::OFF_WS;
     float* misc = reinterpret_cast<float*>(sm + G::OFF_MISC);
+    uint64_t* mma_bar = reinterpret_cast<uint64_t*>(misc + G::M_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + G::M_BAR + 2);
     int* rp = reinterpret_cast<int*>(misc + G::M_RP);
     int* rec = reinterpret_cast<int*>(misc + G::M_REC);
     float* alpha_s = misc + G::M_ALPHA;
@@ -242,7 +259,7 @@ mp_fused_kernel(const MpParams p) {
         // the batch violates a precondition of this path (graph > 128 nodes / too many edges / edge crossing graphs / edge_attr
         // not one-hot): poison the outputs so the failure cannot go unnoticed (the host checks meta[1] outside graph capture)
         const float nanv = CUDART_NAN_F;
-        const int64_t nc = p.N * C, i0 = blockIdx.x * (int64_t)kMpThreads + tid, di = (int64_t)gridDim.x * kMpThreads;
+        const int64_t nc = p.N * C, i0 = blockIdx.x * (int64_t)NT + tid, di = (int64_t)gridDim.x * NT;
         if (p.x_out) for (int64_t i = i0; i < (p.keep_all ? (int64_t)p.steps * nc : nc); i += di) p.x_out[i] = nanv;
         if (p.h_out) for (int64_t i = i0; i < nc; i += di) p.h_out[i] = nanv;
         if (p.sX) for (int64_t i = i0; i < (int64_t)(p.steps + 1) * nc; i += di) p.sX[i] = nanv;
@@ -250,59 +267,64 @@ mp_fused_kernel(const MpParams p) {
         return;
     }
     if ((int)blockIdx.x >= ntiles) return;
+    if (smem_u32(sm) & 1023u) __trap();                        // SWIZZLE_128B panels need the 1024-byte alignment asked for above
 
     // ---------------------------------------------------------------- one-time setup: barriers, TMEM, weights
-    if (tid == 0) { mbar_init(&mma_bar, 1); fence_mbar_init(); }
-    if (warp == 1) tmem_alloc(&tmem_slot, 512u);
+    if (tid == 0) { mbar_init(mma_bar, 1); fence_mbar_init(); }
+    if (warp == 1) tmem_alloc(tmem_slot, 512u);
     {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = tid; i < (G::OFF_MISC - G::OFF_WN) / 16; i += kMpThreads) sts128(WN + 16 * i, z);    // all weight panels
-        for (int i = tid; i < kMpPanel / 16; i += kMpThreads) sts128(AT + 16 * i, z);                      // tails incl. K padding
+        for (int i = tid; i < (G::OFF_MISC - G::OFF_WN) / 16; i += NT) sts128(WN + 16 * i, z);    // all weight panels
+        for (int i = tid; i < kMpPanel / 16; i += NT) sts128(AT + 16 * i, z);                      // tails incl. K padding
     }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
     {
         // Wn: B[n][k] = w_ext[k][n], n < HC
-        for (int i = tid; i < HC * CQ; i += kMpThreads) {
-            const int n = i / CQ, q = i - n * CQ;
+        for (int i = tid; i < HC * CQ; i += NT) {
+            const int q = i / HC, n = i - q * HC;                // consecutive lanes: consecutive n (coalesced reads)
             const float* w = p.w_ext + (size_t)(4 * q) * p.ldw + n;
             const float4 v = make_float4(__ldg(w), __ldg(w + p.ldw), __ldg(w + 2 * p.ldw), __ldg(w + 3 * p.ldw));
             sts128(q < 8 ? WN + pan_off(n, q) : WT + pan_off(n, q - 8), v);
         }
         // Wscale: B[n][k] = w_scale[k][n], n < C, k < HC
-        for (int i = tid; i < C * NQ; i += kMpThreads) {
-            const int n = i / NQ, q = i - n * NQ;
+        for (int i = tid; i < C * NQ; i += NT) {
+            const int q = i / C, n = i - q * C;
             const float* w = p.w_scale + (size_t)(4 * q) * C + n;
             const float4 v = make_float4(__ldg(w), __ldg(w + C), __ldg(w + 2 * C), __ldg(w + 3 * C));
             sts128(WS + (q >> 3) * (G::NS * 128) + pan_off(n, q), v);
         }
         if (!p.conv_only) {
             // GRU weights are [3C][C] row-major = B[n][k] as stored
-            for (int i = tid; i < 3 * C * CQ; i += kMpThreads) {
+            for (int i = tid; i < 3 * C * CQ; i += NT) {
                 const int n = i / CQ, q = i - n * CQ;
                 const float4 vi = __ldg(reinterpret_cast<const float4*>(p.w_ih + (size_t)n * C) + q);
                 const float4 vh = __ldg(reinterpret_cast<const float4*>(p.w_hh + (size_t)n * C) + q);
                 sts128(q < 8 ? WI + pan_off(n, q) : WT + pan_off(n, 2 + q - 8), vi);
                 sts128(q < 8 ? WH + pan_off(n, q) : WT + pan_off(n, 4 + q - 8), vh);
             }
-            for (int i = tid; i < 4 * C; i += kMpThreads) {
+            for (int i = tid; i < 4 * C; i += NT) {
                 const int c = i >> 2, g = i & 3;
                 gb[i] = g == 0 ? p.b_ih[c] + p.b_hh[c] : g == 1 ? p.b_ih[C + c] + p.b_hh[C + c] : g == 2 ? p.b_ih[2 * C + c] : p.b_hh[2 * C + c];
             }
         }
-        for (int i = tid; i < p.De * HC; i += kMpThreads) We[i] = p.w_edge[i];
-        for (int i = tid; i < p.De * H; i += kMpThreads) Ae[i] = p.att_edge[i];
-        for (int i = tid; i < C * 2 * H; i += kMpThreads) { const int c = i / (2 * H), k = i - c * 2 * H; U[i] = p.w_ext[(size_t)c * p.ldw + HC + k]; }
-        for (int i = tid; i < C; i += kMpThreads) bias_s[i] = p.bias[i];
+        for (int i = tid; i < p.De * HC; i += NT) We[i] = p.w_edge[i];
+        for (int i = tid; i < p.De * H; i += NT) Ae[i] = p.att_edge[i];
+        // exact logit weights, packed per head as float4 {u_i[c], u_j[c], u_i[c+1], u_j[c+1]}: one broadcast load per two channels
+        for (int i = tid; i < C * 2 * H; i += NT) {
+            const int h = i / (2 * C), rem = i - h * 2 * C, c = rem >> 1, which = rem & 1;
+            U[i] = p.w_ext[(size_t)c * p.ldw + HC + which * H + h];
+        }
+        for (int i = tid; i < C; i += NT) bias_s[i] = p.bias[i];
     }
     fence_proxy_async_smem();
     __syncthreads();
 
     const uint32_t xm_a = smem_u32(XM), hm_a = smem_u32(HM), at_a = smem_u32(AT), reg_a = smem_u32(REG);
     const uint32_t wn_a = smem_u32(WN), wi_a = smem_u32(WI), wh_a = smem_u32(WH), wt_a = smem_u32(WT), ws_a = smem_u32(WS);
-    const int q4 = warp & 3, cg = warp >> 2;                     // TMEM lane quarter of this warp / its column group
+    const int q4 = warp & 3, cg = warp >> 2;                     // TMEM lane quarter of this warp / its index among the quarter's warps
     const int row = q4 * 32 + lane;                              // the tile row this thread owns in the epilogues
     const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
     uint32_t ph = 0;
@@ -312,7 +334,7 @@ mp_fused_kernel(const MpParams p) {
         const int4 td = p.tiles[t];
         const int n0 = td.x, nd = td.y - td.x, e0 = td.z, ne = td.w - td.z;
         // ------------------------------------------------------------ tile load: x (and h) rows -> operand panels; index words
-        for (int i = tid; i < kMpM * CQ; i += kMpThreads) {
+        for (int i = tid; i < kMpM * CQ; i += NT) {
             const int r = i / CQ, q = i - r * CQ;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f), hv = v;
             if (r < nd) {
@@ -326,10 +348,24 @@ mp_fused_kernel(const MpParams p) {
             sts128(q < 8 ? XM + pan_off(r, q) : AT + pan_off(r, q - 8), v);
             if (p.h0) sts128(q < 8 ? HM + pan_off(r, q) : AT + pan_off(r, 2 + q - 8), hv);
         }
-        for (int i = tid; i <= kMpM; i += kMpThreads) rp[i] = i <= nd ? p.rowptr[n0 + i] - e0 : ne;
-        for (int e = tid; e < ne; e += kMpThreads) rec[e] = (p.src[e0 + e] - n0) | ((int)p.etype[e0 + e] << 8);
+        for (int i = tid; i <= kMpM; i += NT) rp[i] = i <= nd ? p.rowptr[n0 + i] - e0 : ne;
+        for (int e = tid; e < ne; e += NT) rec[e] = (p.src[e0 + e] - n0) | ((int)p.etype[e0 + e] << 8);
         fence_proxy_async_smem();
         __syncthreads();
+        if (t + (int)gridDim.x < ntiles) {
+            // the next tile's rows and index words on their way into L2 while this tile computes
+            const int4 tn = p.tiles[t + gridDim.x];
+            const char* xb = reinterpret_cast<const char*>(p.x0 + (size_t)tn.x * C);
+            const int xbytes = (tn.y - tn.x) * C * 4;
+            for (int o = tid * 128; o < xbytes; o += NT * 128) prefetch_l2(xb + o);
+            if (p.h0) { const char* hb = reinterpret_cast<const char*>(p.h0 + (size_t)tn.x * C); for (int o = tid * 128; o < xbytes; o += NT * 128) prefetch_l2(hb + o); }
+            const char* sb = reinterpret_cast<const char*>(p.src + tn.z);
+            for (int o = tid * 128; o < (tn.w - tn.z) * 4; o += NT * 128) prefetch_l2(sb + o);
+            const char* rb = reinterpret_cast<const char*>(p.rowptr + tn.x);
+            for (int o = tid * 128; o < (tn.y - tn.x + 1) * 4; o += NT * 128) prefetch_l2(rb + o);
+            const char* eb = reinterpret_cast<const char*>(p.etype + tn.z);
+            for (int o = tid * 128; o < (tn.w - tn.z); o += NT * 128) prefetch_l2(eb + o);
+        }
 
         for (int s = 0; s < p.steps; ++s) {
             const bool h_is_x = (s == 0 && p.h0 == nullptr);     // first step: h = x (layer.py:253-254)
@@ -343,28 +379,32 @@ mp_fused_kernel(const MpParams p) {
                     const uint32_t b = ks < 4 ? wn_a + ks * 32 : wt_a;
                     mma_tf32_ss(tmem_base + G::TM_XP, make_smem_desc(a, 16, 1024), make_smem_desc(b, 16, 1024), idesc, ks > 0 ? 1u : 0u);
                 }
-                mma_commit(&mma_bar);
+                mma_commit(mma_bar);
             }
-            for (int task = tid; task < kMpM * 2 * H; task += kMpThreads) {
-                const int r = task & (kMpM - 1), k = task >> 7;
-                float acc = 0.f;
+            // a thread per (row, head): s_i and s_j of that head from one pass over the row
+            for (int task = tid; task < kMpM * H; task += NT) {
+                const int r = task & (kMpM - 1), h = task >> 7;
+                float ai = 0.f, aj = 0.f;
+                const float4* u = reinterpret_cast<const float4*>(U + h * 2 * C);
 #pragma unroll
                 for (int q = 0; q < CQ; ++q) {
                     const float4 v = q < 8 ? lds128(XM + pan_off(r, q)) : lds128(AT + pan_off(r, q - 8));
-                    const float* u = U + (4 * q) * 2 * H + k;
-                    acc = fmaf(v.x, u[0], acc); acc = fmaf(v.y, u[2 * H], acc); acc = fmaf(v.z, u[4 * H], acc); acc = fmaf(v.w, u[6 * H], acc);
+                    const float4 u0 = u[2 * q], u1 = u[2 * q + 1];
+                    ai = fmaf(v.x, u0.x, ai); aj = fmaf(v.x, u0.y, aj); ai = fmaf(v.y, u0.z, ai); aj = fmaf(v.y, u0.w, aj);
+                    ai = fmaf(v.z, u1.x, ai); aj = fmaf(v.z, u1.y, aj); ai = fmaf(v.w, u1.z, ai); aj = fmaf(v.w, u1.w, aj);
                 }
-                xp[r * LD + HC + k] = acc;
+                xp[r * LD + HC + h] = ai;
+                xp[r * LD + HC + H + h] = aj;
             }
             if (LD > HC + 2 * H)
-                for (int i = tid; i < kMpM * (LD - HC - 2 * H); i += kMpThreads) {
+                for (int i = tid; i < kMpM * (LD - HC - 2 * H); i += NT) {
                     const int r = i / (LD - HC - 2 * H), k = i - r * (LD - HC - 2 * H);
                     xp[r * LD + HC + 2 * H + k] = 0.f;
                 }
-            mbar_wait_guarded(&mma_bar, ph); ph ^= 1u;
+            mbar_wait_guarded(mma_bar, ph); ph ^= 1u;
             tc_fence_after_sync();
             // -------------------------------------------------------- P2: TMEM -> xp tile (row-major, pitch LD)
-            for (int c0 = 32 * cg; c0 < 32 * cg + 32 && c0 < G::NXP; c0 += 16) {
+            for (int c0 = 16 * cg; c0 < HC; c0 += 16 * WQ) {
                 float v[16];
                 tmem_ld16(lane_base + G::TM_XP + c0, v);
 #pragma unroll
@@ -373,12 +413,37 @@ mp_fused_kernel(const MpParams p) {
             }
             tc_fence_before_sync();
             __syncthreads();
-            if (SAVE) copy_out_flat(xp, p.sXPE + ((size_t)s * p.N + n0) * LD, nd * LD / 4);
+            if (SAVE) copy_out_flat<NT>(xp, p.sXPE + ((size_t)s * p.N + n0) * LD, nd * LD / 4);
             // -------------------------------------------------------- P3: segment softmax per (destination, head)
-            for (int task = tid; task < nd * H; task += kMpThreads) {
+            for (int task = tid; task < nd * H; task += NT) {
                 const int d = task / H, h = task - d * H;
-                const int beg = rp[d], end = rp[d + 1];
+                const int beg = rp[d], end = rp[d + 1], deg = end - beg;
                 const float si = xp[d * LD + HC + h];
+                if (deg <= 4) {
+                    // molecular graphs: valence-bounded in-degree — registers only, no shared-memory round trips
+                    float l[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        l[k] = -INFINITY;
+                        if (k < deg) {
+                            const int rc = rec[beg + k];
+                            const float v = si + Ae[(rc >> 8) * H + h] + xp[(rc & 0xff) * LD + HC + H + h];
+                            l[k] = v > 0.f ? v : p.slope * v;
+                        }
+                    }
+                    const float mx = fmaxf(fmaxf(l[0], l[1]), fmaxf(l[2], l[3]));
+                    float sum = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {                // same summation order as the loop below
+                        l[k] = k < deg ? expf(l[k] - mx) : 0.f;
+                        if (k < deg) sum += l[k];
+                    }
+                    sum += 1e-16f;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < deg) alpha_s[(beg + k) * H + h] = l[k] / sum;
+                    continue;
+                }
                 float mx = -INFINITY, sum = 0.f;
                 for (int e = beg; e < end; ++e) {
                     const int rc = rec[e];
@@ -398,29 +463,33 @@ mp_fused_kernel(const MpParams p) {
             __syncthreads();
             if (SAVE) {
                 float* ad = p.sALPHA + ((size_t)s * p.E + e0) * H;
-                for (int i = tid; i < ne * H; i += kMpThreads) ad[i] = alpha_s[i];
+                for (int i = tid; i < ne * H; i += NT) ad[i] = alpha_s[i];
             }
-            // -------------------------------------------------------- P4: aggregate into registers
-            float4 acc[G::ROUNDS][G::CPI];
+            // -------------------------------------------------------- P4: aggregate into registers: WQ threads per destination
+            // row, each owning CPT consecutive 16-byte chunks of it (at most two heads)
+            float4 acc[G::CPT];
+            const int ad_ = tid / WQ, ak = tid - ad_ * WQ, aq0 = ak * G::CPT;
+            {
 #pragma unroll
-            for (int rd = 0; rd < G::ROUNDS; ++rd) {
+                for (int i = 0; i < G::CPT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int h0 = min(H - 1, aq0 / CQ), h1 = min(H - 1, h0 + 1);
+                const int ib = (h0 + 1) * CQ - aq0;              // chunks i < ib belong to head h0, the rest to h1
+                const int beg = rp[ad_], end = rp[ad_ + 1];
+                int rc_n = 0; float c0_n = 0.f, c1_n = 0.f;
+                if (beg < end) { rc_n = rec[beg]; c0_n = alpha_s[beg * H + h0]; c1_n = alpha_s[beg * H + h1]; }
+                for (int e = beg; e < end; ++e) {
+                    const int rc = rc_n;
+                    const float c0 = c0_n, c1 = c1_n;
+                    if (e + 1 < end) { rc_n = rec[e + 1]; c0_n = alpha_s[(e + 1) * H + h0]; c1_n = alpha_s[(e + 1) * H + h1]; }
+                    const float4* xj = reinterpret_cast<const float4*>(xp + (rc & 0xff) * LD) + aq0;
+                    const float4* w = reinterpret_cast<const float4*>(We + (rc >> 8) * HC) + aq0;
 #pragma unroll
-                for (int k = 0; k < G::CPI; ++k) acc[rd][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int task = tid + rd * kMpThreads;
-                if (task < G::TASKS) {
-                    const int d = task / G::NI, g = task - d * G::NI;
-                    const int h = g / G::TPH, q0 = g * G::CPI;
-                    const int beg = rp[d], end = rp[d + 1];
-                    for (int e = beg; e < end; ++e) {
-                        const int rc = rec[e];
-                        const float c = alpha_s[e * H + h];
-                        const float4* xj = reinterpret_cast<const float4*>(xp + (rc & 0xff) * LD) + q0;
-                        const float4* w = reinterpret_cast<const float4*>(We + (rc >> 8) * HC) + q0;
-#pragma unroll
-                        for (int k = 0; k < G::CPI; ++k) {
-                            const float4 a = xj[k], b = w[k];
-                            acc[rd][k].x = fmaf(c, a.x * b.x, acc[rd][k].x); acc[rd][k].y = fmaf(c, a.y * b.y, acc[rd][k].y);
-                            acc[rd][k].z = fmaf(c, a.z * b.z, acc[rd][k].z); acc[rd][k].w = fmaf(c, a.w * b.w, acc[rd][k].w);
+                    for (int i = 0; i < G::CPT; ++i) {
+                        if (aq0 + i < NQ) {
+                            const float4 a = xj[i], b = w[i];
+                            const float c = i < ib ? c0 : c1;
+                            acc[i].x = fmaf(c, a.x * b.x, acc[i].x); acc[i].y = fmaf(c, a.y * b.y, acc[i].y);
+                            acc[i].z = fmaf(c, a.z * b.z, acc[i].z); acc[i].w = fmaf(c, a.w * b.w, acc[i].w);
                         }
                     }
                 }
@@ -428,20 +497,14 @@ mp_fused_kernel(const MpParams p) {
             __syncthreads();                                     // every read of the xp tile is done: its bytes become the agg panels
             // -------------------------------------------------------- P5: registers -> agg operand panels
 #pragma unroll
-            for (int rd = 0; rd < G::ROUNDS; ++rd) {
-                const int task = tid + rd * kMpThreads;
-                if (task < G::TASKS) {
-                    const int d = task / G::NI, g = task - d * G::NI, q0 = g * G::CPI;
-#pragma unroll
-                    for (int k = 0; k < G::CPI; ++k) {
-                        const int q = q0 + k;
-                        sts128(REG + (q >> 3) * kMpPanel + pan_off(d, q), acc[rd][k]);
-                    }
-                }
+            for (int i = 0; i < G::CPT; ++i) {
+                const int q = aq0 + i;
+                if (q < G::KAGG / 4)                             // chunks in [NQ, KAGG/4) are the K padding: zeros
+                    sts128(REG + (q >> 3) * kMpPanel + pan_off(ad_, q), q < NQ ? acc[i] : make_float4(0.f, 0.f, 0.f, 0.f));
             }
-            if (G::KAGG > HC)                                    // K padding of the scale product
-                for (int i = tid; i < kMpM * (G::KAGG - HC) / 4; i += kMpThreads) {
-                    const int r = i / ((G::KAGG - HC) / 4), q = NQ + i - r * ((G::KAGG - HC) / 4);
+            if (WQ * G::CPT < G::KAGG / 4)
+                for (int i = tid; i < kMpM * (G::KAGG / 4 - WQ * G::CPT); i += NT) {
+                    const int r = i / (G::KAGG / 4 - WQ * G::CPT), q = WQ * G::CPT + i - r * (G::KAGG / 4 - WQ * G::CPT);
                     sts128(REG + (q >> 3) * kMpPanel + pan_off(r, q), make_float4(0.f, 0.f, 0.f, 0.f));
                 }
             fence_proxy_async_smem();
@@ -456,35 +519,33 @@ mp_fused_kernel(const MpParams p) {
                     mma_tf32_ss(tmem_base + G::TM_PRE, make_smem_desc(reg_a + pan * kMpPanel + within, 16, 1024),
                                 make_smem_desc(ws_a + pan * (G::NS * 128) + within, 16, 1024), idesc, ks > 0 ? 1u : 0u);
                 }
-                mma_commit(&mma_bar);
+                mma_commit(mma_bar);
             }
             if (SAVE) {
                 float* ag = p.sAGG + ((size_t)s * p.N + n0) * HC;
-                for (int i = tid; i < nd * NQ; i += kMpThreads) {
+                for (int i = tid; i < nd * NQ; i += NT) {
                     const int r = i / NQ, q = i - r * NQ;
                     reinterpret_cast<float4*>(ag)[i] = lds128(REG + (q >> 3) * kMpPanel + pan_off(r, q));
                 }
             }
-            mbar_wait_guarded(&mma_bar, ph); ph ^= 1u;
+            mbar_wait_guarded(mma_bar, ph); ph ^= 1u;
             tc_fence_after_sync();
-            __syncthreads();                                     // agg copy-out done before m overwrites panel 0
+            if (SAVE) __syncthreads();                           // agg copy-out done before m overwrites panel 0
             // -------------------------------------------------------- P7: epilogue: + bias, CELU -> m operand panels (or the conv output)
             float* ostage = reinterpret_cast<float*>(REG + 2 * kMpPanel);        // conv-only: row-major [128][C] output staging
-            if (16 * cg < C) {
-                float v[16];
-                tmem_ld16(lane_base + G::TM_PRE + 16 * cg, v);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int cq = 4 * cg + i;
-                    if (cq < CQ) {
-                        const float4 b = lds128(bias_s + 4 * cq);
-                        float4 m4 = make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w);
-                        if (p.conv_only) {
-                            sts128(ostage + row * C + 4 * cq, m4);
-                        } else {
-                            m4.x = celu1(m4.x); m4.y = celu1(m4.y); m4.z = celu1(m4.z); m4.w = celu1(m4.w);
-                            sts128(cq < 8 ? REG + pan_off(row, cq) : AT + pan_off(row, 4 + cq - 8), m4);
-                        }
+            for (int jj = 0; jj < G::JPW; ++jj) {
+                const int cq = cg + WQ * jj;
+                if (cq < CQ) {                                   // warp-uniform
+                    float v[4];
+                    tmem_ld4(lane_base + G::TM_PRE + 4 * cq, v);
+                    const float4 b = lds128(bias_s + 4 * cq);
+                    float4 m4 = make_float4(v[0] + b.x, v[1] + b.y, v[2] + b.z, v[3] + b.w);
+                    if (p.conv_only) {
+                        sts128(ostage + row * C + 4 * cq, m4);
+                    } else {
+                        m4.x = celu_fast(m4.x); m4.y = celu_fast(m4.y); m4.z = celu_fast(m4.z); m4.w = celu_fast(m4.w);
+                        sts128(cq < 8 ? REG + pan_off(row, cq) : AT + pan_off(row, 4 + cq - 8), m4);
                     }
                 }
             }
@@ -492,7 +553,7 @@ mp_fused_kernel(const MpParams p) {
             fence_proxy_async_smem();
             __syncthreads();
             if (p.conv_only) {
-                copy_out_flat(ostage, p.x_out + (size_t)n0 * C, nd * CQ);
+                copy_out_flat<NT>(ostage, p.x_out + (size_t)n0 * C, nd * CQ);
                 __syncthreads();
                 continue;
             }
@@ -512,18 +573,18 @@ mp_fused_kernel(const MpParams p) {
                     const uint32_t b = ks < 4 ? wh_a + ks * 32 : wt_a + 64;
                     mma_tf32_ss(tmem_base + G::TM_GH, make_smem_desc(a, 16, 1024), make_smem_desc(b, 16, 1024), idesc, ks > 0 ? 1u : 0u);
                 }
-                mma_commit(&mma_bar);
+                mma_commit(mma_bar);
             }
-            if (SAVE) copy_out_panels<CQ>(REG, AT, 2, p.sM + ((size_t)s * p.N + n0) * C, nd);
-            mbar_wait_guarded(&mma_bar, ph); ph ^= 1u;
+            if (SAVE) copy_out_panels<CQ, NT>(REG, AT, 2, p.sM + ((size_t)s * p.N + n0) * C, nd);
+            mbar_wait_guarded(mma_bar, ph); ph ^= 1u;
             tc_fence_after_sync();
             if (SAVE) __syncthreads();                           // m copy-out done before the r|z|n staging overwrites the region
             // -------------------------------------------------------- P9: gates; h' and x' in place
             float* rstage = reinterpret_cast<float*>(REG);       // save mode: r|z|n rows, pitch 3C
-            float4 ghn[(CQ + 3) / 4];
+            float4 ghn[G::JPW];
 #pragma unroll
-            for (int jj = 0; jj < (CQ + 3) / 4; ++jj) {
-                const int j = cg + 4 * jj;
+            for (int jj = 0; jj < G::JPW; ++jj) {
+                const int j = cg + WQ * jj;
                 ghn[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (j < CQ) {                                    // warp-uniform
                     float v[24];
@@ -544,10 +605,16 @@ mp_fused_kernel(const MpParams p) {
         z.k = fast_sigmoid(v[4 + i] + v[16 + i] + b.y);                                        \
         nn.k = fast_tanh((v[8 + i] + b.z) + r.k * gn.k);                                       \
         hw.k = (1.f - z.k) * nn.k + z.k * hv.k;                                                \
-        xo.k = act_fwd(hw.k + xv.k, p.act, p.act_param);                                       \
+        xo.k = hw.k + xv.k;                                                                    \
     }
                     MP_GATE(x, 0) MP_GATE(y, 1) MP_GATE(z, 2) MP_GATE(w, 3)
 #undef MP_GATE
+                    if (p.act == ACT_CELU) { xo.x = celu_fast(xo.x); xo.y = celu_fast(xo.y); xo.z = celu_fast(xo.z); xo.w = celu_fast(xo.w); }
+                    else if (p.act != ACT_NONE) {                // relu = leaky with slope 0
+                        const float sl = p.act == ACT_LEAKY ? p.act_param : 0.f;
+                        xo.x = xo.x > 0.f ? xo.x : sl * xo.x; xo.y = xo.y > 0.f ? xo.y : sl * xo.y;
+                        xo.z = xo.z > 0.f ? xo.z : sl * xo.z; xo.w = xo.w > 0.f ? xo.w : sl * xo.w;
+                    }
                     sts128(hdst, hw);
                     sts128(xdst, xo);
                     if (SAVE) {
@@ -563,24 +630,24 @@ mp_fused_kernel(const MpParams p) {
             __syncthreads();
             // -------------------------------------------------------- outputs of the step
             if (SAVE) {
-                copy_out_panels<CQ>(XM, AT, 0, p.sX + (size_t)(s + 1) * NC + (size_t)n0 * C, nd);
-                copy_out_panels<CQ>(HM, AT, 1, p.sHH + (size_t)(s + 1) * NC + (size_t)n0 * C, nd);
-                copy_out_flat(rstage, p.sRZN + ((size_t)s * p.N + n0) * 3 * C, nd * 3 * CQ);
+                copy_out_panels<CQ, NT>(XM, AT, 0, p.sX + (size_t)(s + 1) * NC + (size_t)n0 * C, nd);
+                copy_out_panels<CQ, NT>(HM, AT, 1, p.sHH + (size_t)(s + 1) * NC + (size_t)n0 * C, nd);
+                copy_out_flat<NT>(rstage, p.sRZN + ((size_t)s * p.N + n0) * 3 * C, nd * 3 * CQ);
                 __syncthreads();
                 float* gstage = reinterpret_cast<float*>(REG);   // gh_n rows, pitch C
 #pragma unroll
-                for (int jj = 0; jj < (CQ + 3) / 4; ++jj) {
-                    const int j = cg + 4 * jj;
+                for (int jj = 0; jj < G::JPW; ++jj) {
+                    const int j = cg + WQ * jj;
                     if (j < CQ) sts128(gstage + row * C + 4 * j, ghn[jj]);
                 }
                 __syncthreads();
-                copy_out_flat(gstage, p.sGH + ((size_t)s * p.N + n0) * C, nd * CQ);
+                copy_out_flat<NT>(gstage, p.sGH + ((size_t)s * p.N + n0) * C, nd * CQ);
                 __syncthreads();                                 // before the next step's P1 writes the logit columns into the region
             } else {
                 const bool last = s == p.steps - 1;
                 if (p.keep_all || last)
-                    copy_out_panels<CQ>(XM, AT, 0, p.x_out + (p.keep_all ? (size_t)s * NC : (size_t)0) + (size_t)n0 * C, nd);
-                if (last && p.h_out) copy_out_panels<CQ>(HM, AT, 1, p.h_out + (size_t)n0 * C, nd);
+                    copy_out_panels<CQ, NT>(XM, AT, 0, p.x_out + (p.keep_all ? (size_t)s * NC : (size_t)0) + (size_t)n0 * C, nd);
+                if (last && p.h_out) copy_out_panels<CQ, NT>(HM, AT, 1, p.h_out + (size_t)n0 * C, nd);
             }
         }
         __syncthreads();                                         // all reads of the tile (copy-outs) done before the next tile load
@@ -592,16 +659,22 @@ mp_fused_kernel(const MpParams p) {
 
 bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-template <int CQ, int H>
-int mp_launch(const MpParams& p, bool save, cudaStream_t stream) {
-    using G = MpGeom<CQ, H>;
+int g_mp_threads = 512;                                          // GLAM_B200_MP_THREADS=1024 selects the 32-warp variant (A/B timing)
+
+template <int CQ, int H, int NT>
+int mp_launch_nt(const MpParams& p, bool save, cudaStream_t stream) {
+    using G = MpGeom<CQ, H, NT>;
     auto go = [&](auto kernel) -> int {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         if (e != cudaSuccess) { set_error("glam_message_stack_fwd: cudaFuncSetAttribute(%d bytes): %s", G::SMEM, cudaGetErrorString(e)); return (int)e; }
-        kernel<<<kNumSMs, kMpThreads, G::SMEM, stream>>>(p);
+        kernel<<<kNumSMs, NT, G::SMEM, stream>>>(p);
         return 0;
     };
-    return save ? go(mp_fused_kernel<CQ, H, true>) : go(mp_fused_kernel<CQ, H, false>);
+    return save ? go(mp_fused_kernel<CQ, H, NT, true>) : go(mp_fused_kernel<CQ, H, NT, false>);
+}
+template <int CQ, int H>
+int mp_launch(const MpParams& p, bool save, cudaStream_t stream) {
+    return g_mp_threads == 1024 ? mp_launch_nt<CQ, H, 1024>(p, save, stream) : mp_launch_nt<CQ, H, 512>(p, save, stream);
 }
 
 }  // namespace
@@ -622,7 +695,10 @@ extern "C" int glam_build_graph_tiles(const int32_t* graph_ptr, int64_t num_grap
     GLAM_REQUIRE(al16(tiles), "glam_build_graph_tiles: tiles must be 16-byte aligned");
     GLAM_REQUIRE(num_graphs < ((int64_t)1 << 30), "glam_build_graph_tiles: too many graphs");
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int G = (int)((num_graphs + 1023) / 1024 > 0 ? (num_graphs + 1023) / 1024 : 1);
+    // graphs per packer thread: tiles never span chunks, so a chunk must hold many tiles' worth of graphs (>= 64 graphs:
+    // one partly filled tile in ~13); beyond 64k graphs the 1024 packers simply take longer chunks
+    const int64_t gmin = (num_graphs + 1023) / 1024;
+    const int G = (int)(gmin > 64 ? gmin : 64);
     graph_tiles_kernel<<<1, 1024, 0, stream>>>(graph_ptr, num_graphs, dst_rowptr, G, kMpM, kMpMaxEdges, reinterpret_cast<int4*>(tiles), meta);
     GLAM_CHECK_LAUNCH();
     if (num_graphs > 0 && num_edges > 0 && dst_src) {
@@ -684,6 +760,8 @@ extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const fl
     p.sM = save_m; p.sRZN = save_rzn; p.sGH = save_gh;
     int rc = 0;
     cudaStream_t stream = (cudaStream_t)stream_;
+    static const int threads_env = [] { const char* e = getenv("GLAM_B200_MP_THREADS"); return e ? atoi(e) : 0; }();
+    if (threads_env == 512 || threads_env == 1024) g_mp_threads = threads_env;
     switch (channels) {
         case 32: rc = mp_launch<8, 3>(p, save, stream); break;
         case 36: rc = mp_launch<9, 3>(p, save, stream); break;

@@ -17,7 +17,7 @@ DEV = "cuda"
 
 
 def _rel(a, b):
-    a, b = a.double(), b.double()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
 
 
@@ -30,7 +30,7 @@ def _batch(n_graphs, node_dim, edge_dim, seed, **kw):
 def _host_tiles(gptr, rowptr, max_nodes, max_edges):
     """The definition: greedy packing of consecutive graphs, chunked as the kernel chunks them (G graphs per packer)."""
     B = len(gptr) - 1
-    Gc = max((B + 1023) // 1024, 1)
+    Gc = max((B + 1023) // 1024, 64)
     tiles = []
     for c0 in range(0, B, Gc):
         g, g1 = c0, min(B, c0 + Gc)
@@ -182,7 +182,11 @@ def test_fused_stack_saved_tensors_and_grads_match_per_op(C, De, n_graphs):
                 e = _rel(got, want)
                 print(f"step {s} {name}: rel err {e:.2e}")
                 assert torch.isfinite(got).all(), f"step {s} {name}: non-finite"
-                assert e < 3e-4, f"step {s} {name}: rel err {e:.3e}"
+                # step 0 sees identical inputs (observed: bit-equal up to the gate non-linearities); later steps start from
+                # inputs that differ in the last bits, which TF32 operand truncation can turn into 2^-11 steps
+                # (the CELU of m uses ex2.approx here and an exact expm1 in the per-op epilogue: 2e-7 absolute, same effect)
+                exact = s == 0 and name in ("X", "HH", "XPE", "ALPHA", "AGG")
+                assert e < (3e-6 if exact else 2e-3), f"step {s} {name}: rel err {e:.3e}"
             x, h = x_new, h_new
 
     def run(fused):
@@ -288,7 +292,6 @@ def test_bench_shape_forward_and_gradients_vs_oracle():
     from glam_b200.synth import make_molecule_batch
     from helpers import tf32_emulated
     _lib.set_math_mode("tf32")
-    torch.backends.cuda.matmul.allow_tf32 = True
     o32, m = _gp_pair(4096)
     o64 = copy.deepcopy(o32).double()
     b = make_molecule_batch(4096, seed=1234, total_nodes=25 * 4096, total_edges=54 * 4096, node_dim=9, edge_dim=3)
@@ -303,11 +306,16 @@ def test_bench_shape_forward_and_gradients_vs_oracle():
     bd = b.to(DEV)
     m.train()
     n0 = _lib.launch_count()
-    out = m(bd)
-    n_fwd = _lib.launch_count() - n0
-    loss = torch.nn.functional.mse_loss(out, bd.y)
-    loss.backward()
-    torch.cuda.synchronize()
+    tf32_was = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True           # as bench.py runs it: the wide LinearBlocks are torch matmuls
+    try:
+        out = m(bd)
+        n_fwd = _lib.launch_count() - n0
+        loss = torch.nn.functional.mse_loss(out, bd.y)
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32_was
     print(f"forward launches {n_fwd}; loss ours {loss.item():.6f} oracle32 {l32.item():.6f} oracle64 {l64.item():.6f}")
     e_out = _rel(out, out64)
     print(f"output: rel err {e_out:.2e} (fp32 oracle vs fp64: {_rel(out32, out64):.2e})")
