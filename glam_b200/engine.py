@@ -20,23 +20,37 @@ from . import graph as G
 from .synth import GraphBatch
 
 
-def _static_like(b: GraphBatch, device) -> GraphBatch:
+def _tup(b):
+    """A step's input is one GraphBatch (GLAM-GP) or a tuple of them (the two towers of GLAM-DDI / GLAM-DTI: the model is
+    called as model(*batches), the target is the first batch's y)."""
+    return tuple(b) if isinstance(b, (tuple, list)) else (b,)
+
+
+def _static_like(b, device):
     z = lambda t: None if t is None else torch.empty_like(t, device=device)
-    return GraphBatch(z(b.x), z(b.edge_index), z(b.edge_attr), z(b.batch), z(b.y), b.num_graphs)
+    return tuple(GraphBatch(z(g.x), z(g.edge_index), z(g.edge_attr), z(g.batch), z(g.y), g.num_graphs) for g in _tup(b))
 
 
-def _copy_into(dst: GraphBatch, src: GraphBatch) -> int:
+def _copy_into(dst, src) -> int:
     """Async copies of every field (H2D from pinned memory or D2D); returns bytes moved."""
     n = 0
-    for name in ("x", "edge_index", "edge_attr", "batch", "y"):
-        s, d = getattr(src, name), getattr(dst, name)
-        if s is None:
-            continue
-        if s.shape != d.shape:
-            raise ValueError(f"batch field {name} has shape {tuple(s.shape)}, the captured step expects {tuple(d.shape)}")
-        d.copy_(s, non_blocking=True)
-        n += s.numel() * s.element_size()
+    dst, src = _tup(dst), _tup(src)
+    if len(dst) != len(src):
+        raise ValueError(f"the captured step takes {len(dst)} graph batches per call, got {len(src)}")
+    for dg, sg in zip(dst, src):
+        for name in ("x", "edge_index", "edge_attr", "batch", "y"):
+            s, d = getattr(sg, name), getattr(dg, name)
+            if s is None:
+                continue
+            if s.shape != d.shape:
+                raise ValueError(f"batch field {name} has shape {tuple(s.shape)}, the captured step expects {tuple(d.shape)}")
+            d.copy_(s, non_blocking=True)
+            n += s.numel() * s.element_size()
     return n
+
+
+def batch_nbytes(b) -> int:
+    return sum(g.nbytes() for g in _tup(b))
 
 
 class FlatGrads:
@@ -149,11 +163,11 @@ class TrainStep:
         if use_cuda_graph:
             self._capture(warmup)
 
-    def _body(self, static: Optional[GraphBatch] = None):
+    def _body(self, static=None):
         static = self.static if static is None else static
         self.grads.zero()
-        out = self.model(static)
-        loss = self.loss_fn(out, static.y)
+        out = self.model(*static)
+        loss = self.loss_fn(out, static[0].y)
         loss.backward()
         self.grads.collect()
         if self.world > 1:
@@ -162,6 +176,12 @@ class TrainStep:
         self.loss.copy_(loss.detach())
 
     def _capture(self, warmup: int):
+        # the warm-up iterations (allocator / cuBLAS / NCCL initialisation outside capture) are real optimisation steps:
+        # snapshot parameters, both Adam moments and the step counter first and put them back afterwards, so that
+        # constructing a TrainStep leaves the model and the optimizer exactly as the caller built them
+        # (torch.optim.Adam starts from step 0, src_1gp/trainer.py:49-50)
+        snap = [t.clone() for t in (self.opt.flat, self.opt.exp_avg, self.opt.exp_avg_sq, self.opt.state)]
+        bufs = [(b, b.clone()) for b in self.model.buffers()]
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
@@ -170,6 +190,11 @@ class TrainStep:
                 self._body()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
+        with torch.no_grad():
+            for dst, src in zip((self.opt.flat, self.opt.exp_avg, self.opt.exp_avg_sq, self.opt.state), snap):
+                dst.copy_(src)
+            for b, saved in bufs:
+                b.copy_(saved)
         pool = None
         for st in self.statics:
             G.clear_caches()                  # the index build must be part of the captured step
@@ -201,9 +226,9 @@ class TrainStep:
             return self.run_resident()
         main = torch.cuda.current_stream(self.device)
         slot = self._slot
-        if self._prefetched is batch:
-            main.wait_event(self._copied[slot])                   # the copy was enqueued during the previous step
-        else:
+        if self._prefetched is not None:
+            main.wait_event(self._copied[slot])                   # the copy enqueued during the previous step (also when the
+        if self._prefetched is not batch:                         # caller then passes a different batch: it overwrites it)
             _copy_into(self.statics[slot], batch)
         self._prefetched = None
         self.run_resident()
@@ -249,7 +274,7 @@ class ScreenStep:
                 with torch.cuda.stream(s):
                     for _ in range(max(warmup, 1)):
                         G.clear_caches()
-                        self.model(self.static)
+                        self.model(*self.static)
                 torch.cuda.current_stream(self.device).wait_stream(s)
                 torch.cuda.synchronize(self.device)
                 pool = None
@@ -257,7 +282,7 @@ class ScreenStep:
                     G.clear_caches()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, pool=pool):
-                        self.outs[i] = self.model(st)
+                        self.outs[i] = self.model(*st)
                     pool = g.pool()
                     self.graphs.append(g)
                 G.clear_caches()
@@ -273,7 +298,7 @@ class ScreenStep:
         else:
             with torch.no_grad():
                 G.clear_caches()
-                self.outs[self._slot] = self.model(self.statics[self._slot])
+                self.outs[self._slot] = self.model(*self.statics[self._slot])
         return self.outs[self._slot]
 
     def step(self, batch: GraphBatch, prefetch: Optional[GraphBatch] = None) -> torch.Tensor:
@@ -282,9 +307,9 @@ class ScreenStep:
             return self.run_resident()
         main = torch.cuda.current_stream(self.device)
         slot = self._slot
-        if self._prefetched is batch:
+        if self._prefetched is not None:
             main.wait_event(self._copied[slot])
-        else:
+        if self._prefetched is not batch:
             _copy_into(self.statics[slot], batch)
         self._prefetched = None
         out = self.run_resident()

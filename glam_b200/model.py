@@ -59,12 +59,21 @@ class ArchitectureGP(nn.Module):
         self.mol_readout = _readout(mol_readout, hid)
         self.mol_flat = LinearBlock(_readout_width(mol_readout) * hid, e_dim, norm=flat_norm, dropout=flat_do, act=flat_act)
         self.lin_out1 = LinearBlock(e_dim, out_dim, norm=end_norm, dropout=end_do, act="_None")
+        # False: step the block exactly as the reference's model.py does (`for _: xm, hm = self.mol_conv(...)`,
+        # src_1gp/model.py:52-54) instead of handing the whole loop to MessageBlock.run_steps — same values, more launches
+        self.stack_steps = True
 
     def forward(self, data_mol):
         B = _num_graphs(data_mol)
         xm = self.mol_lin0(data_mol.x, batch=data_mol.batch)
-        xs, _ = self.mol_conv.run_steps(xm, data_mol.edge_index, data_mol.edge_attr, self.message_steps, batch=data_mol.batch,
-                                        num_graphs=B, keep="last")
+        if self.stack_steps:
+            xs, _ = self.mol_conv.run_steps(xm, data_mol.edge_index, data_mol.edge_attr, self.message_steps, batch=data_mol.batch,
+                                            num_graphs=B, keep="last")
+        else:
+            hm = None
+            for _ in range(self.message_steps):
+                xm, hm = self.mol_conv(xm, data_mol.edge_index, data_mol.edge_attr, h=hm, batch=data_mol.batch, num_graphs=B)
+            xs = [xm]
         outm = self.mol_readout(xs[-1], data_mol.batch, num_graphs=B)
         return self.lin_out1(self.mol_flat(outm))
 

@@ -519,13 +519,12 @@ def test_captured_train_steps_follow_oracle_training():
             loss.backward()
             opt.step()
             ref_losses.append(loss.item())
-        ts = TrainStep(m, torch.nn.functional.mse_loss, batches[0], lr=1e-3, device=DEV, use_cuda_graph=True, warmup=0)
-        # capture ran the body (warm-up + capture pass) on batch 0: rewind parameters and optimizer state
         sd = {k: v.to(DEV) for k, v in _gp_pair(9, 3, "Set2Set", "_TripletMessage")[1].state_dict().items()}
-        with torch.no_grad():
-            for k, p in m.state_dict().items():
-                p.copy_(sd[k])
-        ts.opt.exp_avg.zero_(); ts.opt.exp_avg_sq.zero_(); ts.opt.state.zero_()
+        ts = TrainStep(m, torch.nn.functional.mse_loss, batches[0], lr=1e-3, device=DEV, use_cuda_graph=True, warmup=3)
+        # constructing the step (3 warm-up iterations + capture) must not train: parameters and Adam state as built
+        for k, p in m.state_dict().items():
+            assert torch.equal(p, sd[k]), k
+        assert not ts.opt.exp_avg.any() and not ts.opt.exp_avg_sq.any() and not ts.opt.state.any()
         losses = [ts.step(b.pin_memory()).item() for b in batches]
         for a, r in zip(losses, ref_losses):
             assert abs(a - r) <= 2e-4 * max(1.0, abs(r)), (losses, ref_losses)
@@ -533,12 +532,8 @@ def test_captured_train_steps_follow_oracle_training():
             torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=2e-3, atol=2e-4, msg=lambda s, n=n: f"{n}: {s}")
         # double-buffered inputs with the next batch's copy in flight during the step: bitwise the same training run
         m2, _ = _gp_pair(9, 3, "Set2Set", "_TripletMessage")
-        ts2 = TrainStep(m2, torch.nn.functional.mse_loss, batches[0], lr=1e-3, device=DEV, use_cuda_graph=True, warmup=0,
+        ts2 = TrainStep(m2, torch.nn.functional.mse_loss, batches[0], lr=1e-3, device=DEV, use_cuda_graph=True, warmup=1,
                         double_buffer=True)
-        with torch.no_grad():
-            for k, p in m2.state_dict().items():
-                p.copy_(sd[k])
-        ts2.opt.exp_avg.zero_(); ts2.opt.exp_avg_sq.zero_(); ts2.opt.state.zero_()
         pinned = [b.pin_memory() for b in batches]
         losses2 = [ts2.step(b, prefetch=pinned[i + 1] if i + 1 < len(pinned) else None).item() for i, b in enumerate(pinned)]
         assert losses2 == losses, (losses2, losses)
