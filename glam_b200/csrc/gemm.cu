@@ -187,29 +187,31 @@ __global__ void colsum_partial_kernel(const float* __restrict__ G, int64_t ldg, 
 // destination), so they are kept out of the TF32 path; they are also far too narrow for a tensor-core tile.
 // One warp per row (lanes over the wide operand's features), 8 warps x S CTAs, fixed-order reductions.
 constexpr int kSkinnyWarps = 8;
-template <int KPL>
+// QW = 8 or 16: register width of the narrow operand (16 covers the 9 / 15-feature input projections of the models, whose
+// weight gradients otherwise fell to the scalar fp32 A^T B kernel: 81 us for 18 MB of operands at the bench shape)
+template <int KPL, int QW = 8>
 __global__ void __launch_bounds__(kSkinnyWarps * 32)
 skinny_tn_kernel(const float* __restrict__ P, int64_t ldp, int Wp, const float* __restrict__ Q, int64_t ldq, int Wq, int64_t M,
                  int64_t rows_per_cta, float* __restrict__ partial) {
-    extern __shared__ float red[];                     // [kSkinnyWarps][Wp][8]
+    extern __shared__ float red[];                     // [kSkinnyWarps][Wp][QW]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t mbeg = (int64_t)blockIdx.x * rows_per_cta;
     int64_t mend = mbeg + rows_per_cta;
     if (mend > M) mend = M;
-    float acc[KPL][8];
+    float acc[KPL][QW];
 #pragma unroll
     for (int t = 0; t < KPL; ++t)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+        for (int j = 0; j < QW; ++j) acc[t][j] = 0.f;
     // 4 rows per iteration: 4 independent load groups in flight per warp
     for (int64_t m0 = mbeg + warp; m0 < mend; m0 += 4 * kSkinnyWarps) {
-        float q[4][8], a[4][KPL];
+        float q[4][QW], a[4][KPL];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t m = m0 + (int64_t)u * kSkinnyWarps;
             const bool ok = m < mend;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) q[u][j] = (ok && j < Wq) ? Q[m * ldq + j] : 0.f;
+            for (int j = 0; j < QW; ++j) q[u][j] = (ok && j < Wq) ? Q[m * ldq + j] : 0.f;
 #pragma unroll
             for (int t = 0; t < KPL; ++t) {
                 const int f = lane + 32 * t;
@@ -221,14 +223,14 @@ skinny_tn_kernel(const float* __restrict__ P, int64_t ldp, int Wp, const float* 
 #pragma unroll
             for (int t = 0; t < KPL; ++t)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(a[u][t], q[u][j], acc[t][j]);
+                for (int j = 0; j < QW; ++j) acc[t][j] = fmaf(a[u][t], q[u][j], acc[t][j]);
     }
 #pragma unroll
     for (int t = 0; t < KPL; ++t) {
         const int f = lane + 32 * t;
         if (f < Wp)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) red[((size_t)warp * Wp + f) * 8 + j] = acc[t][j];
+            for (int j = 0; j < QW; ++j) red[((size_t)warp * Wp + f) * QW + j] = acc[t][j];
     }
     __syncthreads();
     float* out = partial + (int64_t)blockIdx.x * Wp * Wq;
@@ -236,7 +238,7 @@ skinny_tn_kernel(const float* __restrict__ P, int64_t ldp, int Wp, const float* 
         const int f = idx / Wq, j = idx - f * Wq;
         float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < kSkinnyWarps; ++w) v += red[((size_t)w * Wp + f) * 8 + j];
+        for (int w = 0; w < kSkinnyWarps; ++w) v += red[((size_t)w * Wp + f) * QW + j];
         out[idx] = v;
     }
 }
@@ -392,26 +394,37 @@ extern "C" int glam_gemm_tn_ex(const float* A, int64_t lda, const float* B, int6
     GLAM_REQUIRE(A && B && lda >= Ka && ldb >= Kb, "glam_gemm_tn_ex: bad inputs");
     GLAM_REQUIRE(workspace && workspace_bytes >= glam_gemm_tn_ex_workspace_bytes(M, Ka, Kb, colsum_b != nullptr),
                  "glam_gemm_tn_ex: workspace too small");
-    if (!colsum_b && (Ka <= 8 || Kb <= 8) && Ka <= 288 && Kb <= 288) {
+    const int64_t knarrow = Ka < Kb ? Ka : Kb;
+    if ((knarrow <= 8 || (knarrow <= 16 && Ka <= 64 && Kb <= 64)) && Ka <= 288 && Kb <= 288) {
         // skinny product: exact fp32, result partial is [Wp][Wq] with the wide operand first
-        const bool a_wide = Kb <= 8;
+        const bool a_wide = Kb <= Ka;
         const float* P = a_wide ? A : B; const float* Q = a_wide ? B : A;
         const int64_t ldp = a_wide ? lda : ldb, ldq = a_wide ? ldb : lda;
         const int Wp = (int)(a_wide ? Ka : Kb), Wq = (int)(a_wide ? Kb : Ka);
         const int S = skinny_grid(M);
         const int64_t rpc = (M + S - 1) / S;
-        const size_t smem = sizeof(float) * kSkinnyWarps * Wp * 8;
+        const int qw = Wq <= 8 ? 8 : 16;
+        const size_t smem = sizeof(float) * kSkinnyWarps * Wp * qw;
         const int kpl = (Wp + 31) / 32;
         auto launch = [&](auto fn) {
             if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             fn<<<S, kSkinnyWarps * 32, smem, stream>>>(P, ldp, Wp, Q, ldq, Wq, M, rpc, (float*)workspace);
         };
-        if (kpl <= 2) launch(skinny_tn_kernel<2>); else if (kpl <= 4) launch(skinny_tn_kernel<4>);
+        if (qw == 16) launch(skinny_tn_kernel<2, 16>);
+        else if (kpl <= 2) launch(skinny_tn_kernel<2>); else if (kpl <= 4) launch(skinny_tn_kernel<4>);
         else if (kpl <= 6) launch(skinny_tn_kernel<6>); else launch(skinny_tn_kernel<9>);
         GLAM_CHECK_LAUNCH();
         // partial holds [Wp][Wq]; out is [Ka][Kb]: transposed w.r.t. the partial exactly when A is the narrow operand
         const int tr = (a_wide ? 0 : 1) ^ (transpose_out ? 1 : 0);
-        return launch_reduce_partials((const float*)workspace, S, Wp, Wq, 0, out, ldo, tr, nullptr, stream);
+        if (int rc = launch_reduce_partials((const float*)workspace, S, Wp, Wq, 0, out, ldo, tr, nullptr, stream)) return rc;
+        if (colsum_b) {
+            const int S2 = colsum_splits(M);
+            int64_t rps2 = (M + S2 - 1) / S2;
+            colsum_partial_kernel<<<S2, dim3(32, 8), 0, stream>>>(B, ldb, M, (int)Kb, rps2, (float*)workspace);
+            GLAM_CHECK_LAUNCH();
+            return launch_reduce_partials((const float*)workspace, S2, 1, (int)Kb, 0, colsum_b, Kb, 0, nullptr, stream);
+        }
+        return 0;
     }
     if (tc_gemm_tn_eligible(A, lda, B, ldb, M, Ka, Kb, colsum_b != nullptr))
         return tc_gemm_tn_launch(A, lda, B, ldb, M, Ka, Kb, out, ldo, transpose_out, colsum_b, workspace, stream);

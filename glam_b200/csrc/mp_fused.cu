@@ -52,68 +52,83 @@ constexpr int kMpPanel = kMpM * kPanelRowBytes;      // 16 KB
 enum : int { kFlagNodes = 1, kFlagEdges = 2, kFlagCross = 4, kFlagEdgeAttr = 8 };
 
 // ------------------------------------------------------------------------------------------------ graph tiles
-// Greedy packing of consecutive whole graphs into tiles of <= max_nodes nodes and <= max_edges in-edges.  One CTA; thread c
-// packs the graphs [c*G, (c+1)*G) (tiles never span chunks: one partly filled tile per chunk), counts, block scan, emit.
-template <typename Emit>
-__device__ __forceinline__ int pack_chunk(const int32_t* __restrict__ gptr, const int32_t* __restrict__ rowptr, int64_t g0, int64_t g1,
-                                          int max_nodes, int max_edges, int& flags, Emit emit) {
-    int count = 0;
-    int64_t g = g0;
-    while (g < g1) {
-        const int n0 = gptr[g], e0 = rowptr[n0];
-        int64_t k = g;
-        int n1 = n0, e1 = e0;
-        while (k < g1) {
-            const int nn = gptr[k + 1], ee = rowptr[nn];
-            if (nn - n0 > max_nodes || ee - e0 > max_edges) break;
-            n1 = nn; e1 = ee; ++k;
-        }
-        if (k == g) {                                  // a single graph over the caps: its own (flagged) tile
-            n1 = gptr[g + 1]; e1 = rowptr[n1];
-            flags |= (n1 - n0 > max_nodes ? kFlagNodes : 0) | (e1 - e0 > max_edges ? kFlagEdges : 0);
-            k = g + 1;
-        }
-        if (n1 > n0) { emit(count, make_int4(n0, n1, e0, e1)); ++count; }
-        g = k;
+// Greedy packing of consecutive whole graphs into tiles of <= max_nodes nodes and <= max_edges in-edges, in chunks of 64
+// graphs (tiles never span chunks: one partly filled tile per chunk of ~13).  Three small launches:
+//   (1) a warp per chunk: the lanes fetch the chunk's node / edge end offsets in parallel (two dependent loads per lane
+//       instead of 128 in a row), lane 0 walks them out of shared memory and emits the chunk's tiles into the chunk's own
+//       slots of a scratch array (slot c*64 + i) and the chunk's tile count;
+//   (2) one CTA: exclusive scan of the chunk counts (fixed order), total -> meta[0];
+//   (3) a warp per chunk: scratch slots -> final positions.
+constexpr int kTileChunk = 64;
+constexpr int kTileWarps = 8;
+
+__global__ void __launch_bounds__(kTileWarps * 32)
+graph_tiles_pack_kernel(const int32_t* __restrict__ gptr, int64_t B, const int32_t* __restrict__ rowptr, int max_nodes, int max_edges,
+                        int4* __restrict__ scratch, int32_t* __restrict__ counts, int32_t* __restrict__ meta) {
+    __shared__ int nend[kTileWarps][kTileChunk + 1], eend[kTileWarps][kTileChunk + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * kTileWarps + warp;
+    const int64_t g0 = c * kTileChunk;
+    if (g0 >= B) return;
+    const int ng = (int)min((int64_t)kTileChunk, B - g0);
+    for (int i = lane; i <= ng; i += 32) {
+        const int nn = gptr[g0 + i];
+        nend[warp][i] = nn;
+        eend[warp][i] = rowptr[nn];
     }
-    return count;
+    __syncwarp();
+    if (lane == 0) {
+        int count = 0, flags = 0, g = 0;
+        while (g < ng) {
+            const int n0 = nend[warp][g], e0 = eend[warp][g];
+            int k = g, n1 = n0, e1 = e0;
+            while (k < ng) {
+                const int nn = nend[warp][k + 1], ee = eend[warp][k + 1];
+                if (nn - n0 > max_nodes || ee - e0 > max_edges) break;
+                n1 = nn; e1 = ee; ++k;
+            }
+            if (k == g) {                              // a single graph over the caps: its own (flagged) tile
+                n1 = nend[warp][g + 1]; e1 = eend[warp][g + 1];
+                flags |= (n1 - n0 > max_nodes ? kFlagNodes : 0) | (e1 - e0 > max_edges ? kFlagEdges : 0);
+                k = g + 1;
+            }
+            if (n1 > n0) { scratch[c * kTileChunk + count] = make_int4(n0, n1, e0, e1); ++count; }
+            g = k;
+        }
+        counts[c] = count;
+        if (flags) atomicOr(&meta[1], flags);          // meta is zeroed by the caller; every builder ORs its findings in
+    }
 }
 
+// counts[c] -> exclusive prefix (in place); total -> meta[0].  One CTA, 1024 threads, each a contiguous run of chunks.
 __global__ void __launch_bounds__(1024)
-graph_tiles_kernel(const int32_t* __restrict__ gptr, int64_t B, const int32_t* __restrict__ rowptr, int G, int max_nodes, int max_edges,
-                   int4* __restrict__ tiles, int32_t* __restrict__ meta) {
-    __shared__ int warp_tot[32];
-    __shared__ int flags_s;
-    const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
-    if (c == 0) flags_s = 0;
+graph_tiles_scan_kernel(int32_t* __restrict__ counts, int64_t chunks, int32_t* __restrict__ meta) {
+    __shared__ int part[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (chunks + 1023) / 1024, c0 = min(chunks, t * per), c1 = min(chunks, c0 + per);
+    int sum = 0;
+    for (int64_t c = c0; c < c1; ++c) sum += counts[c];
+    part[t] = sum;
     __syncthreads();
-    const int64_t g0 = min((int64_t)c * G, B), g1 = min(B, g0 + G);
-    int flags = 0;
-    const int mine = pack_chunk(gptr, rowptr, g0, g1, max_nodes, max_edges, flags, [](int, int4) {});
-    int incl = mine;                                   // block-wide exclusive scan of the counts
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+    for (int o = 1; o < 1024; o <<= 1) {               // Hillis-Steele inclusive scan (integers: order is irrelevant)
+        const int v = t >= o ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
     }
-    if (lane == 31) warp_tot[warp] = incl;
-    if (flags) atomicOr(&flags_s, flags);
-    __syncthreads();
-    if (warp == 0) {
-        int v = warp_tot[lane], s = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += u;
-        }
-        warp_tot[lane] = s - v;                        // exclusive prefix of the warp totals
-        if (lane == 31) meta[0] = s;
-    }
-    __syncthreads();
-    const int base = warp_tot[warp] + incl - mine;
-    int dummy = 0;
-    pack_chunk(gptr, rowptr, g0, g1, max_nodes, max_edges, dummy, [&](int i, int4 t) { tiles[base + i] = t; });
-    if (c == 0 && flags_s) atomicOr(&meta[1], flags_s);       // meta is zeroed by the caller; every builder ORs its findings in
+    int run = part[t] - sum;
+    for (int64_t c = c0; c < c1; ++c) { const int n = counts[c]; counts[c] = run; run += n; }
+    if (t == 1023) meta[0] = part[1023];
+}
+
+__global__ void __launch_bounds__(kTileWarps * 32)
+graph_tiles_emit_kernel(const int4* __restrict__ scratch, const int32_t* __restrict__ offsets, int64_t chunks, const int32_t* __restrict__ meta,
+                        int4* __restrict__ tiles) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * kTileWarps + warp;
+    if (c >= chunks) return;
+    const int base = offsets[c], n = (c + 1 < chunks ? offsets[c + 1] : meta[0]) - base;
+    for (int i = lane; i < n; i += 32) tiles[base + i] = scratch[c * kTileChunk + i];
 }
 
 // a warp per tile: every source of the tile's in-edges must be one of its own rows (block-diagonal batch)
@@ -688,18 +703,31 @@ extern "C" int glam_graph_tile_caps(int* max_nodes, int* max_edges) {
     return 0;
 }
 
+extern "C" size_t glam_graph_tiles_workspace_bytes(int64_t num_graphs) {
+    const size_t chunks = (size_t)((num_graphs + kTileChunk - 1) / kTileChunk);
+    return chunks * kTileChunk * sizeof(int4) + (chunks + 1) * sizeof(int32_t) + 16;
+}
+
 extern "C" int glam_build_graph_tiles(const int32_t* graph_ptr, int64_t num_graphs, const int32_t* dst_rowptr, const int32_t* dst_src,
-                                      int64_t num_nodes, int64_t num_edges, int32_t* tiles, int32_t* meta, void* stream_) {
+                                      int64_t num_nodes, int64_t num_edges, int32_t* tiles, int32_t* meta, void* workspace,
+                                      size_t workspace_bytes, void* stream_) {
     GLAM_REQUIRE(num_graphs >= 0 && num_nodes >= 0 && num_edges >= 0, "glam_build_graph_tiles: bad sizes");
     GLAM_REQUIRE(graph_ptr && dst_rowptr && tiles && meta, "glam_build_graph_tiles: null pointer");
     GLAM_REQUIRE(al16(tiles), "glam_build_graph_tiles: tiles must be 16-byte aligned");
     GLAM_REQUIRE(num_graphs < ((int64_t)1 << 30), "glam_build_graph_tiles: too many graphs");
     cudaStream_t stream = (cudaStream_t)stream_;
-    // graphs per packer thread: tiles never span chunks, so a chunk must hold many tiles' worth of graphs (>= 64 graphs:
-    // one partly filled tile in ~13); beyond 64k graphs the 1024 packers simply take longer chunks
-    const int64_t gmin = (num_graphs + 1023) / 1024;
-    const int G = (int)(gmin > 64 ? gmin : 64);
-    graph_tiles_kernel<<<1, 1024, 0, stream>>>(graph_ptr, num_graphs, dst_rowptr, G, kMpM, kMpMaxEdges, reinterpret_cast<int4*>(tiles), meta);
+    GLAM_REQUIRE(workspace && workspace_bytes >= glam_graph_tiles_workspace_bytes(num_graphs) && al16(workspace),
+                 "glam_build_graph_tiles: workspace too small or not 16-byte aligned");
+    const int64_t chunks = (num_graphs + kTileChunk - 1) / kTileChunk;
+    if (chunks == 0) return 0;                                   // meta[0] stays 0
+    int4* scratch = reinterpret_cast<int4*>(workspace);
+    int32_t* counts = reinterpret_cast<int32_t*>(scratch + chunks * kTileChunk);
+    const unsigned grid = (unsigned)((chunks + kTileWarps - 1) / kTileWarps);
+    graph_tiles_pack_kernel<<<grid, kTileWarps * 32, 0, stream>>>(graph_ptr, num_graphs, dst_rowptr, kMpM, kMpMaxEdges, scratch, counts, meta);
+    GLAM_CHECK_LAUNCH();
+    graph_tiles_scan_kernel<<<1, 1024, 0, stream>>>(counts, chunks, meta);
+    GLAM_CHECK_LAUNCH();
+    graph_tiles_emit_kernel<<<grid, kTileWarps * 32, 0, stream>>>(scratch, counts, chunks, meta, reinterpret_cast<int4*>(tiles));
     GLAM_CHECK_LAUNCH();
     if (num_graphs > 0 && num_edges > 0 && dst_src) {
         const int64_t warps = num_graphs;

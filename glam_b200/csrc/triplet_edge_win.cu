@@ -103,7 +103,6 @@ struct WinArgs {
     const int4* tiles;
     int64_t N; int C, De, D, rmax; int64_t T;
     float slope;
-    int dbg;                                              // profiling only: 1 skip softmax, 2 skip aggregate, 4 skip window copy, 8 skip records
 };
 
 // shared-memory carve-up (all kernels): rows | We4 | records ... ; offsets in floats from a 128-byte aligned base
@@ -297,93 +296,6 @@ __device__ __noinline__ void fwd_overflow_tile(const WinArgs& a, const float4* W
     }
 }
 
-template <int H, int CPI, bool USE_EP>
-__global__ void __launch_bounds__(kWinThreads, kWinCtasPerSM)
-edge_win_fwd_kernel(const __grid_constant__ WinArgs a, float* __restrict__ agg, float* __restrict__ alpha) {
-    extern __shared__ __align__(128) float smem_f[];
-    const int HC = H * a.C, nq = HC >> 2, De = a.De, ld = (int)a.ld;
-    const ItemGeom ig{nq / CPI, (a.C >> 2) / CPI};
-    WinSmem s = win_carve(smem_f, a.rmax, a.ld, De, nq, H, USE_EP);
-    int2* rec_st = reinterpret_cast<int2*>(s.rec);
-    float* rec_val = s.rec + 2 * kWinMaxEdges;
-    float* rec_c = rec_val + kWinMaxEdges;                        // [kWinMaxEdges][H]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (USE_EP)
-        for (int i = tid; i < De * nq; i += kWinThreads) s.We4[i] = ld4(a.w_edge + 4 * i);
-    for (int i = tid; i < De * H; i += kWinThreads) s.Ae[i] = a.att_edge[i];
-    if (tid == 0) { tc::mbar_init(s.bar, 1); tc::fence_mbar_init(); }
-    uint32_t parity = 0;
-    __syncthreads();
-    int4 desc = blockIdx.x < a.T ? a.tiles[blockIdx.x] : make_int4(0, 0, 0, 0);
-    for (int64_t tile = blockIdx.x; tile < a.T; tile += gridDim.x) {
-        const int64_t t0 = tile * a.D;
-        const int nd = (int)min((int64_t)a.D, a.N - t0);
-        const int lo = desc.x, nrows = desc.y - desc.x, e0 = desc.z, ne = desc.w - desc.z;
-        const int64_t nxt = tile + gridDim.x;
-        if (nxt < a.T) desc = a.tiles[nxt];                         // next descriptor in flight during this tile
-        const bool overflow = ne > kWinMaxEdges;
-        const bool near = !overflow && nrows <= a.rmax && ne > 0;
-        if (near && warp == 0 && !(a.dbg & 4)) {
-            tc::fence_proxy_async_smem();
-            bulk_window(s.rows, a.xpe + (int64_t)lo * a.ld, (uint32_t)nrows * (uint32_t)ld * 4u, s.bar, lane);
-        }
-        if (tid <= nd) s.rp[tid] = a.rowptr[t0 + tid] - e0;
-        if (overflow) {
-            __syncthreads();
-            fwd_overflow_tile<H, USE_EP>(a, s.We4, s.Ae, s.rp, nd, t0, e0, agg, alpha);
-            __syncthreads();
-            continue;
-        }
-        // ---- records: one thread per edge (coalesced index / edge_attr reads; overlaps the window copy)
-        const int base = near ? lo : 0;
-        for (int e = tid; e < ((a.dbg & 8) ? 0 : ne); e += kWinThreads) {
-            const int p = e0 + e;
-            const float* earow = a.ea + (int64_t)p * De;
-            float l[H];
-#pragma unroll
-            for (int h = 0; h < H; ++h) l[h] = 0.f;
-            int nz = 0, ty = 0;
-            float val = 0.f;
-            for (int d = 0; d < De; ++d) {
-                const float v = earow[d];
-                if (v != 0.f) { ++nz; ty = d; val = v; }
-#pragma unroll
-                for (int h = 0; h < H; ++h) l[h] = fmaf(v, s.Ae[d * H + h], l[h]);
-            }
-            rec_st[e] = make_int2(a.other[p] - base, nz == 1 ? ty : -1);
-            rec_val[e] = nz == 1 ? val : 1.f;
-#pragma unroll
-            for (int h = 0; h < H; ++h) rec_c[e * H + h] = l[h];
-        }
-        __syncthreads();
-        if (near) {
-            if (!(a.dbg & 4)) {
-                tc::mbar_wait(s.bar, parity);
-                parity ^= 1u;
-            }
-            if (!(a.dbg & 1))
-                fwd_softmax<H, USE_EP, int>(s.rows, ld, (int)(t0 - lo), HC, nd, e0, a.slope, s.rp, rec_st, rec_val, rec_c, alpha);
-            __syncthreads();
-            if (!(a.dbg & 2))
-                win_aggregate<H, CPI, USE_EP, int>(s.rows, ld, nq, ig, nd, t0, De, a.ea, nullptr, e0, s.We4, s.rp, rec_st, rec_c, agg, HC);
-            else
-                for (int i = tid; i < nd * nq; i += kWinThreads) reinterpret_cast<float4*>(agg + t0 * HC)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            fwd_softmax<H, USE_EP, int64_t>(a.xpe, ld, t0, HC, nd, e0, a.slope, s.rp, rec_st, rec_val, rec_c, alpha);
-            __syncthreads();
-            win_aggregate<H, CPI, USE_EP, int64_t>(a.xpe, ld, nq, ig, nd, t0, De, a.ea, nullptr, e0, s.We4, s.rp, rec_st, rec_c, agg, HC);
-        }
-        __syncthreads();                                            // records and window are dead
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ forward, pipelined
-// Same phases as edge_win_fwd_kernel with the memory latency taken off the per-tile critical path:
-//   * two window buffers per CTA (two CTAs per SM): the bulk copy of tile k+1 is issued as soon as tile k's records are
-//     published and lands while tile k computes;
-//   * the index / edge_attr words of tile k+1 are loaded into REGISTERS during tile k (up to two edges per thread) and
-//     only turned into records at the top of tile k+1 — no global load is waited for between tiles;
-//   * the block size is chosen by the host so that the (node, item) work of a tile fills every pass.
 constexpr int kWin2CtasPerSM = 2;
 constexpr int kWin2MaxThreads = 256;      // 8 warps x 2 CTAs = 4 warps per SM sub-partition at up to 128 registers
 constexpr int kWin2SmemBudget = 108 * 1024;
@@ -850,135 +762,6 @@ __device__ __noinline__ void bwd_dst_overflow_tile(const WinArgs& a, const float
 }
 
 // smem: rows (xpe window) | We4 | Ae | rp | bar | rec4 | rec_a | rec_g | gagg [D][HC] | ovf slabs [warps][De][nq] float4
-template <int H, int CPI, bool USE_EP, int DR>
-__global__ void __launch_bounds__(kWinThreads, kWinDstCtasPerSM)
-edge_win_bwd_dst_kernel(const __grid_constant__ WinArgs a, const float* __restrict__ alpha, const float* __restrict__ g_agg,
-                        float* __restrict__ g_logit, float* __restrict__ g_xpe, float* __restrict__ gwe_partial) {
-    extern __shared__ __align__(128) float smem_f[];
-    const int HC = H * a.C, nq = HC >> 2, De = a.De, ld = (int)a.ld;
-    const ItemGeom ig{nq / CPI, (a.C >> 2) / CPI};
-    WinSmem s = win_carve(smem_f, a.rmax, a.ld, De, nq, H, USE_EP);
-    int4* rec4 = reinterpret_cast<int4*>(s.rec);
-    float* rec_a = s.rec + 4 * kWinMaxEdges;                      // [kWinMaxEdges][H]
-    float* rec_g = rec_a + kWinMaxEdges * H;                      // [kWinMaxEdges][H]
-    float* gagg = rec_g + kWinMaxEdges * H;                       // [kWinMaxTile][HC]
-    float4* ovf = reinterpret_cast<float4*>(gagg + kWinMaxTile * HC);   // [kWinWarps][De][nq]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (USE_EP)
-        for (int i = tid; i < De * nq; i += kWinThreads) s.We4[i] = ld4(a.w_edge + 4 * i);
-    for (int i = tid; i < De * H; i += kWinThreads) s.Ae[i] = a.att_edge[i];
-    if (USE_EP)
-        for (int i = tid; i < kWinWarps * De * nq; i += kWinThreads) ovf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid == 0) { tc::mbar_init(s.bar, 1); tc::fence_mbar_init(); }
-    float4 gw[DR][CPI];
-#pragma unroll
-    for (int d = 0; d < DR; ++d)
-#pragma unroll
-        for (int k = 0; k < CPI; ++k) gw[d][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t parity = 0;
-    __syncthreads();
-    int4 desc = blockIdx.x < a.T ? a.tiles[blockIdx.x] : make_int4(0, 0, 0, 0);
-    for (int64_t tile = blockIdx.x; tile < a.T; tile += gridDim.x) {
-        const int64_t t0 = tile * a.D;
-        const int nd = (int)min((int64_t)a.D, a.N - t0);
-        const int lo = desc.x, nrows = desc.y - desc.x, e0 = desc.z, ne = desc.w - desc.z;
-        const int64_t nxt = tile + gridDim.x;
-        if (nxt < a.T) desc = a.tiles[nxt];
-        const bool overflow = ne > kWinMaxEdges;
-        const bool staged = !overflow && ne > 0;
-        const bool near = staged && nrows <= a.rmax;
-        if (staged && warp == 0) {
-            tc::fence_proxy_async_smem();
-            const uint32_t wbytes = near ? (uint32_t)nrows * (uint32_t)ld * 4u : 0u, gbytes = (uint32_t)nd * (uint32_t)HC * 4u;
-            if (lane == 0) tc::mbar_expect_tx(s.bar, wbytes + gbytes);
-            __syncwarp();
-            for (uint32_t off = (uint32_t)lane * kBulkChunk; off < wbytes; off += 32u * kBulkChunk)
-                bulk_g2s(reinterpret_cast<char*>(s.rows) + off, reinterpret_cast<const char*>(a.xpe + (int64_t)lo * a.ld) + off,
-                         min(kBulkChunk, wbytes - off), s.bar);
-            for (uint32_t off = (uint32_t)lane * kBulkChunk; off < gbytes; off += 32u * kBulkChunk)
-                bulk_g2s(reinterpret_cast<char*>(gagg) + off, reinterpret_cast<const char*>(g_agg + t0 * HC) + off,
-                         min(kBulkChunk, gbytes - off), s.bar);
-        }
-        if (tid <= nd) s.rp[tid] = a.rowptr[t0 + tid] - e0;
-        __syncthreads();
-        if (overflow) {
-            bwd_dst_overflow_tile<H, USE_EP>(a, s.We4, s.Ae, s.rp, nd, t0, e0, alpha, g_agg, g_logit, g_xpe, ovf + warp * De * nq);
-            __syncthreads();
-            continue;
-        }
-        // ---- records: a thread per edge for the global words, a thread per destination for the local dst index
-        const int base = near ? lo : 0;
-        int* rec_w = reinterpret_cast<int*>(rec4);
-        for (int e = tid; e < ne; e += kWinThreads) {
-            const int p = e0 + e;
-            const float* earow = a.ea + (int64_t)p * De;
-            int nz = 0, ty = 0;
-            float val = 0.f;
-            for (int dd = 0; dd < De; ++dd) {
-                const float v = earow[dd];
-                if (v != 0.f) { ++nz; ty = dd; val = v; }
-            }
-            rec_w[4 * e + 0] = a.other[p] - base;
-            rec_w[4 * e + 2] = nz == 1 ? ty : -1;
-            rec_w[4 * e + 3] = __float_as_int(nz == 1 ? val : 1.f);
-        }
-        for (int d = tid; d < nd; d += kWinThreads)
-            for (int e = s.rp[d]; e < s.rp[d + 1]; ++e) rec_w[4 * e + 1] = d;
-        for (int i = tid; i < ne * H; i += kWinThreads) rec_a[i] = alpha[(int64_t)e0 * H + i];
-        __syncthreads();
-        if (staged) {
-            tc::mbar_wait(s.bar, parity);
-            parity ^= 1u;
-        }
-        const float4* gagg4 = reinterpret_cast<const float4*>(gagg);
-        if (near) {
-            bwd_dots<H, CPI, USE_EP, DR, int>(s.rows, ld, gagg4, nq, ig, ne, e0, De, a.ea, s.We4, rec4, rec_a, rec_g, gw);
-            __syncthreads();
-            bwd_softmax<H, int>(s.rows, ld, (int)(t0 - lo), HC, nd, t0, e0, De, a.slope, a.ea, s.Ae, s.rp, rec4, rec_a, rec_g, g_logit, g_xpe,
-                                a.ld);
-        } else {
-            bwd_dots<H, CPI, USE_EP, DR, int64_t>(a.xpe, ld, gagg4, nq, ig, ne, e0, De, a.ea, s.We4, rec4, rec_a, rec_g, gw);
-            __syncthreads();
-            bwd_softmax<H, int64_t>(a.xpe, ld, t0, HC, nd, t0, e0, De, a.slope, a.ea, s.Ae, s.rp, rec4, rec_a, rec_g, g_logit, g_xpe, a.ld);
-        }
-        __syncthreads();
-    }
-    if (USE_EP) {
-        // fixed-order reduction: lanes (edge slot, item) of every warp -> staging in the (dead) window area -> one partial per CTA
-        __syncthreads();
-        float4* stage = reinterpret_cast<float4*>(s.rows);        // [kWinWarps][epw][De][nq]
-        const int epw = 32 / ig.ni, el = lane / ig.ni, g = lane - el * ig.ni;
-        if (el < epw)
-#pragma unroll
-            for (int d = 0; d < DR; ++d)
-                if (d < De)
-#pragma unroll
-                    for (int k = 0; k < CPI; ++k) stage[((warp * epw + el) * De + d) * nq + g * CPI + k] = gw[d][k];
-        __syncthreads();
-        float4* P = reinterpret_cast<float4*>(gwe_partial) + (int64_t)blockIdx.x * De * nq;
-        for (int idx = tid; idx < De * nq; idx += kWinThreads) {
-            float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int w = 0; w < kWinWarps * epw; ++w) {
-                const float4 v = stage[w * De * nq + idx];
-                sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w;
-            }
-            for (int w = 0; w < kWinWarps; ++w) {                 // hub-tile contributions
-                const float4 v = ovf[w * De * nq + idx];
-                sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w;
-            }
-            P[idx] = sacc;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ backward, destination pass, pipelined
-// ncu on edge_win_bwd_dst_kernel: 45 % of the warp samples sit on the two DRAM round trips at the top of every tile (rowptr,
-// then the index / edge_attr / alpha words) and on the barriers behind them.  Here
-//   * the raw words of tile k+1 (rowptr slice, sources, edge_attr rows, alpha) are copied global -> shared with cp.async
-//     (LDGSTS: no registers, nothing waits) while tile k computes, and turned into records at the top of tile k+1;
-//   * the softmax phase reads s_i / s_j from the records (stashed right after the window lands), so the window and g_agg
-//     buffers are free as soon as the dots are done: the bulk copy of tile k+1 is issued THERE and overlaps the softmax
-//     phase of tile k.
 constexpr int kDstMaxEdges = 256;            // records per tile (molecular tiles: <= 4 in-edges per atom)
 
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
@@ -1382,23 +1165,6 @@ int edge_win_build_tiles(const int32_t* dst_rowptr, const int32_t* dst_src, cons
     return 0;
 }
 
-static int win_debug() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("GLAM_B200_EDGE_WIN_DEBUG");
-        v = e ? atoi(e) : 0;
-    }
-    return v;
-}
-static int win_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("GLAM_B200_EDGE_WIN");
-        v = e ? atoi(e) : 2;
-    }
-    return v;
-}
-
 // *launched = 1 when the windowed kernel took the call, 0 when the configuration does not fit (caller takes the gather path)
 int edge_win_fwd(const float* xpe, int64_t ldxp, const float* ea, const float* w_edge, const float* att_edge, const int32_t* rowptr,
                  const int32_t* srcs, const int32_t* tiles, int64_t N, int heads, int C, int De, float slope, float* agg, float* alpha,
@@ -1409,33 +1175,19 @@ int edge_win_fwd(const float* xpe, int64_t ldxp, const float* ea, const float* w
     const int D = edge_tile_rows(N);
     const int rec = 3 + heads;
     const int64_t T = (N + D - 1) / D;
-    if (win_variant() >= 2) {
-        // pipelined kernel: two window buffers, block size fitted to the (node, item) work of a tile
-        const int rmax2 = win_rmax(kWin2SmemBudget, 2 * ldxp, De, nq, use_ep, rec, 0);
-        const int items = D * ni, passes = (items + kWin2MaxThreads - 1) / kWin2MaxThreads;
-        int nthr = ((items + passes - 1) / passes + 31) / 32 * 32;
-        if (nthr < 256) nthr = 256;
-        if (rmax2 >= D + 24 && nthr <= kWin2MaxThreads && ni <= nthr) {
-            WinArgs a{xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax2, T, slope, win_debug()};
-            const size_t smem = win_smem_bytes(2 * rmax2, ldxp, De, nq, use_ep, rec, 0);
-            GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
-                auto fn = edge_win2_fwd_kernel<HH_, CPI_, UE_>;
-                win_allow_smem(fn, smem);
-                fn<<<win_grid(T, kWin2CtasPerSM), nthr, smem, stream>>>(a, agg, alpha);
-            })
-            GLAM_CHECK_LAUNCH();
-            *launched = 1;
-            return 0;
-        }
-    }
-    const int rmax = win_rmax(kWinSmemBudget, ldxp, De, nq, use_ep, rec, 0);
-    if (rmax < D + 8 || ni > kWinThreads) return 0;
-    WinArgs a{xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax, T, slope, win_debug()};
-    const size_t smem = win_smem_bytes(rmax, ldxp, De, nq, use_ep, rec, 0);
+    // pipelined kernel: two window buffers, block size fitted to the (node, item) work of a tile; configurations that do not
+    // fit (very wide rows) leave *launched = 0 and the caller takes the per-edge gather kernels
+    const int rmax2 = win_rmax(kWin2SmemBudget, 2 * ldxp, De, nq, use_ep, rec, 0);
+    const int items = D * ni, passes = (items + kWin2MaxThreads - 1) / kWin2MaxThreads;
+    int nthr = ((items + passes - 1) / passes + 31) / 32 * 32;
+    if (nthr < 256) nthr = 256;
+    if (rmax2 < D + 24 || nthr > kWin2MaxThreads || ni > nthr) return 0;
+    WinArgs a{xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax2, T, slope};
+    const size_t smem = win_smem_bytes(2 * rmax2, ldxp, De, nq, use_ep, rec, 0);
     GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
-        auto fn = edge_win_fwd_kernel<HH_, CPI_, UE_>;
+        auto fn = edge_win2_fwd_kernel<HH_, CPI_, UE_>;
         win_allow_smem(fn, smem);
-        fn<<<win_grid(a.T, kWinCtasPerSM), kWinThreads, smem, stream>>>(a, agg, alpha);
+        fn<<<win_grid(T, kWin2CtasPerSM), nthr, smem, stream>>>(a, agg, alpha);
     })
     GLAM_CHECK_LAUNCH();
     *launched = 1;
@@ -1453,49 +1205,23 @@ int edge_win_bwd_dst(const float* xpe, int64_t ldxp, const float* ea, const floa
     const int HC = heads * C, nq = HC / 4, cpi = pick_cpi(C), ni = nq / cpi;
     if (De > kWinRegDe || ni > 32) return 0;
     const int D = edge_tile_rows(N);
-    if (win_variant() >= 2) {
-        // pipelined kernel: cp.async staging of the next tile's raw words, next window issued behind the dots
-        const size_t fixed = sizeof(float) * dst2_fixed_floats(De, nq, heads, use_ep);
-        const size_t stage2 = sizeof(float4) * (size_t)kWinWarps * (32 / ni) * De * nq;
-        int rmax2 = fixed + 1024 < (size_t)kWinDstSmemBudget ? (int)(((size_t)kWinDstSmemBudget - fixed) / (sizeof(float) * (size_t)ldxp)) : 0;
-        if (rmax2 >= D + 24 && (!use_ep || (size_t)rmax2 * ldxp * 4 >= stage2)) {
-            WinArgs a{xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax2, (N + D - 1) / D,
-                      slope, win_debug()};
-            const size_t smem = fixed + sizeof(float) * (size_t)rmax2 * ldxp;
-            if (De <= 3) {
-                GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
-                    auto fn = edge_win_bwd_dst2_kernel<HH_, CPI_, UE_, 3>;
-                    win_allow_smem(fn, smem);
-                    fn<<<win_grid(a.T, kWinDstCtasPerSM), kWinThreads, smem, stream>>>(a, alpha, g_agg, g_logit, g_xpe, gwe_partial);
-                })
-            } else {
-                GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
-                    auto fn = edge_win_bwd_dst2_kernel<HH_, CPI_, UE_, kWinRegDe>;
-                    win_allow_smem(fn, smem);
-                    fn<<<win_grid(a.T, kWinDstCtasPerSM), kWinThreads, smem, stream>>>(a, alpha, g_agg, g_logit, g_xpe, gwe_partial);
-                })
-            }
-            GLAM_CHECK_LAUNCH();
-            *launched = 1;
-            return 0;
-        }
-    }
-    const int rec = 4 + 2 * heads;
-    const int extra = kWinMaxTile * HC + (use_ep ? kWinWarps * De * nq * 4 : 0);
-    const int rmax = win_rmax(kWinDstSmemBudget, ldxp, De, nq, use_ep, rec, extra);
-    const size_t stage = sizeof(float4) * (size_t)kWinWarps * (32 / ni) * De * nq;     // end-of-kernel staging lives in the window area
-    if (rmax < D + 8 || (use_ep && (size_t)rmax * ldxp * 4 < stage)) return 0;
-    WinArgs a{xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax, (N + D - 1) / D, slope, win_debug()};
-    const size_t smem = win_smem_bytes(rmax, ldxp, De, nq, use_ep, rec, extra);
+    // pipelined kernel: cp.async staging of the next tile's raw words, next window issued behind the dots
+    const size_t fixed = sizeof(float) * dst2_fixed_floats(De, nq, heads, use_ep);
+    const size_t stage2 = sizeof(float4) * (size_t)kWinWarps * (32 / ni) * De * nq;
+    int rmax2 = fixed + 1024 < (size_t)kWinDstSmemBudget ? (int)(((size_t)kWinDstSmemBudget - fixed) / (sizeof(float) * (size_t)ldxp)) : 0;
+    if (rmax2 < D + 24 || (use_ep && (size_t)rmax2 * ldxp * 4 < stage2)) return 0;
+    WinArgs a{xpe, ldxp, ea, w_edge, att_edge, rowptr, srcs, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax2, (N + D - 1) / D,
+              slope};
+    const size_t smem = fixed + sizeof(float) * (size_t)rmax2 * ldxp;
     if (De <= 3) {
         GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
-            auto fn = edge_win_bwd_dst_kernel<HH_, CPI_, UE_, 3>;
+            auto fn = edge_win_bwd_dst2_kernel<HH_, CPI_, UE_, 3>;
             win_allow_smem(fn, smem);
             fn<<<win_grid(a.T, kWinDstCtasPerSM), kWinThreads, smem, stream>>>(a, alpha, g_agg, g_logit, g_xpe, gwe_partial);
         })
     } else {
         GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
-            auto fn = edge_win_bwd_dst_kernel<HH_, CPI_, UE_, kWinRegDe>;
+            auto fn = edge_win_bwd_dst2_kernel<HH_, CPI_, UE_, kWinRegDe>;
             win_allow_smem(fn, smem);
             fn<<<win_grid(a.T, kWinDstCtasPerSM), kWinThreads, smem, stream>>>(a, alpha, g_agg, g_logit, g_xpe, gwe_partial);
         })
@@ -1516,7 +1242,7 @@ int edge_win_bwd_src(const float* ea, const float* w_edge, const float* alpha, c
     const int rmax = win_rmax(kWinSmemBudget, HC, De, nq, use_ep, rec, 0);
     if (rmax < D + 8 || nq / cpi > kWinThreads) return 0;
     WinArgs a{nullptr, ldxp, ea, w_edge, nullptr, src_rowptr, src_dst, reinterpret_cast<const int4*>(tiles), N, C, De, D, rmax,
-              (N + D - 1) / D, 0.f, win_debug()};
+              (N + D - 1) / D, 0.f};
     const size_t smem = win_smem_bytes(rmax, HC, De, nq, use_ep, rec, 0);
     GLAM_WIN_DISPATCH(heads, use_ep, cpi, {
         auto fn = edge_win_bwd_src_kernel<HH_, CPI_, UE_>;

@@ -10,8 +10,9 @@ GlobalLAPool / Set2Set and dot_and_global_pool2 runs in hand-written sm_100a ker
 (include/glam_b200.h).  There is no CPU path: CPU tensors raise.
 
 Out of the hot path and therefore plain torch here: the norm wrappers, dropout,
-activations, `LinearBlock`, `GlobalPool5`.  `_NNConv/_GCNConv/_GATConv` are third-party PyG layers and are
-not provided.
+activations and the wide graph-level `LinearBlock`s.  The reference's defaults `_NNConv`, `_GCNConv` and
+`GlobalPool5` run on the library too; `_GATConv` is a third-party PyG layer outside the path
+and raises at construction.
 """
 from __future__ import annotations
 
@@ -230,6 +231,9 @@ class NNConv(nn.Module):
         self.reset_parameters()
 
     def reset_parameters(self):
+        for m in self.nn.modules():                          # PyG: reset(self.nn) first, then root and bias (same RNG order)
+            if m is not self.nn and hasattr(m, "reset_parameters"):
+                m.reset_parameters()
         bound = 1.0 / (self.in_channels ** 0.5)
         nn.init.uniform_(self.root, -bound, bound)
         zeros_(self.bias)
@@ -492,7 +496,7 @@ class MessageBlock(nn.Module):
     """One message-passing step: norm -> dropout -> conv -> CELU -> GRU -> (+identity) -> act
     (src_1gp/layer.py:240-267).  forward(x, edge_index, edge_attr, h=None, batch=None) -> (x, h)."""
 
-    def __init__(self, in_dim=32, out_dim=64, in_edge_dim=13, norm="_None", dropout="Dropout(0.2)", conv="_TripletMessage",
+    def __init__(self, in_dim=32, out_dim=64, in_edge_dim=13, norm="_None", dropout="Dropout(0.2)", conv="_NNConv",
                  act="ReLU", res=True):
         super().__init__()
         self.norm = _NORMS[norm](in_channels=in_dim)

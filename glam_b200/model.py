@@ -46,10 +46,11 @@ class _Tower(object):
 
 class ArchitectureGP(nn.Module):
     def __init__(self, mol_in_dim=15, mol_edge_in_dim=4, hid_dim_alpha=4, e_dim=1024, out_dim=1,
-                 mol_block="_TripletMessage", message_steps=3, mol_readout="Set2Set",
+                 mol_block="_NNConv", message_steps=3, mol_readout="GlobalPool5",
                  pre_norm="_None", graph_norm="_None", flat_norm="_None", end_norm="_None",
                  pre_do="_None()", graph_do="Dropout(0.2)", flat_do="_None()", end_do="Dropout(0.2)",
                  pre_act="RReLU", graph_act="RReLU", flat_act="RReLU", graph_res=True):
+        # defaults = the reference's (src_1gp/model.py:24-33), so a default-constructed model loads a reference checkpoint
         super().__init__()
         hid = mol_in_dim * hid_dim_alpha
         self.mol_lin0 = LinearBlock(mol_in_dim, hid, norm=pre_norm, dropout=pre_do, act=pre_act)
@@ -120,11 +121,11 @@ class ArchitectureDDI(_PairArchitecture):
     prefixes = ("mol1", "mol2")
 
     def __init__(self, mol_in_dim=15, mol_edge_in_dim=4, hid_dim_alpha=4, e_dim=1024, out_dim=1,
-                 mol_block="_TripletMessage", message_steps=3, mol_readout="Set2Set",
+                 mol_block="_NNConv", message_steps=3, mol_readout="GlobalPool5",
                  pre_norm="_None", graph_norm="_None", flat_norm="_None", end_norm="_None",
                  pre_do="_None()", graph_do="Dropout(0.2)", flat_do="_None()", end_do="Dropout(0.2)",
                  pre_act="RReLU", graph_act="RReLU", flat_act="RReLU", end_act="RReLU", graph_res=True):
-        super().__init__()
+        super().__init__()                                   # defaults: src_2gi_ddi/model.py:10-19
         self._build((mol_in_dim, mol_in_dim), (mol_edge_in_dim, mol_edge_in_dim), (mol_block, mol_block),
                     (mol_readout, mol_readout), mol_in_dim * hid_dim_alpha, e_dim, out_dim, message_steps,
                     (pre_norm, graph_norm, flat_norm, end_norm), (pre_do, graph_do, flat_do, end_do),
@@ -135,7 +136,7 @@ class ArchitectureDTI(_PairArchitecture):
     prefixes = ("mol", "pro")
 
     def __init__(self, mol_in_dim=15, pro_in_dim=49, mol_edge_in_dim=4, pro_edge_in_dim=8, hid_dim_alpha=4, e_dim=1024,
-                 out_dim=1, mol_block="_TripletMessage", pro_block="_GCNConv", message_steps=3,
+                 out_dim=1, mol_block="_NNConv", pro_block="_GCNConv", message_steps=3,
                  mol_readout="GlobalPool5", pro_readout="GlobalPool5",
                  pre_norm="_None", graph_norm="_None", flat_norm="_None", end_norm="_None",
                  pre_do="_None()", graph_do="Dropout(0.2)", flat_do="_None()", end_do="Dropout(0.2)",

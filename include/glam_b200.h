@@ -280,8 +280,9 @@ int glam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
  * stay resident from step to step.  xp [N,HC+2H] and agg [N,HC] never reach HBM (unless saved for backward).
  *
  * glam_build_graph_tiles — greedy packing of consecutive whole graphs (graph_ptr, B+1 entries) into tiles of
- *   <= max_nodes rows and <= max_edges in-edges (glam_graph_tile_caps).  tiles: 4*B int32 {n0, n1, e0, e1} per tile, 16-byte
- *   aligned; meta: int32[4], ZEROED by the caller: meta[0] = tile count, meta[1] = OR of precondition violations
+ *   <= max_nodes rows and <= max_edges in-edges (glam_graph_tile_caps), 64 graphs per packing chunk (tiles do not span
+ *   chunks).  tiles: 4*max(B, 64*ceil(B/64)) int32 {n0, n1, e0, e1} per tile, 16-byte aligned; workspace >=
+ *   glam_graph_tiles_workspace_bytes(B); meta: int32[4], ZEROED by the caller: meta[0] = tile count, meta[1] = OR of precondition violations
  *   (1 a graph has more rows than a tile, 2 more in-edges than a tile, 4 an edge crosses tiles i.e. graphs,
  *   8 an edge_attr row is not one-hot).  glam_edge_types — bond type per dst-ordered edge (index of the 1 in the
  *   one-hot row, src_1gp/dataset.py:82), ORs 8 into meta[1] otherwise.
@@ -296,8 +297,10 @@ int glam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
  *   glam_message_stack_supported: tf32 math mode, heads == 3, channels in {32,36,40}, edge_dim <= 4.
  * --------------------------------------------------------------------------------------------- */
 int glam_graph_tile_caps(int* max_nodes, int* max_edges);
+size_t glam_graph_tiles_workspace_bytes(int64_t num_graphs);
 int glam_build_graph_tiles(const int32_t* graph_ptr, int64_t num_graphs, const int32_t* dst_rowptr, const int32_t* dst_src,
-                           int64_t num_nodes, int64_t num_edges, int32_t* tiles, int32_t* meta, void* stream);
+                           int64_t num_nodes, int64_t num_edges, int32_t* tiles, int32_t* meta, void* workspace,
+                           size_t workspace_bytes, void* stream);
 int glam_edge_types(const float* edge_attr_sorted, int64_t num_edges, int edge_dim, uint8_t* etype, int32_t* meta, void* stream);
 int glam_message_stack_supported(int channels, int heads, int edge_dim);
 int glam_message_stack_fwd(const float* x0, const float* h0, const float* w_ext, int64_t ldw, const float* w_edge,

@@ -94,9 +94,12 @@ class NNConv(MessagePassing):
         self.in_channels, self.out_channels, self.nn = in_channels, out_channels, nn
         self.root = Parameter(torch.Tensor(in_channels, out_channels))
         self.bias = Parameter(torch.Tensor(out_channels))
+        for m in nn.modules():                               # reset_parameters @1.7.2: reset(nn); uniform(in, root); zeros(bias)
+            if m is not nn and hasattr(m, "reset_parameters"):
+                m.reset_parameters()
         bound = 1.0 / math.sqrt(in_channels)
         self.root.data.uniform_(-bound, bound)
-        self.bias.data.zero_()                               # reset_parameters @1.7.2: uniform(in, root); zeros(bias)
+        self.bias.data.zero_()
 
     def forward(self, x, edge_index, edge_attr=None, size=None):
         out = self.propagate(edge_index, x=x, edge_attr=edge_attr, size=size)

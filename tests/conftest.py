@@ -56,3 +56,22 @@ def math_mode(request):
     yield request.param
     _lib.set_math_mode("tf32")
     helpers.MATH_MODE["mode"] = "fp32"
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Realised parity errors of the run (tests/helpers.tol_check): the largest error / tensor-scale per math mode, next to the
+    bound that was applied — so a loose bound cannot hide a large error."""
+    try:
+        import helpers
+    except ImportError:
+        return
+    if not helpers.REALISED:
+        return
+    tr = terminalreporter
+    for mode in ("fp32", "tf32"):
+        rows = sorted((r for r in helpers.REALISED if r[1] == mode), key=lambda r: -r[2])
+        if not rows:
+            continue
+        tr.write_line(f"parity, {mode} mode: {len(rows)} tensors checked; largest realised |err| / scale:")
+        for name, _, e, b in rows[:8]:
+            tr.write_line(f"    {e:9.2e}  (bound {b:8.2e})  {name}")

@@ -22,10 +22,16 @@ def ns(x, edge_index, edge_attr, batch):
     return types.SimpleNamespace(x=x, edge_index=edge_index, edge_attr=edge_attr, batch=batch)
 
 
-# TF32 projections (10-bit mantissa operands, fp32 accumulate): stated tolerance 1e-2 of the tensor scale for
-# outputs and gradients of multi-step models ("TF32 projections: rtol 2e-3" per contraction).
+# TF32 projections (10-bit mantissa operands, fp32 accumulate).  SURVEY.md §8c states "TF32 projections: rtol 2e-3" PER
+# CONTRACTION; a model output / gradient is a chain of 10-20 of them (3 message steps x {node, scale, 2 GRU products} + readout),
+# whose rounding errors add, so the stated tolerance for multi-step outputs and gradients is 1e-2 of the tensor scale.  Some
+# gradients amplify operand rounding further (zero-sum softmax gradients, S.max() routing of the dot-pool): there the bound is
+# 4x what TF32 operand truncation alone does to the fp64 ORACLE (the reference's own sensitivity), and never more than TF32_CAP.
+# Every check records its realised error; the session prints the largest ones (conftest.py) so that the slack is visible.
 TF32_RTOL = 1e-2
+TF32_CAP = 1e-1
 MATH_MODE = {"mode": "fp32"}
+REALISED = []          # (name, mode, err / scale, bound / scale)
 
 
 def tf32_emulated(fn):
@@ -48,6 +54,7 @@ def tol_check(ours, ref32, ref64, name="", rtol=1e-4, atol=1e-5, emu64=None):
         rtol = max(rtol, TF32_RTOL) if rtol < TF32_RTOL else rtol
         if emu64 is not None:
             extra = 4 * (emu64.double().cpu() - ref64.double().cpu()).abs().max()
+            extra = torch.minimum(extra, TF32_CAP * ref64.double().cpu().abs().max())
     """SURVEY.md §8c tolerance: |ours - ref64| <= max(2*|ref32 - ref64|, atol + rtol*|ref64|), evaluated with a
     tensor-level scale so that near-zero entries are judged against the magnitude of the tensor."""
     o, r32, r64 = ours.double().cpu(), ref32.double().cpu(), ref64.double().cpu()
@@ -55,5 +62,6 @@ def tol_check(ours, ref32, ref64, name="", rtol=1e-4, atol=1e-5, emu64=None):
     err = (o - r64).abs().max()
     base = (r32 - r64).abs().max()
     bound = torch.maximum(torch.maximum(2 * base, atol + rtol * scale), torch.as_tensor(extra, dtype=torch.float64))
+    REALISED.append((name, MATH_MODE["mode"], float(err / scale), float(bound / scale)))
     assert err <= bound, (f"{name}: err {err:.3e} > bound {bound:.3e} (fp32-ref err {base:.3e}, scale {scale:.3e}, "
                           f"4x tf32-oracle deviation {float(extra):.3e})")

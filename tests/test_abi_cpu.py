@@ -86,7 +86,7 @@ def test_state_dict_keys_match_reference(golden_models):
     for k, v in m.state_dict().items():
         assert v.shape == c["state"][k].shape, k
     d = golden_models["ddi_set2set"]
-    m2 = model.ArchitectureDDI(9, 3, e_dim=32)
+    m2 = model.ArchitectureDDI(9, 3, e_dim=32, mol_block="_TripletMessage", mol_readout="Set2Set")
     assert list(m2.state_dict().keys()) == list(d["state"].keys())
     c2 = golden_models["gp_lapool_light"]
     m3 = model.ArchitectureGP(15, 4, e_dim=32, mol_readout="GlobalLAPool", mol_block="_TripletMessageLight")

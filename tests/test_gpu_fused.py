@@ -28,9 +28,9 @@ def _batch(n_graphs, node_dim, edge_dim, seed, **kw):
 
 # ---------------------------------------------------------------------------------------------- tiles
 def _host_tiles(gptr, rowptr, max_nodes, max_edges):
-    """The definition: greedy packing of consecutive graphs, chunked as the kernel chunks them (G graphs per packer)."""
+    """The definition: greedy packing of consecutive graphs, in chunks of 64 graphs (tiles do not span chunks)."""
     B = len(gptr) - 1
-    Gc = max((B + 1023) // 1024, 64)
+    Gc = 64
     tiles = []
     for c0 in range(0, B, Gc):
         g, g1 = c0, min(B, c0 + Gc)
@@ -349,3 +349,61 @@ def test_screen_step_fused_matches_oracle_and_eager():
     finally:
         layer.USE_FUSED_STACK = True
     assert _rel(got, ref) < 2e-4
+
+
+# ---------------------------------------------------------------------------------------------- train-mode randomness
+@pytest.mark.parametrize("graph_do,graph_act,pre_act", [("Dropout(0.2)", "CELU", "ReLU"), ("_None()", "RReLU", "ReLU"),
+                                                        ("Dropout(0.2)", "RReLU", "RReLU")])
+def test_train_mode_dropout_and_rrelu_against_oracle_replay(graph_do, graph_act, pre_act, math_mode):
+    """The reference's default train-mode randomness — Dropout(0.2) on the block input (src_1gp/run.py:31-34) and RReLU
+    activations (run.py:35-37) — with the SAME random draws replayed into the oracle: the oracle is pure torch, so it runs on the
+    GPU too; seeded identically it issues the same philox-consuming ops (same op, same element count, same order) and therefore
+    sees the same dropout masks and RReLU slopes.  Outputs and every parameter gradient must agree."""
+    from glam_b200 import model
+    from oracle import glam_oracle as O
+    kw = dict(hid_dim_alpha=4, e_dim=64, out_dim=1, mol_block="_TripletMessage", message_steps=3, mol_readout="Set2Set",
+              pre_act=pre_act, graph_act=graph_act, flat_act="ReLU", graph_do=graph_do, flat_do="_None()", end_do="Dropout(0.2)")
+    torch.manual_seed(11)
+    o = O.ArchitectureGP(9, 3, **kw)
+    m = model.ArchitectureGP(9, 3, **kw)
+    m.load_state_dict(o.state_dict())
+    o, m = o.to(DEV).train(), m.to(DEV).train()
+    b = _batch(96, 9, 3, 21).to(DEV)
+    tf32_was = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False                        # the oracle replay is the exact-fp32 reference
+    try:
+        torch.manual_seed(77)
+        ref = o(b)
+        torch.nn.functional.mse_loss(ref, b.y).backward()
+        torch.manual_seed(77)
+        out = m(b)
+        torch.nn.functional.mse_loss(out, b.y).backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32_was
+    tol = 2e-4 if math_mode == "fp32" else 1e-2
+    e = _rel(out, ref)
+    print(f"{graph_do} {graph_act} [{math_mode}]: output rel err {e:.2e}")
+    assert e < tol
+    for (n, p), q in zip(m.named_parameters(), o.parameters()):
+        eg = _rel(p.grad, q.grad)
+        assert eg < (2e-3 if math_mode == "fp32" else 5e-2), f"grad {n}: {eg:.3e}"
+
+
+def test_reference_loop_matches_stacked_path():
+    """glam_b200.model with stack_steps=False steps the block exactly as the reference's model.py does (src_1gp/model.py:52-54:
+    `xm, hm = self.mol_conv(xm, edge_index, edge_attr, h=hm, batch=batch)` three times): same outputs and gradients as the
+    one-node stacked path."""
+    o32, m = _gp_pair(64, seed=5)
+    b = _batch(64, 9, 3, 8).to(DEV)
+    res = []
+    for stack in (True, False):
+        m.stack_steps = stack
+        for p in m.parameters():
+            p.grad = None
+        out = m.train()(b)
+        torch.nn.functional.mse_loss(out, b.y).backward()
+        res.append((out.detach().clone(), [p.grad.clone() for p in m.parameters()]))
+    assert _rel(res[1][0], res[0][0]) < 2e-4
+    for a, c in zip(res[1][1], res[0][1]):
+        assert _rel(a, c) < 2e-3
+    assert _rel(res[0][0], o32(b.to("cpu"))) < 2e-3

@@ -84,7 +84,8 @@ def test_graph_ptr_and_gather():
 
 
 # ---------------------------------------------------------------------------------------------- dense pieces
-@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (63, 36, 36), (1000, 116, 36), (777, 60, 180), (4096, 188, 60), (130, 270, 90)])
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (63, 36, 36), (1000, 116, 36), (777, 60, 180), (4096, 188, 60), (130, 270, 90),
+                                   (5000, 36, 9), (3000, 60, 15), (2500, 12, 40)])
 def test_gemm_variants(M, N, K, math_mode):
     from glam_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
@@ -280,7 +281,8 @@ def test_model_ddi_golden(golden_models, math_mode):
     c = golden_models["ddi_set2set"]
     cfg = c["cfg"]
     m = model.ArchitectureDDI(cfg["Din"], cfg["De"], hid_dim_alpha=4, e_dim=cfg["e_dim"], out_dim=1, graph_do="_None()",
-                              end_do="_None()", pre_act="ReLU", graph_act="ReLU", flat_act="CELU", end_act="ReLU")
+                              end_do="_None()", pre_act="ReLU", graph_act="ReLU", flat_act="CELU", end_act="ReLU",
+                              mol_block="_TripletMessage", mol_readout="Set2Set")
     m = _load(m, c["state"]).eval()
     o64 = O.ArchitecturePair(cfg["Din"], cfg["Din"], cfg["De"], cfg["De"], prefixes=("mol1", "mol2"), hid_dim_alpha=4,
                              e_dim=cfg["e_dim"], out_dim=1, graph_act="ReLU", pre_act="ReLU", flat_act="CELU", end_act="ReLU")
@@ -358,8 +360,8 @@ def test_dti_shaped_pair_vs_oracle(math_mode):
     kw = dict(hid_dim_alpha=2, e_dim=64, out_dim=2, message_steps=2)
     o32 = O.ArchitecturePair(15, 49, 4, 8, prefixes=("mol", "pro"), graph_act="CELU", **kw).eval()
     m = model.ArchitectureDTI(15, 49, 4, 8, graph_do="_None()", end_do="_None()", pre_act="ReLU", graph_act="CELU",
-                              flat_act="ReLU", end_act="ReLU", pro_block="_TripletMessage", mol_readout="Set2Set",
-                              pro_readout="Set2Set", **kw)
+                              flat_act="ReLU", end_act="ReLU", mol_block="_TripletMessage", pro_block="_TripletMessage",
+                              mol_readout="Set2Set", pro_readout="Set2Set", **kw)
     m.load_state_dict(o32.state_dict())
     m = m.to(DEV).eval()
     o64 = copy.deepcopy(o32).double()
