@@ -26,9 +26,26 @@ def _tup(b):
     return tuple(b) if isinstance(b, (tuple, list)) else (b,)
 
 
+_GRAPH_FIELDS = ("x", "edge_index", "edge_attr", "batch", "y")
+
+
+def _fields(g):
+    from .packed import FIELDS, PackedBatch
+    return FIELDS if isinstance(g, PackedBatch) else _GRAPH_FIELDS
+
+
 def _static_like(b, device):
+    from .packed import PackedBatch
     z = lambda t: None if t is None else torch.empty_like(t, device=device)
-    return tuple(GraphBatch(z(g.x), z(g.edge_index), z(g.edge_attr), z(g.batch), z(g.y), g.num_graphs) for g in _tup(b))
+    return tuple(g._map(z) if isinstance(g, PackedBatch) else
+                 GraphBatch(z(g.x), z(g.edge_index), z(g.edge_attr), z(g.batch), z(g.y), g.num_graphs) for g in _tup(b))
+
+
+def _model_args(static):
+    """What the model is called with: packed batches (glam_b200/packed.py) are unpacked on the device first — inside the
+    captured graph, so a replay consumes whatever packed bytes were copied into the static buffers."""
+    from .packed import PackedBatch
+    return tuple(g.unpack() if isinstance(g, PackedBatch) else g for g in static)
 
 
 def _copy_into(dst, src) -> int:
@@ -38,7 +55,7 @@ def _copy_into(dst, src) -> int:
     if len(dst) != len(src):
         raise ValueError(f"the captured step takes {len(dst)} graph batches per call, got {len(src)}")
     for dg, sg in zip(dst, src):
-        for name in ("x", "edge_index", "edge_attr", "batch", "y"):
+        for name in _fields(sg):
             s, d = getattr(sg, name), getattr(dg, name)
             if s is None:
                 continue
@@ -274,7 +291,7 @@ class ScreenStep:
                 with torch.cuda.stream(s):
                     for _ in range(max(warmup, 1)):
                         G.clear_caches()
-                        self.model(*self.static)
+                        self.model(*_model_args(self.static))
                 torch.cuda.current_stream(self.device).wait_stream(s)
                 torch.cuda.synchronize(self.device)
                 pool = None
@@ -282,7 +299,7 @@ class ScreenStep:
                     G.clear_caches()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, pool=pool):
-                        self.outs[i] = self.model(*st)
+                        self.outs[i] = self.model(*_model_args(st))
                     pool = g.pool()
                     self.graphs.append(g)
                 G.clear_caches()
@@ -298,7 +315,7 @@ class ScreenStep:
         else:
             with torch.no_grad():
                 G.clear_caches()
-                self.outs[self._slot] = self.model(*self.statics[self._slot])
+                self.outs[self._slot] = self.model(*_model_args(self.statics[self._slot]))
         return self.outs[self._slot]
 
     def step(self, batch: GraphBatch, prefetch: Optional[GraphBatch] = None) -> torch.Tensor:

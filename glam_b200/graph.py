@@ -129,7 +129,9 @@ def _capturing() -> bool:
     return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
 
 
-def graph_index(edge_index: torch.Tensor, num_nodes: int) -> GraphIndex:
+def graph_index(edge_index, num_nodes: int):
+    if not torch.is_tensor(edge_index):                  # packed store: the index came prebuilt (glam_b200/packed.py)
+        return edge_index
     key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), int(num_nodes), edge_index.device)
     hit = _graph_cache.get(key)
     if hit is not None:
@@ -145,6 +147,8 @@ def graph_index(edge_index: torch.Tensor, num_nodes: int) -> GraphIndex:
 def graph_ptr(batch: torch.Tensor, num_graphs: Optional[int] = None):
     """(graph_ptr int32 [B+1], B).  `num_graphs=None` reads batch[-1] back to the host once per batch tensor
     (the reference does `batch.max().item()` on every readout call)."""
+    if not torch.is_tensor(batch):                       # packed store: graph offsets came prebuilt
+        return batch.index.gptr, batch.index.num_graphs
     key = (batch.data_ptr(), batch._version, tuple(batch.shape), num_graphs, batch.device)
     hit = _ptr_cache.get(key)
     if hit is not None:

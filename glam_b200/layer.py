@@ -527,7 +527,6 @@ class MessageBlock(nn.Module):
             return (xs if keep == "all" else xs[-1:]), h
         p_drop = float(drop.p) if (isinstance(drop, nn.Dropout) and self.training) else 0.0
         g = G.graph_index(edge_index, x.shape[0])
-        ea = g.sorted_edge_attr(edge_attr)
         w_ext, att_edge = inner.derived()
         gru = self.gru
         fi = _fused_index(g, x, edge_attr, batch, num_graphs, inner.heads, inner.node_channels) if p_drop == 0.0 else None
@@ -538,6 +537,7 @@ class MessageBlock(nn.Module):
                 gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, g, fi, inner.heads, inner.node_channels,
                 int(steps), inner.negative_slope, fused[0], fused[1], bool(self.res), keep_all=(keep == "all"))
             return list(x_out.unbind(0)), h_out.unsqueeze(0)
+        ea = g.sorted_edge_attr(edge_attr)
         out = Fn.MessageStackFn.apply(
             x, w_ext, inner.weight_edge, att_edge, inner.weight_scale, inner.bias,
             gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, ea, g,

@@ -261,13 +261,13 @@ def graph_tile_caps():
     return a.value, b.value
 
 
-def build_graph_tiles(gptr: torch.Tensor, num_graphs: int, g, meta: torch.Tensor) -> torch.Tensor:
+def build_graph_tiles(gptr: torch.Tensor, num_graphs: int, g, meta: torch.Tensor, check_edges: bool = True) -> torch.Tensor:
     """Graph-aligned tiles {n0, n1, e0, e1} (int32 [B,4]; meta[0] of them are valid) for the fused message kernel."""
     _need_cuda(gptr)
     B = int(num_graphs)
     tiles = torch.empty((max((B + 63) // 64 * 64, 64), 4), dtype=torch.int32, device=gptr.device)
     ws = _ws(_lib.load().glam_graph_tiles_workspace_bytes(B), gptr.device)
-    _call("glam_build_graph_tiles", _p(gptr), B, _p(g.dst_rowptr), _p(g.dst_src), g.num_nodes, g.num_edges,
+    _call("glam_build_graph_tiles", _p(gptr), B, _p(g.dst_rowptr), _p(g.dst_src if check_edges else None), g.num_nodes, g.num_edges,
           _p(tiles), _p(meta), _p(ws), ws.numel(), _stream(gptr))
     return tiles
 

@@ -313,6 +313,19 @@ int glam_message_stack_fwd(const float* x0, const float* h0, const float* w_ext,
                            float* save_xpe, float* save_agg, float* save_alpha, float* save_m, float* save_rzn,
                            float* save_gh, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (9) Packed graph store -> device index (csrc/packed.cu).  The reference ships every batch as fp32
+ * features + int64 edge_index + fp32 one-hot edge_attr + int64 batch (src_1gp/dataset.py:60-97 + Batch.from_data_list,
+ * ~2.6 KB per 25-atom molecule) and the index is rebuilt from it per batch.  The packed store (glam_b200/packed.py) keeps the
+ * dst-sorted in-edge lists with graph-local uint8 source ids, uint8 bond types / degrees / atom features (~360 B per
+ * molecule); unpacking is two scans + a warp per graph and yields graph_ptr [B+1], dst_rowptr [N+1], dst_src [E]
+ * (bit-identical to glam_graph_ptr / glam_build_csr on the raw batch) and x [N,node_dim] fp32.  edge_ptr [B+1]: scratch
+ * (first in-edge of every graph).  The bond types feed glam_message_stack_fwd as they are.
+ * --------------------------------------------------------------------------------------------- */
+int glam_unpack_graphs(const uint8_t* n_g, const uint16_t* e_g, const uint8_t* deg, const uint8_t* nbr, const uint8_t* xq,
+                       int64_t num_graphs, int64_t num_nodes, int64_t num_edges, int node_dim, int32_t* graph_ptr,
+                       int32_t* edge_ptr, int32_t* dst_rowptr, int32_t* dst_src, float* x, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
