@@ -20,6 +20,17 @@ from . import graph as G
 from .synth import GraphBatch
 
 
+def _on_device(model: torch.nn.Module, device: torch.device) -> torch.nn.Module:
+    """Move the model only if it is not there yet.  `module.to()` is NOT a no-op for a model that already lives on the device:
+    nn.GRU / nn.LSTM re-flatten their weights into a freshly allocated buffer on every `_apply`, i.e. the parameters MOVE —
+    which would leave every previously captured CUDA graph (and FlatAdam's parameter views) pointing at freed memory."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else (torch.cuda.current_device() if dev.type == "cuda" else None)
+    there = all(t.device.type == dev.type and (idx is None or t.device.index == idx)
+                for t in list(model.parameters()) + list(model.buffers()))
+    return model if there else model.to(dev)
+
+
 def _tup(b):
     """A step's input is one GraphBatch (GLAM-GP) or a tuple of them (the two towers of GLAM-DDI / GLAM-DTI: the model is
     called as model(*batches), the target is the first batch's y)."""
@@ -157,7 +168,7 @@ class TrainStep:
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, example: GraphBatch, lr: float = 1e-3,
                  device="cuda", world_size: int = 1, use_cuda_graph: bool = True, warmup: int = 3,
                  double_buffer: bool = False):
-        self.model = model.to(device)
+        self.model = _on_device(model, device)
         self.loss_fn = loss_fn
         self.device = torch.device(device)
         self.world = world_size
@@ -270,7 +281,7 @@ class ScreenStep:
 
     def __init__(self, model: torch.nn.Module, example: GraphBatch, device="cuda", use_cuda_graph: bool = True,
                  warmup: int = 3, double_buffer: bool = False):
-        self.model = model.to(device).eval()
+        self.model = _on_device(model, device).eval()
         self.device = torch.device(device)
         self.statics = [_static_like(example, self.device) for _ in range(2 if double_buffer else 1)]
         for st in self.statics:

@@ -468,3 +468,23 @@ def test_screening_from_packed_store_matches_raw_fields():
         got = pk.step(pks[i], prefetch=pks[(i + 1) % 3]).clone()
         assert torch.equal(got, want), i
         assert _rel(got, o32(b)) < 2e-3
+
+
+def test_screen_step_after_train_step_leaves_parameters_in_place():
+    """nn.GRU / nn.LSTM re-flatten (re-allocate) their weights on every module.to(): building a ScreenStep on a model that a
+    TrainStep already captured must not move a single parameter (captured graphs and FlatAdam's views point at them)."""
+    from glam_b200.engine import ScreenStep, TrainStep
+    _, m = _gp_pair(64, seed=2)
+    b = _batch(64, 9, 3, 4, total_nodes=25 * 64, total_edges=54 * 64).to(DEV)
+    ts = TrainStep(m.train(), torch.nn.functional.mse_loss, b, device=DEV)
+    ptrs = [p.data_ptr() for p in m.parameters()]
+    l0 = float(ts.step(b))
+    ss = ScreenStep(m, b, device=DEV)
+    assert [p.data_ptr() for p in m.parameters()] == ptrs
+    lo, hi = ts.opt.flat.data_ptr(), ts.opt.flat.data_ptr() + ts.opt.flat.numel() * 4
+    assert all(lo <= q < hi for q in ptrs)
+    s0 = ss.step(b).clone()
+    m.train()
+    l1 = float(ts.step(b))                                       # the captured training step still sees (and updates) the weights
+    assert l1 != l0 and torch.isfinite(torch.tensor(l1))
+    assert not torch.equal(ss.step(b), s0)                       # ... and the captured screening step sees the update
