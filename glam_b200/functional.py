@@ -228,13 +228,14 @@ class MessageBlockFn(Function):
 class MessageStackFn(Function):
     @staticmethod
     def forward(ctx, x0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, ea, g,
-                heads, channels, slope, act, act_param, res, steps, p_drop, fi):
+                heads, channels, slope, act, act_param, res, steps, p_drop, fi, pn=None):
+        """pn = (graph_ptr, num_graphs, eps): PairNorm on every step's block input (src_1gp/layer.py:255) inside the node."""
         (x0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh) = map(
             _c, (x0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh))
         ops._need_cuda(x0, w_ext)
         N, C = x0.shape
         S, H, HC, ld, E, dev = steps, heads, heads * channels, w_ext.shape[1], ea.shape[0], x0.device
-        if fi is not None and p_drop == 0.0:
+        if fi is not None and p_drop == 0.0 and pn is None:
             # ONE launch for all steps (csrc/mp_fused.cu): x and h stay in shared memory from step to step; what backward
             # reads leaves the SM as tile-sized contiguous copies
             sv = _stack_buffers(x0, S, H, channels, ld, E)
@@ -242,8 +243,8 @@ class MessageStackFn(Function):
                                   slope, act, act_param, res, save=sv)
             X, HH = sv["X"], sv["HH"]
             ctx.save_for_backward(w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ea, X, HH, X, None, sv["XPE"], sv["AGG"],
-                                  sv["ALPHA"], sv["M"], sv["RZN"], sv["GH"])
-            ctx.g, ctx.cfg = g, (H, channels, slope, act, act_param, res, S, p_drop)
+                                  sv["ALPHA"], sv["M"], sv["RZN"], sv["GH"], None)
+            ctx.g, ctx.cfg = g, (H, channels, slope, act, act_param, res, S, p_drop, None)
             ctx.set_materialize_grads(False)
             return tuple(X[s + 1] for s in range(S)) + (HH[S],)
         new = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype, device=dev)
@@ -251,14 +252,17 @@ class MessageStackFn(Function):
         X[0].copy_(x0)
         HH[0].copy_(x0)                                          # h = x.unsqueeze(0) on the first step (layer.py:254)
         drop = p_drop > 0.0
-        XD = new(S, N, C) if drop else X                         # conv inputs (after dropout)
+        XN = new(S, N, C) if pn is not None else X               # block inputs after PairNorm
+        XD = new(S, N, C) if drop else XN                        # conv inputs (after dropout)
         MASK = new(S, N, C, dtype=torch.bool) if drop else None
         XPE, AGG, ALPHA = new(S, N, ld), new(S, N, HC), new(S, E, H)
         fused_gru = ops.gru_fused_supported(XPE[0], HH[0], C)        # then only the n-gate part of gh is kept: [N,C]
         M, RZN, GH = new(S, N, C), new(S, N, 3 * C), new(S, N, C if fused_gru else 3 * C)
         for s in range(S):
+            if pn is not None:
+                ops.pair_norm_fwd(X[s], pn[0], pn[1], pn[2], out=XN[s])
             if drop:
-                torch.ops.aten.native_dropout.out(X[s], p_drop, True, out0=XD[s], out1=MASK[s])
+                torch.ops.aten.native_dropout.out(XN[s], p_drop, True, out0=XD[s], out1=MASK[s])
             ops.gemm(XD[s], w_ext, exact_cols=(HC, HC + 2 * H), out=XPE[s])
             ops.triplet_edge_fwd(XPE[s], ea, w_edge, att_edge, g, H, channels, slope, agg=AGG[s], alpha=ALPHA[s])
             ops.gemm(AGG[s], w_scale, bias=bias, epilogue=EPI_CELU, out=M[s])
@@ -269,15 +273,16 @@ class MessageStackFn(Function):
                 ops.gemm(M[s], w_ih, transpose_w=True, bias=b_ih, out=RZN[s])
                 ops.gemm(HH[s], w_hh, transpose_w=True, bias=b_hh, out=GH[s])
                 ops.gru_gates_fwd(RZN[s], GH[s], HH[s], X[s] if res else None, act, act_param, h_new=HH[s + 1], x_out=X[s + 1])
-        ctx.save_for_backward(w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ea, X, HH, XD, MASK, XPE, AGG, ALPHA, M, RZN, GH)
-        ctx.g, ctx.cfg = g, (H, channels, slope, act, act_param, res, S, p_drop)
+        ctx.save_for_backward(w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ea, X, HH, XD, MASK, XPE, AGG, ALPHA, M, RZN, GH,
+                              None if pn is None else pn[0])
+        ctx.g, ctx.cfg = g, (H, channels, slope, act, act_param, res, S, p_drop, None if pn is None else (pn[1], pn[2]))
         ctx.set_materialize_grads(False)
         return tuple(X[s + 1] for s in range(S)) + (HH[S],)      # every step's output (the pair models pool them) + final h
 
     @staticmethod
     def backward(ctx, *grads):
-        (w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ea, X, HH, XD, MASK, XPE, AGG, ALPHA, M, RZN, GH) = ctx.saved_tensors
-        H, C, slope, act, act_param, res, S, p_drop = ctx.cfg
+        (w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ea, X, HH, XD, MASK, XPE, AGG, ALPHA, M, RZN, GH, pn_ptr) = ctx.saved_tensors
+        H, C, slope, act, act_param, res, S, p_drop, pn = ctx.cfg
         g = ctx.g
         N, HC, ld, E, De, dev = X.shape[1], H * C, XPE.shape[2], ea.shape[0], ea.shape[1], X.device
         new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
@@ -296,10 +301,13 @@ class MessageStackFn(Function):
             g_agg = ops.gemm(G_PRE[s], w_scale, transpose_w=True)                             # [N,HC]
             ops.triplet_edge_bwd(XPE[s], ea, w_edge, att_edge, ALPHA[s], g_agg, g, H, C, slope,
                                  g_xpe=G_XPE[s], g_logit=G_LOGIT[s], g_we=G_WE[s])
-            if p_drop > 0.0:
-                g_xd = ops.gemm(G_XPE[s], w_ext, transpose_w=True)
-                g_x = torch.ops.aten.native_dropout_backward(g_xd, MASK[s], 1.0 / (1.0 - p_drop))
-                if res:
+            if p_drop > 0.0 or pn is not None:
+                g_x = ops.gemm(G_XPE[s], w_ext, transpose_w=True)                                 # d/d(conv input)
+                if p_drop > 0.0:
+                    g_x = torch.ops.aten.native_dropout_backward(g_x, MASK[s], 1.0 / (1.0 - p_drop))
+                if pn is not None:                                                               # through PairNorm, onto the residual
+                    g_x = ops.pair_norm_bwd(X[s], g_x, pn_ptr, pn[0], pn[1], out=g_id if res else None, accumulate=res)
+                elif res:
                     g_x.add_(g_id)
             elif res:
                 g_x = ops.gemm(G_XPE[s], w_ext, transpose_w=True, epilogue=EPI_ACCUM, out=g_id)
@@ -319,7 +327,26 @@ class MessageStackFn(Function):
         g_att_edge, _ = ops.gemm_tn_ex(ea, G_LOGIT.sum(0) if S > 1 else G_LOGIT[0])
         g_w_edge = G_WE.sum(0) if S > 1 else G_WE[0]
         return (g_x0, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias, g_w_ih, g_w_hh, g_b_ih, g_b_hh,
-                None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None)
+
+
+# --------------------------------------------------------------------------------------------------
+# PairNorm per graph (the reference's default graph_norm): deterministic warp-per-graph kernels
+# --------------------------------------------------------------------------------------------------
+class PairNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gptr, num_graphs, eps):
+        x = _c(x)
+        ops._need_cuda(x)
+        ctx.save_for_backward(x, gptr)
+        ctx.cfg = (num_graphs, eps)
+        return ops.pair_norm_fwd(x, gptr, num_graphs, eps)
+
+    @staticmethod
+    def backward(ctx, g_y):
+        x, gptr = ctx.saved_tensors
+        num_graphs, eps = ctx.cfg
+        return ops.pair_norm_bwd(x, _c(g_y), gptr, num_graphs, eps), None, None, None
 
 
 # --------------------------------------------------------------------------------------------------

@@ -148,7 +148,7 @@ class _None(nn.Module):
     def __init__(self, **params):
         super().__init__()
 
-    def forward(self, x, batch=None):
+    def forward(self, x, batch=None, num_graphs=None):
         return x
 
 
@@ -278,7 +278,7 @@ class _BatchNorm(nn.Module):
         self.norm = nn.Module()
         self.norm.module = nn.BatchNorm1d(in_channels)       # PyG BatchNorm keeps it under `.module`
 
-    def forward(self, x, batch=None):
+    def forward(self, x, batch=None, num_graphs=None):
         return self.norm.module(x)
 
 
@@ -292,12 +292,12 @@ class _LayerNorm(nn.Module):
         self.norm.bias = Parameter(torch.zeros(in_channels))
         self.eps = eps
 
-    def forward(self, x, batch=None):
+    def forward(self, x, batch=None, num_graphs=None):
         if batch is None:
             x = x - x.mean()
             out = x / (x.std(unbiased=False) + self.eps)
         else:
-            B = int(batch[-1]) + 1
+            B = int(batch[-1]) + 1 if num_graphs is None else num_graphs
             mean = _seg_mean(x, batch, B).mean(dim=-1, keepdim=True)
             x = x - mean[batch]
             var = _seg_mean(x * x, batch, B).mean(dim=-1, keepdim=True)
@@ -314,6 +314,14 @@ class _PairNorm(nn.Module):
         if batch is None:
             x = x - x.mean(dim=0, keepdim=True)
             return x / (self.eps + x.pow(2).sum(-1).mean()).sqrt()
+        if x.is_cuda and x.dim() == 2 and x.shape[1] <= 128:
+            # one warp per graph, fixed-order reductions (csrc/norm.cu): reproducible run to run, no index_add_ atomics
+            gptr, B = G.graph_ptr(batch, num_graphs)
+            return Fn.PairNormFn.apply(x, gptr, B, self.eps)
+        return self.composed_forward(x, batch, num_graphs)
+
+    def composed_forward(self, x, batch, num_graphs=None):
+        """The same in torch ops (CPU tensors; kept as an independent cross-check of the kernel)."""
         B = int(batch[-1]) + 1 if num_graphs is None else num_graphs
         x = x - _seg_mean(x, batch, B)[batch]
         return x / torch.sqrt(self.eps + _seg_mean(x.pow(2).sum(-1, keepdim=True), batch, B)[batch])
@@ -323,7 +331,7 @@ class _GraphSizeNorm(nn.Module):
     def __init__(self, in_channels):
         super().__init__()
 
-    def forward(self, x, batch=None):
+    def forward(self, x, batch=None, num_graphs=None):
         return x / (x.shape[0] ** 0.5)                       # called without batch in the reference (:194)
 
 
@@ -516,7 +524,8 @@ class MessageBlock(nn.Module):
         inner = getattr(self.conv, "conv", None)
         fused = _fusable_act(self.act, self.training)
         drop = self.dropout
-        stackable = (self.gru is not None and isinstance(inner, TripletMessage) and isinstance(self.norm, _None)
+        pairnorm = isinstance(self.norm, _PairNorm) and batch is not None and x.shape[1] <= 128
+        stackable = (self.gru is not None and isinstance(inner, TripletMessage) and (isinstance(self.norm, _None) or pairnorm)
                      and fused is not None and isinstance(drop, (_None, nn.Dropout)) and x.is_cuda and steps >= 1
                      and x.shape[1] == inner.node_channels and self.gru.hidden_size == x.shape[1])
         if not stackable:
@@ -529,7 +538,11 @@ class MessageBlock(nn.Module):
         g = G.graph_index(edge_index, x.shape[0])
         w_ext, att_edge = inner.derived()
         gru = self.gru
-        fi = _fused_index(g, x, edge_attr, batch, num_graphs, inner.heads, inner.node_channels) if p_drop == 0.0 else None
+        pn = None
+        if pairnorm:
+            gptr_pn, B_pn = G.graph_ptr(batch, num_graphs)
+            pn = (gptr_pn, B_pn, float(self.norm.eps))
+        fi = _fused_index(g, x, edge_attr, batch, num_graphs, inner.heads, inner.node_channels) if (p_drop == 0.0 and pn is None) else None
         if fi is not None and not _wants_grad(x, *self.parameters()):
             # screening / evaluation: nothing is kept for backward, only the outputs leave the SM
             x_out, h_out = ops.message_stack_fwd(
@@ -541,7 +554,7 @@ class MessageBlock(nn.Module):
         out = Fn.MessageStackFn.apply(
             x, w_ext, inner.weight_edge, att_edge, inner.weight_scale, inner.bias,
             gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, ea, g,
-            inner.heads, inner.node_channels, inner.negative_slope, fused[0], fused[1], bool(self.res), int(steps), p_drop, fi)
+            inner.heads, inner.node_channels, inner.negative_slope, fused[0], fused[1], bool(self.res), int(steps), p_drop, fi, pn)
         xs = list(out[:steps])
         return (xs if keep == "all" else xs[-1:]), out[steps].unsqueeze(0)
 
@@ -549,7 +562,7 @@ class MessageBlock(nn.Module):
         identity = x
         if h is None:
             h = x.unsqueeze(0)
-        x = self.dropout(self.norm(x, batch))
+        x = self.dropout(self.norm(x, batch, num_graphs))
         if self.gru is None:
             x = self.conv(x, edge_index, edge_attr)
             x = x + identity if self.res else x

@@ -427,6 +427,23 @@ def pair_dot_pool_bwd(xa, xb, ptr_a, ptr_b, g_out, argmax, sa, sb, num_pairs):
     return g_xa, g_xb
 
 
+# ------------------------------------------------------------------------------------------------ norms
+def pair_norm_fwd(x, gptr, num_graphs, eps, out=None):
+    _need_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    out = torch.empty_like(x, memory_format=torch.contiguous_format) if out is None else out
+    _call("glam_pair_norm_fwd", _p(x), x.stride(0), _p(gptr), int(num_graphs), x.shape[1], float(eps), _p(out), out.stride(0), _stream(x))
+    return out
+
+
+def pair_norm_bwd(x, g_y, gptr, num_graphs, eps, out=None, accumulate=False):
+    assert x.stride(1) == 1 and g_y.stride(1) == 1
+    out = torch.empty_like(x, memory_format=torch.contiguous_format) if out is None else out
+    _call("glam_pair_norm_bwd", _p(x), x.stride(0), _p(g_y), g_y.stride(0), _p(gptr), int(num_graphs), x.shape[1], float(eps), _p(out),
+          out.stride(0), 1 if accumulate else 0, _stream(x))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ next rows (§8f)
 def pool5_fwd(x, gptr, num_graphs):
     N, C = x.shape

@@ -326,6 +326,17 @@ int glam_unpack_graphs(const uint8_t* n_g, const uint16_t* e_g, const uint8_t* d
                        int64_t num_graphs, int64_t num_nodes, int64_t num_edges, int node_dim, int32_t* graph_ptr,
                        int32_t* edge_ptr, int32_t* dst_rowptr, int32_t* dst_src, float* x, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (10) PairNorm per graph (PyG PairNorm(scale=1, scale_individually=False, eps) @1.7.2 — the reference's default graph_norm,
+ * src_1gp/run.py:28, src_1gp/layer.py:179-185,255): y = (x - mean_g(x)) / sqrt(eps + mean_g(sum_c (x - mean_g(x))^2)).
+ * One warp per graph, fixed-order reductions (the torch formulation scatters with floating-point atomics).  Backward
+ * recomputes the statistics from x; accumulate = 1 adds into g_x.
+ * --------------------------------------------------------------------------------------------- */
+int glam_pair_norm_fwd(const float* x, int64_t ldx, const int32_t* graph_ptr, int64_t num_graphs, int channels, float eps,
+                       float* y, int64_t ldy, void* stream);
+int glam_pair_norm_bwd(const float* x, int64_t ldx, const float* g_y, int64_t ldg, const int32_t* graph_ptr, int64_t num_graphs,
+                       int channels, float eps, float* g_x, int64_t ldgx, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

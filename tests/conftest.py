@@ -68,7 +68,7 @@ def pytest_terminal_summary(terminalreporter):
     if not helpers.REALISED:
         return
     tr = terminalreporter
-    for mode in ("fp32", "tf32"):
+    for mode in ("fp32", "tf32", "fp32-abs", "tf32-abs"):
         rows = sorted((r for r in helpers.REALISED if r[1] == mode), key=lambda r: -r[2])
         if not rows:
             continue

@@ -62,7 +62,9 @@ def tol_check(ours, ref32, ref64, name="", rtol=1e-4, atol=1e-5, emu64=None):
     err = (o - r64).abs().max()
     base = (r32 - r64).abs().max()
     bound = torch.maximum(torch.maximum(2 * base, atol + rtol * scale), torch.as_tensor(extra, dtype=torch.float64))
-    denom = torch.clamp(scale, min=1e-6)     # tensors that are exactly zero in the reference (shift-invariant gate bias) would blow up
-    REALISED.append((name, MATH_MODE["mode"], float(err / denom), float(bound / denom)))
+    if float(scale.detach()) >= 1e-6:                 # (tensors that are exactly zero in the reference — the shift-invariant gate bias of
+        REALISED.append((name, MATH_MODE["mode"], float(err.detach() / scale.detach()), float(bound.detach() / scale.detach())))
+    else:                                    # GlobalAttention — have no scale to be relative to: absolute error, listed apart)
+        REALISED.append((name + " [reference == 0: absolute error]", MATH_MODE["mode"] + "-abs", float(err.detach()), float(bound.detach())))
     assert err <= bound, (f"{name}: err {err:.3e} > bound {bound:.3e} (fp32-ref err {base:.3e}, scale {scale:.3e}, "
                           f"4x tf32-oracle deviation {float(extra):.3e})")

@@ -488,3 +488,70 @@ def test_screen_step_after_train_step_leaves_parameters_in_place():
     l1 = float(ts.step(b))                                       # the captured training step still sees (and updates) the weights
     assert l1 != l0 and torch.isfinite(torch.tensor(l1))
     assert not torch.equal(ss.step(b), s0)                       # ... and the captured screening step sees the update
+
+
+# ---------------------------------------------------------------------------------------------- PairNorm
+@pytest.mark.parametrize("C,n_graphs", [(36, 200), (60, 33), (100, 5)])
+def test_pair_norm_kernel_matches_composition_and_is_deterministic(C, n_graphs):
+    from glam_b200 import layer
+    b = _batch(n_graphs, 9, 3, 17).to(DEV)
+    gen = torch.Generator().manual_seed(1)
+    x = (torch.randn(b.num_nodes, C, generator=gen) * 2 + 0.5).to(DEV)
+    cot = torch.randn(b.num_nodes, C, generator=gen).to(DEV)
+    pn = layer._PairNorm(C)
+    xr = x.clone().requires_grad_(True)
+    y = pn(xr, b.batch, num_graphs=b.num_graphs)
+    (y * cot).sum().backward()
+    x64 = x.double().cpu().requires_grad_(True)
+    y64 = pn.composed_forward(x64, b.batch.cpu(), b.num_graphs)
+    (y64 * cot.double().cpu()).sum().backward()
+    assert _rel(y, y64) < 2e-6 and _rel(xr.grad, x64.grad) < 2e-5
+    xr2 = x.clone().requires_grad_(True)
+    y2 = pn(xr2, b.batch, num_graphs=b.num_graphs)
+    (y2 * cot).sum().backward()
+    assert torch.equal(y2, y) and torch.equal(xr2.grad, xr.grad)          # bitwise run to run
+
+
+def test_pairnorm_block_runs_stacked_and_matches_loop(math_mode):
+    """The reference's default graph_norm on the one-node stacked path (MessageStackFn with PairNorm inside) against the plain
+    loop over MessageBlock.forward, outputs and gradients; the stacked path must actually be taken (launch count)."""
+    from glam_b200 import _lib, layer, functional as Fn
+    C, De = 36, 3
+    torch.manual_seed(4)
+    blk = layer.MessageBlock(C, C, De, norm="_PairNorm", dropout="_None()", conv="_TripletMessage", act="CELU", res=True).to(DEV).train()
+    b = _batch(150, C, De, 6).to(DEV)
+    gen = torch.Generator().manual_seed(8)
+    x0 = torch.randn(b.num_nodes, C, generator=gen).to(DEV)
+    cot = torch.randn(b.num_nodes, C, generator=gen).to(DEV)
+
+    def run(stacked):
+        for p in blk.parameters():
+            p.grad = None
+        xin = x0.clone().requires_grad_(True)
+        n0 = _lib.launch_count()
+        if stacked:
+            xs, h = blk.run_steps(xin, b.edge_index, b.edge_attr, 3, batch=b.batch, num_graphs=b.num_graphs)
+        else:
+            xs, h, xi = [], None, xin
+            for _ in range(3):
+                xi, h = blk(xi, b.edge_index, b.edge_attr, h=h, batch=b.batch, num_graphs=b.num_graphs)
+                xs.append(xi)
+        n_fwd = _lib.launch_count() - n0
+        (xs[-1] * cot).sum().backward()
+        return xs[-1].detach(), xin.grad.clone(), [p.grad.clone() for p in blk.parameters()], n_fwd
+
+    calls = []
+    orig = Fn.MessageStackFn.forward
+    Fn.MessageStackFn.forward = staticmethod(lambda *a, **k: (calls.append(1), orig(*a, **k))[1])
+    try:
+        ys, gxs, gps, _ = run(True)
+    finally:
+        Fn.MessageStackFn.forward = orig
+    assert calls, "PairNorm block did not take the stacked node"
+    yl, gxl, gpl, _ = run(False)
+    tol = 2e-4 if math_mode == "fp32" else 2e-2
+    assert _rel(ys, yl) < tol and _rel(gxs, gxl) < 10 * tol
+    for a, c in zip(gps, gpl):
+        assert _rel(a, c) < 10 * tol
+    ys2, gxs2, gps2, _ = run(True)
+    assert torch.equal(ys2, ys) and torch.equal(gxs2, gxs) and all(torch.equal(a, c) for a, c in zip(gps2, gps))
