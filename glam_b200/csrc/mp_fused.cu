@@ -47,6 +47,7 @@ namespace {
 constexpr int kMpM = 128;                    // rows per tile = UMMA M
 constexpr int kMpMaxEdges = 768;             // in-edges per tile (molecular tiles: ~2.2 per atom)
 constexpr int kMpMaxDe = 4;                  // bond types
+constexpr int kMpMaxRaw = 16;                // raw atom features of the optional input LinearBlock
 constexpr int kMpPanel = kMpM * kPanelRowBytes;      // 16 KB
 
 enum : int { kFlagNodes = 1, kFlagEdges = 2, kFlagCross = 4, kFlagEdgeAttr = 8 };
@@ -165,6 +166,7 @@ edge_types_kernel(const float* __restrict__ ea, int64_t E, int De, uint8_t* __re
 // ------------------------------------------------------------------------------------------------ the fused kernel
 struct MpParams {
     const float* x0; const float* h0;
+    const float* x_raw; const float* w_pre; const float* b_pre; int raw_dim, pre_act; float pre_act_param;   // optional input LinearBlock
     const float* w_ext; int ldw;
     const float* w_edge; const float* att_edge;
     const float* w_scale; const float* bias;
@@ -223,7 +225,8 @@ struct MpGeom {
     // misc (floats / ints)
     static constexpr int M_BAR = 0, M_RP = 4, M_REC = 136, M_ALPHA = M_REC + kMpMaxEdges, M_WE = M_ALPHA + kMpMaxEdges * H;
     static constexpr int M_AE = M_WE + kMpMaxDe * HC, M_U = M_AE + kMpMaxDe * H, M_BIAS = M_U + C * 2 * H, M_GB = M_BIAS + C;
-    static constexpr int M_END = (M_GB + 4 * C + 3) / 4 * 4;
+    static constexpr int M_PRE = (M_GB + 4 * C + 3) / 4 * 4;            // input LinearBlock: W [C][raw_dim <= kMpMaxRaw] | b [C]
+    static constexpr int M_END = M_PRE + C * kMpMaxRaw + C;
     static constexpr int SMEM = OFF_MISC + M_END * 4;
     static_assert(NT == 512 || NT == 1024, "threads");
     static_assert(KSX <= 5 && TQ <= 2, "tail panel holds 8 features per operand");
@@ -266,6 +269,7 @@ mp_fused_kernel(const MpParams p) {
     float* alpha_s = misc + G::M_ALPHA;
     float* We = misc + G::M_WE;  float* Ae = misc + G::M_AE;  float* U = misc + G::M_U;
     float* bias_s = misc + G::M_BIAS;  float* gb = misc + G::M_GB;
+    float* Wp = misc + G::M_PRE;  float* bp = Wp + C * kMpMaxRaw;
     float* xp = reinterpret_cast<float*>(REG);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = p.meta[0], flags = p.meta[1];
@@ -333,6 +337,10 @@ mp_fused_kernel(const MpParams p) {
             U[i] = p.w_ext[(size_t)c * p.ldw + HC + which * H + h];
         }
         for (int i = tid; i < C; i += NT) bias_s[i] = p.bias[i];
+        if (p.x_raw) {
+            for (int i = tid; i < C * p.raw_dim; i += NT) Wp[i] = p.w_pre[i];
+            for (int i = tid; i < C; i += NT) bp[i] = p.b_pre ? p.b_pre[i] : 0.f;
+        }
     }
     fence_proxy_async_smem();
     __syncthreads();
@@ -353,7 +361,22 @@ mp_fused_kernel(const MpParams p) {
             const int r = i / CQ, q = i - r * CQ;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f), hv = v;
             if (r < nd) {
-                v = __ldg(reinterpret_cast<const float4*>(p.x0 + (size_t)(n0 + r) * C) + q);
+                if (p.x_raw) {
+                    // the model's input LinearBlock (src_1gp/model.py:49: Linear(raw_dim -> C) + activation) applied while the
+                    // rows are loaded: exact fp32 FMAs (what the per-op path does for K % 4 != 0), x0 never exists in HBM
+                    const float* xr = p.x_raw + (size_t)(n0 + r) * p.raw_dim;
+                    const float* w = Wp + 4 * q * p.raw_dim;
+                    v = lds128(bp + 4 * q);
+                    for (int k = 0; k < p.raw_dim; ++k) {
+                        const float xv = __ldg(xr + k);
+                        v.x = fmaf(xv, w[k], v.x); v.y = fmaf(xv, w[p.raw_dim + k], v.y);
+                        v.z = fmaf(xv, w[2 * p.raw_dim + k], v.z); v.w = fmaf(xv, w[3 * p.raw_dim + k], v.w);
+                    }
+                    v.x = act_fwd(v.x, p.pre_act, p.pre_act_param); v.y = act_fwd(v.y, p.pre_act, p.pre_act_param);
+                    v.z = act_fwd(v.z, p.pre_act, p.pre_act_param); v.w = act_fwd(v.w, p.pre_act, p.pre_act_param);
+                } else {
+                    v = __ldg(reinterpret_cast<const float4*>(p.x0 + (size_t)(n0 + r) * C) + q);
+                }
                 if (p.h0) hv = __ldg(reinterpret_cast<const float4*>(p.h0 + (size_t)(n0 + r) * C) + q);
                 if (SAVE && !p.conv_only) {
                     reinterpret_cast<float4*>(p.sX + (size_t)(n0 + r) * C)[q] = v;
@@ -370,10 +393,11 @@ mp_fused_kernel(const MpParams p) {
         if (t + (int)gridDim.x < ntiles) {
             // the next tile's rows and index words on their way into L2 while this tile computes
             const int4 tn = p.tiles[t + gridDim.x];
-            const char* xb = reinterpret_cast<const char*>(p.x0 + (size_t)tn.x * C);
-            const int xbytes = (tn.y - tn.x) * C * 4;
+            const char* xb = p.x_raw ? reinterpret_cast<const char*>(p.x_raw + (size_t)tn.x * p.raw_dim)
+                                     : reinterpret_cast<const char*>(p.x0 + (size_t)tn.x * C);
+            const int xbytes = (tn.y - tn.x) * (p.x_raw ? p.raw_dim : C) * 4;
             for (int o = tid * 128; o < xbytes; o += NT * 128) prefetch_l2(xb + o);
-            if (p.h0) { const char* hb = reinterpret_cast<const char*>(p.h0 + (size_t)tn.x * C); for (int o = tid * 128; o < xbytes; o += NT * 128) prefetch_l2(hb + o); }
+            if (p.h0) { const char* hb = reinterpret_cast<const char*>(p.h0 + (size_t)tn.x * C); for (int o = tid * 128; o < (tn.y - tn.x) * C * 4; o += NT * 128) prefetch_l2(hb + o); }
             const char* sb = reinterpret_cast<const char*>(p.src + tn.z);
             for (int o = tid * 128; o < (tn.w - tn.z) * 4; o += NT * 128) prefetch_l2(sb + o);
             const char* rb = reinterpret_cast<const char*>(p.rowptr + tn.x);
@@ -752,7 +776,8 @@ extern "C" int glam_message_stack_supported(int channels, int heads, int edge_di
     return (channels == 32 || channels == 36 || channels == 40) ? 1 : 0;
 }
 
-extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const float* w_ext, int64_t ldw, const float* w_edge,
+extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const float* x_raw, int raw_dim, const float* w_pre,
+                                      const float* b_pre, int pre_act, float pre_act_param, const float* w_ext, int64_t ldw, const float* w_edge,
                                       const float* att_edge, const float* w_scale, const float* bias, const float* w_ih,
                                       const float* w_hh, const float* b_ih, const float* b_hh, const int32_t* tiles,
                                       const int32_t* tile_meta, const int32_t* dst_rowptr, const int32_t* dst_src,
@@ -767,8 +792,9 @@ extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const fl
     GLAM_REQUIRE(num_nodes >= 0 && num_edges >= 0 && steps >= 1, "glam_message_stack_fwd: bad sizes");
     if (num_nodes == 0) return 0;
     const bool save = save_xpe != nullptr;              // training: also write what MessageStackFn.backward / TripletConvFn.backward read
-    GLAM_REQUIRE(x0 && w_ext && w_edge && att_edge && w_scale && bias && tiles && tile_meta && dst_rowptr && (num_edges == 0 || (dst_src && etype)),
+    GLAM_REQUIRE((x0 || x_raw) && w_ext && w_edge && att_edge && w_scale && bias && tiles && tile_meta && dst_rowptr && (num_edges == 0 || (dst_src && etype)),
                  "glam_message_stack_fwd: null pointer");
+    GLAM_REQUIRE(!x_raw || (w_pre && raw_dim >= 1 && raw_dim <= kMpMaxRaw), "glam_message_stack_fwd: input LinearBlock needs weights and raw_dim <= %d", kMpMaxRaw);
     GLAM_REQUIRE(conv_only ? steps == 1 : (w_ih && w_hh && b_ih && b_hh), "glam_message_stack_fwd: GRU weights missing / conv-only takes one step");
     GLAM_REQUIRE(save ? (save_agg && save_alpha && (conv_only ? x_out != nullptr : (save_x && save_h && save_m && save_rzn && save_gh)))
                       : (x_out != nullptr),
@@ -780,7 +806,8 @@ extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const fl
                  "glam_message_stack_fwd: pointers must be 16-byte aligned");
     GLAM_REQUIRE(num_nodes < ((int64_t)1 << 31) && num_edges < ((int64_t)1 << 31), "glam_message_stack_fwd: too large");
     MpParams p;
-    p.x0 = x0; p.h0 = h0; p.w_ext = w_ext; p.ldw = (int)ldw; p.w_edge = w_edge; p.att_edge = att_edge; p.w_scale = w_scale; p.bias = bias;
+    p.x0 = x0; p.h0 = h0; p.x_raw = x_raw; p.raw_dim = raw_dim; p.w_pre = w_pre; p.b_pre = b_pre; p.pre_act = pre_act; p.pre_act_param = pre_act_param;
+    p.w_ext = w_ext; p.ldw = (int)ldw; p.w_edge = w_edge; p.att_edge = att_edge; p.w_scale = w_scale; p.bias = bias;
     p.w_ih = w_ih; p.w_hh = w_hh; p.b_ih = b_ih; p.b_hh = b_hh; p.tiles = reinterpret_cast<const int4*>(tiles); p.meta = tile_meta;
     p.rowptr = dst_rowptr; p.src = dst_src; p.etype = etype; p.N = num_nodes; p.E = num_edges; p.De = edge_dim; p.steps = steps;
     p.act = act; p.res = res; p.conv_only = conv_only; p.keep_all = keep_all; p.slope = negative_slope; p.act_param = act_param;

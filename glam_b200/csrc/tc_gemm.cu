@@ -297,7 +297,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p)
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&w_bar);
-            if (has_exact) mbar_wait(&w_bar, 0);                 // the exact columns read W rows from shared memory
+            if (has_exact) {                                     // the exact columns read W rows from shared memory
+                mbar_wait(&w_bar, 0);
+                // (redundant with the mbarrier's release/acquire; named barrier 3 over the 256 epilogue threads makes the ordering
+                // visible to compute-sanitizer's racecheck, which does not model inline-PTX mbarrier waits)
+                asm volatile("bar.sync 3, %0;" ::"n"(128 * kEpiGroups) : "memory");
+            }
         }
         if (p.staged_out) {
             const uint32_t xs_a = smem_u32(Xs), ws_a = smem_u32(Ws), og_a = smem_u32(Og);

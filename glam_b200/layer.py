@@ -490,6 +490,15 @@ class LinearBlock(nn.Module):
         self.linear = nn.Linear(in_dim, out_dim)
         self.act = _build_act(act)
 
+    def fusable_into_stack(self, x):
+        """(weight, bias, act code, act param) when this block can be applied inside the fused message kernel while it loads
+        its input rows (no norm, dropout inactive, kernel-side activation, <= 16 raw features), else None."""
+        act = _fusable_act(self.act, self.training)
+        drop_off = isinstance(self.dropout, _None) or not self.training or getattr(self.dropout, "p", 1.0) == 0.0
+        if act is None or not drop_off or not isinstance(self.norm, _None) or x.dim() != 2 or x.shape[1] > 16 or x.dtype != torch.float32:
+            return None
+        return self.linear.weight, self.linear.bias, act[0], act[1]
+
     def forward(self, x, batch=None):
         z = self.dropout(self.norm(x, batch))
         lin = self.linear
@@ -516,19 +525,29 @@ class MessageBlock(nn.Module):
         self.act = _build_act(act)
         self.res = res
 
-    def run_steps(self, x, edge_index, edge_attr, steps, batch=None, num_graphs=None, keep="all"):
+    def run_steps(self, x, edge_index, edge_attr, steps, batch=None, num_graphs=None, keep="all", pre=None):
         """`steps` applications of this block starting from h=None (the loop of src_1gp/model.py:60-62), returning
         ([x_1 .. x_steps], h) — or ([x_steps], h) with keep="last".  With the triplet layer, no norm and a fusable
         activation the whole loop is one autograd node (functional.MessageStackFn) and, when the batch meets the
-        preconditions of csrc/mp_fused.cu, ONE kernel launch; otherwise it is the plain loop over forward()."""
+        preconditions of csrc/mp_fused.cu, ONE kernel launch; otherwise it is the plain loop over forward().
+        `pre`: the LinearBlock that produces this block's input (src_1gp/model.py:49) — `x` is then ITS input (the raw
+        features); in evaluation it is applied inside the fused kernel, otherwise simply called first."""
         inner = getattr(self.conv, "conv", None)
+        pre_fused = None
+        if pre is not None:
+            pre_fused = pre.fusable_into_stack(x) if (x.is_cuda and not _wants_grad(x, *self.parameters(), *pre.parameters())) else None
+            if pre_fused is None:
+                x, pre = pre(x, batch=batch), None
+        width = pre.linear.out_features if pre is not None else x.shape[1]
         fused = _fusable_act(self.act, self.training)
         drop = self.dropout
         pairnorm = isinstance(self.norm, _PairNorm) and batch is not None and x.shape[1] <= 128
         stackable = (self.gru is not None and isinstance(inner, TripletMessage) and (isinstance(self.norm, _None) or pairnorm)
                      and fused is not None and isinstance(drop, (_None, nn.Dropout)) and x.is_cuda and steps >= 1
-                     and x.shape[1] == inner.node_channels and self.gru.hidden_size == x.shape[1])
+                     and width == inner.node_channels and self.gru.hidden_size == width)
         if not stackable:
+            if pre is not None:
+                x, pre = pre(x, batch=batch), None
             xs, h = [], None
             for _ in range(steps):
                 x, h = self.forward(x, edge_index, edge_attr, h=h, batch=batch, num_graphs=num_graphs)
@@ -548,8 +567,10 @@ class MessageBlock(nn.Module):
             x_out, h_out = ops.message_stack_fwd(
                 x.contiguous(), None, w_ext, inner.weight_edge, att_edge, inner.weight_scale, inner.bias,
                 gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, g, fi, inner.heads, inner.node_channels,
-                int(steps), inner.negative_slope, fused[0], fused[1], bool(self.res), keep_all=(keep == "all"))
+                int(steps), inner.negative_slope, fused[0], fused[1], bool(self.res), keep_all=(keep == "all"), pre=pre_fused)
             return list(x_out.unbind(0)), h_out.unsqueeze(0)
+        if pre is not None:
+            x = pre(x, batch=batch)
         ea = g.sorted_edge_attr(edge_attr)
         out = Fn.MessageStackFn.apply(
             x, w_ext, inner.weight_edge, att_edge, inner.weight_scale, inner.bias,

@@ -66,11 +66,12 @@ class ArchitectureGP(nn.Module):
 
     def forward(self, data_mol):
         B = _num_graphs(data_mol)
-        xm = self.mol_lin0(data_mol.x, batch=data_mol.batch)
         if self.stack_steps:
-            xs, _ = self.mol_conv.run_steps(xm, data_mol.edge_index, data_mol.edge_attr, self.message_steps, batch=data_mol.batch,
-                                            num_graphs=B, keep="last")
+            # the input LinearBlock goes along: in evaluation it is applied inside the fused message kernel (x0 never exists)
+            xs, _ = self.mol_conv.run_steps(data_mol.x, data_mol.edge_index, data_mol.edge_attr, self.message_steps,
+                                            batch=data_mol.batch, num_graphs=B, keep="last", pre=self.mol_lin0)
         else:
+            xm = self.mol_lin0(data_mol.x, batch=data_mol.batch)
             hm = None
             for _ in range(self.message_steps):
                 xm, hm = self.mol_conv(xm, data_mol.edge_index, data_mol.edge_attr, h=hm, batch=data_mol.batch, num_graphs=B)

@@ -284,14 +284,23 @@ def message_stack_supported(channels: int, heads: int, edge_dim: int) -> bool:
 
 
 def message_stack_fwd(x0, h0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, g, fi, heads, channels, steps,
-                      slope, act, act_param, res, conv_only=False, keep_all=False, save=None):
+                      slope, act, act_param, res, conv_only=False, keep_all=False, save=None, pre=None):
     """The whole message stack in one launch (csrc/mp_fused.cu).  Eval (save=None): returns (x_out [S|1,N,C], h_out [N,C]|None).
     Training: `save` = dict of preallocated stacked tensors X, HH, XPE, AGG, ALPHA, M, RZN, GH (conv_only: XPE, AGG, ALPHA) that
     the kernel fills; returns (x_out|None, None)."""
     _need_cuda(x0, w_ext)
-    N, C = x0.shape
+    N, C = x0.shape[0], channels
     E, dev = g.num_edges, x0.device
     assert x0.is_contiguous() and (h0 is None or h0.is_contiguous()) and w_ext.is_contiguous()
+    # pre = (weight [C, raw_dim], bias [C] | None, act code, act param): the model's input LinearBlock, applied in the kernel
+    # to x0 = the RAW features [N, raw_dim]
+    x_in, x_raw, raw_dim, w_pre, b_pre, pre_act, pre_par = x0, None, 0, None, None, 0, 0.0
+    if pre is not None:
+        w_pre, b_pre, pre_act, pre_par = pre
+        assert w_pre.is_contiguous() and w_pre.shape == (C, x0.shape[1]) and (b_pre is None or b_pre.is_contiguous())
+        x_in, x_raw, raw_dim = None, x0, x0.shape[1]
+    else:
+        assert x0.shape[1] == C
     x_out = h_out = None
     if save is None or conv_only:
         x_out = torch.empty(((steps if keep_all else 1), N, C), dtype=torch.float32, device=dev)
@@ -300,7 +309,7 @@ def message_stack_fwd(x0, h0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh
     sv = save or {}
     for k, t in sv.items():
         assert t.is_contiguous(), k
-    _call("glam_message_stack_fwd", _p(x0), _p(h0), _p(w_ext), w_ext.stride(0), _p(w_edge), _p(att_edge), _p(w_scale), _p(bias),
+    _call("glam_message_stack_fwd", _p(x_in), _p(h0), _p(x_raw), raw_dim, _p(w_pre), _p(b_pre), pre_act, float(pre_par), _p(w_ext), w_ext.stride(0), _p(w_edge), _p(att_edge), _p(w_scale), _p(bias),
           _p(w_ih), _p(w_hh), _p(b_ih), _p(b_hh), _p(fi.tiles), _p(fi.meta), _p(g.dst_rowptr), _p(g.dst_src), _p(fi.etype),
           N, E, channels, heads, fi.edge_dim, steps, float(slope), act, float(act_param), 1 if res else 0,
           1 if conv_only else 0, 1 if keep_all else 0, _p(x_out), _p(h_out), _p(sv.get("X")), _p(sv.get("HH")), _p(sv.get("XPE")),

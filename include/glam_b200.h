@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLAM_B200_ABI_VERSION 5
+#define GLAM_B200_ABI_VERSION 6
 #define GLAM_MAX_HEADS 4
 
 int glam_abi_version(void);
@@ -287,7 +287,9 @@ int glam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
  *   8 an edge_attr row is not one-hot).  glam_edge_types — bond type per dst-ordered edge (index of the 1 in the
  *   one-hot row, src_1gp/dataset.py:82), ORs 8 into meta[1] otherwise.
  * glam_message_stack_fwd — w_ext / att_edge are glam_triplet_prep_fwd's derived weights.  h0 NULL: h = x on the first
- *   step (layer.py:253-254).  conv_only = 1: x_out = TripletMessage(x0) alone (steps must be 1, GRU arguments NULL).
+ *   step (layer.py:253-254).  x_raw != NULL: the model's input LinearBlock (src_1gp/model.py:49) is applied while the rows are
+ *   loaded — x0 = act(x_raw [N,raw_dim] w_pre^T + b_pre), w_pre [C,raw_dim] as torch.nn.Linear stores it, raw_dim <= 16,
+ *   exact fp32 — and x0 may be NULL.  conv_only = 1: x_out = TripletMessage(x0) alone (steps must be 1, GRU arguments NULL).
  *   Eval (save_xpe == NULL): x_out [keep_all ? steps : 1][N][C] = the step outputs (last only unless keep_all), h_out [N][C]
  *   (may be NULL) = the final GRU state.  Training (save_xpe != NULL): what the backward kernels consume is written as
  *   stacked tensors — save_x, save_h [steps+1][N][C] (block inputs / states; entry 0 = x0 / h0), save_xpe [steps][N][ld],
@@ -303,7 +305,8 @@ int glam_build_graph_tiles(const int32_t* graph_ptr, int64_t num_graphs, const i
                            size_t workspace_bytes, void* stream);
 int glam_edge_types(const float* edge_attr_sorted, int64_t num_edges, int edge_dim, uint8_t* etype, int32_t* meta, void* stream);
 int glam_message_stack_supported(int channels, int heads, int edge_dim);
-int glam_message_stack_fwd(const float* x0, const float* h0, const float* w_ext, int64_t ldw, const float* w_edge,
+int glam_message_stack_fwd(const float* x0, const float* h0, const float* x_raw, int raw_dim, const float* w_pre,
+                           const float* b_pre, int pre_act, float pre_act_param, const float* w_ext, int64_t ldw, const float* w_edge,
                            const float* att_edge, const float* w_scale, const float* bias, const float* w_ih,
                            const float* w_hh, const float* b_ih, const float* b_hh, const int32_t* tiles,
                            const int32_t* tile_meta, const int32_t* dst_rowptr, const int32_t* dst_src,
