@@ -178,6 +178,7 @@ struct MpParams {
     float slope, act_param;
     float* x_out; float* h_out;
     float* sX; float* sHH; float* sXPE; float* sAGG; float* sALPHA; float* sM; float* sRZN; float* sGH;
+    unsigned long long* phase_clock;         // profiling aid (glam_message_stack_phase_clock): [grid][16] cycles per phase, or NULL
 };
 
 __device__ __forceinline__ float4 lds128(const void* p) { return *reinterpret_cast<const float4*>(p); }
@@ -191,6 +192,27 @@ __device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, rcp_appro
 // CELU(alpha = 1) with exp from ex2.approx: absolute error <= 2e-7 (common.cuh's celu1 costs ~30 instructions per element)
 __device__ __forceinline__ float celu_fast(float x) { return x > 0.f ? x : ex2_approx(1.4426950408889634f * x) - 1.f; }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100a): per lane the same IEEE round-to-nearest result as the scalar forms
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 sigmoid2(float2 x) {
+    const float2 t = mul2(x, f2(-1.4426950408889634f));
+    const float2 d = add2(f2(ex2_approx(t.x), ex2_approx(t.y)), f2(1.f));
+    return f2(rcp_approx(d.x), rcp_approx(d.y));
+}
+__device__ __forceinline__ float2 tanh2(float2 x) {
+    const float2 t = mul2(x, f2(-2.8853900817779268f));
+    const float2 d = add2(f2(ex2_approx(t.x), ex2_approx(t.y)), f2(1.f));
+    return fma2(f2(2.f), f2(rcp_approx(d.x), rcp_approx(d.y)), f2(-1.f));
+}
+__device__ __forceinline__ float2 celu2(float2 x) {
+    const float2 t = mul2(x, f2(1.4426950408889634f));
+    const float2 e = add2(f2(ex2_approx(t.x), ex2_approx(t.y)), f2(-1.f));
+    return f2(x.x > 0.f ? x.x : e.x, x.y > 0.f ? x.y : e.y);
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
     uint32_t r[4];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
@@ -215,7 +237,6 @@ struct MpGeom {
     static constexpr int WROWS = NXP > NG ? NXP : NG;
     static constexpr int TM_XP = 0, TM_PRE = NXP, TM_GI = NXP + NS, TM_GH = NXP + NS + NG, TM_COLS = NXP + NS + 2 * NG;
     static constexpr int WQ = NT / 128;                                 // warps per TMEM lane quarter = threads per tile row
-    static constexpr int CPT = (NQ + WQ - 1) / WQ;                      // aggregation: 16-byte chunks of a row per thread
     static constexpr int JPW = (CQ + WQ - 1) / WQ;                      // epilogues: 4-channel chunks per warp
     static constexpr int REGB0 = NPA * kMpPanel, REGB1 = kMpM * LD * 4, REGB2 = kMpM * 3 * C * 4;
     static constexpr int REGB = ((REGB0 > REGB1 ? (REGB0 > REGB2 ? REGB0 : REGB2) : (REGB1 > REGB2 ? REGB1 : REGB2)) + 1023) / 1024 * 1024;
@@ -226,13 +247,14 @@ struct MpGeom {
     static constexpr int M_BAR = 0, M_RP = 4, M_REC = 136, M_ALPHA = M_REC + kMpMaxEdges, M_WE = M_ALPHA + kMpMaxEdges * H;
     static constexpr int M_AE = M_WE + kMpMaxDe * HC, M_U = M_AE + kMpMaxDe * H, M_BIAS = M_U + C * 2 * H, M_GB = M_BIAS + C;
     static constexpr int M_PRE = (M_GB + 4 * C + 3) / 4 * 4;            // input LinearBlock: W [C][raw_dim <= kMpMaxRaw] | b [C]
-    static constexpr int M_END = M_PRE + C * kMpMaxRaw + C;
+    static constexpr int M_CLK = (M_PRE + C * kMpMaxRaw + C + 3) / 4 * 4;  // 16 phase-cycle counters (profiling aid)
+    static constexpr int M_END = M_CLK + 16;
     static constexpr int SMEM = OFF_MISC + M_END * 4;
-    static_assert(NT == 512 || NT == 1024, "threads");
+    static_assert(NT % 128 == 0 && NT >= 256 && NT <= 1024, "threads");
     static_assert(KSX <= 5 && TQ <= 2, "tail panel holds 8 features per operand");
     static_assert(TM_COLS <= 512, "TMEM columns");
     static_assert(NPA <= 4 && NXP <= 256 && NG <= 256, "shape");
-    static_assert(CPT <= CQ, "an aggregation thread spans at most two heads");
+    static_assert(KAGG / 4 <= 32, "aggregation: one lane per 16-byte chunk of a row");
     static_assert((NS * 128) % 1024 == 0 && (NXP * 128) % 1024 == 0 && (NG * 128) % 1024 == 0, "panel alignment");
 };
 
@@ -270,8 +292,11 @@ mp_fused_kernel(const MpParams p) {
     float* We = misc + G::M_WE;  float* Ae = misc + G::M_AE;  float* U = misc + G::M_U;
     float* bias_s = misc + G::M_BIAS;  float* gb = misc + G::M_GB;
     float* Wp = misc + G::M_PRE;  float* bp = Wp + C * kMpMaxRaw;
+    unsigned int* clk = reinterpret_cast<unsigned int*>(misc + G::M_CLK);
     float* xp = reinterpret_cast<float*>(REG);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned int clk_start = (unsigned int)clock64();
+    const bool mma_thread = tid == NT - 32;                     // lane 0 of the last warp (it has no logit / softmax task) issues every MMA
     const int ntiles = p.meta[0], flags = p.meta[1];
 
     if (flags != 0) {
@@ -324,16 +349,17 @@ mp_fused_kernel(const MpParams p) {
                 sts128(q < 8 ? WI + pan_off(n, q) : WT + pan_off(n, 2 + q - 8), vi);
                 sts128(q < 8 ? WH + pan_off(n, q) : WT + pan_off(n, 4 + q - 8), vh);
             }
+            // gate biases per 4-channel chunk j: gb[(4 j + g) 4 + i], g = r (b_ir + b_hr) | z (b_iz + b_hz) | i_n | h_n
             for (int i = tid; i < 4 * C; i += NT) {
-                const int c = i >> 2, g = i & 3;
+                const int j = i >> 4, g = (i >> 2) & 3, c = 4 * j + (i & 3);
                 gb[i] = g == 0 ? p.b_ih[c] + p.b_hh[c] : g == 1 ? p.b_ih[C + c] + p.b_hh[C + c] : g == 2 ? p.b_ih[2 * C + c] : p.b_hh[2 * C + c];
             }
         }
         for (int i = tid; i < p.De * HC; i += NT) We[i] = p.w_edge[i];
         for (int i = tid; i < p.De * H; i += NT) Ae[i] = p.att_edge[i];
-        // exact logit weights, packed per head as float4 {u_i[c], u_j[c], u_i[c+1], u_j[c+1]}: one broadcast load per two channels
+        // exact logit weights per head and 4-channel chunk q: U[(h CQ + q) 8 + which 4 + i] = u_{i|j},h[4 q + i]
         for (int i = tid; i < C * 2 * H; i += NT) {
-            const int h = i / (2 * C), rem = i - h * 2 * C, c = rem >> 1, which = rem & 1;
+            const int h = i / (2 * C), rem = i - h * 2 * C, q = rem >> 3, which = (rem >> 2) & 1, c = 4 * q + (rem & 3);
             U[i] = p.w_ext[(size_t)c * p.ldw + HC + which * H + h];
         }
         for (int i = tid; i < C; i += NT) bias_s[i] = p.bias[i];
@@ -347,113 +373,188 @@ mp_fused_kernel(const MpParams p) {
 
     const uint32_t xm_a = smem_u32(XM), hm_a = smem_u32(HM), at_a = smem_u32(AT), reg_a = smem_u32(REG);
     const uint32_t wn_a = smem_u32(WN), wi_a = smem_u32(WI), wh_a = smem_u32(WH), wt_a = smem_u32(WT), ws_a = smem_u32(WS);
+    // operand descriptors once per kernel: every operand lives at a fixed shared-memory address, and a K-slice (+32 B) or panel
+    // step is a plain add on the encoded start-address field (bytes >> 4) — building a descriptor per MMA cost ~80 cycles each
+    // in the issuing thread (29 MMAs per step)
+    const uint64_t d_xm = make_smem_desc(xm_a, 16, 1024), d_hm = make_smem_desc(hm_a, 16, 1024), d_at = make_smem_desc(at_a, 16, 1024);
+    const uint64_t d_reg = make_smem_desc(reg_a, 16, 1024), d_wn = make_smem_desc(wn_a, 16, 1024), d_wi = make_smem_desc(wi_a, 16, 1024);
+    const uint64_t d_wh = make_smem_desc(wh_a, 16, 1024), d_wt = make_smem_desc(wt_a, 16, 1024), d_ws = make_smem_desc(ws_a, 16, 1024);
+    auto dsc = [](uint64_t base, uint32_t byte_off) { return base + (uint64_t)(byte_off >> 4); };
     const int q4 = warp & 3, cg = warp >> 2;                     // TMEM lane quarter of this warp / its index among the quarter's warps
     const int row = q4 * 32 + lane;                              // the tile row this thread owns in the epilogues
     const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
     uint32_t ph = 0;
     const int64_t NC = p.N * C;
 
+    // phase clock (profiling aid): thread 0 adds the cycles since its previous tick to counter I — only when a buffer was given
+    unsigned int clk_last = (unsigned int)clock64();
+    if (p.phase_clock && tid < 16) clk[tid] = tid == 14 ? clk_last - clk_start : 0;      // [14] = set-up (weights, TMEM)
+#define MP_TICK(I)                                                              \
+    if (p.phase_clock && tid == 0) {                                            \
+        const unsigned int now_ = (unsigned int)clock64();                      \
+        clk[I] += now_ - clk_last;                                              \
+        clk_last = now_;                                                        \
+    }
+    // ---------------------------------------------------------------- tile loop: the next tile's words travel in registers
+    // while the current tile computes (x rows or raw feature words, source / bond-type words, row pointers)
+    constexpr int XPF = (kMpM * CQ + NT - 1) / NT;               // float4 of x rows per thread
+    constexpr int RPF = (kMpM * kMpMaxRaw + NT - 1) / NT;        // raw feature words per thread (input LinearBlock mode)
+    constexpr int EPF = (kMpMaxEdges + NT - 1) / NT;             // edges per thread
+    float4 pfx[XPF];
+    float pfr[RPF];
+    int pfs[EPF], pft[EPF], pfp = 0;
+    const bool raw = p.x_raw != nullptr;
+#define MP_PREFETCH(TD)                                                                                              \
+    {                                                                                                                \
+        const int n0_ = (TD).x, nd_ = (TD).y - (TD).x, e0_ = (TD).z, ne_ = (TD).w - (TD).z;                          \
+        if (raw) {                                                                                                   \
+            const float* xr_ = p.x_raw + (size_t)n0_ * p.raw_dim;                                                    \
+            _Pragma("unroll") for (int k = 0; k < RPF; ++k) {                                                        \
+                const int i_ = k * NT + tid;                                                                         \
+                pfr[k] = i_ < nd_ * p.raw_dim ? __ldg(xr_ + i_) : 0.f;                                               \
+            }                                                                                                        \
+        } else {                                                                                                     \
+            const float4* xr_ = reinterpret_cast<const float4*>(p.x0 + (size_t)n0_ * C);                             \
+            _Pragma("unroll") for (int k = 0; k < XPF; ++k) {                                                        \
+                const int i_ = k * NT + tid;                                                                         \
+                pfx[k] = i_ < nd_ * CQ ? __ldg(xr_ + i_) : make_float4(0.f, 0.f, 0.f, 0.f);                          \
+            }                                                                                                        \
+        }                                                                                                            \
+        _Pragma("unroll") for (int k = 0; k < EPF; ++k) {                                                            \
+            const int e_ = k * NT + tid;                                                                             \
+            pfs[k] = e_ < ne_ ? __ldg(p.src + e0_ + e_) - n0_ : 0;                                                   \
+            pft[k] = e_ < ne_ ? (int)__ldg(p.etype + e0_ + e_) : 0;                                                  \
+        }                                                                                                            \
+        if (tid <= kMpM) pfp = tid <= nd_ ? __ldg(p.rowptr + n0_ + tid) - e0_ : ne_;                                 \
+    }
+    int4 td = p.tiles[blockIdx.x];
+    int4 tdn = (int)(blockIdx.x + gridDim.x) < ntiles ? p.tiles[blockIdx.x + gridDim.x] : make_int4(0, 0, 0, 0);
+    MP_PREFETCH(td)
+
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int4 td = p.tiles[t];
         const int n0 = td.x, nd = td.y - td.x, e0 = td.z, ne = td.w - td.z;
-        // ------------------------------------------------------------ tile load: x (and h) rows -> operand panels; index words
-        for (int i = tid; i < kMpM * CQ; i += NT) {
-            const int r = i / CQ, q = i - r * CQ;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f), hv = v;
-            if (r < nd) {
-                if (p.x_raw) {
-                    // the model's input LinearBlock (src_1gp/model.py:49: Linear(raw_dim -> C) + activation) applied while the
-                    // rows are loaded: exact fp32 FMAs (what the per-op path does for K % 4 != 0), x0 never exists in HBM
-                    const float* xr = p.x_raw + (size_t)(n0 + r) * p.raw_dim;
+        // ------------------------------------------------------------ tile load: registers -> operand panels / index words
+        if (raw) {
+            // the model's input LinearBlock (src_1gp/model.py:49: Linear(raw_dim -> C) + activation) applied while the tile is
+            // loaded: the raw rows are staged (the xp region is free here), then exact fp32 FMAs (what the per-op path does
+            // for K % 4 != 0); x0 never exists in HBM
+            float* rs = reinterpret_cast<float*>(REG);
+#pragma unroll
+            for (int k = 0; k < RPF; ++k) rs[k * NT + tid] = pfr[k];
+            __syncthreads();
+            for (int i = tid; i < kMpM * CQ; i += NT) {
+                const int r = i / CQ, q = i - r * CQ;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < nd) {
+                    const float* xr = rs + r * p.raw_dim;
                     const float* w = Wp + 4 * q * p.raw_dim;
                     v = lds128(bp + 4 * q);
                     for (int k = 0; k < p.raw_dim; ++k) {
-                        const float xv = __ldg(xr + k);
+                        const float xv = xr[k];
                         v.x = fmaf(xv, w[k], v.x); v.y = fmaf(xv, w[p.raw_dim + k], v.y);
                         v.z = fmaf(xv, w[2 * p.raw_dim + k], v.z); v.w = fmaf(xv, w[3 * p.raw_dim + k], v.w);
                     }
                     v.x = act_fwd(v.x, p.pre_act, p.pre_act_param); v.y = act_fwd(v.y, p.pre_act, p.pre_act_param);
                     v.z = act_fwd(v.z, p.pre_act, p.pre_act_param); v.w = act_fwd(v.w, p.pre_act, p.pre_act_param);
-                } else {
-                    v = __ldg(reinterpret_cast<const float4*>(p.x0 + (size_t)(n0 + r) * C) + q);
+                    if (SAVE && !p.conv_only) {
+                        reinterpret_cast<float4*>(p.sX + (size_t)(n0 + r) * C)[q] = v;
+                        if (!p.h0) reinterpret_cast<float4*>(p.sHH + (size_t)(n0 + r) * C)[q] = v;
+                    }
                 }
-                if (p.h0) hv = __ldg(reinterpret_cast<const float4*>(p.h0 + (size_t)(n0 + r) * C) + q);
-                if (SAVE && !p.conv_only) {
-                    reinterpret_cast<float4*>(p.sX + (size_t)(n0 + r) * C)[q] = v;
-                    reinterpret_cast<float4*>(p.sHH + (size_t)(n0 + r) * C)[q] = p.h0 ? hv : v;
+                sts128(q < 8 ? XM + pan_off(r, q) : AT + pan_off(r, q - 8), v);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < XPF; ++k) {
+                const int i = k * NT + tid;
+                if (i < kMpM * CQ) {
+                    const int r = i / CQ, q = i - r * CQ;
+                    const float4 v = pfx[k];                     // zeros beyond the tile's rows
+                    if (SAVE && !p.conv_only && r < nd) {
+                        reinterpret_cast<float4*>(p.sX + (size_t)(n0 + r) * C)[q] = v;
+                        if (!p.h0) reinterpret_cast<float4*>(p.sHH + (size_t)(n0 + r) * C)[q] = v;
+                    }
+                    sts128(q < 8 ? XM + pan_off(r, q) : AT + pan_off(r, q - 8), v);
                 }
             }
-            sts128(q < 8 ? XM + pan_off(r, q) : AT + pan_off(r, q - 8), v);
-            if (p.h0) sts128(q < 8 ? HM + pan_off(r, q) : AT + pan_off(r, 2 + q - 8), hv);
         }
-        for (int i = tid; i <= kMpM; i += NT) rp[i] = i <= nd ? p.rowptr[n0 + i] - e0 : ne;
-        for (int e = tid; e < ne; e += NT) rec[e] = (p.src[e0 + e] - n0) | ((int)p.etype[e0 + e] << 8);
+        if (p.h0)
+            for (int i = tid; i < kMpM * CQ; i += NT) {
+                const int r = i / CQ, q = i - r * CQ;
+                float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < nd) {
+                    hv = __ldg(reinterpret_cast<const float4*>(p.h0 + (size_t)(n0 + r) * C) + q);
+                    if (SAVE && !p.conv_only) reinterpret_cast<float4*>(p.sHH + (size_t)(n0 + r) * C)[q] = hv;
+                }
+                sts128(q < 8 ? HM + pan_off(r, q) : AT + pan_off(r, 2 + q - 8), hv);
+            }
+        if (tid <= kMpM) rp[tid] = pfp;
+#pragma unroll
+        for (int k = 0; k < EPF; ++k) {
+            const int e = k * NT + tid;
+            if (e < ne) rec[e] = pfs[k] | (pft[k] << 8);
+        }
         fence_proxy_async_smem();
         __syncthreads();
-        if (t + (int)gridDim.x < ntiles) {
-            // the next tile's rows and index words on their way into L2 while this tile computes
-            const int4 tn = p.tiles[t + gridDim.x];
-            const char* xb = p.x_raw ? reinterpret_cast<const char*>(p.x_raw + (size_t)tn.x * p.raw_dim)
-                                     : reinterpret_cast<const char*>(p.x0 + (size_t)tn.x * C);
-            const int xbytes = (tn.y - tn.x) * (p.x_raw ? p.raw_dim : C) * 4;
-            for (int o = tid * 128; o < xbytes; o += NT * 128) prefetch_l2(xb + o);
-            if (p.h0) { const char* hb = reinterpret_cast<const char*>(p.h0 + (size_t)tn.x * C); for (int o = tid * 128; o < (tn.y - tn.x) * C * 4; o += NT * 128) prefetch_l2(hb + o); }
-            const char* sb = reinterpret_cast<const char*>(p.src + tn.z);
-            for (int o = tid * 128; o < (tn.w - tn.z) * 4; o += NT * 128) prefetch_l2(sb + o);
-            const char* rb = reinterpret_cast<const char*>(p.rowptr + tn.x);
-            for (int o = tid * 128; o < (tn.y - tn.x + 1) * 4; o += NT * 128) prefetch_l2(rb + o);
-            const char* eb = reinterpret_cast<const char*>(p.etype + tn.z);
-            for (int o = tid * 128; o < (tn.w - tn.z); o += NT * 128) prefetch_l2(eb + o);
+        MP_TICK(0)
+        {
+            const int tnn = t + 2 * (int)gridDim.x;
+            const int4 tdnn = tnn < ntiles ? p.tiles[tnn] : make_int4(0, 0, 0, 0);
+            if (t + (int)gridDim.x < ntiles) MP_PREFETCH(tdn)
+            td = tdn; tdn = tdnn;                                // (the current tile's n0 / nd / e0 / ne were taken above)
         }
 
         for (int s = 0; s < p.steps; ++s) {
             const bool h_is_x = (s == 0 && p.h0 == nullptr);     // first step: h = x (layer.py:253-254)
-            // -------------------------------------------------------- P1: xp = x Wn on the tensor core; exact logit columns
-            if (tid == 0) {
+            // -------------------------------------------------------- P1: xp = x Wn on the tensor core (and, right behind it,
+            // gh = h W_hh^T, which depends on nothing this step computes); exact logit columns on the CUDA cores meanwhile
+            if (mma_thread) {
+                const unsigned int ci0 = (unsigned int)clock64();
                 tc_fence_after_sync();
                 const uint32_t idesc = make_idesc_tf32(kMpM, G::NXP, 0, 0);
 #pragma unroll
                 for (int ks = 0; ks < G::KSX; ++ks) {
-                    const uint32_t a = ks < 4 ? xm_a + ks * 32 : at_a;
-                    const uint32_t b = ks < 4 ? wn_a + ks * 32 : wt_a;
-                    mma_tf32_ss(tmem_base + G::TM_XP, make_smem_desc(a, 16, 1024), make_smem_desc(b, 16, 1024), idesc, ks > 0 ? 1u : 0u);
+                    const uint64_t a = ks < 4 ? dsc(d_xm, ks * 32) : d_at;
+                    const uint64_t b = ks < 4 ? dsc(d_wn, ks * 32) : d_wt;
+                    mma_tf32_ss(tmem_base + G::TM_XP, a, b, idesc, ks > 0 ? 1u : 0u);
                 }
                 mma_commit(mma_bar);
+                if (!p.conv_only) {
+                    const uint32_t idesc_g = make_idesc_tf32(kMpM, G::NG, 0, 0);
+#pragma unroll
+                    for (int ks = 0; ks < G::KSX; ++ks) {
+                        const uint64_t a = ks < 4 ? dsc(h_is_x ? d_xm : d_hm, ks * 32) : dsc(d_at, h_is_x ? 0 : 32);
+                        const uint64_t b = ks < 4 ? dsc(d_wh, ks * 32) : dsc(d_wt, 64);
+                        mma_tf32_ss(tmem_base + G::TM_GH, a, b, idesc_g, ks > 0 ? 1u : 0u);
+                    }                                            // completes before the P6 / P8 commits do (in-order)
+                }
+                if (p.phase_clock) clk[13] += (unsigned int)clock64() - ci0;
             }
-            // a thread per (row, head): s_i and s_j of that head from one pass over the row
+            // a thread per (row, head): s_i and s_j of that head from one pass over the row, two channels per FFMA2
             for (int task = tid; task < kMpM * H; task += NT) {
                 const int r = task & (kMpM - 1), h = task >> 7;
-                float ai = 0.f, aj = 0.f;
+                float2 ai = f2(0.f), aj = f2(0.f), bi = f2(0.f), bj = f2(0.f);
                 const float4* u = reinterpret_cast<const float4*>(U + h * 2 * C);
 #pragma unroll
                 for (int q = 0; q < CQ; ++q) {
                     const float4 v = q < 8 ? lds128(XM + pan_off(r, q)) : lds128(AT + pan_off(r, q - 8));
-                    const float4 u0 = u[2 * q], u1 = u[2 * q + 1];
-                    ai = fmaf(v.x, u0.x, ai); aj = fmaf(v.x, u0.y, aj); ai = fmaf(v.y, u0.z, ai); aj = fmaf(v.y, u0.w, aj);
-                    ai = fmaf(v.z, u1.x, ai); aj = fmaf(v.z, u1.y, aj); ai = fmaf(v.w, u1.z, ai); aj = fmaf(v.w, u1.w, aj);
+                    const float4 ui = u[2 * q], uj = u[2 * q + 1];
+                    ai = fma2(f2(v.x, v.y), f2(ui.x, ui.y), ai); bi = fma2(f2(v.z, v.w), f2(ui.z, ui.w), bi);
+                    aj = fma2(f2(v.x, v.y), f2(uj.x, uj.y), aj); bj = fma2(f2(v.z, v.w), f2(uj.z, uj.w), bj);
                 }
-                xp[r * LD + HC + h] = ai;
-                xp[r * LD + HC + H + h] = aj;
+                ai = add2(ai, bi); aj = add2(aj, bj);
+                xp[r * LD + HC + h] = ai.x + ai.y;
+                xp[r * LD + HC + H + h] = aj.x + aj.y;
             }
             if (LD > HC + 2 * H)
                 for (int i = tid; i < kMpM * (LD - HC - 2 * H); i += NT) {
                     const int r = i / (LD - HC - 2 * H), k = i - r * (LD - HC - 2 * H);
                     xp[r * LD + HC + 2 * H + k] = 0.f;
                 }
-            mbar_wait_guarded(mma_bar, ph); ph ^= 1u;
-            tc_fence_after_sync();
-            // -------------------------------------------------------- P2: TMEM -> xp tile (row-major, pitch LD)
-            for (int c0 = 16 * cg; c0 < HC; c0 += 16 * WQ) {
-                float v[16];
-                tmem_ld16(lane_base + G::TM_XP + c0, v);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (c0 + 4 * i < HC) sts128(xp + row * LD + c0 + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-            }
-            tc_fence_before_sync();
             __syncthreads();
-            if (SAVE) copy_out_flat<NT>(xp, p.sXPE + ((size_t)s * p.N + n0) * LD, nd * LD / 4);
-            // -------------------------------------------------------- P3: segment softmax per (destination, head)
+            MP_TICK(1)
+            // -------------------------------------------------------- P3: segment softmax per (destination, head) — needs only
+            // the logit columns, so it runs while the projection is still on the tensor core
             for (int task = tid; task < nd * H; task += NT) {
                 const int d = task / H, h = task - d * H;
                 const int beg = rp[d], end = rp[d + 1], deg = end - beg;
@@ -474,13 +575,13 @@ mp_fused_kernel(const MpParams p) {
                     float sum = 0.f;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {                // same summation order as the loop below
-                        l[k] = k < deg ? expf(l[k] - mx) : 0.f;
+                        l[k] = k < deg ? ex2_approx((l[k] - mx) * 1.4426950408889634f) : 0.f;
                         if (k < deg) sum += l[k];
                     }
-                    sum += 1e-16f;
+                    const float inv = 1.f / (sum + 1e-16f);      // PyG: exp(a - max) / (sum + 1e-16)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (k < deg) alpha_s[(beg + k) * H + h] = l[k] / sum;
+                        if (k < deg) alpha_s[(beg + k) * H + h] = l[k] * inv;
                     continue;
                 }
                 float mx = -INFINITY, sum = 0.f;
@@ -492,71 +593,84 @@ mp_fused_kernel(const MpParams p) {
                     mx = fmaxf(mx, l);
                 }
                 for (int e = beg; e < end; ++e) {
-                    const float x = expf(alpha_s[e * H + h] - mx);
+                    const float x = ex2_approx((alpha_s[e * H + h] - mx) * 1.4426950408889634f);
                     alpha_s[e * H + h] = x;
                     sum += x;
                 }
-                sum += 1e-16f;
-                for (int e = beg; e < end; ++e) alpha_s[e * H + h] = alpha_s[e * H + h] / sum;
+                const float inv = 1.f / (sum + 1e-16f);
+                for (int e = beg; e < end; ++e) alpha_s[e * H + h] = alpha_s[e * H + h] * inv;
             }
+            MP_TICK(2)
+            mbar_wait_guarded(mma_bar, ph); ph ^= 1u;
+            MP_TICK(3)
+            tc_fence_after_sync();
+            // -------------------------------------------------------- P2: TMEM -> xp tile (row-major, pitch LD)
+            for (int c0 = 16 * cg; c0 < HC; c0 += 16 * WQ) {
+                float v[16];
+                tmem_ld16(lane_base + G::TM_XP + c0, v);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (c0 + 4 * i < HC) sts128(xp + row * LD + c0 + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+            }
+            tc_fence_before_sync();
             __syncthreads();
+            MP_TICK(4)
             if (SAVE) {
+                copy_out_flat<NT>(xp, p.sXPE + ((size_t)s * p.N + n0) * LD, nd * LD / 4);
                 float* ad = p.sALPHA + ((size_t)s * p.E + e0) * H;
                 for (int i = tid; i < ne * H; i += NT) ad[i] = alpha_s[i];
             }
-            // -------------------------------------------------------- P4: aggregate into registers: WQ threads per destination
-            // row, each owning CPT consecutive 16-byte chunks of it (at most two heads)
-            float4 acc[G::CPT];
-            const int ad_ = tid / WQ, ak = tid - ad_ * WQ, aq0 = ak * G::CPT;
+            // -------------------------------------------------------- P4: aggregate: a warp takes RPW consecutive destination
+            // rows one after the other, lane = 16-byte chunk of the row (NQ of 32 lanes): the edge loop is warp-uniform (no
+            // divergence over in-degrees), x_j rows are read as contiguous runs, the record / alpha words are broadcasts and the
+            // lane's slice of weight_edge stays in registers (one float4 per bond type)
+            constexpr int NW = NT / 32, RPW = (kMpM + NW - 1) / NW;
+            float4 acc[RPW];
             {
+                const int lq = lane < NQ ? lane : 0, hq = lq / CQ;
+                float4 wt[kMpMaxDe];
 #pragma unroll
-                for (int i = 0; i < G::CPT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int h0 = min(H - 1, aq0 / CQ), h1 = min(H - 1, h0 + 1);
-                const int ib = (h0 + 1) * CQ - aq0;              // chunks i < ib belong to head h0, the rest to h1
-                const int beg = rp[ad_], end = rp[ad_ + 1];
-                int rc_n = 0; float c0_n = 0.f, c1_n = 0.f;
-                if (beg < end) { rc_n = rec[beg]; c0_n = alpha_s[beg * H + h0]; c1_n = alpha_s[beg * H + h1]; }
-                for (int e = beg; e < end; ++e) {
-                    const int rc = rc_n;
-                    const float c0 = c0_n, c1 = c1_n;
-                    if (e + 1 < end) { rc_n = rec[e + 1]; c0_n = alpha_s[(e + 1) * H + h0]; c1_n = alpha_s[(e + 1) * H + h1]; }
-                    const float4* xj = reinterpret_cast<const float4*>(xp + (rc & 0xff) * LD) + aq0;
-                    const float4* w = reinterpret_cast<const float4*>(We + (rc >> 8) * HC) + aq0;
+                for (int ty = 0; ty < kMpMaxDe; ++ty) wt[ty] = ty < p.De ? lds128(We + ty * HC + 4 * lq) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int i = 0; i < G::CPT; ++i) {
-                        if (aq0 + i < NQ) {
-                            const float4 a = xj[i], b = w[i];
-                            const float c = i < ib ? c0 : c1;
-                            acc[i].x = fmaf(c, a.x * b.x, acc[i].x); acc[i].y = fmaf(c, a.y * b.y, acc[i].y);
-                            acc[i].z = fmaf(c, a.z * b.z, acc[i].z); acc[i].w = fmaf(c, a.w * b.w, acc[i].w);
+                for (int k = 0; k < RPW; ++k) {
+                    const int d = warp * RPW + k;
+                    float2 a0 = f2(0.f), a1 = f2(0.f);
+                    if (d < kMpM) {
+                        const int beg = rp[d], end = rp[d + 1];
+                        for (int e = beg; e < end; ++e) {
+                            const int rc = rec[e], ty = rc >> 8;
+                            const float c = alpha_s[e * H + hq];
+                            const float4 xj = lds128(xp + (rc & 0xff) * LD + 4 * lq);
+                            const float4 w = ty == 0 ? wt[0] : ty == 1 ? wt[1] : ty == 2 ? wt[2] : wt[3];
+                            a0 = fma2(f2(c), mul2(f2(xj.x, xj.y), f2(w.x, w.y)), a0);
+                            a1 = fma2(f2(c), mul2(f2(xj.z, xj.w), f2(w.z, w.w)), a1);
                         }
                     }
+                    acc[k] = make_float4(a0.x, a0.y, a1.x, a1.y);
                 }
             }
             __syncthreads();                                     // every read of the xp tile is done: its bytes become the agg panels
+            MP_TICK(5)
             // -------------------------------------------------------- P5: registers -> agg operand panels
+            if (lane < G::KAGG / 4) {                            // chunks in [NQ, KAGG/4) are the K padding: zeros
 #pragma unroll
-            for (int i = 0; i < G::CPT; ++i) {
-                const int q = aq0 + i;
-                if (q < G::KAGG / 4)                             // chunks in [NQ, KAGG/4) are the K padding: zeros
-                    sts128(REG + (q >> 3) * kMpPanel + pan_off(ad_, q), q < NQ ? acc[i] : make_float4(0.f, 0.f, 0.f, 0.f));
-            }
-            if (WQ * G::CPT < G::KAGG / 4)
-                for (int i = tid; i < kMpM * (G::KAGG / 4 - WQ * G::CPT); i += NT) {
-                    const int r = i / (G::KAGG / 4 - WQ * G::CPT), q = WQ * G::CPT + i - r * (G::KAGG / 4 - WQ * G::CPT);
-                    sts128(REG + (q >> 3) * kMpPanel + pan_off(r, q), make_float4(0.f, 0.f, 0.f, 0.f));
+                for (int k = 0; k < RPW; ++k) {
+                    const int d = warp * RPW + k;
+                    if (d < kMpM) sts128(REG + (lane >> 3) * kMpPanel + pan_off(d, lane), lane < NQ ? acc[k] : make_float4(0.f, 0.f, 0.f, 0.f));
                 }
+            }
             fence_proxy_async_smem();
             __syncthreads();
+            MP_TICK(6)
             // -------------------------------------------------------- P6: pre = agg Wscale
-            if (tid == 0) {
+            if (mma_thread) {
                 tc_fence_after_sync();
                 const uint32_t idesc = make_idesc_tf32(kMpM, G::NS, 0, 0);
 #pragma unroll
                 for (int ks = 0; ks < G::KSA; ++ks) {
                     const uint32_t pan = ks >> 2, within = (ks & 3) * 32;
-                    mma_tf32_ss(tmem_base + G::TM_PRE, make_smem_desc(reg_a + pan * kMpPanel + within, 16, 1024),
-                                make_smem_desc(ws_a + pan * (G::NS * 128) + within, 16, 1024), idesc, ks > 0 ? 1u : 0u);
+                    mma_tf32_ss(tmem_base + G::TM_PRE, dsc(d_reg, pan * kMpPanel + within), dsc(d_ws, pan * (G::NS * 128) + within), idesc,
+                                ks > 0 ? 1u : 0u);
                 }
                 mma_commit(mma_bar);
             }
@@ -568,6 +682,7 @@ mp_fused_kernel(const MpParams p) {
                 }
             }
             mbar_wait_guarded(mma_bar, ph); ph ^= 1u;
+            MP_TICK(7)
             tc_fence_after_sync();
             if (SAVE) __syncthreads();                           // agg copy-out done before m overwrites panel 0
             // -------------------------------------------------------- P7: epilogue: + bias, CELU -> m operand panels (or the conv output)
@@ -579,46 +694,42 @@ mp_fused_kernel(const MpParams p) {
                     float v[4];
                     tmem_ld4(lane_base + G::TM_PRE + 4 * cq, v);
                     const float4 b = lds128(bias_s + 4 * cq);
-                    float4 m4 = make_float4(v[0] + b.x, v[1] + b.y, v[2] + b.z, v[3] + b.w);
+                    float2 m01 = add2(f2(v[0], v[1]), f2(b.x, b.y)), m23 = add2(f2(v[2], v[3]), f2(b.z, b.w));
                     if (p.conv_only) {
-                        sts128(ostage + row * C + 4 * cq, m4);
+                        sts128(ostage + row * C + 4 * cq, make_float4(m01.x, m01.y, m23.x, m23.y));
                     } else {
-                        m4.x = celu_fast(m4.x); m4.y = celu_fast(m4.y); m4.z = celu_fast(m4.z); m4.w = celu_fast(m4.w);
-                        sts128(cq < 8 ? REG + pan_off(row, cq) : AT + pan_off(row, 4 + cq - 8), m4);
+                        m01 = celu2(m01); m23 = celu2(m23);
+                        sts128(cq < 8 ? REG + pan_off(row, cq) : AT + pan_off(row, 4 + cq - 8), make_float4(m01.x, m01.y, m23.x, m23.y));
                     }
                 }
             }
             tc_fence_before_sync();
             fence_proxy_async_smem();
             __syncthreads();
+            MP_TICK(8)
             if (p.conv_only) {
                 copy_out_flat<NT>(ostage, p.x_out + (size_t)n0 * C, nd * CQ);
                 __syncthreads();
                 continue;
             }
-            // -------------------------------------------------------- P8: gi = m W_ih^T, gh = h W_hh^T
-            if (tid == 0) {
+            // -------------------------------------------------------- P8: gi = m W_ih^T (gh was issued with the projection)
+            if (mma_thread) {
                 tc_fence_after_sync();
                 const uint32_t idesc = make_idesc_tf32(kMpM, G::NG, 0, 0);
 #pragma unroll
                 for (int ks = 0; ks < G::KSX; ++ks) {
-                    const uint32_t a = ks < 4 ? reg_a + ks * 32 : at_a + 64;
-                    const uint32_t b = ks < 4 ? wi_a + ks * 32 : wt_a + 32;
-                    mma_tf32_ss(tmem_base + G::TM_GI, make_smem_desc(a, 16, 1024), make_smem_desc(b, 16, 1024), idesc, ks > 0 ? 1u : 0u);
-                }
-#pragma unroll
-                for (int ks = 0; ks < G::KSX; ++ks) {
-                    const uint32_t a = ks < 4 ? (h_is_x ? xm_a : hm_a) + ks * 32 : at_a + (h_is_x ? 0 : 32);
-                    const uint32_t b = ks < 4 ? wh_a + ks * 32 : wt_a + 64;
-                    mma_tf32_ss(tmem_base + G::TM_GH, make_smem_desc(a, 16, 1024), make_smem_desc(b, 16, 1024), idesc, ks > 0 ? 1u : 0u);
+                    const uint64_t a = ks < 4 ? dsc(d_reg, ks * 32) : dsc(d_at, 64);
+                    const uint64_t b = ks < 4 ? dsc(d_wi, ks * 32) : dsc(d_wt, 32);
+                    mma_tf32_ss(tmem_base + G::TM_GI, a, b, idesc, ks > 0 ? 1u : 0u);
                 }
                 mma_commit(mma_bar);
             }
             if (SAVE) copy_out_panels<CQ, NT>(REG, AT, 2, p.sM + ((size_t)s * p.N + n0) * C, nd);
             mbar_wait_guarded(mma_bar, ph); ph ^= 1u;
+            MP_TICK(9)
             tc_fence_after_sync();
             if (SAVE) __syncthreads();                           // m copy-out done before the r|z|n staging overwrites the region
-            // -------------------------------------------------------- P9: gates; h' and x' in place
+            // -------------------------------------------------------- P9: gates on channel pairs; h' and x' in place
             float* rstage = reinterpret_cast<float*>(REG);       // save mode: r|z|n rows, pitch 3C
             float4 ghn[G::JPW];
 #pragma unroll
@@ -635,38 +746,40 @@ mp_fused_kernel(const MpParams p) {
                     uint8_t* hdst = j < 8 ? HM + pan_off(row, j) : AT + pan_off(row, 2 + j - 8);
                     const float4 hv = lds128(hsrc);
                     const float4 xv = p.res ? lds128(xdst) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 r, z, nn, gn, hw, xo;
-#define MP_GATE(k, i)                                                                          \
-    {                                                                                          \
-        const float4 b = lds128(gb + 4 * (4 * j + i));                                         \
-        gn.k = v[20 + i] + b.w;                                                                \
-        r.k = fast_sigmoid(v[i] + v[12 + i] + b.x);                                            \
-        z.k = fast_sigmoid(v[4 + i] + v[16 + i] + b.y);                                        \
-        nn.k = fast_tanh((v[8 + i] + b.z) + r.k * gn.k);                                       \
-        hw.k = (1.f - z.k) * nn.k + z.k * hv.k;                                                \
-        xo.k = hw.k + xv.k;                                                                    \
+                    const float4 b_r = lds128(gb + 16 * j), b_z = lds128(gb + 16 * j + 4), b_n = lds128(gb + 16 * j + 8), b_h = lds128(gb + 16 * j + 12);
+                    float2 r[2], z[2], nn[2], gn[2], hw[2], xo[2];
+#define MP_GATE2(k, i, BR, BZ, BN, BH, HV, XV)                                                                    \
+    {                                                                                                              \
+        gn[k] = add2(f2(v[20 + i], v[21 + i]), BH);                                                                \
+        r[k] = sigmoid2(add2(add2(f2(v[i], v[i + 1]), f2(v[12 + i], v[13 + i])), BR));                             \
+        z[k] = sigmoid2(add2(add2(f2(v[4 + i], v[5 + i]), f2(v[16 + i], v[17 + i])), BZ));                         \
+        nn[k] = tanh2(fma2(r[k], gn[k], add2(f2(v[8 + i], v[9 + i]), BN)));                                        \
+        hw[k] = fma2(fma2(z[k], f2(-1.f), f2(1.f)), nn[k], mul2(z[k], HV));                                        \
+        xo[k] = add2(hw[k], XV);                                                                                   \
     }
-                    MP_GATE(x, 0) MP_GATE(y, 1) MP_GATE(z, 2) MP_GATE(w, 3)
-#undef MP_GATE
-                    if (p.act == ACT_CELU) { xo.x = celu_fast(xo.x); xo.y = celu_fast(xo.y); xo.z = celu_fast(xo.z); xo.w = celu_fast(xo.w); }
+                    MP_GATE2(0, 0, f2(b_r.x, b_r.y), f2(b_z.x, b_z.y), f2(b_n.x, b_n.y), f2(b_h.x, b_h.y), f2(hv.x, hv.y), f2(xv.x, xv.y))
+                    MP_GATE2(1, 2, f2(b_r.z, b_r.w), f2(b_z.z, b_z.w), f2(b_n.z, b_n.w), f2(b_h.z, b_h.w), f2(hv.z, hv.w), f2(xv.z, xv.w))
+#undef MP_GATE2
+                    if (p.act == ACT_CELU) { xo[0] = celu2(xo[0]); xo[1] = celu2(xo[1]); }
                     else if (p.act != ACT_NONE) {                // relu = leaky with slope 0
                         const float sl = p.act == ACT_LEAKY ? p.act_param : 0.f;
-                        xo.x = xo.x > 0.f ? xo.x : sl * xo.x; xo.y = xo.y > 0.f ? xo.y : sl * xo.y;
-                        xo.z = xo.z > 0.f ? xo.z : sl * xo.z; xo.w = xo.w > 0.f ? xo.w : sl * xo.w;
+                        xo[0].x = xo[0].x > 0.f ? xo[0].x : sl * xo[0].x; xo[0].y = xo[0].y > 0.f ? xo[0].y : sl * xo[0].y;
+                        xo[1].x = xo[1].x > 0.f ? xo[1].x : sl * xo[1].x; xo[1].y = xo[1].y > 0.f ? xo[1].y : sl * xo[1].y;
                     }
-                    sts128(hdst, hw);
-                    sts128(xdst, xo);
+                    sts128(hdst, make_float4(hw[0].x, hw[0].y, hw[1].x, hw[1].y));
+                    sts128(xdst, make_float4(xo[0].x, xo[0].y, xo[1].x, xo[1].y));
                     if (SAVE) {
-                        sts128(rstage + row * 3 * C + 4 * j, r);
-                        sts128(rstage + row * 3 * C + C + 4 * j, z);
-                        sts128(rstage + row * 3 * C + 2 * C + 4 * j, nn);
-                        ghn[jj] = gn;
+                        sts128(rstage + row * 3 * C + 4 * j, make_float4(r[0].x, r[0].y, r[1].x, r[1].y));
+                        sts128(rstage + row * 3 * C + C + 4 * j, make_float4(z[0].x, z[0].y, z[1].x, z[1].y));
+                        sts128(rstage + row * 3 * C + 2 * C + 4 * j, make_float4(nn[0].x, nn[0].y, nn[1].x, nn[1].y));
+                        ghn[jj] = make_float4(gn[0].x, gn[0].y, gn[1].x, gn[1].y);
                     }
                 }
             }
             tc_fence_before_sync();
             fence_proxy_async_smem();
             __syncthreads();
+            MP_TICK(10)
             // -------------------------------------------------------- outputs of the step
             if (SAVE) {
                 copy_out_panels<CQ, NT>(XM, AT, 0, p.sX + (size_t)(s + 1) * NC + (size_t)n0 * C, nd);
@@ -688,9 +801,14 @@ mp_fused_kernel(const MpParams p) {
                     copy_out_panels<CQ, NT>(XM, AT, 0, p.x_out + (p.keep_all ? (size_t)s * NC : (size_t)0) + (size_t)n0 * C, nd);
                 if (last && p.h_out) copy_out_panels<CQ, NT>(HM, AT, 1, p.h_out + (size_t)n0 * C, nd);
             }
+            MP_TICK(11)
         }
         __syncthreads();                                         // all reads of the tile (copy-outs) done before the next tile load
+        MP_TICK(12)
     }
+#undef MP_PREFETCH
+#undef MP_TICK
+    if (p.phase_clock && tid < 16) p.phase_clock[blockIdx.x * 16 + tid] = clk[tid];
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512u);
@@ -698,6 +816,7 @@ mp_fused_kernel(const MpParams p) {
 
 bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+unsigned long long* g_mp_phase_clock = nullptr;                  // glam_message_stack_phase_clock
 int g_mp_threads = 512;                                          // GLAM_B200_MP_THREADS=1024 selects the 32-warp variant (A/B timing)
 
 template <int CQ, int H, int NT>
@@ -713,7 +832,12 @@ int mp_launch_nt(const MpParams& p, bool save, cudaStream_t stream) {
 }
 template <int CQ, int H>
 int mp_launch(const MpParams& p, bool save, cudaStream_t stream) {
-    return g_mp_threads == 1024 ? mp_launch_nt<CQ, H, 1024>(p, save, stream) : mp_launch_nt<CQ, H, 512>(p, save, stream);
+    switch (g_mp_threads) {
+        case 384: return mp_launch_nt<CQ, H, 384>(p, save, stream);
+        case 768: return mp_launch_nt<CQ, H, 768>(p, save, stream);
+        case 1024: return mp_launch_nt<CQ, H, 1024>(p, save, stream);
+        default: return mp_launch_nt<CQ, H, 512>(p, save, stream);
+    }
 }
 
 }  // namespace
@@ -770,6 +894,11 @@ extern "C" int glam_edge_types(const float* edge_attr_sorted, int64_t num_edges,
     return 0;
 }
 
+extern "C" int glam_message_stack_phase_clock(unsigned long long* cycles) {
+    g_mp_phase_clock = cycles;
+    return 0;
+}
+
 extern "C" int glam_message_stack_supported(int channels, int heads, int edge_dim) {
     if (g_math_mode_get() == 0) return 0;                        // exact-fp32 mode keeps the CUDA-core projections
     if (heads != 3 || edge_dim < 1 || edge_dim > kMpMaxDe) return 0;
@@ -812,11 +941,11 @@ extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const fl
     p.rowptr = dst_rowptr; p.src = dst_src; p.etype = etype; p.N = num_nodes; p.E = num_edges; p.De = edge_dim; p.steps = steps;
     p.act = act; p.res = res; p.conv_only = conv_only; p.keep_all = keep_all; p.slope = negative_slope; p.act_param = act_param;
     p.x_out = x_out; p.h_out = h_out; p.sX = save_x; p.sHH = save_h; p.sXPE = save_xpe; p.sAGG = save_agg; p.sALPHA = save_alpha;
-    p.sM = save_m; p.sRZN = save_rzn; p.sGH = save_gh;
+    p.sM = save_m; p.sRZN = save_rzn; p.sGH = save_gh; p.phase_clock = g_mp_phase_clock;
     int rc = 0;
     cudaStream_t stream = (cudaStream_t)stream_;
     static const int threads_env = [] { const char* e = getenv("GLAM_B200_MP_THREADS"); return e ? atoi(e) : 0; }();
-    if (threads_env == 512 || threads_env == 1024) g_mp_threads = threads_env;
+    if (threads_env == 384 || threads_env == 512 || threads_env == 768 || threads_env == 1024) g_mp_threads = threads_env;
     switch (channels) {
         case 32: rc = mp_launch<8, 3>(p, save, stream); break;
         case 36: rc = mp_launch<9, 3>(p, save, stream); break;

@@ -305,6 +305,11 @@ int glam_build_graph_tiles(const int32_t* graph_ptr, int64_t num_graphs, const i
                            size_t workspace_bytes, void* stream);
 int glam_edge_types(const float* edge_attr_sorted, int64_t num_edges, int edge_dim, uint8_t* etype, int32_t* meta, void* stream);
 int glam_message_stack_supported(int channels, int heads, int edge_dim);
+/* Profiling aid: when `cycles` (device memory, [148][16] unsigned 64-bit) is not NULL, every following glam_message_stack_fwd
+ * launch has thread 0 of each CTA add the SM cycles spent between consecutive phase boundaries to cycles[cta][phase]
+ * (0 tile load, 1 logits, 2 softmax, 3 projection wait, 4 TMEM -> xp tile, 5 aggregation, 6 agg panels, 7 scale wait,
+ * 8 CELU epilogue, 9 GRU wait, 10 gates, 11 step outputs, 12 tile end).  Results are unaffected.  NULL switches it off. */
+int glam_message_stack_phase_clock(unsigned long long* cycles);
 int glam_message_stack_fwd(const float* x0, const float* h0, const float* x_raw, int raw_dim, const float* w_pre,
                            const float* b_pre, int pre_act, float pre_act_param, const float* w_ext, int64_t ldw, const float* w_edge,
                            const float* att_edge, const float* w_scale, const float* bias, const float* w_ih,

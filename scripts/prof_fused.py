@@ -1,5 +1,5 @@
 """Timing / profiling driver of the fused message-stack kernel at the bench shape (4096 graphs; or argv[2] graphs).
-    python scripts/prof_fused.py [time|ncu] [graphs]
+    python scripts/prof_fused.py [time|ncu|phases] [graphs]
 `time`: CUDA-event medians (L2 flushed between launches) of the eval, save and conv-only modes next to the per-op path.
 `ncu` : a few launches of each mode for `ncu -k regex:mp_fused`."""
 import os
@@ -75,7 +75,21 @@ def timeit(name, fn, nbytes, reps=9):
 n, e = N / graphs, E / graphs
 blk_bytes = graphs * (4 * (4 * n * C + e * De) + 8 * e + 4 * (n + 1))          # MessageBlock fwd per step
 conv_bytes = graphs * (4 * (2 * n * C + e * De) + 8 * e + 4 * (n + 1))         # TripletMessage fwd
-if mode == "ncu":
+PHASES = ["tile load", "logits", "softmax", "proj wait", "tmem->xp", "aggregate", "agg panels", "scale wait", "celu epi", "gru wait",
+          "gates", "outputs", "tile end"]
+if mode == "phases":
+    lib = _lib.load()
+    clk = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+    for name, fn in (("eval x3", f_eval), ("save x3", f_save), ("conv only", f_conv)):
+        fn(); torch.cuda.synchronize()
+        lib.glam_message_stack_phase_clock(clk.data_ptr())
+        fn(); torch.cuda.synchronize()
+        lib.glam_message_stack_phase_clock(None)
+        c = clk.double().mean(0).cpu()
+        tot = float(c[:13].sum())
+        print(f"{name}: {tot/1.965e3:.1f} us of SM cycles per CTA; " + ", ".join(f"{n} {100*float(c[i])/tot:.1f}%" for i, n in enumerate(PHASES))
+              + f"; [issue of the projection + gh MMAs {100*float(c[13])/tot:.1f}%; set-up before the first tile {float(c[14])/1.965e3:.1f} us]")
+elif mode == "ncu":
     for fn in (f_eval, f_save, f_conv):
         fn(); fn()
     torch.cuda.synchronize()
