@@ -33,22 +33,21 @@
 #include <cuda.h>
 #include <math_constants.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "mp_common.cuh"
 
 namespace glam {
 
 using namespace tc;
+using namespace mp;
 
 int g_math_mode_get();
+unsigned long long* g_mp_phase_clock = nullptr;                  // glam_message_stack_phase_clock (shared with mp_fused_bwd.cu)
 
 namespace {
 
-constexpr int kMpM = 128;                    // rows per tile = UMMA M
-constexpr int kMpMaxEdges = 768;             // in-edges per tile (molecular tiles: ~2.2 per atom)
-constexpr int kMpMaxDe = 4;                  // bond types
-constexpr int kMpMaxRaw = 16;                // raw atom features of the optional input LinearBlock
-constexpr int kMpPanel = kMpM * kPanelRowBytes;      // 16 KB
 
 enum : int { kFlagNodes = 1, kFlagEdges = 2, kFlagCross = 4, kFlagEdgeAttr = 8 };
 
@@ -178,51 +177,10 @@ struct MpParams {
     float slope, act_param;
     float* x_out; float* h_out;
     float* sX; float* sHH; float* sXPE; float* sAGG; float* sALPHA; float* sM; float* sRZN; float* sGH;
+    float* sGT;                              // tile-blocked gate save for the one-launch backward (replaces sRZN / sGH), or NULL
     unsigned long long* phase_clock;         // profiling aid (glam_message_stack_phase_clock): [grid][16] cycles per phase, or NULL
 };
 
-__device__ __forceinline__ float4 lds128(const void* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void sts128(void* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-// gate non-linearities straight on the SFU: ex2.approx / rcp.approx (relative error ~2^-22 each), 4 instructions per
-// sigmoid — the gate epilogue was 31 % of the kernel's instructions with the library forms
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * x)), -1.f); }
-// CELU(alpha = 1) with exp from ex2.approx: absolute error <= 2e-7 (common.cuh's celu1 costs ~30 instructions per element)
-__device__ __forceinline__ float celu_fast(float x) { return x > 0.f ? x : ex2_approx(1.4426950408889634f * x) - 1.f; }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100a): per lane the same IEEE round-to-nearest result as the scalar forms
-__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
-__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float2 sigmoid2(float2 x) {
-    const float2 t = mul2(x, f2(-1.4426950408889634f));
-    const float2 d = add2(f2(ex2_approx(t.x), ex2_approx(t.y)), f2(1.f));
-    return f2(rcp_approx(d.x), rcp_approx(d.y));
-}
-__device__ __forceinline__ float2 tanh2(float2 x) {
-    const float2 t = mul2(x, f2(-2.8853900817779268f));
-    const float2 d = add2(f2(ex2_approx(t.x), ex2_approx(t.y)), f2(1.f));
-    return fma2(f2(2.f), f2(rcp_approx(d.x), rcp_approx(d.y)), f2(-1.f));
-}
-__device__ __forceinline__ float2 celu2(float2 x) {
-    const float2 t = mul2(x, f2(1.4426950408889634f));
-    const float2 e = add2(f2(ex2_approx(t.x), ex2_approx(t.y)), f2(-1.f));
-    return f2(x.x > 0.f ? x.x : e.x, x.y > 0.f ? x.y : e.y);
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
-    uint32_t r[4];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// byte offset of the 16-byte chunk q (4 features) of row r inside a 128-byte-row SWIZZLE_128B panel
-__device__ __forceinline__ uint32_t pan_off(int r, int q) { return (uint32_t)(r * kPanelRowBytes + (((q & 7) ^ (r & 7)) << 4)); }
 
 template <int CQ, int H, int NT>
 struct MpGeom {
@@ -700,6 +658,8 @@ mp_fused_kernel(const MpParams p) {
                     } else {
                         m01 = celu2(m01); m23 = celu2(m23);
                         sts128(cq < 8 ? REG + pan_off(row, cq) : AT + pan_off(row, 4 + cq - 8), make_float4(m01.x, m01.y, m23.x, m23.y));
+                        if (SAVE && p.sGT && row < nd)
+                            reinterpret_cast<float4*>(p.sGT + ((size_t)s * p.N + n0) * 7 * C)[(6 * CQ + cq) * nd + row] = make_float4(m01.x, m01.y, m23.x, m23.y);
                     }
                 }
             }
@@ -768,7 +728,19 @@ mp_fused_kernel(const MpParams p) {
                     }
                     sts128(hdst, make_float4(hw[0].x, hw[0].y, hw[1].x, hw[1].y));
                     sts128(xdst, make_float4(xo[0].x, xo[0].y, xo[1].x, xo[1].y));
-                    if (SAVE) {
+                    if (SAVE && p.sGT) {
+                        // tile-blocked save for the one-launch backward: slot-major inside the tile ([r z n gh_n h x' m] x CQ chunks,
+                        // then the tile's rows), so a warp's 32 rows of one chunk are 512 contiguous bytes here AND in its gate phase
+                        if (row < nd) {
+                            float4* gt = reinterpret_cast<float4*>(p.sGT + ((size_t)s * p.N + n0) * 7 * C);
+                            gt[j * nd + row] = make_float4(r[0].x, r[0].y, r[1].x, r[1].y);
+                            gt[(CQ + j) * nd + row] = make_float4(z[0].x, z[0].y, z[1].x, z[1].y);
+                            gt[(2 * CQ + j) * nd + row] = make_float4(nn[0].x, nn[0].y, nn[1].x, nn[1].y);
+                            gt[(3 * CQ + j) * nd + row] = make_float4(gn[0].x, gn[0].y, gn[1].x, gn[1].y);
+                            gt[(4 * CQ + j) * nd + row] = hv;
+                            gt[(5 * CQ + j) * nd + row] = make_float4(xo[0].x, xo[0].y, xo[1].x, xo[1].y);
+                        }
+                    } else if (SAVE) {
                         sts128(rstage + row * 3 * C + 4 * j, make_float4(r[0].x, r[0].y, r[1].x, r[1].y));
                         sts128(rstage + row * 3 * C + C + 4 * j, make_float4(z[0].x, z[0].y, z[1].x, z[1].y));
                         sts128(rstage + row * 3 * C + 2 * C + 4 * j, make_float4(nn[0].x, nn[0].y, nn[1].x, nn[1].y));
@@ -784,17 +756,19 @@ mp_fused_kernel(const MpParams p) {
             if (SAVE) {
                 copy_out_panels<CQ, NT>(XM, AT, 0, p.sX + (size_t)(s + 1) * NC + (size_t)n0 * C, nd);
                 copy_out_panels<CQ, NT>(HM, AT, 1, p.sHH + (size_t)(s + 1) * NC + (size_t)n0 * C, nd);
-                copy_out_flat<NT>(rstage, p.sRZN + ((size_t)s * p.N + n0) * 3 * C, nd * 3 * CQ);
-                __syncthreads();
-                float* gstage = reinterpret_cast<float*>(REG);   // gh_n rows, pitch C
+                if (!p.sGT) {
+                    copy_out_flat<NT>(rstage, p.sRZN + ((size_t)s * p.N + n0) * 3 * C, nd * 3 * CQ);
+                    __syncthreads();
+                    float* gstage = reinterpret_cast<float*>(REG);   // gh_n rows, pitch C
 #pragma unroll
-                for (int jj = 0; jj < G::JPW; ++jj) {
-                    const int j = cg + WQ * jj;
-                    if (j < CQ) sts128(gstage + row * C + 4 * j, ghn[jj]);
+                    for (int jj = 0; jj < G::JPW; ++jj) {
+                        const int j = cg + WQ * jj;
+                        if (j < CQ) sts128(gstage + row * C + 4 * j, ghn[jj]);
+                    }
+                    __syncthreads();
+                    copy_out_flat<NT>(gstage, p.sGH + ((size_t)s * p.N + n0) * C, nd * CQ);
                 }
-                __syncthreads();
-                copy_out_flat<NT>(gstage, p.sGH + ((size_t)s * p.N + n0) * C, nd * CQ);
-                __syncthreads();                                 // before the next step's P1 writes the logit columns into the region
+                __syncthreads();                                 // before the next step's P1 writes the logit columns into the region / the panels
             } else {
                 const bool last = s == p.steps - 1;
                 if (p.keep_all || last)
@@ -808,7 +782,7 @@ mp_fused_kernel(const MpParams p) {
     }
 #undef MP_PREFETCH
 #undef MP_TICK
-    if (p.phase_clock && tid < 16) p.phase_clock[blockIdx.x * 16 + tid] = clk[tid];
+    if (p.phase_clock && tid < 16) p.phase_clock[blockIdx.x * 32 + tid] = clk[tid];
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512u);
@@ -816,28 +790,18 @@ mp_fused_kernel(const MpParams p) {
 
 bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-unsigned long long* g_mp_phase_clock = nullptr;                  // glam_message_stack_phase_clock
-int g_mp_threads = 512;                                          // GLAM_B200_MP_THREADS=1024 selects the 32-warp variant (A/B timing)
+constexpr int kMpThreads = 512;                                 // 384 / 768 / 1024 threads measured slower
 
-template <int CQ, int H, int NT>
-int mp_launch_nt(const MpParams& p, bool save, cudaStream_t stream) {
-    using G = MpGeom<CQ, H, NT>;
+template <int CQ, int H>
+int mp_launch(const MpParams& p, bool save, cudaStream_t stream) {
+    using G = MpGeom<CQ, H, kMpThreads>;
     auto go = [&](auto kernel) -> int {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         if (e != cudaSuccess) { set_error("glam_message_stack_fwd: cudaFuncSetAttribute(%d bytes): %s", G::SMEM, cudaGetErrorString(e)); return (int)e; }
-        kernel<<<kNumSMs, NT, G::SMEM, stream>>>(p);
+        kernel<<<kNumSMs, kMpThreads, G::SMEM, stream>>>(p);
         return 0;
     };
-    return save ? go(mp_fused_kernel<CQ, H, NT, true>) : go(mp_fused_kernel<CQ, H, NT, false>);
-}
-template <int CQ, int H>
-int mp_launch(const MpParams& p, bool save, cudaStream_t stream) {
-    switch (g_mp_threads) {
-        case 384: return mp_launch_nt<CQ, H, 384>(p, save, stream);
-        case 768: return mp_launch_nt<CQ, H, 768>(p, save, stream);
-        case 1024: return mp_launch_nt<CQ, H, 1024>(p, save, stream);
-        default: return mp_launch_nt<CQ, H, 512>(p, save, stream);
-    }
+    return save ? go(mp_fused_kernel<CQ, H, kMpThreads, true>) : go(mp_fused_kernel<CQ, H, kMpThreads, false>);
 }
 
 }  // namespace
@@ -914,7 +878,7 @@ extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const fl
                                       int edge_dim, int steps, float negative_slope, int act, float act_param, int res,
                                       int conv_only, int keep_all, float* x_out, float* h_out, float* save_x, float* save_h,
                                       float* save_xpe, float* save_agg, float* save_alpha, float* save_m, float* save_rzn,
-                                      float* save_gh, void* stream_) {
+                                      float* save_gh, float* save_gt, void* stream_) {
     GLAM_REQUIRE(glam_message_stack_supported(channels, heads, edge_dim),
                  "glam_message_stack_fwd: unsupported (channels=%d heads=%d edge_dim=%d math mode %d); use the per-op calls", channels,
                  heads, edge_dim, g_math_mode_get());
@@ -925,13 +889,13 @@ extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const fl
                  "glam_message_stack_fwd: null pointer");
     GLAM_REQUIRE(!x_raw || (w_pre && raw_dim >= 1 && raw_dim <= kMpMaxRaw), "glam_message_stack_fwd: input LinearBlock needs weights and raw_dim <= %d", kMpMaxRaw);
     GLAM_REQUIRE(conv_only ? steps == 1 : (w_ih && w_hh && b_ih && b_hh), "glam_message_stack_fwd: GRU weights missing / conv-only takes one step");
-    GLAM_REQUIRE(save ? (save_agg && save_alpha && (conv_only ? x_out != nullptr : (save_x && save_h && save_m && save_rzn && save_gh)))
+    GLAM_REQUIRE(save ? (save_agg && save_alpha && (conv_only ? x_out != nullptr : (save_x && save_h && save_m && (save_gt || (save_rzn && save_gh)))))
                       : (x_out != nullptr),
                  "glam_message_stack_fwd: output pointers missing");
     const int HC = heads * channels, ld = (HC + 2 * heads + 3) / 4 * 4;
     GLAM_REQUIRE(ldw == ld, "glam_message_stack_fwd: w_ext pitch %lld, expected %d", (long long)ldw, ld);
     GLAM_REQUIRE(al16(x0) && al16(h0) && al16(w_ih) && al16(w_hh) && al16(x_out) && al16(h_out) && al16(save_x) && al16(save_h) &&
-                 al16(save_xpe) && al16(save_agg) && al16(save_m) && al16(save_rzn) && al16(save_gh) && al16(tiles),
+                 al16(save_xpe) && al16(save_agg) && al16(save_m) && al16(save_rzn) && al16(save_gh) && al16(save_gt) && al16(tiles),
                  "glam_message_stack_fwd: pointers must be 16-byte aligned");
     GLAM_REQUIRE(num_nodes < ((int64_t)1 << 31) && num_edges < ((int64_t)1 << 31), "glam_message_stack_fwd: too large");
     MpParams p;
@@ -941,11 +905,9 @@ extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const fl
     p.rowptr = dst_rowptr; p.src = dst_src; p.etype = etype; p.N = num_nodes; p.E = num_edges; p.De = edge_dim; p.steps = steps;
     p.act = act; p.res = res; p.conv_only = conv_only; p.keep_all = keep_all; p.slope = negative_slope; p.act_param = act_param;
     p.x_out = x_out; p.h_out = h_out; p.sX = save_x; p.sHH = save_h; p.sXPE = save_xpe; p.sAGG = save_agg; p.sALPHA = save_alpha;
-    p.sM = save_m; p.sRZN = save_rzn; p.sGH = save_gh; p.phase_clock = g_mp_phase_clock;
+    p.sM = save_m; p.sRZN = save_rzn; p.sGH = save_gh; p.sGT = save_gt; p.phase_clock = g_mp_phase_clock;
     int rc = 0;
     cudaStream_t stream = (cudaStream_t)stream_;
-    static const int threads_env = [] { const char* e = getenv("GLAM_B200_MP_THREADS"); return e ? atoi(e) : 0; }();
-    if (threads_env == 384 || threads_env == 512 || threads_env == 768 || threads_env == 1024) g_mp_threads = threads_env;
     switch (channels) {
         case 32: rc = mp_launch<8, 3>(p, save, stream); break;
         case 36: rc = mp_launch<9, 3>(p, save, stream); break;

@@ -177,12 +177,20 @@ class GRUUpdateFn(Function):
 # --------------------------------------------------------------------------------------------------
 # fused MessageBlock core: conv -> CELU -> GRU -> (+identity) -> act   (src_1gp/layer.py:259-266)
 # --------------------------------------------------------------------------------------------------
-def _stack_buffers(x0, S, H, C, ld, E):
-    """The stacked activations of `S` message steps that backward consumes (see MessageStackFn)."""
+def _stack_buffers(x0, S, H, C, ld, E, tiled_gates=False):
+    """The stacked activations of `S` message steps that backward consumes (see MessageStackFn).  tiled_gates: the gate-side
+    tensors in the tile-blocked layout the one-launch backward reads (GT [S,N,7C]) instead of row-major RZN / GH."""
     N, dev = x0.shape[0], x0.device
     new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
-    return dict(X=new(S + 1, N, C), HH=new(S + 1, N, C), XPE=new(S, N, ld), AGG=new(S, N, H * C), ALPHA=new(S, E, H),
-                M=new(S, N, C), RZN=new(S, N, 3 * C), GH=new(S, N, C))
+    sv = dict(X=new(S + 1, N, C), HH=new(S + 1, N, C), XPE=new(S, N, ld), AGG=new(S, N, H * C), ALPHA=new(S, E, H), M=new(S, N, C))
+    if tiled_gates:
+        sv["GT"] = new(S, N, 7 * C)
+    else:
+        sv.update(RZN=new(S, N, 3 * C), GH=new(S, N, C))
+    return sv
+
+
+USE_FUSED_BWD = True       # one-launch backward of the message stack (tests flip it to compare with the per-op path)
 
 
 class MessageBlockFn(Function):
@@ -238,13 +246,16 @@ class MessageStackFn(Function):
         if fi is not None and p_drop == 0.0 and pn is None:
             # ONE launch for all steps (csrc/mp_fused.cu): x and h stay in shared memory from step to step; what backward
             # reads leaves the SM as tile-sized contiguous copies
-            sv = _stack_buffers(x0, S, H, channels, ld, E)
+            fused_bwd = (USE_FUSED_BWD and g.src_rowptr is not None and ops.message_stack_bwd_supported(channels, H, ea.shape[1], S))
+            sv = _stack_buffers(x0, S, H, channels, ld, E, tiled_gates=fused_bwd)
             ops.message_stack_fwd(x0, None, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, g, fi, H, channels, S,
                                   slope, act, act_param, res, save=sv)
             X, HH = sv["X"], sv["HH"]
             ctx.save_for_backward(w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ea, X, HH, X, None, sv["XPE"], sv["AGG"],
-                                  sv["ALPHA"], sv["M"], sv["RZN"], sv["GH"], None)
+                                  sv["ALPHA"], sv["M"], sv.get("RZN"), sv.get("GH"), None)
+            ctx.gt = sv.get("GT")
             ctx.g, ctx.cfg = g, (H, channels, slope, act, act_param, res, S, p_drop, None)
+            ctx.fi = fi                                          # the same tile table serves the one-launch backward
             ctx.set_materialize_grads(False)
             return tuple(X[s + 1] for s in range(S)) + (HH[S],)
         new = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype, device=dev)
@@ -287,9 +298,22 @@ class MessageStackFn(Function):
         N, HC, ld, E, De, dev = X.shape[1], H * C, XPE.shape[2], ea.shape[0], ea.shape[1], X.device
         new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
         G_GI, G_GH, G_PRE = new(S, N, 3 * C), new(S, N, 3 * C), new(S, N, C)
-        G_XPE, G_LOGIT, G_WE = new(S, N, ld), new(S, E, H), new(S, De, HC)
+        G_XPE = new(S, N, ld)
+        fi = getattr(ctx, "fi", None)
+        gt = getattr(ctx, "gt", None)                            # forward saved the gate side tile-blocked: only the one-launch backward reads it
+        fused_bwd = gt is not None or (USE_FUSED_BWD and fi is not None and p_drop == 0.0 and pn is None and g.src_rowptr is not None
+                                       and ops.message_stack_bwd_supported(C, H, De, S))
+        if fused_bwd:
+            # ONE launch for the reverse loop (csrc/mp_fused_bwd.cu): gate backward, input-gradient projections and both edge
+            # passes per tile, the carried gradients resident on the SM; what the weight-gradient contractions read comes out
+            sv = dict(X=X, HH=HH, XPE=XPE, ALPHA=ALPHA, M=M, RZN=RZN, GH=GH, GT=gt)
+            g_x0, g_w_edge, g_att_edge = ops.message_stack_bwd(sv, list(grads[:S]), _c(grads[S]), w_ext, w_edge, att_edge, w_scale,
+                                                               w_ih, w_hh, g, fi, H, C, S, slope, act, act_param, res,
+                                                               G_GI, G_GH, G_PRE, G_XPE)
+        else:
+            G_LOGIT, G_WE = new(S, E, H), new(S, De, HC)
         g_ext, g_h, g_x = grads[:S], _c(grads[S]), None
-        for s in range(S - 1, -1, -1):
+        for s in (() if fused_bwd else range(S - 1, -1, -1)):
             if g_ext[s] is not None:                             # gradient arriving at this step's output from outside
                 g_x = _c(g_ext[s]) if g_x is None else g_x.add_(g_ext[s])
             if g_x is None:
@@ -314,7 +338,8 @@ class MessageStackFn(Function):
             else:
                 g_x = ops.gemm(G_XPE[s], w_ext, transpose_w=True)
             g_h = g_h_prev
-        g_x0 = g_x.add_(g_h)                                                                  # X[0] and HH[0] are both x0
+        if not fused_bwd:
+            g_x0 = g_x.add_(g_h)                                                              # X[0] and HH[0] are both x0
         SN = S * N
         g_w_ih, g_b_ih = ops.gemm_tn_ex(M.view(SN, C), G_GI.view(SN, 3 * C), transpose_out=True, want_colsum=True)
         g_w_hh, g_b_hh = ops.gemm_tn_ex(HH[:S].view(SN, C), G_GH.view(SN, 3 * C), transpose_out=True, want_colsum=True)
@@ -324,8 +349,9 @@ class MessageStackFn(Function):
         g_w_ext, _ = ops.gemm_tn_ex(xd, gxpe)
         # the 2H logit columns are near-total cancellations (softmax gradients are zero-sum per destination): exact fp32
         ops.gemm_tn_ex(xd, gxpe[:, HC:HC + 2 * H], out=g_w_ext[:, HC:HC + 2 * H])
-        g_att_edge, _ = ops.gemm_tn_ex(ea, G_LOGIT.sum(0) if S > 1 else G_LOGIT[0])
-        g_w_edge = G_WE.sum(0) if S > 1 else G_WE[0]
+        if not fused_bwd:
+            g_att_edge, _ = ops.gemm_tn_ex(ea, G_LOGIT.sum(0) if S > 1 else G_LOGIT[0])
+            g_w_edge = G_WE.sum(0) if S > 1 else G_WE[0]
         return (g_x0, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias, g_w_ih, g_w_hh, g_b_ih, g_b_hh,
                 None, None, None, None, None, None, None, None, None, None, None, None)
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLAM_B200_ABI_VERSION 6
+#define GLAM_B200_ABI_VERSION 7
 #define GLAM_MAX_HEADS 4
 
 int glam_abi_version(void);
@@ -294,7 +294,10 @@ int glam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
  *   (may be NULL) = the final GRU state.  Training (save_xpe != NULL): what the backward kernels consume is written as
  *   stacked tensors — save_x, save_h [steps+1][N][C] (block inputs / states; entry 0 = x0 / h0), save_xpe [steps][N][ld],
  *   save_agg [steps][N][HC], save_alpha [steps][E][H], save_m [steps][N][C], save_rzn [steps][N][3C], save_gh [steps][N][C]
- *   (conv_only: save_xpe, save_agg, save_alpha and x_out only).  If meta[1] != 0 the outputs are filled with NaN: callers
+ *   (conv_only: save_xpe, save_agg, save_alpha and x_out only).  save_gt != NULL (then save_rzn / save_gh may be NULL): the
+ *   gate-side tensors for glam_message_stack_bwd in its tile-blocked layout instead — [steps][N][7C]; inside step s the tile
+ *   {n0, n1} owns floats [n0*7C, n1*7C) as 7*C/4 slots (r, z, n, gh_n, h, x', m; C/4 16-byte chunks each) of n1-n0 rows x
+ *   16 bytes: a warp's 32 rows of one chunk are contiguous in the forward's stores and in the backward's loads.  If meta[1] != 0 the outputs are filled with NaN: callers
  *   check meta[1] on the host when they can (outside CUDA-graph capture) and fall back to the per-op entry points.
  *   glam_message_stack_supported: tf32 math mode, heads == 3, channels in {32,36,40}, edge_dim <= 4.
  * --------------------------------------------------------------------------------------------- */
@@ -305,10 +308,13 @@ int glam_build_graph_tiles(const int32_t* graph_ptr, int64_t num_graphs, const i
                            size_t workspace_bytes, void* stream);
 int glam_edge_types(const float* edge_attr_sorted, int64_t num_edges, int edge_dim, uint8_t* etype, int32_t* meta, void* stream);
 int glam_message_stack_supported(int channels, int heads, int edge_dim);
-/* Profiling aid: when `cycles` (device memory, [148][16] unsigned 64-bit) is not NULL, every following glam_message_stack_fwd
- * launch has thread 0 of each CTA add the SM cycles spent between consecutive phase boundaries to cycles[cta][phase]
- * (0 tile load, 1 logits, 2 softmax, 3 projection wait, 4 TMEM -> xp tile, 5 aggregation, 6 agg panels, 7 scale wait,
- * 8 CELU epilogue, 9 GRU wait, 10 gates, 11 step outputs, 12 tile end).  Results are unaffected.  NULL switches it off. */
+/* Profiling aid: when `cycles` (device memory, [148][32] unsigned 64-bit) is not NULL, every following glam_message_stack_fwd /
+ * glam_message_stack_bwd launch has thread 0 of each CTA add the SM cycles spent between consecutive phase boundaries to
+ * cycles[cta][phase] — forward: 0 tile load, 1 logits, 2 softmax, 3 projection wait, 4 TMEM -> xp tile, 5 aggregation, 6 agg
+ * panels, 7 scale wait, 8 CELU epilogue, 9 GRU wait, 10 gates, 11 step outputs, 12 tile end, 13 MMA issue, 14 set-up;
+ * backward: 16 index words, 17 gate backward, 18 G copy-out + GRU MMAs, 19 CELU' epilogue, 20 G_PRE copy-out + scale MMA,
+ * 21 TMEM -> g_agg tile, 22 destination pass, 23 source pass, 24 G_XPE copy-out, 25 tile output.  Results are unaffected.
+ * NULL switches it off. */
 int glam_message_stack_phase_clock(unsigned long long* cycles);
 int glam_message_stack_fwd(const float* x0, const float* h0, const float* x_raw, int raw_dim, const float* w_pre,
                            const float* b_pre, int pre_act, float pre_act_param, const float* w_ext, int64_t ldw, const float* w_edge,
@@ -319,7 +325,33 @@ int glam_message_stack_fwd(const float* x0, const float* h0, const float* x_raw,
                            int edge_dim, int steps, float negative_slope, int act, float act_param, int res,
                            int conv_only, int keep_all, float* x_out, float* h_out, float* save_x, float* save_h,
                            float* save_xpe, float* save_agg, float* save_alpha, float* save_m, float* save_rzn,
-                           float* save_gh, void* stream);
+                           float* save_gh, float* save_gt, void* stream);
+
+/* glam_message_stack_bwd — backward of glam_message_stack_fwd's training mode (h0 == NULL, no conv_only) in ONE launch
+ *   (csrc/mp_fused_bwd.cu), on the same tile table: gate backward, the four input-gradient projections, the edge backward
+ *   by destination and by source, with the carried gradients g_x / g_h resident on the SM between steps (the reverse of the
+ *   loop of src_1gp/model.py:53-54 over src_1gp/layer.py:252-267).  Reads what the forward saved (the gate-side tensors either
+ *   row-major — save_h, save_x, save_m, save_rzn, save_gh — or, when save_gt != NULL, from the tile-blocked save); h_g_ext is a HOST array of
+ *   `steps` device pointers (NULL entries allowed): the gradient arriving at every step's output x_{s+1} [N][C] from outside;
+ *   g_h_final [N][C] (may be NULL) the gradient of the final GRU state.  Writes what the weight-gradient contractions read
+ *   — g_gi, g_gh [steps][N][3C], g_pre [steps][N][C], g_xpe [steps][N][ld] — plus g_x0 [N][C] (gradient of x0, both as the
+ *   first block input and the first GRU state) and the parameter gradients of the edge phase summed over steps: g_w_edge
+ *   [edge_dim][HC], g_att_edge [edge_dim][H] (= d/d att_edge of glam_triplet_prep_fwd).  needs the source-side index of
+ *   glam_build_csr.  workspace >= glam_message_stack_bwd_workspace_bytes(), 16-byte aligned.  If meta[1] != 0, g_x0 and the
+ *   parameter gradients are filled with NaN.  Supported: tf32 math mode, heads == 3, channels in {32,36}, edge_dim <= 4,
+ *   steps <= 8. */
+int glam_message_stack_bwd_supported(int channels, int heads, int edge_dim, int steps);
+size_t glam_message_stack_bwd_workspace_bytes(int channels, int heads, int edge_dim);
+int glam_message_stack_bwd(const float* save_x, const float* save_h, const float* save_xpe, const float* save_alpha,
+                           const float* save_m, const float* save_rzn, const float* save_gh, const float* save_gt,
+                           const float* const* h_g_ext,
+                           const float* g_h_final, const float* w_ext, int64_t ldw, const float* w_edge, const float* att_edge,
+                           const float* w_scale, const float* w_ih, const float* w_hh, const int32_t* tiles,
+                           const int32_t* tile_meta, const int32_t* dst_rowptr, const int32_t* dst_src, const uint8_t* etype,
+                           const int32_t* src_rowptr, const int32_t* src_pos, const int32_t* src_dst, int64_t num_nodes,
+                           int64_t num_edges, int channels, int heads, int edge_dim, int steps, float negative_slope, int act,
+                           float act_param, int res, float* g_gi, float* g_gh, float* g_pre, float* g_xpe, float* g_x0,
+                           float* g_w_edge, float* g_att_edge, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (9) Packed graph store -> device index (csrc/packed.cu).  The reference ships every batch as fp32

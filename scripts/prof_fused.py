@@ -79,7 +79,7 @@ PHASES = ["tile load", "logits", "softmax", "proj wait", "tmem->xp", "aggregate"
           "gates", "outputs", "tile end"]
 if mode == "phases":
     lib = _lib.load()
-    clk = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+    clk = torch.zeros(148, 32, dtype=torch.int64, device=dev)
     for name, fn in (("eval x3", f_eval), ("save x3", f_save), ("conv only", f_conv)):
         fn(); torch.cuda.synchronize()
         lib.glam_message_stack_phase_clock(clk.data_ptr())

@@ -213,6 +213,57 @@ def test_fused_stack_saved_tensors_and_grads_match_per_op(C, De, n_graphs):
         assert e < 2e-3, f"grad {n}: {e}"
 
 
+@pytest.mark.parametrize("C,De,act,res,n_graphs,which", [(36, 3, "CELU", True, 300, "all"), (36, 3, "CELU", True, 700, "last"),
+                                                          (32, 4, "ReLU", False, 90, "all"), (36, 3, "LeakyReLU", True, 1, "all"),
+                                                          (32, 2, "CELU", True, 33, "h")])
+def test_fused_backward_matches_per_op_backward(C, De, act, res, n_graphs, which):
+    """The one-launch backward (csrc/mp_fused_bwd.cu) against the per-op backward kernels ON THE SAME saved activations: the
+    input gradient and every parameter gradient of a loss on all step outputs + the final state / on the last output alone /
+    on the final state alone; bitwise run to run."""
+    from glam_b200 import _lib, functional as Fn
+    _lib.set_math_mode("tf32")
+    blk = _block(C, De, act, res, 7).train()
+    b = _batch(n_graphs, C, De, 13).to(DEV)
+    gen = torch.Generator().manual_seed(4)
+    x0 = torch.randn(b.num_nodes, C, generator=gen).to(DEV)
+    cot = [torch.randn(b.num_nodes, C, generator=gen).to(DEV) for _ in range(4)]
+
+    def run(fused_bwd):
+        Fn.USE_FUSED_BWD = fused_bwd
+        try:
+            for p in blk.parameters():
+                p.grad = None
+            xin = x0.clone().requires_grad_(True)
+            n0 = _lib.launch_count()
+            xs, hh = blk.run_steps(xin, b.edge_index, b.edge_attr, 3, batch=b.batch, num_graphs=b.num_graphs)
+            if which == "all":
+                loss = sum((xo * c).sum() for xo, c in zip(xs, cot)) + (hh[0] * cot[3]).sum()
+            elif which == "last":
+                loss = (xs[2] * cot[2]).sum()
+            else:
+                loss = (hh[0] * cot[3]).sum()
+            loss.backward()
+            torch.cuda.synchronize()
+            return xin.grad, {n: p.grad.clone() for n, p in blk.named_parameters()}, _lib.launch_count() - n0
+        finally:
+            Fn.USE_FUSED_BWD = True
+
+    gx_f, gp_f, n_f = run(True)
+    gx_u, gp_u, n_u = run(False)
+    gx_f2, gp_f2, _ = run(True)
+    assert n_f < n_u, f"one-launch backward not taken: {n_f} library launches against {n_u}"
+    assert torch.isfinite(gx_f).all()
+    e = _rel(gx_f, gx_u)
+    print(f"g_x0: rel err {e:.2e}")
+    assert e < 1e-3, e
+    for n in gp_u:
+        e = _rel(gp_f[n], gp_u[n])
+        print(f"grad {n}: rel err {e:.2e}")
+        assert e < 2e-3, f"grad {n}: {e}"
+        assert torch.equal(gp_f[n], gp_f2[n]), f"grad {n}: not reproducible"
+    assert torch.equal(gx_f, gx_f2)
+
+
 @pytest.mark.parametrize("C,De", [(36, 3), (40, 4)])
 def test_fused_conv_only_matches_per_op(C, De):
     from glam_b200 import _lib, layer
