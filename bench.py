@@ -229,6 +229,8 @@ def module_bytes(name, graphs, n=NODES_PER, e=EDGES_PER, Cc=C, De=DE):
     per = {"TripletMessage fwd": 4 * (2 * n * Cc + e * De) + 8 * e + 4 * (n + 1),
            "TripletMessage bwd": 4 * (3 * n * Cc + e * De) + 8 * e + 4 * (n + 1),
            "MessageBlock fwd": 4 * (4 * n * Cc + e * De) + 8 * e + 4 * (n + 1),
+           # by analogy with SURVEY 8(d)'s recompute-based backward rows: x, h in; g_x', g_h' in; g_x, g_h out (+ the graph)
+           "MessageBlock bwd": 4 * (6 * n * Cc + e * De) + 8 * e + 4 * (n + 1),
            "GRU update": 12 * n * Cc,
            "Set2Set step": 4 * n * Cc + 4 * n + 16 * Cc,
            "GlobalAttention": 4 * n * Cc + 4 * n + 8 * Cc}[name]
@@ -245,6 +247,9 @@ def kernel_bytes_model(label, N, E, B, Cc=C, Hh=H, De=DE):
         out = 4 * N * Cc * (2 if not save else 0)
         sv = 4 * S * (N * (ld + HC + Cc + 3 * Cc + Cc + 2 * Cc) + E * Hh) + 8 * N * Cc if save else 0
         return 4 * N * Cc + 5 * E + 4 * N + out + sv
+    if label.startswith("glam_message_stack_bwd"):   # reads the tile-blocked gate save, xpe, alpha; writes G_GI, G_GH, G_PRE, G_XPE
+        S = int(re.search(r"S=(\d+)", label).group(1))
+        return 4 * S * (N * (7 * Cc + ld) + E * Hh + N * (7 * Cc + ld)) + 4 * 2 * N * Cc + 4 * (3 * E + 2 * N)
     if label.startswith("glam_triplet_edge_fwd"):
         return 4 * (N * ld + N * HC + E * De + E * Hh) + 4 * (E + N + 1)
     if label.startswith("glam_triplet_edge_bwd_dst"):
@@ -275,7 +280,7 @@ def kernel_bytes_model(label, N, E, B, Cc=C, Hh=H, De=DE):
 
 def kernel_family(label):
     """ncu kernel name behind a profiled library call (so that shape-suffixed labels do not split one kernel's share)."""
-    for prefix, kern in (("glam_message_stack_fwd", "mp_fused_kernel"), ("glam_gemm_tn", "tc_gemm_tn_kernel"), ("glam_gemm_ex", "tc_gemm_kernel"),
+    for prefix, kern in (("glam_message_stack_fwd", "mp_fused_kernel"), ("glam_message_stack_bwd", "mp_fused_bwd_kernel"), ("glam_gemm_tn", "tc_gemm_tn_kernel"), ("glam_gemm_ex", "tc_gemm_kernel"),
                          ("glam_triplet_edge_bwd_dst", "edge_win_bwd_dst2_kernel"), ("glam_triplet_edge_bwd_src", "edge_win_bwd_src_kernel"),
                          ("glam_triplet_edge_fwd", "edge_win2_fwd_kernel"), ("glam_gru_gates_bwd", "gru_gates_bwd_vec"),
                          ("glam_gru_fused_fwd", "tc_gru_fwd_kernel"), ("glam_set2set_round_fwd", "set2set_round_fwd_rows_kernel"),
@@ -485,6 +490,25 @@ def module_rooflines(dev, peak):
                 timeit(lambda: conv(x0, b.edge_index, b.edge_attr)), GRAPHS)
         finally:
             layer.USE_FUSED_STACK = True
+    # backward of the 3-step stack: gradients of sum(x_3) w.r.t. x0 and all weights (weight-gradient contractions included)
+    from glam_b200 import functional as Fn
+    blk.train()
+    xg = x0.clone().requires_grad_(True)
+
+    def stack_bwd(fused):
+        Fn.USE_FUSED_BWD = fused
+        try:
+            xs, _ = blk.run_steps(xg, b.edge_index, b.edge_attr, 3, keep="last", **kw)
+            go = torch.ones_like(xs[0])
+            torch.cuda.synchronize()
+            t = timeit(lambda: torch.autograd.grad(xs[0], [xg] + list(blk.parameters()), go, retain_graph=True), reps=5)
+        finally:
+            Fn.USE_FUSED_BWD = True
+        return t
+    put("MessageBlock bwd x3 (one-launch backward + weight-gradient contractions)", 3 * module_bytes("MessageBlock bwd", GRAPHS), stack_bwd(True), GRAPHS)
+    put("MessageBlock bwd x3 (per-op backward kernels + weight-gradient contractions)", 3 * module_bytes("MessageBlock bwd", GRAPHS), stack_bwd(False), GRAPHS)
+    blk.eval()
+    with torch.no_grad():
         s2s = layer.Set2Set(C, 3).to(dev)
         put("Set2Set readout (3 steps)", 3 * module_bytes("Set2Set step", GRAPHS), timeit(lambda: s2s(x0, b.batch, num_graphs=b.num_graphs)), GRAPHS)
         gla = layer.GlobalLAPool(C).to(dev)
@@ -674,6 +698,9 @@ def run_ours(args):
         if top[0].startswith("glam_message_stack_fwd"):
             abytes = 3 * module_bytes("MessageBlock fwd", GRAPHS)
             what = "3 x MessageBlock fwd (SURVEY.md 8d: 15 584 B/graph/step x 4096 graphs)"
+        elif top[0].startswith("glam_message_stack_bwd"):
+            abytes = 3 * module_bytes("MessageBlock bwd", GRAPHS)
+            what = "3 x MessageBlock bwd (x, h, g_x', g_h' in; g_x, g_h out; edge_attr + CSR: 22 784 B/graph/step x 4096 graphs)"
         else:
             abytes, what = kbytes, "operands of the call read/written once"
         traffic = None
