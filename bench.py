@@ -621,6 +621,33 @@ def run_ours(args):
         run = lambda: train_workload(hz, dti_net, xent, make_dti_batches(1, rank, DTI_PAIRS), max(args.steps // 2, 5), args.warmup, DTI_PAIRS,
                                      extra_warm=10 if world > 1 else 0)
         dti = head_timer(run) if args.workload == "dti" else run()
+    dti_scr = None
+    if dti is not None and world == 1 and not args.quick:
+        # DTI virtual screening against ONE target (LIT-PCBA shape: src_2gi_dti_scr/dataset.py:297): the reference collates one
+        # protein copy per pair; `pro_index` keeps the protein once (same scores, tests/test_gpu_parity.py)
+        from glam_b200.synth import make_molecule_batch, make_protein_batch
+        P = 1024
+        dti_net.eval()
+        lig = make_molecule_batch(P, seed=31, total_nodes=NODES_PER * P, total_edges=EDGES_PER * P, **DIMS).to(dev)
+        one = make_protein_batch(1, seed=32, min_len=500, max_len=500).to(dev)
+        rep = make_protein_batch(P, seed=32, min_len=500, max_len=500, same_protein=True).to(dev)
+        idx = torch.zeros(P, dtype=torch.int32, device=dev)
+
+        def timed(fn, reps=5):
+            with torch.no_grad():
+                fn(); torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        t_one, t_rep = timed(lambda: dti_net(lig, one, pro_index=idx)), timed(lambda: dti_net(lig, rep))
+        dti_scr = {"pairs_per_batch": P, "protein_residues": one.num_nodes,
+                   "distinct protein once (pro_index)": {"value": P / (t_one * 1e-3), "unit": "pairs/s", "ms_per_batch": t_one},
+                   "one protein copy per pair (the reference's collation)": {"value": P / (t_rep * 1e-3), "unit": "pairs/s", "ms_per_batch": t_rep},
+                   "note": "eval-mode forward, eager (no CUDA graph), inputs resident"}
+        dti_net.train()
     if clk is not None:
         clk.__exit__(None, None, None)
 
@@ -631,6 +658,8 @@ def run_ours(args):
 
     also = {"GLAM-GP training (configs[1])": brief(gp, UNIT), "GLAM-DDI training (configs[2])": brief(ddi, "pairs/s"),
             "GLAM-DTI training (configs[3])": brief(dti, "pairs/s"), "screening (configs[4])": scr}
+    if dti_scr is not None:
+        also["GLAM-DTI screening against one target (SURVEY 8f N3)"] = dti_scr
     if ddi is not None:
         also["GLAM-DDI training (configs[2])"]["shape"] = f"{DDI_PAIRS} pairs/GPU, two {NODES_PER}-atom towers, dot-pool2 x3, Set2Set"
     if dti is not None:

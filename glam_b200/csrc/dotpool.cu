@@ -14,8 +14,8 @@ constexpr int kPairTile = 32;
 
 __global__ void __launch_bounds__(kPairThreads)
 pair_dot_pool_fwd_kernel(const float* __restrict__ xa, const float* __restrict__ xb, const int32_t* __restrict__ ptr_a,
-                         const int32_t* __restrict__ ptr_b, int C, float* __restrict__ out, int32_t* __restrict__ argmax,
-                         float* __restrict__ sum_a, float* __restrict__ sum_b) {
+                         const int32_t* __restrict__ ptr_b, const int32_t* __restrict__ idx_b, int C, float* __restrict__ out,
+                         int32_t* __restrict__ argmax, float* __restrict__ sum_a, float* __restrict__ sum_b) {
     extern __shared__ float smem[];
     const int ld = C | 1;                               // odd stride: conflict-free row reads
     float* As = smem;                                   // [32][ld]
@@ -24,7 +24,8 @@ pair_dot_pool_fwd_kernel(const float* __restrict__ xa, const float* __restrict__
     __shared__ long long red_i[kPairThreads / 32];
     __shared__ float red_dot[kPairThreads / 32];
     const int g = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const int a0 = ptr_a[g], a1 = ptr_a[g + 1], b0 = ptr_b[g], b1 = ptr_b[g + 1];
+    const int gb = idx_b ? idx_b[g] : g;                // shared second operand: pair g reads graph idx_b[g] of the b side
+    const int a0 = ptr_a[g], a1 = ptr_a[g + 1], b0 = ptr_b[gb], b1 = ptr_b[gb + 1];
     const int na = a1 - a0, nb = b1 - b0;
 
     // column sums (fixed row order) and the mean
@@ -143,8 +144,24 @@ extern "C" int glam_pair_dot_pool_fwd(const float* xa, const float* xb, const in
     const size_t smem = sizeof(float) * 2 * kPairTile * (C | 1);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(pair_dot_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pair_dot_pool_fwd_kernel<<<(unsigned)num_pairs, kPairThreads, smem, (cudaStream_t)stream_>>>(xa, xb, ptr_a, ptr_b, C, out, argmax,
-                                                                                               sum_a, sum_b);
+    pair_dot_pool_fwd_kernel<<<(unsigned)num_pairs, kPairThreads, smem, (cudaStream_t)stream_>>>(xa, xb, ptr_a, ptr_b, nullptr, C, out,
+                                                                                               argmax, sum_a, sum_b);
+    GLAM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int glam_pair_dot_pool_fwd_idx(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b,
+                                          const int32_t* idx_b, int64_t num_pairs, int C, float* out, int32_t* argmax,
+                                          float* sum_a, float* sum_b, void* stream_) {
+    GLAM_REQUIRE(num_pairs >= 0 && C > 0 && C <= 512, "glam_pair_dot_pool_fwd_idx: bad shape");
+    if (num_pairs == 0) return 0;
+    GLAM_REQUIRE(xa && xb && ptr_a && ptr_b && idx_b && out && argmax && sum_a && sum_b, "glam_pair_dot_pool_fwd_idx: null pointer");
+    GLAM_REQUIRE(num_pairs < (int64_t)1 << 31, "glam_pair_dot_pool_fwd_idx: too many pairs");
+    const size_t smem = sizeof(float) * 2 * kPairTile * (C | 1);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(pair_dot_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pair_dot_pool_fwd_kernel<<<(unsigned)num_pairs, kPairThreads, smem, (cudaStream_t)stream_>>>(xa, xb, ptr_a, ptr_b, idx_b, C, out,
+                                                                                               argmax, sum_a, sum_b);
     GLAM_CHECK_LAUNCH();
     return 0;
 }

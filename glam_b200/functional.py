@@ -497,10 +497,12 @@ class Set2SetFn(Function):
 # --------------------------------------------------------------------------------------------------
 class PairDotPoolFn(Function):
     @staticmethod
-    def forward(ctx, xa, xb, ptr_a, ptr_b, num_pairs):
+    def forward(ctx, xa, xb, ptr_a, ptr_b, num_pairs, idx_b=None):
         xa, xb = _c(xa), _c(xb)
         ops._need_cuda(xa, xb)
-        out, argmax, sa, sb = ops.pair_dot_pool_fwd(xa, xb, ptr_a, ptr_b, num_pairs)
+        if idx_b is not None and (xa.requires_grad or xb.requires_grad):
+            raise ops._lib.GlamError("dot_and_global_pool2 with a shared protein index (pro_index) is forward-only (evaluation / screening)")
+        out, argmax, sa, sb = ops.pair_dot_pool_fwd(xa, xb, ptr_a, ptr_b, num_pairs, idx_b)
         ctx.save_for_backward(xa, xb, ptr_a, ptr_b, argmax, sa, sb)
         ctx.num_pairs = num_pairs
         return out
@@ -509,7 +511,7 @@ class PairDotPoolFn(Function):
     def backward(ctx, g_out):
         xa, xb, ptr_a, ptr_b, argmax, sa, sb = ctx.saved_tensors
         g_xa, g_xb = ops.pair_dot_pool_bwd(xa, xb, ptr_a, ptr_b, _c(g_out), argmax, sa, sb, ctx.num_pairs)
-        return g_xa, g_xb, None, None, None
+        return g_xa, g_xb, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------------------

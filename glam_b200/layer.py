@@ -623,8 +623,16 @@ class MessageBlock(nn.Module):
 # --------------------------------------------------------------------------------------------------
 # cross-graph interaction pool
 # --------------------------------------------------------------------------------------------------
-def dot_and_global_pool2(mol_out, pro_out, mol_batch, pro_batch, num_graphs: Optional[int] = None):
-    """Per pair [max, mean] of X_mol X_pro^T — src_2gi_ddi/layer.py:270-283 — as one kernel launch, no host loop."""
+def dot_and_global_pool2(mol_out, pro_out, mol_batch, pro_batch, num_graphs: Optional[int] = None, pro_index=None,
+                         num_pro_graphs: Optional[int] = None):
+    """Per pair [max, mean] of X_mol X_pro^T — src_2gi_ddi/layer.py:270-283 — as one kernel launch, no host loop.
+    `pro_index` (int [num_pairs], evaluation only): the protein side holds every DISTINCT graph once (`num_pro_graphs` of them)
+    and pair g reads graph pro_index[g] — the reference collates one protein copy per pair (src_2gi_dti_scr/dataset.py:329-335)
+    although a screening set has one protein per target (dataset.py:297)."""
     ptr_a, B = G.graph_ptr(mol_batch, num_graphs)
-    ptr_b, _ = G.graph_ptr(pro_batch, B)
-    return Fn.PairDotPoolFn.apply(mol_out, pro_out, ptr_a, ptr_b, B)
+    if pro_index is None:
+        ptr_b, _ = G.graph_ptr(pro_batch, B)
+        return Fn.PairDotPoolFn.apply(mol_out, pro_out, ptr_a, ptr_b, B)
+    ptr_b, _ = G.graph_ptr(pro_batch, num_pro_graphs)
+    idx = pro_index if pro_index.dtype == torch.int32 else pro_index.to(torch.int32)
+    return Fn.PairDotPoolFn.apply(mol_out, pro_out, ptr_a, ptr_b, B, idx.contiguous())

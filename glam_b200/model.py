@@ -103,19 +103,38 @@ class _PairArchitecture(nn.Module):
         self.lin_out0 = LinearBlock(hid * 2 + message_steps * 2, e_dim, norm=end_norm, dropout=end_do, act=end_act)
         self.lin_out1 = LinearBlock(e_dim, out_dim, norm=end_norm, dropout=end_do, act="_None")
 
-    def forward(self, da, db):
+    def forward(self, da, db, pro_index=None):
+        """`pro_index` (int [pairs], evaluation only): `db` then holds every DISTINCT second-side graph once and
+        pair g uses graph pro_index[g] — the tower of the second side runs on the distinct graphs only and its readout rows are
+        gathered per pair (`dedupe_keys` builds the index from per-pair identifiers).  Same values as the duplicated batch."""
         ta, tb = _Tower(self, self.prefixes[0]), _Tower(self, self.prefixes[1])
         B = _num_graphs(da)
+        Bb = B if pro_index is None else _num_graphs(db)
         xa = ta.lin0(da.x, batch=da.batch)
         xb = tb.lin0(db.x, batch=db.batch)
         # the towers only meet in the pools, so each runs all its steps first (same values as the lock-step loop)
         xas, _ = ta.conv.run_steps(xa, da.edge_index, da.edge_attr, self.message_steps, batch=da.batch, num_graphs=B)
-        xbs, _ = tb.conv.run_steps(xb, db.edge_index, db.edge_attr, self.message_steps, batch=db.batch, num_graphs=B)
-        fusion = [dot_and_global_pool2(a, b, da.batch, db.batch, num_graphs=B) for a, b in zip(xas, xbs)]
+        xbs, _ = tb.conv.run_steps(xb, db.edge_index, db.edge_attr, self.message_steps, batch=db.batch, num_graphs=Bb)
+        fusion = [dot_and_global_pool2(a, b, da.batch, db.batch, num_graphs=B, pro_index=pro_index, num_pro_graphs=Bb)
+                  for a, b in zip(xas, xbs)]
         oa = ta.flat(ta.readout(xas[-1], da.batch, num_graphs=B))
-        ob = tb.flat(tb.readout(xbs[-1], db.batch, num_graphs=B))
+        ob = tb.flat(tb.readout(xbs[-1], db.batch, num_graphs=Bb))
+        if pro_index is not None:
+            ob = ob.index_select(0, pro_index.long())
         out = self.lin_out0(torch.cat([oa, ob] + fusion, dim=-1))
         return self.lin_out1(out)
+
+
+def dedupe_keys(keys, device=None):
+    """Per-pair identifiers of the second-side graphs (any hashables, e.g. target names) -> (positions of the first occurrence
+    of every distinct key, in order of appearance; int32 index tensor pair -> distinct graph) for `forward(..., pro_index=)`."""
+    first, index = {}, []
+    for i, k in enumerate(keys):
+        index.append(first.setdefault(k, len(first)))
+    pos = [0] * len(first)
+    for i in range(len(keys) - 1, -1, -1):
+        pos[index[i]] = i
+    return pos, torch.tensor(index, dtype=torch.int32, device=device)
 
 
 class ArchitectureDDI(_PairArchitecture):

@@ -450,12 +450,18 @@ def set2set_round_bwd(x, gates, c_prev, c_new, att, gptr, num_graphs, g_u, g_c, 
           _p(att), _p(g_u), g_u.stride(0), g_u.shape[1], _p(g_c), _p(g_x), 1 if accumulate else 0, _p(G), _stream(x))
 
 
-def pair_dot_pool_fwd(xa, xb, ptr_a, ptr_b, num_pairs):
+def pair_dot_pool_fwd(xa, xb, ptr_a, ptr_b, num_pairs, idx_b=None):
+    """idx_b (int32 [num_pairs], optional): pair g reads graph idx_b[g] of the b side (distinct graphs stored once)."""
     C, dev = xa.shape[1], xa.device
     out = torch.empty((num_pairs, 2), dtype=torch.float32, device=dev)
     argmax = torch.empty((num_pairs, 2), dtype=torch.int32, device=dev)
     sa = torch.empty((num_pairs, C), dtype=torch.float32, device=dev)
     sb = torch.empty((num_pairs, C), dtype=torch.float32, device=dev)
+    if idx_b is not None:
+        assert idx_b.dtype == torch.int32 and idx_b.is_contiguous() and idx_b.numel() == num_pairs
+        _call("glam_pair_dot_pool_fwd_idx", _p(xa), _p(xb), _p(ptr_a), _p(ptr_b), _p(idx_b), num_pairs, C, _p(out), _p(argmax),
+              _p(sa), _p(sb), _stream(xa))
+        return out, argmax, sa, sb
     _call("glam_pair_dot_pool_fwd", _p(xa), _p(xb), _p(ptr_a), _p(ptr_b), num_pairs, C, _p(out), _p(argmax),
                                                   _p(sa), _p(sb), _stream(xa))
     return out, argmax, sa, sb

@@ -222,6 +222,12 @@ int glam_set2set_round_bwd(const float* x, int64_t ldx, const int32_t* graph_ptr
 int glam_pair_dot_pool_fwd(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b,
                            int64_t num_pairs, int channels, float* out, int32_t* argmax, float* sum_a,
                            float* sum_b, void* stream);
+/* Shared second operand (evaluation): pair g reads graph idx_b[g] of the b side, so a virtual-screening
+ * batch holds every distinct protein graph ONCE (LIT-PCBA has one protein per target, src_2gi_dti_scr/dataset.py:297; the
+ * reference collates one copy per pair, dataset.py:329-335).  ptr_b has one entry per DISTINCT graph (+1).  Forward only. */
+int glam_pair_dot_pool_fwd_idx(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b,
+                               const int32_t* idx_b, int64_t num_pairs, int channels, float* out, int32_t* argmax,
+                               float* sum_a, float* sum_b, void* stream);
 int glam_pair_dot_pool_bwd(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b,
                            const float* g_out, const int32_t* argmax, const float* sum_a, const float* sum_b,
                            int64_t num_pairs, int channels, float* g_xa, float* g_xb, void* stream);

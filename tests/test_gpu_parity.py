@@ -860,3 +860,45 @@ def test_screen_step_double_buffer_matches_eager():
         o1 = s1.step(b).clone()
         o2 = s2.step(b, prefetch=batches[i + 1] if i + 1 < len(batches) else None).clone()
         assert torch.equal(o1, want[i]) and torch.equal(o2, want[i])
+
+
+# ---------------------------------------------------------------------------------------------- DTI screening: distinct proteins once
+def _repeat_graphs(u, index):
+    """The collated batch the reference would build (one copy of its protein graph per pair, src_2gi_dti_scr/dataset.py:329-335)
+    from a batch `u` of distinct graphs and the pair -> graph index."""
+    from glam_b200.synth import GraphBatch
+    nptr = torch.zeros(u.num_graphs + 1, dtype=torch.long)
+    nptr[1:] = torch.bincount(u.batch, minlength=u.num_graphs).cumsum(0)
+    eg = u.batch[u.edge_index[0]]
+    xs, eis, eas, bs, off = [], [], [], [], 0
+    for p, gidx in enumerate(index):
+        n0, n1 = int(nptr[gidx]), int(nptr[gidx + 1])
+        sel = eg == gidx
+        xs.append(u.x[n0:n1]); eas.append(u.edge_attr[sel]); eis.append(u.edge_index[:, sel] - n0 + off)
+        bs.append(torch.full((n1 - n0,), p, dtype=torch.long)); off += n1 - n0
+    return GraphBatch(torch.cat(xs), torch.cat(eis, 1), torch.cat(eas), torch.cat(bs), None, len(index))
+
+
+@pytest.mark.parametrize("keys", [["T1"] * 12, ["a", "b", "a", "c", "b", "a", "c", "c", "a"]])
+def test_dti_screening_with_distinct_proteins_once(keys, math_mode):
+    """the protein side of a screening batch holds every distinct protein once (`pro_index`); scores are
+    bitwise those of the reference-style batch with one protein copy per pair."""
+    from glam_b200 import model
+    from glam_b200.synth import make_molecule_batch, make_protein_batch
+    pos, index = model.dedupe_keys(keys)
+    assert [keys[i] for i in pos] == list(dict.fromkeys(keys)) and [list(dict.fromkeys(keys))[i] for i in index.tolist()] == keys
+    P = len(keys)
+    torch.manual_seed(3)
+    m = model.ArchitectureDTI(15, 49, 4, 8, hid_dim_alpha=4, e_dim=64, out_dim=1, mol_block="_TripletMessage", pro_block="_GCNConv",
+                              message_steps=3, mol_readout="GlobalPool5", pro_readout="GlobalPool5", graph_do="_None()", end_do="_None()",
+                              pre_act="ReLU", graph_act="LeakyReLU", flat_act="CELU", end_act="ReLU").to(DEV).eval()
+    lig = make_molecule_batch(P, node_dim=15, edge_dim=4, seed=21)
+    uniq = make_protein_batch(len(pos), seed=22, min_len=60, max_len=140)
+    full = _repeat_graphs(uniq, index.tolist())
+    with torch.no_grad():
+        want = m(lig.to(DEV), full.to(DEV))
+        got = m(lig.to(DEV), uniq.to(DEV), pro_index=index.to(DEV))
+    assert torch.isfinite(got).all() and torch.equal(got, want)
+    with pytest.raises(Exception):                       # forward-only: gradients through a shared protein are not defined here
+        m.train()
+        m(lig.to(DEV), uniq.to(DEV), pro_index=index.to(DEV)).sum().backward()
