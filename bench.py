@@ -705,6 +705,15 @@ def run_ours(args):
             variants["per-op kernels (fused message kernel off)"] = {"value": r["value"], "ms_per_step": r["ms"], "gpu_launches_per_step": r["launches"]}
         finally:
             layer.USE_FUSED_STACK = True
+        # the reference CLI's own defaults for the block (src_1gp/run.py:28,31-37): PairNorm, Dropout(0.2), RReLU — train-mode
+        # RReLU and dropout are torch's (philox), so this configuration runs the per-op stacked / looped path, not the fused kernels
+        torch.manual_seed(0)
+        kw_def = dict(MODEL_KW); kw_def.update(pre_act="RReLU", graph_act="RReLU", flat_act="RReLU")
+        net_def = M.ArchitectureGP(DIMS["node_dim"], DIMS["edge_dim"], graph_norm="_PairNorm", graph_do="Dropout(0.2)",
+                                   flat_do="_None()", end_do="Dropout(0.2)", **kw_def).train()
+        r = train_workload(hz, net_def, mse, host[:4], 10, 3, GRAPHS)
+        variants["reference CLI defaults (graph_norm=_PairNorm, graph_do=Dropout(0.2), RReLU everywhere)"] = {
+            "value": r["value"], "ms_per_step": r["ms"], "gpu_launches_per_step": r["launches"]}
         _lib.set_math_mode("fp32"); torch.backends.cuda.matmul.allow_tf32 = False
         try:
             r = train_workload(hz, gp_net(), mse, host[:4], 10, 3, GRAPHS)
