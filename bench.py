@@ -407,6 +407,15 @@ def screening_workload(hz, net, rank, graphs=SCREEN_GRAPHS, total=SCREEN_TOTAL, 
     sp = ScreenStep(net, pk_dev[0], device=hz.dev, double_buffer=True)
     ms_pk = run(lambda i: sp.step(pk_dev[i % n_batches]))
     ms_pk_e2e = run(lambda i: sums.append(sp.step(pk_host[i % n_batches], prefetch=pk_host[(i + 1) % n_batches]).sum().item()))
+    del sp
+    # the same job with the reference's default graph_norm (_PairNorm, src_1gp/run.py:28): applied inside the fused kernel
+    import copy
+    net_pn = copy.deepcopy(net)
+    from glam_b200 import layer as _layer
+    net_pn.mol_conv.norm = _layer._PairNorm(C)
+    spn = ScreenStep(net_pn, dev_b[0], device=hz.dev, double_buffer=True)
+    ms_pn = hz.timed(lambda i: spn.step(dev_b[i % n_batches]), 12) / 12
+    del spn
     return {"value": graphs * hz.world / (ms * 1e-3), "unit": UNIT, "graphs_per_gpu_batch": graphs, "batches_per_gpu": steps,
             "molecules_per_job": steps * graphs * hz.world, "ms_per_batch": ms,
             "e2e": {"value": graphs * hz.world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_batch": ms_e2e,
@@ -416,6 +425,8 @@ def screening_workload(hz, net, rank, graphs=SCREEN_GRAPHS, total=SCREEN_TOTAL, 
                                      "h2d_bytes_per_batch": pk_host[0].nbytes(), "d2h_bytes_per_batch": 4},
                              "note": "inputs from glam_b200.packed.PackedBatch (uint8/uint16 prebuilt index, unpacked on the device "
                                      "inside the captured step); same molecules, bitwise the same scores"},
+            "graph_norm=_PairNorm (the reference's default, inside the fused kernel)": {"value": graphs * hz.world / (ms_pn * 1e-3), "unit": UNIT,
+                                                                                        "ms_per_batch": ms_pn},
             "note": "eval-mode forward, graphs sharded by molecule, no collective; value = inputs resident in HBM (3 distinct "
                     "171 MB batches rotate: larger than L2), e2e = pinned host batches through ScreenStep.step(batch, prefetch=next) "
                     "+ checksum read-back"}
@@ -642,7 +653,9 @@ def run_ours(args):
                     fn()
                 e1.record(); torch.cuda.synchronize()
             return e0.elapsed_time(e1) / reps
-        t_one, t_rep = timed(lambda: dti_net(lig, one, pro_index=idx)), timed(lambda: dti_net(lig, rep))
+        f_one, f_rep = (lambda: dti_net(lig, one, pro_index=idx)), (lambda: dti_net(lig, rep))
+        timed(f_one, 2); timed(f_rep, 2)                         # first calls build the per-batch indices and size the allocator
+        t_one, t_rep = min(timed(f_one), timed(f_one)), min(timed(f_rep), timed(f_rep))
         dti_scr = {"pairs_per_batch": P, "protein_residues": one.num_nodes,
                    "distinct protein once (pro_index)": {"value": P / (t_one * 1e-3), "unit": "pairs/s", "ms_per_batch": t_one},
                    "one protein copy per pair (the reference's collation)": {"value": P / (t_rep * 1e-3), "unit": "pairs/s", "ms_per_batch": t_rep},

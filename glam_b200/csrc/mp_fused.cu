@@ -178,6 +178,7 @@ struct MpParams {
     float* x_out; float* h_out;
     float* sX; float* sHH; float* sXPE; float* sAGG; float* sALPHA; float* sM; float* sRZN; float* sGH;
     float* sGT;                              // tile-blocked gate save for the one-launch backward (replaces sRZN / sGH), or NULL
+    const int64_t* pn_batch; float pn_eps;   // PairNorm on every step's block input (evaluation): graph id per node, or NULL
     unsigned long long* phase_clock;         // profiling aid (glam_message_stack_phase_clock): [grid][16] cycles per phase, or NULL
 };
 
@@ -193,7 +194,7 @@ struct MpGeom {
     static constexpr int NS = (C + 15) / 16 * 16;                       // N of the scale projection
     static constexpr int NG = (3 * C + 15) / 16 * 16;                   // N of each GRU product
     static constexpr int WROWS = NXP > NG ? NXP : NG;
-    static constexpr int TM_XP = 0, TM_PRE = NXP, TM_GI = NXP + NS, TM_GH = NXP + NS + NG, TM_COLS = NXP + NS + 2 * NG;
+    static constexpr int TM_XP = 0, TM_PRE = NXP, TM_GI = NXP + NS, TM_GH = NXP + NS + NG, TM_XRES = NXP + NS + 2 * NG, TM_COLS = TM_XRES + C;   // XRES: the pre-norm block input (PairNorm mode)
     static constexpr int WQ = NT / 128;                                 // warps per TMEM lane quarter = threads per tile row
     static constexpr int JPW = (CQ + WQ - 1) / WQ;                      // epilogues: 4-channel chunks per warp
     static constexpr int REGB0 = NPA * kMpPanel, REGB1 = kMpM * LD * 4, REGB2 = kMpM * 3 * C * 4;
@@ -206,7 +207,8 @@ struct MpGeom {
     static constexpr int M_AE = M_WE + kMpMaxDe * HC, M_U = M_AE + kMpMaxDe * H, M_BIAS = M_U + C * 2 * H, M_GB = M_BIAS + C;
     static constexpr int M_PRE = (M_GB + 4 * C + 3) / 4 * 4;            // input LinearBlock: W [C][raw_dim <= kMpMaxRaw] | b [C]
     static constexpr int M_CLK = (M_PRE + C * kMpMaxRaw + C + 3) / 4 * 4;  // 16 phase-cycle counters (profiling aid)
-    static constexpr int M_END = M_CLK + 16;
+    static constexpr int M_GID = M_CLK + 16;                            // PairNorm: local graph id per tile row (bytes)
+    static constexpr int M_END = M_GID + kMpM / 4;
     static constexpr int SMEM = OFF_MISC + M_END * 4;
     static_assert(NT % 128 == 0 && NT >= 256 && NT <= 1024, "threads");
     static_assert(KSX <= 5 && TQ <= 2, "tail panel holds 8 features per operand");
@@ -251,6 +253,7 @@ mp_fused_kernel(const MpParams p) {
     float* bias_s = misc + G::M_BIAS;  float* gb = misc + G::M_GB;
     float* Wp = misc + G::M_PRE;  float* bp = Wp + C * kMpMaxRaw;
     unsigned int* clk = reinterpret_cast<unsigned int*>(misc + G::M_CLK);
+    uint8_t* gid_s = reinterpret_cast<uint8_t*>(misc + G::M_GID);
     float* xp = reinterpret_cast<float*>(REG);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned int clk_start = (unsigned int)clock64();
@@ -452,6 +455,10 @@ mp_fused_kernel(const MpParams p) {
             const int e = k * NT + tid;
             if (e < ne) rec[e] = pfs[k] | (pft[k] << 8);
         }
+        if (p.pn_batch) {                                        // PairNorm: local graph id of every tile row (0 .. 127)
+            const int64_t gfirst = p.pn_batch[n0];
+            for (int i = tid; i < kMpM; i += NT) gid_s[i] = i < nd ? (uint8_t)(p.pn_batch[n0 + i] - gfirst) : (uint8_t)255;
+        }
         fence_proxy_async_smem();
         __syncthreads();
         MP_TICK(0)
@@ -463,7 +470,69 @@ mp_fused_kernel(const MpParams p) {
         }
 
         for (int s = 0; s < p.steps; ++s) {
-            const bool h_is_x = (s == 0 && p.h0 == nullptr);     // first step: h = x (layer.py:253-254)
+            const bool pn = p.pn_batch != nullptr;
+            const bool h_is_x = (s == 0 && p.h0 == nullptr && !pn); // first step: h = x (layer.py:253-254); PairNorm copies x into the h panels
+            if (pn) {
+                // ---------------------------------------------------- P0: PairNorm of the block input per graph (PyG PairNorm(scale=1) @1.7.2
+                // behind _PairNorm, src_1gp/layer.py:179-185,255): xc = x - mean_g(x), y = xc / sqrt(eps + mean_g(sum_c xc^2)).
+                // The tile holds whole graphs, so the statistics are tile-local; the pre-norm rows are parked in tensor memory
+                // for the residual (layer.py:264) and, on the first step, copied into the h panels (h = x BEFORE the norm, :253)
+                float* mu = reinterpret_cast<float*>(REG);           // [graphs of the tile <= 128][C]   (the region is free here)
+                float* rsq = mu + kMpM * C;                          // [128] squared deviation of a row
+                float* isg = rsq + kMpM;                             // [128] 1 / sqrt(eps + ...) per graph
+                int* gst = reinterpret_cast<int*>(isg + kMpM);       // [129] first row of every graph
+                const int ng = nd > 0 ? (int)gid_s[nd - 1] + 1 : 0;
+                for (int r = tid; r < nd; r += NT)
+                    if (r == 0 || gid_s[r] != gid_s[r - 1]) gst[gid_s[r]] = r;
+                if (tid == 0) gst[ng] = nd;
+                __syncthreads();
+                for (int i = tid; i < ng * C; i += NT) {             // mean per (graph, channel), rows in order
+                    const int k = i / C, c = i - k * C, q = c >> 2;
+                    float acc = 0.f;
+                    for (int r = gst[k]; r < gst[k + 1]; ++r)
+                        acc += *reinterpret_cast<const float*>((q < 8 ? XM + pan_off(r, q) : AT + pan_off(r, q - 8)) + 4 * (c & 3));
+                    mu[i] = acc / (float)(gst[k + 1] - gst[k]);
+                }
+                __syncthreads();
+                for (int r = tid; r < nd; r += NT) {                 // squared deviation of every row
+                    const float4* m4 = reinterpret_cast<const float4*>(mu + gid_s[r] * C);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int q = 0; q < CQ; ++q) {
+                        const float4 v = q < 8 ? lds128(XM + pan_off(r, q)) : lds128(AT + pan_off(r, q - 8)), m = m4[q];
+                        const float dx = v.x - m.x, dy = v.y - m.y, dz = v.z - m.z, dw = v.w - m.w;
+                        acc = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, acc))));
+                    }
+                    rsq[r] = acc;
+                }
+                __syncthreads();
+                for (int k = tid; k < ng; k += NT) {
+                    float acc = 0.f;
+                    for (int r = gst[k]; r < gst[k + 1]; ++r) acc += rsq[r];
+                    isg[k] = 1.f / sqrtf(p.pn_eps + acc / (float)(gst[k + 1] - gst[k]));
+                }
+                __syncthreads();
+#pragma unroll
+                for (int jj = 0; jj < G::JPW; ++jj) {
+                    const int j = cg + WQ * jj;
+                    if (j < CQ) {                                    // warp-uniform
+                        uint8_t* xd = j < 8 ? XM + pan_off(row, j) : AT + pan_off(row, j - 8);
+                        const float4 v = lds128(xd);
+                        tmem_st4(lane_base + G::TM_XRES + 4 * j, v);
+                        if (s == 0 && p.h0 == nullptr) sts128(j < 8 ? HM + pan_off(row, j) : AT + pan_off(row, 2 + j - 8), v);
+                        if (row < nd) {
+                            const int k = gid_s[row];
+                            const float4 m = lds128(mu + k * C + 4 * j);
+                            const float sc = isg[k];
+                            sts128(xd, make_float4((v.x - m.x) * sc, (v.y - m.y) * sc, (v.z - m.z) * sc, (v.w - m.w) * sc));
+                        }
+                    }
+                }
+                tmem_st_wait();
+                tc_fence_before_sync();
+                fence_proxy_async_smem();
+                __syncthreads();
+            }
             // -------------------------------------------------------- P1: xp = x Wn on the tensor core (and, right behind it,
             // gh = h W_hh^T, which depends on nothing this step computes); exact logit columns on the CUDA cores meanwhile
             if (mma_thread) {
@@ -705,7 +774,8 @@ mp_fused_kernel(const MpParams p) {
                     uint8_t* xdst = j < 8 ? XM + pan_off(row, j) : AT + pan_off(row, j - 8);
                     uint8_t* hdst = j < 8 ? HM + pan_off(row, j) : AT + pan_off(row, 2 + j - 8);
                     const float4 hv = lds128(hsrc);
-                    const float4 xv = p.res ? lds128(xdst) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.res) { if (pn) { float t4[4]; tmem_ld4(lane_base + G::TM_XRES + 4 * j, t4); xv = make_float4(t4[0], t4[1], t4[2], t4[3]); } else xv = lds128(xdst); }
                     const float4 b_r = lds128(gb + 16 * j), b_z = lds128(gb + 16 * j + 4), b_n = lds128(gb + 16 * j + 8), b_h = lds128(gb + 16 * j + 12);
                     float2 r[2], z[2], nn[2], gn[2], hw[2], xo[2];
 #define MP_GATE2(k, i, BR, BZ, BN, BH, HV, XV)                                                                    \
@@ -878,13 +948,14 @@ extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const fl
                                       int edge_dim, int steps, float negative_slope, int act, float act_param, int res,
                                       int conv_only, int keep_all, float* x_out, float* h_out, float* save_x, float* save_h,
                                       float* save_xpe, float* save_agg, float* save_alpha, float* save_m, float* save_rzn,
-                                      float* save_gh, float* save_gt, void* stream_) {
+                                      float* save_gh, float* save_gt, const int64_t* pn_batch, float pn_eps, void* stream_) {
     GLAM_REQUIRE(glam_message_stack_supported(channels, heads, edge_dim),
                  "glam_message_stack_fwd: unsupported (channels=%d heads=%d edge_dim=%d math mode %d); use the per-op calls", channels,
                  heads, edge_dim, g_math_mode_get());
     GLAM_REQUIRE(num_nodes >= 0 && num_edges >= 0 && steps >= 1, "glam_message_stack_fwd: bad sizes");
     if (num_nodes == 0) return 0;
     const bool save = save_xpe != nullptr;              // training: also write what MessageStackFn.backward / TripletConvFn.backward read
+    GLAM_REQUIRE(!pn_batch || (!save && !conv_only && !h0), "glam_message_stack_fwd: PairNorm inside the kernel is an evaluation-mode path (no saves, no conv_only, h0 == NULL)");
     GLAM_REQUIRE((x0 || x_raw) && w_ext && w_edge && att_edge && w_scale && bias && tiles && tile_meta && dst_rowptr && (num_edges == 0 || (dst_src && etype)),
                  "glam_message_stack_fwd: null pointer");
     GLAM_REQUIRE(!x_raw || (w_pre && raw_dim >= 1 && raw_dim <= kMpMaxRaw), "glam_message_stack_fwd: input LinearBlock needs weights and raw_dim <= %d", kMpMaxRaw);
@@ -905,7 +976,7 @@ extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const fl
     p.rowptr = dst_rowptr; p.src = dst_src; p.etype = etype; p.N = num_nodes; p.E = num_edges; p.De = edge_dim; p.steps = steps;
     p.act = act; p.res = res; p.conv_only = conv_only; p.keep_all = keep_all; p.slope = negative_slope; p.act_param = act_param;
     p.x_out = x_out; p.h_out = h_out; p.sX = save_x; p.sHH = save_h; p.sXPE = save_xpe; p.sAGG = save_agg; p.sALPHA = save_alpha;
-    p.sM = save_m; p.sRZN = save_rzn; p.sGH = save_gh; p.sGT = save_gt; p.phase_clock = g_mp_phase_clock;
+    p.sM = save_m; p.sRZN = save_rzn; p.sGH = save_gh; p.sGT = save_gt; p.pn_batch = pn_batch; p.pn_eps = pn_eps; p.phase_clock = g_mp_phase_clock;
     int rc = 0;
     cudaStream_t stream = (cudaStream_t)stream_;
     switch (channels) {

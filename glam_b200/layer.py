@@ -561,14 +561,22 @@ class MessageBlock(nn.Module):
         if pairnorm:
             gptr_pn, B_pn = G.graph_ptr(batch, num_graphs)
             pn = (gptr_pn, B_pn, float(self.norm.eps))
-        fi = _fused_index(g, x, edge_attr, batch, num_graphs, inner.heads, inner.node_channels) if (p_drop == 0.0 and pn is None) else None
-        if fi is not None and not _wants_grad(x, *self.parameters()):
+        no_grad = not _wants_grad(x, *self.parameters())
+        # PairNorm runs inside the fused kernel in evaluation (tile-local statistics: tiles are whole graphs); training with
+        # PairNorm keeps the per-op stacked node (deterministic norm kernels)
+        pn_in_kernel = pn is not None and no_grad and torch.is_tensor(batch) and batch.dtype == torch.int64 and batch.is_contiguous()
+        fi = (_fused_index(g, x, edge_attr, batch, num_graphs, inner.heads, inner.node_channels)
+              if (p_drop == 0.0 and (pn is None or pn_in_kernel)) else None)
+        if fi is not None and no_grad:
             # screening / evaluation: nothing is kept for backward, only the outputs leave the SM
             x_out, h_out = ops.message_stack_fwd(
                 x.contiguous(), None, w_ext, inner.weight_edge, att_edge, inner.weight_scale, inner.bias,
                 gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, g, fi, inner.heads, inner.node_channels,
-                int(steps), inner.negative_slope, fused[0], fused[1], bool(self.res), keep_all=(keep == "all"), pre=pre_fused)
+                int(steps), inner.negative_slope, fused[0], fused[1], bool(self.res), keep_all=(keep == "all"), pre=pre_fused,
+                pn=(batch, float(self.norm.eps)) if pn_in_kernel else None)
             return list(x_out.unbind(0)), h_out.unsqueeze(0)
+        if pn is not None:
+            fi = None                                            # (the training-mode fused pair has no PairNorm)
         if pre is not None:
             x = pre(x, batch=batch)
         ea = g.sorted_edge_attr(edge_attr)

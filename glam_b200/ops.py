@@ -284,7 +284,7 @@ def message_stack_supported(channels: int, heads: int, edge_dim: int) -> bool:
 
 
 def message_stack_fwd(x0, h0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, g, fi, heads, channels, steps,
-                      slope, act, act_param, res, conv_only=False, keep_all=False, save=None, pre=None):
+                      slope, act, act_param, res, conv_only=False, keep_all=False, save=None, pre=None, pn=None):
     """The whole message stack in one launch (csrc/mp_fused.cu).  Eval (save=None): returns (x_out [S|1,N,C], h_out [N,C]|None).
     Training: `save` = dict of preallocated stacked tensors X, HH, XPE, AGG, ALPHA, M, RZN, GH (conv_only: XPE, AGG, ALPHA) that
     the kernel fills; returns (x_out|None, None)."""
@@ -301,6 +301,10 @@ def message_stack_fwd(x0, h0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh
         x_in, x_raw, raw_dim = None, x0, x0.shape[1]
     else:
         assert x0.shape[1] == C
+    # pn = (batch int64 [N], eps): PairNorm on every step's block input inside the kernel (evaluation only)
+    pn_batch, pn_eps = (None, 0.0) if pn is None else pn
+    if pn_batch is not None:
+        assert save is None and not conv_only and h0 is None and pn_batch.dtype == torch.int64 and pn_batch.is_contiguous() and pn_batch.numel() == N
     x_out = h_out = None
     if save is None or conv_only:
         x_out = torch.empty(((steps if keep_all else 1), N, C), dtype=torch.float32, device=dev)
@@ -313,7 +317,8 @@ def message_stack_fwd(x0, h0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh
           _p(w_ih), _p(w_hh), _p(b_ih), _p(b_hh), _p(fi.tiles), _p(fi.meta), _p(g.dst_rowptr), _p(g.dst_src), _p(fi.etype),
           N, E, channels, heads, fi.edge_dim, steps, float(slope), act, float(act_param), 1 if res else 0,
           1 if conv_only else 0, 1 if keep_all else 0, _p(x_out), _p(h_out), _p(sv.get("X")), _p(sv.get("HH")), _p(sv.get("XPE")),
-          _p(sv.get("AGG")), _p(sv.get("ALPHA")), _p(sv.get("M")), _p(sv.get("RZN")), _p(sv.get("GH")), _p(sv.get("GT")), _stream(x0),
+          _p(sv.get("AGG")), _p(sv.get("ALPHA")), _p(sv.get("M")), _p(sv.get("RZN")), _p(sv.get("GH")), _p(sv.get("GT")),
+          _p(pn_batch), float(pn_eps), _stream(x0),
           label=f"[N={N},S={steps},{'save' if save is not None else 'eval'}{',conv' if conv_only else ''}]")
     return x_out, h_out
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLAM_B200_ABI_VERSION 7
+#define GLAM_B200_ABI_VERSION 8
 #define GLAM_MAX_HEADS 4
 
 int glam_abi_version(void);
@@ -303,7 +303,10 @@ int glam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
  *   (conv_only: save_xpe, save_agg, save_alpha and x_out only).  save_gt != NULL (then save_rzn / save_gh may be NULL): the
  *   gate-side tensors for glam_message_stack_bwd in its tile-blocked layout instead — [steps][N][7C]; inside step s the tile
  *   {n0, n1} owns floats [n0*7C, n1*7C) as 7*C/4 slots (r, z, n, gh_n, h, x', m; C/4 16-byte chunks each) of n1-n0 rows x
- *   16 bytes: a warp's 32 rows of one chunk are contiguous in the forward's stores and in the backward's loads.  If meta[1] != 0 the outputs are filled with NaN: callers
+ *   16 bytes: a warp's 32 rows of one chunk are contiguous in the forward's stores and in the backward's loads.  pn_batch !=
+ *   NULL (evaluation only: no saves, h0 == NULL): PairNorm(scale=1, eps=pn_eps) per graph on every step's block input inside the
+ *   kernel (_PairNorm, the reference's default graph_norm, src_1gp/layer.py:179-185,255; pn_batch = the int64 `batch` vector);
+ *   the residual and the first step's h use the un-normalised rows, as the reference does (layer.py:253,264).  If meta[1] != 0 the outputs are filled with NaN: callers
  *   check meta[1] on the host when they can (outside CUDA-graph capture) and fall back to the per-op entry points.
  *   glam_message_stack_supported: tf32 math mode, heads == 3, channels in {32,36,40}, edge_dim <= 4.
  * --------------------------------------------------------------------------------------------- */
@@ -331,7 +334,7 @@ int glam_message_stack_fwd(const float* x0, const float* h0, const float* x_raw,
                            int edge_dim, int steps, float negative_slope, int act, float act_param, int res,
                            int conv_only, int keep_all, float* x_out, float* h_out, float* save_x, float* save_h,
                            float* save_xpe, float* save_agg, float* save_alpha, float* save_m, float* save_rzn,
-                           float* save_gh, float* save_gt, void* stream);
+                           float* save_gh, float* save_gt, const int64_t* pn_batch, float pn_eps, void* stream);
 
 /* glam_message_stack_bwd — backward of glam_message_stack_fwd's training mode (h0 == NULL, no conv_only) in ONE launch
  *   (csrc/mp_fused_bwd.cu), on the same tile table: gate backward, the four input-gradient projections, the edge backward

@@ -606,3 +606,42 @@ def test_pairnorm_block_runs_stacked_and_matches_loop(math_mode):
         assert _rel(a, c) < 10 * tol
     ys2, gxs2, gps2, _ = run(True)
     assert torch.equal(ys2, ys) and torch.equal(gxs2, gxs) and all(torch.equal(a, c) for a, c in zip(gps2, gps))
+
+
+@pytest.mark.parametrize("C,De,act,res,n_graphs", [(36, 3, "CELU", True, 300), (32, 4, "RReLU", True, 90), (36, 3, "ReLU", False, 1)])
+def test_pairnorm_inside_the_fused_kernel_in_evaluation(C, De, act, res, n_graphs):
+    """The reference's default graph_norm (_PairNorm) applied to every step's block input INSIDE the one-launch forward
+    (evaluation / screening): against the per-op path (deterministic PairNorm kernels + per-op message kernels) and against the
+    plain loop over MessageBlock.forward; the fused kernel must actually be taken (launch count); bitwise run to run."""
+    from glam_b200 import _lib, layer
+    _lib.set_math_mode("tf32")
+    torch.manual_seed(9)
+    blk = layer.MessageBlock(C, C, De, norm="_PairNorm", dropout="_None()", conv="_TripletMessage", act=act, res=res)
+    with torch.no_grad():
+        for p in blk.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.2, 0.2)
+    blk = blk.to(DEV).eval()
+    b = _batch(n_graphs, C, De, 17).to(DEV)
+    x = (2.0 * torch.randn(b.num_nodes, C, generator=torch.Generator().manual_seed(5)) + 0.7).to(DEV)
+    with torch.no_grad():
+        layer.USE_FUSED_STACK = False
+        try:
+            xs_ref, h_ref = blk.run_steps(x, b.edge_index, b.edge_attr, 3, batch=b.batch, num_graphs=b.num_graphs)
+        finally:
+            layer.USE_FUSED_STACK = True
+        n0 = _lib.launch_count()
+        xs, h = blk.run_steps(x, b.edge_index, b.edge_attr, 3, batch=b.batch, num_graphs=b.num_graphs)
+        n_all = _lib.launch_count() - n0
+        xs2, h2 = blk.run_steps(x, b.edge_index, b.edge_attr, 3, batch=b.batch, num_graphs=b.num_graphs)
+        xi, hi = x, None
+        for _ in range(3):
+            xi, hi = blk(xi, b.edge_index, b.edge_attr, h=hi, batch=b.batch, num_graphs=b.num_graphs)
+    torch.cuda.synchronize()
+    assert n_all <= 8, f"fused path not taken: {n_all} launches"
+    for s in range(3):
+        e = _rel(xs[s], xs_ref[s])
+        print(f"step {s}: rel err {e:.2e}")
+        assert torch.isfinite(xs[s]).all() and e < 5e-4, f"step {s}: {e}"
+    assert _rel(h, h_ref) < 5e-4 and _rel(xs[2], xi) < 5e-4 and _rel(h, hi) < 5e-4
+    assert all(torch.equal(a, c) for a, c in zip(xs, xs2)) and torch.equal(h, h2)
