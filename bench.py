@@ -41,6 +41,7 @@ TOTAL_NODES, TOTAL_EDGES = NODES_PER * GRAPHS, EDGES_PER * GRAPHS      # 102 400
 MODEL_KW = dict(hid_dim_alpha=4, e_dim=1024, out_dim=1, mol_block="_TripletMessage", message_steps=3,
                 mol_readout="Set2Set", pre_act="ReLU", graph_act="CELU", flat_act="ReLU")
 NO_DROPOUT = dict(graph_do="_None()", flat_do="_None()", end_do="_None()")
+OVERLAP_ALLREDUCE = False            # engine.TrainStep's opt-in early gradient bucket (measured slower on 8 GPUs: DESIGN.md §6)
 N_RESIDENT = 16                      # distinct batches rotated through (16 x 10.7 MB inputs; each step also writes
                                      # ~0.7 GB of activations) -> nothing survives in the 126 MB L2 between steps
 SCREEN_GRAPHS = 65536                # configs[4]: 64k-graph batches
@@ -355,8 +356,8 @@ def train_workload(hz, net, loss_fn, host, steps, warmup, units, capture=True, e
     resident = [tuple(g.to(hz.dev) for g in b) if isinstance(b, tuple) else b.to(hz.dev) for b in host]
     n0 = _lib.launch_count()
     ts = TrainStep(net, loss_fn, resident[0], lr=1e-3, device=hz.dev, world_size=hz.world, use_cuda_graph=capture, warmup=3,
-                   double_buffer=True)
-    launches = (_lib.launch_count() - n0) // 5 if ts.graph is not None else None       # 3 warm-ups + 2 captures
+                   double_buffer=True, overlap_allreduce=OVERLAP_ALLREDUCE)
+    launches = (_lib.launch_count() - n0) // (6 if ts.overlap_allreduce else 5) if ts.graph is not None else None   # (probe +) 3 warm-ups + 2 captures
     nb = len(host)
 
     def step_resident(i):
@@ -550,6 +551,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    global OVERLAP_ALLREDUCE
+    OVERLAP_ALLREDUCE = bool(args.allreduce_overlap)
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     _lib.load()                                      # fail loudly if the CUDA library is missing
@@ -696,7 +699,7 @@ def run_ours(args):
                                 "issued on a copy stream one step ahead into the other input buffer set"},
                 "gpu_launches": int((head["launches"] or 0) * steps), "gpu_launches_per_step": head["launches"], "final_loss": head["loss"]}
     line.update({"n_gpus": world, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
-                 "data": "synthetic", "cuda_graph": gp["ts"].graph is not None, "warmup_internal_extra": 10 if world > 1 else 0,
+                 "data": "synthetic", "cuda_graph": gp["ts"].graph is not None, "allreduce_overlapped_with_backward": bool(gp["ts"].overlap_allreduce), "warmup_internal_extra": 10 if world > 1 else 0,
                  "clocks": clk.summary(t_head[0], t_head[1]) if clk is not None else None})
     cfg = workload_config(world, args.workload)
     cfg["also_measured"] = also
@@ -814,6 +817,7 @@ def main():
     ap.add_argument("--workload", default="gp", choices=["gp", "ddi", "dti", "screen"])
     ap.add_argument("--quick", action="store_true", help="only the headline workload (no other configs, variants, rooflines)")
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--allreduce-overlap", action="store_true", help="N > 1: engine.TrainStep's early gradient bucket, reduced under the stack's backward (A/B; slower)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-range", action="store_true", help="profiler range around the timed resident steps, then exit")
     args = ap.parse_args()

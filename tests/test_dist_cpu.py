@@ -29,12 +29,36 @@ def _worker(rank, world, port, out):
     loss = torch.nn.functional.mse_loss(model(mine), mine.y)
     loss.backward()
     grads.all_reduce_mean(world)
+    # the same step with the gathered bucket split in two: the parameters behind the message stack are reduced from a gradient
+    # hook while backward is still running (engine.TrainStep at world_size > 1), the rest at the end
+    flat_one = grads.flat.clone()
+    reduced = [p.grad.clone() for p in model.parameters()]
+    g2 = FlatGrads(model.parameters(), gather=True)
+    assert g2.enable_early_bucket(model, (O.MessageBlock,))
+    early = sum(p.numel() for p in g2.params[g2._early_at:])
+
+    def fwd_bwd():
+        g2.zero()
+        torch.nn.functional.mse_loss(model(mine), mine.y).backward()
+        g2.collect()
+        g2.all_reduce_mean(world)
+    ok_order = g2.check_early_order(fwd_bwd)
+    fired = []
+    orig = dist.all_reduce
+    dist.all_reduce = lambda t, *a, **k: (fired.append((t.numel(), bool(k.get("async_op")))), orig(t, *a, **k))[1]
+    try:
+        fwd_bwd()
+    finally:
+        dist.all_reduce = orig
+    err2 = (g2.flat - flat_one).abs().max().item()
+    g2.disable_early_bucket()
     if rank == 0:
         ref = O.ArchitectureGP(9, 3, **kw)
         ref.load_state_dict(model.state_dict())
         torch.nn.functional.mse_loss(ref(full), full.y).backward()
-        err = max((p.grad - q.grad).abs().max().item() for p, q in zip(model.parameters(), ref.parameters()))
-        torch.save({"err": err, "nodes": mine.num_nodes, "flat": grads.flat.numel()}, out)
+        err = max((g - q.grad).abs().max().item() for g, q in zip(reduced, ref.parameters()))
+        torch.save({"err": err, "nodes": mine.num_nodes, "flat": grads.flat.numel(), "err2": err2, "ok_order": ok_order, "fired": fired,
+                    "early": early}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -47,6 +71,11 @@ def test_sharded_step_matches_full_batch(tmp_path):
     res = torch.load(out)
     assert res["err"] < 1e-6, res
     assert res["flat"] > 1000
+    # two-bucket path: same reduced gradients; the early bucket (everything behind the message stack) went asynchronously from the
+    # hook BEFORE the rest, and its gradients were final before the stack's
+    assert res["ok_order"] and res["err2"] < 1e-7, res
+    assert res["fired"] == [(res["early"], True), (res["flat"] - res["early"], False)], res
+    assert res["early"] > res["flat"] // 2
 
 
 def test_shards_partition_the_batch():
