@@ -62,6 +62,8 @@ SIGNATURES = {
     "glam_set2set_round_bwd": (I32, [P, I64, P, I64, I32, P, P, P, P, P, I64, I32, P, P, I32, P, P]),
     "glam_pair_dot_pool_fwd": (I32, [P, P, P, P, I64, I32, P, P, P, P, P]),
     "glam_pair_dot_pool_fwd_idx": (I32, [P, P, P, P, P, I64, I32, P, P, P, P, P]),
+    "glam_pair_dot_pool_fwd_tc": (I32, [P, P, P, P, P, I64, I32, P, P, P, P, P]),
+    "glam_pair_dot_pool_tc_supported": (I32, [I32]),
     "glam_pair_dot_pool_bwd": (I32, [P, P, P, P, P, P, P, P, I64, I32, P, P, P]),
     "glam_graph_tile_caps": (I32, [P, P]),
     "glam_graph_tiles_workspace_bytes": (SZ, [I64]),

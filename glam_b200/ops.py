@@ -19,7 +19,12 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+_call_dev = None     # device of the stream handed to the next library call (see _call)
+
+
 def _stream(t: torch.Tensor):
+    global _call_dev
+    _call_dev = t.device
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
@@ -47,6 +52,16 @@ def set_profile(sink):
 
 def _call(name: str, *args, label: str = ""):
     fn = getattr(_lib.load(), name)
+    dev = _call_dev
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        # tensors on a device that is not the current one (one process driving several GPUs): the launch, the per-device
+        # function attributes and the workspace queries must see THAT device
+        with torch.cuda.device(dev):
+            return _call_on_device(fn, name, args, label)
+    return _call_on_device(fn, name, args, label)
+
+
+def _call_on_device(fn, name, args, label):
     if _profile is None:
         _lib.check(fn(*args), name)
         return
@@ -455,6 +470,9 @@ def set2set_round_bwd(x, gates, c_prev, c_new, att, gptr, num_graphs, g_u, g_c, 
           _p(att), _p(g_u), g_u.stride(0), g_u.shape[1], _p(g_c), _p(g_x), 1 if accumulate else 0, _p(G), _stream(x))
 
 
+TC_DOT_POOL_MIN_ROWS = 96    # average rows per graph of the second side from which the tensor-core dot-pool is used
+
+
 def pair_dot_pool_fwd(xa, xb, ptr_a, ptr_b, num_pairs, idx_b=None):
     """idx_b (int32 [num_pairs], optional): pair g reads graph idx_b[g] of the b side (distinct graphs stored once)."""
     C, dev = xa.shape[1], xa.device
@@ -462,6 +480,15 @@ def pair_dot_pool_fwd(xa, xb, ptr_a, ptr_b, num_pairs, idx_b=None):
     argmax = torch.empty((num_pairs, 2), dtype=torch.int32, device=dev)
     sa = torch.empty((num_pairs, C), dtype=torch.float32, device=dev)
     sb = torch.empty((num_pairs, C), dtype=torch.float32, device=dev)
+    # second side large (drug-target pairs: ~500 residues): S = Xa Xb^T is a real GEMM -> tensor cores (tf32 math mode); small
+    # second sides (drug-drug: 25 x 25) stay on the exact CUDA-core kernel, which is faster there
+    rows_b = xb.shape[0] / max(int(ptr_b.numel()) - 1, 1)
+    if rows_b >= TC_DOT_POOL_MIN_ROWS and xa.is_contiguous() and xb.is_contiguous() and _lib.load().glam_pair_dot_pool_tc_supported(C):
+        if idx_b is not None:
+            assert idx_b.dtype == torch.int32 and idx_b.is_contiguous() and idx_b.numel() == num_pairs
+        _call("glam_pair_dot_pool_fwd_tc", _p(xa), _p(xb), _p(ptr_a), _p(ptr_b), _p(idx_b), num_pairs, C, _p(out), _p(argmax),
+              _p(sa), _p(sb), _stream(xa))
+        return out, argmax, sa, sb
     if idx_b is not None:
         assert idx_b.dtype == torch.int32 and idx_b.is_contiguous() and idx_b.numel() == num_pairs
         _call("glam_pair_dot_pool_fwd_idx", _p(xa), _p(xb), _p(ptr_a), _p(ptr_b), _p(idx_b), num_pairs, C, _p(out), _p(argmax),

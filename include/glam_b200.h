@@ -228,6 +228,13 @@ int glam_pair_dot_pool_fwd(const float* xa, const float* xb, const int32_t* ptr_
 int glam_pair_dot_pool_fwd_idx(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b,
                                const int32_t* idx_b, int64_t num_pairs, int channels, float* out, int32_t* argmax,
                                float* sum_a, float* sum_b, void* stream);
+/* Tensor-core variant of the forward for pairs whose second side is large (drug-target: 25 x ~500 x C is a real GEMM): S on
+ * tcgen05 with TF32 operands ([128 x 256] accumulator tiles in TMEM, thread = ligand row scans for the max / first arg-max);
+ * the mean and sum_a / sum_b stay exact fp32.  idx_b may be NULL.  Needs tf32 math mode, channels % 4 == 0 in [32, 64]. */
+int glam_pair_dot_pool_tc_supported(int channels);
+int glam_pair_dot_pool_fwd_tc(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b,
+                              const int32_t* idx_b, int64_t num_pairs, int channels, float* out, int32_t* argmax,
+                              float* sum_a, float* sum_b, void* stream);
 int glam_pair_dot_pool_bwd(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b,
                            const float* g_out, const int32_t* argmax, const float* sum_a, const float* sum_b,
                            int64_t num_pairs, int channels, float* g_xa, float* g_xb, void* stream);

@@ -40,3 +40,18 @@ torch.cuda.synchronize(); e0.record()
 for _ in range(10): ss.run_resident()
 e1.record(); torch.cuda.synchronize()
 print(f"captured forward: {e0.elapsed_time(e1)/10*1e3:.1f} us per {graphs}-graph batch = {graphs/(e0.elapsed_time(e1)/10*1e-3)/1e6:.2f} M graphs/s")
+
+# phase clock of the fused kernel inside the captured forward (glam_message_stack_phase_clock)
+PH = ["tile load", "logits", "softmax", "proj wait", "tmem->xp", "aggregate", "agg panels", "scale wait", "celu epi", "gru wait", "gates",
+      "outputs", "tile end"]
+lib = _lib.load()
+clk = torch.zeros(148, 32, dtype=torch.int64, device=dev)
+with torch.no_grad():
+    G.clear_caches(); net(b); torch.cuda.synchronize()
+    lib.glam_message_stack_phase_clock(clk.data_ptr())
+    G.clear_caches(); net(b); torch.cuda.synchronize()
+    lib.glam_message_stack_phase_clock(None)
+c = clk.double().mean(0).cpu()
+tot = float(c[:13].sum())
+print(f"fused kernel in the screening forward: {tot/1.965e3:.1f} us of SM cycles per CTA; " + ", ".join(f"{n} {100*float(c[i])/tot:.1f}%" for i, n in enumerate(PH))
+      + f"; set-up {float(c[14])/1.965e3:.1f} us")

@@ -196,7 +196,9 @@ def test_readouts_golden(golden_layers, name, kind, C, math_mode):
 
 
 @pytest.mark.parametrize("name", ["dotpool_ddi_C36", "dotpool_dti_C60"])
-def test_dot_pool_golden(golden_layers, name):
+def test_dot_pool_golden(golden_layers, name, math_mode):
+    """fp32 mode: exact fp32 products on the CUDA cores; tf32 mode: S = Xa Xb^T on the tcgen05 tensor cores (TF32 operands), the
+    mean and the column sums backward needs exact in both."""
     from glam_b200 import layer
     c32, c64 = golden_layers[f"{name}_f32"], case(golden_layers, f"{name}_f64")
     xa = c32["xa"].to(DEV).requires_grad_(True)
