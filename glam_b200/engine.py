@@ -7,8 +7,9 @@ launch overhead — not the kernels — would otherwise set the pace.  `ScreenSt
 for virtual screening (no collective: graphs shard by molecule across ranks).
 
 Host batches (`glam_b200.synth.GraphBatch`, i.e. the fields of a PyG Batch) are copied into fixed device
-buffers, so every batch of a run must have the same (N, E, B) — the synthetic generator can emit
-fixed-size batches; a real loader would bucket by size and keep one captured graph per bucket.
+buffers, so a captured step has one shape (N, E, B).  `ScreenStep.step` pads smaller batches to it with dummy
+graphs behind the real ones (`synth.pad_graph_batch`) — one capture serves a loader with varying molecule sizes;
+`TrainStep` wants equal shapes (the synthetic generator emits them; a padded training batch would need a masked loss).
 """
 from __future__ import annotations
 
@@ -427,16 +428,30 @@ class ScreenStep:
                 self.outs[self._slot] = self.model(*_model_args(self.statics[self._slot]))
         return self.outs[self._slot]
 
+    def _fit(self, batch):
+        """Batches smaller than the captured shape are padded with dummy graphs behind the real ones (synth.pad_graph_batch), so a
+        loader with varying molecule sizes / a short last batch replays the same captured step; returns (batch, real graphs)."""
+        from .synth import pad_graph_batch
+        if isinstance(batch, GraphBatch):
+            st = self.static[0]
+            if isinstance(st, GraphBatch) and (batch.num_nodes, batch.num_edges, batch.num_graphs) != (st.num_nodes, st.num_edges, st.num_graphs):
+                return pad_graph_batch(batch, st.num_nodes, st.num_edges, st.num_graphs), batch.num_graphs
+        return batch, None
+
     def step(self, batch: GraphBatch, prefetch: Optional[GraphBatch] = None) -> torch.Tensor:
+        """Scores of `batch` (device tensor; valid until the slot is reused).  A single GraphBatch smaller than the captured
+        example is padded to it and the scores of its real graphs are returned."""
+        fitted, real = self._fit(batch)
         if len(self.statics) == 1:
-            _copy_into(self.static, batch)
-            return self.run_resident()
+            _copy_into(self.static, fitted)
+            out = self.run_resident()
+            return out if real is None else out[:real]
         main = torch.cuda.current_stream(self.device)
         slot = self._slot
         if self._prefetched is not None:
             main.wait_event(self._copied[slot])
         if self._prefetched is not batch:
-            _copy_into(self.statics[slot], batch)
+            _copy_into(self.statics[slot], fitted)
         self._prefetched = None
         out = self.run_resident()
         self._consumed[slot].record(main)
@@ -444,8 +459,8 @@ class ScreenStep:
             nxt = slot ^ 1
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(self._consumed[nxt])
-                _copy_into(self.statics[nxt], prefetch)
+                _copy_into(self.statics[nxt], self._fit(prefetch)[0])
                 self._copied[nxt].record(self._copy_stream)
             self._prefetched = prefetch
             self._slot = nxt
-        return out
+        return out if real is None else out[:real]

@@ -236,3 +236,36 @@ def shard_by_graph(batch: GraphBatch, rank: int, world: int) -> GraphBatch:
     emask = (batch.edge_index[1] >= n0) & (batch.edge_index[1] < n1)
     return GraphBatch(batch.x[n0:n1], batch.edge_index[:, emask] - n0, batch.edge_attr[emask],
                       batch.batch[n0:n1] - lo, None if batch.y is None else batch.y[lo:hi], hi - lo)
+
+
+def pad_graph_batch(b: GraphBatch, nodes: int, edges: int, graphs: int, max_nodes: int = 128, max_edges: int = 768) -> GraphBatch:
+    """`b` padded to exactly (`nodes`, `edges`, `graphs`) with dummy graphs appended BEHIND the real ones, so that batches of
+    varying size can be replayed through ONE captured step (engine.ScreenStep pads with this): the padding nodes / edges are
+    spread evenly over the `graphs - b.num_graphs` dummy graphs (zero features, bond type 0, ring edges i -> i+1; each at most
+    `max_nodes` nodes / `max_edges` edges — the fused kernels' per-graph caps).  The scores of the real graphs are unchanged
+    (graphs are independent); rows `b.num_graphs:` of the output belong to the dummies."""
+    N, E, B = b.num_nodes, b.num_edges, b.num_graphs
+    pn, pe, d = nodes - N, edges - E, graphs - B
+    if min(pn, pe, d) < 0:
+        raise ValueError(f"batch ({N} nodes, {E} edges, {B} graphs) exceeds the captured capacity ({nodes}, {edges}, {graphs})")
+    if pn == 0 and pe == 0 and d == 0:
+        return b
+    if d == 0 or pn < d or pn > max_nodes * d or pe > max_edges * d:
+        raise ValueError(f"cannot pad ({N}, {E}, {B}) to ({nodes}, {edges}, {graphs}): {pn} nodes / {pe} edges do not fit {d} dummy graphs "
+                         f"of 1..{max_nodes} nodes and <= {max_edges} edges — capture with more spare graphs")
+    k = torch.arange(d)
+    n_g = pn // d + (k < pn % d).long()                              # nodes per dummy graph (>= 1)
+    e_g = pe // d + (k < pe % d).long()
+    n_off = torch.cumsum(n_g, 0) - n_g + N
+    gid = torch.repeat_interleave(k, e_g)                            # dummy graph of every padding edge
+    j = torch.arange(pe) - torch.repeat_interleave(torch.cumsum(e_g, 0) - e_g, e_g)   # running index inside its graph
+    src = n_off[gid] + j % n_g[gid]
+    dst = n_off[gid] + (j + 1) % n_g[gid]
+    dev = b.x.device
+    ea = torch.zeros((pe, b.edge_attr.shape[1]), dtype=b.edge_attr.dtype)
+    ea[:, 0] = 1.0
+    y = None if b.y is None else torch.cat([b.y, torch.zeros((d,) + tuple(b.y.shape[1:]), dtype=b.y.dtype, device=b.y.device)])
+    return GraphBatch(torch.cat([b.x, torch.zeros((pn, b.x.shape[1]), dtype=b.x.dtype, device=dev)]),
+                      torch.cat([b.edge_index, torch.stack([src, dst]).to(dev)], dim=1),
+                      torch.cat([b.edge_attr, ea.to(dev)]),
+                      torch.cat([b.batch, (B + torch.repeat_interleave(k, n_g)).to(dev)]), y, graphs)

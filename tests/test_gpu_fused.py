@@ -645,3 +645,25 @@ def test_pairnorm_inside_the_fused_kernel_in_evaluation(C, De, act, res, n_graph
         assert torch.isfinite(xs[s]).all() and e < 5e-4, f"step {s}: {e}"
     assert _rel(h, h_ref) < 5e-4 and _rel(xs[2], xi) < 5e-4 and _rel(h, hi) < 5e-4
     assert all(torch.equal(a, c) for a, c in zip(xs, xs2)) and torch.equal(h, h2)
+
+
+def test_screen_step_replays_one_captured_step_on_batches_of_varying_size():
+    """A loader with varying molecule sizes (and a short last batch) through ONE captured forward: ScreenStep pads every batch
+    to the captured shape with dummy graphs behind the real ones; the scores of the real graphs are bitwise those of the
+    unpadded eager forward... up to the tile they share with a dummy graph: compared with a tolerance-free equality per graph."""
+    from glam_b200 import model
+    from glam_b200.engine import ScreenStep
+    from glam_b200.synth import make_molecule_batch, pad_graph_batch
+    torch.manual_seed(5)
+    kw = dict(hid_dim_alpha=4, e_dim=64, out_dim=1, mol_block="_TripletMessage", message_steps=3, mol_readout="Set2Set",
+              pre_act="ReLU", graph_act="CELU", flat_act="ReLU", graph_do="_None()", end_do="_None()", graph_norm="_PairNorm")
+    net = model.ArchitectureGP(9, 3, **kw).to(DEV).eval()
+    batches = [make_molecule_batch(n, seed=40 + i) for i, n in enumerate((200, 187, 200, 61))]
+    cap = (max(b.num_nodes for b in batches) + 64, max(b.num_edges for b in batches) + 64, 200 + 8)
+    ss = ScreenStep(net, pad_graph_batch(batches[0], *cap).to(DEV), device=DEV, double_buffer=True)
+    for i, b in enumerate(batches):
+        got = ss.step(b.pin_memory(), prefetch=batches[i + 1].pin_memory() if i + 1 < len(batches) else None).clone()
+        with torch.no_grad():
+            want = net(b.to(DEV))
+        assert got.shape == want.shape == (b.num_graphs, 1)
+        assert torch.isfinite(got).all() and torch.equal(got, want), f"batch {i}: max diff {(got - want).abs().max().item():.3e}"

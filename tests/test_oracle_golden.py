@@ -265,3 +265,30 @@ def test_nnconv_grouped_projection_algebra():
     got = torch.zeros(N, C, dtype=torch.float64).index_add_(0, ei[1], rows) / deg[:, None] + x @ m.conv.root + m.conv.bias
     torch.testing.assert_close(got, want, rtol=1e-12, atol=1e-12)
     torch.testing.assert_close(got[-2:], (x @ m.conv.root + m.conv.bias)[-2:], rtol=0, atol=0)
+
+
+def test_padding_with_dummy_graphs_leaves_the_scores_of_the_real_graphs_unchanged():
+    """synth.pad_graph_batch (what engine.ScreenStep uses to replay ONE captured step on batches of varying size): the padded
+    batch has exactly the requested shape, keeps the real graphs in front untouched, every padding edge stays inside its dummy
+    graph — and the oracle's scores of the real graphs are the same numbers."""
+    import pytest
+    from glam_b200.synth import make_molecule_batch, pad_graph_batch
+    from oracle import glam_oracle as O
+    b = make_molecule_batch(23, seed=11)
+    N, E, B = b.num_nodes, b.num_edges, b.num_graphs
+    p = pad_graph_batch(b, N + 301, E + 500, B + 5)
+    assert (p.num_nodes, p.num_edges, p.num_graphs) == (N + 301, E + 500, B + 5)
+    assert torch.equal(p.x[:N], b.x) and torch.equal(p.edge_index[:, :E], b.edge_index) and torch.equal(p.edge_attr[:E], b.edge_attr)
+    assert bool((p.batch[1:] >= p.batch[:-1]).all()) and int(p.batch[-1]) == B + 4
+    assert torch.equal(p.batch[p.edge_index[0, E:]], p.batch[p.edge_index[1, E:]])
+    assert bool((p.edge_attr[E:].sum(1) == 1).all()) and int(torch.bincount(p.batch)[B:].max()) <= 128
+    torch.manual_seed(0)
+    m = O.ArchitectureGP(9, 3, hid_dim_alpha=2, e_dim=16, out_dim=1, message_steps=2, mol_readout="Set2Set", graph_act="CELU",
+                         graph_norm="_PairNorm").eval()
+    with torch.no_grad():
+        torch.testing.assert_close(m(p)[:B], m(b), rtol=1e-6, atol=1e-7)
+    assert pad_graph_batch(b, N, E, B) is b
+    with pytest.raises(ValueError):
+        pad_graph_batch(b, N + 3000, E, B + 2)               # 3000 nodes do not fit two dummy graphs of <= 128
+    with pytest.raises(ValueError):
+        pad_graph_batch(b, N - 1, E, B)
