@@ -9,7 +9,7 @@ for virtual screening (no collective: graphs shard by molecule across ranks).
 Host batches (`glam_b200.synth.GraphBatch`, i.e. the fields of a PyG Batch) are copied into fixed device
 buffers, so a captured step has one shape (N, E, B).  `ScreenStep.step` pads smaller batches to it with dummy
 graphs behind the real ones (`synth.pad_graph_batch`) — one capture serves a loader with varying molecule sizes;
-`TrainStep` wants equal shapes (the synthetic generator emits them; a padded training batch would need a masked loss).
+`TrainStep` does the same when captured on a padded example with `masked_loss` (dummy graphs weigh zero).
 """
 from __future__ import annotations
 
@@ -38,7 +38,7 @@ def _tup(b):
     return tuple(b) if isinstance(b, (tuple, list)) else (b,)
 
 
-_GRAPH_FIELDS = ("x", "edge_index", "edge_attr", "batch", "y")
+_GRAPH_FIELDS = ("x", "edge_index", "edge_attr", "batch", "y", "mask")
 
 
 def _fields(g):
@@ -50,7 +50,7 @@ def _static_like(b, device):
     from .packed import PackedBatch
     z = lambda t: None if t is None else torch.empty_like(t, device=device)
     return tuple(g._map(z) if isinstance(g, PackedBatch) else
-                 GraphBatch(z(g.x), z(g.edge_index), z(g.edge_attr), z(g.batch), z(g.y), g.num_graphs) for g in _tup(b))
+                 GraphBatch(z(g.x), z(g.edge_index), z(g.edge_attr), z(g.batch), z(g.y), g.num_graphs, z(g.mask)) for g in _tup(b))
 
 
 def _model_args(static):
@@ -80,6 +80,17 @@ def _copy_into(dst, src) -> int:
 
 def batch_nbytes(b) -> int:
     return sum(g.nbytes() for g in _tup(b))
+
+
+def masked_loss(fn: Callable) -> Callable:
+    """`fn(out, y, reduction="none")` (e.g. torch.nn.functional.mse_loss) -> loss(out, y, mask): the mean over the REAL graphs of a
+    padded batch (mask = 1 real / 0 dummy, synth.pad_graph_batch).  With it a TrainStep captured on a padded example takes
+    batches of varying size: the dummy graphs carry zero weight, so they contribute neither loss nor gradient."""
+    def loss(out, y, mask):
+        per = fn(out, y, reduction="none")
+        per = per.reshape(per.shape[0], -1).mean(1)
+        return (per * mask).sum() / mask.sum()
+    return loss
 
 
 class FlatGrads:
@@ -283,7 +294,8 @@ class TrainStep:
         if self.overlap_allreduce:
             self.grads.stream = torch.cuda.current_stream(self.device)
         out = self.model(*static)
-        loss = self.loss_fn(out, static[0].y)
+        m = getattr(static[0], "mask", None)                    # padded batches: the loss weights the real graphs (masked_loss)
+        loss = self.loss_fn(out, static[0].y) if m is None else self.loss_fn(out, static[0].y, m)
         loss.backward()
         self.grads.collect()
         if self.world > 1:
@@ -342,8 +354,18 @@ class TrainStep:
             self._body(self.statics[self._slot])
         return self.loss
 
+    def _fit(self, batch):
+        """A TrainStep captured on a PADDED example (its static batch has a mask) takes any batch that fits: it is padded with dummy
+        graphs of zero loss weight (synth.pad_graph_batch; the loss must be a masked one, engine.masked_loss)."""
+        st = self.static[0]
+        if isinstance(batch, GraphBatch) and isinstance(st, GraphBatch) and st.mask is not None:
+            from .synth import pad_graph_batch
+            if batch.mask is None or (batch.num_nodes, batch.num_edges, batch.num_graphs) != (st.num_nodes, st.num_edges, st.num_graphs):
+                return pad_graph_batch(batch, st.num_nodes, st.num_edges, st.num_graphs, with_mask=True)
+        return batch
+
     def load(self, batch: GraphBatch) -> int:
-        return _copy_into(self.statics[self._slot], batch)
+        return _copy_into(self.statics[self._slot], self._fit(batch))
 
     def step(self, batch: GraphBatch, prefetch: Optional[GraphBatch] = None) -> torch.Tensor:
         """Public API: host (pinned) or device batch in, loss tensor (device scalar) out.  `prefetch` (double_buffer
@@ -356,7 +378,7 @@ class TrainStep:
         if self._prefetched is not None:
             main.wait_event(self._copied[slot])                   # the copy enqueued during the previous step (also when the
         if self._prefetched is not batch:                         # caller then passes a different batch: it overwrites it)
-            _copy_into(self.statics[slot], batch)
+            _copy_into(self.statics[slot], self._fit(batch))
         self._prefetched = None
         self.run_resident()
         self._consumed[slot].record(main)
@@ -364,7 +386,7 @@ class TrainStep:
             nxt = slot ^ 1
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(self._consumed[nxt])  # the last step that read those buffers is done
-                _copy_into(self.statics[nxt], prefetch)
+                _copy_into(self.statics[nxt], self._fit(prefetch))
                 self._copied[nxt].record(self._copy_stream)
             self._prefetched = prefetch
             self._slot = nxt

@@ -29,20 +29,21 @@ class GraphBatch:
     batch: torch.Tensor        # [N] int64, non-decreasing
     y: Optional[torch.Tensor] = None
     num_graphs: int = 0
+    mask: Optional[torch.Tensor] = None     # [num_graphs] fp32, 1 = real graph, 0 = padding (pad_graph_batch); None = all real
 
     def to(self, device, non_blocking: bool = False) -> "GraphBatch":
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)
         return GraphBatch(mv(self.x), mv(self.edge_index), mv(self.edge_attr), mv(self.batch), mv(self.y),
-                          self.num_graphs)
+                          self.num_graphs, mv(self.mask))
 
     def pin_memory(self) -> "GraphBatch":
         pm = lambda t: None if t is None else t.pin_memory()
         return GraphBatch(pm(self.x), pm(self.edge_index), pm(self.edge_attr), pm(self.batch), pm(self.y),
-                          self.num_graphs)
+                          self.num_graphs, pm(self.mask))
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in
-                   (self.x, self.edge_index, self.edge_attr, self.batch, self.y) if t is not None)
+                   (self.x, self.edge_index, self.edge_attr, self.batch, self.y, self.mask) if t is not None)
 
     @property
     def num_nodes(self) -> int:
@@ -238,17 +239,22 @@ def shard_by_graph(batch: GraphBatch, rank: int, world: int) -> GraphBatch:
                       batch.batch[n0:n1] - lo, None if batch.y is None else batch.y[lo:hi], hi - lo)
 
 
-def pad_graph_batch(b: GraphBatch, nodes: int, edges: int, graphs: int, max_nodes: int = 128, max_edges: int = 768) -> GraphBatch:
+def pad_graph_batch(b: GraphBatch, nodes: int, edges: int, graphs: int, max_nodes: int = 128, max_edges: int = 768,
+                    with_mask: bool = False) -> GraphBatch:
     """`b` padded to exactly (`nodes`, `edges`, `graphs`) with dummy graphs appended BEHIND the real ones, so that batches of
     varying size can be replayed through ONE captured step (engine.ScreenStep pads with this): the padding nodes / edges are
     spread evenly over the `graphs - b.num_graphs` dummy graphs (zero features, bond type 0, ring edges i -> i+1; each at most
     `max_nodes` nodes / `max_edges` edges — the fused kernels' per-graph caps).  The scores of the real graphs are unchanged
-    (graphs are independent); rows `b.num_graphs:` of the output belong to the dummies."""
+    (graphs are independent); rows `b.num_graphs:` of the output belong to the dummies.  `mask` [graphs] marks the real graphs
+    (always attached when padding happens; `with_mask` attaches an all-ones mask to a batch that already fits) — what a masked
+    training loss weights by (engine.masked_loss)."""
     N, E, B = b.num_nodes, b.num_edges, b.num_graphs
     pn, pe, d = nodes - N, edges - E, graphs - B
     if min(pn, pe, d) < 0:
         raise ValueError(f"batch ({N} nodes, {E} edges, {B} graphs) exceeds the captured capacity ({nodes}, {edges}, {graphs})")
     if pn == 0 and pe == 0 and d == 0:
+        if with_mask and b.mask is None:
+            return GraphBatch(b.x, b.edge_index, b.edge_attr, b.batch, b.y, B, torch.ones(B, dtype=torch.float32, device=b.x.device))
         return b
     if d == 0 or pn < d or pn > max_nodes * d or pe > max_edges * d:
         raise ValueError(f"cannot pad ({N}, {E}, {B}) to ({nodes}, {edges}, {graphs}): {pn} nodes / {pe} edges do not fit {d} dummy graphs "
@@ -268,4 +274,5 @@ def pad_graph_batch(b: GraphBatch, nodes: int, edges: int, graphs: int, max_node
     return GraphBatch(torch.cat([b.x, torch.zeros((pn, b.x.shape[1]), dtype=b.x.dtype, device=dev)]),
                       torch.cat([b.edge_index, torch.stack([src, dst]).to(dev)], dim=1),
                       torch.cat([b.edge_attr, ea.to(dev)]),
-                      torch.cat([b.batch, (B + torch.repeat_interleave(k, n_g)).to(dev)]), y, graphs)
+                      torch.cat([b.batch, (B + torch.repeat_interleave(k, n_g)).to(dev)]), y, graphs,
+                      torch.cat([torch.ones(B), torch.zeros(d)]).to(dev))

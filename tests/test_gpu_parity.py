@@ -904,3 +904,38 @@ def test_dti_screening_with_distinct_proteins_once(keys, math_mode):
     with pytest.raises(Exception):                       # forward-only: gradients through a shared protein are not defined here
         m.train()
         m(lig.to(DEV), uniq.to(DEV), pro_index=index.to(DEV)).sum().backward()
+
+
+def test_captured_train_steps_on_batches_of_varying_size():
+    """A TrainStep captured on a PADDED example (synth.pad_graph_batch + engine.masked_loss) trains on batches of different sizes
+    through one CUDA graph: losses and parameters follow the oracle trained with torch.optim.Adam on the UNPADDED batches (the
+    dummy graphs carry zero loss weight, hence no gradient)."""
+    from glam_b200._lib import set_math_mode, get_math_mode
+    from glam_b200.engine import TrainStep, masked_loss
+    from glam_b200.synth import make_molecule_batch, pad_graph_batch
+    prev = get_math_mode()
+    set_math_mode("fp32")
+    try:
+        m, o32 = _gp_pair(9, 3, "Set2Set", "_TripletMessage")
+        batches = [make_molecule_batch(n, seed=800 + i) for i, n in enumerate((48, 41, 48, 17))]
+        opt = torch.optim.Adam(o32.parameters(), lr=1e-3)
+        ref_losses = []
+        for b in batches:
+            opt.zero_grad()
+            loss = torch.nn.functional.mse_loss(o32(ns(b.x, b.edge_index, b.edge_attr, b.batch)), b.y)
+            loss.backward()
+            opt.step()
+            ref_losses.append(loss.item())
+        cap = (max(b.num_nodes for b in batches) + 40, max(b.num_edges for b in batches) + 40, 48 + 6)
+        example = pad_graph_batch(batches[0], *cap, with_mask=True)
+        assert example.mask is not None and int(example.mask.sum()) == 48
+        ts = TrainStep(m, masked_loss(torch.nn.functional.mse_loss), example, lr=1e-3, device=DEV, use_cuda_graph=True, warmup=2,
+                       double_buffer=True)
+        pinned = [b.pin_memory() for b in batches]
+        losses = [ts.step(b, prefetch=pinned[i + 1] if i + 1 < len(pinned) else None).item() for i, b in enumerate(pinned)]
+        for a, r in zip(losses, ref_losses):
+            assert abs(a - r) <= 2e-4 * max(1.0, abs(r)), (losses, ref_losses)
+        for (n, p), q in zip(m.named_parameters(), o32.parameters()):
+            torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=2e-3, atol=2e-4, msg=lambda s, n=n: f"{n}: {s}")
+    finally:
+        set_math_mode(prev)
