@@ -290,6 +290,7 @@ mp_fused_bwd_kernel(const BwParams p) {
             };
             GateIn nxt = gate_load(0);
             if (!first) { mbar_wait_guarded(mma_bar, ph); ph ^= 1u; tc_fence_after_sync(); }        // the previous step's g_x MMA
+            BW_TICK(10)
 #pragma unroll
             for (int jj = 0; jj < G::JPW; ++jj) {
                 const int j = cg + WQ * jj;
@@ -329,6 +330,7 @@ mp_fused_bwd_kernel(const BwParams p) {
                 for (int q = 3 * CQ; q < G::KI; ++q) sts128(GP + (q >> 3) * kMpPanel + pan_off(row, q), z0);
                 for (int q = G::NR0 + CQ; q < G::GCH; ++q) sts128(GP + (q >> 3) * kMpPanel + pan_off(row, q), z0);
             }
+            BW_TICK(11)
             tmem_st_wait();
             tc_fence_before_sync();
             fence_proxy_async_smem();

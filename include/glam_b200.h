@@ -329,7 +329,8 @@ int glam_message_stack_supported(int channels, int heads, int edge_dim);
  * cycles[cta][phase] — forward: 0 tile load, 1 logits, 2 softmax, 3 projection wait, 4 TMEM -> xp tile, 5 aggregation, 6 agg
  * panels, 7 scale wait, 8 CELU epilogue, 9 GRU wait, 10 gates, 11 step outputs, 12 tile end, 13 MMA issue, 14 set-up;
  * backward: 16 index words, 17 gate backward, 18 G copy-out + GRU MMAs, 19 CELU' epilogue, 20 G_PRE copy-out + scale MMA,
- * 21 TMEM -> g_agg tile, 22 destination pass, 23 source pass, 24 G_XPE copy-out, 25 tile output.  Results are unaffected.
+ * 21 TMEM -> g_agg tile, 22 destination pass, 23 source pass, 24 G_XPE copy-out, 25 tile output; 17 is split further: 26 wait
+ * for the previous step's g_x MMA + first loads, 27 the gate rounds (17 = the barrier behind them).  Results are unaffected.
  * NULL switches it off. */
 int glam_message_stack_phase_clock(unsigned long long* cycles);
 int glam_message_stack_fwd(const float* x0, const float* h0, const float* x_raw, int raw_dim, const float* w_pre,

@@ -136,4 +136,6 @@ if "phases" in sys.argv:
     lib.glam_message_stack_phase_clock(None)
     c = clk.double().mean(0).cpu()[16:]
     tot = float(c[:10].sum())
-    print(f"backward: {tot/1.965e3:.1f} us of SM cycles per CTA; " + ", ".join(f"{n} {100*float(c[i])/tot:.1f}%" for i, n in enumerate(names)))
+    tot += float(c[10] + c[11])
+    print(f"backward: {tot/1.965e3:.1f} us of SM cycles per CTA; " + ", ".join(f"{n} {100*float(c[i])/tot:.1f}%" for i, n in enumerate(names))
+          + f"; [gate bwd split: wait for g_x MMA + first loads {100*float(c[10])/tot:.1f}%, rounds (thread 0) {100*float(c[11])/tot:.1f}%, rest = barrier]")
