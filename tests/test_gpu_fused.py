@@ -667,3 +667,73 @@ def test_screen_step_replays_one_captured_step_on_batches_of_varying_size():
             want = net(b.to(DEV))
         assert got.shape == want.shape == (b.num_graphs, 1)
         assert torch.isfinite(got).all() and torch.equal(got, want), f"batch {i}: max diff {(got - want).abs().max().item():.3e}"
+
+
+def _dense_small_graphs(n_graphs, De, seed):
+    """Random directed graphs of 3..40 nodes with in-degrees 0..9 (duplicate edges and isolated nodes included): beyond the
+    valence-bounded routines of the fused kernels (in-/out-degree <= 4), so the general per-row loops run."""
+    from glam_b200.synth import GraphBatch
+    g = torch.Generator().manual_seed(seed)
+    xs, srcs, dsts, bs, off = [], [], [], [], 0
+    for k in range(n_graphs):
+        n = int(torch.randint(3, 41, (1,), generator=g))
+        deg = torch.randint(0, 10, (n,), generator=g)
+        deg[torch.randint(0, n, (1,), generator=g)] = 0                      # at least one node without in-edges
+        dst = torch.repeat_interleave(torch.arange(n), deg)
+        src = torch.randint(0, n, (int(deg.sum()),), generator=g)
+        srcs.append(src + off); dsts.append(dst + off); bs.append(torch.full((n,), k)); off += n
+    ei = torch.stack([torch.cat(srcs), torch.cat(dsts)])
+    E = ei.shape[1]
+    ea = torch.nn.functional.one_hot(torch.randint(0, De, (E,), generator=g), De).float()
+    return GraphBatch(torch.zeros(off, 1), ei, ea, torch.cat(bs), None, n_graphs)
+
+
+@pytest.mark.parametrize("C,De,n_graphs", [(36, 3, 120), (32, 4, 37)])
+def test_fused_kernels_on_graphs_beyond_the_valence_bound(C, De, n_graphs):
+    """In-/out-degrees up to 9, duplicate edges, isolated nodes: forward (evaluation and training saves) and the one-launch
+    backward against the per-op kernels."""
+    from glam_b200 import _lib, layer, functional as Fn
+    _lib.set_math_mode("tf32")
+    blk = _block(C, De, "CELU", True, 3)
+    b = _dense_small_graphs(n_graphs, De, 23).to(DEV)
+    gen = torch.Generator().manual_seed(6)
+    x0 = torch.randn(b.num_nodes, C, generator=gen).to(DEV)
+    cot = [torch.randn(b.num_nodes, C, generator=gen).to(DEV) for _ in range(4)]
+    deg_in = torch.bincount(b.edge_index[1], minlength=b.num_nodes)
+    deg_out = torch.bincount(b.edge_index[0], minlength=b.num_nodes)
+    assert int(deg_in.max()) > 4 and int(deg_out.max()) > 4 and int((deg_in == 0).sum()) > 0
+    blk.eval()
+    with torch.no_grad():
+        layer.USE_FUSED_STACK = False
+        try:
+            xs_ref, h_ref = blk.run_steps(x0, b.edge_index, b.edge_attr, 3, batch=b.batch, num_graphs=b.num_graphs)
+        finally:
+            layer.USE_FUSED_STACK = True
+        n0 = _lib.launch_count()
+        xs, h = blk.run_steps(x0, b.edge_index, b.edge_attr, 3, batch=b.batch, num_graphs=b.num_graphs)
+        assert _lib.launch_count() - n0 <= 8, "fused path not taken"
+    for s in range(3):
+        assert _rel(xs[s], xs_ref[s]) < 2e-4, (s, _rel(xs[s], xs_ref[s]))
+    assert _rel(h, h_ref) < 2e-4
+    blk.train()
+
+    def run(fused_fwd, fused_bwd):
+        layer.USE_FUSED_STACK, Fn.USE_FUSED_BWD = fused_fwd, fused_bwd
+        try:
+            for p in blk.parameters():
+                p.grad = None
+            xin = x0.clone().requires_grad_(True)
+            xs, hh = blk.run_steps(xin, b.edge_index, b.edge_attr, 3, batch=b.batch, num_graphs=b.num_graphs)
+            (sum((xo * c).sum() for xo, c in zip(xs, cot)) + (hh[0] * cot[3]).sum()).backward()
+            torch.cuda.synchronize()
+            return xin.grad, {n: p.grad.clone() for n, p in blk.named_parameters()}
+        finally:
+            layer.USE_FUSED_STACK, Fn.USE_FUSED_BWD = True, True
+
+    gx_f, gp_f = run(True, True)
+    gx_u, gp_u = run(False, False)
+    assert torch.isfinite(gx_f).all() and _rel(gx_f, gx_u) < 1e-3, _rel(gx_f, gx_u)
+    for n in gp_u:
+        e = _rel(gp_f[n], gp_u[n])
+        print(f"grad {n}: rel err {e:.2e}")
+        assert e < 2e-3, f"grad {n}: {e}"
