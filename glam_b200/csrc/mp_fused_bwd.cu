@@ -99,6 +99,7 @@ struct BwParams {
     int De, steps, act, res;
     float slope, act_param;
     float* G_GI; float* G_GH; float* G_PRE; float* G_XPE; float* g_x0;
+    float* g_h0;                                      // separate gradient of the initial GRU state (h0 was its own tensor), or NULL
     float* partial;                                   // [grid][De*HC + De*H]
     unsigned long long* phase_clock;                  // profiling aid (glam_message_stack_phase_clock), or NULL
 };
@@ -645,9 +646,14 @@ mp_fused_bwd_kernel(const BwParams p) {
         for (int jj = 0; jj < G::JPW; ++jj) {
             const int j = cg + WQ * jj;
             if (j < CQ) {
-                float4 g = add4(tmem_ld4v(lane_base + G::TM_X + 4 * j), add4(tmem_ld4v(lane_base + G::TM_H + 4 * j), tmem_ld4v(lane_base + G::TM_GHZ + 4 * j)));
+                float4 g = tmem_ld4v(lane_base + G::TM_X + 4 * j);
+                const float4 gh = add4(tmem_ld4v(lane_base + G::TM_H + 4 * j), tmem_ld4v(lane_base + G::TM_GHZ + 4 * j));
                 if (p.res) g = add4(g, tmem_ld4v(lane_base + G::TM_GID + 4 * j));
-                if (row < nd) *reinterpret_cast<float4*>(p.g_x0 + (size_t)(n0 + row) * C + 4 * j) = g;
+                if (!p.g_h0) g = add4(g, gh);                // h0 == x0 (layer.py:253-254): one tensor, one gradient
+                if (row < nd) {
+                    *reinterpret_cast<float4*>(p.g_x0 + (size_t)(n0 + row) * C + 4 * j) = g;
+                    if (p.g_h0) *reinterpret_cast<float4*>(p.g_h0 + (size_t)(n0 + row) * C + 4 * j) = gh;
+                }
             }
         }
         tc_fence_before_sync();
@@ -722,7 +728,7 @@ extern "C" int glam_message_stack_bwd(const float* save_x, const float* save_h, 
                                       const int32_t* dst_src, const uint8_t* etype, const int32_t* src_rowptr, const int32_t* src_pos,
                                       const int32_t* src_dst, int64_t num_nodes, int64_t num_edges, int channels, int heads,
                                       int edge_dim, int steps, float negative_slope, int act, float act_param, int res, float* g_gi,
-                                      float* g_gh, float* g_pre, float* g_xpe, float* g_x0, float* g_w_edge, float* g_att_edge,
+                                      float* g_gh, float* g_pre, float* g_xpe, float* g_x0, float* g_h0, float* g_w_edge, float* g_att_edge,
                                       void* workspace, size_t workspace_bytes, void* stream_) {
     GLAM_REQUIRE(glam_message_stack_bwd_supported(channels, heads, edge_dim, steps),
                  "glam_message_stack_bwd: unsupported (channels=%d heads=%d edge_dim=%d steps=%d math mode %d); use the per-op calls",
@@ -744,7 +750,7 @@ extern "C" int glam_message_stack_bwd(const float* save_x, const float* save_h, 
     GLAM_REQUIRE(workspace_bytes >= glam_message_stack_bwd_workspace_bytes(channels, heads, edge_dim) && al16b(workspace),
                  "glam_message_stack_bwd: workspace too small or not 16-byte aligned");
     GLAM_REQUIRE(al16b(save_x) && al16b(save_h) && al16b(save_xpe) && al16b(save_m) && al16b(save_rzn) && al16b(save_gh) && al16b(save_gt) && al16b(w_ext) &&
-                 al16b(w_scale) && al16b(g_gi) && al16b(g_gh) && al16b(g_pre) && al16b(g_xpe) && al16b(g_x0) && al16b(g_h_final) && al16b(tiles),
+                 al16b(w_scale) && al16b(g_gi) && al16b(g_gh) && al16b(g_pre) && al16b(g_xpe) && al16b(g_x0) && al16b(g_h0) && al16b(g_h_final) && al16b(tiles),
                  "glam_message_stack_bwd: pointers must be 16-byte aligned");
     GLAM_REQUIRE(num_nodes < ((int64_t)1 << 31) && num_edges < ((int64_t)1 << 31), "glam_message_stack_bwd: too large");
     BwParams p;
@@ -761,7 +767,7 @@ extern "C" int glam_message_stack_bwd(const float* save_x, const float* save_h, 
     p.tiles = reinterpret_cast<const int4*>(tiles); p.meta = tile_meta; p.rowptr = dst_rowptr; p.src = dst_src; p.etype = etype;
     p.src_rowptr = src_rowptr; p.src_pos = src_pos; p.src_dst = src_dst; p.N = num_nodes; p.E = num_edges; p.De = edge_dim;
     p.steps = steps; p.act = act; p.res = res; p.slope = negative_slope; p.act_param = act_param;
-    p.G_GI = g_gi; p.G_GH = g_gh; p.G_PRE = g_pre; p.G_XPE = g_xpe; p.g_x0 = g_x0; p.phase_clock = g_mp_phase_clock;
+    p.G_GI = g_gi; p.G_GH = g_gh; p.G_PRE = g_pre; p.G_XPE = g_xpe; p.g_x0 = g_x0; p.g_h0 = g_h0; p.phase_clock = g_mp_phase_clock;
     int rc = 0;
     switch (channels) {
         case 32: rc = bwd_launch<8, 3>(p, w_ih, w_hh, image, stream); break;

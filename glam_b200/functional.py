@@ -200,13 +200,18 @@ class MessageBlockFn(Function):
         (x, identity, h, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh) = map(
             _c, (x, identity, h, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh))
         ops._need_cuda(x, h)
+        ctx.fused = None
         if fi is not None and (identity is None or identity is x):
-            # one launch for the whole block (csrc/mp_fused.cu); the tensors backward reads come out as side outputs
-            sv = _stack_buffers(x, 1, heads, channels, w_ext.shape[1], ea.shape[0])
+            # one launch for the whole block (csrc/mp_fused.cu); the tensors backward reads come out as side outputs — for the
+            # one-launch backward (csrc/mp_fused_bwd.cu, steps = 1, its own h0) with the gate side in the tile-blocked layout
+            fused_bwd = (USE_FUSED_BWD and g.src_rowptr is not None and ops.message_stack_bwd_supported(channels, heads, ea.shape[1], 1))
+            sv = _stack_buffers(x, 1, heads, channels, w_ext.shape[1], ea.shape[0], tiled_gates=fused_bwd)
             ops.message_stack_fwd(x, h, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, g, fi, heads, channels, 1,
                                   slope, act, act_param, identity is not None, save=sv)
-            xpe, agg, alpha, m, rzn, gh, x_out, h_new = (sv["XPE"][0], sv["AGG"][0], sv["ALPHA"][0], sv["M"][0], sv["RZN"][0],
-                                                         sv["GH"][0], sv["X"][1], sv["HH"][1])
+            xpe, agg, alpha, m, x_out, h_new = sv["XPE"][0], sv["AGG"][0], sv["ALPHA"][0], sv["M"][0], sv["X"][1], sv["HH"][1]
+            rzn, gh = (None, None) if fused_bwd else (sv["RZN"][0], sv["GH"][0])
+            if fused_bwd:
+                ctx.fused = (sv, fi)
         else:
             xpe, agg, alpha, m = _conv_fwd(x, w_ext, w_edge, att_edge, w_scale, bias, ea, g, heads, channels, slope, EPI_CELU)
             rzn, gh, h_new, x_out = _gru_fwd(m, h, identity, w_ih, w_hh, b_ih, b_hh, act, act_param)
@@ -219,6 +224,22 @@ class MessageBlockFn(Function):
     def backward(ctx, g_x_out, g_h_new):
         (x, h, w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, xpe, agg, alpha, m, rzn, gh, x_out, ea) = ctx.saved_tensors
         heads, channels, slope, act, act_param, has_id = ctx.cfg
+        if ctx.fused is not None:
+            # the whole reverse chain of the block in one launch; the residual's gradient is part of g_x (identity IS x)
+            sv, fi = ctx.fused
+            N, C, HC, ld = x.shape[0], channels, heads * channels, xpe.shape[1]
+            new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=x.device)
+            G_GI, G_GH, G_PRE, G_XPE = new(1, N, 3 * C), new(1, N, 3 * C), new(1, N, C), new(1, N, ld)
+            (g_x, g_h), g_w_edge, g_att_edge = ops.message_stack_bwd(
+                sv, [_c(g_x_out)], _c(g_h_new), w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ctx.g, fi, heads, C, 1, slope, act,
+                act_param, has_id, G_GI, G_GH, G_PRE, G_XPE, separate_h0=True)
+            g_w_ih, g_b_ih = ops.gemm_tn_ex(m, G_GI[0], transpose_out=True, want_colsum=True)
+            g_w_hh, g_b_hh = ops.gemm_tn_ex(h, G_GH[0], transpose_out=True, want_colsum=True)
+            g_w_scale, g_bias = ops.gemm_tn_ex(agg, G_PRE[0], want_colsum=True)
+            g_w_ext, _ = ops.gemm_tn_ex(x, G_XPE[0])
+            ops.gemm_tn_ex(x, G_XPE[0][:, HC:HC + 2 * heads], out=g_w_ext[:, HC:HC + 2 * heads])      # logit columns: exact fp32
+            return (g_x, None, g_h, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias, g_w_ih, g_w_hh, g_b_ih, g_b_hh,
+                    None, None, None, None, None, None, None, None)
         g_pre, g_h, g_id, g_w_ih, g_w_hh, g_b_ih, g_b_hh = _gru_bwd(
             _c(g_x_out), _c(g_h_new), rzn, gh, h, m, x_out, w_ih, w_hh, act, act_param, has_id, m)
         g_x, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias = _conv_bwd(

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLAM_B200_ABI_VERSION 8
+#define GLAM_B200_ABI_VERSION 9
 #define GLAM_MAX_HEADS 4
 
 int glam_abi_version(void);
@@ -352,7 +352,8 @@ int glam_message_stack_fwd(const float* x0, const float* h0, const float* x_raw,
  *   `steps` device pointers (NULL entries allowed): the gradient arriving at every step's output x_{s+1} [N][C] from outside;
  *   g_h_final [N][C] (may be NULL) the gradient of the final GRU state.  Writes what the weight-gradient contractions read
  *   — g_gi, g_gh [steps][N][3C], g_pre [steps][N][C], g_xpe [steps][N][ld] — plus g_x0 [N][C] (gradient of x0, both as the
- *   first block input and the first GRU state) and the parameter gradients of the edge phase summed over steps: g_w_edge
+ *   first block input and the first GRU state; when the forward was given its own h0 tensor pass g_h0 [N][C] != NULL and the two
+ *   gradients come out apart) and the parameter gradients of the edge phase summed over steps: g_w_edge
  *   [edge_dim][HC], g_att_edge [edge_dim][H] (= d/d att_edge of glam_triplet_prep_fwd).  needs the source-side index of
  *   glam_build_csr.  workspace >= glam_message_stack_bwd_workspace_bytes(), 16-byte aligned.  If meta[1] != 0, g_x0 and the
  *   parameter gradients are filled with NaN.  Supported: tf32 math mode, heads == 3, channels in {32,36}, edge_dim <= 4,
@@ -368,7 +369,7 @@ int glam_message_stack_bwd(const float* save_x, const float* save_h, const float
                            const int32_t* src_rowptr, const int32_t* src_pos, const int32_t* src_dst, int64_t num_nodes,
                            int64_t num_edges, int channels, int heads, int edge_dim, int steps, float negative_slope, int act,
                            float act_param, int res, float* g_gi, float* g_gh, float* g_pre, float* g_xpe, float* g_x0,
-                           float* g_w_edge, float* g_att_edge, void* workspace, size_t workspace_bytes, void* stream);
+                           float* g_h0, float* g_w_edge, float* g_att_edge, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (9) Packed graph store -> device index (csrc/packed.cu).  The reference ships every batch as fp32

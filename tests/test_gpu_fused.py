@@ -737,3 +737,42 @@ def test_fused_kernels_on_graphs_beyond_the_valence_bound(C, De, n_graphs):
         e = _rel(gp_f[n], gp_u[n])
         print(f"grad {n}: rel err {e:.2e}")
         assert e < 2e-3, f"grad {n}: {e}"
+
+
+@pytest.mark.parametrize("C,De,act,res", [(36, 3, "CELU", True), (32, 4, "ReLU", False)])
+def test_single_block_one_launch_backward_in_the_reference_loop(C, De, act, res):
+    """The reference's own loop (model.py steps MessageBlock.forward with the carried h, src_1gp/model.py:53-54): every block
+    application is one forward launch and ONE backward launch (steps = 1, h0 its own tensor, g_x and g_h apart) — against the
+    per-op backward kernels on the same loop."""
+    from glam_b200 import _lib, functional as Fn
+    _lib.set_math_mode("tf32")
+    blk = _block(C, De, act, res, 12).train()
+    b = _batch(150, C, De, 19).to(DEV)
+    gen = torch.Generator().manual_seed(2)
+    x0 = torch.randn(b.num_nodes, C, generator=gen).to(DEV)
+    cot = [torch.randn(b.num_nodes, C, generator=gen).to(DEV) for _ in range(2)]
+
+    def run(fused_bwd):
+        Fn.USE_FUSED_BWD = fused_bwd
+        try:
+            for p in blk.parameters():
+                p.grad = None
+            xin = x0.clone().requires_grad_(True)
+            n0 = _lib.launch_count()
+            xi, hi = xin, None
+            for _ in range(3):
+                xi, hi = blk(xi, b.edge_index, b.edge_attr, h=hi, batch=b.batch, num_graphs=b.num_graphs)
+            ((xi * cot[0]).sum() + (hi[0] * cot[1]).sum()).backward()
+            torch.cuda.synchronize()
+            return xi.detach(), xin.grad, {n: p.grad.clone() for n, p in blk.named_parameters()}, _lib.launch_count() - n0
+        finally:
+            Fn.USE_FUSED_BWD = True
+
+    y_f, gx_f, gp_f, n_f = run(True)
+    y_u, gx_u, gp_u, n_u = run(False)
+    assert n_f < n_u, (n_f, n_u)
+    assert _rel(y_f, y_u) < 2e-4 and torch.isfinite(gx_f).all() and _rel(gx_f, gx_u) < 1e-3, (_rel(y_f, y_u), _rel(gx_f, gx_u))
+    for n in gp_u:
+        e = _rel(gp_f[n], gp_u[n])
+        print(f"grad {n}: rel err {e:.2e}")
+        assert e < 2e-3, f"grad {n}: {e}"
