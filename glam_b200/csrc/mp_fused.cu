@@ -178,6 +178,7 @@ struct MpParams {
     float* x_out; float* h_out;
     float* sX; float* sHH; float* sXPE; float* sAGG; float* sALPHA; float* sM; float* sRZN; float* sGH;
     float* sGT;                              // tile-blocked gate save for the one-launch backward (replaces sRZN / sGH), or NULL
+    float* sMH;                              // [steps][N][2C+4] = m | h_in | 1 0 0 0 (replaces sM): ONE operand for both GRU weight gradients
     const int64_t* pn_batch; float pn_eps;   // PairNorm on every step's block input (evaluation): graph id per node, or NULL
     unsigned long long* phase_clock;         // profiling aid (glam_message_stack_phase_clock): [grid][16] cycles per phase, or NULL
 };
@@ -753,7 +754,21 @@ mp_fused_kernel(const MpParams p) {
                 }
                 mma_commit(mma_bar);
             }
-            if (SAVE) copy_out_panels<CQ, NT>(REG, AT, 2, p.sM + ((size_t)s * p.N + n0) * C, nd);
+            if (SAVE && p.sMH) {
+                // m | h_in | 1: the row operand of the merged GRU weight-gradient contraction [m h 1]^T [g_r g_z g_n g_n r] (the
+                // constant column yields both bias gradients as a row of the product)
+                float4* mh = reinterpret_cast<float4*>(p.sMH + ((size_t)s * p.N + n0) * (2 * C + 4));
+                const uint8_t* hp = h_is_x ? XM : HM;
+                const int hslot = h_is_x ? 0 : 1;
+                for (int i = tid; i < nd * (2 * CQ + 1); i += NT) {
+                    const int r = i / (2 * CQ + 1), q = i - r * (2 * CQ + 1);
+                    float4 v = make_float4(1.f, 0.f, 0.f, 0.f);
+                    if (q < CQ) v = q < 8 ? lds128(REG + pan_off(r, q)) : lds128(AT + pan_off(r, 4 + q - 8));
+                    else if (q < 2 * CQ) { const int qh = q - CQ; v = qh < 8 ? lds128(hp + pan_off(r, qh)) : lds128(AT + pan_off(r, 2 * hslot + qh - 8)); }
+                    mh[i] = v;
+                }
+            }
+            if (SAVE && p.sM) copy_out_panels<CQ, NT>(REG, AT, 2, p.sM + ((size_t)s * p.N + n0) * C, nd);
             mbar_wait_guarded(mma_bar, ph); ph ^= 1u;
             MP_TICK(9)
             tc_fence_after_sync();
@@ -948,7 +963,7 @@ extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const fl
                                       int edge_dim, int steps, float negative_slope, int act, float act_param, int res,
                                       int conv_only, int keep_all, float* x_out, float* h_out, float* save_x, float* save_h,
                                       float* save_xpe, float* save_agg, float* save_alpha, float* save_m, float* save_rzn,
-                                      float* save_gh, float* save_gt, const int64_t* pn_batch, float pn_eps, void* stream_) {
+                                      float* save_gh, float* save_gt, float* save_mh, const int64_t* pn_batch, float pn_eps, void* stream_) {
     GLAM_REQUIRE(glam_message_stack_supported(channels, heads, edge_dim),
                  "glam_message_stack_fwd: unsupported (channels=%d heads=%d edge_dim=%d math mode %d); use the per-op calls", channels,
                  heads, edge_dim, g_math_mode_get());
@@ -960,13 +975,13 @@ extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const fl
                  "glam_message_stack_fwd: null pointer");
     GLAM_REQUIRE(!x_raw || (w_pre && raw_dim >= 1 && raw_dim <= kMpMaxRaw), "glam_message_stack_fwd: input LinearBlock needs weights and raw_dim <= %d", kMpMaxRaw);
     GLAM_REQUIRE(conv_only ? steps == 1 : (w_ih && w_hh && b_ih && b_hh), "glam_message_stack_fwd: GRU weights missing / conv-only takes one step");
-    GLAM_REQUIRE(save ? (save_agg && save_alpha && (conv_only ? x_out != nullptr : (save_x && save_h && save_m && (save_gt || (save_rzn && save_gh)))))
+    GLAM_REQUIRE(save ? (save_agg && save_alpha && (conv_only ? x_out != nullptr : (save_x && save_h && (save_m || save_mh) && (save_gt || (save_rzn && save_gh)))))
                       : (x_out != nullptr),
                  "glam_message_stack_fwd: output pointers missing");
     const int HC = heads * channels, ld = (HC + 2 * heads + 3) / 4 * 4;
     GLAM_REQUIRE(ldw == ld, "glam_message_stack_fwd: w_ext pitch %lld, expected %d", (long long)ldw, ld);
     GLAM_REQUIRE(al16(x0) && al16(h0) && al16(w_ih) && al16(w_hh) && al16(x_out) && al16(h_out) && al16(save_x) && al16(save_h) &&
-                 al16(save_xpe) && al16(save_agg) && al16(save_m) && al16(save_rzn) && al16(save_gh) && al16(save_gt) && al16(tiles),
+                 al16(save_xpe) && al16(save_agg) && al16(save_m) && al16(save_rzn) && al16(save_gh) && al16(save_gt) && al16(save_mh) && al16(tiles),
                  "glam_message_stack_fwd: pointers must be 16-byte aligned");
     GLAM_REQUIRE(num_nodes < ((int64_t)1 << 31) && num_edges < ((int64_t)1 << 31), "glam_message_stack_fwd: too large");
     MpParams p;
@@ -976,7 +991,7 @@ extern "C" int glam_message_stack_fwd(const float* x0, const float* h0, const fl
     p.rowptr = dst_rowptr; p.src = dst_src; p.etype = etype; p.N = num_nodes; p.E = num_edges; p.De = edge_dim; p.steps = steps;
     p.act = act; p.res = res; p.conv_only = conv_only; p.keep_all = keep_all; p.slope = negative_slope; p.act_param = act_param;
     p.x_out = x_out; p.h_out = h_out; p.sX = save_x; p.sHH = save_h; p.sXPE = save_xpe; p.sAGG = save_agg; p.sALPHA = save_alpha;
-    p.sM = save_m; p.sRZN = save_rzn; p.sGH = save_gh; p.sGT = save_gt; p.pn_batch = pn_batch; p.pn_eps = pn_eps; p.phase_clock = g_mp_phase_clock;
+    p.sM = save_m; p.sRZN = save_rzn; p.sGH = save_gh; p.sGT = save_gt; p.sMH = save_mh; p.pn_batch = pn_batch; p.pn_eps = pn_eps; p.phase_clock = g_mp_phase_clock;
     int rc = 0;
     cudaStream_t stream = (cudaStream_t)stream_;
     switch (channels) {

@@ -99,6 +99,7 @@ struct BwParams {
     int De, steps, act, res;
     float slope, act_param;
     float* G_GI; float* G_GH; float* G_PRE; float* G_XPE; float* g_x0;
+    float* G4;                                        // [steps][N][4C] = g_r | g_z | g_n | g_n r (replaces G_GI / G_GH), or NULL
     float* g_h0;                                      // separate gradient of the initial GRU state (h0 was its own tensor), or NULL
     float* partial;                                   // [grid][De*HC + De*H]
     unsigned long long* phase_clock;                  // profiling aid (glam_message_stack_phase_clock), or NULL
@@ -354,7 +355,13 @@ mp_fused_bwd_kernel(const BwParams p) {
                 mma_commit(mma_bar);
             }
             bw_ph ^= 1u;
-            {
+            if (p.G4) {                                     // one [4C] row per node: both GRU weight gradients read it
+                float4* g4 = reinterpret_cast<float4*>(p.G4 + ((size_t)s * p.N + n0) * 4 * C);
+                for (int i = tid; i < nd * 4 * CQ; i += NT) {
+                    const int r = i / (4 * CQ), q = i - r * (4 * CQ), qi = q < 3 * CQ ? q : G::NR0 + q - 3 * CQ;
+                    g4[i] = lds128(GP + (qi >> 3) * kMpPanel + pan_off(r, qi));
+                }
+            } else {
                 float4* gi = reinterpret_cast<float4*>(p.G_GI + ((size_t)s * p.N + n0) * 3 * C);
                 float4* gh = reinterpret_cast<float4*>(p.G_GH + ((size_t)s * p.N + n0) * 3 * C);
                 for (int i = tid; i < nd * 3 * CQ; i += NT) {
@@ -728,7 +735,7 @@ extern "C" int glam_message_stack_bwd(const float* save_x, const float* save_h, 
                                       const int32_t* dst_src, const uint8_t* etype, const int32_t* src_rowptr, const int32_t* src_pos,
                                       const int32_t* src_dst, int64_t num_nodes, int64_t num_edges, int channels, int heads,
                                       int edge_dim, int steps, float negative_slope, int act, float act_param, int res, float* g_gi,
-                                      float* g_gh, float* g_pre, float* g_xpe, float* g_x0, float* g_h0, float* g_w_edge, float* g_att_edge,
+                                      float* g_gh, float* g4, float* g_pre, float* g_xpe, float* g_x0, float* g_h0, float* g_w_edge, float* g_att_edge,
                                       void* workspace, size_t workspace_bytes, void* stream_) {
     GLAM_REQUIRE(glam_message_stack_bwd_supported(channels, heads, edge_dim, steps),
                  "glam_message_stack_bwd: unsupported (channels=%d heads=%d edge_dim=%d steps=%d math mode %d); use the per-op calls",
@@ -743,14 +750,14 @@ extern "C" int glam_message_stack_bwd(const float* save_x, const float* save_h, 
         return 0;
     }
     GLAM_REQUIRE(save_xpe && (save_gt || (save_x && save_h && save_m && save_rzn && save_gh)) && w_ext && w_edge && att_edge && w_scale && w_ih && w_hh &&
-                 tiles && tile_meta && dst_rowptr && src_rowptr && g_gi && g_gh && g_pre && g_xpe && g_x0 && workspace &&
+                 tiles && tile_meta && dst_rowptr && src_rowptr && (g4 || (g_gi && g_gh)) && g_pre && g_xpe && g_x0 && workspace &&
                  (num_edges == 0 || (save_alpha && dst_src && etype && src_pos && src_dst)),
                  "glam_message_stack_bwd: null pointer");
     GLAM_REQUIRE(ldw == ld, "glam_message_stack_bwd: w_ext pitch %lld, expected %d", (long long)ldw, ld);
     GLAM_REQUIRE(workspace_bytes >= glam_message_stack_bwd_workspace_bytes(channels, heads, edge_dim) && al16b(workspace),
                  "glam_message_stack_bwd: workspace too small or not 16-byte aligned");
     GLAM_REQUIRE(al16b(save_x) && al16b(save_h) && al16b(save_xpe) && al16b(save_m) && al16b(save_rzn) && al16b(save_gh) && al16b(save_gt) && al16b(w_ext) &&
-                 al16b(w_scale) && al16b(g_gi) && al16b(g_gh) && al16b(g_pre) && al16b(g_xpe) && al16b(g_x0) && al16b(g_h0) && al16b(g_h_final) && al16b(tiles),
+                 al16b(w_scale) && al16b(g_gi) && al16b(g_gh) && al16b(g4) && al16b(g_pre) && al16b(g_xpe) && al16b(g_x0) && al16b(g_h0) && al16b(g_h_final) && al16b(tiles),
                  "glam_message_stack_bwd: pointers must be 16-byte aligned");
     GLAM_REQUIRE(num_nodes < ((int64_t)1 << 31) && num_edges < ((int64_t)1 << 31), "glam_message_stack_bwd: too large");
     BwParams p;
@@ -767,7 +774,7 @@ extern "C" int glam_message_stack_bwd(const float* save_x, const float* save_h, 
     p.tiles = reinterpret_cast<const int4*>(tiles); p.meta = tile_meta; p.rowptr = dst_rowptr; p.src = dst_src; p.etype = etype;
     p.src_rowptr = src_rowptr; p.src_pos = src_pos; p.src_dst = src_dst; p.N = num_nodes; p.E = num_edges; p.De = edge_dim;
     p.steps = steps; p.act = act; p.res = res; p.slope = negative_slope; p.act_param = act_param;
-    p.G_GI = g_gi; p.G_GH = g_gh; p.G_PRE = g_pre; p.G_XPE = g_xpe; p.g_x0 = g_x0; p.g_h0 = g_h0; p.phase_clock = g_mp_phase_clock;
+    p.G_GI = g_gi; p.G_GH = g_gh; p.G4 = g4; p.G_PRE = g_pre; p.G_XPE = g_xpe; p.g_x0 = g_x0; p.g_h0 = g_h0; p.phase_clock = g_mp_phase_clock;
     int rc = 0;
     switch (channels) {
         case 32: rc = bwd_launch<8, 3>(p, w_ih, w_hh, image, stream); break;

@@ -237,11 +237,9 @@ int tc_gemm_tn_launch(const float* A, int64_t lda, const float* B, int64_t ldb, 
     CUtensorMap tp, tq;
     if (int rc = make_tmap_rows(&tp, P, M, p.Wp, ldp, kTnRows, (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     if (int rc = make_tmap_rows(&tq, Q, M, p.Wq, ldq, kTnRows, (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-    static size_t configured = 0;
-    if (smem > configured) {
+    {   // (per DEVICE attribute: set on every launch)
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("tc_gemm_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        configured = smem;
     }
     tc_gemm_tn_kernel<<<grid, kTnThreads, smem, stream>>>(tp, tq, p);
     GLAM_CHECK_LAUNCH();

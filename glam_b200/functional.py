@@ -182,12 +182,26 @@ def _stack_buffers(x0, S, H, C, ld, E, tiled_gates=False):
     tensors in the tile-blocked layout the one-launch backward reads (GT [S,N,7C]) instead of row-major RZN / GH."""
     N, dev = x0.shape[0], x0.device
     new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
-    sv = dict(X=new(S + 1, N, C), HH=new(S + 1, N, C), XPE=new(S, N, ld), AGG=new(S, N, H * C), ALPHA=new(S, E, H), M=new(S, N, C))
+    sv = dict(X=new(S + 1, N, C), HH=new(S + 1, N, C), XPE=new(S, N, ld), AGG=new(S, N, H * C), ALPHA=new(S, E, H))
     if tiled_gates:
-        sv["GT"] = new(S, N, 7 * C)
+        # GT: gate side, tile-blocked; MH: rows m | h_in | 1 — with the backward's G4 rows the one operand pair of both GRU
+        # weight gradients (M alone is not needed then: the backward kernel reads m from GT)
+        sv.update(GT=new(S, N, 7 * C), MH=new(S, N, 2 * C + 4))
     else:
-        sv.update(RZN=new(S, N, 3 * C), GH=new(S, N, C))
+        sv.update(M=new(S, N, C), RZN=new(S, N, 3 * C), GH=new(S, N, C))
     return sv
+
+
+def _gru_wgrads(MH, G4, C):
+    """Both GRU weight gradients and both bias gradients from ONE contraction: [m | h | 1]^T [g_r | g_z | g_n | g_n r] over all
+    rows ([2C+4] x [4C]; the constant column of MH makes row 2C the column sums of G4).  G_GI = G4[:, :3C], G_GH = G4[:, :2C] |
+    G4[:, 3C:] (the r and z gradients are shared by the input- and the hidden-side products)."""
+    Dt, _ = ops.gemm_tn_ex(MH, G4, transpose_out=True)                         # [4C, 2C+4]
+    g_w_ih = Dt[:3 * C, :C]
+    g_w_hh = torch.cat([Dt[:2 * C, C:2 * C], Dt[3 * C:, C:2 * C]])
+    g_b_ih = Dt[:3 * C, 2 * C]
+    g_b_hh = torch.cat([Dt[:2 * C, 2 * C], Dt[3 * C:, 2 * C]])
+    return g_w_ih, g_w_hh, g_b_ih, g_b_hh
 
 
 USE_FUSED_BWD = True       # one-launch backward of the message stack (tests flip it to compare with the per-op path)
@@ -208,8 +222,8 @@ class MessageBlockFn(Function):
             sv = _stack_buffers(x, 1, heads, channels, w_ext.shape[1], ea.shape[0], tiled_gates=fused_bwd)
             ops.message_stack_fwd(x, h, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, g, fi, heads, channels, 1,
                                   slope, act, act_param, identity is not None, save=sv)
-            xpe, agg, alpha, m, x_out, h_new = sv["XPE"][0], sv["AGG"][0], sv["ALPHA"][0], sv["M"][0], sv["X"][1], sv["HH"][1]
-            rzn, gh = (None, None) if fused_bwd else (sv["RZN"][0], sv["GH"][0])
+            xpe, agg, alpha, x_out, h_new = sv["XPE"][0], sv["AGG"][0], sv["ALPHA"][0], sv["X"][1], sv["HH"][1]
+            m, rzn, gh = (None, None, None) if fused_bwd else (sv["M"][0], sv["RZN"][0], sv["GH"][0])
             if fused_bwd:
                 ctx.fused = (sv, fi)
         else:
@@ -229,12 +243,11 @@ class MessageBlockFn(Function):
             sv, fi = ctx.fused
             N, C, HC, ld = x.shape[0], channels, heads * channels, xpe.shape[1]
             new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=x.device)
-            G_GI, G_GH, G_PRE, G_XPE = new(1, N, 3 * C), new(1, N, 3 * C), new(1, N, C), new(1, N, ld)
+            G4, G_PRE, G_XPE = new(1, N, 4 * C), new(1, N, C), new(1, N, ld)
             (g_x, g_h), g_w_edge, g_att_edge = ops.message_stack_bwd(
                 sv, [_c(g_x_out)], _c(g_h_new), w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ctx.g, fi, heads, C, 1, slope, act,
-                act_param, has_id, G_GI, G_GH, G_PRE, G_XPE, separate_h0=True)
-            g_w_ih, g_b_ih = ops.gemm_tn_ex(m, G_GI[0], transpose_out=True, want_colsum=True)
-            g_w_hh, g_b_hh = ops.gemm_tn_ex(h, G_GH[0], transpose_out=True, want_colsum=True)
+                act_param, has_id, None, None, G_PRE, G_XPE, separate_h0=True, G4=G4)
+            g_w_ih, g_w_hh, g_b_ih, g_b_hh = _gru_wgrads(sv["MH"].view(N, 2 * C + 4), G4.view(N, 4 * C), C)
             g_w_scale, g_bias = ops.gemm_tn_ex(agg, G_PRE[0], want_colsum=True)
             g_w_ext, _ = ops.gemm_tn_ex(x, G_XPE[0])
             ops.gemm_tn_ex(x, G_XPE[0][:, HC:HC + 2 * heads], out=g_w_ext[:, HC:HC + 2 * heads])      # logit columns: exact fp32
@@ -273,8 +286,8 @@ class MessageStackFn(Function):
                                   slope, act, act_param, res, save=sv)
             X, HH = sv["X"], sv["HH"]
             ctx.save_for_backward(w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ea, X, HH, X, None, sv["XPE"], sv["AGG"],
-                                  sv["ALPHA"], sv["M"], sv.get("RZN"), sv.get("GH"), None)
-            ctx.gt = sv.get("GT")
+                                  sv["ALPHA"], sv.get("M"), sv.get("RZN"), sv.get("GH"), None)
+            ctx.gt, ctx.mh = sv.get("GT"), sv.get("MH")
             ctx.g, ctx.cfg = g, (H, channels, slope, act, act_param, res, S, p_drop, None)
             ctx.fi = fi                                          # the same tile table serves the one-launch backward
             ctx.set_materialize_grads(False)
@@ -318,8 +331,7 @@ class MessageStackFn(Function):
         g = ctx.g
         N, HC, ld, E, De, dev = X.shape[1], H * C, XPE.shape[2], ea.shape[0], ea.shape[1], X.device
         new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
-        G_GI, G_GH, G_PRE = new(S, N, 3 * C), new(S, N, 3 * C), new(S, N, C)
-        G_XPE = new(S, N, ld)
+        G_PRE, G_XPE = new(S, N, C), new(S, N, ld)
         fi = getattr(ctx, "fi", None)
         gt = getattr(ctx, "gt", None)                            # forward saved the gate side tile-blocked: only the one-launch backward reads it
         fused_bwd = gt is not None or (USE_FUSED_BWD and fi is not None and p_drop == 0.0 and pn is None and g.src_rowptr is not None
@@ -327,11 +339,15 @@ class MessageStackFn(Function):
         if fused_bwd:
             # ONE launch for the reverse loop (csrc/mp_fused_bwd.cu): gate backward, input-gradient projections and both edge
             # passes per tile, the carried gradients resident on the SM; what the weight-gradient contractions read comes out
+            mh = getattr(ctx, "mh", None)
+            G4 = new(S, N, 4 * C) if mh is not None else None
+            G_GI, G_GH = (None, None) if mh is not None else (new(S, N, 3 * C), new(S, N, 3 * C))
             sv = dict(X=X, HH=HH, XPE=XPE, ALPHA=ALPHA, M=M, RZN=RZN, GH=GH, GT=gt)
             g_x0, g_w_edge, g_att_edge = ops.message_stack_bwd(sv, list(grads[:S]), _c(grads[S]), w_ext, w_edge, att_edge, w_scale,
                                                                w_ih, w_hh, g, fi, H, C, S, slope, act, act_param, res,
-                                                               G_GI, G_GH, G_PRE, G_XPE)
+                                                               G_GI, G_GH, G_PRE, G_XPE, G4=G4)
         else:
+            G_GI, G_GH, G4, mh = new(S, N, 3 * C), new(S, N, 3 * C), None, None
             G_LOGIT, G_WE = new(S, E, H), new(S, De, HC)
         g_ext, g_h, g_x = grads[:S], _c(grads[S]), None
         for s in (() if fused_bwd else range(S - 1, -1, -1)):
@@ -362,8 +378,11 @@ class MessageStackFn(Function):
         if not fused_bwd:
             g_x0 = g_x.add_(g_h)                                                              # X[0] and HH[0] are both x0
         SN = S * N
-        g_w_ih, g_b_ih = ops.gemm_tn_ex(M.view(SN, C), G_GI.view(SN, 3 * C), transpose_out=True, want_colsum=True)
-        g_w_hh, g_b_hh = ops.gemm_tn_ex(HH[:S].view(SN, C), G_GH.view(SN, 3 * C), transpose_out=True, want_colsum=True)
+        if G4 is not None:
+            g_w_ih, g_w_hh, g_b_ih, g_b_hh = _gru_wgrads(mh.view(SN, 2 * C + 4), G4.view(SN, 4 * C), C)
+        else:
+            g_w_ih, g_b_ih = ops.gemm_tn_ex(M.view(SN, C), G_GI.view(SN, 3 * C), transpose_out=True, want_colsum=True)
+            g_w_hh, g_b_hh = ops.gemm_tn_ex(HH[:S].view(SN, C), G_GH.view(SN, 3 * C), transpose_out=True, want_colsum=True)
         g_w_scale, g_bias = ops.gemm_tn_ex(AGG.view(SN, HC), G_PRE.view(SN, C), want_colsum=True)
         xd = XD[:S].view(SN, C)
         gxpe = G_XPE.view(SN, ld)

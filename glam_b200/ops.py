@@ -333,7 +333,7 @@ def message_stack_fwd(x0, h0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh
           N, E, channels, heads, fi.edge_dim, steps, float(slope), act, float(act_param), 1 if res else 0,
           1 if conv_only else 0, 1 if keep_all else 0, _p(x_out), _p(h_out), _p(sv.get("X")), _p(sv.get("HH")), _p(sv.get("XPE")),
           _p(sv.get("AGG")), _p(sv.get("ALPHA")), _p(sv.get("M")), _p(sv.get("RZN")), _p(sv.get("GH")), _p(sv.get("GT")),
-          _p(pn_batch), float(pn_eps), _stream(x0),
+          _p(sv.get("MH")), _p(pn_batch), float(pn_eps), _stream(x0),
           label=f"[N={N},S={steps},{'save' if save is not None else 'eval'}{',conv' if conv_only else ''}]")
     return x_out, h_out
 
@@ -343,7 +343,7 @@ def message_stack_bwd_supported(channels: int, heads: int, edge_dim: int, steps:
 
 
 def message_stack_bwd(sv, g_ext, g_h_final, w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, g, fi, heads, channels, steps, slope, act,
-                      act_param, res, G_GI, G_GH, G_PRE, G_XPE, separate_h0=False):
+                      act_param, res, G_GI, G_GH, G_PRE, G_XPE, separate_h0=False, G4=None):
     """Backward of the whole message stack in one launch (csrc/mp_fused_bwd.cu).  `sv` = the tensors message_stack_fwd saved;
     `g_ext` = per-step gradients of the step outputs (None entries allowed), `g_h_final` = gradient of the final GRU state.
     Fills G_GI, G_GH [S,N,3C], G_PRE [S,N,C], G_XPE [S,N,ld]; returns (g_x0 [N,C], g_w_edge [De,HC], g_att_edge [De,H]) — with
@@ -353,7 +353,7 @@ def message_stack_bwd(sv, g_ext, g_h_final, w_ext, w_edge, att_edge, w_scale, w_
     _need_cuda(X, w_ext)
     N, C, E, dev = X.shape[1], channels, g.num_edges, X.device
     De, HC = fi.edge_dim, heads * channels
-    for t in (X, sv.get("HH"), sv["XPE"], sv["ALPHA"], sv.get("M"), sv.get("RZN"), sv.get("GH"), sv.get("GT"), G_GI, G_GH, G_PRE, G_XPE,
+    for t in (X, sv.get("HH"), sv["XPE"], sv["ALPHA"], sv.get("M"), sv.get("RZN"), sv.get("GH"), sv.get("GT"), G_GI, G_GH, G4, G_PRE, G_XPE,
               w_ext, w_edge, att_edge, w_scale, w_ih, w_hh):
         assert t is None or t.is_contiguous()
     g_ext = [None if t is None else (t if t.is_contiguous() else t.contiguous()) for t in g_ext]
@@ -368,7 +368,7 @@ def message_stack_bwd(sv, g_ext, g_h_final, w_ext, w_edge, att_edge, w_scale, w_
           _p(sv.get("GH")), _p(sv.get("GT")), ctypes.cast(ptrs, ctypes.c_void_p), _p(g_h_final), _p(w_ext), w_ext.stride(0), _p(w_edge), _p(att_edge), _p(w_scale),
           _p(w_ih), _p(w_hh), _p(fi.tiles), _p(fi.meta), _p(g.dst_rowptr), _p(g.dst_src), _p(fi.etype), _p(g.src_rowptr),
           _p(g.src_pos), _p(g.src_dst), N, E, channels, heads, De, steps, float(slope), act, float(act_param), 1 if res else 0,
-          _p(G_GI), _p(G_GH), _p(G_PRE), _p(G_XPE), _p(g_x0), _p(g_h0), _p(g_we), _p(g_ae), _p(ws), ws.numel(), _stream(X),
+          _p(G_GI), _p(G_GH), _p(G4), _p(G_PRE), _p(G_XPE), _p(g_x0), _p(g_h0), _p(g_we), _p(g_ae), _p(ws), ws.numel(), _stream(X),
           label=f"[N={N},S={steps}]")
     return ((g_x0, g_h0) if separate_h0 else g_x0), g_we, g_ae
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLAM_B200_ABI_VERSION 9
+#define GLAM_B200_ABI_VERSION 10
 #define GLAM_MAX_HEADS 4
 
 int glam_abi_version(void);
@@ -310,7 +310,9 @@ int glam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
  *   (conv_only: save_xpe, save_agg, save_alpha and x_out only).  save_gt != NULL (then save_rzn / save_gh may be NULL): the
  *   gate-side tensors for glam_message_stack_bwd in its tile-blocked layout instead — [steps][N][7C]; inside step s the tile
  *   {n0, n1} owns floats [n0*7C, n1*7C) as 7*C/4 slots (r, z, n, gh_n, h, x', m; C/4 16-byte chunks each) of n1-n0 rows x
- *   16 bytes: a warp's 32 rows of one chunk are contiguous in the forward's stores and in the backward's loads.  pn_batch !=
+ *   16 bytes: a warp's 32 rows of one chunk are contiguous in the forward's stores and in the backward's loads.  save_mh != NULL
+ *   (then save_m may be NULL): [steps][N][2C+4] rows m | h_in | 1 0 0 0 — with glam_message_stack_bwd's g4 rows the ONE pair of
+ *   operands of both GRU weight gradients ([m h 1]^T [g_r g_z g_n g_n r]; the constant column yields the bias gradients).  pn_batch !=
  *   NULL (evaluation only: no saves, h0 == NULL): PairNorm(scale=1, eps=pn_eps) per graph on every step's block input inside the
  *   kernel (_PairNorm, the reference's default graph_norm, src_1gp/layer.py:179-185,255; pn_batch = the int64 `batch` vector);
  *   the residual and the first step's h use the un-normalised rows, as the reference does (layer.py:253,264).  If meta[1] != 0 the outputs are filled with NaN: callers
@@ -342,7 +344,7 @@ int glam_message_stack_fwd(const float* x0, const float* h0, const float* x_raw,
                            int edge_dim, int steps, float negative_slope, int act, float act_param, int res,
                            int conv_only, int keep_all, float* x_out, float* h_out, float* save_x, float* save_h,
                            float* save_xpe, float* save_agg, float* save_alpha, float* save_m, float* save_rzn,
-                           float* save_gh, float* save_gt, const int64_t* pn_batch, float pn_eps, void* stream);
+                           float* save_gh, float* save_gt, float* save_mh, const int64_t* pn_batch, float pn_eps, void* stream);
 
 /* glam_message_stack_bwd — backward of glam_message_stack_fwd's training mode (h0 == NULL, no conv_only) in ONE launch
  *   (csrc/mp_fused_bwd.cu), on the same tile table: gate backward, the four input-gradient projections, the edge backward
@@ -351,7 +353,8 @@ int glam_message_stack_fwd(const float* x0, const float* h0, const float* x_raw,
  *   row-major — save_h, save_x, save_m, save_rzn, save_gh — or, when save_gt != NULL, from the tile-blocked save); h_g_ext is a HOST array of
  *   `steps` device pointers (NULL entries allowed): the gradient arriving at every step's output x_{s+1} [N][C] from outside;
  *   g_h_final [N][C] (may be NULL) the gradient of the final GRU state.  Writes what the weight-gradient contractions read
- *   — g_gi, g_gh [steps][N][3C], g_pre [steps][N][C], g_xpe [steps][N][ld] — plus g_x0 [N][C] (gradient of x0, both as the
+ *   — g_gi, g_gh [steps][N][3C] (or, when g4 != NULL, g4 [steps][N][4C] = g_r | g_z | g_n | g_n r in their place), g_pre
+ *   [steps][N][C], g_xpe [steps][N][ld] — plus g_x0 [N][C] (gradient of x0, both as the
  *   first block input and the first GRU state; when the forward was given its own h0 tensor pass g_h0 [N][C] != NULL and the two
  *   gradients come out apart) and the parameter gradients of the edge phase summed over steps: g_w_edge
  *   [edge_dim][HC], g_att_edge [edge_dim][H] (= d/d att_edge of glam_triplet_prep_fwd).  needs the source-side index of
@@ -368,8 +371,8 @@ int glam_message_stack_bwd(const float* save_x, const float* save_h, const float
                            const int32_t* tile_meta, const int32_t* dst_rowptr, const int32_t* dst_src, const uint8_t* etype,
                            const int32_t* src_rowptr, const int32_t* src_pos, const int32_t* src_dst, int64_t num_nodes,
                            int64_t num_edges, int channels, int heads, int edge_dim, int steps, float negative_slope, int act,
-                           float act_param, int res, float* g_gi, float* g_gh, float* g_pre, float* g_xpe, float* g_x0,
-                           float* g_h0, float* g_w_edge, float* g_att_edge, void* workspace, size_t workspace_bytes, void* stream);
+                           float act_param, int res, float* g_gi, float* g_gh, float* g4, float* g_pre, float* g_xpe,
+                           float* g_x0, float* g_h0, float* g_w_edge, float* g_att_edge, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (9) Packed graph store -> device index (csrc/packed.cu).  The reference ships every batch as fp32
