@@ -189,20 +189,26 @@ __global__ void colsum_partial_kernel(const float* __restrict__ G, int64_t ldg, 
 constexpr int kSkinnyWarps = 8;
 // QW = 8 or 16: register width of the narrow operand (16 covers the 9 / 15-feature input projections of the models, whose
 // weight gradients otherwise fell to the scalar fp32 A^T B kernel: 81 us for 18 MB of operands at the bench shape)
+// colsum: 0 none, 1 column sums of P, 2 column sums of Q ride along (the bias gradient of a LinearBlock: no second pass over B);
+// they follow the [Wp][Wq] block of the CTA's partial.
 template <int KPL, int QW = 8>
 __global__ void __launch_bounds__(kSkinnyWarps * 32)
 skinny_tn_kernel(const float* __restrict__ P, int64_t ldp, int Wp, const float* __restrict__ Q, int64_t ldq, int Wq, int64_t M,
-                 int64_t rows_per_cta, float* __restrict__ partial) {
+                 int64_t rows_per_cta, float* __restrict__ partial, int colsum) {
     extern __shared__ float red[];                     // [kSkinnyWarps][Wp][QW]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t mbeg = (int64_t)blockIdx.x * rows_per_cta;
     int64_t mend = mbeg + rows_per_cta;
     if (mend > M) mend = M;
-    float acc[KPL][QW];
+    float acc[KPL][QW], csp[KPL], csq[QW];
 #pragma unroll
-    for (int t = 0; t < KPL; ++t)
+    for (int t = 0; t < KPL; ++t) {
+        csp[t] = 0.f;
 #pragma unroll
         for (int j = 0; j < QW; ++j) acc[t][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < QW; ++j) csq[j] = 0.f;
     // 4 rows per iteration: 4 independent load groups in flight per warp
     for (int64_t m0 = mbeg + warp; m0 < mend; m0 += 4 * kSkinnyWarps) {
         float q[4][QW], a[4][KPL];
@@ -219,11 +225,16 @@ skinny_tn_kernel(const float* __restrict__ P, int64_t ldp, int Wp, const float* 
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u) {
 #pragma unroll
-            for (int t = 0; t < KPL; ++t)
+            for (int t = 0; t < KPL; ++t) {
+                csp[t] += a[u][t];
 #pragma unroll
                 for (int j = 0; j < QW; ++j) acc[t][j] = fmaf(a[u][t], q[u][j], acc[t][j]);
+            }
+#pragma unroll
+            for (int j = 0; j < QW; ++j) csq[j] += q[u][j];
+        }
     }
 #pragma unroll
     for (int t = 0; t < KPL; ++t) {
@@ -233,13 +244,31 @@ skinny_tn_kernel(const float* __restrict__ P, int64_t ldp, int Wp, const float* 
             for (int j = 0; j < QW; ++j) red[((size_t)warp * Wp + f) * QW + j] = acc[t][j];
     }
     __syncthreads();
-    float* out = partial + (int64_t)blockIdx.x * Wp * Wq;
+    const int extra = colsum == 1 ? Wp : colsum == 2 ? Wq : 0;
+    float* out = partial + (int64_t)blockIdx.x * (Wp * Wq + extra);
     for (int idx = threadIdx.x; idx < Wp * Wq; idx += blockDim.x) {
         const int f = idx / Wq, j = idx - f * Wq;
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < kSkinnyWarps; ++w) v += red[((size_t)w * Wp + f) * QW + j];
         out[idx] = v;
+    }
+    if (colsum) {                                      // second use of the staging area: per-warp column sums, fixed order over warps
+        __syncthreads();
+        if (colsum == 1) {
+#pragma unroll
+            for (int t = 0; t < KPL; ++t) { const int f = lane + 32 * t; if (f < Wp) red[warp * Wp + f] = csp[t]; }
+        } else if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < QW; ++j) if (j < Wq) red[warp * Wq + j] = csq[j];
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < extra; idx += blockDim.x) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kSkinnyWarps; ++w) v += red[w * extra + idx];
+            out[Wp * Wq + idx] = v;
+        }
     }
 }
 
@@ -373,7 +402,7 @@ extern "C" int glam_colsum(const float* G, int64_t ldg, int64_t M, int64_t N, fl
 extern "C" size_t glam_gemm_tn_ex_workspace_bytes(int64_t M, int64_t Ka, int64_t Kb, int want_colsum) {
     size_t a = glam_gemm_tn_workspace_bytes(M, Ka, Kb), b = want_colsum ? glam_colsum_workspace_bytes(M, Kb) : 0;
     size_t c = tc_gemm_tn_workspace(M, Ka, Kb, want_colsum);
-    size_t d = sizeof(float) * (size_t)skinny_grid(M) * (size_t)Ka * (size_t)Kb;
+    size_t d = sizeof(float) * (size_t)skinny_grid(M) * ((size_t)Ka * (size_t)Kb + (size_t)(Ka > Kb ? Ka : Kb));
     size_t m = a > b ? a : b;
     m = m > c ? m : c;
     return m > d ? m : d;
@@ -406,9 +435,10 @@ extern "C" int glam_gemm_tn_ex(const float* A, int64_t lda, const float* B, int6
         const int qw = Wq <= 8 ? 8 : 16;
         const size_t smem = sizeof(float) * kSkinnyWarps * Wp * qw;
         const int kpl = (Wp + 31) / 32;
+        const int cs_mode = !colsum_b ? 0 : (a_wide ? 2 : 1);               // colsum(B): B is Q when A is the wide operand, else P
         auto launch = [&](auto fn) {
             if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            fn<<<S, kSkinnyWarps * 32, smem, stream>>>(P, ldp, Wp, Q, ldq, Wq, M, rpc, (float*)workspace);
+            fn<<<S, kSkinnyWarps * 32, smem, stream>>>(P, ldp, Wp, Q, ldq, Wq, M, rpc, (float*)workspace, cs_mode);
         };
         if (qw == 16) launch(skinny_tn_kernel<2, 16>);
         else if (kpl <= 2) launch(skinny_tn_kernel<2>); else if (kpl <= 4) launch(skinny_tn_kernel<4>);
@@ -416,15 +446,8 @@ extern "C" int glam_gemm_tn_ex(const float* A, int64_t lda, const float* B, int6
         GLAM_CHECK_LAUNCH();
         // partial holds [Wp][Wq]; out is [Ka][Kb]: transposed w.r.t. the partial exactly when A is the narrow operand
         const int tr = (a_wide ? 0 : 1) ^ (transpose_out ? 1 : 0);
-        if (int rc = launch_reduce_partials((const float*)workspace, S, Wp, Wq, 0, out, ldo, tr, nullptr, stream)) return rc;
-        if (colsum_b) {
-            const int S2 = colsum_splits(M);
-            int64_t rps2 = (M + S2 - 1) / S2;
-            colsum_partial_kernel<<<S2, dim3(32, 8), 0, stream>>>(B, ldb, M, (int)Kb, rps2, (float*)workspace);
-            GLAM_CHECK_LAUNCH();
-            return launch_reduce_partials((const float*)workspace, S2, 1, (int)Kb, 0, colsum_b, Kb, 0, nullptr, stream);
-        }
-        return 0;
+        // colsum(B) rode along in the same pass: it follows the product in every partial and leaves through the reduction's out2
+        return launch_reduce_partials((const float*)workspace, S, Wp, Wq, colsum_b ? (int)Kb : 0, out, ldo, tr, colsum_b, stream);
     }
     if (tc_gemm_tn_eligible(A, lda, B, ldb, M, Ka, Kb, colsum_b != nullptr))
         return tc_gemm_tn_launch(A, lda, B, ldb, M, Ka, Kb, out, ldo, transpose_out, colsum_b, workspace, stream);
