@@ -272,6 +272,142 @@ skinny_tn_kernel(const float* __restrict__ P, int64_t ldp, int Wp, const float* 
     }
 }
 
+// The same product for Wp <= 64, Wq <= 16 (every skinny product of the models), staged through shared memory.  The warp-per-row
+// kernel above keeps ~11 warps per SM each waiting on one row's loads (41 us for 18 MB at the bench shape, 6 % of HBM rate).
+// Here 96-row tiles of both operands arrive by cp.async through a 3-deep ring (2 CTAs per SM, 64 KB in flight per SM).
+// A lane owns four features (one 16-byte chunk of the P row) of one of RS = 2..4 rows, so a warp pass covers RS rows with
+// ONE LDS.128 of P and QW/4 LDS.128 of Q (shared-memory cycles, not FMAs, bounded the first version: a broadcast LDS.128
+// still costs four).  Column Wp of the P tile is a column of ones, so colsum(Q) is one more feature; colsum(P) is one FADD
+// per value.  Every reduction runs in a fixed order.
+constexpr int kStRows = 96, kStPitch = 68, kStThreads = 256, kStStages = 3;
+constexpr int kStSmem = kStStages * (kStRows * kStPitch + kStRows * 16) * 4;
+__device__ __forceinline__ void st_cp4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void st_cp16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+template <int QW>
+__global__ void __launch_bounds__(kStThreads)
+skinny_tile_kernel(const float* __restrict__ P, int64_t ldp, int Wp, const float* __restrict__ Q, int64_t ldq, int Wq, int64_t M,
+                   int tiles_per_cta, float* __restrict__ partial, int colsum, int p_vec) {
+    extern __shared__ __align__(16) float st_smem[];
+    float* const Qs = st_smem;                                             // [stages][96][16]
+    float* const Ps = st_smem + kStStages * kStRows * 16;                  // [stages][96][68]
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int FG = (Wp + (colsum == 2 ? 1 : 0) + 3) / 4;                   // feature groups of 4 (<= 16)
+    const int RS = FG <= 8 ? 4 : FG <= 10 ? 3 : 2;                         // rows per warp pass
+    const int fg = lane % FG, rsub = lane / FG;
+    const bool live = rsub < RS;
+    const int64_t ntiles = (M + kStRows - 1) / kStRows;
+    const int64_t tile0 = (int64_t)blockIdx.x * tiles_per_cta;
+    const int n = (int)((tile0 + tiles_per_cta <= ntiles ? tile0 + tiles_per_cta : ntiles) - tile0);
+    const int WpQ = Wp >> 2;
+    auto issue = [&](int buf, int64_t tile) {
+        const int64_t row0 = tile * kStRows;
+        const int rows = (int)(M - row0 < kStRows ? M - row0 : kStRows);
+        float* ps = Ps + buf * kStRows * kStPitch; float* qs = Qs + buf * kStRows * 16;
+        if (p_vec) {                                                        // rows are 16-byte aligned: one copy per 4 features
+            int r = t / WpQ, c = t - r * WpQ;
+            const int dr = kStThreads / WpQ, dc = kStThreads - dr * WpQ;
+            for (; r < kStRows; ) {
+                if (r < rows) st_cp16(ps + r * kStPitch + 4 * c, P + (row0 + r) * ldp + 4 * c);
+                else *reinterpret_cast<float4*>(ps + r * kStPitch + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+                r += dr; c += dc;
+                if (c >= WpQ) { c -= WpQ; ++r; }
+            }
+        } else {
+            int r = t / Wp, c = t - r * Wp;
+            const int dr = kStThreads / Wp, dc = kStThreads - dr * Wp;
+            for (; r < kStRows; ) {
+                if (r < rows) st_cp4(ps + r * kStPitch + c, P + (row0 + r) * ldp + c); else ps[r * kStPitch + c] = 0.f;
+                r += dr; c += dc;
+                if (c >= Wp) { c -= Wp; ++r; }
+            }
+        }
+        for (int idx = t; idx < kStRows * QW; idx += kStThreads) {
+            const int r = idx / QW, c = idx % QW;
+            if (r < rows && c < Wq) st_cp4(qs + r * 16 + c, Q + (row0 + r) * ldq + c); else qs[r * 16 + c] = 0.f;
+        }
+        if (t < kStRows) {                                                  // ones column, and zeros up to the end of its group
+            const float one = t < rows ? 1.f : 0.f;
+            for (int c = Wp; c < 4 * FG; ++c) ps[t * kStPitch + c] = c == Wp ? one : 0.f;
+        }
+    };
+    float acc[4][QW], csp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < QW; ++j) acc[i][j] = 0.f;
+    for (int i = 0; i < kStStages - 1; ++i) {                               // one commit per slot, empty when there is no tile
+        if (i < n) issue(i, tile0 + i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const int rows_per_warp = kStRows / (kStThreads / 32);                  // 12
+    for (int i = 0; i < n; ++i) {
+        if (i + kStStages - 1 < n) issue((i + kStStages - 1) % kStStages, tile0 + i + kStStages - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(kStStages - 1) : "memory");
+        __syncthreads();
+        const float* ps = Ps + (i % kStStages) * kStRows * kStPitch + 4 * fg;
+        const float* qs = Qs + (i % kStStages) * kStRows * 16;
+        if (live) {
+            for (int rr = rsub; rr < rows_per_warp; rr += RS) {
+                const int r = warp * rows_per_warp + rr;
+                const float4 pv = *reinterpret_cast<const float4*>(ps + r * kStPitch);
+                csp[0] += pv.x; csp[1] += pv.y; csp[2] += pv.z; csp[3] += pv.w;
+#pragma unroll
+                for (int j4 = 0; j4 < QW / 4; ++j4) {
+                    const float4 q = *reinterpret_cast<const float4*>(qs + r * 16 + 4 * j4);
+                    const float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        acc[0][4 * j4 + jj] = fmaf(pv.x, qq[jj], acc[0][4 * j4 + jj]);
+                        acc[1][4 * j4 + jj] = fmaf(pv.y, qq[jj], acc[1][4 * j4 + jj]);
+                        acc[2][4 * j4 + jj] = fmaf(pv.z, qq[jj], acc[2][4 * j4 + jj]);
+                        acc[3][4 * j4 + jj] = fmaf(pv.w, qq[jj], acc[3][4 * j4 + jj]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // every (warp, row slot) leaves its block in the idle ring; the output threads add them in a fixed order
+    constexpr int RW = QW + 1;
+    float* red = st_smem;                                                   // [8 warps][RS][4 FG][RW]
+    if (live) {
+        float* rp = red + (((warp * RS + rsub) * FG + fg) * 4) * RW;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int j = 0; j < QW; ++j) rp[i * RW + j] = acc[i][j];
+            rp[i * RW + QW] = csp[i];
+        }
+    }
+    __syncthreads();
+    const int extra = colsum == 1 ? Wp : colsum == 2 ? Wq : 0;
+    float* out = partial + (int64_t)blockIdx.x * (Wp * Wq + extra);
+    const int slots = (kStThreads / 32) * RS, slot_stride = FG * 4 * RW;
+    for (int idx = t; idx < Wp * Wq + extra; idx += kStThreads) {
+        int ff, j;
+        if (idx < Wp * Wq) { ff = idx / Wq; j = idx - ff * Wq; }
+        else if (colsum == 1) { ff = idx - Wp * Wq; j = QW; }
+        else { ff = Wp; j = idx - Wp * Wq; }
+        const float* rp = red + ff * RW + j;
+        float v = 0.f;
+        for (int s2 = 0; s2 < slots; ++s2) v += rp[s2 * slot_stride];
+        out[idx] = v;
+    }
+}
+static int skinny_tile_grid(int64_t M, int* tiles_per_cta) {
+    const int64_t ntiles = (M + kStRows - 1) / kStRows;
+    int64_t tpc = (ntiles + 2 * kNumSMs - 1) / (2 * kNumSMs);
+    if (tpc < 1) tpc = 1;
+    if (tiles_per_cta) *tiles_per_cta = (int)tpc;
+    const int64_t g = (ntiles + tpc - 1) / tpc;
+    return (int)(g < 1 ? 1 : g);
+}
+
 // out[r, c] (or transposed) = sum_s partial[s][r*cols + c]; 4 thread rows split S, combined in a fixed order
 __global__ void __launch_bounds__(256)
 reduce4_kernel(const float* __restrict__ partial, int S, int rows, int cols, float* __restrict__ out, int64_t ldo, int transpose_out) {
@@ -402,7 +538,8 @@ extern "C" int glam_colsum(const float* G, int64_t ldg, int64_t M, int64_t N, fl
 extern "C" size_t glam_gemm_tn_ex_workspace_bytes(int64_t M, int64_t Ka, int64_t Kb, int want_colsum) {
     size_t a = glam_gemm_tn_workspace_bytes(M, Ka, Kb), b = want_colsum ? glam_colsum_workspace_bytes(M, Kb) : 0;
     size_t c = tc_gemm_tn_workspace(M, Ka, Kb, want_colsum);
-    size_t d = sizeof(float) * (size_t)skinny_grid(M) * ((size_t)Ka * (size_t)Kb + (size_t)(Ka > Kb ? Ka : Kb));
+    const int sg = skinny_grid(M), tg = skinny_tile_grid(M, nullptr);
+    size_t d = sizeof(float) * (size_t)(sg > tg ? sg : tg) * ((size_t)Ka * (size_t)Kb + (size_t)(Ka > Kb ? Ka : Kb));
     size_t m = a > b ? a : b;
     m = m > c ? m : c;
     return m > d ? m : d;
@@ -430,12 +567,25 @@ extern "C" int glam_gemm_tn_ex(const float* A, int64_t lda, const float* B, int6
         const float* P = a_wide ? A : B; const float* Q = a_wide ? B : A;
         const int64_t ldp = a_wide ? lda : ldb, ldq = a_wide ? ldb : lda;
         const int Wp = (int)(a_wide ? Ka : Kb), Wq = (int)(a_wide ? Kb : Ka);
+        const int cs_mode = !colsum_b ? 0 : (a_wide ? 2 : 1);               // colsum(B): B is Q when A is the wide operand, else P
+        const int tr = (a_wide ? 0 : 1) ^ (transpose_out ? 1 : 0);
+        if (Wp + (cs_mode == 2 ? 1 : 0) <= 64 && Wq <= 16) {
+            int tpc = 1;
+            const int S = skinny_tile_grid(M, &tpc);
+            auto go = [&](auto fn) {
+                cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kStSmem);
+                const int p_vec = (Wp % 4 == 0 && ldp % 4 == 0 && ((uintptr_t)P & 15) == 0) ? 1 : 0;
+                fn<<<S, kStThreads, kStSmem, stream>>>(P, ldp, Wp, Q, ldq, Wq, M, tpc, (float*)workspace, cs_mode, p_vec);
+            };
+            if (Wq <= 8) go(skinny_tile_kernel<8>); else go(skinny_tile_kernel<16>);
+            GLAM_CHECK_LAUNCH();
+            return launch_reduce_partials((const float*)workspace, S, Wp, Wq, colsum_b ? (int)Kb : 0, out, ldo, tr, colsum_b, stream);
+        }
         const int S = skinny_grid(M);
         const int64_t rpc = (M + S - 1) / S;
         const int qw = Wq <= 8 ? 8 : 16;
         const size_t smem = sizeof(float) * kSkinnyWarps * Wp * qw;
         const int kpl = (Wp + 31) / 32;
-        const int cs_mode = !colsum_b ? 0 : (a_wide ? 2 : 1);               // colsum(B): B is Q when A is the wide operand, else P
         auto launch = [&](auto fn) {
             if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             fn<<<S, kSkinnyWarps * 32, smem, stream>>>(P, ldp, Wp, Q, ldq, Wq, M, rpc, (float*)workspace, cs_mode);
@@ -445,7 +595,6 @@ extern "C" int glam_gemm_tn_ex(const float* A, int64_t lda, const float* B, int6
         else if (kpl <= 6) launch(skinny_tn_kernel<6>); else launch(skinny_tn_kernel<9>);
         GLAM_CHECK_LAUNCH();
         // partial holds [Wp][Wq]; out is [Ka][Kb]: transposed w.r.t. the partial exactly when A is the narrow operand
-        const int tr = (a_wide ? 0 : 1) ^ (transpose_out ? 1 : 0);
         // colsum(B) rode along in the same pass: it follows the product in every partial and leaves through the reduction's out2
         return launch_reduce_partials((const float*)workspace, S, Wp, Wq, colsum_b ? (int)Kb : 0, out, ldo, tr, colsum_b, stream);
     }

@@ -36,6 +36,9 @@ if which in ("all", "tn"):
     timeit("gemm_tn [N,36]^T[N,108] +colsum", lambda: ops.gemm_tn_ex(x, g108, transpose_out=True, want_colsum=True), 4 * N * (C + HC))
     timeit("gemm_tn [N,36]^T[N,116]", lambda: ops.gemm_tn_ex(x, g116), 4 * N * (C + ld))
     timeit("skinny_tn [N,36]^T[N,6]", lambda: ops.gemm_tn_ex(x, g116[:, 108:114]), 4 * N * (C + 6))
+    x3 = torch.randn(3 * N, C, device=dev); g3 = torch.randn(3 * N, ld, device=dev); xr = torch.randn(N, 9, device=dev)
+    timeit("skinny_tn [3N,36]^T[3N,6] (logit columns)", lambda: ops.gemm_tn_ex(x3, g3[:, 108:114]), 4 * 3 * N * (C + 6))
+    timeit("skinny_tn [N,9]^T[N,36] +colsum (input lin)", lambda: ops.gemm_tn_ex(xr, x, want_colsum=True), 4 * N * (C + 9))
 if which in ("all", "edge"):
     b = make_molecule_batch(4096, total_nodes=N, total_edges=221184, seed=1).to(dev)
     g = graph.graph_index(b.edge_index, N); ea = g.sorted_edge_attr(b.edge_attr); E = b.num_edges

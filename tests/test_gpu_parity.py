@@ -133,6 +133,28 @@ def test_gemm_tn_long_and_deterministic(math_mode):
         tol_check(c1.cpu(), B.sum(0).cpu(), B.double().sum(0).cpu(), f"gemm_tn_ex colsum {ka}x{kb}")
 
 
+def test_skinny_weight_gradients_with_riding_column_sums(math_mode):
+    """Exact fp32 A^T B for narrow operands (input LinearBlock 9/15 features, attention-logit columns): every row count around
+    the 64-row tile, both operand orders (column sums of the wide and of the narrow operand), strided views."""
+    from glam_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    for M in (1, 63, 64, 65, 1000, 50_001):
+        for (ka, kb) in [(9, 36), (36, 9), (15, 36), (36, 6), (63, 16), (64, 8), (3, 3), (64, 16), (16, 64)]:
+            A, B = torch.randn(M, ka, generator=g).to(DEV), torch.randn(M, kb, generator=g).to(DEV)
+            for tr in (False, True):
+                o, c = ops.gemm_tn_ex(A, B, transpose_out=tr, want_colsum=True)
+                o2, c2 = ops.gemm_tn_ex(A, B, transpose_out=tr, want_colsum=True)
+                assert torch.equal(o, o2) and torch.equal(c, c2)
+                r = (A.double().t() @ B.double())
+                r = r.t() if tr else r
+                assert torch.allclose(o.double(), r, rtol=1e-5, atol=1e-4 * max(1.0, M ** 0.5) * 1e-1), (M, ka, kb, tr)
+                assert torch.allclose(c.double(), B.double().sum(0), rtol=1e-5, atol=1e-5 * max(1.0, M ** 0.5)), (M, ka, kb)
+    wide = torch.randn(5000, 116, generator=g).to(DEV)
+    X = torch.randn(5000, 36, generator=g).to(DEV)
+    o, _ = ops.gemm_tn_ex(X, wide[:, 108:114])                                # the logit columns of g_xpe, in place
+    assert torch.allclose(o.double(), X.double().t() @ wide[:, 108:114].double(), rtol=1e-5, atol=1e-3)
+
+
 # ---------------------------------------------------------------------------------------------- golden layer cases
 @pytest.mark.parametrize("name,C,De", [("triplet_C36", 36, 3), ("triplet_C60", 60, 4), ("triplet_C15_edge", 15, 4)])
 def test_triplet_message_golden(golden_layers, name, C, De, math_mode):
