@@ -38,6 +38,7 @@ struct TcGemmParams {
     int64_t M; int N, K, epi;
     int KP, Npad, tmem_cols, vec_store, stages, staged_out, og_groups, w_vec;
     int exact_begin, exact_end;   // output columns computed with exact fp32 FMAs (attention-logit columns)
+    int n_chunk;                  // > 0: blockIdx.y owns output columns [y * n_chunk, ...) (few row tiles: fill the SMs by columns)
     unsigned long long* dbg;      // optional phase timestamps of CTA 0 (globaltimer ns), 8 slots
 };
 
@@ -180,7 +181,17 @@ __device__ __forceinline__ void staged_epilogue_loop(const TcGemmParams& p, uint
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcGemmParams p_in) {
+    TcGemmParams p = p_in;
+    if (p.n_chunk > 0) {                                         // this CTA's column block: every N-side pointer moves with it
+        const int n0 = blockIdx.y * p.n_chunk;
+        p.W += (int64_t)n0 * p.w_sn;
+        if (p.bias) p.bias += n0;
+        if (p.aux) p.aux += n0;
+        p.Y += n0;
+        p.N = min(p.n_chunk, p.N - n0);
+        p.Npad = (p.N + 15) / 16 * 16;
+    }
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2], w_bar;
     __shared__ uint32_t tmem_slot;
@@ -468,16 +479,24 @@ int tc_gemm_launch(const float* X, int64_t ldx, const float* W, int64_t w_sk, in
     GLAM_REQUIRE(smem > 0, "tc_gemm: operands do not fit in shared memory (N=%lld K=%lld)", (long long)N, (long long)K);
     CUtensorMap tmap;
     if (int rc = make_tmap_rows(&tmap, X, M, K, ldx, kTileM, (int)CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    static size_t configured = 0;
-    if (smem > configured) {
+    {                                                            // the attribute is per device: set it on every call
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("tc_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        configured = smem;
     }
     const int64_t ntiles = (M + kTileM - 1) / kTileM;
     int64_t grid = kNumSMs;
     if (grid > ntiles) grid = ntiles;
-    tc_gemm_kernel<<<(unsigned)grid, kTcThreads, smem, stream>>>(tmap, p);
+    // Few row tiles (graph-level GEMMs: 4096 rows = 32 tiles): split the output columns over blockIdx.y so that the W image
+    // build and the epilogue, which dominate such launches, shrink with it and more SMs take part.
+    p.n_chunk = 0;
+    unsigned gy = 1;
+    if (exact_end <= exact_begin && ntiles * 2 <= kNumSMs && N >= 64) {
+        const int64_t ways = kNumSMs / ntiles;
+        int64_t chunk = ((N + ways - 1) / ways + 15) / 16 * 16;
+        if (chunk < 32) chunk = 32;
+        if (chunk < N) { p.n_chunk = (int)chunk; gy = (unsigned)((N + chunk - 1) / chunk); }
+    }
+    tc_gemm_kernel<<<dim3((unsigned)grid, gy), kTcThreads, smem, stream>>>(tmap, p);
     GLAM_CHECK_LAUNCH();
     return 0;
 }

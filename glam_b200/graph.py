@@ -34,7 +34,8 @@ class GraphIndex:
         self.src_rowptr = csr["src_rowptr"]
         self.src_pos = csr["src_pos"]
         self.src_dst = csr["src_dst"]
-        self.dst_tiles, self.src_tiles = ops.build_edge_tiles(csr, self.num_nodes)
+        self._csr = csr
+        self._edge_tiles = None
         self._edge_attr_key = None
         self._edge_attr_sorted = None
         self._gcn = None
@@ -42,6 +43,20 @@ class GraphIndex:
         self._nn = None
         self._fused_key = None
         self._fused = None
+
+    def _tiles(self):
+        # tile descriptors of the windowed per-op edge kernels: built on first use (the one-launch kernels never read them)
+        if self._edge_tiles is None:
+            self._edge_tiles = ops.build_edge_tiles(self._csr, self.num_nodes)
+        return self._edge_tiles
+
+    @property
+    def dst_tiles(self):
+        return self._tiles()[0]
+
+    @property
+    def src_tiles(self):
+        return self._tiles()[1]
 
     def fused_index(self, gptr: torch.Tensor, num_graphs: int, edge_attr: torch.Tensor):
         """Index of the fused message kernel (csrc/mp_fused.cu) for this batch, or None when the batch does not meet its

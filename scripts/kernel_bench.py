@@ -32,6 +32,12 @@ if which in ("all", "gemm"):
     timeit("gemm scale^T [N,108]x[36,108]^T", lambda: ops.gemm(agg, w_scale.t().contiguous(), transpose_w=True), 4 * N * (HC + C))
     timeit("gemm gru [N,36]x[36,108]^T", lambda: ops.gemm(x, w_ih, transpose_w=True, bias=b3), 4 * N * (C + HC))
     timeit("gemm dgrad [N,116]x[116,36]^T", lambda: ops.gemm(g116, w_ext, transpose_w=True), 4 * N * (ld + C))
+if which in ("all", "gemm", "small"):
+    B_ = 4096
+    q = torch.randn(B_, 3 * C, device=dev); wl = torch.randn(4 * C, 3 * C, device=dev); bl = torch.randn(4 * C, device=dev)
+    timeit("gemm lstm gates [4096,108]x[108,144]^T", lambda: ops.gemm(q, wl, transpose_w=True, bias=bl), 4 * B_ * 7 * C)
+    gg = torch.randn(B_, 4 * C, device=dev)
+    timeit("gemm lstm dgrad [4096,144]x[144,108]", lambda: ops.gemm(gg, wl), 4 * B_ * 7 * C)
 if which in ("all", "tn"):
     timeit("gemm_tn [N,36]^T[N,108] +colsum", lambda: ops.gemm_tn_ex(x, g108, transpose_out=True, want_colsum=True), 4 * N * (C + HC))
     timeit("gemm_tn [N,36]^T[N,116]", lambda: ops.gemm_tn_ex(x, g116), 4 * N * (C + ld))
