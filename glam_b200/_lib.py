@@ -77,7 +77,7 @@ SIGNATURES = {
     "glam_message_stack_bwd_supported": (I32, [I32, I32, I32, I32]),
     "glam_message_stack_bwd_workspace_bytes": (SZ, [I32, I32, I32]),
     "glam_message_stack_bwd": (I32, [P, P, P, P, P, P, P, P, P, P, P, I64, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I32, I32, I32, I32,
-                                     F32, I32, F32, I32, P, P, P, P, P, P, P, P, P, P, SZ, P]),
+                                     F32, I32, F32, I32, I32, F32, P, P, P, P, P, P, P, P, P, P, SZ, P]),
     "glam_message_stack_fwd": (I32, [P, P, P, I32, P, P, I32, F32, P, I64, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I32, I32, I32, I32, F32, I32, F32,
                                      I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, F32, P]),
 }

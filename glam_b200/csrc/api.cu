@@ -1,4 +1,7 @@
 // Library-level entry points: version, error string, launch counter.
+#include <map>
+#include <mutex>
+#include <utility>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -46,6 +49,19 @@ reduce_partials_fixed_kernel(const float* __restrict__ partial, int S, int rows,
         const int r = i / cols, c = i - r * cols;
         if (transpose_out) out[(int64_t)c * ldo + r] = v; else out[(int64_t)r * ldo + c] = v;
     }
+}
+cudaError_t ensure_dyn_smem(const void* fn, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> have;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = have[{fn, dev}];
+    if (bytes <= cur) return cudaSuccess;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
 }
 int launch_reduce_partials(const float* partial, int S, int rows, int cols, int extra, float* out, int64_t ldo, int transpose_out,
                            float* out2, cudaStream_t stream) {

@@ -77,6 +77,10 @@ inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 __global__ void __launch_bounds__(256)
 reduce_partials_fixed_kernel(const float* __restrict__ partial, int S, int rows, int cols, int extra, float* __restrict__ out,
                              int64_t ldo, int transpose_out, float* __restrict__ out2);
+// Raise a kernel's dynamic shared-memory limit.  The attribute is per (function, device) and sticky, so it is only ever
+// raised: lowering it for a later, smaller launch would break tools that re-launch the nodes of an instantiated CUDA
+// graph on their own (ncu) — they pick up the function's CURRENT limit, not the one the node was captured with.
+cudaError_t ensure_dyn_smem(const void* fn, size_t bytes);
 int launch_reduce_partials(const float* partial, int S, int rows, int cols, int extra, float* out, int64_t ldo, int transpose_out,
                            float* out2, cudaStream_t stream);
 

@@ -309,7 +309,7 @@ static int pair_tc_launch(const float* xa, const float* xb, const int32_t* ptr_a
     const int KP = C <= 32 ? 1 : 2;
     const size_t smem = (size_t)KP * (mp::kMpPanel + kPairTcN * 128) + sizeof(float) * 16 * 16 * 4 + 1024;
     auto go = [&](auto kern) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ensure_dyn_smem((const void*)kern, (size_t)((int)smem));
         kern<<<(unsigned)num_pairs, kPairTcThreads, smem, stream>>>(xa, xb, ptr_a, ptr_b, idx_b, C, out, argmax, sum_a, sum_b);
     };
     if (KP == 1) go(pair_dot_pool_tc_kernel<1>); else go(pair_dot_pool_tc_kernel<2>);
@@ -329,7 +329,7 @@ extern "C" int glam_pair_dot_pool_fwd(const float* xa, const float* xb, const in
     GLAM_REQUIRE(num_pairs < (int64_t)1 << 31, "glam_pair_dot_pool_fwd: too many pairs");
     const size_t smem = sizeof(float) * 2 * kPairTile * (C | 1);
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(pair_dot_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ensure_dyn_smem((const void*)pair_dot_pool_fwd_kernel, (size_t)((int)smem));
     pair_dot_pool_fwd_kernel<<<(unsigned)num_pairs, kPairThreads, smem, (cudaStream_t)stream_>>>(xa, xb, ptr_a, ptr_b, nullptr, C, out,
                                                                                                argmax, sum_a, sum_b);
     GLAM_CHECK_LAUNCH();
@@ -345,7 +345,7 @@ extern "C" int glam_pair_dot_pool_fwd_idx(const float* xa, const float* xb, cons
     GLAM_REQUIRE(num_pairs < (int64_t)1 << 31, "glam_pair_dot_pool_fwd_idx: too many pairs");
     const size_t smem = sizeof(float) * 2 * kPairTile * (C | 1);
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(pair_dot_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ensure_dyn_smem((const void*)pair_dot_pool_fwd_kernel, (size_t)((int)smem));
     pair_dot_pool_fwd_kernel<<<(unsigned)num_pairs, kPairThreads, smem, (cudaStream_t)stream_>>>(xa, xb, ptr_a, ptr_b, idx_b, C, out,
                                                                                                argmax, sum_a, sum_b);
     GLAM_CHECK_LAUNCH();

@@ -573,7 +573,7 @@ extern "C" int glam_gemm_tn_ex(const float* A, int64_t lda, const float* B, int6
             int tpc = 1;
             const int S = skinny_tile_grid(M, &tpc);
             auto go = [&](auto fn) {
-                cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kStSmem);
+                ensure_dyn_smem((const void*)fn, (size_t)(kStSmem));
                 const int p_vec = (Wp % 4 == 0 && ldp % 4 == 0 && ((uintptr_t)P & 15) == 0) ? 1 : 0;
                 fn<<<S, kStThreads, kStSmem, stream>>>(P, ldp, Wp, Q, ldq, Wq, M, tpc, (float*)workspace, cs_mode, p_vec);
             };
@@ -587,7 +587,7 @@ extern "C" int glam_gemm_tn_ex(const float* A, int64_t lda, const float* B, int6
         const size_t smem = sizeof(float) * kSkinnyWarps * Wp * qw;
         const int kpl = (Wp + 31) / 32;
         auto launch = [&](auto fn) {
-            if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (smem > 48 * 1024) ensure_dyn_smem((const void*)fn, (size_t)((int)smem));
             fn<<<S, kSkinnyWarps * 32, smem, stream>>>(P, ldp, Wp, Q, ldq, Wq, M, rpc, (float*)workspace, cs_mode);
         };
         if (qw == 16) launch(skinny_tn_kernel<2, 16>);

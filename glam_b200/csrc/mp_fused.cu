@@ -881,7 +881,7 @@ template <int CQ, int H>
 int mp_launch(const MpParams& p, bool save, cudaStream_t stream) {
     using G = MpGeom<CQ, H, kMpThreads>;
     auto go = [&](auto kernel) -> int {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        cudaError_t e = ensure_dyn_smem((const void*)kernel, (size_t)(G::SMEM));
         if (e != cudaSuccess) { set_error("glam_message_stack_fwd: cudaFuncSetAttribute(%d bytes): %s", G::SMEM, cudaGetErrorString(e)); return (int)e; }
         kernel<<<kNumSMs, kMpThreads, G::SMEM, stream>>>(p);
         return 0;

@@ -101,6 +101,7 @@ struct BwParams {
     float* G_GI; float* G_GH; float* G_PRE; float* G_XPE; float* g_x0;
     float* G4;                                        // [steps][N][4C] = g_r | g_z | g_n | g_n r (replaces G_GI / G_GH), or NULL
     float* g_h0;                                      // separate gradient of the initial GRU state (h0 was its own tensor), or NULL
+    int pre_act; float pre_act_param;                 // activation of the input LinearBlock the forward applied (x0 = act(..)): g_x0 *= act'(x0)
     float* partial;                                   // [grid][De*HC + De*H]
     unsigned long long* phase_clock;                  // profiling aid (glam_message_stack_phase_clock), or NULL
 };
@@ -657,6 +658,11 @@ mp_fused_bwd_kernel(const BwParams p) {
                 const float4 gh = add4(tmem_ld4v(lane_base + G::TM_H + 4 * j), tmem_ld4v(lane_base + G::TM_GHZ + 4 * j));
                 if (p.res) g = add4(g, tmem_ld4v(lane_base + G::TM_GID + 4 * j));
                 if (!p.g_h0) g = add4(g, gh);                // h0 == x0 (layer.py:253-254): one tensor, one gradient
+                if (p.pre_act && row < nd) {                 // through the input LinearBlock's activation: what leaves is d/d(pre-activation)
+                    const float4 x0v = *reinterpret_cast<const float4*>(p.X + (size_t)(n0 + row) * C + 4 * j);
+                    g.x *= act_grad_from_out(x0v.x, p.pre_act, p.pre_act_param); g.y *= act_grad_from_out(x0v.y, p.pre_act, p.pre_act_param);
+                    g.z *= act_grad_from_out(x0v.z, p.pre_act, p.pre_act_param); g.w *= act_grad_from_out(x0v.w, p.pre_act, p.pre_act_param);
+                }
                 if (row < nd) {
                     *reinterpret_cast<float4*>(p.g_x0 + (size_t)(n0 + row) * C + 4 * j) = g;
                     if (p.g_h0) *reinterpret_cast<float4*>(p.g_h0 + (size_t)(n0 + row) * C + 4 * j) = gh;
@@ -702,7 +708,7 @@ template <int CQ, int H>
 int bwd_launch(const BwParams& p, const float* w_ih, const float* w_hh, uint8_t* image, cudaStream_t stream) {
     using G = BwGeom<CQ, H>;
     bw_image_kernel<CQ, H><<<8, 256, 0, stream>>>(w_ih, w_hh, image);
-    cudaError_t e = cudaFuncSetAttribute(mp_fused_bwd_kernel<CQ, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    cudaError_t e = ensure_dyn_smem((const void*)mp_fused_bwd_kernel<CQ, H>, (size_t)(G::SMEM));
     if (e != cudaSuccess) { set_error("glam_message_stack_bwd: cudaFuncSetAttribute(%d bytes): %s", G::SMEM, cudaGetErrorString(e)); return (int)e; }
     mp_fused_bwd_kernel<CQ, H><<<kNumSMs, kBwThreads, G::SMEM, stream>>>(p);
     return 0;
@@ -734,7 +740,8 @@ extern "C" int glam_message_stack_bwd(const float* save_x, const float* save_h, 
                                       const float* w_hh, const int32_t* tiles, const int32_t* tile_meta, const int32_t* dst_rowptr,
                                       const int32_t* dst_src, const uint8_t* etype, const int32_t* src_rowptr, const int32_t* src_pos,
                                       const int32_t* src_dst, int64_t num_nodes, int64_t num_edges, int channels, int heads,
-                                      int edge_dim, int steps, float negative_slope, int act, float act_param, int res, float* g_gi,
+                                      int edge_dim, int steps, float negative_slope, int act, float act_param, int res, int pre_act,
+                                      float pre_act_param, float* g_gi,
                                       float* g_gh, float* g4, float* g_pre, float* g_xpe, float* g_x0, float* g_h0, float* g_w_edge, float* g_att_edge,
                                       void* workspace, size_t workspace_bytes, void* stream_) {
     GLAM_REQUIRE(glam_message_stack_bwd_supported(channels, heads, edge_dim, steps),
@@ -753,6 +760,8 @@ extern "C" int glam_message_stack_bwd(const float* save_x, const float* save_h, 
                  tiles && tile_meta && dst_rowptr && src_rowptr && (g4 || (g_gi && g_gh)) && g_pre && g_xpe && g_x0 && workspace &&
                  (num_edges == 0 || (save_alpha && dst_src && etype && src_pos && src_dst)),
                  "glam_message_stack_bwd: null pointer");
+    GLAM_REQUIRE(pre_act == ACT_NONE || (save_x && !g_h0 && pre_act >= ACT_RELU && pre_act <= ACT_CELU),
+                 "glam_message_stack_bwd: pre_act needs save_x (x0 = the activated input projection) and the combined g_x0");
     GLAM_REQUIRE(ldw == ld, "glam_message_stack_bwd: w_ext pitch %lld, expected %d", (long long)ldw, ld);
     GLAM_REQUIRE(workspace_bytes >= glam_message_stack_bwd_workspace_bytes(channels, heads, edge_dim) && al16b(workspace),
                  "glam_message_stack_bwd: workspace too small or not 16-byte aligned");
@@ -775,6 +784,7 @@ extern "C" int glam_message_stack_bwd(const float* save_x, const float* save_h, 
     p.src_rowptr = src_rowptr; p.src_pos = src_pos; p.src_dst = src_dst; p.N = num_nodes; p.E = num_edges; p.De = edge_dim;
     p.steps = steps; p.act = act; p.res = res; p.slope = negative_slope; p.act_param = act_param;
     p.G_GI = g_gi; p.G_GH = g_gh; p.G4 = g4; p.G_PRE = g_pre; p.G_XPE = g_xpe; p.g_x0 = g_x0; p.g_h0 = g_h0; p.phase_clock = g_mp_phase_clock;
+    p.pre_act = pre_act; p.pre_act_param = pre_act_param;
     int rc = 0;
     switch (channels) {
         case 32: rc = bwd_launch<8, 3>(p, w_ih, w_hh, image, stream); break;

@@ -16,7 +16,7 @@ __global__ void triplet_prep_fwd_kernel(const float* __restrict__ wn, const floa
     const int HC = H * C;
     const int att_ld = light ? 2 * C + De : 3 * C;
     const int aj_off = light ? C + De : 2 * C;
-    for (int idx = threadIdx.x; idx < C * ldxp; idx += blockDim.x) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < C * ldxp; idx += gridDim.x * blockDim.x) {
         const int k = idx / ldxp, n = idx - k * ldxp;
         float v = 0.f;
         if (n < HC) v = wn[k * HC + n];
@@ -27,7 +27,7 @@ __global__ void triplet_prep_fwd_kernel(const float* __restrict__ wn, const floa
         }
         w_ext[idx] = v;
     }
-    for (int idx = threadIdx.x; idx < De * H; idx += blockDim.x) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < De * H; idx += gridDim.x * blockDim.x) {
         const int d = idx / H, h = idx - d * H;
         float v = 0.f;
         if (light) v = att[C + d];
@@ -45,14 +45,14 @@ __global__ void triplet_prep_bwd_kernel(const float* __restrict__ wn, const floa
     const int HC = H * C;
     const int att_ld = light ? 2 * C + De : 3 * C;
     const int aj_off = light ? C + De : 2 * C;
-    for (int idx = threadIdx.x; idx < C * HC; idx += blockDim.x) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < C * HC; idx += gridDim.x * blockDim.x) {
         const int k = idx / HC, n = idx - k * HC, h = n / C, c = n - h * C;
         float v = g_w_ext[k * ldxp + n];
         v = fmaf(g_w_ext[k * ldxp + HC + h], att[h * att_ld + c], v);
         v = fmaf(g_w_ext[k * ldxp + HC + H + h], att[h * att_ld + aj_off + c], v);
         g_wn[idx] = v;
     }
-    for (int idx = threadIdx.x; idx < H * C; idx += blockDim.x) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < H * C; idx += gridDim.x * blockDim.x) {
         const int h = idx / C, c = idx - h * C;
         float gi = 0.f, gj = 0.f;
         for (int k = 0; k < C; ++k) {
@@ -69,9 +69,9 @@ __global__ void triplet_prep_bwd_kernel(const float* __restrict__ wn, const floa
         }
     }
     if (light) {
-        for (int d = threadIdx.x; d < De; d += blockDim.x) g_att[C + d] = g_att_edge[d];
+        for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < De; d += gridDim.x * blockDim.x) g_att[C + d] = g_att_edge[d];
     } else {
-        for (int idx = threadIdx.x; idx < De * HC; idx += blockDim.x) {
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < De * HC; idx += gridDim.x * blockDim.x) {
             const int d = idx / HC, n = idx - d * HC, h = n / C, c = n - h * C;
             g_we[idx] = fmaf(g_att_edge[d * H + h], att[h * att_ld + C + c], g_we_direct ? g_we_direct[idx] : 0.f);
         }
@@ -87,7 +87,7 @@ extern "C" int glam_triplet_prep_fwd(const float* weight_node, const float* weig
     GLAM_REQUIRE(C > 0 && H > 0 && De > 0 && ldxp >= H * C + 2 * H, "glam_triplet_prep_fwd: bad shape");
     GLAM_REQUIRE(!light || H == 1, "glam_triplet_prep_fwd: the Light layer is single-head");
     GLAM_REQUIRE(weight_node && att && w_ext && att_edge && (light || weight_edge), "glam_triplet_prep_fwd: null pointer");
-    triplet_prep_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream_>>>(weight_node, weight_edge, att, C, H, De, light, ldxp, w_ext, att_edge);
+    triplet_prep_fwd_kernel<<<(unsigned)((C * ldxp + 127) / 128), 128, 0, (cudaStream_t)stream_>>>(weight_node, weight_edge, att, C, H, De, light, ldxp, w_ext, att_edge);
     GLAM_CHECK_LAUNCH();
     return 0;
 }
@@ -99,7 +99,7 @@ extern "C" int glam_triplet_prep_bwd(const float* weight_node, const float* weig
     GLAM_REQUIRE(C > 0 && H > 0 && De > 0 && ldxp >= H * C + 2 * H, "glam_triplet_prep_bwd: bad shape");
     GLAM_REQUIRE(weight_node && att && g_w_ext && g_att_edge && g_weight_node && g_att, "glam_triplet_prep_bwd: null pointer");
     GLAM_REQUIRE(light || (weight_edge && g_weight_edge), "glam_triplet_prep_bwd: null edge pointers");
-    triplet_prep_bwd_kernel<<<1, 1024, 0, (cudaStream_t)stream_>>>(weight_node, weight_edge, att, g_w_ext, g_att_edge, g_w_edge_direct, C,
+    triplet_prep_bwd_kernel<<<(unsigned)((C * H * C + 127) / 128), 128, 0, (cudaStream_t)stream_>>>(weight_node, weight_edge, att, g_w_ext, g_att_edge, g_w_edge_direct, C,
                                                                    H, De, light, ldxp, g_weight_node, g_weight_edge, g_att);
     GLAM_CHECK_LAUNCH();
     return 0;

@@ -225,7 +225,7 @@ extern "C" int glam_seg_attn_pool_fwd(const float* x, int64_t ldx, const float* 
     if (B == 0) return 0;
     GLAM_REQUIRE(x && q && graph_ptr && a && r, "glam_seg_attn_pool_fwd: null pointer");
     // (the attribute is per DEVICE: set on every call — a process-wide "configured" flag broke the second GPU of a process)
-    cudaFuncSetAttribute(seg_attn_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmem);
+    ensure_dyn_smem((const void*)seg_attn_pool_fwd_kernel, (size_t)((int)kPoolSmem));
     seg_attn_pool_fwd_kernel<<<pool_grid(B), kPoolWarps * 32, kPoolSmem, (cudaStream_t)stream_>>>(x, ldx, q, q_stride, q_bias, graph_ptr,
                                                                                                 B, C, a, r, ldr, asum);
     GLAM_CHECK_LAUNCH();
@@ -239,7 +239,7 @@ extern "C" int glam_seg_attn_pool_bwd(const float* x, int64_t ldx, const float* 
     GLAM_REQUIRE(B >= 0 && C > 0 && C <= 1024 && ldx >= C && ldgr >= C && ldgx >= C, "glam_seg_attn_pool_bwd: bad shape");
     if (B == 0) return 0;
     GLAM_REQUIRE(x && q && a && g_r && graph_ptr && g_x && g_q && g_e, "glam_seg_attn_pool_bwd: null pointer");
-    cudaFuncSetAttribute(seg_attn_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmem);
+    ensure_dyn_smem((const void*)seg_attn_pool_bwd_kernel, (size_t)((int)kPoolSmem));
     seg_attn_pool_bwd_kernel<<<pool_grid(B), kPoolWarps * 32, kPoolSmem, (cudaStream_t)stream_>>>(x, ldx, q, q_stride, a, g_r, ldgr, g_asum,
                                                                                                 graph_ptr, B, C, accumulate, g_x,
                                                                                                 ldgx, g_q, g_e);

@@ -275,6 +275,189 @@ __device__ __forceinline__ void column_sums(const float* tile, int lane, int row
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Chunk-per-lane path for graphs of <= 32 nodes (every molecule): a lane owns one 16-byte chunk of the row, so a warp
+// load covers RP = 32 / (C/4) consecutive rows of the graph as ONE contiguous span (4 lines instead of 32 per request),
+// the rows stay in registers for both passes, row dots are segmented shuffles over the C/4 lanes of a row, and the
+// per-graph sums (r, g_h) are register accumulations reduced over the RP row groups — no shared-memory tile at all.
+// ---------------------------------------------------------------------------------------------------------------
+template <int CH>
+__device__ __forceinline__ float seg_sum(float v, int q, int seg_base) {
+    constexpr int P2 = CH >= 16 ? 16 : CH >= 8 ? 8 : CH >= 4 ? 4 : CH >= 2 ? 2 : 1;
+    if (CH > P2) { const float t = __shfl_down_sync(0xffffffffu, v, P2); if (q + P2 < CH) v += t; }
+#pragma unroll
+    for (int off = P2 / 2; off >= 1; off >>= 1) { const float t = __shfl_down_sync(0xffffffffu, v, off); if (q < off) v += t; }
+    return __shfl_sync(0xffffffffu, v, seg_base);
+}
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+// sum of a per-row-group float4 over the RP groups, valid in the lanes of group 0 (fixed order)
+template <int CH, int RP>
+__device__ __forceinline__ float4 group_sum4(float4 v, int rg) {
+#pragma unroll
+    for (int r = 1; r < RP; ++r) {
+        const float tx = __shfl_down_sync(0xffffffffu, v.x, r * CH), ty = __shfl_down_sync(0xffffffffu, v.y, r * CH);
+        const float tz = __shfl_down_sync(0xffffffffu, v.z, r * CH), tw = __shfl_down_sync(0xffffffffu, v.w, r * CH);
+        if (rg == 0) { v.x += tx; v.y += ty; v.z += tz; v.w += tw; }
+    }
+    return v;
+}
+
+template <int C4>
+__device__ __forceinline__ void set2set_fwd_small(const S2SRoundFwd& p, int64_t g, int n0, int n, int lane, float* h) {
+    constexpr int C = 4 * C4, CH = C4, RP = 32 / CH, MAXP = (32 + RP - 1) / RP;
+    const int q = lane % CH, rg = lane / CH, seg_base = rg * CH;
+    const bool live = rg < RP;
+    float4 xq[MAXP];
+#pragma unroll
+    for (int pp = 0; pp < MAXP; ++pp) {
+        const int i = pp * RP + rg;
+        xq[pp] = (live && i < n) ? __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)(n0 + i) * p.ldx) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float* gr = p.gates + g * 4 * C;
+    float hv[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int k = lane + 32 * j;
+        if (k < C) {
+            const float i_ = sigmoidf_(gr[k]), f_ = sigmoidf_(gr[C + k]), g_ = tanhf(gr[2 * C + k]), o_ = sigmoidf_(gr[3 * C + k]);
+            const float cn = f_ * p.c_prev[g * C + k] + i_ * g_;
+            gr[k] = i_; gr[C + k] = f_; gr[2 * C + k] = g_; gr[3 * C + k] = o_;
+            p.c_new[g * C + k] = cn;
+            hv[j] = o_ * tanhf(cn);
+            h[k] = hv[j];
+        }
+    }
+    __syncwarp();
+    const float4 h4 = live ? *reinterpret_cast<const float4*>(h + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float e[MAXP], mx = -INFINITY;
+#pragma unroll
+    for (int pp = 0; pp < MAXP; ++pp) {
+        e[pp] = seg_sum<CH>(dot4(xq[pp], h4), q, seg_base);
+        if (live && pp * RP + rg < n) mx = fmaxf(mx, e[pp]);
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < RP; ++r) m = fmaxf(m, __shfl_sync(0xffffffffu, mx, r * CH));
+    float sl = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < MAXP; ++pp) {
+        e[pp] = (live && pp * RP + rg < n) ? expf(e[pp] - m) : 0.f;
+        sl += e[pp];
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < RP; ++r) sum += __shfl_sync(0xffffffffu, sl, r * CH);
+    sum += 1e-16f;
+    float* att_s = p.att + n0;
+    float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int pp = 0; pp < MAXP; ++pp) {
+        const float a = e[pp] / sum;
+        const int i = pp * RP + rg;
+        if (live && q == 0 && i < n) att_s[i] = a;
+        racc.x = fmaf(a, xq[pp].x, racc.x); racc.y = fmaf(a, xq[pp].y, racc.y);
+        racc.z = fmaf(a, xq[pp].z, racc.z); racc.w = fmaf(a, xq[pp].w, racc.w);
+    }
+    racc = group_sum4<CH, RP>(racc, rg);
+    float* un = p.u_next + g * 3 * C;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int k = lane + 32 * j;
+        if (k < C) {
+            un[k] = hv[j]; un[2 * C + k] = hv[j];
+            if (p.q_star) p.q_star[g * 2 * C + k] = hv[j];
+        }
+    }
+    if (rg == 0) {
+        const float rv[4] = {racc.x, racc.y, racc.z, racc.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            un[C + 4 * q + u] = rv[u];
+            if (p.q_star) p.q_star[g * 2 * C + C + 4 * q + u] = rv[u];
+        }
+    }
+}
+
+template <int C4>
+__device__ __forceinline__ void set2set_bwd_small(const S2SRoundBwd& p, int64_t g, int n0, int n, int lane, float* h, float* g_r) {
+    constexpr int C = 4 * C4, CH = C4, RP = 32 / CH, MAXP = (32 + RP - 1) / RP;
+    const int q = lane % CH, rg = lane / CH, seg_base = rg * CH;
+    const bool live = rg < RP;
+    float4 xq[MAXP];
+#pragma unroll
+    for (int pp = 0; pp < MAXP; ++pp) {
+        const int i = pp * RP + rg;
+        xq[pp] = (live && i < n) ? __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)(n0 + i) * p.ldx) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float a_mine = lane < n ? p.att[n0 + lane] : 0.f;
+    const float* gs = p.gates + g * 4 * C;
+    const float* gu = p.g_u + g * p.ldgu;
+    float gh[2] = {0.f, 0.f}, tc[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int k = lane + 32 * j;
+        if (k < C) {
+            tc[j] = tanhf(p.c_new[g * C + k]);
+            h[k] = gs[3 * C + k] * tc[j];
+            gh[j] = gu[k] + (p.gu_cols == 3 * C ? gu[2 * C + k] : 0.f);
+            g_r[k] = gu[C + k];
+        }
+    }
+    __syncwarp();
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 h4 = live ? *reinterpret_cast<const float4*>(h + 4 * q) : zero4;
+    const float4 r4 = live ? *reinterpret_cast<const float4*>(g_r + 4 * q) : zero4;
+    float ga[MAXP], a[MAXP], part = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < MAXP; ++pp) {
+        ga[pp] = seg_sum<CH>(dot4(xq[pp], r4), q, seg_base);
+        const int i = pp * RP + rg;
+        a[pp] = __shfl_sync(0xffffffffu, a_mine, i < 32 ? i : 31);
+        if (!(live && i < n)) a[pp] = 0.f;
+        part = fmaf(a[pp], ga[pp], part);
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int r = 0; r < RP; ++r) dot += __shfl_sync(0xffffffffu, part, r * CH);
+    float4 hacc = zero4;
+#pragma unroll
+    for (int pp = 0; pp < MAXP; ++pp) {
+        const float ge = a[pp] * (ga[pp] - dot);
+        const int i = pp * RP + rg;
+        if (live && i < n) {
+            float4 v = make_float4(fmaf(a[pp], r4.x, ge * h4.x), fmaf(a[pp], r4.y, ge * h4.y), fmaf(a[pp], r4.z, ge * h4.z), fmaf(a[pp], r4.w, ge * h4.w));
+            float4* dst = reinterpret_cast<float4*>(p.g_x + (int64_t)(n0 + i) * C) + q;
+            // earlier rounds' g_x: a 16-byte reduction at L2, no read back (one adder per element and launch: deterministic)
+            if (p.accumulate) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            else *dst = v;
+        }
+        hacc.x = fmaf(ge, xq[pp].x, hacc.x); hacc.y = fmaf(ge, xq[pp].y, hacc.y);
+        hacc.z = fmaf(ge, xq[pp].z, hacc.z); hacc.w = fmaf(ge, xq[pp].w, hacc.w);
+    }
+    hacc = group_sum4<CH, RP>(hacc, rg);
+    __syncwarp();                                          // every lane holds its g_r chunk in registers: the slot is free
+    if (rg == 0) *reinterpret_cast<float4*>(g_r + 4 * q) = hacc;
+    __syncwarp();
+    float* Gr = p.G + g * 4 * C;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int k = lane + 32 * j;
+        if (k < C) {
+            const float ghk = gh[j] + g_r[k];
+            const float i_ = gs[k], f_ = gs[C + k], gg = gs[2 * C + k], o_ = gs[3 * C + k];
+            const float gc = p.g_c[g * C + k] + ghk * o_ * (1.f - tc[j] * tc[j]);
+            Gr[k] = gc * gg * i_ * (1.f - i_);
+            Gr[C + k] = gc * p.c_prev[g * C + k] * f_ * (1.f - f_);
+            Gr[2 * C + k] = gc * i_ * (1.f - gg * gg);
+            Gr[3 * C + k] = ghk * tc[j] * o_ * (1.f - o_);
+            p.g_c[g * C + k] = gc * f_;
+        }
+    }
+}
+
 template <int C4>
 __global__ void __launch_bounds__(kS2SWarps * 32)
 set2set_round_fwd_rows_kernel(const S2SRoundFwd p) {
@@ -286,6 +469,7 @@ set2set_round_fwd_rows_kernel(const S2SRoundFwd p) {
     const int64_t g = (int64_t)blockIdx.x * kS2SWarps + wid;
     if (g >= p.B) return;
     const int n0 = p.gptr[g], n = p.gptr[g + 1] - n0;
+    if (n <= 32) { set2set_fwd_small<C4>(p, g, n0, n, lane, h); return; }
     const int nch = (n + 31) >> 5;
     float4 xr[C4];
     if (lane < n) load_row<C4>(xr, p.x + (int64_t)(n0 + lane) * p.ldx);          // in flight while the cell is computed
@@ -364,6 +548,7 @@ set2set_round_bwd_rows_kernel(const S2SRoundBwd p) {
     const int64_t g = (int64_t)blockIdx.x * kS2SWarps + wid;
     if (g >= p.B) return;
     const int n0 = p.gptr[g], n = p.gptr[g + 1] - n0;
+    if (n <= 32) { set2set_bwd_small<C4>(p, g, n0, n, lane, h, g_r); return; }
     const int nch = (n + 31) >> 5;
     float4 xr[C4], old[C4];
     if (lane < n) load_row<C4>(xr, p.x + (int64_t)(n0 + lane) * p.ldx);
@@ -466,14 +651,14 @@ extern "C" int glam_set2set_round_fwd(const float* x, int64_t ldx, const int32_t
         const unsigned grid_r = (unsigned)((num_graphs + kS2SWarps - 1) / kS2SWarps);
         S2S_ROWS_DISPATCH(channels, {
             const size_t sm = s2s_rows_smem<C4>(false);
-            cudaFuncSetAttribute(set2set_round_fwd_rows_kernel<C4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            ensure_dyn_smem((const void*)set2set_round_fwd_rows_kernel<C4>, (size_t)((int)sm));
             set2set_round_fwd_rows_kernel<C4><<<grid_r, kS2SWarps * 32, sm, (cudaStream_t)stream_>>>(p);
         })
         GLAM_CHECK_LAUNCH();
         return 0;
     }
     const size_t smem = sizeof(float) * kS2SWarps * (size_t)(kS2STileFloats + 2 * channels);
-    cudaFuncSetAttribute(set2set_round_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dyn_smem((const void*)set2set_round_fwd_kernel, (size_t)((int)smem));
     const unsigned grid = (unsigned)((num_graphs + kS2SWarps - 1) / kS2SWarps);
     set2set_round_fwd_kernel<<<grid, kS2SWarps * 32, smem, (cudaStream_t)stream_>>>(p);
     GLAM_CHECK_LAUNCH();
@@ -494,14 +679,14 @@ extern "C" int glam_set2set_round_bwd(const float* x, int64_t ldx, const int32_t
         const unsigned grid_r = (unsigned)((num_graphs + kS2SWarps - 1) / kS2SWarps);
         S2S_ROWS_DISPATCH(channels, {
             const size_t sm = s2s_rows_smem<C4>(true);
-            cudaFuncSetAttribute(set2set_round_bwd_rows_kernel<C4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            ensure_dyn_smem((const void*)set2set_round_bwd_rows_kernel<C4>, (size_t)((int)sm));
             set2set_round_bwd_rows_kernel<C4><<<grid_r, kS2SWarps * 32, sm, (cudaStream_t)stream_>>>(p);
         })
         GLAM_CHECK_LAUNCH();
         return 0;
     }
     const size_t smem = sizeof(float) * kS2SWarps * (size_t)(kS2STileFloats + 3 * channels);
-    cudaFuncSetAttribute(set2set_round_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dyn_smem((const void*)set2set_round_bwd_kernel, (size_t)((int)smem));
     const unsigned grid = (unsigned)((num_graphs + kS2SWarps - 1) / kS2SWarps);
     set2set_round_bwd_kernel<<<grid, kS2SWarps * 32, smem, (cudaStream_t)stream_>>>(p);
     GLAM_CHECK_LAUNCH();

@@ -480,7 +480,7 @@ int tc_gemm_launch(const float* X, int64_t ldx, const float* W, int64_t w_sk, in
     CUtensorMap tmap;
     if (int rc = make_tmap_rows(&tmap, X, M, K, ldx, kTileM, (int)CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     {                                                            // the attribute is per device: set it on every call
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_dyn_smem((const void*)tc_gemm_kernel, (size_t)((int)smem));
         if (e != cudaSuccess) { set_error("tc_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     }
     const int64_t ntiles = (M + kTileM - 1) / kTileM;

@@ -238,7 +238,7 @@ int tc_gemm_tn_launch(const float* A, int64_t lda, const float* B, int64_t ldb, 
     if (int rc = make_tmap_rows(&tp, P, M, p.Wp, ldp, kTnRows, (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     if (int rc = make_tmap_rows(&tq, Q, M, p.Wq, ldq, kTnRows, (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     {   // (per DEVICE attribute: set on every launch)
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_dyn_smem((const void*)tc_gemm_tn_kernel, (size_t)((int)smem));
         if (e != cudaSuccess) { set_error("tc_gemm_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     }
     tc_gemm_tn_kernel<<<grid, kTnThreads, smem, stream>>>(tp, tq, p);

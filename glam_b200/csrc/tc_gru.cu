@@ -329,7 +329,7 @@ extern "C" int glam_gru_fused_fwd(const float* m, int64_t ldm, const float* h, i
     const int64_t ntiles = (N + kGruTileM - 1) / kGruTileM;
     const int64_t grid = ntiles < kNumSMs ? ntiles : kNumSMs;
     auto launch = [&](auto kernel) -> int {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_dyn_smem((const void*)kernel, (size_t)((int)smem));
         if (e != cudaSuccess) { set_error("glam_gru_fused_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         kernel<<<(unsigned)grid, kGruThreads, smem, (cudaStream_t)stream_>>>(tm, th, p);
         return 0;

@@ -384,7 +384,7 @@ static int pick_kpl(int HC) {
 template <typename F>
 static cudaError_t allow_smem(F fn, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return ensure_dyn_smem((const void*)fn, (size_t)((int)bytes));
 }
 
 bool edge_vec_eligible(const float* xpe, int64_t ldxp, int heads, int C, int De, const float* a1, const float* a2);

@@ -736,7 +736,7 @@ static void vec_geometry(int nq, int* G, int* cpl) {
 
 template <typename F>
 static void vec_allow_smem(F fn, size_t bytes) {
-    if (bytes > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (bytes > 48 * 1024) ensure_dyn_smem((const void*)fn, (size_t)((int)bytes));
 }
 
 int edge_vec_fwd(const float* xpe, int64_t ldxp, const float* ea, const float* w_edge, const float* att_edge,

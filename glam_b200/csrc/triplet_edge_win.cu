@@ -1140,7 +1140,7 @@ bool edge_win_eligible(int heads, int C, int De, int64_t ldxp) {
 
 template <typename F>
 static void win_allow_smem(F fn, size_t bytes) {
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    ensure_dyn_smem((const void*)fn, (size_t)((int)bytes));
     cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 

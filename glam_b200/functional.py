@@ -270,20 +270,30 @@ class MessageBlockFn(Function):
 class MessageStackFn(Function):
     @staticmethod
     def forward(ctx, x0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, ea, g,
-                heads, channels, slope, act, act_param, res, steps, p_drop, fi, pn=None):
-        """pn = (graph_ptr, num_graphs, eps): PairNorm on every step's block input (src_1gp/layer.py:255) inside the node."""
+                heads, channels, slope, act, act_param, res, steps, p_drop, fi, pn=None, w_pre=None, b_pre=None, pre_act=None):
+        """pn = (graph_ptr, num_graphs, eps): PairNorm on every step's block input (src_1gp/layer.py:255) inside the node.
+        w_pre / b_pre / pre_act = (code, param): the model's input LinearBlock (src_1gp/model.py:49) applied inside the one-launch
+        kernels — x0 is then the RAW feature matrix [N, raw_dim] and the node also returns that block's weight / bias gradients
+        (only offered by run_steps when both one-launch kernels take the batch)."""
         (x0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh) = map(
             _c, (x0, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh))
         ops._need_cuda(x0, w_ext)
-        N, C = x0.shape
+        N, C = x0.shape[0], channels
         S, H, HC, ld, E, dev = steps, heads, heads * channels, w_ext.shape[1], ea.shape[0], x0.device
+        ctx.pre = None
+        if w_pre is not None:
+            assert fi is not None and p_drop == 0.0 and pn is None
+            w_pre, b_pre = _c(w_pre), (None if b_pre is None else _c(b_pre))
+            ctx.pre = (x0, b_pre is not None, pre_act)
         if fi is not None and p_drop == 0.0 and pn is None:
             # ONE launch for all steps (csrc/mp_fused.cu): x and h stay in shared memory from step to step; what backward
             # reads leaves the SM as tile-sized contiguous copies
             fused_bwd = (USE_FUSED_BWD and g.src_rowptr is not None and ops.message_stack_bwd_supported(channels, H, ea.shape[1], S))
             sv = _stack_buffers(x0, S, H, channels, ld, E, tiled_gates=fused_bwd)
+            assert fused_bwd or w_pre is None
             ops.message_stack_fwd(x0, None, w_ext, w_edge, att_edge, w_scale, bias, w_ih, w_hh, b_ih, b_hh, g, fi, H, channels, S,
-                                  slope, act, act_param, res, save=sv)
+                                  slope, act, act_param, res, save=sv,
+                                  pre=None if w_pre is None else (w_pre, b_pre, pre_act[0], pre_act[1]))
             X, HH = sv["X"], sv["HH"]
             ctx.save_for_backward(w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, ea, X, HH, X, None, sv["XPE"], sv["AGG"],
                                   sv["ALPHA"], sv.get("M"), sv.get("RZN"), sv.get("GH"), None)
@@ -345,7 +355,8 @@ class MessageStackFn(Function):
             sv = dict(X=X, HH=HH, XPE=XPE, ALPHA=ALPHA, M=M, RZN=RZN, GH=GH, GT=gt)
             g_x0, g_w_edge, g_att_edge = ops.message_stack_bwd(sv, list(grads[:S]), _c(grads[S]), w_ext, w_edge, att_edge, w_scale,
                                                                w_ih, w_hh, g, fi, H, C, S, slope, act, act_param, res,
-                                                               G_GI, G_GH, G_PRE, G_XPE, G4=G4)
+                                                               G_GI, G_GH, G_PRE, G_XPE, G4=G4,
+                                                               pre_act=(ops.ACT_NONE, 0.0) if ctx.pre is None else ctx.pre[2])
         else:
             G_GI, G_GH, G4, mh = new(S, N, 3 * C), new(S, N, 3 * C), None, None
             G_LOGIT, G_WE = new(S, E, H), new(S, De, HC)
@@ -392,8 +403,15 @@ class MessageStackFn(Function):
         if not fused_bwd:
             g_att_edge, _ = ops.gemm_tn_ex(ea, G_LOGIT.sum(0) if S > 1 else G_LOGIT[0])
             g_w_edge = G_WE.sum(0) if S > 1 else G_WE[0]
+        g_w_pre = g_b_pre = None
+        if getattr(ctx, "pre", None) is not None:
+            # g_x0 left the kernel as the gradient of the input LinearBlock's pre-activation rows: its weight / bias gradients
+            # are one skinny exact contraction with the raw features, which themselves need no gradient
+            x_raw, has_bias, _ = ctx.pre
+            g_w_pre, g_b_pre = ops.gemm_tn_ex(x_raw, g_x0, transpose_out=True, want_colsum=has_bias)
+            g_x0 = None
         return (g_x0, g_w_ext, g_w_edge, g_att_edge, g_w_scale, g_bias, g_w_ih, g_w_hh, g_b_ih, g_b_hh,
-                None, None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None, g_w_pre, g_b_pre, None)
 
 
 # --------------------------------------------------------------------------------------------------

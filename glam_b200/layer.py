@@ -533,10 +533,14 @@ class MessageBlock(nn.Module):
         `pre`: the LinearBlock that produces this block's input (src_1gp/model.py:49) — `x` is then ITS input (the raw
         features); in evaluation it is applied inside the fused kernel, otherwise simply called first."""
         inner = getattr(self.conv, "conv", None)
-        pre_fused = None
+        pre_fused = pre_train = pre_block = None
         if pre is not None:
-            pre_fused = pre.fusable_into_stack(x) if (x.is_cuda and not _wants_grad(x, *self.parameters(), *pre.parameters())) else None
-            if pre_fused is None:
+            can = pre.fusable_into_stack(x) if (x.is_cuda and not _wants_grad(x)) else None
+            if can is not None and _wants_grad(*self.parameters(), *pre.parameters()):
+                pre_train, pre_block = can, pre                  # decided below, once the batch's tile index is known
+            else:
+                pre_fused = can
+            if can is None:
                 x, pre = pre(x, batch=batch), None
         width = pre.linear.out_features if pre is not None else x.shape[1]
         fused = _fusable_act(self.act, self.training)
@@ -577,13 +581,23 @@ class MessageBlock(nn.Module):
             return list(x_out.unbind(0)), h_out.unsqueeze(0)
         if pn is not None:
             fi = None                                            # (the training-mode fused pair has no PairNorm)
-        if pre is not None:
+        if pre_fused is not None:
             x = pre(x, batch=batch)
         ea = g.sorted_edge_attr(edge_attr)
+        pre_args = (None, None, None)
+        if pre_train is not None:
+            # training: the input LinearBlock runs inside the one-launch pair too when both kernels take this batch (its
+            # weight / bias gradients come back from the same autograd node); otherwise it is simply called first
+            if (fi is not None and Fn.USE_FUSED_BWD and g.src_rowptr is not None
+                    and ops.message_stack_bwd_supported(inner.node_channels, inner.heads, ea.shape[1], int(steps))):
+                pre_args = (pre_train[0], pre_train[1], (pre_train[2], pre_train[3]))
+            else:
+                x = pre_block(x, batch=batch)
         out = Fn.MessageStackFn.apply(
             x, w_ext, inner.weight_edge, att_edge, inner.weight_scale, inner.bias,
             gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, ea, g,
-            inner.heads, inner.node_channels, inner.negative_slope, fused[0], fused[1], bool(self.res), int(steps), p_drop, fi, pn)
+            inner.heads, inner.node_channels, inner.negative_slope, fused[0], fused[1], bool(self.res), int(steps), p_drop, fi, pn,
+            *pre_args)
         xs = list(out[:steps])
         return (xs if keep == "all" else xs[-1:]), out[steps].unsqueeze(0)
 

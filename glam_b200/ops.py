@@ -343,11 +343,12 @@ def message_stack_bwd_supported(channels: int, heads: int, edge_dim: int, steps:
 
 
 def message_stack_bwd(sv, g_ext, g_h_final, w_ext, w_edge, att_edge, w_scale, w_ih, w_hh, g, fi, heads, channels, steps, slope, act,
-                      act_param, res, G_GI, G_GH, G_PRE, G_XPE, separate_h0=False, G4=None):
+                      act_param, res, G_GI, G_GH, G_PRE, G_XPE, separate_h0=False, G4=None, pre_act=(ACT_NONE, 0.0)):
     """Backward of the whole message stack in one launch (csrc/mp_fused_bwd.cu).  `sv` = the tensors message_stack_fwd saved;
     `g_ext` = per-step gradients of the step outputs (None entries allowed), `g_h_final` = gradient of the final GRU state.
     Fills G_GI, G_GH [S,N,3C], G_PRE [S,N,C], G_XPE [S,N,ld]; returns (g_x0 [N,C], g_w_edge [De,HC], g_att_edge [De,H]) — with
-    separate_h0 (the forward had its own h0 tensor) g_x0 is the pair (g_x0, g_h0)."""
+    separate_h0 (the forward had its own h0 tensor) g_x0 is the pair (g_x0, g_h0).  pre_act = (code, param) of the input
+    LinearBlock the forward applied in the kernel: g_x0 is then the gradient of that block's pre-activation rows."""
     import ctypes
     X = sv["X"]
     _need_cuda(X, w_ext)
@@ -368,7 +369,7 @@ def message_stack_bwd(sv, g_ext, g_h_final, w_ext, w_edge, att_edge, w_scale, w_
           _p(sv.get("GH")), _p(sv.get("GT")), ctypes.cast(ptrs, ctypes.c_void_p), _p(g_h_final), _p(w_ext), w_ext.stride(0), _p(w_edge), _p(att_edge), _p(w_scale),
           _p(w_ih), _p(w_hh), _p(fi.tiles), _p(fi.meta), _p(g.dst_rowptr), _p(g.dst_src), _p(fi.etype), _p(g.src_rowptr),
           _p(g.src_pos), _p(g.src_dst), N, E, channels, heads, De, steps, float(slope), act, float(act_param), 1 if res else 0,
-          _p(G_GI), _p(G_GH), _p(G4), _p(G_PRE), _p(G_XPE), _p(g_x0), _p(g_h0), _p(g_we), _p(g_ae), _p(ws), ws.numel(), _stream(X),
+          int(pre_act[0]), float(pre_act[1]), _p(G_GI), _p(G_GH), _p(G4), _p(G_PRE), _p(G_XPE), _p(g_x0), _p(g_h0), _p(g_we), _p(g_ae), _p(ws), ws.numel(), _stream(X),
           label=f"[N={N},S={steps}]")
     return ((g_x0, g_h0) if separate_h0 else g_x0), g_we, g_ae
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLAM_B200_ABI_VERSION 10
+#define GLAM_B200_ABI_VERSION 11
 #define GLAM_MAX_HEADS 4
 
 int glam_abi_version(void);
@@ -360,7 +360,10 @@ int glam_message_stack_fwd(const float* x0, const float* h0, const float* x_raw,
  *   [edge_dim][HC], g_att_edge [edge_dim][H] (= d/d att_edge of glam_triplet_prep_fwd).  needs the source-side index of
  *   glam_build_csr.  workspace >= glam_message_stack_bwd_workspace_bytes(), 16-byte aligned.  If meta[1] != 0, g_x0 and the
  *   parameter gradients are filled with NaN.  Supported: tf32 math mode, heads == 3, channels in {32,36}, edge_dim <= 4,
- *   steps <= 8. */
+ *   steps <= 8.
+ *   pre_act != 0 (ABI v11): the forward applied the model's input LinearBlock in the kernel (x_raw / w_pre, activation pre_act
+ *   with parameter pre_act_param; save_x[0] holds its output x0); g_x0 then leaves as the gradient of that block's
+ *   PRE-activation rows, g_x0 * act'(x0), ready for the block's weight / bias contraction. */
 int glam_message_stack_bwd_supported(int channels, int heads, int edge_dim, int steps);
 size_t glam_message_stack_bwd_workspace_bytes(int channels, int heads, int edge_dim);
 int glam_message_stack_bwd(const float* save_x, const float* save_h, const float* save_xpe, const float* save_alpha,
@@ -371,7 +374,8 @@ int glam_message_stack_bwd(const float* save_x, const float* save_h, const float
                            const int32_t* tile_meta, const int32_t* dst_rowptr, const int32_t* dst_src, const uint8_t* etype,
                            const int32_t* src_rowptr, const int32_t* src_pos, const int32_t* src_dst, int64_t num_nodes,
                            int64_t num_edges, int channels, int heads, int edge_dim, int steps, float negative_slope, int act,
-                           float act_param, int res, float* g_gi, float* g_gh, float* g4, float* g_pre, float* g_xpe,
+                           float act_param, int res, int pre_act, float pre_act_param, float* g_gi, float* g_gh, float* g4,
+                           float* g_pre, float* g_xpe,
                            float* g_x0, float* g_h0, float* g_w_edge, float* g_att_edge, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
