@@ -282,6 +282,10 @@ __device__ __forceinline__ void column_sums(const float* tile, int lane, int row
 // the rows stay in registers for both passes, row dots are segmented shuffles over the C/4 lanes of a row, and the
 // per-graph sums (r, g_h) are register accumulations reduced over the RP row groups — no shared-memory tile at all.
 // ---------------------------------------------------------------------------------------------------------------
+// SFU forms for this path (ex2.approx / rcp.approx: relative error ~2^-22, the same the one-launch message kernels use):
+// the accurate expf / tanhf / divisions were 40 % of the warp's instructions, and the kernel is issue-latency bound
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, fast_sigmoid(2.f * x), -1.f); }
 template <int CH>
 __device__ __forceinline__ float seg_sum(float v, int q, int seg_base) {
     constexpr int P2 = CH >= 16 ? 16 : CH >= 8 ? 8 : CH >= 4 ? 4 : CH >= 2 ? 2 : 1;
@@ -322,11 +326,11 @@ __device__ __forceinline__ void set2set_fwd_small(const S2SRoundFwd& p, int64_t 
     for (int j = 0; j < 2; ++j) {
         const int k = lane + 32 * j;
         if (k < C) {
-            const float i_ = sigmoidf_(gr[k]), f_ = sigmoidf_(gr[C + k]), g_ = tanhf(gr[2 * C + k]), o_ = sigmoidf_(gr[3 * C + k]);
+            const float i_ = fast_sigmoid(gr[k]), f_ = fast_sigmoid(gr[C + k]), g_ = fast_tanh(gr[2 * C + k]), o_ = fast_sigmoid(gr[3 * C + k]);
             const float cn = f_ * p.c_prev[g * C + k] + i_ * g_;
             gr[k] = i_; gr[C + k] = f_; gr[2 * C + k] = g_; gr[3 * C + k] = o_;
             p.c_new[g * C + k] = cn;
-            hv[j] = o_ * tanhf(cn);
+            hv[j] = o_ * fast_tanh(cn);
             h[k] = hv[j];
         }
     }
@@ -335,8 +339,11 @@ __device__ __forceinline__ void set2set_fwd_small(const S2SRoundFwd& p, int64_t 
     float e[MAXP], mx = -INFINITY;
 #pragma unroll
     for (int pp = 0; pp < MAXP; ++pp) {
-        e[pp] = seg_sum<CH>(dot4(xq[pp], h4), q, seg_base);
-        if (live && pp * RP + rg < n) mx = fmaxf(mx, e[pp]);
+        e[pp] = 0.f;
+        if (pp * RP < n) {                                   // warp-uniform: passes beyond the graph's last row are skipped
+            e[pp] = seg_sum<CH>(dot4(xq[pp], h4), q, seg_base);
+            if (live && pp * RP + rg < n) mx = fmaxf(mx, e[pp]);
+        }
     }
     float m = -INFINITY;
 #pragma unroll
@@ -344,18 +351,20 @@ __device__ __forceinline__ void set2set_fwd_small(const S2SRoundFwd& p, int64_t 
     float sl = 0.f;
 #pragma unroll
     for (int pp = 0; pp < MAXP; ++pp) {
-        e[pp] = (live && pp * RP + rg < n) ? expf(e[pp] - m) : 0.f;
+        e[pp] = (live && pp * RP + rg < n) ? __expf(e[pp] - m) : 0.f;
         sl += e[pp];
     }
     float sum = 0.f;
 #pragma unroll
     for (int r = 0; r < RP; ++r) sum += __shfl_sync(0xffffffffu, sl, r * CH);
     sum += 1e-16f;
+    const float inv_sum = __fdividef(1.f, sum);
     float* att_s = p.att + n0;
     float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int pp = 0; pp < MAXP; ++pp) {
-        const float a = e[pp] / sum;
+        if (pp * RP >= n) break;
+        const float a = e[pp] * inv_sum;
         const int i = pp * RP + rg;
         if (live && q == 0 && i < n) att_s[i] = a;
         racc.x = fmaf(a, xq[pp].x, racc.x); racc.y = fmaf(a, xq[pp].y, racc.y);
@@ -400,7 +409,7 @@ __device__ __forceinline__ void set2set_bwd_small(const S2SRoundBwd& p, int64_t 
     for (int j = 0; j < 2; ++j) {
         const int k = lane + 32 * j;
         if (k < C) {
-            tc[j] = tanhf(p.c_new[g * C + k]);
+            tc[j] = fast_tanh(p.c_new[g * C + k]);
             h[k] = gs[3 * C + k] * tc[j];
             gh[j] = gu[k] + (p.gu_cols == 3 * C ? gu[2 * C + k] : 0.f);
             g_r[k] = gu[C + k];
@@ -413,11 +422,14 @@ __device__ __forceinline__ void set2set_bwd_small(const S2SRoundBwd& p, int64_t 
     float ga[MAXP], a[MAXP], part = 0.f;
 #pragma unroll
     for (int pp = 0; pp < MAXP; ++pp) {
-        ga[pp] = seg_sum<CH>(dot4(xq[pp], r4), q, seg_base);
-        const int i = pp * RP + rg;
-        a[pp] = __shfl_sync(0xffffffffu, a_mine, i < 32 ? i : 31);
-        if (!(live && i < n)) a[pp] = 0.f;
-        part = fmaf(a[pp], ga[pp], part);
+        ga[pp] = 0.f; a[pp] = 0.f;
+        if (pp * RP < n) {                                   // warp-uniform
+            ga[pp] = seg_sum<CH>(dot4(xq[pp], r4), q, seg_base);
+            const int i = pp * RP + rg;
+            a[pp] = __shfl_sync(0xffffffffu, a_mine, i < 32 ? i : 31);
+            if (!(live && i < n)) a[pp] = 0.f;
+            part = fmaf(a[pp], ga[pp], part);
+        }
     }
     float dot = 0.f;
 #pragma unroll
@@ -425,6 +437,7 @@ __device__ __forceinline__ void set2set_bwd_small(const S2SRoundBwd& p, int64_t 
     float4 hacc = zero4;
 #pragma unroll
     for (int pp = 0; pp < MAXP; ++pp) {
+        if (pp * RP >= n) break;
         const float ge = a[pp] * (ga[pp] - dot);
         const int i = pp * RP + rg;
         if (live && i < n) {
@@ -459,7 +472,7 @@ __device__ __forceinline__ void set2set_bwd_small(const S2SRoundBwd& p, int64_t 
 }
 
 template <int C4>
-__global__ void __launch_bounds__(kS2SWarps * 32)
+__global__ void __launch_bounds__(kS2SWarps * 32, C4 <= 9 ? 3 : 1)
 set2set_round_fwd_rows_kernel(const S2SRoundFwd p) {
     constexpr int C = 4 * C4;
     extern __shared__ float smem[];
@@ -536,7 +549,7 @@ set2set_round_fwd_rows_kernel(const S2SRoundFwd p) {
 }
 
 template <int C4>
-__global__ void __launch_bounds__(kS2SWarps * 32)
+__global__ void __launch_bounds__(kS2SWarps * 32, C4 <= 9 ? 2 : 1)
 set2set_round_bwd_rows_kernel(const S2SRoundBwd p) {
     constexpr int C = 4 * C4;
     extern __shared__ float smem[];
