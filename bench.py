@@ -462,13 +462,29 @@ def module_rooflines(dev, peak):
     from glam_b200.synth import make_molecule_batch, make_protein_batch
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
 
-    def timeit(fn, reps=7):
-        fn(); torch.cuda.synchronize()
+    def timeit(fn, reps=7, capture=True):
+        # the module's launches are captured once and replayed: a 60 us kernel behind ~100 us of Python (layer dispatch, index
+        # cache lookups, ctypes) would otherwise be timed as the host, not the device
+        fn(); fn(); torch.cuda.synchronize()
+        run = fn
+        try:
+            if not capture:
+                raise RuntimeError("eager")
+            cg = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), torch.cuda.graph(cg, stream=side):
+                fn()
+            torch.cuda.current_stream().wait_stream(side)
+            run = cg.replay
+        except Exception:                                         # not capturable (host read-back inside): eager timing
+            torch.cuda.synchronize()
+        run(); torch.cuda.synchronize()
         ts = []
         for _ in range(reps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            e0.record(); run(); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ts.sort()
         return ts[len(ts) // 2] * 1e-3
@@ -507,16 +523,20 @@ def module_rooflines(dev, peak):
     blk.train()
     xg = x0.clone().requires_grad_(True)
 
+    go = torch.ones(b.num_nodes, C, device=dev)
+    params = list(blk.parameters())
+
     def stack_bwd(fused):
+        # captured forward+backward minus captured forward (training mode: the forward also writes what backward reads)
         Fn.USE_FUSED_BWD = fused
         try:
-            xs, _ = blk.run_steps(xg, b.edge_index, b.edge_attr, 3, keep="last", **kw)
-            go = torch.ones_like(xs[0])
-            torch.cuda.synchronize()
-            t = timeit(lambda: torch.autograd.grad(xs[0], [xg] + list(blk.parameters()), go, retain_graph=True), reps=5)
+            def fwd():
+                return blk.run_steps(xg, b.edge_index, b.edge_attr, 3, keep="last", **kw)[0][0]
+            t_fb = timeit(lambda: torch.autograd.grad(fwd(), [xg] + params, go), reps=5)
+            t_f = timeit(fwd, reps=5)
         finally:
             Fn.USE_FUSED_BWD = True
-        return t
+        return t_fb - t_f
     put("MessageBlock bwd x3 (one-launch backward + weight-gradient contractions)", 3 * module_bytes("MessageBlock bwd", GRAPHS), stack_bwd(True), GRAPHS)
     put("MessageBlock bwd x3 (per-op backward kernels + weight-gradient contractions)", 3 * module_bytes("MessageBlock bwd", GRAPHS), stack_bwd(False), GRAPHS)
     blk.eval()
