@@ -52,14 +52,17 @@ namespace {
 enum : int { kFlagNodes = 1, kFlagEdges = 2, kFlagCross = 4, kFlagEdgeAttr = 8 };
 
 // ------------------------------------------------------------------------------------------------ graph tiles
-// Greedy packing of consecutive whole graphs into tiles of <= max_nodes nodes and <= max_edges in-edges, in chunks of 64
-// graphs (tiles never span chunks: one partly filled tile per chunk of ~13).  Three small launches:
-//   (1) a warp per chunk: the lanes fetch the chunk's node / edge end offsets in parallel (two dependent loads per lane
-//       instead of 128 in a row), lane 0 walks them out of shared memory and emits the chunk's tiles into the chunk's own
-//       slots of a scratch array (slot c*64 + i) and the chunk's tile count;
+// Greedy packing of consecutive whole graphs into tiles of <= max_nodes nodes and <= max_edges in-edges, in chunks of 512
+// graphs (tiles never span chunks: one partly filled tile per chunk of ~100).  Three small launches:
+//   (1) a warp per chunk: the lanes fetch the chunk's node / edge end offsets in parallel, then the warp emits one tile per
+//       trip — the 32 lanes test the next 32 possible tile ends at once — into the chunk's own slots of a scratch array
+//       (slot c*512 + i) and the chunk's tile count;
 //   (2) one CTA: exclusive scan of the chunk counts (fixed order), total -> meta[0];
 //   (3) a warp per chunk: scratch slots -> final positions.
-constexpr int kTileChunk = 64;
+// The kernels' time per tile does not depend on how full the tile is (the phases are lane-parallel over its 128 rows), so the
+// ORDER of the graphs in the batch matters: synth.tile_order() / permute_graphs() arrange a batch so that consecutive graphs
+// fill the tiles (first-fit decreasing), which the greedy pass here then reproduces.
+constexpr int kTileChunk = 512;                 // graphs per warp: a tile never spans chunks, so at most one short tile per 512 graphs
 constexpr int kTileWarps = 8;
 
 __global__ void __launch_bounds__(kTileWarps * 32)
@@ -77,24 +80,32 @@ graph_tiles_pack_kernel(const int32_t* __restrict__ gptr, int64_t B, const int32
         eend[warp][i] = rowptr[nn];
     }
     __syncwarp();
-    if (lane == 0) {
-        int count = 0, flags = 0, g = 0;
-        while (g < ng) {
-            const int n0 = nend[warp][g], e0 = eend[warp][g];
-            int k = g, n1 = n0, e1 = e0;
-            while (k < ng) {
-                const int nn = nend[warp][k + 1], ee = eend[warp][k + 1];
-                if (nn - n0 > max_nodes || ee - e0 > max_edges) break;
-                n1 = nn; e1 = ee; ++k;
-            }
-            if (k == g) {                              // a single graph over the caps: its own (flagged) tile
-                n1 = nend[warp][g + 1]; e1 = eend[warp][g + 1];
-                flags |= (n1 - n0 > max_nodes ? kFlagNodes : 0) | (e1 - e0 > max_edges ? kFlagEdges : 0);
-                k = g + 1;
-            }
-            if (n1 > n0) { scratch[c * kTileChunk + count] = make_int4(n0, n1, e0, e1); ++count; }
-            g = k;
+    // greedy packing, a tile per trip: the 32 lanes test the next 32 tile ends at once (the prefix sums are monotone, so the
+    // graphs that still fit are a prefix of the lanes); all lanes carry the same g / count
+    int count = 0, flags = 0, g = 0;
+    while (g < ng) {
+        const int n0 = nend[warp][g], e0 = eend[warp][g];
+        int k = g;
+        for (bool more = true; more && k < ng;) {
+            const int cand = k + 1 + lane;
+            const bool fit = cand <= ng && nend[warp][cand] - n0 <= max_nodes && eend[warp][cand] - e0 <= max_edges;
+            const unsigned m = __ballot_sync(0xffffffffu, fit);
+            const int adv = m == 0xffffffffu ? 32 : __ffs(~m) - 1;
+            k += adv;
+            more = adv == 32;
         }
+        if (k == g) {                                  // a single graph over the caps: its own (flagged) tile
+            k = g + 1;
+            flags |= (nend[warp][k] - n0 > max_nodes ? kFlagNodes : 0) | (eend[warp][k] - e0 > max_edges ? kFlagEdges : 0);
+        }
+        const int n1 = nend[warp][k], e1 = eend[warp][k];
+        if (n1 > n0) {
+            if (lane == 0) scratch[c * kTileChunk + count] = make_int4(n0, n1, e0, e1);
+            ++count;
+        }
+        g = k;
+    }
+    if (lane == 0) {
         counts[c] = count;
         if (flags) atomicOr(&meta[1], flags);          // meta is zeroed by the caller; every builder ORs its findings in
     }
