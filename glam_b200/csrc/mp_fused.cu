@@ -54,9 +54,8 @@ enum : int { kFlagNodes = 1, kFlagEdges = 2, kFlagCross = 4, kFlagEdgeAttr = 8 }
 // ------------------------------------------------------------------------------------------------ graph tiles
 // Greedy packing of consecutive whole graphs into tiles of <= max_nodes nodes and <= max_edges in-edges, in chunks of 512
 // graphs (tiles never span chunks: one partly filled tile per chunk of ~100).  Three small launches:
-//   (1) a warp per chunk: the lanes fetch the chunk's node / edge end offsets in parallel, then the warp emits one tile per
-//       trip — the 32 lanes test the next 32 possible tile ends at once — into the chunk's own slots of a scratch array
-//       (slot c*512 + i) and the chunk's tile count;
+//   (1) a CTA per chunk: the tiles of the chunk into the chunk's own slots of a scratch array (slot c*512 + i) and the
+//       chunk's tile count;
 //   (2) one CTA: exclusive scan of the chunk counts (fixed order), total -> meta[0];
 //   (3) a warp per chunk: scratch slots -> final positions.
 // The kernels' time per tile does not depend on how full the tile is (the phases are lane-parallel over its 128 rows), so the
@@ -65,50 +64,53 @@ enum : int { kFlagNodes = 1, kFlagEdges = 2, kFlagCross = 4, kFlagEdgeAttr = 8 }
 constexpr int kTileChunk = 512;                 // graphs per warp: a tile never spans chunks, so at most one short tile per 512 graphs
 constexpr int kTileWarps = 8;
 
-__global__ void __launch_bounds__(kTileWarps * 32)
+__global__ void __launch_bounds__(256)
 graph_tiles_pack_kernel(const int32_t* __restrict__ gptr, int64_t B, const int32_t* __restrict__ rowptr, int max_nodes, int max_edges,
                         int4* __restrict__ scratch, int32_t* __restrict__ counts, int32_t* __restrict__ meta) {
-    __shared__ int nend[kTileWarps][kTileChunk + 1], eend[kTileWarps][kTileChunk + 1];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t c = (int64_t)blockIdx.x * kTileWarps + warp;
+    // one CTA per chunk: (a) all threads fetch the chunk's node / edge end offsets, (b) every graph finds, by bisection over the
+    // (monotone) offsets, where a tile that STARTS at it would end, (c) one thread follows those links from the chunk's first
+    // graph — a chain of ~100 shared-memory reads, not 512 dependent global ones —, (d) all threads write the tiles out
+    __shared__ int nend[kTileChunk + 1], eend[kTileChunk + 1], nxt[kTileChunk], starts[kTileChunk], n_tiles;
+    const int tid = threadIdx.x;
+    const int64_t c = blockIdx.x;
     const int64_t g0 = c * kTileChunk;
     if (g0 >= B) return;
     const int ng = (int)min((int64_t)kTileChunk, B - g0);
-    for (int i = lane; i <= ng; i += 32) {
+    for (int i = tid; i <= ng; i += blockDim.x) {
         const int nn = gptr[g0 + i];
-        nend[warp][i] = nn;
-        eend[warp][i] = rowptr[nn];
+        nend[i] = nn;
+        eend[i] = rowptr[nn];
     }
-    __syncwarp();
-    // greedy packing, a tile per trip: the 32 lanes test the next 32 tile ends at once (the prefix sums are monotone, so the
-    // graphs that still fit are a prefix of the lanes); all lanes carry the same g / count
-    int count = 0, flags = 0, g = 0;
-    while (g < ng) {
-        const int n0 = nend[warp][g], e0 = eend[warp][g];
-        int k = g;
-        for (bool more = true; more && k < ng;) {
-            const int cand = k + 1 + lane;
-            const bool fit = cand <= ng && nend[warp][cand] - n0 <= max_nodes && eend[warp][cand] - e0 <= max_edges;
-            const unsigned m = __ballot_sync(0xffffffffu, fit);
-            const int adv = m == 0xffffffffu ? 32 : __ffs(~m) - 1;
-            k += adv;
-            more = adv == 32;
+    __syncthreads();
+    for (int g = tid; g < ng; g += blockDim.x) {
+        const int n0 = nend[g], e0 = eend[g];
+        int lo = g, hi = ng;                             // largest k in [g, ng] whose graphs g..k-1 fit
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (nend[mid] - n0 <= max_nodes && eend[mid] - e0 <= max_edges) lo = mid; else hi = mid - 1;
         }
-        if (k == g) {                                  // a single graph over the caps: its own (flagged) tile
-            k = g + 1;
-            flags |= (nend[warp][k] - n0 > max_nodes ? kFlagNodes : 0) | (eend[warp][k] - e0 > max_edges ? kFlagEdges : 0);
-        }
-        const int n1 = nend[warp][k], e1 = eend[warp][k];
-        if (n1 > n0) {
-            if (lane == 0) scratch[c * kTileChunk + count] = make_int4(n0, n1, e0, e1);
-            ++count;
-        }
-        g = k;
+        nxt[g] = lo == g ? g + 1 : lo;                   // a single graph over the caps: its own (flagged) tile
     }
-    if (lane == 0) {
+    __syncthreads();
+    if (tid == 0) {
+        int count = 0;
+        for (int g = 0; g < ng;) {
+            const int k = nxt[g];
+            if (nend[k] > nend[g]) starts[count++] = g;
+            g = k;
+        }
+        n_tiles = count;
         counts[c] = count;
-        if (flags) atomicOr(&meta[1], flags);          // meta is zeroed by the caller; every builder ORs its findings in
     }
+    __syncthreads();
+    int flags = 0;
+    for (int i = tid; i < n_tiles; i += blockDim.x) {
+        const int g = starts[i], k = nxt[g];
+        const int n0 = nend[g], n1 = nend[k], e0 = eend[g], e1 = eend[k];
+        flags |= (n1 - n0 > max_nodes ? kFlagNodes : 0) | (e1 - e0 > max_edges ? kFlagEdges : 0);
+        scratch[c * kTileChunk + i] = make_int4(n0, n1, e0, e1);
+    }
+    if (flags) atomicOr(&meta[1], flags);                // meta is zeroed by the caller; every builder ORs its findings in
 }
 
 // counts[c] -> exclusive prefix (in place); total -> meta[0].  One CTA, 1024 threads, each a contiguous run of chunks.
@@ -931,7 +933,7 @@ extern "C" int glam_build_graph_tiles(const int32_t* graph_ptr, int64_t num_grap
     int4* scratch = reinterpret_cast<int4*>(workspace);
     int32_t* counts = reinterpret_cast<int32_t*>(scratch + chunks * kTileChunk);
     const unsigned grid = (unsigned)((chunks + kTileWarps - 1) / kTileWarps);
-    graph_tiles_pack_kernel<<<grid, kTileWarps * 32, 0, stream>>>(graph_ptr, num_graphs, dst_rowptr, kMpM, kMpMaxEdges, scratch, counts, meta);
+    graph_tiles_pack_kernel<<<(unsigned)chunks, 256, 0, stream>>>(graph_ptr, num_graphs, dst_rowptr, kMpM, kMpMaxEdges, scratch, counts, meta);
     GLAM_CHECK_LAUNCH();
     graph_tiles_scan_kernel<<<1, 1024, 0, stream>>>(counts, chunks, meta);
     GLAM_CHECK_LAUNCH();
