@@ -66,6 +66,7 @@ SIGNATURES = {
     "glam_pair_dot_pool_tc_supported": (I32, [I32]),
     "glam_pair_dot_pool_bwd": (I32, [P, P, P, P, P, P, P, P, I64, I32, P, P, P]),
     "glam_graph_tile_caps": (I32, [P, P]),
+    "glam_tile_order": (I32, [P, P, I64, I32, I32, P]),
     "glam_graph_tiles_workspace_bytes": (SZ, [I64]),
     "glam_build_graph_tiles": (I32, [P, I64, P, P, I64, I64, P, P, P, SZ, P]),
     "glam_edge_types": (I32, [P, I64, I32, P, P, P]),

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLAM_B200_ABI_VERSION 11
+#define GLAM_B200_ABI_VERSION 12
 #define GLAM_MAX_HEADS 4
 
 int glam_abi_version(void);
@@ -293,8 +293,8 @@ int glam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
  * stay resident from step to step.  xp [N,HC+2H] and agg [N,HC] never reach HBM (unless saved for backward).
  *
  * glam_build_graph_tiles — greedy packing of consecutive whole graphs (graph_ptr, B+1 entries) into tiles of
- *   <= max_nodes rows and <= max_edges in-edges (glam_graph_tile_caps), 64 graphs per packing chunk (tiles do not span
- *   chunks).  tiles: 4*max(B, 64*ceil(B/64)) int32 {n0, n1, e0, e1} per tile, 16-byte aligned; workspace >=
+ *   <= max_nodes rows and <= max_edges in-edges (glam_graph_tile_caps), 512 graphs per packing chunk (tiles do not span
+ *   chunks).  tiles: 4*B int32 {n0, n1, e0, e1} per tile, 16-byte aligned; workspace >=
  *   glam_graph_tiles_workspace_bytes(B); meta: int32[4], ZEROED by the caller: meta[0] = tile count, meta[1] = OR of precondition violations
  *   (1 a graph has more rows than a tile, 2 more in-edges than a tile, 4 an edge crosses tiles i.e. graphs,
  *   8 an edge_attr row is not one-hot).  glam_edge_types — bond type per dst-ordered edge (index of the 1 in the
@@ -320,6 +320,12 @@ int glam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
  *   glam_message_stack_supported: tf32 math mode, heads == 3, channels in {32,36,40}, edge_dim <= 4.
  * --------------------------------------------------------------------------------------------- */
 int glam_graph_tile_caps(int* max_nodes, int* max_edges);
+/* HOST function (no GPU, no stream; ABI v12): the order of a batch's graphs in which CONSECUTIVE graphs fill the tiles — first-fit
+ * decreasing over nodes[B] (and, optionally, in-edges edges[B]); perm[new position] = old graph index.  The kernels' time per
+ * tile does not depend on how full the tile is, and a batch has no order of its own (the reference's DataLoader shuffles,
+ * src_1gp/trainer.py:95-101): collating in this order makes 815 instead of 918 tiles of 4096 MoleculeNet-shaped graphs.  Empty
+ * graphs come first, graphs over cap_nodes last.  O(B); glam_b200/synth.py::tile_order is the numpy statement of the same. */
+int glam_tile_order(const int64_t* nodes, const int64_t* edges, int64_t num_graphs, int cap_nodes, int cap_edges, int64_t* perm);
 size_t glam_graph_tiles_workspace_bytes(int64_t num_graphs);
 int glam_build_graph_tiles(const int32_t* graph_ptr, int64_t num_graphs, const int32_t* dst_rowptr, const int32_t* dst_src,
                            int64_t num_nodes, int64_t num_edges, int32_t* tiles, int32_t* meta, void* workspace,

@@ -322,6 +322,12 @@ def test_tile_aware_graph_order_is_a_permutation_that_fills_tiles_and_changes_no
     odd = np.array([200, 5, 128, 1, 127, 64, 64, 300])
     assert sorted(tile_order(odd).tolist()) == list(range(8))
     assert sorted(tile_order(np.full(10, 30), edges=np.full(10, 400)).tolist()) == list(range(10))
+    # the library's host routine (glam_tile_order, what impl="auto" runs) and the numpy statement give the same permutation,
+    # also when the edge cap binds or a graph exceeds it
+    e = (sizes * 2.2).astype(np.int64)
+    for kw in (dict(), dict(edges=e), dict(edges=e, cap_edges=150), dict(edges=e, cap_nodes=64, cap_edges=100)):
+        assert np.array_equal(tile_order(sizes, impl="native", **kw), tile_order(sizes, impl="numpy", **kw)), kw
+    assert np.array_equal(tile_order(odd, impl="native"), tile_order(odd, impl="numpy"))
     b = make_molecule_batch(40, seed=3)
     perm = tile_order(torch.bincount(b.batch).numpy())
     pb = permute_graphs(b, perm)
