@@ -110,11 +110,10 @@ class _PairArchitecture(nn.Module):
         ta, tb = _Tower(self, self.prefixes[0]), _Tower(self, self.prefixes[1])
         B = _num_graphs(da)
         Bb = B if pro_index is None else _num_graphs(db)
-        xa = ta.lin0(da.x, batch=da.batch)
-        xb = tb.lin0(db.x, batch=db.batch)
-        # the towers only meet in the pools, so each runs all its steps first (same values as the lock-step loop)
-        xas, _ = ta.conv.run_steps(xa, da.edge_index, da.edge_attr, self.message_steps, batch=da.batch, num_graphs=B)
-        xbs, _ = tb.conv.run_steps(xb, db.edge_index, db.edge_attr, self.message_steps, batch=db.batch, num_graphs=Bb)
+        # the towers only meet in the pools, so each runs all its steps first (same values as the lock-step loop); the input
+        # LinearBlocks (src_2gi_ddi/model.py:39-41) go in as `pre`: inside the one-launch kernels when those take the tower
+        xas, _ = ta.conv.run_steps(da.x, da.edge_index, da.edge_attr, self.message_steps, batch=da.batch, num_graphs=B, pre=ta.lin0)
+        xbs, _ = tb.conv.run_steps(db.x, db.edge_index, db.edge_attr, self.message_steps, batch=db.batch, num_graphs=Bb, pre=tb.lin0)
         fusion = [dot_and_global_pool2(a, b, da.batch, db.batch, num_graphs=B, pro_index=pro_index, num_pro_graphs=Bb)
                   for a, b in zip(xas, xbs)]
         oa = ta.flat(ta.readout(xas[-1], da.batch, num_graphs=B))
