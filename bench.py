@@ -251,11 +251,12 @@ def kernel_bytes_model(label, N, E, B, Cc=C, Hh=H, De=DE):
         m = re.search(r"N=(\d+),S=(\d+),(\w+)", label)
         S, save = int(m.group(2)), m.group(3) == "save"
         out = 4 * N * Cc * (2 if not save else 0)
-        sv = 4 * S * (N * (ld + HC + Cc + 3 * Cc + Cc + 2 * Cc) + E * Hh) + 8 * N * Cc if save else 0
+        # saved for backward per step and node: xpe, agg, tile-blocked gates (7C), m | h | 1 rows (2C + 4), x and h outputs
+        sv = 4 * S * (N * (ld + HC + 7 * Cc + 2 * Cc + 4 + 2 * Cc) + E * Hh) + 8 * N * Cc if save else 0
         return 4 * N * Cc + 5 * E + 4 * N + out + sv
-    if label.startswith("glam_message_stack_bwd"):   # reads the tile-blocked gate save, xpe, alpha; writes G_GI, G_GH, G_PRE, G_XPE
+    if label.startswith("glam_message_stack_bwd"):   # reads the tile-blocked gate save, xpe, alpha; writes G4, G_PRE, G_XPE
         S = int(re.search(r"S=(\d+)", label).group(1))
-        return 4 * S * (N * (7 * Cc + ld) + E * Hh + N * (7 * Cc + ld)) + 4 * 2 * N * Cc + 4 * (3 * E + 2 * N)
+        return 4 * S * (N * (7 * Cc + ld) + E * Hh + N * (4 * Cc + Cc + ld)) + 4 * 2 * N * Cc + 4 * (3 * E + 2 * N)
     if label.startswith("glam_triplet_edge_fwd"):
         return 4 * (N * ld + N * HC + E * De + E * Hh) + 4 * (E + N + 1)
     if label.startswith("glam_triplet_edge_bwd_dst"):
