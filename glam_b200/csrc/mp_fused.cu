@@ -853,7 +853,9 @@ mp_fused_kernel(const MpParams p) {
             // -------------------------------------------------------- outputs of the step
             if (SAVE) {
                 copy_out_panels<CQ, NT>(XM, AT, 0, p.sX + (size_t)(s + 1) * NC + (size_t)n0 * C, nd);
-                copy_out_panels<CQ, NT>(HM, AT, 1, p.sHH + (size_t)(s + 1) * NC + (size_t)n0 * C, nd);
+                // with the tile-blocked gate save the backward reads h_in from GT and the weight gradient from MH: only the final
+                // state (an output of the node) is written row-major then
+                if (!p.sGT || s + 1 == p.steps) copy_out_panels<CQ, NT>(HM, AT, 1, p.sHH + (size_t)(s + 1) * NC + (size_t)n0 * C, nd);
                 if (!p.sGT) {
                     copy_out_flat<NT>(rstage, p.sRZN + ((size_t)s * p.N + n0) * 3 * C, nd * 3 * CQ);
                     __syncthreads();

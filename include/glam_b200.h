@@ -310,7 +310,9 @@ int glam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
  *   (conv_only: save_xpe, save_agg, save_alpha and x_out only).  save_gt != NULL (then save_rzn / save_gh may be NULL): the
  *   gate-side tensors for glam_message_stack_bwd in its tile-blocked layout instead — [steps][N][7C]; inside step s the tile
  *   {n0, n1} owns floats [n0*7C, n1*7C) as 7*C/4 slots (r, z, n, gh_n, h, x', m; C/4 16-byte chunks each) of n1-n0 rows x
- *   16 bytes: a warp's 32 rows of one chunk are contiguous in the forward's stores and in the backward's loads.  save_mh != NULL
+ *   16 bytes: a warp's 32 rows of one chunk are contiguous in the forward's stores and in the backward's loads; of save_h only
+ *   entries 0 and `steps` (the initial and the final state) are written then — the states in between live in save_gt / save_mh.
+ *   save_mh != NULL
  *   (then save_m may be NULL): [steps][N][2C+4] rows m | h_in | 1 0 0 0 — with glam_message_stack_bwd's g4 rows the ONE pair of
  *   operands of both GRU weight gradients ([m h 1]^T [g_r g_z g_n g_n r]; the constant column yields the bias gradients).  pn_batch !=
  *   NULL (evaluation only: no saves, h0 == NULL): PairNorm(scale=1, eps=pn_eps) per graph on every step's block input inside the
