@@ -526,7 +526,10 @@ class Set2SetFn(Function):
         U[0].zero_()
         cs[0].zero_()
         for s in range(S):
-            ops.gemm(U[s], w_cat, transpose_w=True, bias=b_sum, out=gates[s])
+            if s == 0:
+                gates[0].copy_(b_sum)                                       # u_0 = 0: the gate pre-activations of the first round ARE the bias
+            else:
+                ops.gemm(U[s], w_cat, transpose_w=True, bias=b_sum, out=gates[s])
             ops.set2set_round_fwd(x, gates[s], cs[s], cs[s + 1], gptr, B, att[s], U[s + 1], out if s == S - 1 else None)
         ctx.save_for_backward(x, w_cat, gptr, U, cs, gates, att)
         ctx.cfg = (B, S)
