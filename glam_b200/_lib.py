@@ -63,6 +63,8 @@ SIGNATURES = {
     "glam_pair_dot_pool_fwd": (I32, [P, P, P, P, I64, I32, P, P, P, P, P]),
     "glam_pair_dot_pool_fwd_idx": (I32, [P, P, P, P, P, I64, I32, P, P, P, P, P]),
     "glam_pair_dot_pool_fwd_tc": (I32, [P, P, P, P, P, I64, I32, P, P, P, P, P]),
+    "glam_pair_dot_pool_fwd_small": (I32, [P, P, P, P, P, I64, I32, P, P, P, P, P]),
+    "glam_pair_dot_pool_small_supported": (I32, [I32]),
     "glam_pair_dot_pool_tc_supported": (I32, [I32]),
     "glam_pair_dot_pool_bwd": (I32, [P, P, P, P, P, P, P, P, I64, I32, P, P, P]),
     "glam_graph_tile_caps": (I32, [P, P]),

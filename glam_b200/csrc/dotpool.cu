@@ -133,6 +133,135 @@ pair_dot_pool_fwd_kernel(const float* __restrict__ xa, const float* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small pairs (drug-drug: 25 x 25 atoms): one WARP per pair, eight pairs per CTA, no block barrier.  Lane a loads row a of
+// the first graph and stores it transposed ([k][a], pitch 36: a broadcast LDS.128 then delivers four rows' values of one
+// channel), lane b keeps row b of the second graph in REGISTERS and owns column b of S = Xa Xb^T: 32 accumulators, the
+// channel loop fully unrolled.  The CTA-per-pair kernel above spent its time in barriers and in the start-up latency of
+// 4096 CTAs (59 us per 4096 pairs, 0.06 of HBM); same values (k-ascending fmaf chains), same arg-max rule.  Column sums come
+// out of the transposed tiles in row order.  Graphs over 32 rows loop over 32-row tiles (correct, not the intended use).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPairWarps = 8;
+constexpr int kPairTP = 36;                              // pitch of the transposed tiles: 16-byte aligned rows of 32 (+4 pad)
+template <int C4>
+__global__ void __launch_bounds__(kPairWarps * 32)
+pair_dot_pool_fwd_warp_kernel(const float* __restrict__ xa, const float* __restrict__ xb, const int32_t* __restrict__ ptr_a,
+                              const int32_t* __restrict__ ptr_b, const int32_t* __restrict__ idx_b, int64_t num_pairs,
+                              float* __restrict__ out, int32_t* __restrict__ argmax, float* __restrict__ sum_a,
+                              float* __restrict__ sum_b) {
+    constexpr int C = 4 * C4;
+    extern __shared__ __align__(16) float pw_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* At = pw_smem + (size_t)wid * (2 * C * kPairTP);       // [C][36]: At[k][a]
+    float* Bt = At + C * kPairTP;                                // [C][36]: Bt[k][b] (column sums only)
+    const int64_t g = (int64_t)blockIdx.x * kPairWarps + wid;
+    if (g >= num_pairs) return;
+    const int gb = idx_b ? idx_b[g] : (int)g;
+    const int a0 = ptr_a[g], a1 = ptr_a[g + 1], b0 = ptr_b[gb], b1 = ptr_b[gb + 1];
+    const int na = a1 - a0, nb = b1 - b0;
+    const bool single = na <= 32 && nb <= 32;
+    float dotp = 0.f;
+    if (!single) {                                       // column sums by a pass over global memory (fixed row order)
+        for (int k = lane; k < C; k += 32) {
+            float sa = 0.f, sb = 0.f;
+            for (int a = a0; a < a1; ++a) sa += xa[(int64_t)a * C + k];
+            for (int b = b0; b < b1; ++b) sb += xb[(int64_t)b * C + k];
+            sum_a[g * C + k] = sa; sum_b[g * C + k] = sb;
+            dotp = fmaf(sa, sb, dotp);
+        }
+    }
+    float best = -INFINITY;
+    long long best_i = 0x7fffffffffffffffLL;
+    for (int at = 0; at < na || (at == 0 && single); at += 32) {
+        __syncwarp();
+        {                                                // row at+lane of A -> At[.][lane]
+            const bool ok = at + lane < na;
+            const float4* row = reinterpret_cast<const float4*>(xa + (int64_t)(a0 + at + (ok ? lane : 0)) * C);
+#pragma unroll
+            for (int q = 0; q < C4; ++q) {
+                const float4 v = ok ? __ldg(row + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                At[(4 * q + 0) * kPairTP + lane] = v.x; At[(4 * q + 1) * kPairTP + lane] = v.y;
+                At[(4 * q + 2) * kPairTP + lane] = v.z; At[(4 * q + 3) * kPairTP + lane] = v.w;
+            }
+        }
+        for (int bt = 0; bt < nb || (bt == 0 && single); bt += 32) {
+            const bool okb = bt + lane < nb;
+            float4 br[C4];
+            {
+                const float4* row = reinterpret_cast<const float4*>(xb + (int64_t)(b0 + bt + (okb ? lane : 0)) * C);
+#pragma unroll
+                for (int q = 0; q < C4; ++q) br[q] = okb ? __ldg(row + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (single) {
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < C4; ++q) {
+                    Bt[(4 * q + 0) * kPairTP + lane] = br[q].x; Bt[(4 * q + 1) * kPairTP + lane] = br[q].y;
+                    Bt[(4 * q + 2) * kPairTP + lane] = br[q].z; Bt[(4 * q + 3) * kPairTP + lane] = br[q].w;
+                }
+            }
+            __syncwarp();
+            if (single) {                                // column sums out of the transposed tiles, rows in order
+                for (int k = lane; k < C; k += 32) {
+                    float sa = 0.f, sb = 0.f;
+                    for (int a = 0; a < na; ++a) sa += At[k * kPairTP + a];
+                    for (int b = 0; b < nb; ++b) sb += Bt[k * kPairTP + b];
+                    sum_a[g * C + k] = sa; sum_b[g * C + k] = sb;
+                    dotp = fmaf(sa, sb, dotp);
+                }
+            }
+            const int rows = min(32, na - at);
+            const int groups = (rows + 3) >> 2;          // warp-uniform
+            float acc[32];
+#pragma unroll
+            for (int a = 0; a < 32; ++a) acc[a] = 0.f;
+#pragma unroll
+            for (int q = 0; q < C4; ++q) {
+                const float bq[4] = {br[q].x, br[q].y, br[q].z, br[q].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float* arow = At + (4 * q + i) * kPairTP;
+#pragma unroll
+                    for (int a4 = 0; a4 < 8; ++a4) {
+                        if (a4 < groups) {
+                            const float4 av = *reinterpret_cast<const float4*>(arow + 4 * a4);
+                            acc[4 * a4 + 0] = fmaf(av.x, bq[i], acc[4 * a4 + 0]); acc[4 * a4 + 1] = fmaf(av.y, bq[i], acc[4 * a4 + 1]);
+                            acc[4 * a4 + 2] = fmaf(av.z, bq[i], acc[4 * a4 + 2]); acc[4 * a4 + 3] = fmaf(av.w, bq[i], acc[4 * a4 + 3]);
+                        }
+                    }
+                }
+            }
+            if (okb) {
+#pragma unroll
+                for (int a = 0; a < 32; ++a) {
+                    if (a < rows) {
+                        const long long lin = (long long)(at + a) * nb + (bt + lane);
+                        if (acc[a] > best || (acc[a] == best && lin < best_i)) { best = acc[a]; best_i = lin; }
+                    }
+                }
+            }
+        }
+    }
+    dotp = warp_sum(dotp);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if (lane == 0) {
+        if (na > 0 && nb > 0) {
+            out[2 * g] = best;
+            out[2 * g + 1] = dotp / ((float)na * (float)nb);
+            argmax[2 * g] = a0 + (int)(best_i / nb);
+            argmax[2 * g + 1] = b0 + (int)(best_i % nb);
+        } else {
+            out[2 * g] = 0.f; out[2 * g + 1] = 0.f;
+            argmax[2 * g] = -1; argmax[2 * g + 1] = -1;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kPairThreads)
 pair_dot_pool_bwd_kernel(const float* __restrict__ xa, const float* __restrict__ xb, const int32_t* __restrict__ ptr_a,
                          const int32_t* __restrict__ ptr_b, const float* __restrict__ g_out,
@@ -373,6 +502,34 @@ extern "C" int glam_pair_dot_pool_fwd_idx(const float* xa, const float* xb, cons
         ensure_dyn_smem((const void*)pair_dot_pool_fwd_kernel, (size_t)((int)smem));
     pair_dot_pool_fwd_kernel<<<(unsigned)num_pairs, kPairThreads, smem, (cudaStream_t)stream_>>>(xa, xb, ptr_a, ptr_b, idx_b, C, out,
                                                                                                argmax, sum_a, sum_b);
+    GLAM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int glam_pair_dot_pool_small_supported(int channels) {
+    return (channels == 32 || channels == 36 || channels == 48 || channels == 64) ? 1 : 0;
+}
+
+extern "C" int glam_pair_dot_pool_fwd_small(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b,
+                                            const int32_t* idx_b, int64_t num_pairs, int C, float* out, int32_t* argmax,
+                                            float* sum_a, float* sum_b, void* stream_) {
+    GLAM_REQUIRE(num_pairs >= 0 && num_pairs < (int64_t)1 << 31, "glam_pair_dot_pool_fwd_small: bad shape");
+    if (num_pairs == 0) return 0;
+    GLAM_REQUIRE(xa && xb && ptr_a && ptr_b && out && argmax && sum_a && sum_b, "glam_pair_dot_pool_fwd_small: null pointer");
+    GLAM_REQUIRE(glam_pair_dot_pool_small_supported(C) && (((uintptr_t)xa | (uintptr_t)xb) & 15) == 0,
+                 "glam_pair_dot_pool_fwd_small: channels must be 32, 36, 48 or 64 and the rows 16-byte aligned (channels=%d)", C);
+    const size_t smem = sizeof(float) * kPairWarps * 2 * (size_t)C * kPairTP;
+    const unsigned grid = (unsigned)((num_pairs + kPairWarps - 1) / kPairWarps);
+    auto go = [&](auto kern) {
+        ensure_dyn_smem((const void*)kern, smem);
+        kern<<<grid, kPairWarps * 32, smem, (cudaStream_t)stream_>>>(xa, xb, ptr_a, ptr_b, idx_b, num_pairs, out, argmax, sum_a, sum_b);
+    };
+    switch (C) {
+        case 32: go(pair_dot_pool_fwd_warp_kernel<8>); break;
+        case 36: go(pair_dot_pool_fwd_warp_kernel<9>); break;
+        case 48: go(pair_dot_pool_fwd_warp_kernel<12>); break;
+        default: go(pair_dot_pool_fwd_warp_kernel<16>); break;
+    }
     GLAM_CHECK_LAUNCH();
     return 0;
 }

@@ -474,6 +474,7 @@ def set2set_round_bwd(x, gates, c_prev, c_new, att, gptr, num_graphs, g_u, g_c, 
 
 
 TC_DOT_POOL_MIN_ROWS = 96    # average rows per graph of the second side from which the tensor-core dot-pool is used
+SMALL_DOT_POOL_MAX_ROWS = 40     # average rows per graph on BOTH sides up to which the warp-per-pair dot-pool kernel is used
 
 
 def pair_dot_pool_fwd(xa, xb, ptr_a, ptr_b, num_pairs, idx_b=None):
@@ -490,6 +491,15 @@ def pair_dot_pool_fwd(xa, xb, ptr_a, ptr_b, num_pairs, idx_b=None):
         if idx_b is not None:
             assert idx_b.dtype == torch.int32 and idx_b.is_contiguous() and idx_b.numel() == num_pairs
         _call("glam_pair_dot_pool_fwd_tc", _p(xa), _p(xb), _p(ptr_a), _p(ptr_b), _p(idx_b), num_pairs, C, _p(out), _p(argmax),
+              _p(sa), _p(sb), _stream(xa))
+        return out, argmax, sa, sb
+    rows_a = xa.shape[0] / max(int(num_pairs), 1)
+    if (rows_a <= SMALL_DOT_POOL_MAX_ROWS and rows_b <= SMALL_DOT_POOL_MAX_ROWS and xa.is_contiguous() and xb.is_contiguous()
+            and _lib.load().glam_pair_dot_pool_small_supported(C)):
+        # both sides small (drug-drug): a warp per pair, no block barrier (csrc/dotpool.cu)
+        if idx_b is not None:
+            assert idx_b.dtype == torch.int32 and idx_b.is_contiguous() and idx_b.numel() == num_pairs
+        _call("glam_pair_dot_pool_fwd_small", _p(xa), _p(xb), _p(ptr_a), _p(ptr_b), _p(idx_b), num_pairs, C, _p(out), _p(argmax),
               _p(sa), _p(sb), _stream(xa))
         return out, argmax, sa, sb
     if idx_b is not None:

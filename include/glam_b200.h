@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLAM_B200_ABI_VERSION 12
+#define GLAM_B200_ABI_VERSION 13
 #define GLAM_MAX_HEADS 4
 
 int glam_abi_version(void);
@@ -232,6 +232,14 @@ int glam_pair_dot_pool_fwd_idx(const float* xa, const float* xb, const int32_t* 
  * tcgen05 with TF32 operands ([128 x 256] accumulator tiles in TMEM, thread = ligand row scans for the max / first arg-max);
  * the mean and sum_a / sum_b stay exact fp32.  idx_b may be NULL.  Needs tf32 math mode, channels % 4 == 0 in [32, 64]. */
 int glam_pair_dot_pool_tc_supported(int channels);
+/* Small pairs (drug-drug, ~25 x 25 atoms; ABI v13): one warp per pair, eight pairs per CTA, the second graph's row in registers and
+ * the first graph's tile transposed in shared memory — same values, arg-max rule and outputs as glam_pair_dot_pool_fwd (idx_b may
+ * be NULL); channels in {32, 36, 48, 64}, 16-byte aligned rows.  Graphs over 32 rows are handled (32-row tiles) but belong on the
+ * CTA-per-pair or the tensor-core entry point. */
+int glam_pair_dot_pool_small_supported(int channels);
+int glam_pair_dot_pool_fwd_small(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b, const int32_t* idx_b,
+                                 int64_t num_pairs, int channels, float* out, int32_t* argmax, float* sum_a, float* sum_b,
+                                 void* stream);
 int glam_pair_dot_pool_fwd_tc(const float* xa, const float* xb, const int32_t* ptr_a, const int32_t* ptr_b,
                               const int32_t* idx_b, int64_t num_pairs, int channels, float* out, int32_t* argmax,
                               float* sum_a, float* sum_b, void* stream);

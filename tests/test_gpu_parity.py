@@ -232,6 +232,42 @@ def test_dot_pool_golden(golden_layers, name, math_mode):
     tol_check(xb.grad, c32["grad_xb"], c64["grad_xb"], f"{name}.grad_xb")
 
 
+@pytest.mark.parametrize("C", [32, 36, 48, 64])
+def test_dot_pool_warp_per_pair_matches_the_cta_per_pair_kernel(C):
+    """glam_pair_dot_pool_fwd_small (drug-drug sized pairs: a warp per pair) against glam_pair_dot_pool_fwd on the same pairs —
+    small graphs, an empty graph on either side, graphs over 32 rows (the tiled loop), a shared second side (idx_b): max and
+    arg-max bitwise (same fmaf chains, same tie rule), column sums bitwise (same row order), mean to fp32 rounding."""
+    from glam_b200 import ops
+    g = torch.Generator().manual_seed(C)
+    na = torch.tensor([25, 1, 32, 0, 7, 33, 70, 12, 31, 5, 29, 40])
+    nb = torch.tensor([25, 32, 1, 9, 0, 20, 45, 33, 31, 64, 3, 2])
+    P = na.numel()
+    ptr_a = torch.zeros(P + 1, dtype=torch.int32); ptr_a[1:] = torch.cumsum(na, 0)
+    ptr_b = torch.zeros(P + 1, dtype=torch.int32); ptr_b[1:] = torch.cumsum(nb, 0)
+    xa = torch.randn(int(na.sum()), C, generator=g).to(DEV)
+    xb = torch.randn(int(nb.sum()), C, generator=g).to(DEV)
+    xb[ptr_b[0]:ptr_b[1]] = xa[ptr_a[0]:ptr_a[1]][torch.randperm(25, generator=g)]   # ties in value are still unlikely; equal rows stress the arg-max
+    pa, pb = ptr_a.to(DEV), ptr_b.to(DEV)
+
+    def run(entry, idx=None):
+        out = torch.full((P, 2), float("nan"), device=DEV); am = torch.full((P, 2), -7, dtype=torch.int32, device=DEV)
+        sa = torch.full((P, C), float("nan"), device=DEV); sb = torch.full((P, C), float("nan"), device=DEV)
+        args = [ops._p(xa), ops._p(xb), ops._p(pa), ops._p(pb)] + ([ops._p(idx)] if entry != "glam_pair_dot_pool_fwd" else []) + \
+               [P, C, ops._p(out), ops._p(am), ops._p(sa), ops._p(sb), ops._stream(xa)]
+        ops._call(entry, *args)
+        torch.cuda.synchronize()
+        return out, am, sa, sb
+    o1, a1, s1, t1 = run("glam_pair_dot_pool_fwd")
+    o2, a2, s2, t2 = run("glam_pair_dot_pool_fwd_small", None)
+    assert torch.equal(a1, a2) and torch.equal(o1[:, 0], o2[:, 0]) and torch.equal(s1, s2) and torch.equal(t1, t2)
+    torch.testing.assert_close(o2[:, 1], o1[:, 1], rtol=1e-5, atol=1e-6)
+    idx = torch.tensor([3, 3, 0, 1, 5, 5, 6, 2, 8, 9, 0, 11], dtype=torch.int32, device=DEV)
+    o3, a3, s3, t3 = run("glam_pair_dot_pool_fwd_idx", idx)
+    o4, a4, s4, t4 = run("glam_pair_dot_pool_fwd_small", idx)
+    assert torch.equal(a3, a4) and torch.equal(o3[:, 0], o4[:, 0]) and torch.equal(s3, s4) and torch.equal(t3, t4)
+    torch.testing.assert_close(o4[:, 1], o3[:, 1], rtol=1e-5, atol=1e-6)
+
+
 def test_pairnorm_block_tf32_vs_tf32_oracle(golden_layers):
     """With PairNorm in the block the gradients amplify operand rounding ~300x (the fp64 oracle with TF32-truncated
     matmul operands is 3e-1 away from the exact one on grad_x).  The tensor-core path must agree with THAT oracle:
