@@ -473,8 +473,25 @@ int tc_gemm_launch(const float* X, int64_t ldx, const float* W, int64_t w_sk, in
     const bool al16 = ((N & 3) == 0) && ((ldy & 3) == 0) && (((uintptr_t)Y & 15) == 0) && (((uintptr_t)bias & 15) == 0) &&
                       (aux == nullptr || (((ldaux & 3) == 0) && (((uintptr_t)aux & 15) == 0)));
     const bool single_tile = M <= (int64_t)kTileM * kNumSMs;
-    const size_t smem = tc_smem_bytes(N, K, al16, &p.stages, &p.staged_out, single_tile);
+    size_t smem = tc_smem_bytes(N, K, al16, &p.stages, &p.staged_out, single_tile);
     p.og_groups = single_tile ? 1 : kEpiGroups;
+    // Many row tiles, but the two [128][N] staging tiles of the coalesced epilogue do not fit beside W and the load ring
+    // (N = 144, K = 108: Set2Set's gate GEMM over 65 536 screening graphs ran the row-per-thread epilogue at 1 TB/s): split the
+    // output columns over blockIdx.y until they do — X tiles are then read once per column block, out of L2.
+    p.n_chunk = 0;
+    unsigned gy = 1;
+    if (!single_tile && al16 && !p.staged_out && exact_end <= exact_begin && N >= 64 && smem > 0) {
+        for (int ways = 2; ways <= 4; ++ways) {
+            const int64_t chunk = ((N + ways - 1) / ways + 15) / 16 * 16;
+            int st = 0, sg = 0;
+            const size_t sm = tc_smem_bytes(chunk, K, true, &st, &sg, false);
+            if (sm > 0 && sg == 1 && st >= 2 && chunk < N) {
+                p.n_chunk = (int)chunk; gy = (unsigned)((N + chunk - 1) / chunk);
+                p.stages = st; p.staged_out = 1; smem = sm;
+                break;
+            }
+        }
+    }
     p.w_vec = (w_sk == 1 && (w_sn & 3) == 0 && ((uintptr_t)W & 15) == 0) ? 1 : 0;
     GLAM_REQUIRE(smem > 0, "tc_gemm: operands do not fit in shared memory (N=%lld K=%lld)", (long long)N, (long long)K);
     CUtensorMap tmap;
@@ -488,8 +505,6 @@ int tc_gemm_launch(const float* X, int64_t ldx, const float* W, int64_t w_sk, in
     if (grid > ntiles) grid = ntiles;
     // Few row tiles (graph-level GEMMs: 4096 rows = 32 tiles): split the output columns over blockIdx.y so that the W image
     // build and the epilogue, which dominate such launches, shrink with it and more SMs take part.
-    p.n_chunk = 0;
-    unsigned gy = 1;
     if (exact_end <= exact_begin && ntiles * 2 <= kNumSMs && N >= 64) {
         const int64_t ways = kNumSMs / ntiles;
         int64_t chunk = ((N + ways - 1) / ways + 15) / 16 * 16;

@@ -36,6 +36,8 @@ if which in ("all", "gemm", "small"):
     B_ = 4096
     q = torch.randn(B_, 3 * C, device=dev); wl = torch.randn(4 * C, 3 * C, device=dev); bl = torch.randn(4 * C, device=dev)
     timeit("gemm lstm gates [4096,108]x[108,144]^T", lambda: ops.gemm(q, wl, transpose_w=True, bias=bl), 4 * B_ * 7 * C)
+    qs = torch.randn(65536, 3 * C, device=dev)
+    timeit("gemm lstm gates [65536,108]x[108,144]^T", lambda: ops.gemm(qs, wl, transpose_w=True, bias=bl), 4 * 65536 * 7 * C)
     gg = torch.randn(B_, 4 * C, device=dev)
     timeit("gemm lstm dgrad [4096,144]x[144,108]", lambda: ops.gemm(gg, wl), 4 * B_ * 7 * C)
 if which in ("all", "tn"):

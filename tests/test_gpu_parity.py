@@ -85,7 +85,7 @@ def test_graph_ptr_and_gather():
 
 # ---------------------------------------------------------------------------------------------- dense pieces
 @pytest.mark.parametrize("M,N,K", [(1, 1, 1), (63, 36, 36), (1000, 116, 36), (777, 60, 180), (4096, 188, 60), (130, 270, 90),
-                                   (5000, 36, 9), (3000, 60, 15), (2500, 12, 40), (4096, 144, 108), (300, 256, 72), (129, 100, 36)])
+                                   (5000, 36, 9), (3000, 60, 15), (2500, 12, 40), (4096, 144, 108), (300, 256, 72), (129, 100, 36), (40000, 144, 108), (30011, 200, 72)])
 def test_gemm_variants(M, N, K, math_mode):
     from glam_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
