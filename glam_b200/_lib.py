@@ -71,7 +71,7 @@ SIGNATURES = {
     "glam_tile_order": (I32, [P, P, I64, I32, I32, P]),
     "glam_graph_tiles_workspace_bytes": (SZ, [I64]),
     "glam_build_graph_tiles": (I32, [P, I64, P, P, I64, I64, P, P, P, SZ, P]),
-    "glam_edge_types": (I32, [P, I64, I32, P, P, P]),
+    "glam_edge_types": (I32, [P, P, I64, I32, P, P, P]),
     "glam_pair_norm_fwd": (I32, [P, I64, P, I64, I32, F32, P, I64, P]),
     "glam_pair_norm_bwd": (I32, [P, I64, P, I64, P, I64, I32, F32, P, I64, I32, P]),
     "glam_unpack_graphs": (I32, [P, P, P, P, P, I64, I64, I64, I32, P, P, P, P, P, P]),

@@ -161,12 +161,14 @@ graph_tiles_check_kernel(const int4* __restrict__ tiles, const int32_t* __restri
 
 // bond type of every (dst-ordered) edge: index of the 1 in an exactly one-hot edge_attr row (src_1gp/dataset.py:82)
 __global__ void __launch_bounds__(256)
-edge_types_kernel(const float* __restrict__ ea, int64_t E, int De, uint8_t* __restrict__ etype, int32_t* __restrict__ meta) {
+edge_types_kernel(const float* __restrict__ ea, const int32_t* __restrict__ perm, int64_t E, int De, uint8_t* __restrict__ etype,
+                  int32_t* __restrict__ meta) {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= E) return;
+    const int64_t row = perm ? perm[e] : e;              // perm: the dst-ordered edge e is row perm[e] of the caller's edge_attr
     int ty = -1, ok = 1;
     for (int d = 0; d < De; ++d) {
-        const float v = ea[e * De + d];
+        const float v = ea[row * De + d];
         if (v == 1.f) { ok &= (ty < 0); ty = d; }
         else ok &= (v == 0.f);
     }
@@ -949,11 +951,12 @@ extern "C" int glam_build_graph_tiles(const int32_t* graph_ptr, int64_t num_grap
     return 0;
 }
 
-extern "C" int glam_edge_types(const float* edge_attr_sorted, int64_t num_edges, int edge_dim, uint8_t* etype, int32_t* meta, void* stream_) {
+extern "C" int glam_edge_types(const float* edge_attr_sorted, const int32_t* perm, int64_t num_edges, int edge_dim, uint8_t* etype,
+                               int32_t* meta, void* stream_) {
     GLAM_REQUIRE(num_edges >= 0 && edge_dim > 0, "glam_edge_types: bad sizes");
     if (num_edges == 0) return 0;
     GLAM_REQUIRE(edge_attr_sorted && etype && meta, "glam_edge_types: null pointer");
-    edge_types_kernel<<<(unsigned)((num_edges + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(edge_attr_sorted, num_edges, edge_dim, etype, meta);
+    edge_types_kernel<<<(unsigned)((num_edges + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(edge_attr_sorted, perm, num_edges, edge_dim, etype, meta);
     GLAM_CHECK_LAUNCH();
     return 0;
 }

@@ -66,9 +66,15 @@ class GraphIndex:
         key = (gptr.data_ptr(), gptr._version, int(num_graphs), edge_attr.data_ptr(), edge_attr._version, tuple(edge_attr.shape))
         if self._fused_key == key:
             return self._fused
-        ea = self.sorted_edge_attr(edge_attr)
+        # the kernels only need the bond TYPE per dst-ordered edge: read it through dst_perm from the caller's rows (fp32,
+        # contiguous) — the dst-ordered copy of edge_attr is made only for callers that want the rows themselves
+        ea = edge_attr if edge_attr.dim() == 2 else edge_attr.view(edge_attr.shape[0], -1)
         meta = torch.zeros(4, dtype=torch.int32, device=ea.device)
-        etype = ops.edge_types(ea, meta)
+        if ea.dtype == torch.float32 and ea.is_contiguous():
+            etype = ops.edge_types(ea, meta, perm=self.dst_perm)
+        else:
+            ea = self.sorted_edge_attr(edge_attr)
+            etype = ops.edge_types(ea, meta)
         tiles = ops.build_graph_tiles(gptr, num_graphs, self, meta)
         shape_key = (self.num_nodes, self.num_edges, int(num_graphs), ea.shape[1], ea.device)
         if _capturing():

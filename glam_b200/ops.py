@@ -287,10 +287,13 @@ def build_graph_tiles(gptr: torch.Tensor, num_graphs: int, g, meta: torch.Tensor
     return tiles
 
 
-def edge_types(ea_sorted: torch.Tensor, meta: torch.Tensor) -> torch.Tensor:
-    E, De = ea_sorted.shape
-    et = torch.empty((max(E, 1),), dtype=torch.uint8, device=ea_sorted.device)
-    _call("glam_edge_types", _p(ea_sorted), E, De, _p(et), _p(meta), _stream(ea_sorted))
+def edge_types(ea: torch.Tensor, meta: torch.Tensor, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Bond type per dst-ordered edge.  `ea` is edge_attr already in dst order, or — with perm = the index's dst_perm — in the
+    caller's edge order (the permuted copy is then never made)."""
+    E, De = ea.shape
+    assert ea.is_contiguous() and ea.dtype == torch.float32 and (perm is None or (perm.dtype == torch.int32 and perm.numel() == E))
+    et = torch.empty((max(E, 1),), dtype=torch.uint8, device=ea.device)
+    _call("glam_edge_types", _p(ea), _p(perm), E, De, _p(et), _p(meta), _stream(ea))
     return et
 
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLAM_B200_ABI_VERSION 13
+#define GLAM_B200_ABI_VERSION 14
 #define GLAM_MAX_HEADS 4
 
 int glam_abi_version(void);
@@ -340,7 +340,10 @@ size_t glam_graph_tiles_workspace_bytes(int64_t num_graphs);
 int glam_build_graph_tiles(const int32_t* graph_ptr, int64_t num_graphs, const int32_t* dst_rowptr, const int32_t* dst_src,
                            int64_t num_nodes, int64_t num_edges, int32_t* tiles, int32_t* meta, void* workspace,
                            size_t workspace_bytes, void* stream);
-int glam_edge_types(const float* edge_attr_sorted, int64_t num_edges, int edge_dim, uint8_t* etype, int32_t* meta, void* stream);
+/* perm (ABI v14; may be NULL): edge_attr is in the CALLER's edge order and the dst-ordered edge e is its row perm[e] (glam_build_csr's
+ * dst_perm) — the evaluation path then never materialises the permuted edge_attr. */
+int glam_edge_types(const float* edge_attr, const int32_t* perm, int64_t num_edges, int edge_dim, uint8_t* etype, int32_t* meta,
+                    void* stream);
 int glam_message_stack_supported(int channels, int heads, int edge_dim);
 /* Profiling aid: when `cycles` (device memory, [148][32] unsigned 64-bit) is not NULL, every following glam_message_stack_fwd /
  * glam_message_stack_bwd launch has thread 0 of each CTA add the SM cycles spent between consecutive phase boundaries to

@@ -43,7 +43,7 @@ def test_arity_matches_header():
 
 
 def test_abi_version_and_workspace_queries(lib):
-    assert lib.glam_abi_version() == 13
+    assert lib.glam_abi_version() == 14
     assert lib.glam_csr_workspace_bytes(1000, 2000) > 4 * (2 * 1001 + 4 * 2000)
     assert lib.glam_gemm_tn_workspace_bytes(100000, 36, 116) >= 36 * 116 * 4
     assert lib.glam_colsum_workspace_bytes(100000, 108) >= 108 * 4

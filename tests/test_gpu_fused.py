@@ -71,6 +71,9 @@ def test_graph_tiles_bit_exact(n_graphs, seed):
     assert all(t[1] - t[0] <= mx_n and t[3] - t[2] <= mx_e for t in want)
     ea = g.sorted_edge_attr(b.edge_attr)
     assert torch.equal(et[:ea.shape[0]].cpu().long(), ea.argmax(1).cpu())
+    meta2 = torch.zeros(4, dtype=torch.int32, device=DEV)
+    et2 = ops.edge_types(b.edge_attr.contiguous(), meta2, perm=g.dst_perm)      # the caller's rows read through dst_perm: same types
+    assert torch.equal(et2, et) and int(meta2[1]) == 0
 
 
 def test_graph_tiles_flags():
