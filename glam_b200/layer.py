@@ -583,13 +583,17 @@ class MessageBlock(nn.Module):
             fi = None                                            # (the training-mode fused pair has no PairNorm)
         if pre_fused is not None:
             x = pre(x, batch=batch)
-        ea = g.sorted_edge_attr(edge_attr)
+        ea2 = edge_attr if edge_attr.dim() == 2 else edge_attr.view(edge_attr.shape[0], -1)
+        both = (fi is not None and Fn.USE_FUSED_BWD and g.src_rowptr is not None
+                and ops.message_stack_bwd_supported(inner.node_channels, inner.heads, ea2.shape[1], int(steps)))
+        # the one-launch pair reads bond types, not edge_attr rows: the node then only needs edge_attr's SHAPE, and the
+        # dst-ordered copy (a gather launch per batch) is made only for the per-op kernels
+        ea = ea2 if both else g.sorted_edge_attr(edge_attr)
         pre_args = (None, None, None)
         if pre_train is not None:
             # training: the input LinearBlock runs inside the one-launch pair too when both kernels take this batch (its
             # weight / bias gradients come back from the same autograd node); otherwise it is simply called first
-            if (fi is not None and Fn.USE_FUSED_BWD and g.src_rowptr is not None
-                    and ops.message_stack_bwd_supported(inner.node_channels, inner.heads, ea.shape[1], int(steps))):
+            if both:
                 pre_args = (pre_train[0], pre_train[1], (pre_train[2], pre_train[3]))
             else:
                 x = pre_block(x, batch=batch)
