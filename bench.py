@@ -503,7 +503,7 @@ def module_rooflines(dev, peak):
         if note:
             out[name]["note"] = note
 
-    b = make_molecule_batch(GRAPHS, seed=1234, total_nodes=TOTAL_NODES, total_edges=TOTAL_EDGES, **DIMS).to(dev)
+    b = make_molecule_batch(GRAPHS, seed=1234, total_nodes=TOTAL_NODES, total_edges=TOTAL_EDGES, tile_pack=TILE_PACK, **DIMS).to(dev)
     torch.manual_seed(0)
     blk = layer.MessageBlock(C, C, DE, norm="_None", dropout="_None()", conv="_TripletMessage", act="CELU", res=True).to(dev).eval()
     x0 = torch.randn(b.num_nodes, C, device=dev)
