@@ -419,26 +419,42 @@ mp_fused_kernel(const MpParams p) {
 #pragma unroll
             for (int k = 0; k < RPF; ++k) rs[k * NT + tid] = pfr[k];
             __syncthreads();
-            for (int i = tid; i < kMpM * CQ; i += NT) {
-                const int r = i / CQ, q = i - r * CQ;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < nd) {
-                    const float* xr = rs + r * p.raw_dim;
-                    const float* w = Wp + 4 * q * p.raw_dim;
-                    v = lds128(bp + 4 * q);
-                    for (int k = 0; k < p.raw_dim; ++k) {
-                        const float xv = xr[k];
-                        v.x = fmaf(xv, w[k], v.x); v.y = fmaf(xv, w[p.raw_dim + k], v.y);
-                        v.z = fmaf(xv, w[2 * p.raw_dim + k], v.z); v.w = fmaf(xv, w[3 * p.raw_dim + k], v.w);
-                    }
-                    v.x = act_fwd(v.x, p.pre_act, p.pre_act_param); v.y = act_fwd(v.y, p.pre_act, p.pre_act_param);
-                    v.z = act_fwd(v.z, p.pre_act, p.pre_act_param); v.w = act_fwd(v.w, p.pre_act, p.pre_act_param);
-                    if (SAVE && !p.conv_only) {
-                        reinterpret_cast<float4*>(p.sX + (size_t)(n0 + r) * C)[q] = v;
-                        if (!p.h0) reinterpret_cast<float4*>(p.sHH + (size_t)(n0 + r) * C)[q] = v;
+            // a thread owns one 4-channel chunk of FOUR consecutive rows: the chunk's weights are read once per feature for the
+            // four rows (8 LDS per 16 FMAs; a thread per (row, chunk) re-read them per row: 2.5x the shared-memory traffic,
+            // 10 % of the screening kernel); lanes run over the chunks of a row group, so panel and HBM stores stay contiguous
+            constexpr int RG = 4;
+            for (int it = tid; it < (kMpM / RG) * CQ; it += NT) {
+                const int rg = it / CQ, q = it - rg * CQ;
+                const int rd = p.raw_dim;
+                const float* w = Wp + 4 * q * rd;
+                const float* xr = rs + rg * RG * rd;
+                const float4 b4 = lds128(bp + 4 * q);
+                float4 v[RG];
+#pragma unroll
+                for (int j = 0; j < RG; ++j) v[j] = b4;
+                for (int k = 0; k < rd; ++k) {
+                    const float w0 = w[k], w1 = w[rd + k], w2 = w[2 * rd + k], w3 = w[3 * rd + k];
+#pragma unroll
+                    for (int j = 0; j < RG; ++j) {
+                        const float xv = xr[j * rd + k];
+                        v[j].x = fmaf(xv, w0, v[j].x); v[j].y = fmaf(xv, w1, v[j].y);
+                        v[j].z = fmaf(xv, w2, v[j].z); v[j].w = fmaf(xv, w3, v[j].w);
                     }
                 }
-                sts128(q < 8 ? XM + pan_off(r, q) : AT + pan_off(r, q - 8), v);
+#pragma unroll
+                for (int j = 0; j < RG; ++j) {
+                    const int r = rg * RG + j;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < nd) {
+                        o.x = act_fwd(v[j].x, p.pre_act, p.pre_act_param); o.y = act_fwd(v[j].y, p.pre_act, p.pre_act_param);
+                        o.z = act_fwd(v[j].z, p.pre_act, p.pre_act_param); o.w = act_fwd(v[j].w, p.pre_act, p.pre_act_param);
+                        if (SAVE && !p.conv_only) {
+                            reinterpret_cast<float4*>(p.sX + (size_t)(n0 + r) * C)[q] = o;
+                            if (!p.h0) reinterpret_cast<float4*>(p.sHH + (size_t)(n0 + r) * C)[q] = o;
+                        }
+                    }
+                    sts128(q < 8 ? XM + pan_off(r, q) : AT + pan_off(r, q - 8), o);
+                }
             }
         } else {
 #pragma unroll
